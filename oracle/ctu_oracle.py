@@ -680,16 +680,23 @@ def fea_trapdct(Y: np.ndarray, o: Opts) -> np.ndarray:
     h = (L + 1) // 2
     with np.errstate(divide="ignore", invalid="ignore"):
         G = np.log(Y)
-    if T < h:
+    if T == 0:
         return np.zeros((0, nb * n))
     hamm = 0.54 - (1 - 0.54) * np.cos(2 * 3.14159265359 * np.arange(L, dtype=np.float64) / (L - 1.0))
     j = np.arange(L, dtype=np.float64)
     out = np.zeros((T, nb * n))
-    pad = np.concatenate([np.repeat(G[:1], h - 1, axis=0), G, np.repeat(G[-1:], h - 1, axis=0)], axis=0)
     cosm = np.array([np.cos(math.pi * (j + 0.5) * k / L) for k in range(1, n + 1)])  # [n, L]
     with np.errstate(invalid="ignore"):
         for t in range(T):
-            win = pad[t: t + L]                       # [L, nb]
+            if T >= h - 1:
+                win = G[np.clip(t + np.arange(L) - (h - 1), 0, T - 1)]      # [L, nb]
+            else:
+                # fewer than h-1 frames: nothing is emitted before flush, and flush r sees
+                # Z = h-T-(r+1) never-written ring rows (zeros in a fresh process) ahead of
+                # the replicated context (src/fea/fea_trap.cc:53-82, 111-127)
+                Z = h - T - (t + 1)
+                win = G[np.clip(np.arange(L) - Z - (h - 1), 0, T - 1)].copy()
+                win[:Z] = 0.0
             for b in range(nb):
                 v = win[:, b]
                 m = _seq_sum(v) / L
@@ -699,28 +706,129 @@ def fea_trapdct(Y: np.ndarray, o: Opts) -> np.ndarray:
 
 
 def fea_delta_block(C: np.ndarray, win: int) -> np.ndarray:
-    """deltaFEA::delta + edge handling, src/fea/fea_delta.cc:70-206: HTK regression
-    d_t = sum_i i (c_{t+i} - c_{t-i}) / (2 sum i^2) with the first/last frame replicated.
-    C: [T, d] -> [T, d].  (Order of accumulation as in the reference loop.)"""
+    """Closed form of one deltaFEA stage in its regular regime (rows >= win + 2):
+    HTK regression d_t = sum_i i (c_{t+i} - c_{t-i}) / (2 sum i^2) with the first/last row
+    replicated (src/fea/fea_delta.cc:146-164 + edge logic :70-130, 178-206).  One quirk
+    survives into the regular regime: with win == 1 the flush writes the replica over the
+    slot the last real row sits in (`index=end`, src/fea/fea_delta.cc:182-185), so the LAST
+    row's delta is exactly 0.  tests/test_oracle_vs_golden.py checks this closed form
+    against the state machine below; the CUDA kernel implements the closed form."""
     T = C.shape[0]
-    if T == 0:
-        return C.copy()
     den = 2.0 * sum(i * i for i in range(1, win + 1))
     idx = np.arange(T)
     acc = np.zeros_like(C)
     for i in range(1, win + 1):
         acc = acc + i * (C[np.minimum(idx + i, T - 1)] - C[np.maximum(idx - i, 0)])
-    return acc / den
+    acc = acc / den
+    if win == 1 and T > 0:
+        acc[-1] = 0.0
+    return acc
+
+
+class DeltaFEA:
+    """Faithful port of the deltaFEA state machine, src/fea/fea_delta.cc:20-206 (ring of
+    2*win+1 input rows, `avail`/`index`/`start`/`end` bookkeeping, first row written `win`
+    times, second row twice, the b(dwlen-1)=b(dwlen-2) patch, flush replicas).  Needed for
+    utterances shorter than win+2 rows, where the output depends on never-written ring
+    rows (zeros in a fresh process: Mat zero-fills all but column 0, src/base/types.h:72)."""
+
+    def __init__(self, fea_c: int, n_order: int, delta_w: int):
+        if delta_w < 1:
+            raise ValueError("FEA: Delta window size must be > 1!")
+        self.fea_c, self.delta_w, self.dwlen, self.n_order = fea_c, delta_w, 2 * delta_w + 1, n_order
+        self.nfea = fea_c * (n_order - 1)
+        self.buf = np.zeros((self.dwlen, self.nfea))
+        self.fvec = np.zeros(fea_c * n_order)
+        self.den = 2.0 * sum(i * i for i in range(1, delta_w + 1))
+        self.new_file()
+
+    def new_file(self):
+        self.start = self.end = 0
+        self.endframe = True
+        self.frame = 1
+        self.avail = self.delta_w + 1
+        self.index = self.avail - 1
+        self.num_c = 1
+
+    def _init_cbuffer(self, f):
+        for _ in range(self.num_c):
+            self.buf[self.index] = f[: self.nfea]
+            self.index = (self.index + 1) % self.dwlen
+
+    def _delta(self):
+        d = self.buf[(self.start + np.arange(self.dwlen)) % self.dwlen]
+        lo, hi = self.fea_c * (self.n_order - 2), self.fea_c * (self.n_order - 1)
+        x = np.zeros(hi - lo)
+        for i in range(1, self.delta_w + 1):
+            x = x + i * (d[self.delta_w + i, lo:hi] - d[self.delta_w - i, lo:hi])
+        self.fvec[lo + self.fea_c: hi + self.fea_c] = x / self.den
+
+    def process_frame(self, f) -> bool:
+        if self.avail != 0:
+            self.num_c = self.delta_w if self.frame == 1 else (2 if self.frame == 2 else 1)
+            self._init_cbuffer(f)
+            self.avail -= 1
+            ready = not self.avail
+            if ready:
+                self._delta()
+                self.buf[self.dwlen - 1] = self.buf[self.dwlen - 2]
+                self.fvec[: self.nfea] = self.buf[self.delta_w]
+            self.start = (self.start + 1) % self.dwlen
+            self.frame += 1
+            return ready
+        fea_x = self.dwlen - 1 if self.start == 0 else self.start - 1
+        self.buf[fea_x] = f[: self.nfea]
+        self._delta()
+        self.fvec[: self.nfea] = self.buf[(fea_x - self.delta_w) % self.dwlen]
+        self.end = self.start
+        self.start = (self.start + 1) % self.dwlen
+        self.frame += 1
+        return True
+
+    def flush_frame(self, f) -> bool:
+        if self.endframe:
+            self.index = self.end
+            self.endframe = False
+        if self.avail < self.delta_w:
+            self._init_cbuffer(f)
+            self._delta()
+            self.fvec[: self.nfea] = self.buf[(self.start - self.delta_w - 1) % self.dwlen]
+            self.start = (self.start + 1) % self.dwlen
+            self.avail += 1
+            return True
+        return False
 
 
 def add_deltas(C: np.ndarray, o: Opts) -> np.ndarray:
     """BATCH::init_delta/fea_delta/flush_fea chain, src/io/batch.cc:122-130, 172-192,
-    251-296: blocks [c, d, dd, ddd]; each higher order is the same operator applied to the
-    previous block, with its own replicated edges."""
+    251-296, driving DeltaFEA stages exactly as the reference does: blocks [c, d, dd, ddd];
+    each higher order is the same operator applied to the previous stage's rows."""
+    wins = [o.d_win, o.a_win, o.t_win][: o.n_order]
+    n = len(wins)
+    fea_c = C.shape[1]
+    st = [DeltaFEA(fea_c, k + 2, wins[k]) for k in range(n)]
+    out = []
+
+    def push(level, vec):
+        if level == n:
+            out.append(np.array(vec, copy=True))
+        elif st[level].process_frame(vec):
+            push(level + 1, st[level].fvec)
+
+    for t in range(C.shape[0]):
+        push(0, C[t])
+    for level in range(n):
+        src = (C[-1] if C.shape[0] else np.zeros(fea_c)) if level == 0 else st[level - 1].fvec
+        while st[level].flush_frame(src):
+            push(level + 1, st[level].fvec)
+    return np.array(out).reshape(len(out), fea_c * (n + 1))
+
+
+def add_deltas_closed_form(C: np.ndarray, o: Opts) -> np.ndarray:
+    """What the CUDA path computes: valid when every stage sees >= win+2 rows."""
     blocks = [C]
-    wins = [o.d_win, o.a_win, o.t_win]
     for k in range(o.n_order):
-        blocks.append(fea_delta_block(blocks[-1], wins[k]))
+        blocks.append(fea_delta_block(blocks[-1], [o.d_win, o.a_win, o.t_win][k]))
     return np.concatenate(blocks, axis=1)
 
 

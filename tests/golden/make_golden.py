@@ -1,0 +1,162 @@
+#!/usr/bin/env python
+"""
+Generates tests/golden/*.npz by running the REFERENCE binary (oracle/_ref/ctucopy4_O0,
+built by oracle/build_ref.sh from the unmodified sources under /root/reference) on small
+inputs.  Run in the build container (where /root/reference exists):
+
+    bash oracle/build_ref.sh && python tests/golden/make_golden.py
+
+The inputs are stored once in inputs.npz, so nothing at test time needs /root/reference.
+Every case runs ONE utterance per reference process: the *ss noise-reduction modes carry
+state from one list entry to the next (src/nr/nr.cc:212-222), and parity for this path is
+defined per utterance.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_runner as rr  # noqa: E402
+from ctucopy_b200 import synthetic  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+B = ["-fs", "16000", "-format_in", "raw", "-dither", "0"]
+MF = ["-preset", "mfcc", "-preem", "0.97"]
+CONF15 = ["-format_out", "htk", "-endian_in", "little", "-endian_out", "little", "-w", "25", "-s", "10", "-preem", "0.97",
+          "-fb_scale", "mel", "-fb_shape", "triang", "-fb_power", "on", "-fb_definition", "30filters", "-nr_mode", "none",
+          "-fb_eqld", "off", "-fb_inld", "off", "-fea_kind", "dctc", "-fea_ncepcoefs", "12", "-fea_c0", "on", "-fea_E", "off",
+          "-fea_lifter", "22", "-fea_rawenergy", "off"]
+
+# name -> (args, kind of output, extra)
+CASES = {
+    # BASELINE config 1 (egs/conf/15 verbatim, egs/conf/01 static, and the 23-filter wording)
+    "mfcc30_d_a": (B + CONF15 + ["-fea_delta", "d_a", "-d_win", "2", "-a_win", "2", "-t_win", "2"], "htk", {}),
+    "mfcc30_static": (B + CONF15, "htk", {}),
+    "mfcc23_d_a": (B + MF + ["-fb_definition", "23filters", "-format_out", "htk", "-fea_delta", "d_a"], "htk", {}),
+    "mfcc26_d_a_t_win3": (B + MF + ["-format_out", "htk", "-fea_delta", "d_a_t", "-d_win", "3", "-a_win", "2", "-t_win", "1"], "htk", {}),
+    "mfcc26_be": (B + MF + ["-format_out", "htk", "-endian_out", "big"], "htk_be", {}),
+    # config 3
+    "plpc_ark": (B + ["-preset", "plpc", "-format_out", "ark={ARK}"], "ark", {}),
+    "plpc_htk_d": (B + ["-preset", "plpc", "-format_out", "htk", "-fea_delta", "d"], "htk", {}),
+    "lpa_mel": (B + MF + ["-fea_kind", "lpa", "-format_out", "htk"], "htk", {}),
+    "lpc_mel_inld": (B + MF + ["-fea_kind", "lpc", "-fb_inld", "on", "-fb_eqld", "on", "-fea_ncepcoefs", "16", "-format_out", "htk"], "htk", {}),
+    # config 5
+    "trapdct_51_8": (B + ["-format_out", "htk", "-fb_definition", "23filters", "-fb_eqld", "off", "-fb_inld", "off", "-preem", "0.97",
+                          "-fea_kind", "trapdct,51,8"], "htk", {}),
+    "trapdct_11_4": (B + ["-format_out", "htk", "-fb_definition", "15filters", "-fb_eqld", "off", "-fb_inld", "off",
+                          "-fea_kind", "trapdct,11,4"], "htk", {}),
+    # spectra / filter banks
+    "spec_lin_rect": (B + ["-format_out", "htk", "-fb_scale", "lin", "-fb_shape", "rect", "-fb_definition", "32filters",
+                           "-fb_eqld", "off", "-fb_inld", "off", "-fb_norm", "off", "-fea_kind", "spec"], "htk", {}),
+    "logspec_bark_tri": (B + ["-format_out", "htk", "-fb_scale", "bark", "-fb_shape", "triang", "-fb_definition", "20filters",
+                              "-fb_eqld", "on", "-fb_inld", "off", "-fea_kind", "logspec", "-preem", "0.95"], "htk", {}),
+    "spec_expolog_mag": (B + ["-format_out", "htk", "-fb_scale", "expolog", "-fb_shape", "triang",
+                              "-fb_definition", "0-4000Hz:1-10/10filters,4000-8000Hz:1-5/5filters", "-fb_power", "off",
+                              "-fb_eqld", "off", "-fb_inld", "on", "-fea_kind", "spec", "-remove_dc", "off"], "htk", {}),
+    "spec_mel_rect_join": (B + ["-format_out", "htk", "-fb_scale", "mel", "-fb_shape", "rect",
+                                "-fb_definition", "0-2000Hz:1-8/8filters,2000-8000Hz:2-6/6filters",
+                                "-fb_eqld", "off", "-fb_inld", "off", "-fea_kind", "spec"], "htk", {}),
+    # config 2
+    "exten_raw": (B + ["-preset", "exten", "-format_out", "raw"], "raw", {}),
+    "exten_wave_a1": (B + ["-preset", "exten", "-nr_a", "1", "-format_out", "wave"], "wave", {}),
+    "exten_raw_a15_2510": (B + ["-preset", "exten", "-nr_a", "1.5", "-w", "25", "-s", "10", "-preem", "0.9", "-format_out", "raw"], "raw", {}),
+    "mfcc_exten_d_a": (B + MF + ["-nr_mode", "exten", "-format_out", "htk", "-fea_delta", "d_a"], "htk", {}),
+    "mfcc_exten_afterFB": (B + MF + ["-nr_mode", "exten", "-nr_when", "afterFB", "-nr_a", "2", "-format_out", "htk"], "htk", {}),
+    # config 4a / 4b and the other spectral-subtraction flavours
+    "fwss_burg_pfile": (B + MF + ["-nr_mode", "fwss", "-vad", "burg", "-nr_when", "beforeFB", "-format_out", "pfile={PFILE}"], "pfile", {}),
+    "hwss_burg_a2": (B + MF + ["-nr_mode", "hwss", "-nr_a", "2", "-fb_power", "off", "-vad", "burg", "-format_out", "htk"], "htk", {}),
+    "2fwss_burg": (B + MF + ["-nr_mode", "2fwss", "-vad", "burg", "-nr_initsegs", "5", "-format_out", "htk"], "htk", {}),
+    "fwss_file_afterFB_pfile": (B + MF + ["-nr_mode", "fwss", "-vad", "file={VADIN}", "-nr_when", "afterFB", "-format_out", "pfile={PFILE}"],
+                                "pfile", {"ext_vad": True}),
+    "fwss_burg_raw": (B + ["-w", "32", "-s", "16", "-nr_mode", "fwss", "-nr_b", "1.5", "-vad", "burg", "-format_out", "raw"], "raw", {}),
+    # VAD module
+    "vad_energy_perc": (B + MF + ["-format_out", "htk", "-vad_out_mode", "vad"], "htk", {"vad_out": True}),
+    "vad_energy_dyn_drop": (B + MF + ["-format_out", "htk", "-vad_out_mode", "vad", "-vad_thr_mode", "dyn", "-vad_apply_mode", "drop"],
+                            "htk", {"vad_out": True}),
+    "vad_cepdist_lpc_adapt": (B + MF + ["-format_out", "htk", "-vad_out_mode", "vad", "-vad_thr_mode", "adapt", "-vad_cri_mode", "cepdist",
+                                        "-vad_cepdist_mode", "lpc", "-vad", "burg"], "htk", {"vad_out": True}),
+    "vad_cepdist_fea_f5_drop": (B + MF + ["-format_out", "htk", "-vad_out_mode", "vad", "-vad_thr_mode", "adapt", "-vad_cri_mode", "cepdist",
+                                          "-vad_cepdist_mode", "fea", "-vad_filter_order", "5", "-vad_apply_mode", "drop"], "htk", {"vad_out": True}),
+    "vad_absolute_f1": (B + MF + ["-format_out", "htk", "-vad_out_mode", "vad", "-vad_thr_mode", "absolute", "-vad_absolute_thr", "100",
+                                  "-vad_filter_order", "1"], "htk", {"vad_out": True}),
+    "vad_perc_d_a_drop": (B + MF + ["-format_out", "htk", "-vad_out_mode", "vad", "-fea_delta", "d_a", "-vad_apply_mode", "drop"],
+                          "htk", {"vad_out": True}),
+}
+
+
+def inputs():
+    utts = [synthetic.utterance(k, 1.0) for k in (0, 1, 5, 13)]           # tone/chirp, noisy + clean
+    utts.append(synthetic.utterance(2, 2.5))
+    ref_sig = "/root/reference/egs/sig/SA000CB1.CS0"
+    if os.path.exists(ref_sig):
+        sp = np.fromfile(ref_sig, dtype="<i2")
+        utts.append(sp[24000:24000 + 19200].copy())                        # 1.2 s of real speech
+    utts.append(synthetic.utterance(7, 0.05)[: 400 + 160 * 2 + 37])        # 3 frames, ragged tail
+    return utts
+
+
+def main():
+    utts = inputs()
+    np.savez_compressed(os.path.join(OUT, "inputs.npz"), **{"in%d" % i: u for i, u in enumerate(utts)})
+    rng = np.random.default_rng(7)
+    names = sys.argv[1:] or list(CASES)
+    for name in names:
+        args, kind, extra = CASES[name]
+        outs, vads, flags_all = [], [], []
+        for u in utts:
+            ev = None
+            if extra.get("ext_vad"):
+                w = 400; s = 160
+                T = (len(u) - (w - s)) // s
+                ev = (rng.random(T) < 0.5).astype(np.uint8)
+                ev[: min(12, T)] = 0
+                flags_all.append(ev)
+            r = rr.run_reference(args, [u], vad_out=bool(extra.get("vad_out")), ext_vad_bytes=None if ev is None else ev.tobytes())
+            assert r["returncode"] == 0, (name, r["stderr"])
+            if kind == "ark":
+                b = r["files"]["out0.ark"]
+                outs.append(np.frombuffer(b, dtype=np.uint8))
+                vads.append(np.frombuffer(r["files"]["out0.scp"], dtype=np.uint8))
+            elif kind == "pfile":
+                outs.append(np.frombuffer(r["files"]["out0.pfile"], dtype=np.uint8))
+            else:
+                outs.append(np.frombuffer(r["outputs"][0], dtype=np.uint8))
+            if extra.get("vad_out"):
+                vads.append(np.frombuffer(r["vad"][0]["vad"], dtype=np.uint8))
+        d = {"args": np.array(json.dumps(args)), "kind": np.array(kind)}
+        for i, u in enumerate(utts):
+            d["out%d" % i] = outs[i]
+            if vads:
+                d["aux%d" % i] = vads[i]
+            if flags_all:
+                d["extvad%d" % i] = flags_all[i]
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+        print(name, "ok", sum(len(o) for o in outs), "bytes")
+    # filter-bank design goldens via the undocumented -fb_printself (src/fea/fb.cc:449-456)
+    fbd = {}
+    for nm, a in {
+        "mel30": ["-fb_definition", "30filters", "-fb_eqld", "off"],
+        "mel26_eqld": ["-fb_definition", "1-26/26filters", "-fb_eqld", "on"],
+        "bark_tri20": ["-fb_scale", "bark", "-fb_definition", "20filters"],
+        "plp": ["-fb_shape", "trapez"],
+        "plp8k": ["-fb_shape", "trapez", "-fs", "8000"],
+        "lin_rect": ["-fb_scale", "lin", "-fb_shape", "rect", "-fb_definition", "32filters", "-fb_norm", "off", "-fb_eqld", "off"],
+        "expolog2": ["-fb_scale", "expolog", "-fb_definition", "0-4000Hz:1-10/10filters,4000-8000Hz:1-5/5filters", "-fb_eqld", "off"],
+        "mel_rect_join": ["-fb_scale", "mel", "-fb_shape", "rect", "-fb_definition", "0-2000Hz:1-8/8filters,2000-8000Hz:2-6/6filters"],
+    }.items():
+        args = ["-fs", "16000", "-format_in", "raw", "-format_out", "htk", "-fea_kind", "spec", "-fb_printself"] + a
+        r = rr.run_reference(args, [utts[0]])
+        rows = [ln for ln in r["stderr"].splitlines() if "\t" in ln]
+        m = np.array([[float(x) for x in ln.split("\t") if x.strip() != ""] for ln in rows])
+        fbd[nm] = m
+        fbd[nm + "_args"] = np.array(json.dumps(args))
+        print("fb", nm, m.shape)
+    np.savez_compressed(os.path.join(OUT, "fb_design.npz"), **fbd)
+
+
+if __name__ == "__main__":
+    main()

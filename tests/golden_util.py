@@ -1,0 +1,61 @@
+"""Loads tests/golden/*.npz (written by tests/golden/make_golden.py from the reference binary)."""
+import json
+import os
+
+import numpy as np
+
+import ref_runner as rr
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+_inputs = None
+
+
+def inputs():
+    global _inputs
+    if _inputs is None:
+        z = np.load(os.path.join(GOLDEN, "inputs.npz"))
+        _inputs = [z["in%d" % i] for i in range(len(z.files))]
+    return _inputs
+
+
+def case_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("inputs.npz", "fb_design.npz"))
+
+
+class Case:
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        self.name = name
+        self.args = json.loads(str(z["args"]))
+        self.kind = str(z["kind"])
+        self.n = len(inputs())
+        self.raw = [z["out%d" % i].tobytes() for i in range(self.n)]
+        self.aux = [z["aux%d" % i].tobytes() if ("aux%d" % i) in z.files else None for i in range(self.n)]
+        self.extvad = [z["extvad%d" % i] if ("extvad%d" % i) in z.files else None for i in range(self.n)]
+
+    def oracle_args(self):
+        """args as given to the reference, with container placeholders made harmless"""
+        return [a.replace("{ARK}", "out.ark").replace("{PFILE}", "out.pfile").replace("{VADIN}", "vadin.bin") for a in self.args]
+
+    def payload(self, i):
+        """golden payload of utterance i as an array (features float32 [T,dim] or int16 PCM)"""
+        b = self.raw[i]
+        if self.kind == "htk":
+            return rr.parse_htk(b)[1]
+        if self.kind == "htk_be":
+            return rr.parse_htk(b, ">")[1].astype("<f4")
+        if self.kind == "ark":
+            return list(rr.parse_ark(b).values())[0]
+        if self.kind == "pfile":
+            return rr.parse_pfile(b)[1]
+        if self.kind == "raw":
+            return np.frombuffer(b, dtype="<i2")
+        if self.kind == "wave":
+            return np.frombuffer(b[44:], dtype="<i2")
+        raise ValueError(self.kind)
+
+
+def same_nonfinite(a, b):
+    return np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.isposinf(a), np.isposinf(b)) and \
+        np.array_equal(np.isneginf(a), np.isneginf(b))

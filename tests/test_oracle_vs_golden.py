@@ -1,0 +1,94 @@
+"""Pins the numpy oracle (oracle/ctu_oracle.py) to the reference binary's own outputs
+(tests/golden/*.npz).  CPU only."""
+import numpy as np
+import pytest
+
+import ctu_oracle as co
+import golden_util as gu
+
+
+# lpa on a mel bank without the ^0.33 law squares the band POWERS (src/fea/fea_impl.cc:165-169);
+# on the "clean" synthetic items the autocorrelation matrix is then so ill-conditioned that
+# the reference's own output moves by 1e-3 when its FFT library's last-bit rounding moves
+# (numpy pocketfft vs the oracle build's shim): no tolerance below that is meaningful.
+ILL_CONDITIONED = {"lpa_mel"}
+
+
+@pytest.mark.parametrize("name", gu.case_names())
+def test_oracle_matches_reference_binary(name):
+    c = gu.Case(name)
+    o = co.parse_args(c.oracle_args())
+    for i, pcm in enumerate(gu.inputs()):
+        res = co.run_pipeline(pcm, o, ext_vad=c.extvad[i])
+        want = c.payload(i)
+        got = res.waveform if c.kind in ("raw", "wave") else res.features
+        assert got.shape == want.shape, (name, i, got.shape, want.shape)
+        if c.kind in ("raw", "wave"):
+            assert np.array_equal(got, want), (name, i)
+        else:
+            assert gu.same_nonfinite(got, want), (name, i)
+            fin = np.isfinite(want)
+            # bit-identical float32 except where a 1e-16 difference between numpy's FFT and
+            # the oracle build's shim FFT is amplified by cancellation (exten X - H*X)
+            ident = (got[fin] == want[fin]).mean() if fin.any() else 1.0
+            if name in ILL_CONDITIONED:
+                np.testing.assert_allclose(got[fin], want[fin], rtol=1e-2, atol=1e-3)
+                continue
+            assert ident > 0.995, (name, i, ident)
+            np.testing.assert_allclose(got[fin], want[fin], rtol=2e-6, atol=2e-6)
+        if c.aux[i] is not None and c.kind not in ("ark",):
+            v = np.frombuffer(c.aux[i], dtype=np.uint8) - 48
+            assert np.array_equal(v, res.vad.vad.astype(np.uint8)), (name, i)
+
+
+def test_container_writers_byte_exact():
+    ins = gu.inputs()
+    c = gu.Case("mfcc30_d_a"); o = co.parse_args(c.oracle_args())
+    for i in (0, 4, 6):
+        assert co.write_htk(co.run_pipeline(ins[i], o).features, o) == c.raw[i]
+    c = gu.Case("mfcc26_be"); o = co.parse_args(c.oracle_args())
+    assert co.write_htk(co.run_pipeline(ins[1], o).features, o) == c.raw[1]
+    c = gu.Case("fwss_burg_pfile"); o = co.parse_args(c.oracle_args())
+    assert co.write_pfile([co.run_pipeline(ins[2], o).features]) == c.raw[2]
+    c = gu.Case("exten_wave_a1"); o = co.parse_args(c.oracle_args())
+    assert co.write_wave(co.run_pipeline(ins[3], o).waveform, 16000) == c.raw[3]
+    c = gu.Case("plpc_ark"); o = co.parse_args(c.oracle_args())
+    b = c.raw[0]
+    key = b[: b.index(b" ")].decode()
+    ark, scp = co.write_ark([(key, co.run_pipeline(ins[0], o).features)], "X")
+    assert ark == b
+    assert scp.split(":")[1] == c.aux[0].decode().split(":")[1]
+
+
+def test_fb_design_matches_printself():
+    import json, os
+    z = np.load(os.path.join(gu.GOLDEN, "fb_design.npz"))
+    for nm in [f for f in z.files if not f.endswith("_args")]:
+        o = co.parse_args(json.loads(str(z[nm + "_args"])))
+        fb = co.fb_design(o)
+        want = z[nm]
+        assert fb.mat.shape == want.shape, nm
+        # -fb_printself prints 6 significant digits
+        np.testing.assert_allclose(fb.mat, want, rtol=2e-5, atol=0)
+
+
+def test_delta_closed_form_equals_state_machine():
+    """The CUDA path implements the closed form; it must equal the reference's state
+    machine whenever every stage sees >= win+2 rows (incl. the win==1 last-row quirk)."""
+    rng = np.random.default_rng(0)
+    for wins in ([2], [2, 2], [2, 2, 2], [3, 2, 1], [1], [1, 1], [4, 3], [1, 3, 2]):
+        for T in list(range(max(wins) + 2, 24)) + [57]:
+            C = rng.standard_normal((T, 3))
+            o = co.Opts(); o.n_order = len(wins)
+            o.d_win, o.a_win, o.t_win = (wins + [2, 2])[:3]
+            a = co.add_deltas(C, o); b = co.add_deltas_closed_form(C, o)
+            assert a.shape == b.shape, (wins, T)
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-13)
+
+
+def test_frame_count_edge_cases():
+    o = co.parse_args(["-fs", "16000", "-preset", "mfcc", "-format_out", "htk"])
+    assert co.num_frames(400, o) == 1 and co.num_frames(399, o) == 0 and co.num_frames(240, o) == 0
+    assert co.num_frames(160000, o) == 998
+    with pytest.raises(ValueError):
+        co.num_frames(239, o)
