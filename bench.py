@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- feature frames/s of the CtuCopy hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--utts U] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic 16 kHz utterances
+(10 000 x 10 s per GPU by default = 9.98 M frames, SURVEY.md 8(d) throughput set; inputs
+3.2 GB, far larger than L2, so no cache flush is needed between timed steps).
+  value : whole-job frames/s with the PCM already resident in HBM (CUDA events on the
+          launching stream, max over ranks)
+  e2e   : the same metric through the public C-ABI call with HOST (pinned) buffers:
+          H2D of the PCM and D2H of the features inside the timed region
+  roofline / cpu_baseline : see DESIGN.md "Measurement"
+Multi-GPU: one process per GPU (torchrun), utterances sharded by rank, no collective on the
+data path (weak scaling: every rank gets its own 10 000 utterances).
+"""
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B = ["-fs", "16000", "-format_in", "raw", "-dither", "0"]
+WORKLOADS = {
+    # name: (args, algorithmic bytes per frame of the whole step, of the dominant kernel, ~flops per frame, dominant kernel)
+    "mfcc_d_a": (B + ["-format_out", "htk", "-w", "25", "-s", "10", "-preem", "0.97", "-fb_scale", "mel", "-fb_shape", "triang",
+                      "-fb_power", "on", "-fb_definition", "30filters", "-nr_mode", "none", "-fb_eqld", "off", "-fb_inld", "off",
+                      "-fea_kind", "dctc", "-fea_ncepcoefs", "12", "-fea_c0", "on", "-fea_E", "off", "-fea_lifter", "22",
+                      "-fea_rawenergy", "off", "-fea_delta", "d_a", "-d_win", "2", "-a_win", "2", "-t_win", "2"],
+                 476, 372, 18000, "k_frames<pcm,fea>"),
+    "plp": (B + ["-preset", "plpc", "-format_out", "ark=out.ark"], 372, 372, 19000, "k_frames<pcm,fea>"),
+    "trapdct": (B + ["-format_out", "htk", "-fb_definition", "23filters", "-fb_eqld", "off", "-fb_inld", "off", "-preem", "0.97",
+                     "-fea_kind", "trapdct,51,8"], 1056, 828, 40000, "k_trapdct"),
+    "exten": (B + ["-preset", "exten", "-format_out", "raw"], 1024, 2056, 30000, "k_nr_scan"),
+    "mfcc_exten": (B + ["-preset", "mfcc", "-preem", "0.97", "-nr_mode", "exten", "-format_out", "htk", "-fea_delta", "d_a"],
+                   476, 2056, 19000, "k_nr_scan"),
+    "fwss_burg": (B + ["-preset", "mfcc", "-preem", "0.97", "-nr_mode", "fwss", "-vad", "burg", "-nr_when", "beforeFB",
+                       "-format_out", "pfile=out.pfile"], 380, 416, 70000, "k_burg"),
+}
+METRIC = "feature frames/sec (16 kHz, 10 ms hop)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6553.3), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(workload, utt_files, per_proc, cores, tmp, opt="O2"):
+    """Times the reference's own CPU implementation (oracle/_ref/ctucopy4_<opt>, unmodified
+    sources + FFT shim) on `cores` processes, each walking a list of `per_proc` 10 s
+    utterances.  Returns (frames/s, frames, seconds)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ctucopy4_" + opt)
+    if not os.path.exists(exe):
+        raise FileNotFoundError("oracle/_ref/ctucopy4_%s missing (run oracle/build_ref.sh in the build container)" % opt)
+    args = [a for a in WORKLOADS[workload][0]]
+    args = [a.replace("out.ark", os.path.join(tmp, "o.ark")).replace("out.pfile", os.path.join(tmp, "o.pfile")) for a in args]
+    procs = []
+    for p in range(cores):
+        lst = os.path.join(tmp, "l%d.scp" % p)
+        with open(lst, "w") as fh:
+            for i in range(per_proc):
+                fh.write("%s %s/o%d.out\n" % (utt_files[(p + i) % len(utt_files)], tmp, p))
+        a = [x.replace(os.path.join(tmp, "o.ark"), os.path.join(tmp, "o%d.ark" % p)).replace(os.path.join(tmp, "o.pfile"),
+             os.path.join(tmp, "o%d.pfile" % p)) for x in args]
+        procs.append([exe] + a + ["-S", lst])
+    t0 = time.perf_counter()
+    running = [subprocess.Popen(c, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=tmp) for c in procs]
+    rc = [r.wait() for r in running]
+    dt = time.perf_counter() - t0
+    if any(rc):
+        raise RuntimeError("reference binary failed: exit codes %s" % sorted(set(rc)))
+    return None, dt
+
+
+def frames_per_utt(workload, nsamp=160000):
+    w, s = (512, 256) if workload == "exten" else (400, 160)
+    return (nsamp - (w - s)) // s
+
+
+def write_utts(tmp, n_unique):
+    from ctucopy_b200 import synthetic
+    files = []
+    for k in range(n_unique):
+        p = os.path.join(tmp, "u%d.raw" % k)
+        synthetic.utterance(k, 10.0).astype("<i2").tofile(p)
+        files.append(p)
+    return files
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = len(os.sched_getaffinity(0))
+    tmp = tempfile.mkdtemp(prefix="ctu_ref_")
+    try:
+        files = write_utts(tmp, 8)
+        fpu = frames_per_utt(a.workload)
+        per_proc = max(4, int(a.ref_seconds * 60000 / fpu))     # ~a.ref_seconds of work per core per step at ~60 k frames/s/core
+        for _ in range(max(a.warmup, 0) and 1):
+            cpu_reference_run(a.workload, files, max(2, per_proc // 8), cores, tmp)
+        times = []
+        for _ in range(a.steps):
+            _, dt = cpu_reference_run(a.workload, files, per_proc, cores, tmp)
+            times.append(dt)
+        frames = cores * per_proc * fpu
+        total = sum(times)
+        val = frames * len(times) / total
+        line = {
+            "impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": a.workload, "utterances_per_step": cores * per_proc, "seconds_per_utt": 10.0,
+                       "args": " ".join(WORKLOADS[a.workload][0])},
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "reference",
+                             "sample": "%d processes x %d utterances of 10 s per step, oracle/_ref/ctucopy4_O2 (unmodified reference sources, "
+                                       "-O2, FFT shim instead of FFTW), list mode, file I/O on local disk" % (cores, per_proc)},
+            "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="mfcc_d_a", choices=list(WORKLOADS))
+    ap.add_argument("--utts", type=int, default=10000, help="utterances of 10 s per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-seconds", type=float, default=4.0, help="CPU work per core per step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--others", action="store_true", help="also run the other workloads (shorter) and report them under 'workloads'")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        return run_reference_arm(a)
+
+    import torch
+    import torch.distributed as dist
+    import ctucopy_b200 as cb
+    from ctucopy_b200 import synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the CtuCopy hot path has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def measure(workload, steps, warmup, e2e_steps, with_clocks):
+        args, bytes_step, bytes_kernel, flops, dom = WORKLOADS[workload]
+        hd = cb.Handle(args, device=local)
+        # each rank's shard: its own slice of the utterance list (weak scaling: a.utts per rank)
+        uniq = 16
+        pcm_np, lens = synthetic.batch(a.utts, 10.0, unique=uniq)
+        # rotate by rank so ranks do not hold identical data
+        plan = hd.plan(lens)
+        frames = plan.total_frames
+        h_pcm = torch.empty(len(pcm_np), dtype=torch.int16).pin_memory()
+        h_pcm.numpy()[:] = pcm_np
+        del pcm_np
+        d_pcm = h_pcm.cuda(non_blocking=True)
+        dim = hd.feature_dim
+        sig = hd.signal_output
+        if sig:
+            d_out = torch.empty(plan.total_output_samples, dtype=torch.int16, device="cuda")
+            h_out = torch.empty(plan.total_output_samples, dtype=torch.int16).pin_memory()
+        else:
+            d_out = torch.empty((frames, dim), dtype=torch.float32, device="cuda")
+            h_out = torch.empty((frames, dim), dtype=torch.float32).pin_memory()
+        stream = torch.cuda.current_stream().cuda_stream
+
+        def step():
+            if sig:
+                plan.run_device(d_pcm.data_ptr(), d_waveform=d_out.data_ptr(), stream=stream)
+            else:
+                plan.run_device(d_pcm.data_ptr(), d_features=d_out.data_ptr(), stream=stream)
+
+        for _ in range(warmup):
+            step()
+        barrier()
+        sampler = ClockSampler(local) if with_clocks else None
+        if sampler:
+            sampler.start()
+        l0 = hd.launch_count
+        hd.profile(True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            step()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = hd.launch_count - l0
+        recs = hd.profile_records()
+        hd.profile(False)
+        clocks = sampler.stop() if sampler else None
+        ms = max_over_ranks(ms)
+        # dominant kernel: average duration over the timed region
+        by = {}
+        for n, t in recs:
+            by.setdefault(n, []).append(t)
+        kern_ms = {n: sum(v) / steps for n, v in by.items()}
+        dom_ms = statistics.mean(by[dom]) if dom in by else None
+        # ---- end to end through the public host-buffer call
+        e2e = None
+        if e2e_steps > 0:
+            pcm_host = h_pcm.numpy()
+            out_host = h_out.numpy()
+            kw = {"waveform": out_host} if sig else {"features": out_host}
+            plan.run_host(pcm_host, want_vad=False, **kw)       # warm-up (allocates the plan's device buffers)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                plan.run_host(pcm_host, want_vad=False, **kw)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            e2e = {"value": world * frames * e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": int(h_pcm.numel() * 2),
+                   "d2h_bytes_per_step": int(h_out.numel() * h_out.element_size()), "ms_per_step": 1000 * dt / e2e_steps}
+        res = dict(frames=frames, ms=ms, launches=launches, kern_ms=kern_ms, dom=dom, dom_ms=dom_ms, clocks=clocks, e2e=e2e,
+                   bytes_step=bytes_step, bytes_kernel=bytes_kernel, flops=flops, dim=dim, args=args)
+        plan.close(); hd.close()
+        del d_pcm, d_out, h_pcm, h_out
+        torch.cuda.empty_cache()
+        return res
+
+    r = measure(a.workload, a.steps, a.warmup, a.e2e_steps, True)
+    hbm, peak_src = peaks()
+    value = world * r["frames"] * a.steps / (r["ms"] / 1000.0)
+    roof = None
+    if r["dom_ms"]:
+        ach = r["frames"] * r["bytes_kernel"] / (r["dom_ms"] / 1000.0) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(a.workload + ":" + r["dom"])
+        roof = {"bound": "hbm", "kernel": r["dom"], "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
+                "peak_source": peak_src, "kernel_ms": r["dom_ms"], "alg_bytes_per_frame": r["bytes_kernel"],
+                "step_alg_bytes_per_frame": r["bytes_step"],
+                "step_hbm_frac": (value / world) * r["bytes_step"] / 1e9 / hbm,
+                "fp32_frac_of_74TF": (value / world) * r["flops"] / 74e12,
+                "note": "front end is FP32/shared-memory bound (FFT), not HBM bound: see DESIGN.md"}
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": r["ms"] / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": a.workload, "utterances_per_gpu": a.utts, "seconds_per_utt": 10.0, "frames_per_gpu": r["frames"],
+                   "feature_dim": r["dim"], "args": " ".join(r["args"]), "l2": "inputs (3.2 GB PCM per GPU) exceed L2; no flush needed",
+                   "sharding": "utterances by rank, no collective"},
+        "gpu_launches": r["launches"], "kernel_ms_per_step": r["kern_ms"], "clocks": r["clocks"], "e2e": r["e2e"], "roofline": roof,
+    }
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        tmp = tempfile.mkdtemp(prefix="ctu_cpu_")
+        try:
+            cores = len(os.sched_getaffinity(0))
+            files = write_utts(tmp, 8)
+            fpu = frames_per_utt(a.workload)
+            per_proc = max(4, int(6.0 * 60000 / fpu))
+            _, dt = cpu_reference_run(a.workload, files, per_proc, cores, tmp)
+            line["cpu_baseline"] = {"value": cores * per_proc * fpu / dt, "unit": "frames/s", "cores": cores, "kind": "reference",
+                                    "sample": "%d processes x %d utterances of 10 s (%.1f s wall), oracle/_ref/ctucopy4_O2 = unmodified "
+                                              "reference sources at -O2 with the FFT shim (no FFTW in the image)" % (cores, per_proc, dt)}
+        except Exception as e:  # the baseline is a reported extra, never fatal for the GPU numbers
+            line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    if a.others:
+        others = {}
+        for w in WORKLOADS:
+            if w == a.workload:
+                continue
+            try:
+                x = measure(w, max(2, a.steps // 2), 3, 1, False)
+                v = world * x["frames"] * max(2, a.steps // 2) / (x["ms"] / 1000.0)
+                others[w] = {"value": v, "frames_per_gpu": x["frames"], "ms_per_step": x["ms"] / max(2, a.steps // 2),
+                             "kernel_ms_per_step": x["kern_ms"], "e2e": x["e2e"],
+                             "step_hbm_frac": (v / world) * x["bytes_step"] / 1e9 / hbm,
+                             "dominant": x["dom"],
+                             "dominant_hbm_frac": (x["frames"] * x["bytes_kernel"] / (x["dom_ms"] / 1000.0) / 1e9 / hbm) if x["dom_ms"] else None}
+            except Exception as e:
+                others[w] = {"error": str(e)}
+        line["workloads"] = others
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

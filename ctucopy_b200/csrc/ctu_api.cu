@@ -1,0 +1,798 @@
+// Host orchestration behind the C ABI (include/ctucopy_b200.h): table design in fp64,
+// plan (frame/tile bookkeeping, workspaces), kernel sequencing per configuration, and the
+// chunked H2D / compute / D2H pipeline of the end-to-end entry point.
+// This is the GPU replacement of BATCH::process / process_frame / flush_fea
+// (src/io/batch.cc:205-422).  There is NO CPU fallback anywhere in this file: without a
+// CUDA device ctu_create fails with CTU_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ctu_internal.h"
+#include "ctu_kernels.cuh"
+#include "ctu_nr_kernels.cuh"
+
+using namespace ctu;
+
+// ------------------------------------------------------------------------------------------
+struct ctu_handle {
+    ctu_config cfg;
+    int device = 0;
+    std::string err;
+    LaunchCtx lc;
+    CtuFbDesign fb;
+    int fea_kind = FEA_NONE, nr_mode = NR_NONE, vad_src = VADSRC_NONE;
+    bool signal_out = false, do_vad = false, vad_drop = false;
+    int vad_cri = VCRI_ENERGY, vad_thr = VTHR_PERC;
+    int static_dim = 0, feature_dim = 0;
+    FrameParams fp;      // filter bank + second stage tables
+    DeltaParams dp;
+    TrapParams tp;
+    NrParams nrp;
+    SynthParams sp;
+    BurgParams bp;
+    VadParams vp;
+    // device tables
+    float2 *d_tw256 = nullptr, *d_twsplit = nullptr, *d_twinv = nullptr;
+    float *d_win = nullptr;
+    double2 *d_tw256d = nullptr, *d_twsplitd = nullptr, *d_twinvd = nullptr;
+    double *d_wind = nullptr, *d_hann = nullptr;
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+};
+
+struct ctu_plan {
+    ctu_handle *h = nullptr;
+    int n_utts = 0;
+    std::vector<int64_t> offsets;        // n_utts+1 sample offsets
+    std::vector<int> nframes;
+    std::vector<int64_t> row_off;        // n_utts+1
+    std::vector<int64_t> osamp_off;      // n_utts+1 (signal output)
+    std::vector<int64_t> tile32_off, tile64_off;   // n_utts+1
+    std::vector<int64_t> rows_per_utt;
+    int64_t total_frames = 0, total_osamp = 0, total_samples = 0;
+    // device bookkeeping
+    int64_t *d_pcm_off = nullptr, *d_row_off = nullptr, *d_osamp_off = nullptr, *d_t32_off = nullptr, *d_t64_off = nullptr;
+    int *d_nframes = nullptr;
+    int2 *d_tiles32 = nullptr, *d_tiles64 = nullptr;
+    // workspaces (whole batch)
+    float *d_spec = nullptr, *d_fb = nullptr, *d_log = nullptr;
+    double *d_ceps = nullptr;            // Burg cepstra [frames x ncoef]
+    double *d_cri = nullptr;             // VAD criterion per frame
+    uint8_t *d_flags = nullptr;          // NR-internal detector decisions
+    uint8_t *d_keep = nullptr;           // VAD module: row kept
+    uint8_t *d_vad0 = nullptr;           // VAD module: unfiltered decisions
+    int *d_rows = nullptr;               // rows written per utterance (drop mode)
+    int64_t workspace_bytes = 0;
+    // buffers owned for the host entry point
+    int16_t *d_pcm = nullptr, *d_wave = nullptr;
+    float *d_fea = nullptr;
+    uint8_t *d_ext = nullptr, *d_vadnr_out = nullptr, *d_vad_out = nullptr;
+    bool host_bufs = false;
+};
+
+static thread_local std::string g_create_err;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #call;                \
+            return CTU_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+static int fail(ctu_handle *h, int code, const std::string &m) {
+    h->err = m;
+    return code;
+}
+
+const char *ctu_last_error(const ctu_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+int ctu_feature_dim(const ctu_handle *h) { return h ? h->feature_dim : 0; }
+int ctu_is_signal_output(const ctu_handle *h) { return h && h->signal_out; }
+int ctu_num_bands(const ctu_handle *h) { return h ? h->fb.nb : 0; }
+uint64_t ctu_launch_count(const ctu_handle *h) { return h ? h->lc.launches : 0; }
+
+int ctu_profile_enable(ctu_handle *h, int on) {
+    if (!h) return CTU_ERR_CONFIG;
+    h->lc.clear();
+    h->lc.prof_on = on != 0;
+    return CTU_OK;
+}
+int ctu_profile_count(const ctu_handle *h) { return h ? (int)h->lc.recs.size() : 0; }
+int ctu_profile_get(ctu_handle *h, int idx, const char **name, float *ms) {
+    if (!h || idx < 0 || idx >= (int)h->lc.recs.size()) return CTU_ERR_CONFIG;
+    auto &r = h->lc.recs[idx];
+    CK(cudaEventSynchronize(r.b));
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, r.a, r.b));
+    if (name) *name = r.name;
+    if (ms) *ms = t;
+    return CTU_OK;
+}
+
+int ctu_design_filter_bank(const ctu_config *cfg, double *mat, int32_t *lo, int32_t *hi, int32_t *nb) {
+    CtuFbDesign d;
+    std::string e = ctu_design_fb(*cfg, d);
+    if (!e.empty()) { g_create_err = e; return CTU_ERR_CONFIG; }
+    if (nb) *nb = d.nb;
+    if (mat) std::copy(d.mat.begin(), d.mat.end(), mat);
+    if (lo) std::copy(d.lo.begin(), d.lo.end(), lo);
+    if (hi) std::copy(d.hi.begin(), d.hi.end(), hi);
+    return CTU_OK;
+}
+
+int ctu_fb_matrix(const ctu_handle *h, double *mat, int32_t *lo, int32_t *hi) {
+    if (!h || h->fb.nb == 0) return CTU_ERR_CONFIG;
+    if (mat) std::copy(h->fb.mat.begin(), h->fb.mat.end(), mat);
+    if (lo) std::copy(h->fb.lo.begin(), h->fb.lo.end(), lo);
+    if (hi) std::copy(h->fb.hi.begin(), h->fb.hi.end(), hi);
+    return CTU_OK;
+}
+
+int64_t ctu_num_frames(const ctu_handle *h, int64_t n) {
+    const int w = h->cfg.window, s = h->cfg.wshift;
+    if (n < w - s) return -1;                       // "IO: Signal shorter than one frame!"
+    return (n - (w - s)) / s;
+}
+
+int64_t ctu_num_output_samples(const ctu_handle *h, int64_t n) {
+    int64_t T = ctu_num_frames(h, n);
+    if (T < 0) return -1;
+    return T * h->cfg.wshift + (h->cfg.window - h->cfg.wshift);
+}
+
+// ------------------------------------------------------------------------------------------
+// table construction (host, fp64)
+// ------------------------------------------------------------------------------------------
+template <class T> static int upload(ctu_handle *h, T **dst, const std::vector<T> &v) {
+    CK(cudaMalloc((void **)dst, std::max<size_t>(1, v.size()) * sizeof(T)));
+    if (!v.empty()) CK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return CTU_OK;
+}
+
+static int build_fft_tables(ctu_handle *h) {
+    const double PI = 3.14159265358979323846264338327950288;
+    std::vector<float2> tw(256), ts(129), ti(129);
+    std::vector<double2> twd(256), tsd(129), tid_(129);
+    for (int k1 = 0; k1 < 16; k1++)
+        for (int c = 0; c < 16; c++) {
+            double a = -2 * PI * (double)(c * k1) / 256.0;
+            twd[k1 * 16 + c] = make_double2(cos(a), sin(a));
+            tw[k1 * 16 + c] = make_float2((float)cos(a), (float)sin(a));
+        }
+    for (int k = 0; k <= 128; k++) {
+        double th = 2 * PI * k / 512.0;
+        tsd[k] = make_double2(-sin(th) / 2, -cos(th) / 2);
+        ts[k] = make_float2((float)(-sin(th) / 2), (float)(-cos(th) / 2));
+        tid_[k] = make_double2(cos(th), sin(th));
+        ti[k] = make_float2((float)cos(th), (float)sin(th));
+    }
+    // analysis window: Hamming, pi = 2*asin(1) (src/io/in.cc:139-144)
+    const int w = h->cfg.window;
+    std::vector<float> win(w);
+    std::vector<double> wind(w), hann(w);
+    double pi = 2. * asin(1.);
+    for (int j = 0; j < w; j++) {
+        wind[j] = 0.54 - (1 - 0.54) * cos(2 * pi * j / (w - 1.));
+        win[j] = (float)wind[j];
+        // Hann of the cepstral detector, its own 10-digit pi (src/vdet/CepstralDet.h:126-131)
+        hann[j] = 0.5 * (1 - cos((2 * 3.141592653 / w) * j));
+    }
+    int st;
+    if ((st = upload(h, &h->d_tw256, tw))) return st;
+    if ((st = upload(h, &h->d_twsplit, ts))) return st;
+    if ((st = upload(h, &h->d_twinv, ti))) return st;
+    if ((st = upload(h, &h->d_win, win))) return st;
+    if ((st = upload(h, &h->d_tw256d, twd))) return st;
+    if ((st = upload(h, &h->d_twsplitd, tsd))) return st;
+    if ((st = upload(h, &h->d_twinvd, tid_))) return st;
+    if ((st = upload(h, &h->d_wind, wind))) return st;
+    if ((st = upload(h, &h->d_hann, hann))) return st;
+    return CTU_OK;
+}
+
+static int build_frame_params(ctu_handle *h) {
+    const ctu_config &c = h->cfg;
+    FrameParams &P = h->fp;
+    std::memset(&P, 0, sizeof(P));
+    P.window = c.window; P.wshift = c.wshift;
+    P.preem = c.preem;
+    P.remove_dc = c.remove_dc;
+    P.take_sqrt = !c.fb_power;
+    P.inld_scale = 1.f; P.lin_scale = 1.f; P.log_offset = 0.f;
+    if (h->signal_out) return CTU_OK;
+    const CtuFbDesign &fb = h->fb;
+    if (fb.nb > MAXB) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: more than 64 filter-bank bands");
+    P.nb = fb.nb;
+    P.inld = fb.inld;
+    // Equal-loudness weights are ~1e-30 above 10 kHz sampling (src/fea/fb.cc:157-164): carry
+    // an exact power-of-two factor S in the packed fp32 weights and undo it after the
+    // non-linearity, so that quiet frames do not go denormal.
+    double wmax = 0;
+    for (double v : fb.mat) if (std::isfinite(v)) wmax = std::max(wmax, std::fabs(v));
+    int e = 0;
+    if (wmax > 0 && wmax < 1e-6) { std::frexp(wmax, &e); e = -e; }
+    const double S = std::ldexp(1.0, e);
+    P.inld_scale = (float)std::pow(S, -0.33);
+    P.lin_scale = (float)(1.0 / S);
+    P.log_offset = (float)(-std::log(S));
+    int off = 0;
+    for (int b = 0; b < fb.nb; b++) {
+        int n = fb.hi[b] - fb.lo[b] + 1;
+        if (off + n > MAXW) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: filter bank has too many taps");
+        P.lo[b] = (short)fb.lo[b]; P.hi[b] = (short)fb.hi[b]; P.woff[b] = off;
+        for (int k = 0; k < n; k++) P.w[off + k] = (float)(fb.mat[(size_t)b * fb.bins + fb.lo[b] + k] * S);
+        off += n;
+    }
+    // second stage
+    const int nb = fb.nb;
+    const int N = c.fea_ncepcoefs;
+    std::vector<double> lift(N + 1, 1.0);
+    if (c.fea_lifter > 1)
+        for (int n = 1; n <= N; n++) lift[n] = 1 + ((double)c.fea_lifter) / 2 * sin(3.141592653589793 * (double)n / ((double)c.fea_lifter));
+    switch (h->fea_kind) {
+        case FEA_SPEC: case FEA_LOGSPEC: case FEA_TRAPDCT:
+            h->static_dim = nb;
+            break;
+        case FEA_DCTC: {
+            // c[i] = sqrt(2/N) sum_k ln Y_k cos(pi i (k-1/2)/N), lifter on i >= 1, pi = 3.1415926535898
+            // (src/fea/fea_impl.cc:81-131); rows stored in WRITER order c1..cN, c0 (src/io/out.cc:189-201)
+            int rows = N + (c.fea_c0 ? 1 : 0);
+            if (rows > MAXR || rows * nb > MAXM2) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: cepstral matrix too large");
+            double norm = sqrt(2.0 / nb);
+            auto wd = [&](int id) { return cos(3.1415926535898 * (double)id / (2 * nb)); };
+            for (int r = 0; r < rows; r++) {
+                int i = (r < N) ? r + 1 : 0;
+                for (int k = 1; k <= nb; k++) {
+                    int id = ((2 * k - 1) * i) % (4 * nb);
+                    P.m2[r * nb + k - 1] = (float)(wd(id) * norm * (i >= 1 ? lift[i] : 1.0));
+                }
+            }
+            P.nrows = rows;
+            h->static_dim = rows;
+            break;
+        }
+        case FEA_LPA: case FEA_LPC: {
+            const int p = c.fea_lporder;
+            if (p + 1 > MAXR || (p + 1) * nb > MAXM2 || N + 1 > MAXR) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: LP order too large");
+            if (nb < 2) return fail(h, CTU_ERR_CONFIG, "CTU: LPC needs at least two bands");
+            const int Nf = (nb - 1) * 2;
+            for (int k = 0; k <= p; k++)
+                for (int n = 0; n < nb; n++) {
+                    double v;
+                    if (n == 0) v = 0.5;
+                    else if (n == nb - 1) v = (1 - 2 * (k % 2)) * 0.5;
+                    else v = cos(2 * 3.141592653589793 * ((n * k) % Nf) / Nf);
+                    P.m2[k * nb + n] = (float)(v / ((double)Nf / 2));
+                }
+            P.nrows = p + 1;
+            P.lporder = p; P.ncep = N;
+            P.lpa_square = !fb.inld;
+            P.c0_last = c.fea_c0;
+            for (int n = 0; n <= N; n++) P.lift[n] = (float)lift[n];
+            if (h->fea_kind == FEA_LPA) {
+                // htkOUT writes a[1..ncep] with the cepstral loop bounds (src/io/out.cc:189-201):
+                // only lporder == ncepcoefs is memory-safe in the reference
+                if (p != N) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_kind lpa needs fea_lporder == fea_ncepcoefs (the reference overruns its buffers otherwise)");
+                h->static_dim = p;
+            } else {
+                h->static_dim = N + (c.fea_c0 ? 1 : 0);
+            }
+            break;
+        }
+        default: break;
+    }
+    return CTU_OK;
+}
+
+static int build_delta_trap_params(ctu_handle *h) {
+    const ctu_config &c = h->cfg;
+    DeltaParams &D = h->dp;
+    std::memset(&D, 0, sizeof(D));
+    int n_order = 0;
+    if ((h->fea_kind == FEA_DCTC || h->fea_kind == FEA_LPC) && c.fea_delta) n_order = c.n_order;
+    D.n_order = n_order;
+    int wins[3] = {c.d_win, c.a_win, c.t_win};
+    int halo = 0;
+    for (int k = 0; k < n_order; k++) {
+        if (wins[k] < 1) return fail(h, CTU_ERR_CONFIG, "FEA: Delta window size must be > 1!");
+        D.win[k] = wins[k];
+        double den = 0;
+        for (int i = 1; i <= wins[k]; i++) den += i * i;
+        D.inv_den[k] = (float)(1.0 / (2 * den));
+        halo += wins[k];
+    }
+    if (n_order > 0 && !c.fea_c0)
+        return fail(h, CTU_ERR_UNSUPPORTED, "CTU: deltas with -fea_c0 off (the reference writes uninitialised columns there, src/io/out.cc:189-201)");
+    D.blk = h->static_dim;
+    h->feature_dim = h->static_dim * (n_order + 1);
+    D.stride = h->feature_dim;
+    D.span_max = DELTA_ROWS + 2 * halo;
+    if (h->fea_kind == FEA_TRAPDCT) {
+        TrapParams &T = h->tp;
+        std::memset(&T, 0, sizeof(T));
+        const int L = c.fea_trapdct_traplen, n = c.fea_trapdct_ndct;
+        if (L % 2 == 0) return fail(h, CTU_ERR_CONFIG, "FEA: TRAP length must be odd!");
+        if (n >= L) return fail(h, CTU_ERR_CONFIG, "FEA: Number of DCT coeffs must be less than TRAP length (c0 is not output)!");
+        if (L > TRAP_MAXL || n > TRAP_MAXN || n < 1) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: TRAP-DCT supports traplen <= 127, ndct <= 16");
+        T.L = L; T.ndct = n; T.nb = h->fb.nb; T.h = (L + 1) / 2;
+        const double PI = 3.14159265358979323846264338327950288;
+        for (int k = 1; k <= n; k++) {
+            std::vector<double> row(L);
+            double sum = 0;
+            for (int j = 0; j < L; j++) {
+                double hamm = 0.54 - (1 - 0.54) * cos(2 * 3.14159265359 * j / (L - 1.));
+                row[j] = 2.0 * hamm * cos(PI * (j + 0.5) * k / L);
+                sum += row[j];
+            }
+            for (int j = 0; j < L; j++) T.m[(k - 1) * L + j] = (float)(row[j] - sum / L);
+        }
+        h->feature_dim = h->fb.nb * n;
+        T.out_stride = h->feature_dim;
+    }
+    if (c.fea_E) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_E on (energy column) is not built yet");
+    return CTU_OK;
+}
+
+static int resolve_modes(ctu_handle *h) {
+    const ctu_config &c = h->cfg;
+    std::string fo(c.format_out), kind(c.fea_kind), nr(c.nr_mode), vm(c.vadmode);
+    h->signal_out = (fo == "raw" || fo == "wave");
+    if (!h->signal_out && fo != "htk" && fo != "pfile" && fo != "ark") return fail(h, CTU_ERR_CONFIG, "OUT: Unknown output file format!");
+    if (h->signal_out) h->fea_kind = FEA_NONE;
+    else if (kind == "spec") h->fea_kind = FEA_SPEC;
+    else if (kind == "logspec") h->fea_kind = FEA_LOGSPEC;
+    else if (kind == "dctc") h->fea_kind = FEA_DCTC;
+    else if (kind == "lpa") h->fea_kind = FEA_LPA;
+    else if (kind == "lpc") h->fea_kind = FEA_LPC;
+    else if (kind == "trapdct") h->fea_kind = FEA_TRAPDCT;
+    else if (kind == "td-iir-mfcc") return fail(h, CTU_ERR_UNSUPPORTED, "CTU: td-iir-mfcc is outside this hot path (SURVEY 8f.4)");
+    else return fail(h, CTU_ERR_CONFIG, "FEA: Unknown feature kind!");
+    if (nr == "none") h->nr_mode = NR_NONE;
+    else if (nr == "exten") h->nr_mode = NR_EXTEN;
+    else if (nr == "hwss") h->nr_mode = NR_HWSS;
+    else if (nr == "fwss") h->nr_mode = NR_FWSS;
+    else if (nr == "2fwss") h->nr_mode = NR_2FWSS;
+    else return fail(h, CTU_ERR_CONFIG, "NR: Unknown noise reduction mode!");
+    h->vad_src = vm == "burg" ? VADSRC_BURG : vm == "file" ? VADSRC_FILE : VADSRC_NONE;
+    if (h->nr_mode >= NR_HWSS) {
+        if (h->vad_src == VADSRC_NONE) return fail(h, CTU_ERR_CONFIG, "NR: Please specify Voice Activity Detector!");
+        if (h->vad_src == VADSRC_BURG && c.nr_when == 1 && !h->signal_out)
+            return fail(h, CTU_ERR_CONFIG, "NR: Cannot use Burg detector after filter bank!");
+    }
+    std::string am(c.vad_apply_mode), om(c.vad_out_mode);
+    h->do_vad = (am != "none" || om != "none");
+    h->vad_drop = (am == "drop");
+    if (h->do_vad && h->signal_out)
+        return fail(h, CTU_ERR_UNSUPPORTED, "CTU: the VAD module with waveform output (the reference dereferences an uninitialised pointer there, src/io/batch.cc:63-65,230-241)");
+    if (h->do_vad) {
+        std::string cm(c.vad_cri_mode), tm(c.vad_thr_mode), dm(c.vad_cepdist_mode);
+        if (cm == "energy") h->vad_cri = VCRI_ENERGY;
+        else if (cm == "cepdist") {
+            if (dm == "lpc") {
+                h->vad_cri = VCRI_CEPDIST_LPC;
+                if (!c.phase_needed) return fail(h, CTU_ERR_CONFIG, "VADcri_cepdist: cannot perform iFFT!");
+            } else if (dm == "fea" || dm == "in") h->vad_cri = VCRI_CEPDIST_FEA;
+            else return fail(h, CTU_ERR_CONFIG, "VADcri_cepdist: unknown vad_cepdist_mode!");
+        } else return fail(h, CTU_ERR_CONFIG, "VAD: unknown vad_cri_mode!");
+        if (tm == "absolute") h->vad_thr = VTHR_ABSOLUTE;
+        else if (tm == "perc") h->vad_thr = VTHR_PERC;
+        else if (tm == "adapt") h->vad_thr = VTHR_ADAPT;
+        else if (tm == "dyn") h->vad_thr = VTHR_DYN;
+        else return fail(h, CTU_ERR_CONFIG, "VAD: unknown vad_thr_mode!");
+        if (c.vad_filter_order < 1 || c.vad_filter_order % 2 == 0)
+            return fail(h, CTU_ERR_CONFIG, "medianFilter: filter order must be positive, odd number!");
+    }
+    if (c.dither != 0.0)
+        return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -dither != 0 draws from glibc rand() in list order (src/io/in.cc:205,454); not reproducible on a parallel device. Use -dither 0.");
+    if (c.remove_dc1) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -remove_dc1 on is not built yet");
+    if (c.wfft != NFFT) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: only 512-point frames (window of 257..512 samples) are built so far");
+    return CTU_OK;
+}
+
+int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
+    if (!cfg || !out) { g_create_err = "CTU: null argument"; return CTU_ERR_CONFIG; }
+    *out = nullptr;
+    if (cfg->abi_version != CTU_ABI_VERSION) { g_create_err = "CTU: ABI version mismatch"; return CTU_ERR_CONFIG; }
+    ctu_handle *h = new ctu_handle;
+    h->cfg = *cfg;
+    h->device = device;
+    auto bail = [&](int st) { g_create_err = h->err; delete h; return st; };
+    int st = ctu_config_finalize(&h->cfg);
+    if (st) { h->err = ctu_config_error(); return bail(st); }
+    if ((st = resolve_modes(h))) return bail(st);
+    if (!h->signal_out) {
+        std::string e = ctu_design_fb(h->cfg, h->fb);
+        if (!e.empty()) { h->err = e; return bail(CTU_ERR_CONFIG); }
+    }
+    if ((st = build_frame_params(h))) return bail(st);
+    if ((st = build_delta_trap_params(h))) return bail(st);
+    if ((st = build_nr_params(h->cfg, h->nr_mode, h->vad_src, h->signal_out, h->fb.nb, h->nrp, h->sp, h->bp, h->vp, h->err))) return bail(st);
+    h->vp.cri = h->vad_cri; h->vp.thr = h->vad_thr; h->vp.drop = h->vad_drop;
+    // the device: fail loudly, there is no CPU path
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0 || device >= ndev) {
+        h->err = std::string("CUDA: no usable device (") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device index out of range") +
+                 "); libctucopy_b200 has no CPU fallback";
+        return bail(CTU_ERR_CUDA);
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { h->err = "CUDA: cudaSetDevice failed"; return bail(CTU_ERR_CUDA); }
+    if ((st = build_fft_tables(h))) return bail(st);
+    for (int i = 0; i < 3; i++)
+        if (cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking) != cudaSuccess) { h->err = "CUDA: stream creation failed"; return bail(CTU_ERR_CUDA); }
+    *out = h;
+    return CTU_OK;
+}
+
+void ctu_destroy(ctu_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_tw256); cudaFree(h->d_twsplit); cudaFree(h->d_twinv); cudaFree(h->d_win);
+    cudaFree(h->d_tw256d); cudaFree(h->d_twsplitd); cudaFree(h->d_twinvd); cudaFree(h->d_wind); cudaFree(h->d_hann);
+    for (int i = 0; i < 3; i++) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+    h->lc.clear();
+    delete h;
+}
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+template <class T> static int dev_alloc(ctu_handle *h, ctu_plan *p, T **ptr, size_t n) {
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    CK(cudaMalloc((void **)ptr, bytes));
+    p->workspace_bytes += (int64_t)bytes;
+    return CTU_OK;
+}
+
+int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out) {
+    if (!h || !off || !out || n < 0) return CTU_ERR_CONFIG;
+    *out = nullptr;
+    CK(cudaSetDevice(h->device));
+    ctu_plan *p = new ctu_plan;
+    p->h = h; p->n_utts = n;
+    p->offsets.assign(off, off + n + 1);
+    p->nframes.resize(n); p->row_off.resize(n + 1); p->osamp_off.resize(n + 1);
+    p->tile32_off.resize(n + 1); p->tile64_off.resize(n + 1);
+    p->rows_per_utt.assign(n, 0);
+    const int w = h->cfg.window, s = h->cfg.wshift;
+    int64_t rows = 0, osamp = 0, t32 = 0, t64 = 0;
+    for (int u = 0; u < n; u++) {
+        int64_t N = off[u + 1] - off[u];
+        if (N < w - s) { delete p; return fail(h, CTU_ERR_INPUT, "IO: Signal shorter than one frame!"); }
+        int64_t T = (N - (w - s)) / s;
+        if (T > 0x7fffffff) { delete p; return fail(h, CTU_ERR_INPUT, "CTU: utterance too long"); }
+        p->nframes[u] = (int)T;
+        p->row_off[u] = rows; p->osamp_off[u] = osamp; p->tile32_off[u] = t32; p->tile64_off[u] = t64;
+        rows += T; osamp += T * s + (w - s);
+        t32 += (T + TILE_F - 1) / TILE_F; t64 += (T + DELTA_ROWS - 1) / DELTA_ROWS;
+        p->rows_per_utt[u] = T;
+        // the delta / TRAP closed forms need win+2 rows; shorter files take the reference's
+        // start-up path whose output depends on never-written ring memory
+        if (h->dp.n_order > 0) {
+            int mw = 0;
+            for (int k = 0; k < h->dp.n_order; k++) mw = std::max(mw, h->dp.win[k]);
+            if (T < mw + 2) { delete p; return fail(h, CTU_ERR_UNSUPPORTED, "CTU: utterance shorter than delta window + 2 frames"); }
+        }
+    }
+    p->row_off[n] = rows; p->osamp_off[n] = osamp; p->tile32_off[n] = t32; p->tile64_off[n] = t64;
+    p->total_frames = rows; p->total_osamp = osamp; p->total_samples = off[n] - off[0];
+    int st = 0;
+    auto up64 = [&](int64_t **d, const std::vector<int64_t> &v) -> int {
+        if ((st = dev_alloc(h, p, d, v.size()))) return st;
+        CK(cudaMemcpy(*d, v.data(), v.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+        return CTU_OK;
+    };
+    std::vector<int64_t> pcm_off(p->offsets.begin(), p->offsets.end());   // same indexing as the caller's buffer
+    if ((st = up64(&p->d_pcm_off, pcm_off)) || (st = up64(&p->d_row_off, p->row_off)) || (st = up64(&p->d_osamp_off, p->osamp_off)) ||
+        (st = up64(&p->d_t32_off, p->tile32_off)) || (st = up64(&p->d_t64_off, p->tile64_off))) { ctu_plan_destroy(p); return st; }
+    if ((st = dev_alloc(h, p, &p->d_nframes, n))) { ctu_plan_destroy(p); return st; }
+    if (n) CK(cudaMemcpy(p->d_nframes, p->nframes.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    if ((st = dev_alloc(h, p, &p->d_tiles32, t32)) || (st = dev_alloc(h, p, &p->d_tiles64, t64))) { ctu_plan_destroy(p); return st; }
+    if (n) {
+        k_build_tiles<<<(n + 127) / 128, 128>>>(p->d_nframes, p->d_t32_off, n, TILE_F, p->d_tiles32);
+        k_build_tiles<<<(n + 127) / 128, 128>>>(p->d_nframes, p->d_t64_off, n, DELTA_ROWS, p->d_tiles64);
+        h->lc.launches += 2;
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+    }
+    // workspaces by configuration
+    const bool nr_on = h->nr_mode != NR_NONE;
+    const bool need_spec = h->signal_out || (nr_on && h->cfg.nr_when == 0) || (h->do_vad && h->vad_cri != VCRI_CEPDIST_FEA);
+    const bool need_fb = !h->signal_out && nr_on && h->cfg.nr_when == 1;
+    if (need_spec && (st = dev_alloc(h, p, &p->d_spec, (size_t)rows * NBIN))) { ctu_plan_destroy(p); return st; }
+    if (need_fb && (st = dev_alloc(h, p, &p->d_fb, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
+    if (h->fea_kind == FEA_TRAPDCT && (st = dev_alloc(h, p, &p->d_log, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
+    const bool burg_nr = h->nr_mode >= NR_HWSS && h->vad_src == VADSRC_BURG;
+    const bool burg_vad = h->do_vad && h->vad_cri == VCRI_CEPDIST_LPC;
+    if ((burg_nr || burg_vad) && (st = dev_alloc(h, p, &p->d_ceps, (size_t)rows * BURG_MAXC))) { ctu_plan_destroy(p); return st; }
+    if ((st = dev_alloc(h, p, &p->d_flags, (size_t)rows))) { ctu_plan_destroy(p); return st; }
+    if (h->do_vad) {
+        if ((st = dev_alloc(h, p, &p->d_cri, (size_t)rows)) || (st = dev_alloc(h, p, &p->d_keep, (size_t)rows)) || (st = dev_alloc(h, p, &p->d_vad0, (size_t)rows)) ||
+            (st = dev_alloc(h, p, &p->d_rows, (size_t)n))) { ctu_plan_destroy(p); return st; }
+    }
+    *out = p;
+    return CTU_OK;
+}
+
+void ctu_plan_destroy(ctu_plan *p) {
+    if (!p) return;
+    cudaSetDevice(p->h->device);
+    cudaFree(p->d_pcm_off); cudaFree(p->d_row_off); cudaFree(p->d_osamp_off); cudaFree(p->d_t32_off); cudaFree(p->d_t64_off);
+    cudaFree(p->d_nframes); cudaFree(p->d_tiles32); cudaFree(p->d_tiles64);
+    cudaFree(p->d_spec); cudaFree(p->d_fb); cudaFree(p->d_log); cudaFree(p->d_ceps); cudaFree(p->d_cri);
+    cudaFree(p->d_flags); cudaFree(p->d_keep); cudaFree(p->d_vad0); cudaFree(p->d_rows);
+    cudaFree(p->d_pcm); cudaFree(p->d_wave); cudaFree(p->d_fea); cudaFree(p->d_ext); cudaFree(p->d_vadnr_out); cudaFree(p->d_vad_out);
+    delete p;
+}
+
+int64_t ctu_plan_total_frames(const ctu_plan *p) { return p ? p->total_frames : 0; }
+int64_t ctu_plan_max_rows(const ctu_plan *p) { return p ? p->total_frames : 0; }
+int64_t ctu_plan_total_output_samples(const ctu_plan *p) { return p ? p->total_osamp : 0; }
+int64_t ctu_plan_workspace_bytes(const ctu_plan *p) { return p ? p->workspace_bytes : 0; }
+int ctu_plan_frames_per_utt(const ctu_plan *p, int64_t *f) {
+    if (!p || !f) return CTU_ERR_CONFIG;
+    for (int u = 0; u < p->n_utts; u++) f[u] = p->nframes[u];
+    return CTU_OK;
+}
+int ctu_plan_rows_per_utt(const ctu_plan *p, int64_t *r) {
+    if (!p || !r) return CTU_ERR_CONFIG;
+    for (int u = 0; u < p->n_utts; u++) r[u] = p->rows_per_utt[u];
+    return CTU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel sequencing
+// ------------------------------------------------------------------------------------------
+struct Range {          // a contiguous run of utterances = contiguous tiles and rows
+    int u0, u1;
+    int64_t t32_0, t32_n, t64_0, t64_n, row0, nrows;
+};
+
+static Range make_range(const ctu_plan *p, int u0, int u1) {
+    Range r;
+    r.u0 = u0; r.u1 = u1;
+    r.t32_0 = p->tile32_off[u0]; r.t32_n = p->tile32_off[u1] - r.t32_0;
+    r.t64_0 = p->tile64_off[u0]; r.t64_n = p->tile64_off[u1] - r.t64_0;
+    r.row0 = p->row_off[u0]; r.nrows = p->row_off[u1] - r.row0;
+    return r;
+}
+
+template <int SRC, int DST, int KIND>
+static int launch_frames_t(ctu_handle *h, const FrameParams &P, const BatchDesc &bd, int64_t ntiles, const int16_t *pcm,
+                           const float *src, float *dst, cudaStream_t s) {
+    if (ntiles <= 0) return CTU_OK;
+    SmemLayout L = smem_layout(P.window, P.wshift, P.nb);
+    size_t bytes = (size_t)L.total * sizeof(float);
+    static thread_local bool attr_done = false;
+    auto kern = k_frames<SRC, DST, KIND>;
+    if (!attr_done || true) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        attr_done = true;
+    }
+    FftTables tb{h->d_tw256, h->d_twsplit, h->d_twinv, h->d_win};
+    static const char *const names[3][3] = {{"k_frames<pcm,spec>", "k_frames<pcm,fb>", "k_frames<pcm,fea>"},
+                                            {"k_frames<spec,spec>", "k_frames<spec,fb>", "k_frames<spec,fea>"},
+                                            {"k_frames<fb,spec>", "k_frames<fb,fb>", "k_frames<fb,fea>"}};
+    h->lc.begin(names[SRC][DST], s);
+    kern<<<(unsigned)ntiles, CTA_THREADS, bytes, s>>>(P, bd, tb, pcm, src, dst);
+    h->lc.end(s);
+    CK(cudaGetLastError());
+    return CTU_OK;
+}
+
+template <int SRC, int DST>
+static int launch_frames_k(ctu_handle *h, int kind, const FrameParams &P, const BatchDesc &bd, int64_t nt, const int16_t *pcm,
+                           const float *src, float *dst, cudaStream_t s) {
+    switch (kind) {
+        case KIND_SPEC: return launch_frames_t<SRC, DST, KIND_SPEC>(h, P, bd, nt, pcm, src, dst, s);
+        case KIND_LOGSPEC: return launch_frames_t<SRC, DST, KIND_LOGSPEC>(h, P, bd, nt, pcm, src, dst, s);
+        case KIND_DCTC: return launch_frames_t<SRC, DST, KIND_DCTC>(h, P, bd, nt, pcm, src, dst, s);
+        case KIND_LPA: return launch_frames_t<SRC, DST, KIND_LPA>(h, P, bd, nt, pcm, src, dst, s);
+        case KIND_LPC: return launch_frames_t<SRC, DST, KIND_LPC>(h, P, bd, nt, pcm, src, dst, s);
+        case KIND_TRAPLOG: return launch_frames_t<SRC, DST, KIND_TRAPLOG>(h, P, bd, nt, pcm, src, dst, s);
+    }
+    return fail(h, CTU_ERR_CONFIG, "CTU: bad kind");
+}
+
+static int kind_of(const ctu_handle *h) {
+    switch (h->fea_kind) {
+        case FEA_SPEC: return KIND_SPEC;
+        case FEA_LOGSPEC: return KIND_LOGSPEC;
+        case FEA_DCTC: return KIND_DCTC;
+        case FEA_LPA: return KIND_LPA;
+        case FEA_LPC: return KIND_LPC;
+        case FEA_TRAPDCT: return KIND_TRAPLOG;
+    }
+    return KIND_SPEC;
+}
+
+// Runs utterances [u0,u1) of the plan on stream s.  All pointers are whole-batch device
+// buffers (rows / samples are addressed through the plan's global offsets).
+static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const uint8_t *d_ext, float *d_fea, int16_t *d_wave,
+                     uint8_t *d_vadnr, uint8_t *d_vadout, cudaStream_t s) {
+    ctu_handle *h = p->h;
+    if (r.nrows <= 0 && !h->signal_out) return CTU_OK;
+    BatchDesc bd32{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tiles32 + r.t32_0};
+    BatchDesc bd64{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tiles64 + r.t64_0};
+    int st;
+    const int kind = kind_of(h);
+    uint8_t *flags = d_vadnr ? d_vadnr : p->d_flags;
+
+    // ---- stage 1: spectrum / band values, noise reduction ---------------------------------
+    const bool nr_on = h->nr_mode != NR_NONE;
+    const bool before = h->cfg.nr_when == 0 || h->signal_out;
+    const bool need_spec = p->d_spec != nullptr;
+    FrameParams P = h->fp;
+    if (need_spec) {
+        P.out_dim = NBIN; P.out_stride = NBIN;
+        if ((st = launch_frames_t<SRC_PCM, DST_SPEC, KIND_SPEC>(h, P, bd32, r.t32_n, d_pcm, nullptr, p->d_spec, s))) return st;
+    }
+    if (nr_on && before) {
+        if (h->nr_mode >= NR_HWSS && h->vad_src == VADSRC_BURG) {
+            if ((st = launch_burg(h->bp, BURG_SRC_NR, bd32, r.t32_n, d_pcm, nullptr, p->d_ceps, h->d_tw256d, h->d_twsplitd, h->d_twinvd, h->d_wind,
+                                  h->d_hann, s, &h->lc, h->err))) return st;
+            if ((st = launch_cepdet(h->bp, p->d_nframes, p->d_row_off, r.u0, r.u1, p->d_ceps, flags, s, &h->lc, h->err))) return st;
+        }
+        const uint8_t *fl = (h->nr_mode >= NR_HWSS) ? (h->vad_src == VADSRC_FILE ? d_ext : flags) : nullptr;
+        if (h->nr_mode >= NR_HWSS && !fl) return fail(h, CTU_ERR_INPUT, "NR: Unable to open VAD file!\n");
+        if ((st = launch_nr_scan(h->nrp, p->d_nframes, p->d_row_off, r.u0, r.u1, NBIN, p->d_spec, fl, s, &h->lc, h->err))) return st;
+        if (h->vad_src == VADSRC_FILE && d_vadnr && h->nr_mode >= NR_HWSS)
+            CK(cudaMemcpyAsync(d_vadnr + r.row0, d_ext + r.row0, r.nrows, cudaMemcpyDeviceToDevice, s));
+    }
+    if (h->signal_out) {
+        return launch_synth(h->sp, h->fp, bd32, p->d_tiles32 + r.t32_0, r.t32_n, p->d_osamp_off, d_pcm, p->d_spec, d_wave, h->d_tw256,
+                            h->d_twsplit, h->d_twinv, h->d_win, s, &h->lc, h->err);
+    }
+
+    // ---- stage 2: features ------------------------------------------------------------------
+    float *fea_dst = d_fea;
+    int od = h->static_dim, ostride = h->feature_dim;
+    if (kind == KIND_TRAPLOG) { fea_dst = p->d_log; od = h->fb.nb; ostride = h->fb.nb; }
+    P = h->fp; P.out_dim = od; P.out_stride = ostride;
+    if (nr_on && !before) {
+        FrameParams Pf = h->fp; Pf.out_dim = h->fb.nb; Pf.out_stride = h->fb.nb;
+        if (need_spec) { if ((st = launch_frames_t<SRC_SPEC, DST_FB, KIND_SPEC>(h, Pf, bd32, r.t32_n, nullptr, p->d_spec, p->d_fb, s))) return st; }
+        else if ((st = launch_frames_t<SRC_PCM, DST_FB, KIND_SPEC>(h, Pf, bd32, r.t32_n, d_pcm, nullptr, p->d_fb, s))) return st;
+        const uint8_t *fl = (h->nr_mode >= NR_HWSS) ? d_ext : nullptr;
+        if (h->nr_mode >= NR_HWSS && !fl) return fail(h, CTU_ERR_INPUT, "NR: Unable to open VAD file!\n");
+        if ((st = launch_nr_scan(h->nrp, p->d_nframes, p->d_row_off, r.u0, r.u1, h->fb.nb, p->d_fb, fl, s, &h->lc, h->err))) return st;
+        if (d_vadnr && fl) CK(cudaMemcpyAsync(d_vadnr + r.row0, d_ext + r.row0, r.nrows, cudaMemcpyDeviceToDevice, s));
+        if ((st = launch_frames_k<SRC_FB, DST_FEA>(h, kind, P, bd32, r.t32_n, nullptr, p->d_fb, fea_dst, s))) return st;
+    } else if (need_spec) {
+        if ((st = launch_frames_k<SRC_SPEC, DST_FEA>(h, kind, P, bd32, r.t32_n, nullptr, p->d_spec, fea_dst, s))) return st;
+    } else {
+        if ((st = launch_frames_k<SRC_PCM, DST_FEA>(h, kind, P, bd32, r.t32_n, d_pcm, nullptr, fea_dst, s))) return st;
+    }
+    // ---- stage 3: long-context ------------------------------------------------------------
+    if (kind == KIND_TRAPLOG && r.t64_n > 0) {
+        size_t bytes = (size_t)(TRAP_ROWS + h->tp.L - 1) * h->tp.nb * sizeof(float);
+        CK(cudaFuncSetAttribute(k_trapdct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        h->lc.begin("k_trapdct", s);
+        k_trapdct<<<(unsigned)r.t64_n, 256, bytes, s>>>(h->tp, bd64, TRAP_ROWS, p->d_log, d_fea);
+        h->lc.end(s);
+        CK(cudaGetLastError());
+    }
+    if (h->dp.n_order > 0 && r.t64_n > 0) {
+        size_t bytes = (size_t)2 * h->dp.span_max * h->dp.blk * sizeof(float);
+        CK(cudaFuncSetAttribute(k_delta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        h->lc.begin("k_delta", s);
+        k_delta<<<(unsigned)r.t64_n, 256, bytes, s>>>(h->dp, bd64, DELTA_ROWS, d_fea);
+        h->lc.end(s);
+        CK(cudaGetLastError());
+    }
+    // ---- stage 4: VAD module -----------------------------------------------------------------
+    if (h->do_vad) {
+        if ((st = launch_vad_module(h->vp, h->bp, bd32, r.t32_n, p->d_nframes, p->d_row_off, r.u0, r.u1, r.row0, r.nrows, d_pcm, p->d_spec, d_fea,
+                                    h->feature_dim, p->d_ceps, p->d_cri, p->d_vad0, d_vadout, p->d_keep, p->d_rows, h->d_tw256d, h->d_twsplitd,
+                                    h->d_twinvd, h->d_wind, s, &h->lc, h->err))) return st;
+    }
+    return CTU_OK;
+}
+
+static int fetch_rows(ctu_plan *p, cudaStream_t s) {
+    ctu_handle *h = p->h;
+    if (!h->do_vad || !h->vad_drop) {
+        for (int u = 0; u < p->n_utts; u++) p->rows_per_utt[u] = p->nframes[u];
+        return CTU_OK;
+    }
+    std::vector<int> rows(p->n_utts);
+    CK(cudaMemcpyAsync(rows.data(), p->d_rows, p->n_utts * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int u = 0; u < p->n_utts; u++) p->rows_per_utt[u] = rows[u];
+    return CTU_OK;
+}
+
+int ctu_plan_run_device(ctu_plan *p, const int16_t *d_pcm, const uint8_t *d_ext_vad, float *d_features, int16_t *d_waveform,
+                        uint8_t *d_vad_nr, uint8_t *d_vad_out, void *stream) {
+    if (!p) return CTU_ERR_CONFIG;
+    ctu_handle *h = p->h;
+    CK(cudaSetDevice(h->device));
+    if (!h->signal_out && !d_features) return fail(h, CTU_ERR_CAPACITY, "CTU: features buffer is NULL");
+    if (h->signal_out && !d_waveform) return fail(h, CTU_ERR_CAPACITY, "CTU: waveform buffer is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    Range r = make_range(p, 0, p->n_utts);
+    if (h->signal_out) CK(cudaMemsetAsync(d_waveform, 0, (size_t)p->total_osamp * sizeof(int16_t), s));
+    int st = run_range(p, r, d_pcm, d_ext_vad, d_features, d_waveform, d_vad_nr, d_vad_out, s);
+    if (st) return st;
+    return fetch_rows(p, s);
+}
+
+int ctu_plan_run_host(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad, float *features, int16_t *waveform, uint8_t *vad_nr,
+                      uint8_t *vad_out) {
+    if (!p) return CTU_ERR_CONFIG;
+    ctu_handle *h = p->h;
+    CK(cudaSetDevice(h->device));
+    if (!h->signal_out && !features) return fail(h, CTU_ERR_CAPACITY, "CTU: features buffer is NULL");
+    if (h->signal_out && !waveform) return fail(h, CTU_ERR_CAPACITY, "CTU: waveform buffer is NULL");
+    int st;
+    if (!p->host_bufs) {
+        if ((st = dev_alloc(h, p, &p->d_pcm, (size_t)p->total_samples + 8))) return st;
+        if (!h->signal_out && (st = dev_alloc(h, p, &p->d_fea, (size_t)p->total_frames * h->feature_dim))) return st;
+        if (h->signal_out && (st = dev_alloc(h, p, &p->d_wave, (size_t)p->total_osamp))) return st;
+        if ((st = dev_alloc(h, p, &p->d_ext, (size_t)p->total_frames))) return st;
+        if ((st = dev_alloc(h, p, &p->d_vadnr_out, (size_t)p->total_frames))) return st;
+        if ((st = dev_alloc(h, p, &p->d_vad_out, (size_t)p->total_frames))) return st;
+        p->host_bufs = true;
+    }
+    // chunks of utterances of roughly 64 MB of PCM, round-robin over three streams so that
+    // H2D of chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap
+    const int64_t chunk_samples = 32ll << 20;
+    int u0 = 0, ci = 0;
+    const int64_t base = p->offsets[0];
+    while (u0 < p->n_utts) {
+        int u1 = u0 + 1;
+        while (u1 < p->n_utts && p->offsets[u1 + 1] - p->offsets[u0] <= chunk_samples) u1++;
+        cudaStream_t s = h->streams[ci % 3];
+        Range r = make_range(p, u0, u1);
+        int64_t so = p->offsets[u0] - base, sn = p->offsets[u1] - p->offsets[u0];
+        CK(cudaMemcpyAsync(p->d_pcm + so, pcm + p->offsets[u0], sn * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+        if (ext_vad && r.nrows) CK(cudaMemcpyAsync(p->d_ext + r.row0, ext_vad + r.row0, r.nrows, cudaMemcpyHostToDevice, s));
+        if (h->signal_out) CK(cudaMemsetAsync(p->d_wave + p->osamp_off[u0], 0, (size_t)(p->osamp_off[u1] - p->osamp_off[u0]) * sizeof(int16_t), s));
+        if ((st = run_range(p, r, p->d_pcm - base, ext_vad ? p->d_ext : nullptr, p->d_fea, p->d_wave, p->d_vadnr_out, p->d_vad_out, s))) return st;
+        if (!h->signal_out && r.nrows)
+            CK(cudaMemcpyAsync(features + r.row0 * h->feature_dim, p->d_fea + r.row0 * h->feature_dim,
+                               (size_t)r.nrows * h->feature_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (h->signal_out) {
+            int64_t o0 = p->osamp_off[u0], on = p->osamp_off[u1] - o0;
+            CK(cudaMemcpyAsync(waveform + o0, p->d_wave + o0, on * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+        }
+        if (vad_nr && r.nrows) CK(cudaMemcpyAsync(vad_nr + r.row0, p->d_vadnr_out + r.row0, r.nrows, cudaMemcpyDeviceToHost, s));
+        if (vad_out && r.nrows && h->do_vad) CK(cudaMemcpyAsync(vad_out + r.row0, p->d_vad_out + r.row0, r.nrows, cudaMemcpyDeviceToHost, s));
+        u0 = u1; ci++;
+    }
+    for (int i = 0; i < 3; i++) CK(cudaStreamSynchronize(h->streams[i]));
+    return fetch_rows(p, h->streams[0]);
+}
+
+int ctu_run(ctu_handle *h, const int16_t *pcm, const int64_t *off, int32_t n, const uint8_t *ext_vad, float *features,
+            int64_t fcap_rows, int16_t *waveform, int64_t wcap, uint8_t *vad_nr, uint8_t *vad_out, int64_t *frames_per_utt,
+            int64_t *rows_per_utt) {
+    ctu_plan *p = nullptr;
+    int st = ctu_plan_create(h, off, n, &p);
+    if (st) return st;
+    if (!h->signal_out && fcap_rows < p->total_frames) { ctu_plan_destroy(p); return fail(h, CTU_ERR_CAPACITY, "CTU: features buffer too small"); }
+    if (h->signal_out && wcap < p->total_osamp) { ctu_plan_destroy(p); return fail(h, CTU_ERR_CAPACITY, "CTU: waveform buffer too small"); }
+    st = ctu_plan_run_host(p, pcm + 0, ext_vad, features, waveform, vad_nr, vad_out);
+    if (!st && frames_per_utt) ctu_plan_frames_per_utt(p, frames_per_utt);
+    if (!st && rows_per_utt) ctu_plan_rows_per_utt(p, rows_per_utt);
+    ctu_plan_destroy(p);
+    return st;
+}
+
+int ctu_debug_spectrum(ctu_plan *p, const int16_t *d_pcm, float *d_spec, void *stream) {
+    if (!p) return CTU_ERR_CONFIG;
+    ctu_handle *h = p->h;
+    CK(cudaSetDevice(h->device));
+    BatchDesc bd32{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tiles32};
+    FrameParams P = h->fp; P.out_dim = NBIN; P.out_stride = NBIN;
+    int st = launch_frames_t<SRC_PCM, DST_SPEC, KIND_SPEC>(h, P, bd32, p->tile32_off[p->n_utts], d_pcm, nullptr, d_spec, (cudaStream_t)stream);
+    if (st) return st;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return CTU_OK;
+}

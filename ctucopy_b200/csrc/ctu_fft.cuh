@@ -1,0 +1,162 @@
+// 512-point real FFT as a 256-point complex FFT (16 x 16 four-step) carried by a GROUP of
+// 16 threads, each holding 16 complex points in registers.  One shared-memory transpose
+// between the two radix-16 passes, one for the real-input split.  The same code is used
+// for float (feature path) and double (Burg detector path) and for the inverse transform
+// (conjugate trick).  Everything here is __host__ __device__ so tests/emu can run the
+// identical index algebra on the CPU, thread by thread.
+//
+// Conventions (match FFTW's R2HC / HC2R as the reference uses them, src/io/in.cc:229,388,
+// src/io/out.cc:391,425): forward X[k] = sum_n x[n] e^{-2 pi i nk/512}; inverse
+// unnormalised.
+#ifndef CTU_FFT_CUH
+#define CTU_FFT_CUH
+
+#if defined(__CUDACC__)
+#define CTU_HD __host__ __device__ __forceinline__
+#else
+#define CTU_HD inline
+#endif
+
+namespace ctu {
+
+constexpr int NFFT = 512;   // real transform length handled by the fast path
+constexpr int NC = 256;     // complex length
+constexpr int NBIN = 257;   // NFFT/2 + 1
+constexpr int GROUP = 16;   // threads per frame
+constexpr int XPAD = 17;    // row pitch (in complex elements) of the 16x16 exchange tile
+
+template <class T> struct cpx { T x, y; };
+
+template <class T> CTU_HD cpx<T> mk(T x, T y) { cpx<T> r; r.x = x; r.y = y; return r; }
+template <class T> CTU_HD cpx<T> operator+(cpx<T> a, cpx<T> b) { return mk<T>(a.x + b.x, a.y + b.y); }
+template <class T> CTU_HD cpx<T> operator-(cpx<T> a, cpx<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
+template <class T> CTU_HD cpx<T> cmul(cpx<T> a, cpx<T> b) { return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+template <class T> CTU_HD cpx<T> conj(cpx<T> a) { return mk<T>(a.x, -a.y); }
+template <class T> CTU_HD cpx<T> mul_mi(cpx<T> a) { return mk<T>(a.y, -a.x); }   // a * (-i)
+
+// forward 4-point DFT, natural order in and out
+template <class T> CTU_HD void dft4(cpx<T> &a0, cpx<T> &a1, cpx<T> &a2, cpx<T> &a3) {
+    cpx<T> s0 = a0 + a2, d0 = a0 - a2, s1 = a1 + a3, d1 = mul_mi(a1 - a3);
+    a0 = s0 + s1; a2 = s0 - s1; a1 = d0 + d1; a3 = d0 - d1;
+}
+
+// forward 16-point DFT in registers (4 x 4), natural order in and out
+template <class T> CTU_HD void dft16(cpx<T> (&a)[16]) {
+    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173, r2 = (T)0.70710678118654752440;
+#pragma unroll
+    for (int n2 = 0; n2 < 4; n2++) dft4(a[n2], a[4 + n2], a[8 + n2], a[12 + n2]);
+    // a[4*k1 + n2] *= W16^(n2*k1)
+    a[5] = cmul(a[5], mk<T>(c1, -s1));                       // 1
+    a[6] = mk<T>((a[6].x + a[6].y) * r2, (a[6].y - a[6].x) * r2);   // 2: (r2,-r2)
+    a[7] = cmul(a[7], mk<T>(s1, -c1));                       // 3
+    a[9] = mk<T>((a[9].x + a[9].y) * r2, (a[9].y - a[9].x) * r2);   // 2
+    a[10] = mul_mi(a[10]);                                   // 4
+    a[11] = mk<T>((a[11].y - a[11].x) * r2, -(a[11].x + a[11].y) * r2);  // 6: (-r2,-r2)
+    a[13] = cmul(a[13], mk<T>(s1, -c1));                     // 3
+    a[14] = mk<T>((a[14].y - a[14].x) * r2, -(a[14].x + a[14].y) * r2);  // 6
+    a[15] = cmul(a[15], mk<T>(-c1, s1));                     // 9
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) dft4(a[4 * k1], a[4 * k1 + 1], a[4 * k1 + 2], a[4 * k1 + 3]);
+    // a[4*k1 + k2] now holds X[k1 + 4*k2]: transpose the 4x4 register tile
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = i + 1; j < 4; j++) { cpx<T> t = a[4 * i + j]; a[4 * i + j] = a[4 * j + i]; a[4 * j + i] = t; }
+}
+
+// ---- 256-point complex FFT over a group of 16 threads ----------------------------------
+// pass 1: thread c holds z[16*n1 + c], n1 = 0..15.  Transforms over n1, applies the
+//         inter-pass twiddle W256^(c*k1) and stores A[k1][c] into the exchange tile.
+// tw256 : [16][16] with tw256[k1*16 + c] = W256^(c*k1)
+template <class T>
+CTU_HD void fft256_pass1(cpx<T> (&a)[16], int c, const cpx<T> *tw256, cpx<T> *xch) {
+    dft16(a);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) {
+        cpx<T> v = a[k1];
+        if (k1 > 0) v = cmul(v, tw256[k1 * 16 + c]);
+        xch[k1 * XPAD + c] = v;
+    }
+}
+// pass 2 (after a group-wide sync): thread c now plays k1 = c; loads A[c][n2], transforms
+// over n2; on return a[k2] = Z[c + 16*k2].
+template <class T>
+CTU_HD void fft256_pass2(cpx<T> (&a)[16], int c, const cpx<T> *xch) {
+#pragma unroll
+    for (int n2 = 0; n2 < 16; n2++) a[n2] = xch[c * XPAD + n2];
+    dft16(a);
+}
+
+// ---- real-input split ---------------------------------------------------------------------
+// After pass 2 every thread stores Z linearly (zlin[c + 16*k2] = a[k2]); after a sync,
+// thread c owns the bin pairs (k, 256-k) for k = c + 16*j, j = 0..7.
+// twsplit[k] = -i/2 * e^{-2 pi i k/512}, k = 0..128
+// Returns X[k] in lo[j] and X[256-k] in hi[j].  For k == 0: lo = X[0], hi = X[256] (both
+// real).  For k == 128 (c == 0, j == 8 does not exist; k = 128 arises for c == 0 only via
+// the dedicated slot `mid`): mid = X[128].
+template <class T>
+CTU_HD void rfft_split(const cpx<T> *zlin, int c, const cpx<T> *twsplit, cpx<T> (&lo)[8], cpx<T> (&hi)[8], cpx<T> &mid) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        int k = c + 16 * j;
+        cpx<T> A = zlin[k];
+        if (k == 0) {
+            lo[j] = mk<T>(A.x + A.y, (T)0);
+            hi[j] = mk<T>(A.x - A.y, (T)0);
+        } else {
+            cpx<T> B = conj(zlin[NC - k]);
+            cpx<T> E = mk<T>((T)0.5 * (A.x + B.x), (T)0.5 * (A.y + B.y));
+            cpx<T> Tt = cmul(twsplit[k], A - B);
+            lo[j] = E + Tt;
+            hi[j] = conj(E - Tt);
+        }
+    }
+    mid = conj(zlin[128]);   // only meaningful for c == 0
+}
+
+// ---- inverse: half-complex spectrum -> 512 real samples (unnormalised) ------------------
+// Thread c provides X[k] (lo[j]) and X[256-k] (hi[j]) for k = c + 16*j and, for c == 0,
+// X[128] in mid.  Writes conj(Zc) into zlin; after a sync run pass1 (loading column c of
+// zlin), pass2, and read time samples x[2n] = Re, x[2n+1] = -Im of a[k2], n = c + 16*k2.
+// twinv[k] = e^{+2 pi i k/512}, k = 0..128
+template <class T>
+CTU_HD void irfft_presplit(cpx<T> *zlin, int c, const cpx<T> *twinv, const cpx<T> (&lo)[8], const cpx<T> (&hi)[8], cpx<T> mid) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        int k = c + 16 * j;
+        if (k == 0) {
+            // X[0], X[256] real:  Zc[0] = (X0 + X256) + i (X0 - X256)
+            zlin[0] = conj(mk<T>(lo[j].x + hi[j].x, lo[j].x - hi[j].x));
+        } else {
+            cpx<T> S = lo[j] + conj(hi[j]);
+            cpx<T> U = cmul(lo[j] - conj(hi[j]), twinv[k]);
+            // Zc[k] = S + i U ; Zc[256-k] = conj(S) + i conj(U)
+            cpx<T> zk = mk<T>(S.x - U.y, S.y + U.x);
+            cpx<T> zn = mk<T>(S.x + U.y, -S.y + U.x);
+            zlin[k] = conj(zk);
+            zlin[NC - k] = conj(zn);
+        }
+    }
+    if (c == 0) {
+        // k = 128 pairs with itself: Zc[128] = 2*conj(X[128]) ... derive from the general
+        // form with X[k] = X[256-k] = mid:  S = mid + conj(mid), U = (mid - conj(mid)) * i
+        cpx<T> S = mk<T>((T)2 * mid.x, (T)0);
+        cpx<T> U = cmul(mk<T>((T)0, (T)2 * mid.y), twinv[128]);
+        zlin[128] = conj(mk<T>(S.x - U.y, S.y + U.x));
+    }
+}
+
+template <class T>
+CTU_HD void fft256_load_column(cpx<T> (&a)[16], int c, const cpx<T> *zlin) {
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) a[n1] = zlin[16 * n1 + c];
+}
+
+template <class T>
+CTU_HD void fft256_store_linear(const cpx<T> (&a)[16], int c, cpx<T> *zlin) {
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++) zlin[c + 16 * k2] = a[k2];
+}
+
+}  // namespace ctu
+#endif

@@ -1,0 +1,522 @@
+// Device code of the CtuCopy hot path for sm_100a.  One CTA processes a TILE of 32
+// consecutive frames of one utterance:
+//   phase A  PCM -> pre-emphasis (once per sample, shared by the overlapping frames)
+//            -> Hamming -> DC removal -> 512-point real FFT (16 threads per frame,
+//            ctu_fft.cuh) -> power / magnitude tile in shared memory       [K1]
+//   phase B  filter bank as banded FMAs with lane == frame (weights are warp-uniform
+//            kernel-parameter loads, the spectrum tile is read conflict-free)   [K1a]
+//   phase C  feature transform (log+DCT+lifter | iDFT+Levinson+cepstrum | ...) [K1b, K1c]
+// and writes each frame's features once.  Replaces rawIN::get_frame (src/io/in.cc:305-419),
+// FB::project_frame (src/fea/fb.cc:72-86) and the FEA::process_frame family
+// (src/fea/fea_impl.cc:37-284) of the reference.
+#ifndef CTU_KERNELS_CUH
+#define CTU_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "ctu_fft.cuh"
+
+namespace ctu {
+
+// host-side launch bookkeeping: counts kernel launches and, when profiling is switched on
+// (ctu_profile_enable), brackets every kernel with CUDA events on its own stream
+struct LaunchCtx {
+    struct Rec { const char *name; cudaEvent_t a, b; };
+    uint64_t launches = 0;
+    bool prof_on = false;
+    std::vector<Rec> recs;
+    void begin(const char *name, cudaStream_t s) {
+        launches++;
+        if (!prof_on) return;
+        Rec r; r.name = name;
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, s);
+        recs.push_back(r);
+    }
+    void end(cudaStream_t s) { if (prof_on) cudaEventRecord(recs.back().b, s); }
+    void clear() { for (auto &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } recs.clear(); }
+};
+
+constexpr int TILE_F = 32;        // frames per CTA tile
+constexpr int CTA_THREADS = 256;  // 8 warps; 16 frames in flight per FFT pass
+constexpr int MAXB = 64;          // filter-bank bands
+constexpr int MAXW = 2560;        // packed filter-bank taps
+constexpr int MAXR = 40;          // rows of the second-stage matrix (cepstra / autocorrelation lags)
+constexpr int MAXM2 = 2048;       // second-stage matrix entries (rows x nb)
+constexpr int LDP = NBIN;         // pitch of the spectrum tile (257: odd -> lane==frame reads are conflict free)
+
+enum Src { SRC_PCM = 0, SRC_SPEC = 1, SRC_FB = 2 };
+enum Dst { DST_SPEC = 0, DST_FB = 1, DST_FEA = 2 };
+enum Kind { KIND_SPEC = 1, KIND_LOGSPEC = 2, KIND_DCTC = 3, KIND_LPA = 4, KIND_LPC = 5, KIND_TRAPLOG = 6 };
+
+// kernel parameter block (lives in the constant bank: warp-uniform indexed loads)
+struct FrameParams {
+    int window, wshift;
+    float preem;
+    int remove_dc;
+    int take_sqrt;         // !fb_power: magnitude instead of power (src/io/in.cc:415-417)
+    // filter bank
+    int nb;
+    int inld;              // ^0.33 (src/fea/fb.cc:81-83)
+    float inld_scale;      // S^-0.33 where the packed weights carry a factor S
+    float lin_scale;       // 1/S
+    float log_offset;      // -ln S
+    short lo[MAXB], hi[MAXB];
+    int woff[MAXB];
+    float w[MAXW];
+    // second stage
+    int nrows;             // rows of m2 (dctc: output columns in writer order; lpc/lpa: lporder+1 lags)
+    float m2[MAXM2];       // [nrows][nb]
+    int lporder, ncep;     // lpc/lpa
+    int lpa_square;        // lpa/lpc without inld: square the band values first (src/fea/fea_impl.cc:165-169)
+    int c0_last;           // lpc: write c1..cN then c0 (fea_c0 on) else c1..cN
+    float lift[MAXR];      // lpc lifter for c1..cN (1 when fea_lifter <= 1)
+    // output geometry
+    int out_dim;           // values this kernel writes per row
+    int out_stride;        // floats per row of the destination matrix
+};
+
+struct BatchDesc {
+    const int64_t *pcm_off;   // [n_utts] first sample of each utterance in the PCM buffer
+    const int *nframes;       // [n_utts]
+    const int64_t *row_off;   // [n_utts] first global frame index
+    const int2 *tiles;        // [n_tiles] (utterance, first frame)
+};
+
+struct FftTables {            // device pointers
+    const float2 *tw256, *twsplit, *twinv;
+    const float *win;
+};
+
+// sum over the 16 lanes of this thread's half warp (the two halves may be divergent, so
+// each names only its own lanes in the mask)
+__device__ __forceinline__ float group_sum16(float v) {
+    const unsigned m = 0xffffu << (threadIdx.x & 16);
+    v += __shfl_xor_sync(m, v, 8);
+    v += __shfl_xor_sync(m, v, 4);
+    v += __shfl_xor_sync(m, v, 2);
+    v += __shfl_xor_sync(m, v, 1);
+    return v;
+}
+
+// shared-memory carve-up (floats)
+struct SmemLayout {
+    int oP, oY, oD, oW, oX, oTw, oTs, oR, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int window, int wshift, int nb) {
+    SmemLayout L;
+    int o = 0;
+    L.oP = o; o += TILE_F * LDP;
+    L.oY = o; o += TILE_F * (MAXB + 1);
+    L.oD = o; o += ((TILE_F - 1) * wshift + window + 3) & ~3;
+    L.oW = o; o += (window + 3) & ~3;
+    L.oX = o; o += (CTA_THREADS / GROUP) * XPAD * 16 * 2;      // one 16x17 complex tile per group
+    L.oTw = o; o += 256 * 2;
+    L.oTs = o; o += 130 * 2;
+    o = (o + 1) & ~1;
+    L.oR = o; o += 2 * TILE_F * (MAXR + 1);                    // doubles: autocorrelation lags
+    L.total = o;
+    (void)nb;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------
+// phase A: tile of PCM -> spectrum tile sP[f][k]
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void phase_fft(const FrameParams &P, const int16_t *__restrict__ pcm, int64_t g0, bool first_tile,
+                                          int nf, const FftTables &tb, float *sm, const SmemLayout &L) {
+    const int tid = threadIdx.x;
+    float *sP = sm + L.oP, *sD = sm + L.oD, *sW = sm + L.oW;
+    cpx<float> *sTw = reinterpret_cast<cpx<float> *>(sm + L.oTw);
+    cpx<float> *sTs = reinterpret_cast<cpx<float> *>(sm + L.oTs);
+    const int w = P.window, s = P.wshift;
+    const int nsamp = (nf - 1) * s + w;
+    // stage: pre-emphasised samples (each sample converted once, shared by overlapping frames)
+    const float alpha = P.preem;
+    for (int i = tid; i < nsamp; i += CTA_THREADS) {
+        float xi = (float)pcm[g0 + i];
+        float xp = (i == 0 && first_tile) ? 0.f : (float)pcm[g0 + i - 1];
+        sD[i] = fmaf(-alpha, xp, xi);
+    }
+    for (int i = tid; i < w; i += CTA_THREADS) sW[i] = tb.win[i];
+    for (int i = tid; i < 256; i += CTA_THREADS) sTw[i] = mk<float>(tb.tw256[i].x, tb.tw256[i].y);
+    for (int i = tid; i < 129; i += CTA_THREADS) sTs[i] = mk<float>(tb.twsplit[i].x, tb.twsplit[i].y);
+    __syncthreads();
+
+    const int c = tid & (GROUP - 1);
+    const int grp = tid / GROUP;                          // 0..15
+    cpx<float> *xch = reinterpret_cast<cpx<float> *>(sm + L.oX) + grp * (XPAD * 16);
+    const float inv_w = 1.0f / (float)w;
+#pragma unroll 1
+    for (int pass = 0; pass < TILE_F / (CTA_THREADS / GROUP); pass++) {
+        const int f = pass * (CTA_THREADS / GROUP) + grp;
+        const bool active = f < nf;
+        cpx<float> a[16];
+        if (active) {
+            const float *d = sD + f * s;
+            float sum = 0.f;
+#pragma unroll
+            for (int n1 = 0; n1 < 16; n1++) {
+                int i0 = 32 * n1 + 2 * c;
+                float y0 = (i0 < w) ? sW[i0] * d[i0] : 0.f;
+                float y1 = (i0 + 1 < w) ? sW[i0 + 1] * d[i0 + 1] : 0.f;
+                a[n1] = mk<float>(y0, y1);
+                sum += y0 + y1;
+            }
+            if (P.remove_dc) {
+                // mean of the WINDOWED frame, subtracted from the window's samples only
+                // (src/io/in.cc:375-382)
+                float mean = group_sum16(sum) * inv_w;
+#pragma unroll
+                for (int n1 = 0; n1 < 16; n1++) {
+                    int i0 = 32 * n1 + 2 * c;
+                    if (i0 < w) a[n1].x -= mean;
+                    if (i0 + 1 < w) a[n1].y -= mean;
+                }
+            }
+            fft256_pass1(a, c, sTw, xch);
+        }
+        __syncwarp();
+        if (active) fft256_pass2(a, c, xch);
+        __syncwarp();
+        if (active) fft256_store_linear(a, c, xch);
+        __syncwarp();
+        if (active) {
+            cpx<float> lo[8], hi[8], mid;
+            rfft_split(xch, c, sTs, lo, hi, mid);
+            float *row = sP + f * LDP;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                int k = c + 16 * j;
+                float pl = lo[j].x * lo[j].x + lo[j].y * lo[j].y;
+                float ph = hi[j].x * hi[j].x + hi[j].y * hi[j].y;
+                if (k == 0 && P.remove_dc) pl = 1e-10f;       // fixed floor (src/io/in.cc:390)
+                if (P.take_sqrt) { pl = sqrtf(pl); ph = sqrtf(ph); }
+                row[k] = pl;
+                row[NC - k] = ph;
+            }
+            if (c == 0) {
+                float pm = mid.x * mid.x + mid.y * mid.y;
+                row[128] = P.take_sqrt ? sqrtf(pm) : pm;
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// phase B: filter bank, lane == frame.  Result (true scale) in sY[f][b].
+//   store_log: write ln(Y) instead (dctc / logspec / trapdct consume logs)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void phase_fb(const FrameParams &P, float *sm, const SmemLayout &L, bool store_log) {
+    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+    const float *row = sm + L.oP + lane * LDP;
+    float *sY = sm + L.oY;
+    for (int b = wv; b < P.nb; b += CTA_THREADS / 32) {
+        const int lo = P.lo[b], hi = P.hi[b];
+        const float *wp = P.w + P.woff[b] - lo;
+        float acc = 0.f;
+        for (int k = lo; k <= hi; k++) acc = fmaf(row[k], wp[k], acc);
+        float y;
+        if (P.inld) {
+            y = powf(acc, 0.33f) * P.inld_scale;
+            if (store_log) y = logf(y);
+        } else {
+            y = store_log ? logf(acc) + P.log_offset : acc * P.lin_scale;
+        }
+        sY[lane * (MAXB + 1) + b] = y;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// phase C variants: sY -> output tile (re-using the spectrum tile area as staging)
+// ------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ void phase_fea(const FrameParams &P, float *sm, const SmemLayout &L) {
+    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+    const float *y = sm + L.oY + lane * (MAXB + 1);
+    float *sO = sm + L.oP;                      // [TILE_F][out_dim], spectrum tile is dead by now
+    const int od = P.out_dim;
+    if (KIND == KIND_SPEC || KIND == KIND_LOGSPEC || KIND == KIND_TRAPLOG) {
+        for (int b = wv; b < P.nb; b += CTA_THREADS / 32) sO[lane * od + b] = y[b];
+    } else if (KIND == KIND_DCTC) {
+        for (int i = wv; i < P.nrows; i += CTA_THREADS / 32) {
+            const float *m = P.m2 + i * P.nb;
+            float acc = 0.f;
+            for (int k = 0; k < P.nb; k++) acc = fmaf(y[k], m[k], acc);
+            sO[lane * od + i] = acc;
+        }
+    } else {  // LPA / LPC
+        double *sR = reinterpret_cast<double *>(sm + L.oR);      // [TILE_F][MAXR+1]
+        const int p = P.lporder;
+        // power spectrum -> autocorrelation (src/fea/fea_impl.cc:181-198); the cos table,
+        // the 1/2 end weights and the 2/N factor are folded into m2 on the host
+        for (int k = wv; k <= p; k += CTA_THREADS / 32) {
+            const float *m = P.m2 + k * P.nb;
+            double acc = 0.0;
+            for (int n = 0; n < P.nb; n++) {
+                float v = y[n];
+                if (P.lpa_square) v = v * v;
+                acc += (double)v * (double)m[n];
+            }
+            sR[lane * (MAXR + 1) + k] = acc;
+        }
+        __syncthreads();
+        if (wv == 0) {
+            // Levinson-Durbin in fp64, one lane per frame (src/fea/fea_impl.cc:200-222)
+            const double *R = sR + lane * (MAXR + 1);
+            double a[MAXR], aa[MAXR];
+            double Pe = R[0];
+            double rc = -R[1] / R[0];
+            Pe = Pe * (1 - rc * rc);
+            a[0] = aa[0] = 1.0;
+            a[1] = aa[1] = rc;
+            for (int ik = 2; ik <= p; ik++) {
+                double dm = R[ik];
+                for (int n = 1; n <= ik - 1; n++) dm += aa[n] * R[ik - n];
+                rc = -dm / Pe;
+                a[ik] = rc;
+                for (int n = 1; n <= ik - 1; n++) a[n] = aa[n] + rc * aa[ik - n];
+                for (int n = 1; n <= ik; n++) aa[n] = a[n];
+                Pe = Pe * (1 - rc * rc);
+            }
+            if (KIND == KIND_LPA) {
+                for (int i = 1; i <= p; i++) sO[lane * od + i - 1] = (float)a[i];   // a0 is not written
+            } else {
+                // LPC -> cepstrum (src/fea/fea_impl.cc:266-284), lifter, writer order
+                double cc[MAXR];
+                const int N = P.ncep;
+                cc[0] = log(Pe);
+                for (int n = 1; n <= N; n++) {
+                    double sum = 0;
+                    if (n <= p) {
+                        for (int k = 1; k <= n - 1; k++) sum += (n - k) * cc[n - k] * a[k];
+                        cc[n] = -a[n] - sum / n;
+                    } else {
+                        for (int k = 1; k <= p; k++) sum += (n - k) * cc[n - k] * a[k];
+                        cc[n] = -sum / n;
+                    }
+                }
+                for (int n = 1; n <= N; n++) sO[lane * od + n - 1] = (float)(cc[n] * (double)P.lift[n]);
+                if (P.c0_last) sO[lane * od + N] = (float)cc[0];
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// the fused frame kernel
+// ------------------------------------------------------------------------------------------
+template <int SRC, int DST, int KIND>
+__global__ void __launch_bounds__(CTA_THREADS, 2)
+k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, const int16_t *__restrict__ pcm,
+         const float *__restrict__ src, float *__restrict__ dst) {
+    extern __shared__ __align__(16) float sm[];
+    const SmemLayout L = smem_layout(P.window, P.wshift, P.nb);
+    const int2 tile = bd.tiles[blockIdx.x];
+    const int u = tile.x, t0 = tile.y;
+    const int nf = min(TILE_F, bd.nframes[u] - t0);
+    const int64_t row0 = bd.row_off[u] + t0;
+    const int tid = threadIdx.x;
+
+    if (SRC == SRC_PCM) {
+        phase_fft(P, pcm, bd.pcm_off[u] + (int64_t)t0 * P.wshift, t0 == 0, nf, tb, sm, L);
+    } else if (SRC == SRC_SPEC) {
+        const float *g = src + row0 * NBIN;
+        float *sP = sm + L.oP;
+        for (int i = tid; i < nf * NBIN; i += CTA_THREADS) sP[i] = g[i];
+        __syncthreads();
+    } else {  // SRC_FB: band values (true scale, post ^0.33) straight into sY
+        const float *g = src + row0 * P.nb;
+        float *sY = sm + L.oY;
+        for (int i = tid; i < nf * P.nb; i += CTA_THREADS) {
+            int f = i / P.nb, b = i - f * P.nb;
+            float v = g[i];
+            if (KIND == KIND_DCTC || KIND == KIND_LOGSPEC || KIND == KIND_TRAPLOG) v = logf(v);
+            sY[f * (MAXB + 1) + b] = v;
+        }
+        __syncthreads();
+    }
+
+    if (DST == DST_SPEC) {
+        float *g = dst + row0 * NBIN;
+        const float *sP = sm + L.oP;
+        for (int i = tid; i < nf * NBIN; i += CTA_THREADS) g[i] = sP[i];
+        return;
+    }
+    if (SRC != SRC_FB) {
+        const bool want_log = (DST == DST_FEA) && (KIND == KIND_DCTC || KIND == KIND_LOGSPEC || KIND == KIND_TRAPLOG);
+        phase_fb(P, sm, L, want_log);
+    }
+    if (DST == DST_FB) {
+        float *g = dst + row0 * P.nb;
+        const float *sY = sm + L.oY;
+        for (int i = tid; i < nf * P.nb; i += CTA_THREADS) {
+            int f = i / P.nb, b = i - f * P.nb;
+            g[i] = sY[f * (MAXB + 1) + b];
+        }
+        return;
+    }
+    phase_fea<KIND>(P, sm, L);
+    const float *sO = sm + L.oP;
+    const int od = P.out_dim;
+    for (int i = tid; i < nf * od; i += CTA_THREADS) {
+        int f = i / od, col = i - f * od;
+        dst[(row0 + f) * P.out_stride + col] = sO[i];
+    }
+}
+
+// one thread per utterance writes that utterance's tile descriptors
+__global__ void k_build_tiles(const int *__restrict__ nframes, const int64_t *__restrict__ tile_off, int n_utts, int tile_f,
+                              int2 *__restrict__ tiles) {
+    int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_utts) return;
+    int T = nframes[u];
+    int64_t o = tile_off[u];
+    for (int t = 0, i = 0; t < T; t += tile_f, i++) tiles[o + i] = make_int2(u, t);
+}
+
+// ------------------------------------------------------------------------------------------
+// K7 deltas: regression over +-win rows with replicated edges, chained per order, the whole
+// chain in one kernel over a tile of rows with halo (src/fea/fea_delta.cc:146-164 and the
+// edge logic :70-130, :178-206 in its regular regime, see oracle fea_delta_block).
+// Reads block 0 (static) of the output matrix, writes blocks 1..n_order in place.
+// ------------------------------------------------------------------------------------------
+struct DeltaParams {
+    int n_order;
+    int win[3];
+    float inv_den[3];
+    int blk;          // columns per block (ncep+1 incl. c0 position)
+    int stride;       // floats per row
+    int span_max;     // tile_rows + 2 * sum(win): rows of one staging buffer
+};
+constexpr int DELTA_ROWS = 64;
+
+__global__ void __launch_bounds__(256)
+k_delta(const __grid_constant__ DeltaParams D, BatchDesc bd, int tile_rows, float *__restrict__ fea) {
+    extern __shared__ __align__(16) float sm[];
+    const int2 tile = bd.tiles[blockIdx.x];
+    const int u = tile.x, t0 = tile.y;
+    const int T = bd.nframes[u];
+    const int nr = min(tile_rows, T - t0);
+    const int64_t row0 = bd.row_off[u];
+    const int blk = D.blk;
+    int halo = 0;
+    for (int k = 0; k < D.n_order; k++) halo += D.win[k];
+    const int span = nr + 2 * halo;                       // rows t0-halo .. t0+nr+halo-1 (clamped)
+    float *cur = sm;                                      // [span][blk]
+    float *nxt = sm + D.span_max * blk;
+    for (int i = threadIdx.x; i < span * blk; i += blockDim.x) {
+        int r = i / blk, col = i - r * blk;
+        int t = min(max(t0 - halo + r, 0), T - 1);
+        cur[i] = fea[(row0 + t) * D.stride + col];
+    }
+    __syncthreads();
+    int h = halo;                                         // halo still valid around `cur`
+    for (int k = 0; k < D.n_order; k++) {
+        const int W = D.win[k];
+        const int hn = h - W;                             // halo of the next block
+        const int rows_n = nr + 2 * hn;
+        for (int i = threadIdx.x; i < rows_n * blk; i += blockDim.x) {
+            int r = i / blk, col = i - r * blk;           // r: index into next (offset hn)
+            int t = t0 - hn + r;                          // absolute row of this output
+            int tc = min(max(t, 0), T - 1);               // replicated edge: value of the clamped row
+            // window rows around tc, each clamped to [0, T-1]; position in `cur` = row - (t0 - h)
+            float acc = 0.f;
+            for (int j = 1; j <= W; j++) {
+                int tp = min(tc + j, T - 1), tm = max(tc - j, 0);
+                acc += (float)j * (cur[(tp - (t0 - h)) * blk + col] - cur[(tm - (t0 - h)) * blk + col]);
+            }
+            float v = acc * D.inv_den[k];
+            if (W == 1 && tc == T - 1) v = 0.f;           // reference quirk for win == 1 (see oracle)
+            nxt[i] = v;
+            if (t >= t0 && t < t0 + nr) fea[(row0 + t) * D.stride + (k + 1) * blk + col] = v;
+        }
+        __syncthreads();
+        float *tmp = cur; cur = nxt; nxt = tmp;
+        h = hn;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K8 TRAP-DCT: per (row, band) a `traplen`-row trajectory of log band energies, mean
+// removal + Hamming + DCT-II folded into one [ndct x traplen] matrix on the host
+// (src/fea/fea_trap.cc:84-108; context replication :63-69, :111-127).
+// in: logfb [rows x nb]; out: [rows x nb*ndct] band-major.
+// ------------------------------------------------------------------------------------------
+constexpr int TRAP_ROWS = 64;
+constexpr int TRAP_MAXL = 128;
+constexpr int TRAP_MAXN = 16;
+struct TrapParams {
+    int L, ndct, nb, h;         // h = (L+1)/2
+    int out_stride;
+    float m[TRAP_MAXN * TRAP_MAXL];   // [ndct][L]: 2*hamm[j]*cos(pi (j+.5) k / L) with the mean removal folded in
+};
+
+__global__ void __launch_bounds__(256)
+k_trapdct(const __grid_constant__ TrapParams Tp, BatchDesc bd, int tile_rows, const float *__restrict__ logfb,
+          float *__restrict__ out) {
+    extern __shared__ __align__(16) float sm[];
+    const int2 tile = bd.tiles[blockIdx.x];
+    const int u = tile.x, t0 = tile.y;
+    const int T = bd.nframes[u];
+    const int nr = min(tile_rows, T - t0);
+    const int64_t row0 = bd.row_off[u];
+    const int nb = Tp.nb, L = Tp.L, h = Tp.h;
+    const bool regular = T >= h - 1;
+    // rows needed: t0-(h-1) .. t0+nr-1+(h-1), clamped (replicated context)
+    const int span = nr + L - 1;
+    if (regular) {
+        for (int i = threadIdx.x; i < span * nb; i += blockDim.x) {
+            int r = i / nb, b = i - r * nb;
+            int t = min(max(t0 - (h - 1) + r, 0), T - 1);
+            sm[i] = logfb[(row0 + t) * nb + b];
+        }
+    } else {
+        // fewer than h-1 frames: all T rows live in the tile (T < h-1 <= tile_rows)
+        for (int i = threadIdx.x; i < T * nb; i += blockDim.x) sm[i] = logfb[row0 * nb + i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nr * nb; i += blockDim.x) {
+        int r = i / nb, b = i - r * nb;
+        float acc[TRAP_MAXN];
+#pragma unroll
+        for (int k = 0; k < TRAP_MAXN; k++) acc[k] = 0.f;
+        // the rows of m sum to zero (mean removal is folded in), so any constant may be
+        // subtracted first: take the centre value to keep the fp32 products small
+        if (regular) {
+            const float *v = sm + r * nb + b;
+            const float ref = v[(h - 1) * nb];
+            for (int j = 0; j < L; j++) {
+                float x = v[j * nb] - ref;
+#pragma unroll
+                for (int k = 0; k < TRAP_MAXN; k++)
+                    if (k < Tp.ndct) acc[k] = fmaf(x, Tp.m[k * L + j], acc[k]);
+            }
+        } else {
+            // flush r of a short file sees Z never-written (zero) ring rows first
+            const int Z = h - T - (r + 1);
+            const float ref = sm[b];
+            for (int j = 0; j < L; j++) {
+                float x = -ref;
+                if (j >= Z) x = sm[min(max(j - Z - (h - 1), 0), T - 1) * nb + b] - ref;
+#pragma unroll
+                for (int k = 0; k < TRAP_MAXN; k++)
+                    if (k < Tp.ndct) acc[k] = fmaf(x, Tp.m[k * L + j], acc[k]);
+            }
+        }
+        float *o = out + (row0 + t0 + r) * Tp.out_stride + b * Tp.ndct;
+#pragma unroll
+        for (int k = 0; k < TRAP_MAXN; k++)
+            if (k < Tp.ndct) o[k] = acc[k];
+    }
+}
+
+}  // namespace ctu
+#endif

@@ -1,0 +1,852 @@
+// Cross-frame kernels of the CtuCopy hot path (sm_100a):
+//   K2/K3 k_nr_scan      extended spectral subtraction and the VAD-driven hwss / fwss / 2fwss
+//                        recursions: one thread per (utterance, bin|band), sequential over
+//                        frames, batched over all utterances (src/nr/nr.cc:86-140, 212-261,
+//                        331-369, 397-442).  HBM-bound: 4 B in + 4 B out per element.
+//   K4    k_burg         per frame, fp64: forward FFT -> (|X|^a, phase) -> unnormalised
+//                        inverse FFT -> [Hann] -> Burg lattice -> LPC cepstrum
+//                        (src/nr/nr.cc:281-292, src/vad/vad.cc:222-237, src/vdet/Burg.h:49-152)
+//   K5    k_cepdet       per utterance: adaptive-threshold cepstral detector
+//                        (src/vdet/CepstralDet.h:134-194)
+//   K6    k_vad_*        VAD module: criterion, threshold state machines, majority filter,
+//                        drop compaction (src/vad/vad.cc:96-107, 220-294, 329-625, 692-745;
+//                        src/vad/vad.h:126-175)
+//   K9    k_synth        (|X|enh, phase of X) -> inverse FFT -> overlap-add in frame order ->
+//                        floor(x/correction) -> clip -> int16 (src/io/out.cc:346-451)
+#ifndef CTU_NR_KERNELS_CUH
+#define CTU_NR_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#include "ctu_internal.h"
+#include "ctu_kernels.cuh"
+
+namespace ctu {
+
+constexpr int BURG_MAXC = 16;     // cepstral coefficients kept per frame (pitch of d_ceps)
+enum { BURG_SRC_NR = 0, BURG_SRC_VAD = 1 };
+
+struct NrParams {
+    int mode;            // CtuNrMode
+    float a, b, p;
+    double ad, pd;
+    int a_kind;          // 1: a == 1, 2: a == 2, 0: general
+    int initsegs;
+};
+
+struct SynthParams {
+    double correction;   // max over offsets of the summed overlapping Hamming windows
+    int hh;              // frames before a tile that still overlap its first sample
+};
+
+struct BurgParams {
+    int window, wshift, remove_dc;
+    double preem;
+    int fb_power;        // spectrum handed to NR is power (else magnitude)
+    int a_kind; double a;  // expansion applied before the detector (hwss/fwss); 2fwss: none
+    int expand;          // 0 for 2fwss
+    int ncoef_nr;        // fea_ncepcoefs (src/nr/nr.cc:266-270)
+    int ncoef_vad;       // vad_lpc_coefs
+    int ninit; double P, Q;   // detector options <- (nr_initsegs, nr_p, nr_q)
+    int use_spec_gain;   // VAD source: post-NR spectrum present (gain from d_spec) else own spectrum
+};
+
+struct VadParams {
+    int cri, thr, drop;
+    int energy_db;
+    int latency;         // rows between a feature row and the spectrum frame the VAD sees
+    int order;           // majority filter length
+    int cep_n;           // length of the cepstral vector (lpc: vad_lpc_coefs, fea: feature dim)
+    int cep_init; double cep_p;
+    double abs_thr;
+    int perc_init; double perc_thr;
+    int adapt_init; double adapt_q, adapt_za;
+    int dyn_init; double dyn_perc, dyn_min, qmaxinc, qmaxdec, qmindec, qmininc;
+};
+
+// ------------------------------------------------------------------------------------------
+static inline int build_nr_params(const ctu_config &c, int nr_mode, int vad_src, bool signal_out, int nb, NrParams &N, SynthParams &S,
+                                  BurgParams &B, VadParams &V, std::string &err) {
+    std::memset(&N, 0, sizeof(N)); std::memset(&S, 0, sizeof(S)); std::memset(&B, 0, sizeof(B)); std::memset(&V, 0, sizeof(V));
+    N.mode = nr_mode;
+    N.a = (float)c.nr_a; N.b = (float)c.nr_b; N.p = (float)c.nr_p; N.ad = c.nr_a; N.pd = c.nr_p;
+    N.a_kind = (c.nr_a == 1.0) ? 1 : (c.nr_a == 2.0) ? 2 : 0;
+    N.initsegs = c.nr_initsegs;
+    // OLA correction (src/io/out.cc:346-372)
+    {
+        const int s = c.wshift, w = c.window;
+        double pi = 2. * asin(1.), corr = 0.;
+        for (int i = 0; i < s; i++) {
+            int x = i; double y = 0.;
+            while (x < w) { y += 0.54 - (1 - 0.54) * cos(2 * pi * (double)x / (w - 1.)); x += s; }
+            if (y > corr) corr = y;
+        }
+        S.correction = corr;
+        S.hh = (w + s - 1) / s - 1;
+    }
+    B.window = c.window; B.wshift = c.wshift; B.remove_dc = c.remove_dc; B.preem = (double)c.preem;
+    B.fb_power = c.fb_power;
+    B.a = c.nr_a; B.a_kind = N.a_kind; B.expand = (nr_mode != NR_2FWSS);
+    B.ncoef_nr = c.fea_ncepcoefs; B.ncoef_vad = c.vad_lpc_coefs;
+    B.ninit = c.nr_initsegs; B.P = c.nr_p; B.Q = c.nr_q;
+    B.use_spec_gain = (nr_mode != NR_NONE && c.nr_when == 0);
+    if (nr_mode >= NR_HWSS && vad_src == VADSRC_BURG && (c.fea_ncepcoefs > BURG_MAXC || c.fea_ncepcoefs < 2)) {
+        err = "CTU: Burg detector supports 2..16 cepstral coefficients"; return CTU_ERR_UNSUPPORTED;
+    }
+    V.energy_db = c.vad_energy_db;
+    V.order = c.vad_filter_order;
+    V.cep_init = c.vad_cepdist_init; V.cep_p = c.vad_cepdist_p;
+    V.abs_thr = c.vad_absolute_thr;
+    V.perc_init = c.vad_perc_init; V.perc_thr = c.vad_perc_thr;
+    V.adapt_init = c.vad_adapt_init; V.adapt_q = c.vad_adapt_q; V.adapt_za = c.vad_adapt_za;
+    V.dyn_init = c.vad_dyn_init; V.dyn_perc = c.vad_dyn_perc; V.dyn_min = c.vad_dyn_min;
+    V.qmaxinc = c.vad_dyn_qmaxinc; V.qmaxdec = c.vad_dyn_qmaxdec; V.qmindec = c.vad_dyn_qmindec; V.qmininc = c.vad_dyn_qmininc;
+    // latency of the feature chain as BATCH::save_frame sees it (src/io/batch.cc:172-204)
+    V.latency = 0;
+    std::string kind(c.fea_kind);
+    if ((kind == "dctc" || kind == "lpc") && c.fea_delta) {
+        int wins[3] = {c.d_win, c.a_win, c.t_win};
+        for (int k = 0; k < c.n_order; k++) V.latency += wins[k];
+    }
+    if (kind == "trapdct") V.latency = (c.fea_trapdct_traplen + 1) / 2 - 1;
+    (void)signal_out; (void)nb;
+    return CTU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 / K3: noise-reduction scans
+// ------------------------------------------------------------------------------------------
+constexpr int SCAN_UNROLL = 8;
+
+__global__ void __launch_bounds__(256)
+k_nr_scan(const __grid_constant__ NrParams N, const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int u0, int n_utts,
+          int size, float *X, const uint8_t *__restrict__ flags) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)n_utts * size) return;
+    const int u = u0 + (int)(gid / size), bin = (int)(gid % size);
+    const int T = nframes[u];
+    float *x = X + row_off[u] * size + bin;
+    const uint8_t *fl = flags ? flags + row_off[u] : nullptr;
+    const float p = N.p, q = 1.f - N.p;
+    if (N.mode == NR_EXTEN) {
+        // state: smoothed noise Navg and smoothed speech Yavg start at 0.95 / 0.05
+        float Navg = 0.95f, Yavg = 0.05f;
+        double Nd = 0.95, Yd = 0.05;
+        for (int t0 = 0; t0 < T; t0 += SCAN_UNROLL) {
+            float v[SCAN_UNROLL];
+#pragma unroll
+            for (int j = 0; j < SCAN_UNROLL; j++) v[j] = (t0 + j < T) ? x[(int64_t)(t0 + j) * size] : 0.f;
+#pragma unroll
+            for (int j = 0; j < SCAN_UNROLL; j++) {
+                if (t0 + j >= T) break;
+                const float xi = v[j];
+                float H, omH;                       // H and 1-H, the latter without cancellation
+                if (N.a_kind == 1) {
+                    float s = Navg + Yavg;
+                    H = Navg / s; omH = Yavg / s;
+                } else if (N.a_kind == 2) {
+                    float hh = sqrtf(fmaf(Navg, Navg, Yavg * Yavg));
+                    H = Navg / hh;
+                    omH = (Yavg * Yavg) / (hh * (hh + Navg));
+                } else {
+                    double Hd = Nd / pow(pow(Nd, N.ad) + pow(Yd, N.ad), 1. / N.ad);
+                    double xd = (double)xi, Nn = Hd * xd;
+                    Nd = N.pd * Nd + (1 - N.pd) * Nn;
+                    Yd = fabs(xd - Nd);
+                    v[j] = (float)(xd - Nn);
+                    continue;
+                }
+                const float Nn = H * xi;
+                Navg = fmaf(p, Navg, q * Nn);
+                Yavg = fabsf(xi - Navg);
+                v[j] = xi * omH;                    // = X - N
+            }
+#pragma unroll
+            for (int j = 0; j < SCAN_UNROLL; j++)
+                if (t0 + j < T) x[(int64_t)(t0 + j) * size] = v[j];
+        }
+        return;
+    }
+    // hwss / fwss / 2fwss
+    float Navg = 0.f, Nravg = 0.f;               // standalone-file start
+    const float b = N.b;
+    const float inv_a = 1.f / N.a;
+    for (int t0 = 0; t0 < T; t0 += SCAN_UNROLL) {
+        float v[SCAN_UNROLL];
+        uint8_t f[SCAN_UNROLL];
+#pragma unroll
+        for (int j = 0; j < SCAN_UNROLL; j++) {
+            bool ok = t0 + j < T;
+            v[j] = ok ? x[(int64_t)(t0 + j) * size] : 0.f;
+            f[j] = ok ? fl[t0 + j] : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < SCAN_UNROLL; j++) {
+            const int t = t0 + j;
+            if (t >= T) break;
+            float xi = v[j];
+            // hwss decrements its counter before use, fwss / 2fwss after (src/nr/nr.cc:226, 367, 440)
+            const int ninit = (N.mode == NR_HWSS) ? N.initsegs - (t + 1) : N.initsegs - t;
+            const bool upd = (f[j] == 0) || ninit > 0;
+            if (N.mode == NR_2FWSS) {
+                if (upd) Navg = fmaf(p, Navg, q * xi);
+                xi = fabsf(xi - Navg);
+                if (upd) Nravg = fmaf(p, Nravg, q * xi);
+                xi = fabsf(xi - Nravg);
+            } else {
+                if (N.a_kind == 2) xi = xi * xi;
+                else if (N.a_kind == 0) xi = powf(xi, N.a);
+                if (upd) Navg = fmaf(p, Navg, q * xi);
+                xi = xi - b * Navg;
+                if (N.mode == NR_HWSS) { if (xi < 0.f) xi = 0.f; }
+                else if (xi < 0.f) xi = -xi;
+                if (N.a_kind == 2) xi = sqrtf(xi);
+                else if (N.a_kind == 0) xi = powf(xi, inv_a);
+            }
+            v[j] = xi;
+        }
+#pragma unroll
+        for (int j = 0; j < SCAN_UNROLL; j++)
+            if (t0 + j < T) x[(int64_t)(t0 + j) * size] = v[j];
+    }
+}
+
+static inline int launch_nr_scan(const NrParams &N, const int *d_nframes, const int64_t *d_row_off, int u0, int u1, int size, float *X,
+                                 const uint8_t *flags, cudaStream_t s, LaunchCtx *lc, std::string &err) {
+    int64_t n = (int64_t)(u1 - u0) * size;
+    if (n <= 0) return CTU_OK;
+    lc->begin("k_nr_scan", s);
+    k_nr_scan<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(N, d_nframes, d_row_off, u0, u1 - u0, size, X, flags);
+    lc->end(s);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e) + " (k_nr_scan)"; return CTU_ERR_CUDA; }
+    return CTU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// shared front end in double precision for one frame held by a 16-thread group
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double group_sum16d(double v) {
+    const unsigned m = 0xffffu << (threadIdx.x & 16);
+    v += __shfl_xor_sync(m, v, 8);
+    v += __shfl_xor_sync(m, v, 4);
+    v += __shfl_xor_sync(m, v, 2);
+    v += __shfl_xor_sync(m, v, 1);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: Burg cepstrum per frame (fp64 throughout so that detector decisions are reproducible)
+// 128 threads = 8 frames per pass, 4 passes per 32-frame tile.
+// ------------------------------------------------------------------------------------------
+constexpr int BURG_THREADS = 128;
+constexpr int BURG_GROUPS = BURG_THREADS / GROUP;
+
+template <int CH>
+__global__ void __launch_bounds__(BURG_THREADS)
+k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const int16_t *__restrict__ pcm, const float *__restrict__ spec,
+       double *__restrict__ ceps, const double2 *__restrict__ g_tw256, const double2 *__restrict__ g_twsplit,
+       const double2 *__restrict__ g_twinv, const double *__restrict__ g_win, const double *__restrict__ g_hann) {
+    extern __shared__ __align__(16) double smd[];
+    const int tid = threadIdx.x;
+    const int w = B.window, s = B.wshift;
+    cpx<double> *sTw = reinterpret_cast<cpx<double> *>(smd);            // 256
+    cpx<double> *sTs = sTw + 256;                                      // 129 (+1 pad)
+    cpx<double> *sTi = sTs + 130;                                      // 129 (+1 pad)
+    cpx<double> *sX = sTi + 130;                                       // BURG_GROUPS * 16*17
+    double *sT = reinterpret_cast<double *>(sX + BURG_GROUPS * XPAD * 16);   // BURG_GROUPS * 512 time samples
+    for (int i = tid; i < 256; i += BURG_THREADS) sTw[i] = mk<double>(g_tw256[i].x, g_tw256[i].y);
+    for (int i = tid; i < 129; i += BURG_THREADS) { sTs[i] = mk<double>(g_twsplit[i].x, g_twsplit[i].y); sTi[i] = mk<double>(g_twinv[i].x, g_twinv[i].y); }
+    __syncthreads();
+    const int2 tile = bd.tiles[blockIdx.x];
+    const int u = tile.x, t0 = tile.y;
+    const int nf = min(TILE_F, bd.nframes[u] - t0);
+    const int64_t row0 = bd.row_off[u] + t0;
+    const int64_t g0 = bd.pcm_off[u];
+    const int c = tid & (GROUP - 1), grp = tid / GROUP;
+    cpx<double> *xch = sX + grp * (XPAD * 16);
+    double *xt = sT + grp * NFFT;
+    const int ncoef = (src_mode == BURG_SRC_NR) ? B.ncoef_nr : B.ncoef_vad;
+#pragma unroll 1
+    for (int pass = 0; pass < TILE_F / BURG_GROUPS; pass++) {
+        const int f = pass * BURG_GROUPS + grp;
+        const bool active = f < nf;
+        cpx<double> a[16];
+        cpx<double> lo[8], hi[8], mid;
+        if (active) {
+            const int64_t fs0 = g0 + (int64_t)(t0 + f) * s;       // first sample of the frame
+            const bool at_start = (t0 + f) == 0;
+            double sum = 0;
+#pragma unroll
+            for (int n1 = 0; n1 < 16; n1++) {
+                int i0 = 32 * n1 + 2 * c;
+                double y0 = 0, y1 = 0;
+                if (i0 < w) {
+                    double xm = (i0 == 0) ? (at_start ? 0.0 : (double)pcm[fs0 - 1]) : (double)pcm[fs0 + i0 - 1];
+                    double x0 = (double)pcm[fs0 + i0];
+                    y0 = g_win[i0] * (x0 - B.preem * xm);
+                    if (i0 + 1 < w) y1 = g_win[i0 + 1] * ((double)pcm[fs0 + i0 + 1] - B.preem * x0);
+                }
+                a[n1] = mk<double>(y0, y1);
+                sum += y0 + y1;
+            }
+            if (B.remove_dc) {
+                double mean = group_sum16d(sum) / (double)w;
+#pragma unroll
+                for (int n1 = 0; n1 < 16; n1++) {
+                    int i0 = 32 * n1 + 2 * c;
+                    if (i0 < w) a[n1].x -= mean;
+                    if (i0 + 1 < w) a[n1].y -= mean;
+                }
+            }
+            fft256_pass1(a, c, sTw, xch);
+        }
+        __syncwarp();
+        if (active) fft256_pass2(a, c, xch);
+        __syncwarp();
+        if (active) fft256_store_linear(a, c, xch);
+        __syncwarp();
+        if (active) {
+            rfft_split(xch, c, sTs, lo, hi, mid);
+            // (|X|^a or the post-NR spectrum) with the phase of X: scale each bin by E/|X|
+            const float *srow = (src_mode == BURG_SRC_VAD && B.use_spec_gain) ? spec + (row0 + f) * NBIN : nullptr;
+            auto scale_bin = [&](cpx<double> X, int k) -> cpx<double> {
+                double m2 = X.x * X.x + X.y * X.y;
+                bool edge = (k == 0 || k == NC);
+                if (k == 0) { if (B.remove_dc) m2 = 1e-10; X = mk<double>(sqrt(m2), 0.0); }   // phase of bin 0 is 0 (src/io/in.cc:398)
+                double m = sqrt(m2);
+                double E;
+                if (srow) E = (double)srow[k];
+                else {
+                    double Xa = B.fb_power ? m2 : m;
+                    if (src_mode == BURG_SRC_NR && B.expand) {
+                        if (B.a_kind == 2) Xa = Xa * Xa;
+                        else if (B.a_kind == 0) Xa = pow(Xa, B.a);
+                    }
+                    E = Xa;
+                }
+                if (m == 0.0) return edge ? mk<double>(E, 0.0) : mk<double>(0.0, -E);   // c_ph(0,0) = -pi/2
+                double g = E / m;
+                if (edge) return mk<double>(X.x * g, 0.0);
+                return mk<double>(X.x * g, X.y * g);
+            };
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                int k = c + 16 * j;
+                lo[j] = scale_bin(lo[j], k);
+                hi[j] = scale_bin(hi[j], NC - k);
+            }
+            mid = scale_bin(mid, 128);
+        }
+        __syncwarp();
+        if (active) irfft_presplit(xch, c, sTi, lo, hi, mid);
+        __syncwarp();
+        if (active) { fft256_load_column(a, c, xch); }
+        __syncwarp();
+        if (active) fft256_pass1(a, c, sTw, xch);
+        __syncwarp();
+        if (active) fft256_pass2(a, c, xch);
+        if (active) {
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++) {
+                int n = c + 16 * k2;
+                xt[2 * n] = a[k2].x;
+                xt[2 * n + 1] = -a[k2].y;
+            }
+        }
+        __syncwarp();
+        if (active) {
+            // ---- Burg lattice on the first w samples; thread c owns i in [c*CH, c*CH+CH) -----
+            double ef[CH], eb[CH];
+            double en = 0;
+#pragma unroll
+            for (int j = 0; j < CH; j++) {
+                int i = c * CH + j;
+                double v = 0;
+                if (i < w) { v = xt[i]; if (src_mode == BURG_SRC_NR) v *= g_hann[i]; }
+                ef[j] = eb[j] = v;
+                en += v * v;
+            }
+            double alpha = group_sum16d(en) / (double)w;
+            double av[BURG_MAXC], aav[BURG_MAXC];
+#pragma unroll
+            for (int i = 0; i < BURG_MAXC; i++) { av[i] = 0; aav[i] = 0; }
+            av[0] = 1.0;
+            const unsigned hm = 0xffffu << (tid & 16);
+#pragma unroll 1
+            for (int ik = 1; ik < ncoef; ik++) {
+                // eb of the element just below this thread's chunk
+                double below = __shfl_up_sync(hm, eb[CH - 1], 1, 16);
+                double num = 0, den = 0;
+#pragma unroll
+                for (int j = 0; j < CH; j++) {
+                    int i = c * CH + j;
+                    double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
+                    if (i >= ik && i < w) { den += ef[j] * ef[j] + pv * pv; num += ef[j] * pv; }
+                }
+                num = group_sum16d(num) * 2.0;
+                den = group_sum16d(den);
+                const double rc = -num / den;
+                alpha *= 1 - rc * rc;
+#pragma unroll
+                for (int j = CH - 1; j >= 0; j--) {
+                    int i = c * CH + j;
+                    double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
+                    if (i >= 1 && i < w) {
+                        double e0 = ef[j];
+                        ef[j] = e0 + rc * pv;
+                        eb[j] = pv + rc * e0;
+                    }
+                }
+#pragma unroll
+                for (int i = 1; i < BURG_MAXC; i++) {
+                    if (i == ik) av[i] = rc;
+                    else if (i < ik) av[i] = aav[i] + rc * aav[(ik - i) & (BURG_MAXC - 1)];
+                }
+#pragma unroll
+                for (int i = 1; i < BURG_MAXC; i++) if (i <= ik) aav[i] = av[i];
+            }
+            if (c == 0) {
+                double cc[BURG_MAXC];
+                double *o = ceps + (row0 + f) * BURG_MAXC;
+#pragma unroll
+                for (int n = 1; n < BURG_MAXC; n++) {
+                    double sum = 0;
+#pragma unroll
+                    for (int k = 1; k < BURG_MAXC; k++) if (k < n) sum += (double)(n - k) * cc[(n - k) & (BURG_MAXC - 1)] * av[k];
+                    cc[n] = -av[n] - sum / n;
+                    if (n < ncoef) o[n] = cc[n];
+                }
+                o[0] = log(alpha);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static inline size_t burg_smem_bytes() {
+    return sizeof(double) * (2 * (256 + 130 + 130 + BURG_GROUPS * XPAD * 16) + BURG_GROUPS * NFFT);
+}
+
+static inline int launch_burg(const BurgParams &B, int src_mode, const BatchDesc &bd, int64_t ntiles, const int16_t *pcm, const float *spec,
+                              double *ceps, const double2 *tw, const double2 *ts, const double2 *ti, const double *win, const double *hann,
+                              cudaStream_t s, LaunchCtx *lc, std::string &err) {
+    if (ntiles <= 0) return CTU_OK;
+    size_t bytes = burg_smem_bytes();
+    cudaError_t e;
+    lc->begin("k_burg", s);
+    if (B.window <= 25 * 16) {
+        e = cudaFuncSetAttribute(k_burg<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess) k_burg<25><<<(unsigned)ntiles, BURG_THREADS, bytes, s>>>(B, src_mode, bd, pcm, spec, ceps, tw, ts, ti, win, hann);
+    } else {
+        e = cudaFuncSetAttribute(k_burg<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess) k_burg<32><<<(unsigned)ntiles, BURG_THREADS, bytes, s>>>(B, src_mode, bd, pcm, spec, ceps, tw, ts, ti, win, hann);
+    }
+    lc->end(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e) + " (k_burg)"; return CTU_ERR_CUDA; }
+    return CTU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: cepstral detector, one thread per utterance
+// ------------------------------------------------------------------------------------------
+__global__ void k_cepdet(const __grid_constant__ BurgParams B, const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int u0,
+                         int n_utts, const double *__restrict__ ceps, uint8_t *__restrict__ flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_utts) return;
+    const int u = u0 + i;
+    const int T = nframes[u];
+    const int nc = B.ncoef_nr;
+    const double *cp = ceps + row_off[u] * BURG_MAXC;
+    uint8_t *fl = flags + row_off[u];
+    double c0[BURG_MAXC];
+    double dMean = 0, dMean2 = 0, dVar = 0, thr = 0;
+    for (int t = 0; t < T; t++, cp += BURG_MAXC) {
+        bool res = false;
+        if (t == 0) {
+            for (int k = 0; k < nc; k++) c0[k] = cp[k];
+        } else {
+            if (t == 1) for (int k = 0; k < nc; k++) c0[k] = (c0[k] + cp[k]) / 2.0;
+            double sum = 0;
+            for (int k = 1; k < nc; k++) { double d = cp[k] - c0[k]; sum += d * d; }
+            const double dist = 4.3429 * sqrt(2 * sum);
+            if (t == 1) { dMean = dist; dMean2 = dist * dist; thr = dMean; }
+            else {
+                res = (t > B.ninit) && (dist >= thr);
+                if (!res) {
+                    for (int k = 0; k < nc; k++) c0[k] = B.P * c0[k] + (1 - B.P) * cp[k];
+                    dMean = B.Q * dMean + (1 - B.Q) * dist;
+                    dMean2 = B.Q * dMean2 + (1 - B.Q) * dist * dist;
+                    dVar = dMean2 - dMean * dMean;
+                    thr = dMean + 2.0 * sqrt(dVar);
+                }
+            }
+        }
+        fl[t] = res ? 1 : 0;
+    }
+}
+
+static inline int launch_cepdet(const BurgParams &B, const int *d_nframes, const int64_t *d_row_off, int u0, int u1, const double *ceps,
+                                uint8_t *flags, cudaStream_t s, LaunchCtx *lc, std::string &err) {
+    int n = u1 - u0;
+    if (n <= 0) return CTU_OK;
+    lc->begin("k_cepdet", s);
+    k_cepdet<<<(n + 63) / 64, 64, 0, s>>>(B, d_nframes, d_row_off, u0, n, ceps, flags);
+    lc->end(s);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e) + " (k_cepdet)"; return CTU_ERR_CUDA; }
+    return CTU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: VAD module
+// ------------------------------------------------------------------------------------------
+// energy criterion: one warp per frame over the (post-NR) spectrum
+__global__ void k_vad_energy(const __grid_constant__ VadParams V, const float *__restrict__ spec, int64_t row0, int64_t nrows,
+                             double *__restrict__ cri) {
+    const int64_t r = row0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= row0 + nrows) return;
+    const int lane = threadIdx.x & 31;
+    const float *x = spec + r * NBIN;
+    double e = 0;
+    for (int k = lane; k < NBIN; k += 32) { double v = (double)x[k]; e += v * v; }
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if (lane == 0) cri[r] = V.energy_db ? 10.0 * log10(DBL_MIN + e) : e;
+}
+
+// thresholds + background update + majority filter, one thread per utterance
+__global__ void k_vad_scan(const __grid_constant__ VadParams V, const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int u0,
+                           int n_utts, const double *__restrict__ cri_frame, const double *__restrict__ ceps,
+                           const float *__restrict__ fea, int fea_dim, uint8_t *__restrict__ vad0_tmp, uint8_t *__restrict__ vad_out,
+                           uint8_t *__restrict__ keep) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_utts) return;
+    const int u = u0 + i;
+    const int T = nframes[u];
+    const int64_t R0 = row_off[u];
+    double c0[64];
+    double s_min = 0, s_max = 0, mean = 0, mean2 = 0, var = 0, dmin = 0, dmax = 0, dyn = 0;
+    const int cn = V.cep_n;
+    for (int r = 0; r < T; r++) {
+        const int64_t fidx = R0 + min(r + V.latency, T - 1);   // spectrum frame this row is paired with
+        double c;
+        if (V.cri == VCRI_ENERGY) {
+            c = cri_frame[fidx];
+        } else {
+            // cepstral distance to the running background c0 (src/vad/vad.cc:249-276)
+            double sum = 0;
+            if (r == 0) {
+                for (int k = 0; k < cn; k++) c0[k] = (V.cri == VCRI_CEPDIST_LPC) ? ceps[fidx * BURG_MAXC + k] : (double)fea[(R0 + r) * fea_dim + k];
+                c = 0.0;
+            } else {
+                for (int k = 0; k < cn; k++) {
+                    double ci = (V.cri == VCRI_CEPDIST_LPC) ? ceps[fidx * BURG_MAXC + k] : (double)fea[(R0 + r) * fea_dim + k];
+                    if (r == 1) c0[k] = (c0[k] + ci) / 2.0;
+                    if (k >= 1) { double d = ci - c0[k]; sum += d * d; }
+                }
+                c = 4.3429 * sqrt(2 * sum);
+            }
+        }
+        bool v;
+        if (V.thr == VTHR_ABSOLUTE) {
+            v = c >= V.abs_thr;
+        } else if (V.thr == VTHR_PERC) {
+            if (r == 0 || (double)r < (double)V.perc_init) { s_min = c; s_max = c; }
+            else { s_min = (c < s_min) ? c : s_min; s_max = (c > s_max) ? c : s_max; }
+            double th = s_min + (V.perc_thr / 100.0) * (s_max - s_min);
+            v = c >= th;
+        } else if (V.thr == VTHR_ADAPT) {
+            if (r == 0) { mean = c; mean2 = c * c; var = 0.0; v = false; }
+            else {
+                double th = mean + V.adapt_za * sqrt(var);
+                if ((c < th) || (r <= V.adapt_init)) {
+                    mean = V.adapt_q * mean + (1.0 - V.adapt_q) * c;
+                    mean2 = V.adapt_q * mean2 + (1.0 - V.adapt_q) * c * c;
+                    var = mean2 - mean * mean;
+                    v = false;
+                } else v = true;
+            }
+        } else {
+            const int i0 = max(1, V.dyn_init);
+            if (r < i0) { dmax = c; dmin = c; dyn = 0.0; v = false; }
+            else if (r == i0) {
+                dmax = fmax(dmax, c) + V.dyn_min / 10.0;
+                dmin = fmin(dmin, c) - V.dyn_min / 10.0;
+                dyn = dmax - dmin; v = false;
+            } else {
+                if (dmax < c) dmax = V.qmaxinc * dmax + (1.0 - V.qmaxinc) * c; else dmax = V.qmaxdec * dmax + (1.0 - V.qmaxdec) * c;
+                if (dmin > c) dmin = V.qmindec * dmin + (1.0 - V.qmindec) * c; else dmin = V.qmininc * dmin + (1.0 - V.qmininc) * c;
+                dyn = dmax - dmin;
+                double th = dmin + (V.dyn_perc / 100.0) * dyn;
+                v = (c > th) && (dyn > V.dyn_min);
+            }
+        }
+        vad0_tmp[R0 + r] = v ? 1 : 0;
+        if (V.cri != VCRI_ENERGY && !(v && r > V.cep_init)) {
+            for (int k = 0; k < cn; k++) {
+                double ci = (V.cri == VCRI_CEPDIST_LPC) ? ceps[fidx * BURG_MAXC + k] : (double)fea[(R0 + r) * fea_dim + k];
+                c0[k] = V.cep_p * c0[k] + (1.0 - V.cep_p) * ci;
+            }
+        }
+    }
+    // majority vote over `order` decisions centred on the row; zeros beyond both ends
+    const int h = (V.order - 1) / 2;
+    for (int r = 0; r < T; r++) {
+        int sum = 0;
+        for (int q = r + h - V.order + 1; q <= r + h; q++)
+            if (q >= 0 && q < T) sum += vad0_tmp[R0 + q];
+        bool dec = ((double)sum / (double)V.order) >= 0.5;
+        if (vad_out) vad_out[R0 + r] = dec ? 1 : 0;
+        keep[R0 + r] = (dec || !V.drop) ? 1 : 0;
+    }
+}
+
+// drop mode: compact the kept rows of each utterance towards its first row (one CTA per
+// utterance, chunks of 32 rows staged through shared memory so in-place moves are safe)
+__global__ void __launch_bounds__(256)
+k_vad_compact(const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int u0, const uint8_t *__restrict__ keep, float *fea,
+              int dim, int *__restrict__ rows_out) {
+    extern __shared__ __align__(16) float smc[];
+    __shared__ int s_pos[33];
+    const int u = u0 + blockIdx.x;
+    const int T = nframes[u];
+    const int64_t R0 = row_off[u];
+    int written = 0;
+    for (int base = 0; base < T; base += 32) {
+        const int n = min(32, T - base);
+        for (int i = threadIdx.x; i < n * dim; i += blockDim.x) smc[i] = fea[(R0 + base) * dim + i];
+        if (threadIdx.x == 0) {
+            int pos = 0;
+            for (int j = 0; j < n; j++) { s_pos[j] = keep[R0 + base + j] ? pos++ : -1; }
+            s_pos[32] = pos;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n * dim; i += blockDim.x) {
+            int j = i / dim, col = i - j * dim;
+            int pos = s_pos[j];
+            if (pos >= 0) fea[(R0 + written + pos) * dim + col] = smc[i];
+        }
+        written += s_pos[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) rows_out[u] = written;
+}
+
+// ------------------------------------------------------------------------------------------
+// K9: synthesis.  One CTA = one tile of 32 output hops of one utterance (plus the frames
+// before the tile that still overlap it).  Every frame's time signal goes to its own
+// shared-memory slot; the overlap-add then sums the slots in frame order, exactly the order
+// in which the reference accumulates (src/io/out.cc:427-429), so the result is deterministic.
+// ------------------------------------------------------------------------------------------
+constexpr int SYN_THREADS = 256;
+constexpr int SYN_GROUPS = SYN_THREADS / GROUP;
+
+__global__ void __launch_bounds__(SYN_THREADS)
+k_synth(const __grid_constant__ SynthParams S, int window, int wshift, float preem, int remove_dc, BatchDesc bd,
+        const int64_t *__restrict__ osamp_off, const int16_t *__restrict__ pcm, const float *__restrict__ spec, int16_t *__restrict__ out,
+        const float2 *__restrict__ g_tw256, const float2 *__restrict__ g_twsplit, const float2 *__restrict__ g_twinv,
+        const float *__restrict__ g_win) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x;
+    const int w = window, s = wshift, hh = S.hh;
+    const int2 tile = bd.tiles[blockIdx.x];
+    const int u = tile.x, t0 = tile.y;
+    const int T = bd.nframes[u];
+    const int nf = min(TILE_F, T - t0);
+    const int tfirst = max(t0 - hh, 0);
+    const int nfr = t0 + nf - tfirst;                     // frames to synthesise (<= 32 + hh)
+    const int nsamp = (nfr - 1) * s + w;
+    // carve-up
+    cpx<float> *sTw = reinterpret_cast<cpx<float> *>(sm);                 // 256
+    cpx<float> *sTs = sTw + 256;                                         // 130
+    cpx<float> *sTi = sTs + 130;                                         // 130
+    cpx<float> *sX = sTi + 130;                                          // SYN_GROUPS * 16*17
+    float *sW = reinterpret_cast<float *>(sX + SYN_GROUPS * XPAD * 16);  // w (padded to 512)
+    float *sD = sW + NFFT;                                               // (32+hh-1)*s + w  (padded)
+    float *sYt = sD + (((TILE_F + hh - 1) * s + w + 3) & ~3);            // (32+hh) * w
+    for (int i = tid; i < 256; i += SYN_THREADS) sTw[i] = mk<float>(g_tw256[i].x, g_tw256[i].y);
+    for (int i = tid; i < 129; i += SYN_THREADS) { sTs[i] = mk<float>(g_twsplit[i].x, g_twsplit[i].y); sTi[i] = mk<float>(g_twinv[i].x, g_twinv[i].y); }
+    for (int i = tid; i < w; i += SYN_THREADS) sW[i] = g_win[i];
+    const int64_t g0 = bd.pcm_off[u] + (int64_t)tfirst * s;
+    for (int i = tid; i < nsamp; i += SYN_THREADS) {
+        float xi = (float)pcm[g0 + i];
+        float xp = (i == 0 && tfirst == 0) ? 0.f : (float)pcm[g0 + i - 1];
+        sD[i] = fmaf(-preem, xp, xi);
+    }
+    __syncthreads();
+    const int c = tid & (GROUP - 1), grp = tid / GROUP;
+    cpx<float> *xch = sX + grp * (XPAD * 16);
+    const float inv_w = 1.0f / (float)w;
+    const int npass = (nfr + SYN_GROUPS - 1) / SYN_GROUPS;
+#pragma unroll 1
+    for (int pass = 0; pass < npass; pass++) {
+        const int f = pass * SYN_GROUPS + grp;
+        const bool active = f < nfr;
+        cpx<float> a[16], lo[8], hi[8], mid;
+        if (active) {
+            const float *d = sD + f * s;
+            float sum = 0.f;
+#pragma unroll
+            for (int n1 = 0; n1 < 16; n1++) {
+                int i0 = 32 * n1 + 2 * c;
+                float y0 = (i0 < w) ? sW[i0] * d[i0] : 0.f;
+                float y1 = (i0 + 1 < w) ? sW[i0 + 1] * d[i0 + 1] : 0.f;
+                a[n1] = mk<float>(y0, y1);
+                sum += y0 + y1;
+            }
+            if (remove_dc) {
+                float mean = group_sum16(sum) * inv_w;
+#pragma unroll
+                for (int n1 = 0; n1 < 16; n1++) {
+                    int i0 = 32 * n1 + 2 * c;
+                    if (i0 < w) a[n1].x -= mean;
+                    if (i0 + 1 < w) a[n1].y -= mean;
+                }
+            }
+            fft256_pass1(a, c, sTw, xch);
+        }
+        __syncwarp();
+        if (active) fft256_pass2(a, c, xch);
+        __syncwarp();
+        if (active) fft256_store_linear(a, c, xch);
+        __syncwarp();
+        if (active) {
+            rfft_split(xch, c, sTs, lo, hi, mid);
+            // enhanced magnitude with the ORIGINAL phase: scale X by |X|enh / (|X| nfft);
+            // bin 0 has phase 0, the Nyquist bin is always written non-negative
+            // (src/io/out.cc:417-424)
+            const float *srow = spec + (bd.row_off[u] + tfirst + f) * NBIN;
+            const float invn = 1.0f / (float)NFFT;
+            auto scale_bin = [&](cpx<float> X, int k) -> cpx<float> {
+                float A = srow[k] * invn;
+                if (k == 0 || k == NC) return mk<float>(A, 0.f);
+                float m = sqrtf(X.x * X.x + X.y * X.y);
+                if (m == 0.f) return mk<float>(0.f, -A);
+                float g = A / m;
+                return mk<float>(X.x * g, X.y * g);
+            };
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                int k = c + 16 * j;
+                lo[j] = scale_bin(lo[j], k);
+                hi[j] = scale_bin(hi[j], NC - k);
+            }
+            mid = scale_bin(mid, 128);
+        }
+        __syncwarp();
+        if (active) irfft_presplit(xch, c, sTi, lo, hi, mid);
+        __syncwarp();
+        if (active) fft256_load_column(a, c, xch);
+        __syncwarp();
+        if (active) fft256_pass1(a, c, sTw, xch);
+        __syncwarp();
+        if (active) {
+            fft256_pass2(a, c, xch);
+            float *yt = sYt + f * w;
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++) {
+                int n = c + 16 * k2;
+                if (2 * n < w) yt[2 * n] = a[k2].x;
+                if (2 * n + 1 < w) yt[2 * n + 1] = -a[k2].y;
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // overlap-add in frame order, quantise
+    const bool last = (t0 + nf == T);
+    const int nout = nf * s + (last ? (w - s) : 0);
+    int16_t *o = out + osamp_off[u] + (int64_t)t0 * s;
+    const int base = (t0 - tfirst) * s;                     // position of the tile's first sample inside the synthesised span
+    for (int i = tid; i < nout; i += SYN_THREADS) {
+        const int pos = base + i;                           // sample index relative to frame `tfirst`
+        int fa = (pos - w) / s + 1;                         // first frame with fa*s + w > pos
+        if (pos < w) fa = 0;
+        int fb = min(pos / s, nfr - 1);
+        double acc = 0.0;
+        for (int f = fa; f <= fb; f++) acc += (double)sYt[f * w + (pos - f * s)];
+        double q = floor(acc / S.correction);
+        int v = (int)q;
+        if (fabsf((float)v) > 32767.f) v = (v < 0) ? -32767 : 32767;
+        o[i] = (int16_t)v;
+    }
+}
+
+static inline size_t synth_smem_bytes(int w, int s, int hh) {
+    size_t fl = 2 * (256 + 130 + 130 + SYN_GROUPS * XPAD * 16) + NFFT + (((TILE_F + hh - 1) * s + w + 3) & ~3) + (size_t)(TILE_F + hh) * w;
+    return fl * sizeof(float);
+}
+
+static inline int launch_synth(const SynthParams &S, const FrameParams &F, const BatchDesc &bd, const int2 *, int64_t ntiles,
+                               const int64_t *d_osamp_off, const int16_t *pcm, const float *spec, int16_t *out, const float2 *tw,
+                               const float2 *ts, const float2 *ti, const float *win, cudaStream_t s, LaunchCtx *lc, std::string &err) {
+    if (ntiles <= 0) return CTU_OK;
+    size_t bytes = synth_smem_bytes(F.window, F.wshift, S.hh);
+    if (bytes > 227 * 1024) { err = "CTU: window/shift combination needs too much shared memory for synthesis"; return CTU_ERR_UNSUPPORTED; }
+    cudaError_t e = cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) {
+        lc->begin("k_synth", s);
+        k_synth<<<(unsigned)ntiles, SYN_THREADS, bytes, s>>>(S, F.window, F.wshift, F.preem, F.remove_dc, bd, d_osamp_off, pcm, spec, out, tw, ts,
+                                                              ti, win);
+        lc->end(s);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e) + " (k_synth)"; return CTU_ERR_CUDA; }
+    return CTU_OK;
+}
+
+static inline int launch_vad_module(VadParams V, const BurgParams &B, const BatchDesc &bd32, int64_t nt32, const int *d_nframes,
+                                    const int64_t *d_row_off, int u0, int u1, int64_t row0, int64_t nrows, const int16_t *d_pcm,
+                                    const float *d_spec, float *d_fea, int fea_dim, double *d_ceps, double *d_cri, uint8_t *d_vad0,
+                                    uint8_t *d_vadout, uint8_t *d_keep, int *d_rows, const double2 *tw, const double2 *ts,
+                                    const double2 *ti, const double *win, cudaStream_t s, LaunchCtx *lc, std::string &err) {
+    const int n = u1 - u0;
+    if (n <= 0) return CTU_OK;
+    cudaError_t e = cudaSuccess;
+    if (V.cri == VCRI_ENERGY) {
+        if (nrows > 0) {
+            lc->begin("k_vad_energy", s);
+            k_vad_energy<<<(unsigned)((nrows + 7) / 8), 256, 0, s>>>(V, d_spec, row0, nrows, d_cri);
+            lc->end(s);
+            e = cudaGetLastError();
+        }
+        V.cep_n = 0;
+    } else if (V.cri == VCRI_CEPDIST_LPC) {
+        V.cep_n = B.ncoef_vad;
+        if (V.cep_n > BURG_MAXC || V.cep_n < 2) { err = "CTU: -vad_lpc_coefs must be 2..16"; return CTU_ERR_UNSUPPORTED; }
+        int st = launch_burg(B, BURG_SRC_VAD, bd32, nt32, d_pcm, d_spec, d_ceps, tw, ts, ti, win, nullptr, s, lc, err);
+        if (st) return st;
+    } else {
+        V.cep_n = fea_dim;
+    }
+    if (V.cep_n > 64) { err = "CTU: cepstral-distance VAD supports vectors of up to 64 values"; return CTU_ERR_UNSUPPORTED; }
+    if (e == cudaSuccess) {
+        lc->begin("k_vad_scan", s);
+        k_vad_scan<<<(n + 63) / 64, 64, 0, s>>>(V, d_nframes, d_row_off, u0, n, d_cri, d_ceps, d_fea, fea_dim, d_vad0, d_vadout, d_keep);
+        lc->end(s);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && V.drop) {
+        size_t bytes = (size_t)32 * fea_dim * sizeof(float);
+        e = cudaFuncSetAttribute(k_vad_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bytes, 1024));
+        if (e == cudaSuccess) {
+            lc->begin("k_vad_compact", s);
+            k_vad_compact<<<n, 256, bytes, s>>>(d_nframes, d_row_off, u0, d_keep, d_fea, fea_dim, d_rows);
+            lc->end(s);
+            e = cudaGetLastError();
+        }
+    }
+    if (e != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e) + " (vad module)"; return CTU_ERR_CUDA; }
+    return CTU_OK;
+}
+
+}  // namespace ctu
+#endif

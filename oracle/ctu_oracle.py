@@ -415,18 +415,24 @@ class FilterBank:
 
 
 def _warp(scale: str, hz):
-    """FB::init_scale / get_filter scale formulas, src/fea/fb.cc:100-132, 311-338."""
-    hz = np.asarray(hz, dtype=np.float64)
-    if scale == "lin":
-        return hz.copy()
-    if scale == "bark":
-        return 6.0 * np.log(hz / 600.0 + np.sqrt((hz / 600.0) * (hz / 600.0) + 1.0))
-    if scale == "expolog":
-        return np.where(hz <= 2000, 700.0 * (np.power(10.0, hz / 3988.0) - 1.0),
-                        2595.0 * np.log10(1.0 + hz / 700.0))
-    if scale == "mel":
-        return 2595 * np.log10(1.0 + hz / 700.0)
-    raise ValueError("FB: Unknown frequency scale!")
+    """FB::init_scale / get_filter scale formulas, src/fea/fb.cc:100-132, 311-338.
+    Uses the C library's log/log10/pow through `math` (numpy's vectorised versions can
+    differ from glibc in the last bit, which the triangle-edge differences amplify)."""
+    scalar = np.ndim(hz) == 0
+    hzv = np.atleast_1d(np.asarray(hz, dtype=np.float64))
+    out = np.empty_like(hzv)
+    for i, f in enumerate(hzv.tolist()):
+        if scale == "lin":
+            out[i] = f
+        elif scale == "bark":
+            out[i] = 6.0 * math.log(f / 600.0 + math.sqrt((f / 600.0) * (f / 600.0) + 1.0))
+        elif scale == "expolog":
+            out[i] = 700.0 * (math.pow(10.0, f / 3988.0) - 1.0) if f <= 2000 else 2595.0 * math.log10(1.0 + f / 700.0)
+        elif scale == "mel":
+            out[i] = 2595 * math.log10(1.0 + f / 700.0)
+        else:
+            raise ValueError("FB: Unknown frequency scale!")
+    return float(out[0]) if scalar else out
 
 
 def _eqloud(om: float, fs: int) -> float:

@@ -1,0 +1,64 @@
+// CPU emulation of the 16-thread FFT group from ctucopy_b200/csrc/ctu_fft.cuh: the same
+// __host__ __device__ code, run "thread by thread" with plain arrays standing in for shared
+// memory.  Checks the index algebra of the four-step 256-point FFT, the real split and
+// the inverse against a naive O(n^2) DFT.  Test infrastructure only.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../../ctucopy_b200/csrc/ctu_fft.cuh"
+using namespace ctu;
+
+template <class T> int run(double tol) {
+    const double PI = 3.14159265358979323846;
+    std::vector<cpx<T>> tw256(256), twsplit(129), twinv(129);
+    for (int k1 = 0; k1 < 16; k1++) for (int c = 0; c < 16; c++) {
+        double a = -2 * PI * (c * k1) / 256.0; tw256[k1 * 16 + c] = mk<T>((T)cos(a), (T)sin(a)); }
+    for (int k = 0; k <= 128; k++) {
+        double th = 2 * PI * k / 512.0;
+        twsplit[k] = mk<T>((T)(-sin(th) / 2), (T)(-cos(th) / 2));
+        twinv[k] = mk<T>((T)cos(th), (T)sin(th));
+    }
+    std::vector<double> x(512, 0.0);
+    srand(3);
+    for (int i = 0; i < 400; i++) x[i] = (rand() / (double)RAND_MAX - 0.5) * 2000;
+    // thread-private registers
+    static cpx<T> reg[16][16]; static cpx<T> lo[16][8], hi[16][8], mid[16];
+    std::vector<cpx<T>> xch(16 * XPAD), zlin(256);
+    for (int c = 0; c < 16; c++) for (int n1 = 0; n1 < 16; n1++) { int n = 16 * n1 + c; reg[c][n1] = mk<T>((T)x[2 * n], (T)x[2 * n + 1]); }
+    for (int c = 0; c < 16; c++) fft256_pass1(reg[c], c, tw256.data(), xch.data());
+    for (int c = 0; c < 16; c++) fft256_pass2(reg[c], c, xch.data());
+    for (int c = 0; c < 16; c++) fft256_store_linear(reg[c], c, zlin.data());
+    for (int c = 0; c < 16; c++) rfft_split(zlin.data(), c, twsplit.data(), lo[c], hi[c], mid[c]);
+    std::vector<double> re(257), im(257);
+    for (int k = 0; k <= 256; k++) { re[k] = im[k] = 0; for (int n = 0; n < 512; n++) { double a = -2 * PI * ((n * k) % 512) / 512.0; re[k] += x[n] * cos(a); im[k] += x[n] * sin(a); } }
+    double emax = 0, ref = 0;
+    for (int k = 0; k <= 256; k++) ref = fmax(ref, hypot(re[k], im[k]));
+    for (int c = 0; c < 16; c++) for (int j = 0; j < 8; j++) {
+        int k = c + 16 * j;
+        emax = fmax(emax, hypot(lo[c][j].x - re[k], lo[c][j].y - im[k]));
+        emax = fmax(emax, hypot(hi[c][j].x - re[256 - k], hi[c][j].y - im[256 - k]));
+    }
+    emax = fmax(emax, hypot(mid[0].x - re[128], mid[0].y - im[128]));
+    printf("forward: max err %.3g (rel %.3g)\n", emax, emax / ref);
+    int bad = (emax / ref > tol);
+    // inverse
+    for (int c = 0; c < 16; c++) irfft_presplit(zlin.data(), c, twinv.data(), lo[c], hi[c], mid[c]);
+    for (int c = 0; c < 16; c++) fft256_load_column(reg[c], c, zlin.data());
+    for (int c = 0; c < 16; c++) fft256_pass1(reg[c], c, tw256.data(), xch.data());
+    for (int c = 0; c < 16; c++) fft256_pass2(reg[c], c, xch.data());
+    double e2 = 0;
+    for (int c = 0; c < 16; c++) for (int k2 = 0; k2 < 16; k2++) {
+        int n = c + 16 * k2;
+        e2 = fmax(e2, fabs(reg[c][k2].x / 512.0 - x[2 * n]));
+        e2 = fmax(e2, fabs(-reg[c][k2].y / 512.0 - x[2 * n + 1]));
+    }
+    printf("inverse: max err %.3g (rel %.3g)\n", e2, e2 / 1000.0);
+    bad |= (e2 / 1000.0 > tol);
+    return bad;
+}
+int main() {
+    int bad = run<float>(2e-6) | run<double>(1e-14);
+    printf(bad ? "FAIL\n" : "OK\n");
+    return bad;
+}
