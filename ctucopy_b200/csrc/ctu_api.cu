@@ -16,6 +16,7 @@
 #include "ctu_internal.h"
 #include "ctu_kernels.cuh"
 #include "ctu_nr_kernels.cuh"
+#include "ctu_precise.cuh"
 
 using namespace ctu;
 
@@ -42,6 +43,10 @@ struct ctu_handle {
     float *d_win = nullptr;
     double2 *d_tw256d = nullptr, *d_twsplitd = nullptr, *d_twinvd = nullptr;
     double *d_wind = nullptr, *d_hann = nullptr;
+    // fp64 tables of the precise path (ctu_precise.cuh)
+    bool precise = false;
+    std::vector<double> w64, m264, lift64;
+    double *d_w64 = nullptr, *d_m264 = nullptr, *d_lift64 = nullptr;
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
 };
 
@@ -61,6 +66,7 @@ struct ctu_plan {
     int2 *d_tiles32 = nullptr, *d_tiles64 = nullptr;
     // workspaces (whole batch)
     float *d_spec = nullptr, *d_fb = nullptr, *d_log = nullptr;
+    double *d_fb64 = nullptr;            // band values of the precise path
     double *d_ceps = nullptr;            // Burg cepstra [frames x ncoef]
     double *d_cri = nullptr;             // VAD criterion per frame
     uint8_t *d_flags = nullptr;          // NR-internal detector decisions
@@ -225,12 +231,20 @@ static int build_frame_params(ctu_handle *h) {
     for (int b = 0; b < fb.nb; b++) {
         int n = fb.hi[b] - fb.lo[b] + 1;
         if (off + n > MAXW) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: filter bank has too many taps");
+        off = (off + 3) & ~3;
+        if (off + n > MAXW) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: filter bank has too many taps");
         P.lo[b] = (short)fb.lo[b]; P.hi[b] = (short)fb.hi[b]; P.woff[b] = off;
-        for (int k = 0; k < n; k++) P.w[off + k] = (float)(fb.mat[(size_t)b * fb.bins + fb.lo[b] + k] * S);
+        h->w64.resize(off + n, 0.0);            // same (4-aligned) offsets as the fp32 copy
+        for (int k = 0; k < n; k++) {
+            P.w[off + k] = (float)(fb.mat[(size_t)b * fb.bins + fb.lo[b] + k] * S);
+            h->w64[off + k] = fb.mat[(size_t)b * fb.bins + fb.lo[b] + k];
+        }
         off += n;
     }
     // second stage
     const int nb = fb.nb;
+    const int nbp = (nb + 3) & ~3;
+    P.nbp = nbp;
     const int N = c.fea_ncepcoefs;
     std::vector<double> lift(N + 1, 1.0);
     if (c.fea_lifter > 1)
@@ -243,14 +257,15 @@ static int build_frame_params(ctu_handle *h) {
             // c[i] = sqrt(2/N) sum_k ln Y_k cos(pi i (k-1/2)/N), lifter on i >= 1, pi = 3.1415926535898
             // (src/fea/fea_impl.cc:81-131); rows stored in WRITER order c1..cN, c0 (src/io/out.cc:189-201)
             int rows = N + (c.fea_c0 ? 1 : 0);
-            if (rows > MAXR || rows * nb > MAXM2) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: cepstral matrix too large");
+            if (rows > MAXR || rows * nbp > MAXM2) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: cepstral matrix too large");
             double norm = sqrt(2.0 / nb);
             auto wd = [&](int id) { return cos(3.1415926535898 * (double)id / (2 * nb)); };
             for (int r = 0; r < rows; r++) {
                 int i = (r < N) ? r + 1 : 0;
                 for (int k = 1; k <= nb; k++) {
                     int id = ((2 * k - 1) * i) % (4 * nb);
-                    P.m2[r * nb + k - 1] = (float)(wd(id) * norm * (i >= 1 ? lift[i] : 1.0));
+                    P.m2[r * nbp + k - 1] = (float)(wd(id) * norm * (i >= 1 ? lift[i] : 1.0));
+                    h->m264.push_back(wd(id) * norm * (i >= 1 ? lift[i] : 1.0));
                 }
             }
             P.nrows = rows;
@@ -259,7 +274,7 @@ static int build_frame_params(ctu_handle *h) {
         }
         case FEA_LPA: case FEA_LPC: {
             const int p = c.fea_lporder;
-            if (p + 1 > MAXR || (p + 1) * nb > MAXM2 || N + 1 > MAXR) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: LP order too large");
+            if (p + 1 > MAXR || (p + 1) * nbp > MAXM2 || N + 1 > MAXR) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: LP order too large");
             if (nb < 2) return fail(h, CTU_ERR_CONFIG, "CTU: LPC needs at least two bands");
             const int Nf = (nb - 1) * 2;
             for (int k = 0; k <= p; k++)
@@ -268,13 +283,16 @@ static int build_frame_params(ctu_handle *h) {
                     if (n == 0) v = 0.5;
                     else if (n == nb - 1) v = (1 - 2 * (k % 2)) * 0.5;
                     else v = cos(2 * 3.141592653589793 * ((n * k) % Nf) / Nf);
-                    P.m2[k * nb + n] = (float)(v / ((double)Nf / 2));
+                    P.m2[k * nbp + n] = (float)(v / ((double)Nf / 2));
+                    h->m264.push_back(v / ((double)Nf / 2));
                 }
             P.nrows = p + 1;
             P.lporder = p; P.ncep = N;
             P.lpa_square = !fb.inld;
             P.c0_last = c.fea_c0;
             for (int n = 0; n <= N; n++) P.lift[n] = (float)lift[n];
+            h->lift64 = lift;
+            if (!fb.inld) h->precise = true;      // LPC from squared band powers: ill-conditioned
             if (h->fea_kind == FEA_LPA) {
                 // htkOUT writes a[1..ncep] with the cepstral loop bounds (src/io/out.cc:189-201):
                 // only lporder == ncepcoefs is memory-safe in the reference
@@ -424,6 +442,10 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     }
     if (cudaSetDevice(device) != cudaSuccess) { h->err = "CUDA: cudaSetDevice failed"; return bail(CTU_ERR_CUDA); }
     if ((st = build_fft_tables(h))) return bail(st);
+    if (h->nr_mode != NR_NONE && h->cfg.nr_when == 1 && !h->signal_out) h->precise = true;   // subtraction on band values
+    if (h->precise) {
+        if ((st = upload(h, &h->d_w64, h->w64)) || (st = upload(h, &h->d_m264, h->m264)) || (st = upload(h, &h->d_lift64, h->lift64))) return bail(st);
+    }
     for (int i = 0; i < 3; i++)
         if (cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking) != cudaSuccess) { h->err = "CUDA: stream creation failed"; return bail(CTU_ERR_CUDA); }
     *out = h;
@@ -434,6 +456,7 @@ void ctu_destroy(ctu_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->d_tw256); cudaFree(h->d_twsplit); cudaFree(h->d_twinv); cudaFree(h->d_win);
+    cudaFree(h->d_w64); cudaFree(h->d_m264); cudaFree(h->d_lift64);
     cudaFree(h->d_tw256d); cudaFree(h->d_twsplitd); cudaFree(h->d_twinvd); cudaFree(h->d_wind); cudaFree(h->d_hann);
     for (int i = 0; i < 3; i++) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     h->lc.clear();
@@ -506,7 +529,8 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     const bool need_spec = h->signal_out || (nr_on && h->cfg.nr_when == 0) || (h->do_vad && h->vad_cri != VCRI_CEPDIST_FEA);
     const bool need_fb = !h->signal_out && nr_on && h->cfg.nr_when == 1;
     if (need_spec && (st = dev_alloc(h, p, &p->d_spec, (size_t)rows * NBIN))) { ctu_plan_destroy(p); return st; }
-    if (need_fb && (st = dev_alloc(h, p, &p->d_fb, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
+    if (need_fb && !h->precise && (st = dev_alloc(h, p, &p->d_fb, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
+    if (need_fb && h->precise && (st = dev_alloc(h, p, &p->d_fb64, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     if (h->fea_kind == FEA_TRAPDCT && (st = dev_alloc(h, p, &p->d_log, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     const bool burg_nr = h->nr_mode >= NR_HWSS && h->vad_src == VADSRC_BURG;
     const bool burg_vad = h->do_vad && h->vad_cri == VCRI_CEPDIST_LPC;
@@ -525,7 +549,7 @@ void ctu_plan_destroy(ctu_plan *p) {
     cudaSetDevice(p->h->device);
     cudaFree(p->d_pcm_off); cudaFree(p->d_row_off); cudaFree(p->d_osamp_off); cudaFree(p->d_t32_off); cudaFree(p->d_t64_off);
     cudaFree(p->d_nframes); cudaFree(p->d_tiles32); cudaFree(p->d_tiles64);
-    cudaFree(p->d_spec); cudaFree(p->d_fb); cudaFree(p->d_log); cudaFree(p->d_ceps); cudaFree(p->d_cri);
+    cudaFree(p->d_spec); cudaFree(p->d_fb); cudaFree(p->d_fb64); cudaFree(p->d_log); cudaFree(p->d_ceps); cudaFree(p->d_cri);
     cudaFree(p->d_flags); cudaFree(p->d_keep); cudaFree(p->d_vad0); cudaFree(p->d_rows);
     cudaFree(p->d_pcm); cudaFree(p->d_wave); cudaFree(p->d_fea); cudaFree(p->d_ext); cudaFree(p->d_vadnr_out); cudaFree(p->d_vad_out);
     delete p;
@@ -563,18 +587,13 @@ static Range make_range(const ctu_plan *p, int u0, int u1) {
     return r;
 }
 
-template <int SRC, int DST, int KIND>
-static int launch_frames_t(ctu_handle *h, const FrameParams &P, const BatchDesc &bd, int64_t ntiles, const int16_t *pcm,
+template <int SRC, int DST, int KIND, int WT>
+static int launch_frames_w(ctu_handle *h, const FrameParams &P, const BatchDesc &bd, int64_t ntiles, const int16_t *pcm,
                            const float *src, float *dst, cudaStream_t s) {
-    if (ntiles <= 0) return CTU_OK;
     SmemLayout L = smem_layout(P.window, P.wshift, P.nb);
     size_t bytes = (size_t)L.total * sizeof(float);
-    static thread_local bool attr_done = false;
-    auto kern = k_frames<SRC, DST, KIND>;
-    if (!attr_done || true) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        attr_done = true;
-    }
+    auto kern = k_frames<SRC, DST, KIND, WT>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     FftTables tb{h->d_tw256, h->d_twsplit, h->d_twinv, h->d_win};
     static const char *const names[3][3] = {{"k_frames<pcm,spec>", "k_frames<pcm,fb>", "k_frames<pcm,fea>"},
                                             {"k_frames<spec,spec>", "k_frames<spec,fb>", "k_frames<spec,fea>"},
@@ -584,6 +603,17 @@ static int launch_frames_t(ctu_handle *h, const FrameParams &P, const BatchDesc 
     h->lc.end(s);
     CK(cudaGetLastError());
     return CTU_OK;
+}
+
+template <int SRC, int DST, int KIND>
+static int launch_frames_t(ctu_handle *h, const FrameParams &P, const BatchDesc &bd, int64_t ntiles, const int16_t *pcm,
+                           const float *src, float *dst, cudaStream_t s) {
+    if (ntiles <= 0) return CTU_OK;
+    // the PCM front end is specialised for the two standard window lengths (25 ms and 32 ms
+    // at 16 kHz); every other length takes the generic instantiation
+    if (SRC == SRC_PCM && P.window == 400) return launch_frames_w<SRC, DST, KIND, 400>(h, P, bd, ntiles, pcm, src, dst, s);
+    if (SRC == SRC_PCM && P.window == 512) return launch_frames_w<SRC, DST, KIND, 512>(h, P, bd, ntiles, pcm, src, dst, s);
+    return launch_frames_w<SRC, DST, KIND, 0>(h, P, bd, ntiles, pcm, src, dst, s);
 }
 
 template <int SRC, int DST>
@@ -655,15 +685,19 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     int od = h->static_dim, ostride = h->feature_dim;
     if (kind == KIND_TRAPLOG) { fea_dst = p->d_log; od = h->fb.nb; ostride = h->fb.nb; }
     P = h->fp; P.out_dim = od; P.out_stride = ostride;
-    if (nr_on && !before) {
-        FrameParams Pf = h->fp; Pf.out_dim = h->fb.nb; Pf.out_stride = h->fb.nb;
-        if (need_spec) { if ((st = launch_frames_t<SRC_SPEC, DST_FB, KIND_SPEC>(h, Pf, bd32, r.t32_n, nullptr, p->d_spec, p->d_fb, s))) return st; }
-        else if ((st = launch_frames_t<SRC_PCM, DST_FB, KIND_SPEC>(h, Pf, bd32, r.t32_n, d_pcm, nullptr, p->d_fb, s))) return st;
-        const uint8_t *fl = (h->nr_mode >= NR_HWSS) ? d_ext : nullptr;
-        if (h->nr_mode >= NR_HWSS && !fl) return fail(h, CTU_ERR_INPUT, "NR: Unable to open VAD file!\n");
-        if ((st = launch_nr_scan(h->nrp, p->d_nframes, p->d_row_off, r.u0, r.u1, h->fb.nb, p->d_fb, fl, s, &h->lc, h->err))) return st;
-        if (d_vadnr && fl) CK(cudaMemcpyAsync(d_vadnr + r.row0, d_ext + r.row0, r.nrows, cudaMemcpyDeviceToDevice, s));
-        if ((st = launch_frames_k<SRC_FB, DST_FEA>(h, kind, P, bd32, r.t32_n, nullptr, p->d_fb, fea_dst, s))) return st;
+    if (h->precise) {
+        // fp64 path (ctu_precise.cuh): band-domain noise reduction / ill-conditioned LPC
+        Tables64 t64{h->d_tw256d, h->d_twsplitd, h->d_wind, h->d_w64, h->d_m264, h->d_lift64};
+        if (nr_on) {
+            const uint8_t *fl = (h->nr_mode >= NR_HWSS) ? d_ext : nullptr;
+            if (h->nr_mode >= NR_HWSS && !fl) return fail(h, CTU_ERR_INPUT, "NR: Unable to open VAD file!\n");
+            if ((st = launch_frames64_t<SRC64_PCM, DST64_FB, KIND_SPEC>(P, bd32, t64, r.t32_n, d_pcm, nullptr, p->d_fb64, nullptr, s, &h->lc, h->err))) return st;
+            if ((st = launch_nr_scan64(h->nrp, p->d_nframes, p->d_row_off, r.u0, r.u1, h->fb.nb, p->d_fb64, fl, s, &h->lc, h->err))) return st;
+            if (d_vadnr && fl) CK(cudaMemcpyAsync(d_vadnr + r.row0, d_ext + r.row0, r.nrows, cudaMemcpyDeviceToDevice, s));
+            if ((st = launch_frames64_k<SRC64_FB, DST64_FEA>(kind, P, bd32, t64, r.t32_n, nullptr, p->d_fb64, nullptr, fea_dst, s, &h->lc, h->err))) return st;
+        } else {
+            if ((st = launch_frames64_k<SRC64_PCM, DST64_FEA>(kind, P, bd32, t64, r.t32_n, d_pcm, nullptr, nullptr, fea_dst, s, &h->lc, h->err))) return st;
+        }
     } else if (need_spec) {
         if ((st = launch_frames_k<SRC_SPEC, DST_FEA>(h, kind, P, bd32, r.t32_n, nullptr, p->d_spec, fea_dst, s))) return st;
     } else {

@@ -65,11 +65,12 @@ struct FrameParams {
     float lin_scale;       // 1/S
     float log_offset;      // -ln S
     short lo[MAXB], hi[MAXB];
-    int woff[MAXB];
-    float w[MAXW];
+    int woff[MAXB];        // multiples of 4: each band's taps start 16-byte aligned
+    alignas(16) float w[MAXW];
     // second stage
     int nrows;             // rows of m2 (dctc: output columns in writer order; lpc/lpa: lporder+1 lags)
-    float m2[MAXM2];       // [nrows][nb]
+    int nbp;               // row pitch of m2: nb rounded up to a multiple of 4 (zero padded)
+    alignas(16) float m2[MAXM2];       // [nrows][nbp]
     int lporder, ncep;     // lpc/lpa
     int lpa_square;        // lpa/lpc without inld: square the band values first (src/fea/fea_impl.cc:165-169)
     int c0_last;           // lpc: write c1..cN then c0 (fea_c0 on) else c1..cN
@@ -126,20 +127,49 @@ __host__ __device__ inline SmemLayout smem_layout(int window, int wshift, int nb
 // ------------------------------------------------------------------------------------------
 // phase A: tile of PCM -> spectrum tile sP[f][k]
 // ------------------------------------------------------------------------------------------
+// int16 -> float without the (quarter-rate) conversion pipe: 1.5*2^23 + x is exact
+__device__ __forceinline__ float s16_to_f32(int x) { return __int_as_float(0x4B400000 + x) - 12582912.0f; }
+
+// WT: window length known at compile time (0 = take it from the parameters)
+template <int WT>
 __device__ __forceinline__ void phase_fft(const FrameParams &P, const int16_t *__restrict__ pcm, int64_t g0, bool first_tile,
                                           int nf, const FftTables &tb, float *sm, const SmemLayout &L) {
     const int tid = threadIdx.x;
     float *sP = sm + L.oP, *sD = sm + L.oD, *sW = sm + L.oW;
     cpx<float> *sTw = reinterpret_cast<cpx<float> *>(sm + L.oTw);
     cpx<float> *sTs = reinterpret_cast<cpx<float> *>(sm + L.oTs);
-    const int w = P.window, s = P.wshift;
+    const int w = WT ? WT : P.window, s = P.wshift;
     const int nsamp = (nf - 1) * s + w;
-    // stage: pre-emphasised samples (each sample converted once, shared by overlapping frames)
+    // stage: pre-emphasised samples (each sample converted once, shared by the overlapping
+    // frames); a thread handles runs of 8 consecutive samples
     const float alpha = P.preem;
-    for (int i = tid; i < nsamp; i += CTA_THREADS) {
-        float xi = (float)pcm[g0 + i];
-        float xp = (i == 0 && first_tile) ? 0.f : (float)pcm[g0 + i - 1];
-        sD[i] = fmaf(-alpha, xp, xi);
+    const int16_t *src = pcm + g0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    for (int i0 = tid * 8; i0 < nsamp; i0 += CTA_THREADS * 8) {
+        float prev = (i0 == 0 && first_tile) ? 0.f : s16_to_f32((int)src[i0 - 1]);
+        float v[8];
+        if (vec && i0 + 8 <= nsamp) {
+            const int4 q = __ldg(reinterpret_cast<const int4 *>(src + i0));
+            const int qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float x0 = s16_to_f32((qq[j] << 16) >> 16), x1 = s16_to_f32(qq[j] >> 16);
+                v[2 * j] = fmaf(-alpha, prev, x0);
+                v[2 * j + 1] = fmaf(-alpha, x0, x1);
+                prev = x1;
+            }
+            *reinterpret_cast<float4 *>(sD + i0) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4 *>(sD + i0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (i0 + j < nsamp) {
+                    float x = s16_to_f32((int)src[i0 + j]);
+                    sD[i0 + j] = fmaf(-alpha, prev, x);
+                    prev = x;
+                }
+            }
+        }
     }
     for (int i = tid; i < w; i += CTA_THREADS) sW[i] = tb.win[i];
     for (int i = tid; i < 256; i += CTA_THREADS) sTw[i] = mk<float>(tb.tw256[i].x, tb.tw256[i].y);
@@ -217,10 +247,19 @@ __device__ __forceinline__ void phase_fb(const FrameParams &P, float *sm, const 
     const float *row = sm + L.oP + lane * LDP;
     float *sY = sm + L.oY;
     for (int b = wv; b < P.nb; b += CTA_THREADS / 32) {
-        const int lo = P.lo[b], hi = P.hi[b];
-        const float *wp = P.w + P.woff[b] - lo;
+        const int lo = P.lo[b], n = P.hi[b] - lo + 1, n4 = n & ~3;
+        const float *wq = P.w + P.woff[b];
+        const float *r = row + lo;
         float acc = 0.f;
-        for (int k = lo; k <= hi; k++) acc = fmaf(row[k], wp[k], acc);
+        int k = 0;
+        for (; k < n4; k += 4) {                     // same summation order as the reference loop
+            const float4 wv4 = *reinterpret_cast<const float4 *>(wq + k);
+            acc = fmaf(r[k], wv4.x, acc);
+            acc = fmaf(r[k + 1], wv4.y, acc);
+            acc = fmaf(r[k + 2], wv4.z, acc);
+            acc = fmaf(r[k + 3], wv4.w, acc);
+        }
+        for (; k < n; k++) acc = fmaf(r[k], wq[k], acc);
         float y;
         if (P.inld) {
             y = powf(acc, 0.33f) * P.inld_scale;
@@ -246,9 +285,15 @@ __device__ __forceinline__ void phase_fea(const FrameParams &P, float *sm, const
         for (int b = wv; b < P.nb; b += CTA_THREADS / 32) sO[lane * od + b] = y[b];
     } else if (KIND == KIND_DCTC) {
         for (int i = wv; i < P.nrows; i += CTA_THREADS / 32) {
-            const float *m = P.m2 + i * P.nb;
+            const float *m = P.m2 + i * P.nbp;
             float acc = 0.f;
-            for (int k = 0; k < P.nb; k++) acc = fmaf(y[k], m[k], acc);
+            for (int k = 0; k < P.nbp; k += 4) {     // pad taps are zero, pad y entries are zeroed
+                const float4 m4 = *reinterpret_cast<const float4 *>(m + k);
+                acc = fmaf(y[k], m4.x, acc);
+                acc = fmaf(y[k + 1], m4.y, acc);
+                acc = fmaf(y[k + 2], m4.z, acc);
+                acc = fmaf(y[k + 3], m4.w, acc);
+            }
             sO[lane * od + i] = acc;
         }
     } else {  // LPA / LPC
@@ -257,7 +302,7 @@ __device__ __forceinline__ void phase_fea(const FrameParams &P, float *sm, const
         // power spectrum -> autocorrelation (src/fea/fea_impl.cc:181-198); the cos table,
         // the 1/2 end weights and the 2/N factor are folded into m2 on the host
         for (int k = wv; k <= p; k += CTA_THREADS / 32) {
-            const float *m = P.m2 + k * P.nb;
+            const float *m = P.m2 + k * P.nbp;
             double acc = 0.0;
             for (int n = 0; n < P.nb; n++) {
                 float v = y[n];
@@ -313,7 +358,7 @@ __device__ __forceinline__ void phase_fea(const FrameParams &P, float *sm, const
 // ------------------------------------------------------------------------------------------
 // the fused frame kernel
 // ------------------------------------------------------------------------------------------
-template <int SRC, int DST, int KIND>
+template <int SRC, int DST, int KIND, int WT>
 __global__ void __launch_bounds__(CTA_THREADS, 2)
 k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, const int16_t *__restrict__ pcm,
          const float *__restrict__ src, float *__restrict__ dst) {
@@ -325,8 +370,13 @@ k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, cons
     const int64_t row0 = bd.row_off[u] + t0;
     const int tid = threadIdx.x;
 
+    if (DST != DST_SPEC) {
+        // pad columns of the band tile (read by the 4-wide second-stage loops) must be finite
+        float *sY = sm + L.oY;
+        for (int i = tid; i < TILE_F * (MAXB + 1); i += CTA_THREADS) sY[i] = 0.f;
+    }
     if (SRC == SRC_PCM) {
-        phase_fft(P, pcm, bd.pcm_off[u] + (int64_t)t0 * P.wshift, t0 == 0, nf, tb, sm, L);
+        phase_fft<WT>(P, pcm, bd.pcm_off[u] + (int64_t)t0 * P.wshift, t0 == 0, nf, tb, sm, L);
     } else if (SRC == SRC_SPEC) {
         const float *g = src + row0 * NBIN;
         float *sP = sm + L.oP;

@@ -1,0 +1,304 @@
+// fp64 variant of the frame pipeline for the configurations whose REFERENCE arithmetic
+// cancels many digits, so that fp32 intermediates cannot reach the parity tolerance:
+//   * noise reduction applied to filter-bank outputs (-nr_when afterFB): |Y - b*Navg| and
+//     exten's Yavg = |Y - Navg| lose 3-5 digits on stationary segments (src/nr/nr.cc:110-132,
+//     245-249, 352-356);
+//   * LPC from squared band powers (lpa / lpc without the ^0.33 law, src/fea/fea_impl.cc:
+//     165-169): the autocorrelation matrix is ill-conditioned.
+// B200 issues FP64 FMAs at half the FP32 rate, so this path costs ~3x, not 30x.
+// Layout: 16 threads per frame (ctu_fft.cuh in double), 8 frames per pass, everything a
+// frame needs stays inside its group: FB bands, cepstral rows and autocorrelation lags are
+// dealt round-robin to the group's 16 threads.
+#ifndef CTU_PRECISE_CUH
+#define CTU_PRECISE_CUH
+
+#include "ctu_kernels.cuh"
+#include "ctu_nr_kernels.cuh"
+
+namespace ctu {
+
+constexpr int P64_THREADS = 128;
+constexpr int P64_GROUPS = P64_THREADS / GROUP;
+constexpr int P64_ROW = 264;          // doubles per spectrum row
+enum { SRC64_PCM = 0, SRC64_FB = 1 };
+enum { DST64_FB = 0, DST64_FEA = 1 };
+
+struct Tables64 {
+    const double2 *tw256, *twsplit;
+    const double *win;
+    const double *w;       // packed filter-bank taps (true scale)
+    const double *m2;      // second-stage matrix [nrows][nb]
+    const double *lift;    // lpc lifter [ncep+1]
+};
+
+template <int SRC, int DST, int KIND>
+__global__ void __launch_bounds__(P64_THREADS)
+k_frames64(const __grid_constant__ FrameParams P, BatchDesc bd, Tables64 tb, const int16_t *__restrict__ pcm, const double *__restrict__ src,
+           double *__restrict__ dst64, float *__restrict__ dst) {
+    extern __shared__ __align__(16) double smd[];
+    const int tid = threadIdx.x;
+    const int w = P.window, s = P.wshift, nb = P.nb;
+    cpx<double> *sTw = reinterpret_cast<cpx<double> *>(smd);          // 256
+    cpx<double> *sTs = sTw + 256;                                    // 130
+    cpx<double> *sX = sTs + 130;                                     // groups * 272
+    double *sP = reinterpret_cast<double *>(sX + P64_GROUPS * XPAD * 16);   // groups * P64_ROW
+    double *sYa = sP + P64_GROUPS * P64_ROW;                         // groups * 64
+    double *sRa = sYa + P64_GROUPS * 64;                             // groups * 64
+    if (SRC == SRC64_PCM) {
+        for (int i = tid; i < 256; i += P64_THREADS) sTw[i] = mk<double>(tb.tw256[i].x, tb.tw256[i].y);
+        for (int i = tid; i < 129; i += P64_THREADS) sTs[i] = mk<double>(tb.twsplit[i].x, tb.twsplit[i].y);
+    }
+    __syncthreads();
+    const int2 tile = bd.tiles[blockIdx.x];
+    const int u = tile.x, t0 = tile.y;
+    const int nf = min(TILE_F, bd.nframes[u] - t0);
+    const int64_t row0 = bd.row_off[u] + t0;
+    const int64_t g0 = bd.pcm_off[u];
+    const int c = tid & (GROUP - 1), grp = tid / GROUP;
+    cpx<double> *xch = sX + grp * (XPAD * 16);
+    double *pr = sP + grp * P64_ROW;
+    double *sY = sYa + grp * 64;
+    double *sR = sRa + grp * 64;
+#pragma unroll 1
+    for (int pass = 0; pass < TILE_F / P64_GROUPS; pass++) {
+        const int f = pass * P64_GROUPS + grp;
+        const bool active = f < nf;
+        if (SRC == SRC64_PCM) {
+            cpx<double> a[16];
+            if (active) {
+                const int64_t fs0 = g0 + (int64_t)(t0 + f) * s;
+                const bool at_start = (t0 + f) == 0;
+                double sum = 0;
+#pragma unroll
+                for (int n1 = 0; n1 < 16; n1++) {
+                    int i0 = 32 * n1 + 2 * c;
+                    double y0 = 0, y1 = 0;
+                    if (i0 < w) {
+                        double xm = (i0 == 0) ? (at_start ? 0.0 : (double)pcm[fs0 - 1]) : (double)pcm[fs0 + i0 - 1];
+                        double x0 = (double)pcm[fs0 + i0];
+                        y0 = tb.win[i0] * (x0 - (double)P.preem * xm);
+                        if (i0 + 1 < w) y1 = tb.win[i0 + 1] * ((double)pcm[fs0 + i0 + 1] - (double)P.preem * x0);
+                    }
+                    a[n1] = mk<double>(y0, y1);
+                    sum += y0 + y1;
+                }
+                if (P.remove_dc) {
+                    double mean = group_sum16d(sum) / (double)w;
+#pragma unroll
+                    for (int n1 = 0; n1 < 16; n1++) {
+                        int i0 = 32 * n1 + 2 * c;
+                        if (i0 < w) a[n1].x -= mean;
+                        if (i0 + 1 < w) a[n1].y -= mean;
+                    }
+                }
+                fft256_pass1(a, c, sTw, xch);
+            }
+            __syncwarp();
+            if (active) fft256_pass2(a, c, xch);
+            __syncwarp();
+            if (active) fft256_store_linear(a, c, xch);
+            __syncwarp();
+            if (active) {
+                cpx<double> lo[8], hi[8], mid;
+                rfft_split(xch, c, sTs, lo, hi, mid);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    int k = c + 16 * j;
+                    double pl = lo[j].x * lo[j].x + lo[j].y * lo[j].y;
+                    double ph = hi[j].x * hi[j].x + hi[j].y * hi[j].y;
+                    if (k == 0 && P.remove_dc) pl = 1e-10;
+                    if (P.take_sqrt) { pl = sqrt(pl); ph = sqrt(ph); }
+                    pr[k] = pl;
+                    pr[NC - k] = ph;
+                }
+                if (c == 0) {
+                    double pm = mid.x * mid.x + mid.y * mid.y;
+                    pr[128] = P.take_sqrt ? sqrt(pm) : pm;
+                }
+            }
+            __syncwarp();
+            // filter bank: bands dealt round-robin to the group's threads, sequential sum
+            // over the taps in the reference's order (src/fea/fb.cc:76-83)
+            if (active) {
+                for (int b = c; b < nb; b += GROUP) {
+                    const int lo_ = P.lo[b], hi_ = P.hi[b];
+                    const double *wp = tb.w + P.woff[b] - lo_;
+                    double acc = 0;
+                    for (int k = lo_; k <= hi_; k++) acc += pr[k] * wp[k];
+                    if (P.inld) acc = pow(acc, 0.33);
+                    sY[b] = acc;
+                }
+            }
+        } else {
+            if (active) for (int b = c; b < nb; b += GROUP) sY[b] = src[(row0 + f) * nb + b];
+        }
+        __syncwarp();
+        if (DST == DST64_FB) {
+            if (active) for (int b = c; b < nb; b += GROUP) dst64[(row0 + f) * nb + b] = sY[b];
+            __syncwarp();
+            continue;
+        }
+        // ---- features --------------------------------------------------------------------------
+        float *orow = dst + (row0 + f) * P.out_stride;
+        double *orow64 = dst64 ? dst64 + (row0 + f) * P.out_stride : nullptr;
+        if (KIND == KIND_SPEC || KIND == KIND_LOGSPEC || KIND == KIND_TRAPLOG) {
+            if (active) for (int b = c; b < nb; b += GROUP) {
+                double v = (KIND == KIND_SPEC) ? sY[b] : log(sY[b]);
+                orow[b] = (float)v;
+                if (orow64) orow64[b] = v;
+            }
+        } else if (KIND == KIND_DCTC) {
+            if (active) for (int b = c; b < nb; b += GROUP) sY[b] = log(sY[b]);
+            __syncwarp();
+            if (active) for (int i = c; i < P.nrows; i += GROUP) {
+                const double *m = tb.m2 + i * nb;
+                double acc = 0;
+                for (int k = 0; k < nb; k++) acc += sY[k] * m[k];
+                orow[i] = (float)acc;
+                if (orow64) orow64[i] = acc;
+            }
+        } else {
+            const int p = P.lporder;
+            if (active && P.lpa_square) for (int b = c; b < nb; b += GROUP) sY[b] = sY[b] * sY[b];
+            __syncwarp();
+            if (active) for (int k = c; k <= p; k += GROUP) {
+                const double *m = tb.m2 + k * nb;
+                double acc = 0;
+                for (int n = 0; n < nb; n++) acc += sY[n] * m[n];
+                sR[k] = acc;
+            }
+            __syncwarp();
+            if (active && c == 0) {
+                double a[MAXR], aa[MAXR];
+                double Pe = sR[0];
+                double rc = -sR[1] / sR[0];
+                Pe = Pe * (1 - rc * rc);
+                a[0] = aa[0] = 1.0; a[1] = aa[1] = rc;
+                for (int ik = 2; ik <= p; ik++) {
+                    double dm = sR[ik];
+                    for (int n = 1; n <= ik - 1; n++) dm += aa[n] * sR[ik - n];
+                    rc = -dm / Pe;
+                    a[ik] = rc;
+                    for (int n = 1; n <= ik - 1; n++) a[n] = aa[n] + rc * aa[ik - n];
+                    for (int n = 1; n <= ik; n++) aa[n] = a[n];
+                    Pe = Pe * (1 - rc * rc);
+                }
+                if (KIND == KIND_LPA) {
+                    for (int i = 1; i <= p; i++) { orow[i - 1] = (float)a[i]; if (orow64) orow64[i - 1] = a[i]; }
+                } else {
+                    double cc[MAXR];
+                    const int N = P.ncep;
+                    cc[0] = log(Pe);
+                    for (int n = 1; n <= N; n++) {
+                        double sum = 0;
+                        if (n <= p) {
+                            for (int k = 1; k <= n - 1; k++) sum += (n - k) * cc[n - k] * a[k];
+                            cc[n] = -a[n] - sum / n;
+                        } else {
+                            for (int k = 1; k <= p; k++) sum += (n - k) * cc[n - k] * a[k];
+                            cc[n] = -sum / n;
+                        }
+                    }
+                    for (int n = 1; n <= N; n++) { double v = cc[n] * tb.lift[n]; orow[n - 1] = (float)v; if (orow64) orow64[n - 1] = v; }
+                    if (P.c0_last) { orow[N] = (float)cc[0]; if (orow64) orow64[N] = cc[0]; }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static inline size_t p64_smem_bytes() {
+    return sizeof(double) * (2 * (256 + 130 + P64_GROUPS * XPAD * 16) + P64_GROUPS * (P64_ROW + 64 + 64));
+}
+
+template <int SRC, int DST, int KIND>
+static int launch_frames64_t(const FrameParams &P, const BatchDesc &bd, const Tables64 &tb, int64_t ntiles, const int16_t *pcm,
+                             const double *src, double *dst64, float *dst, cudaStream_t s, LaunchCtx *lc, std::string &err) {
+    if (ntiles <= 0) return CTU_OK;
+    size_t bytes = p64_smem_bytes();
+    auto kern = k_frames64<SRC, DST, KIND>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) {
+        lc->begin(SRC == SRC64_PCM ? (DST == DST64_FB ? "k_frames64<pcm,fb>" : "k_frames64<pcm,fea>") : "k_frames64<fb,fea>", s);
+        kern<<<(unsigned)ntiles, P64_THREADS, bytes, s>>>(P, bd, tb, pcm, src, dst64, dst);
+        lc->end(s);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e) + " (k_frames64)"; return CTU_ERR_CUDA; }
+    return CTU_OK;
+}
+
+template <int SRC, int DST>
+static int launch_frames64_k(int kind, const FrameParams &P, const BatchDesc &bd, const Tables64 &tb, int64_t nt, const int16_t *pcm,
+                             const double *src, double *dst64, float *dst, cudaStream_t s, LaunchCtx *lc, std::string &err) {
+    switch (kind) {
+        case KIND_SPEC: return launch_frames64_t<SRC, DST, KIND_SPEC>(P, bd, tb, nt, pcm, src, dst64, dst, s, lc, err);
+        case KIND_LOGSPEC: return launch_frames64_t<SRC, DST, KIND_LOGSPEC>(P, bd, tb, nt, pcm, src, dst64, dst, s, lc, err);
+        case KIND_DCTC: return launch_frames64_t<SRC, DST, KIND_DCTC>(P, bd, tb, nt, pcm, src, dst64, dst, s, lc, err);
+        case KIND_LPA: return launch_frames64_t<SRC, DST, KIND_LPA>(P, bd, tb, nt, pcm, src, dst64, dst, s, lc, err);
+        case KIND_LPC: return launch_frames64_t<SRC, DST, KIND_LPC>(P, bd, tb, nt, pcm, src, dst64, dst, s, lc, err);
+        case KIND_TRAPLOG: return launch_frames64_t<SRC, DST, KIND_TRAPLOG>(P, bd, tb, nt, pcm, src, dst64, dst, s, lc, err);
+    }
+    err = "CTU: bad kind";
+    return CTU_ERR_CONFIG;
+}
+
+// ---- fp64 noise-reduction scan over band values (same recursions as k_nr_scan, written as
+// the reference writes them; cancellation is harmless at 53 bits) ----------------------------
+__global__ void __launch_bounds__(128)
+k_nr_scan64(const __grid_constant__ NrParams N, const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int u0, int n_utts,
+            int size, double *X, const uint8_t *__restrict__ flags) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)n_utts * size) return;
+    const int u = u0 + (int)(gid / size), bin = (int)(gid % size);
+    const int T = nframes[u];
+    double *x = X + row_off[u] * size + bin;
+    const uint8_t *fl = flags ? flags + row_off[u] : nullptr;
+    const double p = N.pd, a = N.ad, b = (double)N.b;
+    double Navg = (N.mode == NR_EXTEN) ? 0.95 : 0.0, Yavg = 0.05, Nravg = 0.0;
+    for (int t = 0; t < T; t++) {
+        double xi = x[(int64_t)t * size];
+        if (N.mode == NR_EXTEN) {
+            double H;
+            if (N.a_kind == 1) H = Navg / (Navg + Yavg);
+            else if (N.a_kind == 2) H = Navg / sqrt(Navg * Navg + Yavg * Yavg);
+            else H = Navg / pow(pow(Navg, a) + pow(Yavg, a), 1. / a);
+            const double Nn = H * xi;
+            Navg = p * Navg + (1 - p) * Nn;
+            Yavg = (xi > Navg) ? xi - Navg : Navg - xi;
+            xi -= Nn;
+        } else {
+            const int ninit = (N.mode == NR_HWSS) ? N.initsegs - (t + 1) : N.initsegs - t;
+            const bool upd = (fl[t] == 0) || ninit > 0;
+            if (N.mode == NR_2FWSS) {
+                if (upd) Navg = p * Navg + (1 - p) * xi;
+                xi -= Navg; if (xi < 0.) xi = -xi;
+                if (upd) Nravg = p * Nravg + (1 - p) * xi;
+                xi -= Nravg; if (xi < 0.) xi = -xi;
+            } else {
+                if (N.a_kind == 2) xi *= xi; else if (N.a_kind == 0) xi = pow(xi, a);
+                if (upd) Navg = p * Navg + (1 - p) * xi;
+                xi -= b * Navg;
+                if (xi < 0.) xi = (N.mode == NR_HWSS) ? 0. : -xi;
+                if (N.a_kind == 2) xi = sqrt(xi); else if (N.a_kind == 0) xi = pow(xi, 1.0 / a);
+            }
+        }
+        x[(int64_t)t * size] = xi;
+    }
+}
+
+static inline int launch_nr_scan64(const NrParams &N, const int *d_nframes, const int64_t *d_row_off, int u0, int u1, int size, double *X,
+                                   const uint8_t *flags, cudaStream_t s, LaunchCtx *lc, std::string &err) {
+    int64_t n = (int64_t)(u1 - u0) * size;
+    if (n <= 0) return CTU_OK;
+    lc->begin("k_nr_scan64", s);
+    k_nr_scan64<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(N, d_nframes, d_row_off, u0, u1 - u0, size, X, flags);
+    lc->end(s);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e) + " (k_nr_scan64)"; return CTU_ERR_CUDA; }
+    return CTU_OK;
+}
+
+}  // namespace ctu
+#endif
