@@ -527,7 +527,8 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     // workspaces by configuration
     const bool nr_on = h->nr_mode != NR_NONE;
     const bool need_spec = h->signal_out || (nr_on && h->cfg.nr_when == 0) || (h->do_vad && h->vad_cri != VCRI_CEPDIST_FEA);
-    const bool need_fb = !h->signal_out && nr_on && h->cfg.nr_when == 1;
+    const bool lpc_kind = (h->fea_kind == FEA_LPA || h->fea_kind == FEA_LPC);
+    const bool need_fb = !h->signal_out && ((nr_on && h->cfg.nr_when == 1) || lpc_kind);
     if (need_spec && (st = dev_alloc(h, p, &p->d_spec, (size_t)rows * NBIN))) { ctu_plan_destroy(p); return st; }
     if (need_fb && !h->precise && (st = dev_alloc(h, p, &p->d_fb, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     if (need_fb && h->precise && (st = dev_alloc(h, p, &p->d_fb64, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
@@ -623,11 +624,24 @@ static int launch_frames_k(ctu_handle *h, int kind, const FrameParams &P, const 
         case KIND_SPEC: return launch_frames_t<SRC, DST, KIND_SPEC>(h, P, bd, nt, pcm, src, dst, s);
         case KIND_LOGSPEC: return launch_frames_t<SRC, DST, KIND_LOGSPEC>(h, P, bd, nt, pcm, src, dst, s);
         case KIND_DCTC: return launch_frames_t<SRC, DST, KIND_DCTC>(h, P, bd, nt, pcm, src, dst, s);
-        case KIND_LPA: return launch_frames_t<SRC, DST, KIND_LPA>(h, P, bd, nt, pcm, src, dst, s);
-        case KIND_LPC: return launch_frames_t<SRC, DST, KIND_LPC>(h, P, bd, nt, pcm, src, dst, s);
         case KIND_TRAPLOG: return launch_frames_t<SRC, DST, KIND_TRAPLOG>(h, P, bd, nt, pcm, src, dst, s);
     }
     return fail(h, CTU_ERR_CONFIG, "CTU: bad kind");
+}
+
+// LPC epilogue kernel over rows [row0, row0+nrows) of the band matrix
+static int launch_lpc(ctu_handle *h, const FrameParams &P, bool ceps, int64_t row0, int64_t nrows, const float *fb, float *out, cudaStream_t s) {
+    if (nrows <= 0) return CTU_OK;
+    const unsigned grid = (unsigned)((nrows + LPC_THREADS - 1) / LPC_THREADS);
+    const size_t bytes = (size_t)LPC_THREADS * (P.nb | 1) * sizeof(float);
+    h->lc.begin("k_lpc", s);
+    if (ceps && P.lporder == 12 && P.ncep == 12) k_lpc<12, 12, true><<<grid, LPC_THREADS, bytes, s>>>(P, row0, nrows, fb, out);
+    else if (ceps) k_lpc<0, 0, true><<<grid, LPC_THREADS, bytes, s>>>(P, row0, nrows, fb, out);
+    else if (P.lporder == 12) k_lpc<12, 0, false><<<grid, LPC_THREADS, bytes, s>>>(P, row0, nrows, fb, out);
+    else k_lpc<0, 0, false><<<grid, LPC_THREADS, bytes, s>>>(P, row0, nrows, fb, out);
+    h->lc.end(s);
+    CK(cudaGetLastError());
+    return CTU_OK;
 }
 
 static int kind_of(const ctu_handle *h) {
@@ -698,6 +712,12 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
         } else {
             if ((st = launch_frames64_k<SRC64_PCM, DST64_FEA>(kind, P, bd32, t64, r.t32_n, d_pcm, nullptr, nullptr, fea_dst, s, &h->lc, h->err))) return st;
         }
+    } else if (kind == KIND_LPA || kind == KIND_LPC) {
+        // band values to HBM (76 B per frame for PLP), then one thread per frame for the recursion
+        FrameParams Pf = h->fp; Pf.out_dim = h->fb.nb; Pf.out_stride = h->fb.nb;
+        if (need_spec) { if ((st = launch_frames_t<SRC_SPEC, DST_FB, KIND_SPEC>(h, Pf, bd32, r.t32_n, nullptr, p->d_spec, p->d_fb, s))) return st; }
+        else if ((st = launch_frames_t<SRC_PCM, DST_FB, KIND_SPEC>(h, Pf, bd32, r.t32_n, d_pcm, nullptr, p->d_fb, s))) return st;
+        if ((st = launch_lpc(h, P, kind == KIND_LPC, r.row0, r.nrows, p->d_fb, fea_dst, s))) return st;
     } else if (need_spec) {
         if ((st = launch_frames_k<SRC_SPEC, DST_FEA>(h, kind, P, bd32, r.t32_n, nullptr, p->d_spec, fea_dst, s))) return st;
     } else {
@@ -706,9 +726,14 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     // ---- stage 3: long-context ------------------------------------------------------------
     if (kind == KIND_TRAPLOG && r.t64_n > 0) {
         size_t bytes = (size_t)(TRAP_ROWS + h->tp.L - 1) * h->tp.nb * sizeof(float);
-        CK(cudaFuncSetAttribute(k_trapdct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         h->lc.begin("k_trapdct", s);
-        k_trapdct<<<(unsigned)r.t64_n, 256, bytes, s>>>(h->tp, bd64, TRAP_ROWS, p->d_log, d_fea);
+        if (h->tp.L == 51 && h->tp.ndct == 8) {
+            CK(cudaFuncSetAttribute(k_trapdct<51, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            k_trapdct<51, 8><<<(unsigned)r.t64_n, 256, bytes, s>>>(h->tp, bd64, TRAP_ROWS, p->d_log, d_fea);
+        } else {
+            CK(cudaFuncSetAttribute(k_trapdct<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            k_trapdct<0, 0><<<(unsigned)r.t64_n, 256, bytes, s>>>(h->tp, bd64, TRAP_ROWS, p->d_log, d_fea);
+        }
         h->lc.end(s);
         CK(cudaGetLastError());
     }

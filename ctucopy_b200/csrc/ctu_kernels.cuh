@@ -422,6 +422,86 @@ k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K1c: LPC epilogue as its own kernel, one THREAD per frame (src/fea/fea_impl.cc:163-284:
+// band values -> autocorrelation by cosine transform -> Levinson-Durbin -> [cepstrum,
+// lifter]).  The recursion is a ~1000-instruction dependent fp64 chain per frame; run by one
+// warp inside the fused frame kernel it stalls the whole CTA, here 128 independent frames
+// per CTA and many CTAs per SM hide it.  PORD / NCEP compile-time (0 = runtime) keeps the
+// coefficient arrays in registers.
+// in: band values (true scale, after ^0.33) [rows x nb]; out: rows of the feature matrix.
+// ------------------------------------------------------------------------------------------
+constexpr int LPC_THREADS = 128;
+
+template <int PORD, int NCEP, bool CEPS>
+__global__ void __launch_bounds__(LPC_THREADS)
+k_lpc(const __grid_constant__ FrameParams P, int64_t row0, int64_t nrows, const float *__restrict__ fb, float *__restrict__ out) {
+    extern __shared__ __align__(16) float sm[];
+    const int nb = P.nb, ld = nb | 1;
+    const int64_t r0 = row0 + (int64_t)blockIdx.x * LPC_THREADS;
+    const int nr = (int)min((int64_t)LPC_THREADS, row0 + nrows - r0);
+    for (int i = threadIdx.x; i < nr * nb; i += LPC_THREADS) {
+        int r = i / nb, b = i - r * nb;
+        float v = fb[r0 * nb + i];
+        sm[r * ld + b] = P.lpa_square ? v * v : v;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x >= nr) return;
+    const float *y = sm + threadIdx.x * ld;
+    const int p = PORD ? PORD : P.lporder;
+    constexpr int NA = PORD ? PORD + 1 : MAXR;
+    double R[NA], a[NA], aa[NA];
+#pragma unroll
+    for (int k = 0; k < NA; k++) {
+        if (k <= p) {
+            const float *m = P.m2 + k * P.nbp;
+            double acc = 0.0;
+            for (int n = 0; n < nb; n++) acc += (double)y[n] * (double)m[n];
+            R[k] = acc;
+        }
+    }
+    double Pe = R[0];
+    double rc = -R[1] / R[0];
+    Pe = Pe * (1 - rc * rc);
+    a[0] = aa[0] = 1.0; a[1] = aa[1] = rc;
+#pragma unroll
+    for (int ik = 2; ik < NA; ik++) {
+        if (ik <= p) {
+            double dm = R[ik];
+#pragma unroll
+            for (int n = 1; n < NA; n++) if (n <= ik - 1) dm += aa[n] * R[ik - n];
+            rc = -dm / Pe;
+            a[ik] = rc;
+#pragma unroll
+            for (int n = 1; n < NA; n++) if (n <= ik - 1) a[n] = aa[n] + rc * aa[ik - n];
+#pragma unroll
+            for (int n = 1; n < NA; n++) if (n <= ik) aa[n] = a[n];
+            Pe = Pe * (1 - rc * rc);
+        }
+    }
+    float *o = out + (r0 + threadIdx.x) * P.out_stride;
+    if (!CEPS) {
+#pragma unroll
+        for (int i = 1; i < NA; i++) if (i <= p) o[i - 1] = (float)a[i];       // a0 is not written
+        return;
+    }
+    const int N = NCEP ? NCEP : P.ncep;
+    constexpr int NC_ = NCEP ? NCEP + 1 : MAXR;
+    double cc[NC_];
+    cc[0] = log(Pe);
+#pragma unroll
+    for (int n = 1; n < NC_; n++) {
+        if (n <= N) {
+            double sum = 0;
+#pragma unroll
+            for (int k = 1; k < NA; k++) if (k <= p && k <= n - 1) sum += (double)(n - k) * cc[(n - k) > 0 ? (n - k) : 0] * a[k];
+            cc[n] = (n <= p ? -a[n < NA ? n : 0] : 0.0) - sum / n;
+            o[n - 1] = (float)(cc[n] * (double)P.lift[n]);
+        }
+    }
+    if (P.c0_last) o[N] = (float)cc[0];
+}
+
 // one thread per utterance writes that utterance's tile descriptors
 __global__ void k_build_tiles(const int *__restrict__ nframes, const int64_t *__restrict__ tile_off, int n_utts, int tile_f,
                               int2 *__restrict__ tiles) {
@@ -509,6 +589,10 @@ struct TrapParams {
     float m[TRAP_MAXN * TRAP_MAXL];   // [ndct][L]: 2*hamm[j]*cos(pi (j+.5) k / L) with the mean removal folded in
 };
 
+// LT / NT: trajectory length and coefficient count known at compile time (0 = runtime).
+// With both fixed the j and k loops unroll completely and every matrix entry becomes a
+// constant-bank operand of its FFMA (no load instruction at all).
+template <int LT, int NT>
 __global__ void __launch_bounds__(256)
 k_trapdct(const __grid_constant__ TrapParams Tp, BatchDesc bd, int tile_rows, const float *__restrict__ logfb,
           float *__restrict__ out) {
@@ -518,7 +602,7 @@ k_trapdct(const __grid_constant__ TrapParams Tp, BatchDesc bd, int tile_rows, co
     const int T = bd.nframes[u];
     const int nr = min(tile_rows, T - t0);
     const int64_t row0 = bd.row_off[u];
-    const int nb = Tp.nb, L = Tp.L, h = Tp.h;
+    const int nb = Tp.nb, L = LT ? LT : Tp.L, h = (L + 1) / 2, ND = NT ? NT : Tp.ndct;
     const bool regular = T >= h - 1;
     // rows needed: t0-(h-1) .. t0+nr-1+(h-1), clamped (replicated context)
     const int span = nr + L - 1;
@@ -535,19 +619,29 @@ k_trapdct(const __grid_constant__ TrapParams Tp, BatchDesc bd, int tile_rows, co
     __syncthreads();
     for (int i = threadIdx.x; i < nr * nb; i += blockDim.x) {
         int r = i / nb, b = i - r * nb;
-        float acc[TRAP_MAXN];
+        constexpr int NA = NT ? NT : TRAP_MAXN;
+        float acc[NA];
 #pragma unroll
-        for (int k = 0; k < TRAP_MAXN; k++) acc[k] = 0.f;
+        for (int k = 0; k < NA; k++) acc[k] = 0.f;
         // the rows of m sum to zero (mean removal is folded in), so any constant may be
         // subtracted first: take the centre value to keep the fp32 products small
         if (regular) {
             const float *v = sm + r * nb + b;
             const float ref = v[(h - 1) * nb];
-            for (int j = 0; j < L; j++) {
-                float x = v[j * nb] - ref;
+            if (LT && NT) {
 #pragma unroll
-                for (int k = 0; k < TRAP_MAXN; k++)
-                    if (k < Tp.ndct) acc[k] = fmaf(x, Tp.m[k * L + j], acc[k]);
+                for (int j = 0; j < (LT ? LT : 1); j++) {
+                    const float x = v[j * nb] - ref;
+#pragma unroll
+                    for (int k = 0; k < NA; k++) acc[k] = fmaf(x, Tp.m[k * (LT ? LT : 1) + j], acc[k]);
+                }
+            } else {
+                for (int j = 0; j < L; j++) {
+                    const float x = v[j * nb] - ref;
+#pragma unroll
+                    for (int k = 0; k < NA; k++)
+                        if (k < ND) acc[k] = fmaf(x, Tp.m[k * L + j], acc[k]);
+                }
             }
         } else {
             // flush r of a short file sees Z never-written (zero) ring rows first
@@ -557,14 +651,14 @@ k_trapdct(const __grid_constant__ TrapParams Tp, BatchDesc bd, int tile_rows, co
                 float x = -ref;
                 if (j >= Z) x = sm[min(max(j - Z - (h - 1), 0), T - 1) * nb + b] - ref;
 #pragma unroll
-                for (int k = 0; k < TRAP_MAXN; k++)
-                    if (k < Tp.ndct) acc[k] = fmaf(x, Tp.m[k * L + j], acc[k]);
+                for (int k = 0; k < NA; k++)
+                    if (k < ND) acc[k] = fmaf(x, Tp.m[k * L + j], acc[k]);
             }
         }
-        float *o = out + (row0 + t0 + r) * Tp.out_stride + b * Tp.ndct;
+        float *o = out + (row0 + t0 + r) * Tp.out_stride + b * ND;
 #pragma unroll
-        for (int k = 0; k < TRAP_MAXN; k++)
-            if (k < Tp.ndct) o[k] = acc[k];
+        for (int k = 0; k < NA; k++)
+            if (k < ND) o[k] = acc[k];
     }
 }
 

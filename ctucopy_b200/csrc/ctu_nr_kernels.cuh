@@ -123,98 +123,118 @@ static inline int build_nr_params(const ctu_config &c, int nr_mode, int vad_src,
 // ------------------------------------------------------------------------------------------
 // K2 / K3: noise-reduction scans
 // ------------------------------------------------------------------------------------------
-constexpr int SCAN_UNROLL = 8;
+// One thread per (utterance, bin), frames walked in blocks of SCAN_UNROLL: all loads of a
+// block are issued before the (sequentially dependent) recursion touches them and all
+// stores after it, so each thread keeps SCAN_UNROLL x 4 B of reads in flight.  MODE / AKIND
+// are compile-time so the hot loop carries only the state it needs (register count decides
+// how many bytes per SM are in flight, and this kernel is HBM-bound).
+constexpr int SCAN_UNROLL = 16;
 
+struct ScanState { float Navg, Yavg, Nravg; double Nd, Yd; };
+
+// one frame of the recursion for one bin
+template <int MODE, int AKIND>
+__device__ __forceinline__ float nr_step(const NrParams &N, ScanState &S, float xi, int t, uint8_t flag) {
+    const float p = N.p, q = 1.f - N.p;
+    if (MODE == NR_EXTEN) {
+        if (AKIND == 0) {                   // general exponent: fp64, as the reference writes it
+            double Hd = S.Nd / pow(pow(S.Nd, N.ad) + pow(S.Yd, N.ad), 1. / N.ad);
+            double xd = (double)xi, Nn = Hd * xd;
+            S.Nd = N.pd * S.Nd + (1 - N.pd) * Nn;
+            S.Yd = fabs(xd - S.Nd);
+            return (float)(xd - Nn);
+        }
+        // H = Navg/(Navg+Yavg) (a=1) or Navg/hypot(Navg,Yavg) (a=2); the output X-H*X is formed
+        // as X*(1-H) with 1-H written without cancellation
+        float H, omH;
+        if (AKIND == 1) {
+            const float r = __frcp_rn(S.Navg + S.Yavg);
+            H = S.Navg * r; omH = S.Yavg * r;
+        } else {
+            const float h2 = fmaf(S.Navg, S.Navg, S.Yavg * S.Yavg);
+            const float hh = sqrtf(h2);
+            H = __fdiv_rn(S.Navg, hh);
+            omH = __fdiv_rn(S.Yavg * S.Yavg, hh * (hh + S.Navg));
+        }
+        const float Nn = H * xi;
+        S.Navg = fmaf(p, S.Navg, q * Nn);
+        S.Yavg = fabsf(xi - S.Navg);
+        return xi * omH;
+    }
+    // hwss decrements its counter before use, fwss / 2fwss after (src/nr/nr.cc:226, 367, 440)
+    const int ninit = (MODE == NR_HWSS) ? N.initsegs - (t + 1) : N.initsegs - t;
+    const bool upd = (flag == 0) || ninit > 0;
+    if (MODE == NR_2FWSS) {
+        if (upd) S.Navg = fmaf(p, S.Navg, q * xi);
+        xi = fabsf(xi - S.Navg);
+        if (upd) S.Nravg = fmaf(p, S.Nravg, q * xi);
+        return fabsf(xi - S.Nravg);
+    }
+    if (AKIND == 2) xi = xi * xi;
+    else if (AKIND == 0) xi = powf(xi, N.a);
+    if (upd) S.Navg = fmaf(p, S.Navg, q * xi);
+    xi = xi - N.b * S.Navg;
+    if (MODE == NR_HWSS) { if (xi < 0.f) xi = 0.f; }
+    else if (xi < 0.f) xi = -xi;
+    if (AKIND == 2) xi = sqrtf(xi);
+    else if (AKIND == 0) xi = powf(xi, 1.f / N.a);
+    return xi;
+}
+
+// SIZE: row length known at compile time (257 spectrum bins) so that the SCAN_UNROLL loads of
+// a block share one base register with immediate offsets; 0 = runtime (band domain)
+template <int MODE, int AKIND, int SIZE>
 __global__ void __launch_bounds__(256)
 k_nr_scan(const __grid_constant__ NrParams N, const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int u0, int n_utts,
-          int size, float *X, const uint8_t *__restrict__ flags) {
+          int size_rt, float *X, const uint8_t *__restrict__ flags) {
+    const int size = SIZE ? SIZE : size_rt;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (int64_t)n_utts * size) return;
     const int u = u0 + (int)(gid / size), bin = (int)(gid % size);
     const int T = nframes[u];
     float *x = X + row_off[u] * size + bin;
-    const uint8_t *fl = flags ? flags + row_off[u] : nullptr;
-    const float p = N.p, q = 1.f - N.p;
-    if (N.mode == NR_EXTEN) {
-        // state: smoothed noise Navg and smoothed speech Yavg start at 0.95 / 0.05
-        float Navg = 0.95f, Yavg = 0.05f;
-        double Nd = 0.95, Yd = 0.05;
-        for (int t0 = 0; t0 < T; t0 += SCAN_UNROLL) {
-            float v[SCAN_UNROLL];
-#pragma unroll
-            for (int j = 0; j < SCAN_UNROLL; j++) v[j] = (t0 + j < T) ? x[(int64_t)(t0 + j) * size] : 0.f;
-#pragma unroll
-            for (int j = 0; j < SCAN_UNROLL; j++) {
-                if (t0 + j >= T) break;
-                const float xi = v[j];
-                float H, omH;                       // H and 1-H, the latter without cancellation
-                if (N.a_kind == 1) {
-                    float s = Navg + Yavg;
-                    H = Navg / s; omH = Yavg / s;
-                } else if (N.a_kind == 2) {
-                    float hh = sqrtf(fmaf(Navg, Navg, Yavg * Yavg));
-                    H = Navg / hh;
-                    omH = (Yavg * Yavg) / (hh * (hh + Navg));
-                } else {
-                    double Hd = Nd / pow(pow(Nd, N.ad) + pow(Yd, N.ad), 1. / N.ad);
-                    double xd = (double)xi, Nn = Hd * xd;
-                    Nd = N.pd * Nd + (1 - N.pd) * Nn;
-                    Yd = fabs(xd - Nd);
-                    v[j] = (float)(xd - Nn);
-                    continue;
-                }
-                const float Nn = H * xi;
-                Navg = fmaf(p, Navg, q * Nn);
-                Yavg = fabsf(xi - Navg);
-                v[j] = xi * omH;                    // = X - N
-            }
-#pragma unroll
-            for (int j = 0; j < SCAN_UNROLL; j++)
-                if (t0 + j < T) x[(int64_t)(t0 + j) * size] = v[j];
-        }
-        return;
-    }
-    // hwss / fwss / 2fwss
-    float Navg = 0.f, Nravg = 0.f;               // standalone-file start
-    const float b = N.b;
-    const float inv_a = 1.f / N.a;
-    for (int t0 = 0; t0 < T; t0 += SCAN_UNROLL) {
+    const uint8_t *fl = (MODE != NR_EXTEN) ? flags + row_off[u] : nullptr;
+    // exten: smoothed noise Navg / smoothed speech Yavg start at 0.95 / 0.05 (src/nr/nr.cc:86-93);
+    // *ss: the noise estimate of a standalone file starts at 0 (src/nr/nr.cc:212-222)
+    ScanState S;
+    S.Navg = (MODE == NR_EXTEN) ? 0.95f : 0.f; S.Yavg = 0.05f; S.Nravg = 0.f; S.Nd = 0.95; S.Yd = 0.05;
+    int t0 = 0;
+    for (; t0 + SCAN_UNROLL <= T; t0 += SCAN_UNROLL) {
         float v[SCAN_UNROLL];
         uint8_t f[SCAN_UNROLL];
+        float *xr = x + (int64_t)t0 * size;
 #pragma unroll
         for (int j = 0; j < SCAN_UNROLL; j++) {
-            bool ok = t0 + j < T;
-            v[j] = ok ? x[(int64_t)(t0 + j) * size] : 0.f;
-            f[j] = ok ? fl[t0 + j] : 0;
+            v[j] = xr[j * size];
+            f[j] = (MODE != NR_EXTEN) ? fl[t0 + j] : 0;
         }
 #pragma unroll
-        for (int j = 0; j < SCAN_UNROLL; j++) {
-            const int t = t0 + j;
-            if (t >= T) break;
-            float xi = v[j];
-            // hwss decrements its counter before use, fwss / 2fwss after (src/nr/nr.cc:226, 367, 440)
-            const int ninit = (N.mode == NR_HWSS) ? N.initsegs - (t + 1) : N.initsegs - t;
-            const bool upd = (f[j] == 0) || ninit > 0;
-            if (N.mode == NR_2FWSS) {
-                if (upd) Navg = fmaf(p, Navg, q * xi);
-                xi = fabsf(xi - Navg);
-                if (upd) Nravg = fmaf(p, Nravg, q * xi);
-                xi = fabsf(xi - Nravg);
-            } else {
-                if (N.a_kind == 2) xi = xi * xi;
-                else if (N.a_kind == 0) xi = powf(xi, N.a);
-                if (upd) Navg = fmaf(p, Navg, q * xi);
-                xi = xi - b * Navg;
-                if (N.mode == NR_HWSS) { if (xi < 0.f) xi = 0.f; }
-                else if (xi < 0.f) xi = -xi;
-                if (N.a_kind == 2) xi = sqrtf(xi);
-                else if (N.a_kind == 0) xi = powf(xi, inv_a);
-            }
-            v[j] = xi;
-        }
+        for (int j = 0; j < SCAN_UNROLL; j++) v[j] = nr_step<MODE, AKIND>(N, S, v[j], t0 + j, f[j]);
 #pragma unroll
-        for (int j = 0; j < SCAN_UNROLL; j++)
-            if (t0 + j < T) x[(int64_t)(t0 + j) * size] = v[j];
+        for (int j = 0; j < SCAN_UNROLL; j++) xr[j * size] = v[j];
+    }
+    for (; t0 < T; t0++) {
+        float *xr = x + (int64_t)t0 * size;
+        *xr = nr_step<MODE, AKIND>(N, S, *xr, t0, (MODE != NR_EXTEN) ? fl[t0] : 0);
+    }
+}
+
+template <int MODE, int SIZE>
+static inline void launch_nr_scan_a(const NrParams &N, unsigned grid, cudaStream_t s, const int *d_nframes, const int64_t *d_row_off, int u0,
+                                    int n, int size, float *X, const uint8_t *flags) {
+    if (N.a_kind == 1 || MODE == NR_2FWSS) k_nr_scan<MODE, 1, SIZE><<<grid, 256, 0, s>>>(N, d_nframes, d_row_off, u0, n, size, X, flags);
+    else if (N.a_kind == 2) k_nr_scan<MODE, 2, SIZE><<<grid, 256, 0, s>>>(N, d_nframes, d_row_off, u0, n, size, X, flags);
+    else k_nr_scan<MODE, 0, SIZE><<<grid, 256, 0, s>>>(N, d_nframes, d_row_off, u0, n, size, X, flags);
+}
+
+template <int SIZE>
+static inline void launch_nr_scan_m(const NrParams &N, unsigned grid, cudaStream_t s, const int *d_nframes, const int64_t *d_row_off, int u0,
+                                    int n, int size, float *X, const uint8_t *flags) {
+    switch (N.mode) {
+        case NR_EXTEN: launch_nr_scan_a<NR_EXTEN, SIZE>(N, grid, s, d_nframes, d_row_off, u0, n, size, X, flags); break;
+        case NR_HWSS: launch_nr_scan_a<NR_HWSS, SIZE>(N, grid, s, d_nframes, d_row_off, u0, n, size, X, flags); break;
+        case NR_FWSS: launch_nr_scan_a<NR_FWSS, SIZE>(N, grid, s, d_nframes, d_row_off, u0, n, size, X, flags); break;
+        default: launch_nr_scan_a<NR_2FWSS, SIZE>(N, grid, s, d_nframes, d_row_off, u0, n, size, X, flags); break;
     }
 }
 
@@ -222,8 +242,10 @@ static inline int launch_nr_scan(const NrParams &N, const int *d_nframes, const 
                                  const uint8_t *flags, cudaStream_t s, LaunchCtx *lc, std::string &err) {
     int64_t n = (int64_t)(u1 - u0) * size;
     if (n <= 0) return CTU_OK;
+    const unsigned grid = (unsigned)((n + 255) / 256);
     lc->begin("k_nr_scan", s);
-    k_nr_scan<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(N, d_nframes, d_row_off, u0, u1 - u0, size, X, flags);
+    if (size == NBIN) launch_nr_scan_m<NBIN>(N, grid, s, d_nframes, d_row_off, u0, u1 - u0, size, X, flags);
+    else launch_nr_scan_m<0>(N, grid, s, d_nframes, d_row_off, u0, u1 - u0, size, X, flags);
     lc->end(s);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e) + " (k_nr_scan)"; return CTU_ERR_CUDA; }
