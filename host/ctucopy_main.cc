@@ -1,0 +1,391 @@
+// ctucopy_b200 -- command-line host of the B200-native CtuCopy hot path.
+//
+// Keeps the `ctucopy` command-line surface of the reference for this path: the same
+// options and -C config files (opts::parse, src/io/opts.cc:644-846), the same list format
+// ("in out [spk] [vadout]" per line, src/io/batch.cc:349-356), the same decoders (raw s16
+// with byte order, A-law, mu-law, canonical 44-byte WAVE: src/io/in.cc:434-611,
+// src/io/amulaw.h:20-53) and byte-identical writers (HTK, pfile, Kaldi ark+scp, raw, wave,
+// VAD '0'/'1' files: src/io/out.cc:61-781, src/io/pfile.cc:435-592, src/vad/vad.h:40-75).
+// Everything between decode and write -- the per-frame loop of BATCH::process -- runs on
+// the GPU through the C ABI of libctucopy_b200.so; there is no CPU implementation here.
+//
+// Errors: message on stderr, exit status 255 (src/main.cpp:31-60 returns -1).
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../include/ctucopy_b200.h"
+
+namespace {
+
+struct HostOpts {
+    std::string list, in, out, config, format_in, format_out_arg, pfilename, arkfilename, filevad, vad_out;
+    bool big_in = false, big_out = false, verbose = false, quiet = false, fb_printself = false;
+};
+
+struct ListEntry { std::string in, out, spk, vadout; };
+
+[[noreturn]] void die(const std::string &m) { throw std::runtime_error(m); }
+
+uint32_t bswap32(uint32_t x) { return ((x & 0xFFu) << 24) | ((x & 0xFF00u) << 8) | ((x & 0xFF0000u) >> 8) | ((x & 0xFF000000u) >> 24); }
+uint16_t bswap16(uint16_t x) { return (uint16_t)((x >> 8) | (x << 8)); }
+
+// G.711 expansion exactly as the reference does it (mode 1 = A-law, 0 = mu-law)
+int16_t g711(signed char a, int alaw) {
+    int chord, step, mag;
+    int sgn = (~(a >> 7)) & 1;
+    if (!alaw) {
+        chord = (~(a >> 4)) & 7;
+        step = (~(a)) & 0xf;
+        mag = (((2 * step) + 33) << chord) - 33;
+    } else {
+        chord = ((a ^ 0x55) >> 4) & 7;
+        step = ((a ^ 0x55)) & 0xf;
+        mag = (step << 1) + 1;
+        if (chord > 0) mag += 32; else chord = 1;
+        mag = mag << chord;
+    }
+    int v = ((1 - (2 * sgn)) * mag) & 0xffff;
+    v = (v << 2) & 0xffff;
+    return (int16_t)(uint16_t)v;
+}
+
+std::vector<unsigned char> slurp(const std::string &path, const char *err) {
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) die(err);
+    std::vector<unsigned char> b;
+    unsigned char buf[1 << 16];
+    size_t n;
+    while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) b.insert(b.end(), buf, buf + n);
+    std::fclose(f);
+    return b;
+}
+
+void decode(const HostOpts &o, int fs, const std::string &path, std::vector<int16_t> &pcm) {
+    const std::string &fmt = o.format_in;
+    if (fmt == "raw") {
+        auto b = slurp(path, "IN: Cannot open data file!");
+        size_t n = b.size() / 2, base = pcm.size();
+        pcm.resize(base + n);
+        std::memcpy(pcm.data() + base, b.data(), n * 2);
+        if (o.big_in) for (size_t i = 0; i < n; i++) pcm[base + i] = (int16_t)bswap16((uint16_t)pcm[base + i]);
+    } else if (fmt == "alaw" || fmt == "mulaw") {
+        auto b = slurp(path, "IN: Cannot open data file!");
+        size_t base = pcm.size();
+        pcm.resize(base + b.size());
+        for (size_t i = 0; i < b.size(); i++) pcm[base + i] = g711((signed char)b[i], fmt == "alaw");
+    } else if (fmt == "wave") {
+        auto b = slurp(path, "IN: Cannot open file!");
+        if (b.size() < 44 || std::memcmp(b.data(), "RIFF", 4)) die("IN: No RIFF header in file!");
+        if (std::memcmp(b.data() + 8, "WAVE", 4)) die("IN: Not a WAVE file!");
+        auto u16 = [&](size_t p) { return (int)(b[p] | (b[p + 1] << 8)); };
+        auto u32 = [&](size_t p) { return (uint32_t)b[p] | ((uint32_t)b[p + 1] << 8) | ((uint32_t)b[p + 2] << 16) | ((uint32_t)b[p + 3] << 24); };
+        if (u16(20) != 1) die("IN: Not a PCM WAVE file!");
+        if ((long)u32(24) != fs) die("IN: WAVE file reports different sampling rate than specified!");
+        if (u16(22) != 1) die("IN: Input WAVE file is not mono!");
+        if (u16(34) != 16) die("IN: Not 16 bits per sample!");
+        size_t n = std::min<size_t>(u32(40) / 2, (b.size() - 44) / 2), base = pcm.size();
+        pcm.resize(base + n);
+        std::memcpy(pcm.data() + base, b.data() + 44, n * 2);
+    } else {
+        die("IN: Unknown input file format!");
+    }
+}
+
+// "<ark path>" -> "<scp path>" the way the reference derives it: split on '.', drop the token
+// "ark" and everything after it, append "scp" (src/io/out.cc:756-774; empty tokens vanish)
+std::string ark_to_scp(const std::string &ark) {
+    std::string line, tok;
+    std::vector<std::string> toks;
+    for (char ch : ark) { if (ch == '.') { if (!tok.empty()) toks.push_back(tok); tok.clear(); } else tok += ch; }
+    if (!tok.empty()) toks.push_back(tok);
+    for (auto &t : toks) { if (t == "ark") return line + "scp"; line += t + "."; }
+    return line + "scp";
+}
+
+struct Writers {
+    const HostOpts &o;
+    const ctu_config &c;
+    int dim;
+    FILE *pf = nullptr, *ark = nullptr, *scp = nullptr;
+    std::vector<uint32_t> sent_table{0};
+    uint64_t pf_frames = 0;
+    Writers(const HostOpts &o_, const ctu_config &c_, int dim_) : o(o_), c(c_), dim(dim_) {
+        std::string fo(c.format_out);
+        if (fo == "pfile") {
+            pf = std::fopen(o.pfilename.c_str(), "wb");
+            if (!pf) die("ERROR: Can not open the pfile: " + o.pfilename + ".");
+            std::vector<char> z(32768, 0);
+            std::fwrite(z.data(), 1, z.size(), pf);
+        } else if (fo == "ark") {
+            ark = std::fopen(o.arkfilename.c_str(), "wb");
+            if (!ark) die("OUT: Cannot create output ark file!");
+            scp = std::fopen(ark_to_scp(o.arkfilename).c_str(), "wt");
+            if (!scp) die("Cannot open output scp file for writing!");
+        }
+    }
+    int parmkind() const {
+        std::string k(c.fea_kind);
+        int kind = k == "lpc" ? 11 : k == "dctc" ? 6 : k == "trapdct" ? 9 : k == "spec" ? 8 : k == "logspec" ? 7 : 9;
+        bool c0 = c.fea_c0 && !(k == "lpa" || k == "spec" || k == "logspec");
+        if (c0) kind |= 020000;
+        if (c.fea_E) kind |= 000100;
+        if (c.fea_delta && c.n_order >= 1) kind |= 000400;
+        if (c.fea_delta && c.n_order >= 2) kind |= 001000;
+        if (c.fea_delta && c.n_order == 3) kind |= 0100000;
+        return kind;
+    }
+    void features(const ListEntry &e, const float *rows, int64_t n) {
+        std::string fo(c.format_out);
+        if (fo == "htk") {
+            FILE *f = std::fopen(e.out.c_str(), "wb");
+            if (!f) die("OUT: Cannot create output file!");
+            uint32_t frames = (uint32_t)n, period = (uint32_t)std::floor(.5 + 10000000. * c.wshift / (double)c.fs);
+            uint16_t size = (uint16_t)(4 * dim), kind = (uint16_t)parmkind();
+            if (o.big_out) { frames = bswap32(frames); period = bswap32(period); size = bswap16(size); kind = bswap16(kind); }
+            std::fwrite(&frames, 4, 1, f); std::fwrite(&period, 4, 1, f); std::fwrite(&size, 2, 1, f); std::fwrite(&kind, 2, 1, f);
+            if (o.big_out) {
+                std::vector<uint32_t> t((size_t)n * dim);
+                std::memcpy(t.data(), rows, t.size() * 4);
+                for (auto &v : t) v = bswap32(v);
+                std::fwrite(t.data(), 4, t.size(), f);
+            } else {
+                std::fwrite(rows, 4, (size_t)n * dim, f);
+            }
+            std::fclose(f);
+        } else if (fo == "pfile") {
+            // rows: u32 sentence, u32 frame, float32 x dim, all big-endian (src/io/pfile.cc:470-539)
+            std::vector<uint32_t> row(dim + 2);
+            uint32_t sid = (uint32_t)sent_table.size() - 1;
+            for (int64_t t = 0; t < n; t++) {
+                row[0] = bswap32(sid); row[1] = bswap32((uint32_t)t);
+                std::memcpy(row.data() + 2, rows + t * dim, (size_t)dim * 4);
+                for (int i = 0; i < dim; i++) row[2 + i] = bswap32(row[2 + i]);
+                std::fwrite(row.data(), 4, row.size(), pf);
+            }
+            pf_frames += (uint64_t)n;
+            sent_table.push_back((uint32_t)pf_frames);
+        } else if (fo == "ark") {
+            // "<key> \0BFM \4<rows>\4<cols><data>"; the scp points at the \0 (src/io/out.cc:680-700)
+            std::fprintf(ark, "%s %cBFM %c", e.out.c_str(), 0, 4);
+            uint32_t r = (uint32_t)n; int32_t cols = dim;
+            std::fwrite(&r, 4, 1, ark);
+            std::fprintf(ark, "%c", 4);
+            std::fwrite(&cols, 4, 1, ark);
+            long long idx = (long long)std::ftell(ark) - 15;
+            std::fprintf(scp, "%s %s:%llu\n", e.out.c_str(), o.arkfilename.c_str(), (unsigned long long)idx);
+            std::fwrite(rows, 4, (size_t)n * dim, ark);
+        }
+    }
+    void waveform(const ListEntry &e, const int16_t *s, int64_t n) {
+        FILE *f = std::fopen(e.out.c_str(), "wb");
+        if (!f) die("OUT: Cannot open output stream!");
+        std::string fo(c.format_out);
+        if (fo == "wave") {
+            uint32_t data = (uint32_t)(2 * n), whole = data + 36, fs = (uint32_t)c.fs, bps = fs * 2, pcm = 16;
+            uint16_t one = 1, two = 2, sixteen = 16;
+            std::fwrite("RIFF", 1, 4, f); std::fwrite(&whole, 4, 1, f); std::fwrite("WAVE", 1, 4, f); std::fwrite("fmt ", 1, 4, f);
+            std::fwrite(&pcm, 4, 1, f); std::fwrite(&one, 2, 1, f); std::fwrite(&one, 2, 1, f); std::fwrite(&fs, 4, 1, f);
+            std::fwrite(&bps, 4, 1, f); std::fwrite(&two, 2, 1, f); std::fwrite(&sixteen, 2, 1, f);
+            std::fwrite("data", 1, 4, f); std::fwrite(&data, 4, 1, f);
+            std::fwrite(s, 2, (size_t)n, f);
+        } else if (o.big_out) {
+            std::vector<uint16_t> t((size_t)n);
+            for (int64_t i = 0; i < n; i++) t[i] = bswap16((uint16_t)s[i]);
+            std::fwrite(t.data(), 2, t.size(), f);
+        } else {
+            std::fwrite(s, 2, (size_t)n, f);
+        }
+        std::fclose(f);
+    }
+    void vad(const ListEntry &e, const uint8_t *v, int64_t n) {
+        FILE *f = std::fopen(e.vadout.c_str(), "wb");
+        if (!f) die("FileWriter: cannot open file!");
+        for (int64_t i = 0; i < n; i++) std::fputc(v[i] ? '1' : '0', f);
+        std::fclose(f);
+    }
+    void close() {
+        if (pf) {
+            // sentence table right behind the data, then the ASCII header (src/io/pfile.cc:435-468, 573-592)
+            uint64_t ncol = (uint64_t)dim + 2, nsent = sent_table.size() - 1;
+            for (uint32_t v : sent_table) { uint32_t b = bswap32(v); std::fwrite(&b, 4, 1, pf); }
+            std::string h;
+            auto num = [](uint64_t v) { return std::to_string((unsigned long long)v); };
+            h += "-pfile_header version 0 size 32768\n";
+            h += "-num_sentences " + num(nsent) + "\n";
+            h += "-num_frames " + num(pf_frames) + "\n";
+            h += "-first_feature_column 2\n";
+            h += "-num_features " + num((uint64_t)dim) + "\n";
+            h += "-first_label_column " + num((uint64_t)dim + 2) + "\n";
+            h += "-num_labels 0\n";
+            h += "-format dd" + std::string((size_t)dim, 'f') + "\n";
+            h += "-data size " + num(ncol * pf_frames) + " offset 0 ndim 2 nrow " + num(pf_frames) + " ncol " + num(ncol) + "\n";
+            h += "-sent_table_data size " + num(nsent + 1) + " offset " + num(ncol * pf_frames) + " ndim 1\n";
+            h += "-end\n";
+            std::fseek(pf, 0, SEEK_SET);
+            std::fwrite(h.data(), 1, h.size(), pf);
+            std::fclose(pf); pf = nullptr;
+        }
+        if (ark) { std::fclose(ark); ark = nullptr; }
+        if (scp) { std::fclose(scp); scp = nullptr; }
+    }
+};
+
+void take_host_option(HostOpts &o, const char *l, const char *r) {
+    std::string opt(l);
+    auto val = [&]() { return r ? std::string(r) : std::string(); };
+    if (opt == "-S" && r) o.list = r;
+    else if (opt == "-i" && r) o.in = r;
+    else if (opt == "-o" && r) o.out = r;
+    else if (opt == "-format_in" && r) o.format_in = r;
+    else if (opt == "-format_out" && r) {
+        std::string v = val();
+        size_t eq = v.find('=');
+        if (v.find("pfile=") != std::string::npos) o.pfilename = v.substr(eq + 1);
+        else if (v.find("ark=") != std::string::npos) o.arkfilename = v.substr(eq + 1);
+    } else if (opt == "-endian_in" && r) { if (val() == "big") o.big_in = true; else if (val() == "little") o.big_in = false; }
+    else if (opt == "-endian_out" && r) { if (val() == "big") o.big_out = true; else if (val() == "little") o.big_out = false; }
+    else if (opt == "-vad" && r) { std::string v = val(); if (v.find("file=") != std::string::npos) o.filevad = v.substr(v.find('=') + 1); }
+    else if (opt == "-vad_out" && r) o.vad_out = r;
+    else if (opt == "-v" || opt == "-verbose") { o.verbose = true; o.quiet = false; }
+    else if (opt == "-quiet") { o.quiet = true; o.verbose = false; }
+    else if (opt == "-fb_printself") o.fb_printself = true;
+}
+
+int run(int argc, char **argv) {
+    if (argc == 1) { std::cerr << "usage: ctucopy_b200 <ctucopy options> -S <list>   (see man/ctucopy4 of the reference)" << std::endl; die("OPTS: No command line options!"); }
+    ctu_config cfg;
+    ctu_config_init(&cfg);
+    HostOpts ho;
+    // host-owned options: config file first, then the command line (same order as the library's parser)
+    for (int j = 1; j + 1 < argc; j++) {
+        if (std::strcmp(argv[j], "-C")) continue;
+        std::ifstream cf(argv[j + 1]);
+        std::string line;
+        while (std::getline(cf, line)) {
+            size_t h = line.find('#');
+            if (h != std::string::npos) line.resize(h);
+            char a[1024] = "", b[1024] = "";
+            int n = std::sscanf(line.c_str(), "%1023s %1023s", a, b);
+            if (n >= 1) take_host_option(ho, a, n >= 2 ? b : nullptr);
+        }
+    }
+    for (int j = 1; j < argc; j++) {
+        if (argv[j][0] != '-') continue;
+        const char *r = (j + 1 < argc && argv[j + 1][0] != '-') ? argv[j + 1] : nullptr;
+        take_host_option(ho, argv[j], r);
+    }
+    if (ctu_config_parse(&cfg, argc - 1, (const char *const *)(argv + 1))) die(ctu_config_error());
+    if (ho.fb_printself) {
+        int32_t nb = 0;
+        if (ctu_design_filter_bank(&cfg, nullptr, nullptr, nullptr, &nb)) die(ctu_last_error(nullptr));
+        std::vector<double> mat((size_t)nb * cfg.wfftby2);
+        std::vector<int32_t> lo(nb), hi(nb);
+        ctu_design_filter_bank(&cfg, mat.data(), lo.data(), hi.data(), &nb);
+        for (int b = 0; b < nb; b++) { for (int i = 0; i < cfg.wfftby2; i++) std::cerr << mat[(size_t)b * cfg.wfftby2 + i] << "\t"; std::cerr << std::endl; }
+    }
+    // the list (single-file mode is one list line)
+    std::vector<ListEntry> list;
+    const bool do_vad = std::strcmp(cfg.vad_apply_mode, "none") || std::strcmp(cfg.vad_out_mode, "none");
+    const bool vad_file = std::strcmp(cfg.vad_out_mode, "none") != 0;
+    if (!ho.in.empty() || !ho.out.empty()) {
+        if (ho.in.empty() || ho.out.empty()) die("OPTS: Single file mode has to be set at both sides (input and output)!");
+        list.push_back({ho.in, ho.out, "", ho.vad_out});
+    } else {
+        if (ho.list.empty()) die("BATCH: Nothing to do!");
+        std::ifstream lf(ho.list);
+        if (!lf) die("BATCH: Cannot open list file!");
+        std::string line;
+        while (std::getline(lf, line)) {
+            std::vector<std::string> tok;
+            size_t i = 0;
+            while (i < line.size()) {
+                while (i < line.size() && (line[i] == ' ' || line[i] == '\t')) i++;
+                size_t b = i;
+                while (i < line.size() && line[i] != ' ' && line[i] != '\t') i++;
+                if (i > b) tok.push_back(line.substr(b, i - b));
+            }
+            if (tok.size() < 2) die("BATCH: Bad list format!");
+            if (do_vad && tok.size() < 4) die("BATCH: Bad list format!");
+            list.push_back({tok[0], tok[1], tok.size() > 2 ? tok[2] : "", tok.size() > 3 ? tok[3] : ""});
+        }
+    }
+    ctu_handle *h = nullptr;
+    if (ctu_create(&cfg, 0, &h)) die(ctu_last_error(nullptr));
+    const int dim = ctu_feature_dim(h);
+    const bool sig = ctu_is_signal_output(h);
+    Writers W(ho, cfg, dim);
+    std::vector<unsigned char> extvad;
+    size_t ext_pos = 0;
+    if (!std::strcmp(cfg.vadmode, "file")) extvad = slurp(ho.filevad, "NR: Unable to open VAD file!\n");
+    // batches of at most ~1 Gi samples
+    size_t i0 = 0;
+    while (i0 < list.size()) {
+        std::vector<int16_t> pcm;
+        std::vector<int64_t> off{0};
+        size_t i1 = i0;
+        while (i1 < list.size() && pcm.size() < (size_t(1) << 30)) {
+            decode(ho, cfg.fs, list[i1].in, pcm);
+            off.push_back((int64_t)pcm.size());
+            i1++;
+        }
+        const int n = (int)(i1 - i0);
+        std::vector<int64_t> frames(n), rows(n);
+        int64_t total = 0, total_os = 0;
+        for (int u = 0; u < n; u++) {
+            int64_t T = ctu_num_frames(h, off[u + 1] - off[u]);
+            if (T < 0) die("IO: Signal shorter than one frame!");
+            total += T;
+            total_os += ctu_num_output_samples(h, off[u + 1] - off[u]);
+        }
+        std::vector<float> fea(sig ? 0 : (size_t)total * dim);
+        std::vector<int16_t> wav(sig ? (size_t)total_os : 0);
+        std::vector<uint8_t> vout((size_t)total + 1), vnr((size_t)total + 1);
+        const uint8_t *ev = nullptr;
+        if (!extvad.empty() || !std::strcmp(cfg.vadmode, "file")) {
+            if (ext_pos + (size_t)total > extvad.size()) die("NR: Unexpected end of VAD file!");
+            ev = extvad.data() + ext_pos;
+            ext_pos += (size_t)total;
+        }
+        if (ctu_run(h, pcm.data(), off.data(), n, ev, sig ? nullptr : fea.data(), total, sig ? wav.data() : nullptr, total_os, vnr.data(),
+                    vout.data(), frames.data(), rows.data()))
+            die(ctu_last_error(h));
+        int64_t r0 = 0, s0 = 0;
+        for (int u = 0; u < n; u++) {
+            const ListEntry &e = list[i0 + u];
+            if (ho.verbose) std::cerr << "processing: " << e.in << " ";
+            if (sig) {
+                int64_t ns = ctu_num_output_samples(h, off[u + 1] - off[u]);
+                W.waveform(e, wav.data() + s0, ns);
+                s0 += ns;
+            } else {
+                W.features(e, fea.data() + r0 * dim, rows[u]);
+            }
+            if (do_vad && vad_file) W.vad(e, vout.data() + r0, frames[u]);
+            r0 += frames[u];
+            if (ho.verbose) std::cerr << "- " << frames[u] << " frames." << std::endl;
+        }
+        i0 = i1;
+    }
+    W.close();
+    ctu_destroy(h);
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    try {
+        return run(argc, argv);
+    } catch (const std::exception &e) {
+        std::cerr << e.what() << std::endl;
+        return -1;
+    }
+}

@@ -1,0 +1,104 @@
+"""The C++ command-line host (host/ctucopy_b200) against the reference binary's FILES:
+headers, frame counts and container layout byte-exact; payload within the parity
+tolerance; and for the fp64 band-domain path the whole container byte-identical."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+import ref_runner as rr
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "host", "ctucopy_b200")
+
+
+def run_cli(tmp, args, utts, vad_out=False, ext_vad=None):
+    for i, u in enumerate(utts):
+        np.asarray(u).astype("<i2").tofile(os.path.join(tmp, "u%d.raw" % i))
+    if ext_vad is not None:
+        open(os.path.join(tmp, "vadin.bin"), "wb").write(ext_vad)
+    with open(os.path.join(tmp, "list.scp"), "w") as fh:
+        for i in range(len(utts)):
+            fh.write("%s/u%d.raw %s/u%d.out%s\n" % (tmp, i, tmp, i, (" spk %s/u%d.vad" % (tmp, i)) if vad_out else ""))
+    a = [s.replace("{ARK}", os.path.join(tmp, "o.ark")).replace("{PFILE}", os.path.join(tmp, "o.pfile")).replace("{VADIN}", os.path.join(tmp, "vadin.bin"))
+         for s in args]
+    pr = subprocess.run([EXE] + a + ["-S", os.path.join(tmp, "list.scp")], capture_output=True, cwd=tmp)
+    assert pr.returncode == 0, pr.stderr.decode()
+    return pr
+
+
+def test_cli_htk_files(tmp_path):
+    for name, be in (("mfcc30_d_a", "<"), ("mfcc26_be", ">")):
+        c = gu.Case(name)
+        idx = [0, 4, 5]
+        run_cli(str(tmp_path), c.args, [gu.inputs()[i] for i in idx])
+        for j, i in enumerate(idx):
+            got = open(tmp_path / ("u%d.out" % j), "rb").read()
+            want = c.raw[i]
+            assert len(got) == len(want) and got[:12] == want[:12], (name, i)       # header byte-exact
+            a, b = rr.parse_htk(got, be)[1], rr.parse_htk(want, be)[1]
+            assert np.all(np.abs(a - b) <= 1e-4 * np.abs(b) + 1e-3)
+
+
+def test_cli_pfile_band_domain_path_is_byte_identical(tmp_path):
+    c = gu.Case("fwss_file_afterFB_pfile")
+    for i in (0, 4):
+        run_cli(str(tmp_path), c.args, [gu.inputs()[i]], ext_vad=c.extvad[i].tobytes())
+        assert open(tmp_path / "o.pfile", "rb").read() == c.raw[i]
+
+
+def test_cli_ark_scp_and_multi_sentence_pfile(tmp_path):
+    c = gu.Case("plpc_ark")
+    ins = [gu.inputs()[i] for i in (0, 1, 4)]
+    run_cli(str(tmp_path), c.args, ins)
+    ark = open(tmp_path / "o.ark", "rb").read()
+    mats = rr.parse_ark(ark)
+    assert list(mats) == [str(tmp_path / ("u%d.out" % j)) for j in range(3)]
+    scp = open(tmp_path / "o.scp").read().splitlines()
+    for line, key in zip(scp, mats):
+        k, loc = line.split(" ")
+        off = int(loc.rsplit(":", 1)[1])
+        assert k == key and ark[off: off + 5] == b"\x00BFM "
+    for j, i in enumerate((0, 1, 4)):
+        want = c.payload(i)
+        got = mats[str(tmp_path / ("u%d.out" % j))]
+        assert got.shape == want.shape and np.all(np.abs(got - want) <= 1e-4 * np.abs(want) + 1e-3)
+    c = gu.Case("fwss_burg_pfile")
+    run_cli(str(tmp_path), c.args, ins)
+    meta, feat = rr.parse_pfile(open(tmp_path / "o.pfile", "rb").read())
+    T = [c.payload(i).shape[0] for i in (0, 1, 4)]
+    assert list(meta["table"]) == [0, T[0], T[0] + T[1], sum(T)]
+    assert np.array_equal(meta["sent_id"], np.repeat([0, 1, 2], T))
+    want = np.concatenate([c.payload(i) for i in (0, 1, 4)])
+    assert np.all(np.abs(feat - want) <= 1e-4 * np.abs(want) + 1e-3)
+    assert "-num_sentences 3\n" in meta["header"] and ("-num_frames %d\n" % sum(T)) in meta["header"]
+
+
+def test_cli_waveform_and_vad_files(tmp_path):
+    for name in ("exten_raw", "exten_wave_a1"):
+        c = gu.Case(name)
+        run_cli(str(tmp_path), c.args, [gu.inputs()[1]])
+        got = open(tmp_path / "u0.out", "rb").read()
+        want = c.raw[1]
+        assert len(got) == len(want)
+        hdr = 44 if c.kind == "wave" else 0
+        assert got[:hdr] == want[:hdr]
+        d = np.abs(np.frombuffer(got[hdr:], "<i2").astype(int) - np.frombuffer(want[hdr:], "<i2").astype(int))
+        assert d.max() <= 1
+    c = gu.Case("vad_energy_dyn_drop")
+    run_cli(str(tmp_path), c.args, [gu.inputs()[4]], vad_out=True)
+    assert open(tmp_path / "u0.vad", "rb").read() == c.aux[4]                     # '0'/'1' per frame, byte-exact
+    got = open(tmp_path / "u0.out", "rb").read()
+    assert got[:12] == c.raw[4][:12]                                              # nSamples after drop
+
+
+def test_cli_errors_like_the_reference(tmp_path):
+    pr = subprocess.run([EXE, "-fs", "16000", "-preset", "mfcc", "-format_in", "raw", "-format_out", "htk", "-S", "/nonexistent"], capture_output=True)
+    assert pr.returncode == 255 and b"BATCH: Cannot open list file!" in pr.stderr
+    np.zeros(100, "<i2").tofile(tmp_path / "s.raw")
+    (tmp_path / "l.scp").write_text("%s/s.raw %s/s.out\n" % (tmp_path, tmp_path))
+    pr = subprocess.run([EXE, "-fs", "16000", "-preset", "mfcc", "-format_in", "raw", "-format_out", "htk", "-S", str(tmp_path / "l.scp")], capture_output=True)
+    assert pr.returncode == 255 and b"IO: Signal shorter than one frame!" in pr.stderr
