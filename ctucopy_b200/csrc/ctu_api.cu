@@ -67,6 +67,7 @@ struct ctu_plan {
     // workspaces (whole batch)
     float *d_spec = nullptr, *d_fb = nullptr, *d_log = nullptr;
     double *d_fb64 = nullptr;            // band values of the precise path
+    double *d_fea64 = nullptr;           // fp64 copy of the feature matrix (feature-vector VAD criterion)
     double *d_ceps = nullptr;            // Burg cepstra [frames x ncoef]
     double *d_cri = nullptr;             // VAD criterion per frame
     uint8_t *d_flags = nullptr;          // NR-internal detector decisions
@@ -323,6 +324,7 @@ static int build_delta_trap_params(ctu_handle *h) {
         double den = 0;
         for (int i = 1; i <= wins[k]; i++) den += i * i;
         D.inv_den[k] = (float)(1.0 / (2 * den));
+        D.inv_den64[k] = 1.0 / (2 * den);
         halo += wins[k];
     }
     if (n_order > 0 && !c.fea_c0)
@@ -432,6 +434,10 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     if ((st = build_delta_trap_params(h))) return bail(st);
     if ((st = build_nr_params(h->cfg, h->nr_mode, h->vad_src, h->signal_out, h->fb.nb, h->nrp, h->sp, h->bp, h->vp, h->err))) return bail(st);
     h->vp.cri = h->vad_cri; h->vp.thr = h->vad_thr; h->vp.drop = h->vad_drop;
+    // the reference's vector is in internal order (c0 first, a0 first); rows here are in writer order
+    if (h->fea_kind == FEA_DCTC || h->fea_kind == FEA_LPC) h->vp.fea_skip = h->cfg.fea_c0 ? h->static_dim - 1 : -1;
+    else if (h->fea_kind == FEA_LPA) h->vp.fea_skip = -1;
+    else h->vp.fea_skip = 0;
     // the device: fail loudly, there is no CPU path
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -443,6 +449,9 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     if (cudaSetDevice(device) != cudaSuccess) { h->err = "CUDA: cudaSetDevice failed"; return bail(CTU_ERR_CUDA); }
     if ((st = build_fft_tables(h))) return bail(st);
     if (h->nr_mode != NR_NONE && h->cfg.nr_when == 1 && !h->signal_out) h->precise = true;   // subtraction on band values
+    // VAD criterion = distance between feature vectors, fed to threshold state machines whose
+    // decisions must match the reference bit for bit: features in fp64 like the reference's
+    if (h->do_vad && h->vad_cri == VCRI_CEPDIST_FEA) h->precise = true;
     if (h->precise) {
         if ((st = upload(h, &h->d_w64, h->w64)) || (st = upload(h, &h->d_m264, h->m264)) || (st = upload(h, &h->d_lift64, h->lift64))) return bail(st);
     }
@@ -532,6 +541,7 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     if (need_spec && (st = dev_alloc(h, p, &p->d_spec, (size_t)rows * NBIN))) { ctu_plan_destroy(p); return st; }
     if (need_fb && !h->precise && (st = dev_alloc(h, p, &p->d_fb, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     if (need_fb && h->precise && (st = dev_alloc(h, p, &p->d_fb64, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
+    if (h->do_vad && h->vad_cri == VCRI_CEPDIST_FEA && (st = dev_alloc(h, p, &p->d_fea64, (size_t)rows * h->feature_dim))) { ctu_plan_destroy(p); return st; }
     if (h->fea_kind == FEA_TRAPDCT && (st = dev_alloc(h, p, &p->d_log, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     const bool burg_nr = h->nr_mode >= NR_HWSS && h->vad_src == VADSRC_BURG;
     const bool burg_vad = h->do_vad && h->vad_cri == VCRI_CEPDIST_LPC;
@@ -550,7 +560,7 @@ void ctu_plan_destroy(ctu_plan *p) {
     cudaSetDevice(p->h->device);
     cudaFree(p->d_pcm_off); cudaFree(p->d_row_off); cudaFree(p->d_osamp_off); cudaFree(p->d_t32_off); cudaFree(p->d_t64_off);
     cudaFree(p->d_nframes); cudaFree(p->d_tiles32); cudaFree(p->d_tiles64);
-    cudaFree(p->d_spec); cudaFree(p->d_fb); cudaFree(p->d_fb64); cudaFree(p->d_log); cudaFree(p->d_ceps); cudaFree(p->d_cri);
+    cudaFree(p->d_spec); cudaFree(p->d_fb); cudaFree(p->d_fb64); cudaFree(p->d_fea64); cudaFree(p->d_log); cudaFree(p->d_ceps); cudaFree(p->d_cri);
     cudaFree(p->d_flags); cudaFree(p->d_keep); cudaFree(p->d_vad0); cudaFree(p->d_rows);
     cudaFree(p->d_pcm); cudaFree(p->d_wave); cudaFree(p->d_fea); cudaFree(p->d_ext); cudaFree(p->d_vadnr_out); cudaFree(p->d_vad_out);
     delete p;
@@ -700,17 +710,22 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     if (kind == KIND_TRAPLOG) { fea_dst = p->d_log; od = h->fb.nb; ostride = h->fb.nb; }
     P = h->fp; P.out_dim = od; P.out_stride = ostride;
     if (h->precise) {
-        // fp64 path (ctu_precise.cuh): band-domain noise reduction / ill-conditioned LPC
+        // fp64 path (ctu_precise.cuh): band-domain noise reduction / ill-conditioned LPC /
+        // features that feed VAD decisions
         Tables64 t64{h->d_tw256d, h->d_twsplitd, h->d_wind, h->d_w64, h->d_m264, h->d_lift64};
-        if (nr_on) {
+        double *f64 = (kind == KIND_TRAPLOG) ? nullptr : p->d_fea64;
+        if (nr_on && !before) {
             const uint8_t *fl = (h->nr_mode >= NR_HWSS) ? d_ext : nullptr;
             if (h->nr_mode >= NR_HWSS && !fl) return fail(h, CTU_ERR_INPUT, "NR: Unable to open VAD file!\n");
-            if ((st = launch_frames64_t<SRC64_PCM, DST64_FB, KIND_SPEC>(P, bd32, t64, r.t32_n, d_pcm, nullptr, p->d_fb64, nullptr, s, &h->lc, h->err))) return st;
+            if ((st = launch_frames64_t<SRC64_PCM, DST64_FB, KIND_SPEC>(P, bd32, t64, r.t32_n, d_pcm, nullptr, nullptr, p->d_fb64, nullptr, s, &h->lc, h->err))) return st;
             if ((st = launch_nr_scan64(h->nrp, p->d_nframes, p->d_row_off, r.u0, r.u1, h->fb.nb, p->d_fb64, fl, s, &h->lc, h->err))) return st;
             if (d_vadnr && fl) CK(cudaMemcpyAsync(d_vadnr + r.row0, d_ext + r.row0, r.nrows, cudaMemcpyDeviceToDevice, s));
-            if ((st = launch_frames64_k<SRC64_FB, DST64_FEA>(kind, P, bd32, t64, r.t32_n, nullptr, p->d_fb64, nullptr, fea_dst, s, &h->lc, h->err))) return st;
+            if ((st = launch_frames64_k<SRC64_FB, DST64_FEA>(kind, P, bd32, t64, r.t32_n, nullptr, p->d_fb64, nullptr, f64, fea_dst, s, &h->lc, h->err))) return st;
+        } else if (nr_on && before) {
+            // noise-reduced fp32 spectrum (stage 1) is the source
+            if ((st = launch_frames64_k<SRC64_SPEC, DST64_FEA>(kind, P, bd32, t64, r.t32_n, nullptr, nullptr, p->d_spec, f64, fea_dst, s, &h->lc, h->err))) return st;
         } else {
-            if ((st = launch_frames64_k<SRC64_PCM, DST64_FEA>(kind, P, bd32, t64, r.t32_n, d_pcm, nullptr, nullptr, fea_dst, s, &h->lc, h->err))) return st;
+            if ((st = launch_frames64_k<SRC64_PCM, DST64_FEA>(kind, P, bd32, t64, r.t32_n, d_pcm, nullptr, nullptr, f64, fea_dst, s, &h->lc, h->err))) return st;
         }
     } else if (kind == KIND_LPA || kind == KIND_LPC) {
         // band values to HBM (76 B per frame for PLP), then one thread per frame for the recursion
@@ -739,16 +754,23 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     }
     if (h->dp.n_order > 0 && r.t64_n > 0) {
         size_t bytes = (size_t)2 * h->dp.span_max * h->dp.blk * sizeof(float);
-        CK(cudaFuncSetAttribute(k_delta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        CK(cudaFuncSetAttribute(k_delta<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         h->lc.begin("k_delta", s);
-        k_delta<<<(unsigned)r.t64_n, 256, bytes, s>>>(h->dp, bd64, DELTA_ROWS, d_fea);
+        k_delta<float><<<(unsigned)r.t64_n, 256, bytes, s>>>(h->dp, bd64, DELTA_ROWS, d_fea);
         h->lc.end(s);
         CK(cudaGetLastError());
+        if (p->d_fea64) {
+            CK(cudaFuncSetAttribute(k_delta<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * bytes)));
+            h->lc.begin("k_delta64", s);
+            k_delta<double><<<(unsigned)r.t64_n, 256, 2 * bytes, s>>>(h->dp, bd64, DELTA_ROWS, p->d_fea64);
+            h->lc.end(s);
+            CK(cudaGetLastError());
+        }
     }
     // ---- stage 4: VAD module -----------------------------------------------------------------
     if (h->do_vad) {
         if ((st = launch_vad_module(h->vp, h->bp, bd32, r.t32_n, p->d_nframes, p->d_row_off, r.u0, r.u1, r.row0, r.nrows, d_pcm, p->d_spec, d_fea,
-                                    h->feature_dim, p->d_ceps, p->d_cri, p->d_vad0, d_vadout, p->d_keep, p->d_rows, h->d_tw256d, h->d_twsplitd,
+                                    p->d_fea64, h->feature_dim, p->d_ceps, p->d_cri, p->d_vad0, d_vadout, p->d_keep, p->d_rows, h->d_tw256d, h->d_twsplitd,
                                     h->d_twinvd, h->d_wind, s, &h->lc, h->err))) return st;
     }
     return CTU_OK;

@@ -522,15 +522,18 @@ struct DeltaParams {
     int n_order;
     int win[3];
     float inv_den[3];
+    double inv_den64[3];
     int blk;          // columns per block (ncep+1 incl. c0 position)
     int stride;       // floats per row
     int span_max;     // tile_rows + 2 * sum(win): rows of one staging buffer
 };
 constexpr int DELTA_ROWS = 64;
 
+template <class E>
 __global__ void __launch_bounds__(256)
-k_delta(const __grid_constant__ DeltaParams D, BatchDesc bd, int tile_rows, float *__restrict__ fea) {
-    extern __shared__ __align__(16) float sm[];
+k_delta(const __grid_constant__ DeltaParams D, BatchDesc bd, int tile_rows, E *__restrict__ fea) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    E *sm = reinterpret_cast<E *>(sm_raw);
     const int2 tile = bd.tiles[blockIdx.x];
     const int u = tile.x, t0 = tile.y;
     const int T = bd.nframes[u];
@@ -540,8 +543,8 @@ k_delta(const __grid_constant__ DeltaParams D, BatchDesc bd, int tile_rows, floa
     int halo = 0;
     for (int k = 0; k < D.n_order; k++) halo += D.win[k];
     const int span = nr + 2 * halo;                       // rows t0-halo .. t0+nr+halo-1 (clamped)
-    float *cur = sm;                                      // [span][blk]
-    float *nxt = sm + D.span_max * blk;
+    E *cur = sm;                                          // [span][blk]
+    E *nxt = sm + D.span_max * blk;
     for (int i = threadIdx.x; i < span * blk; i += blockDim.x) {
         int r = i / blk, col = i - r * blk;
         int t = min(max(t0 - halo + r, 0), T - 1);
@@ -558,18 +561,18 @@ k_delta(const __grid_constant__ DeltaParams D, BatchDesc bd, int tile_rows, floa
             int t = t0 - hn + r;                          // absolute row of this output
             int tc = min(max(t, 0), T - 1);               // replicated edge: value of the clamped row
             // window rows around tc, each clamped to [0, T-1]; position in `cur` = row - (t0 - h)
-            float acc = 0.f;
+            E acc = 0;
             for (int j = 1; j <= W; j++) {
                 int tp = min(tc + j, T - 1), tm = max(tc - j, 0);
-                acc += (float)j * (cur[(tp - (t0 - h)) * blk + col] - cur[(tm - (t0 - h)) * blk + col]);
+                acc += (E)j * (cur[(tp - (t0 - h)) * blk + col] - cur[(tm - (t0 - h)) * blk + col]);
             }
-            float v = acc * D.inv_den[k];
-            if (W == 1 && tc == T - 1) v = 0.f;           // reference quirk for win == 1 (see oracle)
+            E v = acc * (sizeof(E) == 8 ? (E)D.inv_den64[k] : (E)D.inv_den[k]);
+            if (W == 1 && tc == T - 1) v = 0;           // reference quirk for win == 1 (see oracle)
             nxt[i] = v;
             if (t >= t0 && t < t0 + nr) fea[(row0 + t) * D.stride + (k + 1) * blk + col] = v;
         }
         __syncthreads();
-        float *tmp = cur; cur = nxt; nxt = tmp;
+        E *tmp = cur; cur = nxt; nxt = tmp;
         h = hn;
     }
 }

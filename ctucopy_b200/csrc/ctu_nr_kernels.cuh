@@ -64,6 +64,8 @@ struct VadParams {
     int latency;         // rows between a feature row and the spectrum frame the VAD sees
     int order;           // majority filter length
     int cep_n;           // length of the cepstral vector (lpc: vad_lpc_coefs, fea: feature dim)
+    int fea_skip;        // fea criterion: WRITER column holding the reference's internal element 0 (left out of the
+                         // distance, src/vad/vad.cc:262-272), or -1 when that element is not written at all
     int cep_init; double cep_p;
     double abs_thr;
     int perc_init; double perc_thr;
@@ -547,7 +549,7 @@ __global__ void k_vad_energy(const __grid_constant__ VadParams V, const float *_
 // thresholds + background update + majority filter, one thread per utterance
 __global__ void k_vad_scan(const __grid_constant__ VadParams V, const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int u0,
                            int n_utts, const double *__restrict__ cri_frame, const double *__restrict__ ceps,
-                           const float *__restrict__ fea, int fea_dim, uint8_t *__restrict__ vad0_tmp, uint8_t *__restrict__ vad_out,
+                           const double *__restrict__ fea, int fea_dim, uint8_t *__restrict__ vad0_tmp, uint8_t *__restrict__ vad_out,
                            uint8_t *__restrict__ keep) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_utts) return;
@@ -566,13 +568,13 @@ __global__ void k_vad_scan(const __grid_constant__ VadParams V, const int *__res
             // cepstral distance to the running background c0 (src/vad/vad.cc:249-276)
             double sum = 0;
             if (r == 0) {
-                for (int k = 0; k < cn; k++) c0[k] = (V.cri == VCRI_CEPDIST_LPC) ? ceps[fidx * BURG_MAXC + k] : (double)fea[(R0 + r) * fea_dim + k];
+                for (int k = 0; k < cn; k++) c0[k] = (V.cri == VCRI_CEPDIST_LPC) ? ceps[fidx * BURG_MAXC + k] : fea[(R0 + r) * fea_dim + k];
                 c = 0.0;
             } else {
                 for (int k = 0; k < cn; k++) {
-                    double ci = (V.cri == VCRI_CEPDIST_LPC) ? ceps[fidx * BURG_MAXC + k] : (double)fea[(R0 + r) * fea_dim + k];
+                    double ci = (V.cri == VCRI_CEPDIST_LPC) ? ceps[fidx * BURG_MAXC + k] : fea[(R0 + r) * fea_dim + k];
                     if (r == 1) c0[k] = (c0[k] + ci) / 2.0;
-                    if (k >= 1) { double d = ci - c0[k]; sum += d * d; }
+                    if ((V.cri == VCRI_CEPDIST_LPC) ? (k >= 1) : (k != V.fea_skip)) { double d = ci - c0[k]; sum += d * d; }
                 }
                 c = 4.3429 * sqrt(2 * sum);
             }
@@ -614,7 +616,7 @@ __global__ void k_vad_scan(const __grid_constant__ VadParams V, const int *__res
         vad0_tmp[R0 + r] = v ? 1 : 0;
         if (V.cri != VCRI_ENERGY && !(v && r > V.cep_init)) {
             for (int k = 0; k < cn; k++) {
-                double ci = (V.cri == VCRI_CEPDIST_LPC) ? ceps[fidx * BURG_MAXC + k] : (double)fea[(R0 + r) * fea_dim + k];
+                double ci = (V.cri == VCRI_CEPDIST_LPC) ? ceps[fidx * BURG_MAXC + k] : fea[(R0 + r) * fea_dim + k];
                 c0[k] = V.cep_p * c0[k] + (1.0 - V.cep_p) * ci;
             }
         }
@@ -827,7 +829,8 @@ static inline int launch_synth(const SynthParams &S, const FrameParams &F, const
 
 static inline int launch_vad_module(VadParams V, const BurgParams &B, const BatchDesc &bd32, int64_t nt32, const int *d_nframes,
                                     const int64_t *d_row_off, int u0, int u1, int64_t row0, int64_t nrows, const int16_t *d_pcm,
-                                    const float *d_spec, float *d_fea, int fea_dim, double *d_ceps, double *d_cri, uint8_t *d_vad0,
+                                    const float *d_spec, float *d_fea, const double *d_fea64, int fea_dim, double *d_ceps, double *d_cri,
+                                    uint8_t *d_vad0,
                                     uint8_t *d_vadout, uint8_t *d_keep, int *d_rows, const double2 *tw, const double2 *ts,
                                     const double2 *ti, const double *win, cudaStream_t s, LaunchCtx *lc, std::string &err) {
     const int n = u1 - u0;
@@ -848,11 +851,12 @@ static inline int launch_vad_module(VadParams V, const BurgParams &B, const Batc
         if (st) return st;
     } else {
         V.cep_n = fea_dim;
+        if (!d_fea64) { err = "CTU: internal: fp64 feature matrix missing for the cepstral-distance VAD"; return CTU_ERR_CONFIG; }
     }
     if (V.cep_n > 64) { err = "CTU: cepstral-distance VAD supports vectors of up to 64 values"; return CTU_ERR_UNSUPPORTED; }
     if (e == cudaSuccess) {
         lc->begin("k_vad_scan", s);
-        k_vad_scan<<<(n + 63) / 64, 64, 0, s>>>(V, d_nframes, d_row_off, u0, n, d_cri, d_ceps, d_fea, fea_dim, d_vad0, d_vadout, d_keep);
+        k_vad_scan<<<(n + 63) / 64, 64, 0, s>>>(V, d_nframes, d_row_off, u0, n, d_cri, d_ceps, d_fea64, fea_dim, d_vad0, d_vadout, d_keep);
         lc->end(s);
         e = cudaGetLastError();
     }

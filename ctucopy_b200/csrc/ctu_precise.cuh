@@ -20,7 +20,7 @@ namespace ctu {
 constexpr int P64_THREADS = 128;
 constexpr int P64_GROUPS = P64_THREADS / GROUP;
 constexpr int P64_ROW = 264;          // doubles per spectrum row
-enum { SRC64_PCM = 0, SRC64_FB = 1 };
+enum { SRC64_PCM = 0, SRC64_FB = 1, SRC64_SPEC = 2 };
 enum { DST64_FB = 0, DST64_FEA = 1 };
 
 struct Tables64 {
@@ -34,7 +34,7 @@ struct Tables64 {
 template <int SRC, int DST, int KIND>
 __global__ void __launch_bounds__(P64_THREADS)
 k_frames64(const __grid_constant__ FrameParams P, BatchDesc bd, Tables64 tb, const int16_t *__restrict__ pcm, const double *__restrict__ src,
-           double *__restrict__ dst64, float *__restrict__ dst) {
+           const float *__restrict__ spec, double *__restrict__ dst64, float *__restrict__ dst) {
     extern __shared__ __align__(16) double smd[];
     const int tid = threadIdx.x;
     const int w = P.window, s = P.wshift, nb = P.nb;
@@ -63,6 +63,11 @@ k_frames64(const __grid_constant__ FrameParams P, BatchDesc bd, Tables64 tb, con
     for (int pass = 0; pass < TILE_F / P64_GROUPS; pass++) {
         const int f = pass * P64_GROUPS + grp;
         const bool active = f < nf;
+        if (SRC == SRC64_SPEC) {
+            // (noise-reduced) fp32 spectrum from HBM, widened
+            if (active) for (int k = c; k < NBIN; k += GROUP) pr[k] = (double)spec[(row0 + f) * NBIN + k];
+            __syncwarp();
+        }
         if (SRC == SRC64_PCM) {
             cpx<double> a[16];
             if (active) {
@@ -117,6 +122,8 @@ k_frames64(const __grid_constant__ FrameParams P, BatchDesc bd, Tables64 tb, con
                 }
             }
             __syncwarp();
+        }
+        if (SRC == SRC64_PCM || SRC == SRC64_SPEC) {
             // filter bank: bands dealt round-robin to the group's threads, sequential sum
             // over the taps in the reference's order (src/fea/fb.cc:76-83)
             if (active) {
@@ -214,14 +221,16 @@ static inline size_t p64_smem_bytes() {
 
 template <int SRC, int DST, int KIND>
 static int launch_frames64_t(const FrameParams &P, const BatchDesc &bd, const Tables64 &tb, int64_t ntiles, const int16_t *pcm,
-                             const double *src, double *dst64, float *dst, cudaStream_t s, LaunchCtx *lc, std::string &err) {
+                             const double *src, const float *spec, double *dst64, float *dst, cudaStream_t s, LaunchCtx *lc,
+                             std::string &err) {
     if (ntiles <= 0) return CTU_OK;
     size_t bytes = p64_smem_bytes();
     auto kern = k_frames64<SRC, DST, KIND>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e == cudaSuccess) {
-        lc->begin(SRC == SRC64_PCM ? (DST == DST64_FB ? "k_frames64<pcm,fb>" : "k_frames64<pcm,fea>") : "k_frames64<fb,fea>", s);
-        kern<<<(unsigned)ntiles, P64_THREADS, bytes, s>>>(P, bd, tb, pcm, src, dst64, dst);
+        lc->begin(SRC == SRC64_PCM ? (DST == DST64_FB ? "k_frames64<pcm,fb>" : "k_frames64<pcm,fea>")
+                  : SRC == SRC64_SPEC ? (DST == DST64_FB ? "k_frames64<spec,fb>" : "k_frames64<spec,fea>") : "k_frames64<fb,fea>", s);
+        kern<<<(unsigned)ntiles, P64_THREADS, bytes, s>>>(P, bd, tb, pcm, src, spec, dst64, dst);
         lc->end(s);
         e = cudaGetLastError();
     }
@@ -231,14 +240,15 @@ static int launch_frames64_t(const FrameParams &P, const BatchDesc &bd, const Ta
 
 template <int SRC, int DST>
 static int launch_frames64_k(int kind, const FrameParams &P, const BatchDesc &bd, const Tables64 &tb, int64_t nt, const int16_t *pcm,
-                             const double *src, double *dst64, float *dst, cudaStream_t s, LaunchCtx *lc, std::string &err) {
+                             const double *src, const float *spec, double *dst64, float *dst, cudaStream_t s, LaunchCtx *lc,
+                             std::string &err) {
     switch (kind) {
-        case KIND_SPEC: return launch_frames64_t<SRC, DST, KIND_SPEC>(P, bd, tb, nt, pcm, src, dst64, dst, s, lc, err);
-        case KIND_LOGSPEC: return launch_frames64_t<SRC, DST, KIND_LOGSPEC>(P, bd, tb, nt, pcm, src, dst64, dst, s, lc, err);
-        case KIND_DCTC: return launch_frames64_t<SRC, DST, KIND_DCTC>(P, bd, tb, nt, pcm, src, dst64, dst, s, lc, err);
-        case KIND_LPA: return launch_frames64_t<SRC, DST, KIND_LPA>(P, bd, tb, nt, pcm, src, dst64, dst, s, lc, err);
-        case KIND_LPC: return launch_frames64_t<SRC, DST, KIND_LPC>(P, bd, tb, nt, pcm, src, dst64, dst, s, lc, err);
-        case KIND_TRAPLOG: return launch_frames64_t<SRC, DST, KIND_TRAPLOG>(P, bd, tb, nt, pcm, src, dst64, dst, s, lc, err);
+        case KIND_SPEC: return launch_frames64_t<SRC, DST, KIND_SPEC>(P, bd, tb, nt, pcm, src, spec, dst64, dst, s, lc, err);
+        case KIND_LOGSPEC: return launch_frames64_t<SRC, DST, KIND_LOGSPEC>(P, bd, tb, nt, pcm, src, spec, dst64, dst, s, lc, err);
+        case KIND_DCTC: return launch_frames64_t<SRC, DST, KIND_DCTC>(P, bd, tb, nt, pcm, src, spec, dst64, dst, s, lc, err);
+        case KIND_LPA: return launch_frames64_t<SRC, DST, KIND_LPA>(P, bd, tb, nt, pcm, src, spec, dst64, dst, s, lc, err);
+        case KIND_LPC: return launch_frames64_t<SRC, DST, KIND_LPC>(P, bd, tb, nt, pcm, src, spec, dst64, dst, s, lc, err);
+        case KIND_TRAPLOG: return launch_frames64_t<SRC, DST, KIND_TRAPLOG>(P, bd, tb, nt, pcm, src, spec, dst64, dst, s, lc, err);
     }
     err = "CTU: bad kind";
     return CTU_ERR_CONFIG;
