@@ -19,6 +19,7 @@
 #include <iostream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../include/ctucopy_b200.h"
@@ -28,6 +29,12 @@ namespace {
 struct HostOpts {
     std::string list, in, out, config, format_in, format_out_arg, pfilename, arkfilename, filevad, vad_out;
     bool big_in = false, big_out = false, verbose = false, quiet = false, fb_printself = false;
+    // multi-GPU extensions (not in the reference)
+    int gpus = 1;                 // -gpus N    : N worker threads in this process, one handle per GPU
+    int shard_r = 0, shard_n = 1; // -shard r/N : this process handles shard r of N (one process per GPU)
+    int merge_n = 0;              // -merge N   : merge the pfile / ark+scp shards of N finished `-shard` runs
+    int device = -1;              // -device d  : CUDA device (default: shard index modulo device count)
+    std::string ark_ref;          // ark path recorded in scp lines (the merged file's name)
 };
 
 struct ListEntry { std::string in, out, spk, vadout; };
@@ -110,6 +117,8 @@ std::string ark_to_scp(const std::string &ark) {
     return line + "scp";
 }
 
+std::string pfile_header(uint64_t nsent, uint64_t frames, uint64_t dim);
+
 struct Writers {
     const HostOpts &o;
     const ctu_config &c;
@@ -180,7 +189,7 @@ struct Writers {
             std::fprintf(ark, "%c", 4);
             std::fwrite(&cols, 4, 1, ark);
             long long idx = (long long)std::ftell(ark) - 15;
-            std::fprintf(scp, "%s %s:%llu\n", e.out.c_str(), o.arkfilename.c_str(), (unsigned long long)idx);
+            std::fprintf(scp, "%s %s:%llu\n", e.out.c_str(), (o.ark_ref.empty() ? o.arkfilename : o.ark_ref).c_str(), (unsigned long long)idx);
             std::fwrite(rows, 4, (size_t)n * dim, ark);
         }
     }
@@ -214,21 +223,9 @@ struct Writers {
     void close() {
         if (pf) {
             // sentence table right behind the data, then the ASCII header (src/io/pfile.cc:435-468, 573-592)
-            uint64_t ncol = (uint64_t)dim + 2, nsent = sent_table.size() - 1;
+            uint64_t nsent = sent_table.size() - 1;
             for (uint32_t v : sent_table) { uint32_t b = bswap32(v); std::fwrite(&b, 4, 1, pf); }
-            std::string h;
-            auto num = [](uint64_t v) { return std::to_string((unsigned long long)v); };
-            h += "-pfile_header version 0 size 32768\n";
-            h += "-num_sentences " + num(nsent) + "\n";
-            h += "-num_frames " + num(pf_frames) + "\n";
-            h += "-first_feature_column 2\n";
-            h += "-num_features " + num((uint64_t)dim) + "\n";
-            h += "-first_label_column " + num((uint64_t)dim + 2) + "\n";
-            h += "-num_labels 0\n";
-            h += "-format dd" + std::string((size_t)dim, 'f') + "\n";
-            h += "-data size " + num(ncol * pf_frames) + " offset 0 ndim 2 nrow " + num(pf_frames) + " ncol " + num(ncol) + "\n";
-            h += "-sent_table_data size " + num(nsent + 1) + " offset " + num(ncol * pf_frames) + " ndim 1\n";
-            h += "-end\n";
+            std::string h = pfile_header(nsent, pf_frames, (uint64_t)dim);
             std::fseek(pf, 0, SEEK_SET);
             std::fwrite(h.data(), 1, h.size(), pf);
             std::fclose(pf); pf = nullptr;
@@ -257,86 +254,172 @@ void take_host_option(HostOpts &o, const char *l, const char *r) {
     else if (opt == "-v" || opt == "-verbose") { o.verbose = true; o.quiet = false; }
     else if (opt == "-quiet") { o.quiet = true; o.verbose = false; }
     else if (opt == "-fb_printself") o.fb_printself = true;
+    else if (opt == "-gpus" && r) o.gpus = std::max(1, std::atoi(r));
+    else if (opt == "-device" && r) o.device = std::atoi(r);
+    else if (opt == "-merge" && r) o.merge_n = std::atoi(r);
+    else if (opt == "-shard" && r) {
+        if (std::sscanf(r, "%d/%d", &o.shard_r, &o.shard_n) != 2 || o.shard_n < 1 || o.shard_r < 0 || o.shard_r >= o.shard_n)
+            die("OPTS: -shard takes r/N with 0 <= r < N");
+    }
 }
 
-int run(int argc, char **argv) {
-    if (argc == 1) { std::cerr << "usage: ctucopy_b200 <ctucopy options> -S <list>   (see man/ctucopy4 of the reference)" << std::endl; die("OPTS: No command line options!"); }
-    ctu_config cfg;
-    ctu_config_init(&cfg);
-    HostOpts ho;
-    // host-owned options: config file first, then the command line (same order as the library's parser)
-    for (int j = 1; j + 1 < argc; j++) {
-        if (std::strcmp(argv[j], "-C")) continue;
-        std::ifstream cf(argv[j + 1]);
-        std::string line;
-        while (std::getline(cf, line)) {
-            size_t h = line.find('#');
-            if (h != std::string::npos) line.resize(h);
-            char a[1024] = "", b[1024] = "";
-            int n = std::sscanf(line.c_str(), "%1023s %1023s", a, b);
-            if (n >= 1) take_host_option(ho, a, n >= 2 ? b : nullptr);
+bool is_host_extension(const char *opt) {
+    return !std::strcmp(opt, "-gpus") || !std::strcmp(opt, "-device") || !std::strcmp(opt, "-merge") || !std::strcmp(opt, "-shard");
+}
+
+// samples a file will decode to, from its size / header only (used to balance shards and to
+// place each shard inside a list-wide external VAD file)
+int64_t count_samples(const HostOpts &o, const std::string &path) {
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) die(o.format_in == "wave" ? "IN: Cannot open file!" : "IN: Cannot open data file!");
+    std::fseek(f, 0, SEEK_END);
+    int64_t size = (int64_t)std::ftell(f), n = 0;
+    if (o.format_in == "raw") n = size / 2;
+    else if (o.format_in == "alaw" || o.format_in == "mulaw") n = size;
+    else if (o.format_in == "wave") {
+        unsigned char b[44] = {0};
+        std::fseek(f, 0, SEEK_SET);
+        if (std::fread(b, 1, 44, f) == 44) {
+            int64_t d = (int64_t)((uint32_t)b[40] | ((uint32_t)b[41] << 8) | ((uint32_t)b[42] << 16) | ((uint32_t)b[43] << 24));
+            n = std::min<int64_t>(d / 2, (size - 44) / 2);
         }
     }
-    for (int j = 1; j < argc; j++) {
-        if (argv[j][0] != '-') continue;
-        const char *r = (j + 1 < argc && argv[j + 1][0] != '-') ? argv[j + 1] : nullptr;
-        take_host_option(ho, argv[j], r);
+    std::fclose(f);
+    return n;
+}
+
+// "<dir>/shard<r>of<n>_<file>": the prefix keeps the ".ark" token where ark_to_scp expects it
+std::string shard_name(const std::string &base, int r, int n) {
+    size_t sl = base.rfind('/');
+    std::string dir = sl == std::string::npos ? "" : base.substr(0, sl + 1), file = sl == std::string::npos ? base : base.substr(sl + 1);
+    return dir + "shard" + std::to_string(r) + "of" + std::to_string(n) + "_" + file;
+}
+
+// contiguous ranges of list lines, balanced by cumulative sample count
+std::vector<size_t> partition(const std::vector<int64_t> &samples, int n) {
+    std::vector<size_t> cut(n + 1, samples.size());
+    cut[0] = 0;
+    long double total = 0, acc = 0;
+    for (int64_t v : samples) total += (long double)v;
+    int r = 1;
+    for (size_t i = 0; i < samples.size() && r < n; i++) {
+        acc += (long double)samples[i];
+        while (r < n && acc >= total * r / n) cut[r++] = i + 1;
     }
-    if (ctu_config_parse(&cfg, argc - 1, (const char *const *)(argv + 1))) die(ctu_config_error());
-    if (ho.fb_printself) {
-        int32_t nb = 0;
-        if (ctu_design_filter_bank(&cfg, nullptr, nullptr, nullptr, &nb)) die(ctu_last_error(nullptr));
-        std::vector<double> mat((size_t)nb * cfg.wfftby2);
-        std::vector<int32_t> lo(nb), hi(nb);
-        ctu_design_filter_bank(&cfg, mat.data(), lo.data(), hi.data(), &nb);
-        for (int b = 0; b < nb; b++) { for (int i = 0; i < cfg.wfftby2; i++) std::cerr << mat[(size_t)b * cfg.wfftby2 + i] << "\t"; std::cerr << std::endl; }
+    return cut;
+}
+
+std::vector<unsigned char> slurp_or_empty(const std::string &path) {
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) die("MERGE: missing shard file " + path);
+    std::fclose(f);
+    return slurp(path, "MERGE: cannot read shard");
+}
+
+// Kaldi ark + scp: byte concatenation, scp offsets shifted by the bytes that precede the shard
+void merge_ark(const std::string &ark, int n) {
+    const std::string scp = ark_to_scp(ark);
+    FILE *fa = std::fopen(ark.c_str(), "wb"), *fs = std::fopen(scp.c_str(), "wt");
+    if (!fa || !fs) die("MERGE: cannot create " + ark);
+    unsigned long long base = 0;
+    for (int r = 0; r < n; r++) {
+        auto b = slurp_or_empty(shard_name(ark, r, n));
+        std::ifstream sl(ark_to_scp(shard_name(ark, r, n)));
+        std::string line;
+        while (std::getline(sl, line)) {
+            size_t c = line.rfind(':');
+            if (c == std::string::npos) continue;
+            unsigned long long off = std::strtoull(line.c_str() + c + 1, nullptr, 10);
+            std::fprintf(fs, "%s:%llu\n", line.substr(0, c).c_str(), off + base);
+        }
+        std::fwrite(b.data(), 1, b.size(), fa);
+        base += b.size();
+        std::remove(shard_name(ark, r, n).c_str());
+        std::remove(ark_to_scp(shard_name(ark, r, n)).c_str());
     }
-    // the list (single-file mode is one list line)
-    std::vector<ListEntry> list;
+    std::fclose(fa); std::fclose(fs);
+}
+
+std::string pfile_header(uint64_t nsent, uint64_t frames, uint64_t dim) {
+    // ASCII header of an ICSI pfile as the reference writes it (src/io/pfile.cc:435-468)
+    auto num = [](uint64_t v) { return std::to_string((unsigned long long)v); };
+    const uint64_t ncol = dim + 2;
+    std::string h;
+    h += "-pfile_header version 0 size 32768\n";
+    h += "-num_sentences " + num(nsent) + "\n";
+    h += "-num_frames " + num(frames) + "\n";
+    h += "-first_feature_column 2\n";
+    h += "-num_features " + num(dim) + "\n";
+    h += "-first_label_column " + num(dim + 2) + "\n";
+    h += "-num_labels 0\n";
+    h += "-format dd" + std::string((size_t)dim, 'f') + "\n";
+    h += "-data size " + num(ncol * frames) + " offset 0 ndim 2 nrow " + num(frames) + " ncol " + num(ncol) + "\n";
+    h += "-sent_table_data size " + num(nsent + 1) + " offset " + num(ncol * frames) + " ndim 1\n";
+    h += "-end\n";
+    return h;
+}
+
+// pfile: rows concatenated with the sentence id rewritten, sentence table rebuilt
+void merge_pfile(const std::string &pf, int n) {
+    FILE *fo = std::fopen(pf.c_str(), "wb");
+    if (!fo) die("MERGE: cannot create " + pf);
+    std::vector<char> z(32768, 0);
+    std::fwrite(z.data(), 1, z.size(), fo);
+    std::vector<uint32_t> table{0};
+    uint64_t frames = 0, dim = 0;
+    for (int r = 0; r < n; r++) {
+        auto b = slurp_or_empty(shard_name(pf, r, n));
+        if (b.size() < 32768) die("MERGE: short pfile shard");
+        std::string head((const char *)b.data(), 32768);
+        auto field = [&](const char *key) -> uint64_t {
+            size_t p = head.find(key);
+            if (p == std::string::npos) die(std::string("MERGE: pfile shard lacks ") + key);
+            return std::strtoull(head.c_str() + p + std::strlen(key), nullptr, 10);
+        };
+        const uint64_t ns = field("-num_sentences "), nf = field("-num_frames "), d = field("-num_features ");
+        if (r && d != dim) die("MERGE: pfile shards differ in feature count");
+        dim = d;
+        const size_t ncol = (size_t)dim + 2;
+        if (b.size() < 32768 + 4 * (ncol * nf + ns + 1)) die("MERGE: truncated pfile shard");
+        uint32_t *rows = reinterpret_cast<uint32_t *>(b.data() + 32768);
+        const uint32_t sent0 = (uint32_t)table.size() - 1;
+        for (uint64_t t = 0; t < nf; t++) rows[t * ncol] = bswap32(bswap32(rows[t * ncol]) + sent0);
+        std::fwrite(rows, 4, ncol * nf, fo);
+        const uint32_t *st = rows + ncol * nf;
+        for (uint64_t k = 1; k <= ns; k++) table.push_back((uint32_t)frames + bswap32(st[k]));
+        frames += nf;
+        std::remove(shard_name(pf, r, n).c_str());
+    }
+    for (uint32_t v : table) { uint32_t x = bswap32(v); std::fwrite(&x, 4, 1, fo); }
+    std::string h = pfile_header(table.size() - 1, frames, dim);
+    std::fseek(fo, 0, SEEK_SET);
+    std::fwrite(h.data(), 1, h.size(), fo);
+    std::fclose(fo);
+}
+
+// One contiguous range [i0, i1) of the list on one device: decode -> C ABI -> writers.
+// frame0 = frames of all list lines before i0 (position inside a list-wide external VAD file).
+void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<ListEntry> &list, size_t i0, size_t i1, int device,
+                   const std::vector<unsigned char> &extvad, size_t frame0) {
     const bool do_vad = std::strcmp(cfg.vad_apply_mode, "none") || std::strcmp(cfg.vad_out_mode, "none");
     const bool vad_file = std::strcmp(cfg.vad_out_mode, "none") != 0;
-    if (!ho.in.empty() || !ho.out.empty()) {
-        if (ho.in.empty() || ho.out.empty()) die("OPTS: Single file mode has to be set at both sides (input and output)!");
-        list.push_back({ho.in, ho.out, "", ho.vad_out});
-    } else {
-        if (ho.list.empty()) die("BATCH: Nothing to do!");
-        std::ifstream lf(ho.list);
-        if (!lf) die("BATCH: Cannot open list file!");
-        std::string line;
-        while (std::getline(lf, line)) {
-            std::vector<std::string> tok;
-            size_t i = 0;
-            while (i < line.size()) {
-                while (i < line.size() && (line[i] == ' ' || line[i] == '\t')) i++;
-                size_t b = i;
-                while (i < line.size() && line[i] != ' ' && line[i] != '\t') i++;
-                if (i > b) tok.push_back(line.substr(b, i - b));
-            }
-            if (tok.size() < 2) die("BATCH: Bad list format!");
-            if (do_vad && tok.size() < 4) die("BATCH: Bad list format!");
-            list.push_back({tok[0], tok[1], tok.size() > 2 ? tok[2] : "", tok.size() > 3 ? tok[3] : ""});
-        }
-    }
     ctu_handle *h = nullptr;
-    if (ctu_create(&cfg, 0, &h)) die(ctu_last_error(nullptr));
+    if (ctu_create(&cfg, device, &h)) die(ctu_last_error(nullptr));
     const int dim = ctu_feature_dim(h);
     const bool sig = ctu_is_signal_output(h);
     Writers W(ho, cfg, dim);
-    std::vector<unsigned char> extvad;
-    size_t ext_pos = 0;
-    if (!std::strcmp(cfg.vadmode, "file")) extvad = slurp(ho.filevad, "NR: Unable to open VAD file!\n");
+    size_t ext_pos = frame0;
     // batches of at most ~1 Gi samples
-    size_t i0 = 0;
-    while (i0 < list.size()) {
+    while (i0 < i1) {
         std::vector<int16_t> pcm;
         std::vector<int64_t> off{0};
-        size_t i1 = i0;
-        while (i1 < list.size() && pcm.size() < (size_t(1) << 30)) {
-            decode(ho, cfg.fs, list[i1].in, pcm);
+        size_t j1 = i0;
+        while (j1 < i1 && pcm.size() < (size_t(1) << 30)) {
+            decode(ho, cfg.fs, list[j1].in, pcm);
             off.push_back((int64_t)pcm.size());
-            i1++;
+            j1++;
         }
-        const int n = (int)(i1 - i0);
+        const int n = (int)(j1 - i0);
         std::vector<int64_t> frames(n), rows(n);
         int64_t total = 0, total_os = 0;
         for (int u = 0; u < n; u++) {
@@ -372,10 +455,115 @@ int run(int argc, char **argv) {
             r0 += frames[u];
             if (ho.verbose) std::cerr << "- " << frames[u] << " frames." << std::endl;
         }
-        i0 = i1;
+        i0 = j1;
     }
     W.close();
     ctu_destroy(h);
+}
+
+int run(int argc, char **argv) {
+    if (argc == 1) { std::cerr << "usage: ctucopy_b200 <ctucopy options> -S <list> [-gpus N | -shard r/N | -merge N]   (options: man/ctucopy4 of the reference)" << std::endl; die("OPTS: No command line options!"); }
+    ctu_config cfg;
+    ctu_config_init(&cfg);
+    HostOpts ho;
+    // host-owned options: config file first, then the command line (same order as the library's parser)
+    for (int j = 1; j + 1 < argc; j++) {
+        if (std::strcmp(argv[j], "-C")) continue;
+        std::ifstream cf(argv[j + 1]);
+        std::string line;
+        while (std::getline(cf, line)) {
+            size_t h = line.find('#');
+            if (h != std::string::npos) line.resize(h);
+            char a[1024] = "", b[1024] = "";
+            int n = std::sscanf(line.c_str(), "%1023s %1023s", a, b);
+            if (n >= 1) take_host_option(ho, a, n >= 2 ? b : nullptr);
+        }
+    }
+    std::vector<const char *> lib_argv;         // the library's parser does not know the multi-GPU extensions
+    for (int j = 1; j < argc; j++) {
+        if (argv[j][0] != '-') { lib_argv.push_back(argv[j]); continue; }
+        const char *r = (j + 1 < argc && argv[j + 1][0] != '-') ? argv[j + 1] : nullptr;
+        take_host_option(ho, argv[j], r);
+        if (is_host_extension(argv[j])) { if (r) j++; continue; }
+        lib_argv.push_back(argv[j]);
+    }
+    if (ctu_config_parse(&cfg, (int)lib_argv.size(), lib_argv.data())) die(ctu_config_error());
+    if (ho.merge_n > 0) {                        // merge step of a multi-process run: no GPU involved
+        if (!ho.pfilename.empty()) merge_pfile(ho.pfilename, ho.merge_n);
+        if (!ho.arkfilename.empty()) merge_ark(ho.arkfilename, ho.merge_n);
+        return 0;
+    }
+    if (ho.fb_printself) {
+        int32_t nb = 0;
+        if (ctu_design_filter_bank(&cfg, nullptr, nullptr, nullptr, &nb)) die(ctu_last_error(nullptr));
+        std::vector<double> mat((size_t)nb * cfg.wfftby2);
+        std::vector<int32_t> lo(nb), hi(nb);
+        ctu_design_filter_bank(&cfg, mat.data(), lo.data(), hi.data(), &nb);
+        for (int b = 0; b < nb; b++) { for (int i = 0; i < cfg.wfftby2; i++) std::cerr << mat[(size_t)b * cfg.wfftby2 + i] << "\t"; std::cerr << std::endl; }
+    }
+    // the list (single-file mode is one list line)
+    std::vector<ListEntry> list;
+    const bool do_vad = std::strcmp(cfg.vad_apply_mode, "none") || std::strcmp(cfg.vad_out_mode, "none");
+    if (!ho.in.empty() || !ho.out.empty()) {
+        if (ho.in.empty() || ho.out.empty()) die("OPTS: Single file mode has to be set at both sides (input and output)!");
+        list.push_back({ho.in, ho.out, "", ho.vad_out});
+    } else {
+        if (ho.list.empty()) die("BATCH: Nothing to do!");
+        std::ifstream lf(ho.list);
+        if (!lf) die("BATCH: Cannot open list file!");
+        std::string line;
+        while (std::getline(lf, line)) {
+            std::vector<std::string> tok;
+            size_t i = 0;
+            while (i < line.size()) {
+                while (i < line.size() && (line[i] == ' ' || line[i] == '\t')) i++;
+                size_t b = i;
+                while (i < line.size() && line[i] != ' ' && line[i] != '\t') i++;
+                if (i > b) tok.push_back(line.substr(b, i - b));
+            }
+            if (tok.size() < 2) die("BATCH: Bad list format!");
+            if (do_vad && tok.size() < 4) die("BATCH: Bad list format!");
+            list.push_back({tok[0], tok[1], tok.size() > 2 ? tok[2] : "", tok.size() > 3 ? tok[3] : ""});
+        }
+    }
+    std::vector<unsigned char> extvad;
+    if (!std::strcmp(cfg.vadmode, "file")) extvad = slurp(ho.filevad, "NR: Unable to open VAD file!\n");
+    const int nparts = ho.gpus > 1 ? ho.gpus : ho.shard_n;
+    if (nparts == 1) {
+        process_range(ho, cfg, list, 0, list.size(), ho.device < 0 ? 0 : ho.device, extvad, 0);
+        return 0;
+    }
+    // ---- utterance sharding: contiguous list ranges balanced by sample count, no exchange between shards
+    std::vector<int64_t> samples(list.size());
+    std::vector<size_t> frames_before(list.size() + 1, 0);
+    for (size_t i = 0; i < list.size(); i++) {
+        samples[i] = count_samples(ho, list[i].in);
+        int64_t T = samples[i] < cfg.window - cfg.wshift ? 0 : (samples[i] - (cfg.window - cfg.wshift)) / cfg.wshift;
+        frames_before[i + 1] = frames_before[i] + (size_t)T;
+    }
+    const std::vector<size_t> cut = partition(samples, nparts);
+    auto shard_opts = [&](int r) {
+        HostOpts o = ho;
+        if (!o.arkfilename.empty()) { o.ark_ref = ho.arkfilename; o.arkfilename = shard_name(ho.arkfilename, r, nparts); }
+        if (!o.pfilename.empty()) o.pfilename = shard_name(ho.pfilename, r, nparts);
+        return o;
+    };
+    if (ho.gpus <= 1) {                          // one process per GPU (e.g. under torchrun): this is shard r
+        process_range(shard_opts(ho.shard_r), cfg, list, cut[ho.shard_r], cut[ho.shard_r + 1], ho.device < 0 ? ho.shard_r : ho.device, extvad,
+                      frames_before[cut[ho.shard_r]]);
+        return 0;
+    }
+    std::vector<std::string> errs(nparts);
+    std::vector<std::thread> th;
+    for (int r = 0; r < nparts; r++)
+        th.emplace_back([&, r]() {
+            try { process_range(shard_opts(r), cfg, list, cut[r], cut[r + 1], r, extvad, frames_before[cut[r]]); }
+            catch (const std::exception &e) { errs[r] = e.what(); if (errs[r].empty()) errs[r] = "unknown error"; }
+        });
+    for (auto &t : th) t.join();
+    for (auto &e : errs) if (!e.empty()) die(e);
+    if (!ho.pfilename.empty()) merge_pfile(ho.pfilename, nparts);
+    if (!ho.arkfilename.empty()) merge_ark(ho.arkfilename, nparts);
     return 0;
 }
 

@@ -102,3 +102,25 @@ def test_cli_errors_like_the_reference(tmp_path):
     (tmp_path / "l.scp").write_text("%s/s.raw %s/s.out\n" % (tmp_path, tmp_path))
     pr = subprocess.run([EXE, "-fs", "16000", "-preset", "mfcc", "-format_in", "raw", "-format_out", "htk", "-S", str(tmp_path / "l.scp")], capture_output=True)
     assert pr.returncode == 255 and b"IO: Signal shorter than one frame!" in pr.stderr
+
+
+def test_cli_sharded_run_merges_to_the_single_process_files(tmp_path):
+    """-shard r/N (one process per GPU; both shards on device 0 here) + -merge N gives the
+    same ark / scp / pfile bytes and the same per-utterance HTK files as one process."""
+    ins = [gu.inputs()[i] for i in (0, 4, 1, 5, 2)]
+    for fmt in ("ark={ARK}", "pfile={PFILE}"):
+        args = ["-fs", "16000", "-format_in", "raw", "-dither", "0", "-preset", "plpc", "-format_out", fmt]
+        one, two = tmp_path / ("one_" + fmt[:3]), tmp_path / ("two_" + fmt[:3])
+        one.mkdir(); two.mkdir()
+        run_cli(str(one), args, ins)
+        for r in range(2):
+            run_cli(str(two), args + ["-shard", "%d/2" % r, "-device", "0"], ins)
+        a = [s.replace("{ARK}", str(two / "o.ark")).replace("{PFILE}", str(two / "o.pfile")) for s in args]
+        pr = subprocess.run([EXE] + a + ["-merge", "2"], capture_output=True)
+        assert pr.returncode == 0, pr.stderr.decode()
+        for fn in ("o.ark", "o.scp", "o.pfile"):
+            if (one / fn).exists():
+                got = open(two / fn, "rb").read().replace(str(two).encode(), b"@")
+                want = open(one / fn, "rb").read().replace(str(one).encode(), b"@")
+                assert got == want, fn
+        assert not [f for f in os.listdir(two) if f.startswith("shard")]
