@@ -57,13 +57,15 @@ struct ctu_plan {
     std::vector<int> nframes;
     std::vector<int64_t> row_off;        // n_utts+1
     std::vector<int64_t> osamp_off;      // n_utts+1 (signal output)
-    std::vector<int64_t> tile32_off, tile64_off;   // n_utts+1
+    std::vector<int64_t> tile32_off, tile64_off, tileS_off;   // n_utts+1 (S: synthesis tiles of syn_tile hops)
+    int syn_tile = 0;
     std::vector<int64_t> rows_per_utt;
     int64_t total_frames = 0, total_osamp = 0, total_samples = 0;
     // device bookkeeping
     int64_t *d_pcm_off = nullptr, *d_row_off = nullptr, *d_osamp_off = nullptr, *d_t32_off = nullptr, *d_t64_off = nullptr;
     int *d_nframes = nullptr;
-    int2 *d_tiles32 = nullptr, *d_tiles64 = nullptr;
+    int2 *d_tiles32 = nullptr, *d_tiles64 = nullptr, *d_tilesS = nullptr;
+    int64_t *d_tS_off = nullptr;
     // workspaces (whole batch)
     float *d_spec = nullptr, *d_fb = nullptr, *d_log = nullptr;
     double *d_fb64 = nullptr;            // band values of the precise path
@@ -490,17 +492,20 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     p->h = h; p->n_utts = n;
     p->offsets.assign(off, off + n + 1);
     p->nframes.resize(n); p->row_off.resize(n + 1); p->osamp_off.resize(n + 1);
-    p->tile32_off.resize(n + 1); p->tile64_off.resize(n + 1);
+    p->tile32_off.resize(n + 1); p->tile64_off.resize(n + 1); p->tileS_off.resize(n + 1);
+    p->syn_tile = std::max(1, SYN_FRAMES - h->sp.hh);
+    if (h->signal_out && h->sp.hh >= SYN_FRAMES) { delete p; return fail(h, CTU_ERR_UNSUPPORTED, "CTU: window / shift ratio too large for synthesis"); }
     p->rows_per_utt.assign(n, 0);
     const int w = h->cfg.window, s = h->cfg.wshift;
-    int64_t rows = 0, osamp = 0, t32 = 0, t64 = 0;
+    int64_t rows = 0, osamp = 0, t32 = 0, t64 = 0, tS = 0;
     for (int u = 0; u < n; u++) {
         int64_t N = off[u + 1] - off[u];
         if (N < w - s) { delete p; return fail(h, CTU_ERR_INPUT, "IO: Signal shorter than one frame!"); }
         int64_t T = (N - (w - s)) / s;
         if (T > 0x7fffffff) { delete p; return fail(h, CTU_ERR_INPUT, "CTU: utterance too long"); }
         p->nframes[u] = (int)T;
-        p->row_off[u] = rows; p->osamp_off[u] = osamp; p->tile32_off[u] = t32; p->tile64_off[u] = t64;
+        p->row_off[u] = rows; p->osamp_off[u] = osamp; p->tile32_off[u] = t32; p->tile64_off[u] = t64; p->tileS_off[u] = tS;
+        tS += (T + p->syn_tile - 1) / p->syn_tile;
         rows += T; osamp += T * s + (w - s);
         t32 += (T + TILE_F - 1) / TILE_F; t64 += (T + DELTA_ROWS - 1) / DELTA_ROWS;
         p->rows_per_utt[u] = T;
@@ -512,7 +517,7 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
             if (T < mw + 2) { delete p; return fail(h, CTU_ERR_UNSUPPORTED, "CTU: utterance shorter than delta window + 2 frames"); }
         }
     }
-    p->row_off[n] = rows; p->osamp_off[n] = osamp; p->tile32_off[n] = t32; p->tile64_off[n] = t64;
+    p->row_off[n] = rows; p->osamp_off[n] = osamp; p->tile32_off[n] = t32; p->tile64_off[n] = t64; p->tileS_off[n] = tS;
     p->total_frames = rows; p->total_osamp = osamp; p->total_samples = off[n] - off[0];
     int st = 0;
     auto up64 = [&](int64_t **d, const std::vector<int64_t> &v) -> int {
@@ -526,10 +531,12 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     if ((st = dev_alloc(h, p, &p->d_nframes, n))) { ctu_plan_destroy(p); return st; }
     if (n) CK(cudaMemcpy(p->d_nframes, p->nframes.data(), n * sizeof(int), cudaMemcpyHostToDevice));
     if ((st = dev_alloc(h, p, &p->d_tiles32, t32)) || (st = dev_alloc(h, p, &p->d_tiles64, t64))) { ctu_plan_destroy(p); return st; }
+    if (h->signal_out && ((st = up64(&p->d_tS_off, p->tileS_off)) || (st = dev_alloc(h, p, &p->d_tilesS, tS)))) { ctu_plan_destroy(p); return st; }
     if (n) {
         k_build_tiles<<<(n + 127) / 128, 128>>>(p->d_nframes, p->d_t32_off, n, TILE_F, p->d_tiles32);
         k_build_tiles<<<(n + 127) / 128, 128>>>(p->d_nframes, p->d_t64_off, n, DELTA_ROWS, p->d_tiles64);
-        h->lc.launches += 2;
+        if (h->signal_out) k_build_tiles<<<(n + 127) / 128, 128>>>(p->d_nframes, p->d_tS_off, n, p->syn_tile, p->d_tilesS);
+        h->lc.launches += h->signal_out ? 3 : 2;
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
     }
@@ -559,7 +566,7 @@ void ctu_plan_destroy(ctu_plan *p) {
     if (!p) return;
     cudaSetDevice(p->h->device);
     cudaFree(p->d_pcm_off); cudaFree(p->d_row_off); cudaFree(p->d_osamp_off); cudaFree(p->d_t32_off); cudaFree(p->d_t64_off);
-    cudaFree(p->d_nframes); cudaFree(p->d_tiles32); cudaFree(p->d_tiles64);
+    cudaFree(p->d_nframes); cudaFree(p->d_tiles32); cudaFree(p->d_tiles64); cudaFree(p->d_tilesS); cudaFree(p->d_tS_off);
     cudaFree(p->d_spec); cudaFree(p->d_fb); cudaFree(p->d_fb64); cudaFree(p->d_fea64); cudaFree(p->d_log); cudaFree(p->d_ceps); cudaFree(p->d_cri);
     cudaFree(p->d_flags); cudaFree(p->d_keep); cudaFree(p->d_vad0); cudaFree(p->d_rows);
     cudaFree(p->d_pcm); cudaFree(p->d_wave); cudaFree(p->d_fea); cudaFree(p->d_ext); cudaFree(p->d_vadnr_out); cudaFree(p->d_vad_out);
@@ -586,7 +593,7 @@ int ctu_plan_rows_per_utt(const ctu_plan *p, int64_t *r) {
 // ------------------------------------------------------------------------------------------
 struct Range {          // a contiguous run of utterances = contiguous tiles and rows
     int u0, u1;
-    int64_t t32_0, t32_n, t64_0, t64_n, row0, nrows;
+    int64_t t32_0, t32_n, t64_0, t64_n, tS_0, tS_n, row0, nrows;
 };
 
 static Range make_range(const ctu_plan *p, int u0, int u1) {
@@ -594,6 +601,7 @@ static Range make_range(const ctu_plan *p, int u0, int u1) {
     r.u0 = u0; r.u1 = u1;
     r.t32_0 = p->tile32_off[u0]; r.t32_n = p->tile32_off[u1] - r.t32_0;
     r.t64_0 = p->tile64_off[u0]; r.t64_n = p->tile64_off[u1] - r.t64_0;
+    r.tS_0 = p->tileS_off[u0]; r.tS_n = p->tileS_off[u1] - r.tS_0;
     r.row0 = p->row_off[u0]; r.nrows = p->row_off[u1] - r.row0;
     return r;
 }
@@ -700,8 +708,9 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
             CK(cudaMemcpyAsync(d_vadnr + r.row0, d_ext + r.row0, r.nrows, cudaMemcpyDeviceToDevice, s));
     }
     if (h->signal_out) {
-        return launch_synth(h->sp, h->fp, bd32, p->d_tiles32 + r.t32_0, r.t32_n, p->d_osamp_off, d_pcm, p->d_spec, d_wave, h->d_tw256,
-                            h->d_twsplit, h->d_twinv, h->d_win, s, &h->lc, h->err);
+        BatchDesc bdS{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tilesS + r.tS_0};
+        return launch_synth(h->sp, h->fp, bdS, p->syn_tile, r.tS_n, p->d_osamp_off, d_pcm, p->d_spec, d_wave, h->d_tw256, h->d_twsplit,
+                            h->d_twinv, h->d_win, s, &h->lc, h->err);
     }
 
     // ---- stage 2: features ------------------------------------------------------------------

@@ -130,23 +130,16 @@ __host__ __device__ inline SmemLayout smem_layout(int window, int wshift, int nb
 // int16 -> float without the (quarter-rate) conversion pipe: 1.5*2^23 + x is exact
 __device__ __forceinline__ float s16_to_f32(int x) { return __int_as_float(0x4B400000 + x) - 12582912.0f; }
 
-// WT: window length known at compile time (0 = take it from the parameters)
-template <int WT>
-__device__ __forceinline__ void phase_fft(const FrameParams &P, const int16_t *__restrict__ pcm, int64_t g0, bool first_tile,
-                                          int nf, const FftTables &tb, float *sm, const SmemLayout &L) {
+// Stage `nsamp` pre-emphasised samples x[n] - alpha*x[n-1] as floats (each sample converted
+// once, shared by the overlapping frames); a thread handles runs of 8 consecutive samples,
+// read as one 16-byte load where the source is aligned.  at_start: x[-1] = 0 (file start,
+// src/io/in.cc:364-372), else src[-1] is read.
+template <int NT>
+__device__ __forceinline__ void stage_preem(float *__restrict__ sD, const int16_t *__restrict__ src, int nsamp, bool at_start, float alpha) {
     const int tid = threadIdx.x;
-    float *sP = sm + L.oP, *sD = sm + L.oD, *sW = sm + L.oW;
-    cpx<float> *sTw = reinterpret_cast<cpx<float> *>(sm + L.oTw);
-    cpx<float> *sTs = reinterpret_cast<cpx<float> *>(sm + L.oTs);
-    const int w = WT ? WT : P.window, s = P.wshift;
-    const int nsamp = (nf - 1) * s + w;
-    // stage: pre-emphasised samples (each sample converted once, shared by the overlapping
-    // frames); a thread handles runs of 8 consecutive samples
-    const float alpha = P.preem;
-    const int16_t *src = pcm + g0;
     const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-    for (int i0 = tid * 8; i0 < nsamp; i0 += CTA_THREADS * 8) {
-        float prev = (i0 == 0 && first_tile) ? 0.f : s16_to_f32((int)src[i0 - 1]);
+    for (int i0 = tid * 8; i0 < nsamp; i0 += NT * 8) {
+        float prev = (i0 == 0 && at_start) ? 0.f : s16_to_f32((int)src[i0 - 1]);
         float v[8];
         if (vec && i0 + 8 <= nsamp) {
             const int4 q = __ldg(reinterpret_cast<const int4 *>(src + i0));
@@ -171,6 +164,19 @@ __device__ __forceinline__ void phase_fft(const FrameParams &P, const int16_t *_
             }
         }
     }
+}
+
+// WT: window length known at compile time (0 = take it from the parameters)
+template <int WT>
+__device__ __forceinline__ void phase_fft(const FrameParams &P, const int16_t *__restrict__ pcm, int64_t g0, bool first_tile,
+                                          int nf, const FftTables &tb, float *sm, const SmemLayout &L) {
+    const int tid = threadIdx.x;
+    float *sP = sm + L.oP, *sD = sm + L.oD, *sW = sm + L.oW;
+    cpx<float> *sTw = reinterpret_cast<cpx<float> *>(sm + L.oTw);
+    cpx<float> *sTs = reinterpret_cast<cpx<float> *>(sm + L.oTs);
+    const int w = WT ? WT : P.window, s = P.wshift;
+    const int nsamp = (nf - 1) * s + w;
+    stage_preem<CTA_THREADS>(sD, pcm + g0, nsamp, first_tile, P.preem);
     for (int i = tid; i < w; i += CTA_THREADS) sW[i] = tb.win[i];
     for (int i = tid; i < 256; i += CTA_THREADS) sTw[i] = mk<float>(tb.tw256[i].x, tb.tw256[i].y);
     for (int i = tid; i < 129; i += CTA_THREADS) sTs[i] = mk<float>(tb.twsplit[i].x, tb.twsplit[i].y);

@@ -269,174 +269,214 @@ __device__ __forceinline__ double group_sum16d(double v) {
 // ------------------------------------------------------------------------------------------
 // K4: Burg cepstrum per frame (fp64 throughout so that detector decisions are reproducible)
 // 128 threads = 8 frames per pass, 4 passes per 32-frame tile.
+//   * the tile's PCM is staged once into shared memory as int16 (16-byte loads);
+//   * forward FFT -> per-bin gain (|X|^a or the post-NR magnitude, over |X|) -> inverse FFT;
+//     the time signal reuses the exchange tile's memory;
+//   * lattice: sample i = c*CH + j lives in thread c's registers.  All updates are
+//     unconditional; the elements the reference no longer reads (i < ik) are driven to exact
+//     zeros instead of being masked: thread 0 keeps ef[0] = 0 and takes `below` = 0, which
+//     makes eb[ik-1] come out 0 by itself, and ef[ik] is cleared after stage ik.  The stage
+//     loop is fully unrolled so every register index is static;
+//   * the predictor coefficients are distributed (thread i holds a_i; one shuffle per stage).
+// CH: samples per thread; EXACT: window == 16*CH (no tail masking in the energy sums).
 // ------------------------------------------------------------------------------------------
 constexpr int BURG_THREADS = 128;
 constexpr int BURG_GROUPS = BURG_THREADS / GROUP;
 
-template <int CH>
+__device__ __forceinline__ double shfl16d(double v, int src) {
+    const unsigned m = 0xffffu << (threadIdx.x & 16);
+    return __shfl_sync(m, v, src, 16);
+}
+
+template <int CH, bool EXACT>
 __global__ void __launch_bounds__(BURG_THREADS)
 k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const int16_t *__restrict__ pcm, const float *__restrict__ spec,
        double *__restrict__ ceps, const double2 *__restrict__ g_tw256, const double2 *__restrict__ g_twsplit,
        const double2 *__restrict__ g_twinv, const double *__restrict__ g_win, const double *__restrict__ g_hann) {
     extern __shared__ __align__(16) double smd[];
     const int tid = threadIdx.x;
-    const int w = B.window, s = B.wshift;
+    const int w = EXACT ? 16 * CH : B.window, s = B.wshift;
     cpx<double> *sTw = reinterpret_cast<cpx<double> *>(smd);            // 256
     cpx<double> *sTs = sTw + 256;                                      // 129 (+1 pad)
     cpx<double> *sTi = sTs + 130;                                      // 129 (+1 pad)
-    cpx<double> *sX = sTi + 130;                                       // BURG_GROUPS * 16*17
-    double *sT = reinterpret_cast<double *>(sX + BURG_GROUPS * XPAD * 16);   // BURG_GROUPS * 512 time samples
-    for (int i = tid; i < 256; i += BURG_THREADS) sTw[i] = mk<double>(g_tw256[i].x, g_tw256[i].y);
-    for (int i = tid; i < 129; i += BURG_THREADS) { sTs[i] = mk<double>(g_twsplit[i].x, g_twsplit[i].y); sTi[i] = mk<double>(g_twinv[i].x, g_twinv[i].y); }
-    __syncthreads();
+    cpx<double> *sX = sTi + 130;                                       // BURG_GROUPS * 16*17 (also the time signal)
+    double *sWin = reinterpret_cast<double *>(sX + BURG_GROUPS * XPAD * 16);   // 512: analysis window
+    double *sHann = sWin + NFFT;                                       // 512: detector's Hann (NR source)
+    int16_t *sPcm = reinterpret_cast<int16_t *>(sHann + NFFT);         // 8 + (TILE_F-1)*s + w + 1 + 8
     const int2 tile = bd.tiles[blockIdx.x];
     const int u = tile.x, t0 = tile.y;
     const int nf = min(TILE_F, bd.nframes[u] - t0);
     const int64_t row0 = bd.row_off[u] + t0;
-    const int64_t g0 = bd.pcm_off[u];
+    // samples [first-1, first + nsamp): the one before the tile feeds the first pre-emphasis
+    const int nsamp = (nf - 1) * s + w + 1;
+    const bool at_start = (t0 == 0);
+    const int16_t *src = pcm + bd.pcm_off[u] + (int64_t)t0 * s - 1;
+    const int phase = (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 1);      // same 16-byte phase in shared memory
+    int16_t *dpcm = sPcm + phase;
+    for (int k0 = tid * 8 - phase; k0 < nsamp; k0 += BURG_THREADS * 8) {
+        if (k0 >= (at_start ? 1 : 0) && k0 + 8 <= nsamp) {
+            *reinterpret_cast<int4 *>(dpcm + k0) = __ldg(reinterpret_cast<const int4 *>(src + k0));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int k = k0 + j;
+                if (k >= 0 && k < nsamp) dpcm[k] = (k == 0 && at_start) ? (int16_t)0 : src[k];
+            }
+        }
+    }
+    for (int i = tid; i < 256; i += BURG_THREADS) sTw[i] = mk<double>(g_tw256[i].x, g_tw256[i].y);
+    for (int i = tid; i < 129; i += BURG_THREADS) { sTs[i] = mk<double>(g_twsplit[i].x, g_twsplit[i].y); sTi[i] = mk<double>(g_twinv[i].x, g_twinv[i].y); }
+    for (int i = tid; i < NFFT; i += BURG_THREADS) {
+        sWin[i] = (i < w) ? g_win[i] : 0.0;
+        sHann[i] = (i < w) ? ((src_mode == BURG_SRC_NR) ? g_hann[i] : 1.0) : 0.0;
+    }
+    __syncthreads();
     const int c = tid & (GROUP - 1), grp = tid / GROUP;
     cpx<double> *xch = sX + grp * (XPAD * 16);
-    double *xt = sT + grp * NFFT;
+    double *xt = reinterpret_cast<double *>(xch);
     const int ncoef = (src_mode == BURG_SRC_NR) ? B.ncoef_nr : B.ncoef_vad;
+    const double inv_w = 1.0 / (double)w;
 #pragma unroll 1
     for (int pass = 0; pass < TILE_F / BURG_GROUPS; pass++) {
         const int f = pass * BURG_GROUPS + grp;
         const bool active = f < nf;
-        cpx<double> a[16];
-        cpx<double> lo[8], hi[8], mid;
-        if (active) {
-            const int64_t fs0 = g0 + (int64_t)(t0 + f) * s;       // first sample of the frame
-            const bool at_start = (t0 + f) == 0;
-            double sum = 0;
-#pragma unroll
-            for (int n1 = 0; n1 < 16; n1++) {
-                int i0 = 32 * n1 + 2 * c;
-                double y0 = 0, y1 = 0;
-                if (i0 < w) {
-                    double xm = (i0 == 0) ? (at_start ? 0.0 : (double)pcm[fs0 - 1]) : (double)pcm[fs0 + i0 - 1];
-                    double x0 = (double)pcm[fs0 + i0];
-                    y0 = g_win[i0] * (x0 - B.preem * xm);
-                    if (i0 + 1 < w) y1 = g_win[i0 + 1] * ((double)pcm[fs0 + i0 + 1] - B.preem * x0);
-                }
-                a[n1] = mk<double>(y0, y1);
-                sum += y0 + y1;
-            }
-            if (B.remove_dc) {
-                double mean = group_sum16d(sum) / (double)w;
+        {
+            cpx<double> a[16];
+            cpx<double> lo[8], hi[8], mid;
+            if (active) {
+                const int16_t *x = dpcm + f * s + 1;                  // x[-1] is the sample before the frame
+                double sum = 0;
 #pragma unroll
                 for (int n1 = 0; n1 < 16; n1++) {
-                    int i0 = 32 * n1 + 2 * c;
-                    if (i0 < w) a[n1].x -= mean;
-                    if (i0 + 1 < w) a[n1].y -= mean;
-                }
-            }
-            fft256_pass1(a, c, sTw, xch);
-        }
-        __syncwarp();
-        if (active) fft256_pass2(a, c, xch);
-        __syncwarp();
-        if (active) fft256_store_linear(a, c, xch);
-        __syncwarp();
-        if (active) {
-            rfft_split(xch, c, sTs, lo, hi, mid);
-            // (|X|^a or the post-NR spectrum) with the phase of X: scale each bin by E/|X|
-            const float *srow = (src_mode == BURG_SRC_VAD && B.use_spec_gain) ? spec + (row0 + f) * NBIN : nullptr;
-            auto scale_bin = [&](cpx<double> X, int k) -> cpx<double> {
-                double m2 = X.x * X.x + X.y * X.y;
-                bool edge = (k == 0 || k == NC);
-                if (k == 0) { if (B.remove_dc) m2 = 1e-10; X = mk<double>(sqrt(m2), 0.0); }   // phase of bin 0 is 0 (src/io/in.cc:398)
-                double m = sqrt(m2);
-                double E;
-                if (srow) E = (double)srow[k];
-                else {
-                    double Xa = B.fb_power ? m2 : m;
-                    if (src_mode == BURG_SRC_NR && B.expand) {
-                        if (B.a_kind == 2) Xa = Xa * Xa;
-                        else if (B.a_kind == 0) Xa = pow(Xa, B.a);
+                    const int i0 = 32 * n1 + 2 * c;
+                    double y0 = 0, y1 = 0;
+                    if (i0 < w) {                                     // w is even for every supported window
+                        const double xm = (double)x[i0 - 1], x0 = (double)x[i0], x1 = (double)x[i0 + 1];
+                        y0 = sWin[i0] * (x0 - B.preem * xm);
+                        y1 = sWin[i0 + 1] * (x1 - B.preem * x0);      // sWin is 0 beyond the window
                     }
-                    E = Xa;
+                    a[n1] = mk<double>(y0, y1);
+                    sum += y0 + y1;
                 }
-                if (m == 0.0) return edge ? mk<double>(E, 0.0) : mk<double>(0.0, -E);   // c_ph(0,0) = -pi/2
-                double g = E / m;
-                if (edge) return mk<double>(X.x * g, 0.0);
-                return mk<double>(X.x * g, X.y * g);
-            };
+                if (B.remove_dc) {
+                    const double mean = group_sum16d(sum) * inv_w;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                int k = c + 16 * j;
-                lo[j] = scale_bin(lo[j], k);
-                hi[j] = scale_bin(hi[j], NC - k);
+                    for (int n1 = 0; n1 < 16; n1++) {
+                        const int i0 = 32 * n1 + 2 * c;
+                        if (i0 < w) a[n1].x -= mean;
+                        if (i0 + 1 < w) a[n1].y -= mean;
+                    }
+                }
+                fft256_pass1(a, c, sTw, xch);
             }
-            mid = scale_bin(mid, 128);
-        }
-        __syncwarp();
-        if (active) irfft_presplit(xch, c, sTi, lo, hi, mid);
-        __syncwarp();
-        if (active) { fft256_load_column(a, c, xch); }
-        __syncwarp();
-        if (active) fft256_pass1(a, c, sTw, xch);
-        __syncwarp();
-        if (active) fft256_pass2(a, c, xch);
-        if (active) {
+            __syncwarp();
+            if (active) fft256_pass2(a, c, xch);
+            __syncwarp();
+            if (active) fft256_store_linear(a, c, xch);
+            __syncwarp();
+            if (active) {
+                rfft_split(xch, c, sTs, lo, hi, mid);
+                // (|X|^a or the post-NR spectrum) with the phase of X: every bin is scaled by
+                // E/|X| -- what Xa*cos(phi), Xa*sin(phi) amount to (src/nr/nr.cc:281-292,
+                // src/vad/vad.cc:222-233) -- with the reference's conventions for bin 0
+                // (phase 0, src/io/in.cc:398), the Nyquist bin (real) and atan(0/0) = -pi/2
+                const float *srow = (src_mode == BURG_SRC_VAD && B.use_spec_gain) ? spec + (row0 + f) * NBIN : nullptr;
+                const bool expand = (src_mode == BURG_SRC_NR && B.expand);
+                auto scale_bin = [&](cpx<double> X, int k) -> cpx<double> {
+                    double m2 = X.x * X.x + X.y * X.y;
+                    const bool edge = (k == 0 || k == NC);
+                    if (k == 0) { if (B.remove_dc) m2 = 1e-10; X = mk<double>(sqrt(m2), 0.0); }
+                    const double rm = (m2 > 0.0) ? rsqrt(m2) : 0.0;          // 1/|X|
+                    const double m = m2 * rm;                                // |X|
+                    double E, g;
+                    if (srow) { E = (double)srow[k]; g = E * rm; }
+                    else {
+                        // E = Xa^a with Xa = |X|^2 (fb_power) or |X|;  g = E/|X| without the division
+                        // where the exponents are small integers
+                        const int ak = expand ? B.a_kind : 1;
+                        if (ak == 0) { E = pow(B.fb_power ? m2 : m, B.a); g = E * rm; }
+                        else if (B.fb_power) { E = (ak == 2) ? m2 * m2 : m2; g = (ak == 2) ? m2 * m : m; }
+                        else { E = (ak == 2) ? m2 : m; g = (ak == 2) ? m : 1.0; }
+                    }
+                    if (m2 == 0.0) return edge ? mk<double>(E, 0.0) : mk<double>(0.0, -E);
+                    return mk<double>(X.x * g, edge ? 0.0 : X.y * g);
+                };
 #pragma unroll
-            for (int k2 = 0; k2 < 16; k2++) {
-                int n = c + 16 * k2;
-                xt[2 * n] = a[k2].x;
-                xt[2 * n + 1] = -a[k2].y;
+                for (int j = 0; j < 8; j++) {
+                    const int k = c + 16 * j;
+                    lo[j] = scale_bin(lo[j], k);
+                    hi[j] = scale_bin(hi[j], NC - k);
+                }
+                mid = scale_bin(mid, 128);
             }
+            __syncwarp();
+            if (active) irfft_presplit(xch, c, sTi, lo, hi, mid);
+            __syncwarp();
+            if (active) fft256_load_column(a, c, xch);
+            __syncwarp();
+            if (active) fft256_pass1(a, c, sTw, xch);
+            __syncwarp();
+            if (active) fft256_pass2(a, c, xch);
+            __syncwarp();                                             // xch is re-used for the time signal
+            if (active) {
+#pragma unroll
+                for (int k2 = 0; k2 < 16; k2++) {
+                    const int n = c + 16 * k2;
+                    xt[2 * n] = a[k2].x;
+                    xt[2 * n + 1] = -a[k2].y;
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
         if (active) {
-            // ---- Burg lattice on the first w samples; thread c owns i in [c*CH, c*CH+CH) -----
+            // ---- Burg lattice (src/vdet/Burg.h:49-95) on the first w samples ------------------
             double ef[CH], eb[CH];
             double en = 0;
 #pragma unroll
             for (int j = 0; j < CH; j++) {
-                int i = c * CH + j;
-                double v = 0;
-                if (i < w) { v = xt[i]; if (src_mode == BURG_SRC_NR) v *= g_hann[i]; }
+                const int i = c * CH + j;
+                double v = (EXACT || i < w) ? xt[i < NFFT ? i : 0] * sHann[i < NFFT ? i : 0] : 0.0;
+                if (!EXACT && i >= w) v = 0.0;
                 ef[j] = eb[j] = v;
                 en += v * v;
             }
-            double alpha = group_sum16d(en) / (double)w;
-            double av[BURG_MAXC], aav[BURG_MAXC];
+            double alpha = group_sum16d(en) * inv_w;
+            if (c == 0) ef[0] = 0.0;                                  // never read by the reference
+            double a_c = (c == 0) ? 1.0 : 0.0, aa_c = a_c;            // thread i holds a_i
 #pragma unroll
-            for (int i = 0; i < BURG_MAXC; i++) { av[i] = 0; aav[i] = 0; }
-            av[0] = 1.0;
-            const unsigned hm = 0xffffu << (tid & 16);
-#pragma unroll 1
-            for (int ik = 1; ik < ncoef; ik++) {
-                // eb of the element just below this thread's chunk
-                double below = __shfl_up_sync(hm, eb[CH - 1], 1, 16);
-                double num = 0, den = 0;
+            for (int ik = 1; ik < BURG_MAXC; ik++) {
+                if (ik < ncoef) {
+                    double below = shfl16d(eb[CH - 1], (c + 15) & 15);
+                    if (c == 0) below = 0.0;
+                    double num = 0, den = 0;
 #pragma unroll
-                for (int j = 0; j < CH; j++) {
-                    int i = c * CH + j;
-                    double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
-                    if (i >= ik && i < w) { den += ef[j] * ef[j] + pv * pv; num += ef[j] * pv; }
-                }
-                num = group_sum16d(num) * 2.0;
-                den = group_sum16d(den);
-                const double rc = -num / den;
-                alpha *= 1 - rc * rc;
+                    for (int j = 0; j < CH; j++) {
+                        const double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
+                        if (EXACT || c * CH + j < w) { den += ef[j] * ef[j] + pv * pv; num += ef[j] * pv; }
+                    }
+                    num = group_sum16d(num) * 2.0;
+                    den = group_sum16d(den);
+                    const double rc = -num / den;
+                    alpha *= 1 - rc * rc;
 #pragma unroll
-                for (int j = CH - 1; j >= 0; j--) {
-                    int i = c * CH + j;
-                    double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
-                    if (i >= 1 && i < w) {
-                        double e0 = ef[j];
+                    for (int j = CH - 1; j >= 0; j--) {
+                        const double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
+                        const double e0 = ef[j];
                         ef[j] = e0 + rc * pv;
                         eb[j] = pv + rc * e0;
                     }
+                    if (c == 0 && ik < CH) ef[ik < CH ? ik : 0] = 0.0;
+                    // a_i = aa_i + rc * aa_{ik-i} (0 < i < ik), a_ik = rc
+                    const double other = shfl16d(aa_c, (ik - c) & 15);
+                    if (c == ik) a_c = rc;
+                    else if (c >= 1 && c < ik) a_c = aa_c + rc * other;
+                    aa_c = a_c;
                 }
-#pragma unroll
-                for (int i = 1; i < BURG_MAXC; i++) {
-                    if (i == ik) av[i] = rc;
-                    else if (i < ik) av[i] = aav[i] + rc * aav[(ik - i) & (BURG_MAXC - 1)];
-                }
-#pragma unroll
-                for (int i = 1; i < BURG_MAXC; i++) if (i <= ik) aav[i] = av[i];
             }
+            // LPC -> cepstrum (src/vdet/Burg.h:141-152), thread 0 of the group
+            double av[BURG_MAXC];
+#pragma unroll
+            for (int k = 0; k < BURG_MAXC; k++) av[k] = shfl16d(a_c, k);
             if (c == 0) {
                 double cc[BURG_MAXC];
                 double *o = ceps + (row0 + f) * BURG_MAXC;
@@ -455,24 +495,27 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const i
     }
 }
 
-static inline size_t burg_smem_bytes() {
-    return sizeof(double) * (2 * (256 + 130 + 130 + BURG_GROUPS * XPAD * 16) + BURG_GROUPS * NFFT);
+static inline size_t burg_smem_bytes(int w, int s) {
+    return sizeof(double) * (2 * (256 + 130 + 130 + BURG_GROUPS * XPAD * 16) + 2 * NFFT) + sizeof(int16_t) * (size_t)(8 + (TILE_F - 1) * s + w + 1 + 8 + 8);
 }
 
 static inline int launch_burg(const BurgParams &B, int src_mode, const BatchDesc &bd, int64_t ntiles, const int16_t *pcm, const float *spec,
                               double *ceps, const double2 *tw, const double2 *ts, const double2 *ti, const double *win, const double *hann,
                               cudaStream_t s, LaunchCtx *lc, std::string &err) {
     if (ntiles <= 0) return CTU_OK;
-    size_t bytes = burg_smem_bytes();
+    if (B.window & 1) { err = "CTU: the Burg detector path needs an even window length"; return CTU_ERR_UNSUPPORTED; }
+    size_t bytes = burg_smem_bytes(B.window, B.wshift);
+    if (bytes > 227 * 1024) { err = "CTU: window shift too large for the Burg detector kernel"; return CTU_ERR_UNSUPPORTED; }
     cudaError_t e;
     lc->begin("k_burg", s);
-    if (B.window <= 25 * 16) {
-        e = cudaFuncSetAttribute(k_burg<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e == cudaSuccess) k_burg<25><<<(unsigned)ntiles, BURG_THREADS, bytes, s>>>(B, src_mode, bd, pcm, spec, ceps, tw, ts, ti, win, hann);
-    } else {
-        e = cudaFuncSetAttribute(k_burg<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e == cudaSuccess) k_burg<32><<<(unsigned)ntiles, BURG_THREADS, bytes, s>>>(B, src_mode, bd, pcm, spec, ceps, tw, ts, ti, win, hann);
-    }
+#define CTU_BURG_LAUNCH(CH, EX)                                                                                        \
+    e = cudaFuncSetAttribute(k_burg<CH, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);                 \
+    if (e == cudaSuccess) k_burg<CH, EX><<<(unsigned)ntiles, BURG_THREADS, bytes, s>>>(B, src_mode, bd, pcm, spec, ceps, tw, ts, ti, win, hann)
+    if (B.window == 400) { CTU_BURG_LAUNCH(25, true); }
+    else if (B.window == 512) { CTU_BURG_LAUNCH(32, true); }
+    else if (B.window <= 400) { CTU_BURG_LAUNCH(25, false); }
+    else { CTU_BURG_LAUNCH(32, false); }
+#undef CTU_BURG_LAUNCH
     lc->end(s);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e) + " (k_burg)"; return CTU_ERR_CUDA; }
@@ -673,20 +716,28 @@ k_vad_compact(const int *__restrict__ nframes, const int64_t *__restrict__ row_o
 constexpr int SYN_THREADS = 256;
 constexpr int SYN_GROUPS = SYN_THREADS / GROUP;
 
+// frames a synthesis tile may hold: two passes of SYN_GROUPS frames.  A tile of the plan's
+// synthesis tile list covers SYN_FRAMES - hh new hops, so that together with the hh frames
+// before it that still overlap its first sample no pass runs partly empty.
+constexpr int SYN_FRAMES = 2 * SYN_GROUPS;
+
+// WT / ST: window and shift known at compile time (0 = runtime) -- turns the divisions of the
+// overlap-add index arithmetic into shifts / multiplies and prunes the zero padding.
+template <int WT, int ST>
 __global__ void __launch_bounds__(SYN_THREADS)
-k_synth(const __grid_constant__ SynthParams S, int window, int wshift, float preem, int remove_dc, BatchDesc bd,
+k_synth(const __grid_constant__ SynthParams S, int window, int wshift, float preem, int remove_dc, BatchDesc bd, int tile_frames,
         const int64_t *__restrict__ osamp_off, const int16_t *__restrict__ pcm, const float *__restrict__ spec, int16_t *__restrict__ out,
         const float2 *__restrict__ g_tw256, const float2 *__restrict__ g_twsplit, const float2 *__restrict__ g_twinv,
         const float *__restrict__ g_win) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x;
-    const int w = window, s = wshift, hh = S.hh;
+    const int w = WT ? WT : window, s = ST ? ST : wshift, hh = S.hh;
     const int2 tile = bd.tiles[blockIdx.x];
     const int u = tile.x, t0 = tile.y;
     const int T = bd.nframes[u];
-    const int nf = min(TILE_F, T - t0);
+    const int nf = min(tile_frames, T - t0);
     const int tfirst = max(t0 - hh, 0);
-    const int nfr = t0 + nf - tfirst;                     // frames to synthesise (<= 32 + hh)
+    const int nfr = t0 + nf - tfirst;                     // frames to synthesise (<= SYN_FRAMES)
     const int nsamp = (nfr - 1) * s + w;
     // carve-up
     cpx<float> *sTw = reinterpret_cast<cpx<float> *>(sm);                 // 256
@@ -694,17 +745,12 @@ k_synth(const __grid_constant__ SynthParams S, int window, int wshift, float pre
     cpx<float> *sTi = sTs + 130;                                         // 130
     cpx<float> *sX = sTi + 130;                                          // SYN_GROUPS * 16*17
     float *sW = reinterpret_cast<float *>(sX + SYN_GROUPS * XPAD * 16);  // w (padded to 512)
-    float *sD = sW + NFFT;                                               // (32+hh-1)*s + w  (padded)
-    float *sYt = sD + (((TILE_F + hh - 1) * s + w + 3) & ~3);            // (32+hh) * w
+    float *sD = sW + NFFT;                                               // (SYN_FRAMES-1)*s + w  (padded)
+    float *sYt = sD + (((SYN_FRAMES - 1) * s + w + 3) & ~3);             // SYN_FRAMES * w
+    stage_preem<SYN_THREADS>(sD, pcm + bd.pcm_off[u] + (int64_t)tfirst * s, nsamp, tfirst == 0, preem);
     for (int i = tid; i < 256; i += SYN_THREADS) sTw[i] = mk<float>(g_tw256[i].x, g_tw256[i].y);
     for (int i = tid; i < 129; i += SYN_THREADS) { sTs[i] = mk<float>(g_twsplit[i].x, g_twsplit[i].y); sTi[i] = mk<float>(g_twinv[i].x, g_twinv[i].y); }
     for (int i = tid; i < w; i += SYN_THREADS) sW[i] = g_win[i];
-    const int64_t g0 = bd.pcm_off[u] + (int64_t)tfirst * s;
-    for (int i = tid; i < nsamp; i += SYN_THREADS) {
-        float xi = (float)pcm[g0 + i];
-        float xp = (i == 0 && tfirst == 0) ? 0.f : (float)pcm[g0 + i - 1];
-        sD[i] = fmaf(-preem, xp, xi);
-    }
     __syncthreads();
     const int c = tid & (GROUP - 1), grp = tid / GROUP;
     cpx<float> *xch = sX + grp * (XPAD * 16);
@@ -715,7 +761,14 @@ k_synth(const __grid_constant__ SynthParams S, int window, int wshift, float pre
         const int f = pass * SYN_GROUPS + grp;
         const bool active = f < nfr;
         cpx<float> a[16], lo[8], hi[8], mid;
+        float Alo[8], Ahi[8], Amid = 0.f;
         if (active) {
+            // enhanced magnitudes of this frame: issued first so that their HBM latency hides
+            // behind the forward transform
+            const float *srow = spec + (bd.row_off[u] + tfirst + f) * NBIN;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { Alo[j] = __ldg(srow + c + 16 * j); Ahi[j] = __ldg(srow + NC - c - 16 * j); }
+            Amid = __ldg(srow + 128);
             const float *d = sD + f * s;
             float sum = 0.f;
 #pragma unroll
@@ -747,23 +800,22 @@ k_synth(const __grid_constant__ SynthParams S, int window, int wshift, float pre
             // enhanced magnitude with the ORIGINAL phase: scale X by |X|enh / (|X| nfft);
             // bin 0 has phase 0, the Nyquist bin is always written non-negative
             // (src/io/out.cc:417-424)
-            const float *srow = spec + (bd.row_off[u] + tfirst + f) * NBIN;
             const float invn = 1.0f / (float)NFFT;
-            auto scale_bin = [&](cpx<float> X, int k) -> cpx<float> {
-                float A = srow[k] * invn;
-                if (k == 0 || k == NC) return mk<float>(A, 0.f);
-                float m = sqrtf(X.x * X.x + X.y * X.y);
-                if (m == 0.f) return mk<float>(0.f, -A);
-                float g = A / m;
+            auto scale_bin = [&](cpx<float> X, float A, bool edge) -> cpx<float> {
+                A *= invn;
+                if (edge) return mk<float>(A, 0.f);
+                float m2 = X.x * X.x + X.y * X.y;
+                if (m2 == 0.f) return mk<float>(0.f, -A);
+                float g = A * rsqrtf(m2);
                 return mk<float>(X.x * g, X.y * g);
             };
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                int k = c + 16 * j;
-                lo[j] = scale_bin(lo[j], k);
-                hi[j] = scale_bin(hi[j], NC - k);
+                const bool edge = (c == 0 && j == 0);           // k == 0 pairs with k == 256
+                lo[j] = scale_bin(lo[j], Alo[j], edge);
+                hi[j] = scale_bin(hi[j], Ahi[j], edge);
             }
-            mid = scale_bin(mid, 128);
+            mid = scale_bin(mid, Amid, false);
         }
         __syncwarp();
         if (active) irfft_presplit(xch, c, sTi, lo, hi, mid);
@@ -778,51 +830,57 @@ k_synth(const __grid_constant__ SynthParams S, int window, int wshift, float pre
 #pragma unroll
             for (int k2 = 0; k2 < 16; k2++) {
                 int n = c + 16 * k2;
-                if (2 * n < w) yt[2 * n] = a[k2].x;
-                if (2 * n + 1 < w) yt[2 * n + 1] = -a[k2].y;
+                if (2 * n + 1 < w) *reinterpret_cast<float2 *>(yt + 2 * n) = make_float2(a[k2].x, -a[k2].y);
+                else if (2 * n < w) yt[2 * n] = a[k2].x;
             }
         }
         __syncwarp();
     }
     __syncthreads();
-    // overlap-add in frame order, quantise
+    // overlap-add in frame order (fp64 accumulator like the reference's cbuffer), quantise:
+    // floor(x / correction), clip to +-32767 (src/io/out.cc:427-451)
     const bool last = (t0 + nf == T);
     const int nout = nf * s + (last ? (w - s) : 0);
     int16_t *o = out + osamp_off[u] + (int64_t)t0 * s;
     const int base = (t0 - tfirst) * s;                     // position of the tile's first sample inside the synthesised span
+    const double corr = S.correction;
     for (int i = tid; i < nout; i += SYN_THREADS) {
         const int pos = base + i;                           // sample index relative to frame `tfirst`
-        int fa = (pos - w) / s + 1;                         // first frame with fa*s + w > pos
-        if (pos < w) fa = 0;
-        int fb = min(pos / s, nfr - 1);
+        const int fa = (pos < w) ? 0 : (pos - w) / s + 1;   // first frame with fa*s + w > pos
+        const int fb = min(pos / s, nfr - 1);
         double acc = 0.0;
         for (int f = fa; f <= fb; f++) acc += (double)sYt[f * w + (pos - f * s)];
-        double q = floor(acc / S.correction);
-        int v = (int)q;
-        if (fabsf((float)v) > 32767.f) v = (v < 0) ? -32767 : 32767;
+        int v = (int)floor(acc / corr);
+        v = max(-32767, min(32767, v));
         o[i] = (int16_t)v;
     }
 }
 
-static inline size_t synth_smem_bytes(int w, int s, int hh) {
-    size_t fl = 2 * (256 + 130 + 130 + SYN_GROUPS * XPAD * 16) + NFFT + (((TILE_F + hh - 1) * s + w + 3) & ~3) + (size_t)(TILE_F + hh) * w;
+static inline size_t synth_smem_bytes(int w, int s) {
+    size_t fl = 2 * (256 + 130 + 130 + SYN_GROUPS * XPAD * 16) + NFFT + (((SYN_FRAMES - 1) * s + w + 3) & ~3) + (size_t)SYN_FRAMES * w;
     return fl * sizeof(float);
 }
 
-static inline int launch_synth(const SynthParams &S, const FrameParams &F, const BatchDesc &bd, const int2 *, int64_t ntiles,
+// tiles: the plan's synthesis tile list, tile_frames = SYN_FRAMES - hh hops per tile
+static inline int launch_synth(const SynthParams &S, const FrameParams &F, const BatchDesc &bd, int tile_frames, int64_t ntiles,
                                const int64_t *d_osamp_off, const int16_t *pcm, const float *spec, int16_t *out, const float2 *tw,
                                const float2 *ts, const float2 *ti, const float *win, cudaStream_t s, LaunchCtx *lc, std::string &err) {
     if (ntiles <= 0) return CTU_OK;
-    size_t bytes = synth_smem_bytes(F.window, F.wshift, S.hh);
-    if (bytes > 227 * 1024) { err = "CTU: window/shift combination needs too much shared memory for synthesis"; return CTU_ERR_UNSUPPORTED; }
-    cudaError_t e = cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e == cudaSuccess) {
-        lc->begin("k_synth", s);
-        k_synth<<<(unsigned)ntiles, SYN_THREADS, bytes, s>>>(S, F.window, F.wshift, F.preem, F.remove_dc, bd, d_osamp_off, pcm, spec, out, tw, ts,
-                                                              ti, win);
-        lc->end(s);
-        e = cudaGetLastError();
-    }
+    size_t bytes = synth_smem_bytes(F.window, F.wshift);
+    if (bytes > 227 * 1024 || tile_frames < 1) { err = "CTU: window/shift combination needs too much shared memory for synthesis"; return CTU_ERR_UNSUPPORTED; }
+    cudaError_t e;
+    lc->begin("k_synth", s);
+#define CTU_SYNTH_LAUNCH(WT, ST)                                                                                                   \
+    e = cudaFuncSetAttribute(k_synth<WT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);                          \
+    if (e == cudaSuccess)                                                                                                          \
+        k_synth<WT, ST><<<(unsigned)ntiles, SYN_THREADS, bytes, s>>>(S, F.window, F.wshift, F.preem, F.remove_dc, bd, tile_frames, \
+                                                                     d_osamp_off, pcm, spec, out, tw, ts, ti, win)
+    if (F.window == 512 && F.wshift == 256) { CTU_SYNTH_LAUNCH(512, 256); }
+    else if (F.window == 400 && F.wshift == 160) { CTU_SYNTH_LAUNCH(400, 160); }
+    else { CTU_SYNTH_LAUNCH(0, 0); }
+#undef CTU_SYNTH_LAUNCH
+    lc->end(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e) + " (k_synth)"; return CTU_ERR_CUDA; }
     return CTU_OK;
 }
