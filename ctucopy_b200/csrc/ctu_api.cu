@@ -15,6 +15,7 @@
 
 #include "ctu_internal.h"
 #include "ctu_kernels.cuh"
+#include "ctu_frames2.cuh"
 #include "ctu_nr_kernels.cuh"
 #include "ctu_precise.cuh"
 
@@ -41,6 +42,10 @@ struct ctu_handle {
     // device tables
     float2 *d_tw256 = nullptr, *d_twsplit = nullptr, *d_twinv = nullptr;
     float *d_win = nullptr;
+    // tables of the group-local frame kernel (ctu_frames2.cuh)
+    float *d_fbw = nullptr, *d_m2p = nullptr;
+    int4 *d_slots = nullptr;
+    Tables2 t2{};
     double2 *d_tw256d = nullptr, *d_twsplitd = nullptr, *d_twinvd = nullptr;
     double *d_wind = nullptr, *d_hann = nullptr;
     // fp64 tables of the precise path (ctu_precise.cuh)
@@ -57,15 +62,15 @@ struct ctu_plan {
     std::vector<int> nframes;
     std::vector<int64_t> row_off;        // n_utts+1
     std::vector<int64_t> osamp_off;      // n_utts+1 (signal output)
-    std::vector<int64_t> tile32_off, tile64_off, tileS_off;   // n_utts+1 (S: synthesis tiles of syn_tile hops)
+    std::vector<int64_t> tile32_off, tile64_off, tileS_off, tileF_off;   // n_utts+1 (S: synthesis tiles of syn_tile hops)
     int syn_tile = 0;
     std::vector<int64_t> rows_per_utt;
     int64_t total_frames = 0, total_osamp = 0, total_samples = 0;
     // device bookkeeping
     int64_t *d_pcm_off = nullptr, *d_row_off = nullptr, *d_osamp_off = nullptr, *d_t32_off = nullptr, *d_t64_off = nullptr;
     int *d_nframes = nullptr;
-    int2 *d_tiles32 = nullptr, *d_tiles64 = nullptr, *d_tilesS = nullptr;
-    int64_t *d_tS_off = nullptr;
+    int2 *d_tiles32 = nullptr, *d_tiles64 = nullptr, *d_tilesS = nullptr, *d_tilesF = nullptr;
+    int64_t *d_tS_off = nullptr, *d_tF_off = nullptr;
     // workspaces (whole batch)
     float *d_spec = nullptr, *d_fb = nullptr, *d_log = nullptr;
     double *d_fb64 = nullptr;            // band values of the precise path
@@ -311,6 +316,41 @@ static int build_frame_params(ctu_handle *h) {
     return CTU_OK;
 }
 
+
+// tables of k_frames2: packed taps, band slots (widest band first, dealt to the 16 lanes in
+// snake order so every lane gets about the same number of taps), second-stage matrix with an
+// odd row pitch
+static int build_tables2(ctu_handle *h) {
+    const FrameParams &P = h->fp;
+    Tables2 &T = h->t2;
+    std::memset(&T, 0, sizeof(T));
+    T.tw256 = h->d_tw256; T.twsplit = h->d_twsplit; T.win = h->d_win;
+    if (h->signal_out) return CTU_OK;
+    const int nb = P.nb;
+    int ntaps = 0;
+    for (int b = 0; b < nb; b++) ntaps = std::max(ntaps, P.woff[b] + (P.hi[b] - P.lo[b] + 1));
+    std::vector<float> fbw(P.w, P.w + ntaps);
+    std::vector<int> order(nb);
+    for (int b = 0; b < nb; b++) order[b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return (P.hi[a] - P.lo[a]) > (P.hi[b] - P.lo[b]); });
+    const int rounds = (nb + GROUP - 1) / GROUP;
+    std::vector<int4> slots((size_t)rounds * GROUP, make_int4(-1, 0, 0, 0));
+    for (int i = 0; i < nb; i++) {
+        const int r = i / GROUP, pos = i % GROUP, lane = (r & 1) ? GROUP - 1 - pos : pos;
+        const int b = order[i];
+        slots[(size_t)r * GROUP + lane] = make_int4(b, P.lo[b], P.hi[b] - P.lo[b] + 1, P.woff[b]);
+    }
+    const int pitch = P.nbp | 1;
+    std::vector<float> m2((size_t)std::max(1, P.nrows) * pitch, 0.f);
+    for (int r = 0; r < P.nrows; r++)
+        for (int k = 0; k < P.nbp; k++) m2[(size_t)r * pitch + k] = P.m2[r * P.nbp + k];
+    int st;
+    if ((st = upload(h, &h->d_fbw, fbw)) || (st = upload(h, &h->d_slots, slots)) || (st = upload(h, &h->d_m2p, m2))) return st;
+    T.fbw = h->d_fbw; T.slots = h->d_slots; T.m2 = h->d_m2p;
+    T.ntaps_total = ntaps; T.nslots = (int)slots.size(); T.m2_pitch = pitch; T.m2_rows = (h->fea_kind == FEA_DCTC) ? P.nrows : 0;
+    return CTU_OK;
+}
+
 static int build_delta_trap_params(ctu_handle *h) {
     const ctu_config &c = h->cfg;
     DeltaParams &D = h->dp;
@@ -450,6 +490,7 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     }
     if (cudaSetDevice(device) != cudaSuccess) { h->err = "CUDA: cudaSetDevice failed"; return bail(CTU_ERR_CUDA); }
     if ((st = build_fft_tables(h))) return bail(st);
+    if ((st = build_tables2(h))) return bail(st);
     if (h->nr_mode != NR_NONE && h->cfg.nr_when == 1 && !h->signal_out) h->precise = true;   // subtraction on band values
     // VAD criterion = distance between feature vectors, fed to threshold state machines whose
     // decisions must match the reference bit for bit: features in fp64 like the reference's
@@ -466,6 +507,7 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
 void ctu_destroy(ctu_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    cudaFree(h->d_fbw); cudaFree(h->d_m2p); cudaFree(h->d_slots);
     cudaFree(h->d_tw256); cudaFree(h->d_twsplit); cudaFree(h->d_twinv); cudaFree(h->d_win);
     cudaFree(h->d_w64); cudaFree(h->d_m264); cudaFree(h->d_lift64);
     cudaFree(h->d_tw256d); cudaFree(h->d_twsplitd); cudaFree(h->d_twinvd); cudaFree(h->d_wind); cudaFree(h->d_hann);
@@ -492,19 +534,20 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     p->h = h; p->n_utts = n;
     p->offsets.assign(off, off + n + 1);
     p->nframes.resize(n); p->row_off.resize(n + 1); p->osamp_off.resize(n + 1);
-    p->tile32_off.resize(n + 1); p->tile64_off.resize(n + 1); p->tileS_off.resize(n + 1);
+    p->tile32_off.resize(n + 1); p->tile64_off.resize(n + 1); p->tileS_off.resize(n + 1); p->tileF_off.resize(n + 1);
     p->syn_tile = std::max(1, SYN_FRAMES - h->sp.hh);
     if (h->signal_out && h->sp.hh >= SYN_FRAMES) { delete p; return fail(h, CTU_ERR_UNSUPPORTED, "CTU: window / shift ratio too large for synthesis"); }
     p->rows_per_utt.assign(n, 0);
     const int w = h->cfg.window, s = h->cfg.wshift;
-    int64_t rows = 0, osamp = 0, t32 = 0, t64 = 0, tS = 0;
+    int64_t rows = 0, osamp = 0, t32 = 0, t64 = 0, tS = 0, tF = 0;
     for (int u = 0; u < n; u++) {
         int64_t N = off[u + 1] - off[u];
         if (N < w - s) { delete p; return fail(h, CTU_ERR_INPUT, "IO: Signal shorter than one frame!"); }
         int64_t T = (N - (w - s)) / s;
         if (T > 0x7fffffff) { delete p; return fail(h, CTU_ERR_INPUT, "CTU: utterance too long"); }
         p->nframes[u] = (int)T;
-        p->row_off[u] = rows; p->osamp_off[u] = osamp; p->tile32_off[u] = t32; p->tile64_off[u] = t64; p->tileS_off[u] = tS;
+        p->row_off[u] = rows; p->osamp_off[u] = osamp; p->tile32_off[u] = t32; p->tile64_off[u] = t64; p->tileS_off[u] = tS; p->tileF_off[u] = tF;
+        tF += (T + F2_TILE - 1) / F2_TILE;
         tS += (T + p->syn_tile - 1) / p->syn_tile;
         rows += T; osamp += T * s + (w - s);
         t32 += (T + TILE_F - 1) / TILE_F; t64 += (T + DELTA_ROWS - 1) / DELTA_ROWS;
@@ -517,7 +560,7 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
             if (T < mw + 2) { delete p; return fail(h, CTU_ERR_UNSUPPORTED, "CTU: utterance shorter than delta window + 2 frames"); }
         }
     }
-    p->row_off[n] = rows; p->osamp_off[n] = osamp; p->tile32_off[n] = t32; p->tile64_off[n] = t64; p->tileS_off[n] = tS;
+    p->row_off[n] = rows; p->osamp_off[n] = osamp; p->tile32_off[n] = t32; p->tile64_off[n] = t64; p->tileS_off[n] = tS; p->tileF_off[n] = tF;
     p->total_frames = rows; p->total_osamp = osamp; p->total_samples = off[n] - off[0];
     int st = 0;
     auto up64 = [&](int64_t **d, const std::vector<int64_t> &v) -> int {
@@ -531,12 +574,14 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     if ((st = dev_alloc(h, p, &p->d_nframes, n))) { ctu_plan_destroy(p); return st; }
     if (n) CK(cudaMemcpy(p->d_nframes, p->nframes.data(), n * sizeof(int), cudaMemcpyHostToDevice));
     if ((st = dev_alloc(h, p, &p->d_tiles32, t32)) || (st = dev_alloc(h, p, &p->d_tiles64, t64))) { ctu_plan_destroy(p); return st; }
+    if ((st = up64(&p->d_tF_off, p->tileF_off)) || (st = dev_alloc(h, p, &p->d_tilesF, tF))) { ctu_plan_destroy(p); return st; }
     if (h->signal_out && ((st = up64(&p->d_tS_off, p->tileS_off)) || (st = dev_alloc(h, p, &p->d_tilesS, tS)))) { ctu_plan_destroy(p); return st; }
     if (n) {
         k_build_tiles<<<(n + 127) / 128, 128>>>(p->d_nframes, p->d_t32_off, n, TILE_F, p->d_tiles32);
         k_build_tiles<<<(n + 127) / 128, 128>>>(p->d_nframes, p->d_t64_off, n, DELTA_ROWS, p->d_tiles64);
+        k_build_tiles<<<(n + 127) / 128, 128>>>(p->d_nframes, p->d_tF_off, n, F2_TILE, p->d_tilesF);
         if (h->signal_out) k_build_tiles<<<(n + 127) / 128, 128>>>(p->d_nframes, p->d_tS_off, n, p->syn_tile, p->d_tilesS);
-        h->lc.launches += h->signal_out ? 3 : 2;
+        h->lc.launches += h->signal_out ? 4 : 3;
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
     }
@@ -566,7 +611,7 @@ void ctu_plan_destroy(ctu_plan *p) {
     if (!p) return;
     cudaSetDevice(p->h->device);
     cudaFree(p->d_pcm_off); cudaFree(p->d_row_off); cudaFree(p->d_osamp_off); cudaFree(p->d_t32_off); cudaFree(p->d_t64_off);
-    cudaFree(p->d_nframes); cudaFree(p->d_tiles32); cudaFree(p->d_tiles64); cudaFree(p->d_tilesS); cudaFree(p->d_tS_off);
+    cudaFree(p->d_nframes); cudaFree(p->d_tiles32); cudaFree(p->d_tiles64); cudaFree(p->d_tilesS); cudaFree(p->d_tS_off); cudaFree(p->d_tilesF); cudaFree(p->d_tF_off);
     cudaFree(p->d_spec); cudaFree(p->d_fb); cudaFree(p->d_fb64); cudaFree(p->d_fea64); cudaFree(p->d_log); cudaFree(p->d_ceps); cudaFree(p->d_cri);
     cudaFree(p->d_flags); cudaFree(p->d_keep); cudaFree(p->d_vad0); cudaFree(p->d_rows);
     cudaFree(p->d_pcm); cudaFree(p->d_wave); cudaFree(p->d_fea); cudaFree(p->d_ext); cudaFree(p->d_vadnr_out); cudaFree(p->d_vad_out);
@@ -593,7 +638,7 @@ int ctu_plan_rows_per_utt(const ctu_plan *p, int64_t *r) {
 // ------------------------------------------------------------------------------------------
 struct Range {          // a contiguous run of utterances = contiguous tiles and rows
     int u0, u1;
-    int64_t t32_0, t32_n, t64_0, t64_n, tS_0, tS_n, row0, nrows;
+    int64_t t32_0, t32_n, t64_0, t64_n, tS_0, tS_n, tF_0, tF_n, row0, nrows;
 };
 
 static Range make_range(const ctu_plan *p, int u0, int u1) {
@@ -602,47 +647,73 @@ static Range make_range(const ctu_plan *p, int u0, int u1) {
     r.t32_0 = p->tile32_off[u0]; r.t32_n = p->tile32_off[u1] - r.t32_0;
     r.t64_0 = p->tile64_off[u0]; r.t64_n = p->tile64_off[u1] - r.t64_0;
     r.tS_0 = p->tileS_off[u0]; r.tS_n = p->tileS_off[u1] - r.tS_0;
+    r.tF_0 = p->tileF_off[u0]; r.tF_n = p->tileF_off[u1] - r.tF_0;
     r.row0 = p->row_off[u0]; r.nrows = p->row_off[u1] - r.row0;
     return r;
 }
 
+struct Range;
+// tile lists of one contiguous run of utterances for the two frame-kernel generations
+struct FrameTiles {
+    const int2 *t32; int64_t n32;     // 32-frame tiles (k_frames)
+    const int2 *t16; int64_t n16;     // 16-frame tiles (k_frames2)
+};
+
+// Two generations of the fused frame kernel are kept because they bind on different things
+// (profiles/): k_frames (32-frame spectrum tile, lane = frame filter bank: fewest shared-memory
+// wavefronts, 2 CTAs/SM) wins whenever a filter bank follows; k_frames2 (group-local, 6
+// CTAs/SM) wins for PCM -> spectrum, where nothing follows the transform inside the kernel.
 template <int SRC, int DST, int KIND, int WT>
-static int launch_frames_w(ctu_handle *h, const FrameParams &P, const BatchDesc &bd, int64_t ntiles, const int16_t *pcm,
+static int launch_frames_w(ctu_handle *h, const FrameParams &P, const ctu_plan *p, const FrameTiles &ft, const int16_t *pcm,
                            const float *src, float *dst, cudaStream_t s) {
-    SmemLayout L = smem_layout(P.window, P.wshift, P.nb);
-    size_t bytes = (size_t)L.total * sizeof(float);
-    auto kern = k_frames<SRC, DST, KIND, WT>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    FftTables tb{h->d_tw256, h->d_twsplit, h->d_twinv, h->d_win};
     static const char *const names[3][3] = {{"k_frames<pcm,spec>", "k_frames<pcm,fb>", "k_frames<pcm,fea>"},
                                             {"k_frames<spec,spec>", "k_frames<spec,fb>", "k_frames<spec,fea>"},
                                             {"k_frames<fb,spec>", "k_frames<fb,fb>", "k_frames<fb,fea>"}};
-    h->lc.begin(names[SRC][DST], s);
-    kern<<<(unsigned)ntiles, CTA_THREADS, bytes, s>>>(P, bd, tb, pcm, src, dst);
-    h->lc.end(s);
+    if constexpr (DST == DST_SPEC) {
+        if (ft.n16 <= 0) return CTU_OK;
+        const Tables2 &T = h->t2;
+        Smem2 L = smem2_layout(P.window, P.wshift, T.ntaps_total, T.nslots, T.m2_pitch, T.m2_rows);
+        size_t bytes = (size_t)L.total * sizeof(float);
+        auto kern = k_frames2<SRC, DST, KIND, WT>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        BatchDesc bd{p->d_pcm_off, p->d_nframes, p->d_row_off, ft.t16};
+        h->lc.begin(names[SRC][DST], s);
+        kern<<<(unsigned)ft.n16, F2_THREADS, bytes, s>>>(P, bd, T, pcm, src, dst);
+        h->lc.end(s);
+    } else {
+        if (ft.n32 <= 0) return CTU_OK;
+        SmemLayout L = smem_layout(P.window, P.wshift, P.nb);
+        size_t bytes = (size_t)L.total * sizeof(float);
+        auto kern = k_frames<SRC, DST, KIND, WT>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        FftTables tb{h->d_tw256, h->d_twsplit, h->d_twinv, h->d_win};
+        BatchDesc bd{p->d_pcm_off, p->d_nframes, p->d_row_off, ft.t32};
+        h->lc.begin(names[SRC][DST], s);
+        kern<<<(unsigned)ft.n32, CTA_THREADS, bytes, s>>>(P, bd, tb, pcm, src, dst);
+        h->lc.end(s);
+    }
     CK(cudaGetLastError());
     return CTU_OK;
 }
 
 template <int SRC, int DST, int KIND>
-static int launch_frames_t(ctu_handle *h, const FrameParams &P, const BatchDesc &bd, int64_t ntiles, const int16_t *pcm,
+static int launch_frames_t(ctu_handle *h, const FrameParams &P, const ctu_plan *p, const FrameTiles &ft, const int16_t *pcm,
                            const float *src, float *dst, cudaStream_t s) {
-    if (ntiles <= 0) return CTU_OK;
     // the PCM front end is specialised for the two standard window lengths (25 ms and 32 ms
     // at 16 kHz); every other length takes the generic instantiation
-    if (SRC == SRC_PCM && P.window == 400) return launch_frames_w<SRC, DST, KIND, 400>(h, P, bd, ntiles, pcm, src, dst, s);
-    if (SRC == SRC_PCM && P.window == 512) return launch_frames_w<SRC, DST, KIND, 512>(h, P, bd, ntiles, pcm, src, dst, s);
-    return launch_frames_w<SRC, DST, KIND, 0>(h, P, bd, ntiles, pcm, src, dst, s);
+    if (SRC == SRC_PCM && P.window == 400) return launch_frames_w<SRC, DST, KIND, 400>(h, P, p, ft, pcm, src, dst, s);
+    if (SRC == SRC_PCM && P.window == 512) return launch_frames_w<SRC, DST, KIND, 512>(h, P, p, ft, pcm, src, dst, s);
+    return launch_frames_w<SRC, DST, KIND, 0>(h, P, p, ft, pcm, src, dst, s);
 }
 
 template <int SRC, int DST>
-static int launch_frames_k(ctu_handle *h, int kind, const FrameParams &P, const BatchDesc &bd, int64_t nt, const int16_t *pcm,
+static int launch_frames_k(ctu_handle *h, int kind, const FrameParams &P, const ctu_plan *p, const FrameTiles &ft, const int16_t *pcm,
                            const float *src, float *dst, cudaStream_t s) {
     switch (kind) {
-        case KIND_SPEC: return launch_frames_t<SRC, DST, KIND_SPEC>(h, P, bd, nt, pcm, src, dst, s);
-        case KIND_LOGSPEC: return launch_frames_t<SRC, DST, KIND_LOGSPEC>(h, P, bd, nt, pcm, src, dst, s);
-        case KIND_DCTC: return launch_frames_t<SRC, DST, KIND_DCTC>(h, P, bd, nt, pcm, src, dst, s);
-        case KIND_TRAPLOG: return launch_frames_t<SRC, DST, KIND_TRAPLOG>(h, P, bd, nt, pcm, src, dst, s);
+        case KIND_SPEC: return launch_frames_t<SRC, DST, KIND_SPEC>(h, P, p, ft, pcm, src, dst, s);
+        case KIND_LOGSPEC: return launch_frames_t<SRC, DST, KIND_LOGSPEC>(h, P, p, ft, pcm, src, dst, s);
+        case KIND_DCTC: return launch_frames_t<SRC, DST, KIND_DCTC>(h, P, p, ft, pcm, src, dst, s);
+        case KIND_TRAPLOG: return launch_frames_t<SRC, DST, KIND_TRAPLOG>(h, P, p, ft, pcm, src, dst, s);
     }
     return fail(h, CTU_ERR_CONFIG, "CTU: bad kind");
 }
@@ -682,6 +753,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     if (r.nrows <= 0 && !h->signal_out) return CTU_OK;
     BatchDesc bd32{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tiles32 + r.t32_0};
     BatchDesc bd64{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tiles64 + r.t64_0};
+    const FrameTiles ft{p->d_tiles32 + r.t32_0, r.t32_n, p->d_tilesF + r.tF_0, r.tF_n};
     int st;
     const int kind = kind_of(h);
     uint8_t *flags = d_vadnr ? d_vadnr : p->d_flags;
@@ -693,7 +765,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     FrameParams P = h->fp;
     if (need_spec) {
         P.out_dim = NBIN; P.out_stride = NBIN;
-        if ((st = launch_frames_t<SRC_PCM, DST_SPEC, KIND_SPEC>(h, P, bd32, r.t32_n, d_pcm, nullptr, p->d_spec, s))) return st;
+        if ((st = launch_frames_t<SRC_PCM, DST_SPEC, KIND_SPEC>(h, P, p, ft, d_pcm, nullptr, p->d_spec, s))) return st;
     }
     if (nr_on && before) {
         if (h->nr_mode >= NR_HWSS && h->vad_src == VADSRC_BURG) {
@@ -739,13 +811,13 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     } else if (kind == KIND_LPA || kind == KIND_LPC) {
         // band values to HBM (76 B per frame for PLP), then one thread per frame for the recursion
         FrameParams Pf = h->fp; Pf.out_dim = h->fb.nb; Pf.out_stride = h->fb.nb;
-        if (need_spec) { if ((st = launch_frames_t<SRC_SPEC, DST_FB, KIND_SPEC>(h, Pf, bd32, r.t32_n, nullptr, p->d_spec, p->d_fb, s))) return st; }
-        else if ((st = launch_frames_t<SRC_PCM, DST_FB, KIND_SPEC>(h, Pf, bd32, r.t32_n, d_pcm, nullptr, p->d_fb, s))) return st;
+        if (need_spec) { if ((st = launch_frames_t<SRC_SPEC, DST_FB, KIND_SPEC>(h, Pf, p, ft, nullptr, p->d_spec, p->d_fb, s))) return st; }
+        else if ((st = launch_frames_t<SRC_PCM, DST_FB, KIND_SPEC>(h, Pf, p, ft, d_pcm, nullptr, p->d_fb, s))) return st;
         if ((st = launch_lpc(h, P, kind == KIND_LPC, r.row0, r.nrows, p->d_fb, fea_dst, s))) return st;
     } else if (need_spec) {
-        if ((st = launch_frames_k<SRC_SPEC, DST_FEA>(h, kind, P, bd32, r.t32_n, nullptr, p->d_spec, fea_dst, s))) return st;
+        if ((st = launch_frames_k<SRC_SPEC, DST_FEA>(h, kind, P, p, ft, nullptr, p->d_spec, fea_dst, s))) return st;
     } else {
-        if ((st = launch_frames_k<SRC_PCM, DST_FEA>(h, kind, P, bd32, r.t32_n, d_pcm, nullptr, fea_dst, s))) return st;
+        if ((st = launch_frames_k<SRC_PCM, DST_FEA>(h, kind, P, p, ft, d_pcm, nullptr, fea_dst, s))) return st;
     }
     // ---- stage 3: long-context ------------------------------------------------------------
     if (kind == KIND_TRAPLOG && r.t64_n > 0) {
@@ -879,9 +951,9 @@ int ctu_debug_spectrum(ctu_plan *p, const int16_t *d_pcm, float *d_spec, void *s
     if (!p) return CTU_ERR_CONFIG;
     ctu_handle *h = p->h;
     CK(cudaSetDevice(h->device));
-    BatchDesc bd32{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tiles32};
+    const FrameTiles ft{p->d_tiles32, p->tile32_off[p->n_utts], p->d_tilesF, p->tileF_off[p->n_utts]};
     FrameParams P = h->fp; P.out_dim = NBIN; P.out_stride = NBIN;
-    int st = launch_frames_t<SRC_PCM, DST_SPEC, KIND_SPEC>(h, P, bd32, p->tile32_off[p->n_utts], d_pcm, nullptr, d_spec, (cudaStream_t)stream);
+    int st = launch_frames_t<SRC_PCM, DST_SPEC, KIND_SPEC>(h, P, p, ft, d_pcm, nullptr, d_spec, (cudaStream_t)stream);
     if (st) return st;
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return CTU_OK;

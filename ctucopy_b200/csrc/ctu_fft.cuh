@@ -78,6 +78,26 @@ CTU_HD void fft256_pass1(cpx<T> (&a)[16], int c, const cpx<T> *tw256, cpx<T> *xc
         xch[k1 * XPAD + c] = v;
     }
 }
+// pass 1 with most inter-pass twiddles formed on the fly: only W^c, W^2c, W^3c, W^4c, W^8c and
+// W^12c (W = e^{-2 pi i/256}) are loaded, the other nine are products of two of them.  Trades
+// nine shared-memory loads per thread for 36 flops; the shared-memory pipe is the scarcer one.
+template <class T>
+CTU_HD void fft256_pass1_rec(cpx<T> (&a)[16], int c, const cpx<T> *tw256, cpx<T> *xch) {
+    dft16(a);
+    const cpx<T> w1 = tw256[16 + c], w2 = tw256[32 + c], w3 = tw256[48 + c];
+    xch[c] = a[0];
+    xch[1 * XPAD + c] = cmul(a[1], w1);
+    xch[2 * XPAD + c] = cmul(a[2], w2);
+    xch[3 * XPAD + c] = cmul(a[3], w3);
+#pragma unroll
+    for (int q = 1; q < 4; q++) {
+        const cpx<T> wq = tw256[64 * q + c];            // W^(4q c)
+        xch[(4 * q) * XPAD + c] = cmul(a[4 * q], wq);
+        xch[(4 * q + 1) * XPAD + c] = cmul(a[4 * q + 1], cmul(wq, w1));
+        xch[(4 * q + 2) * XPAD + c] = cmul(a[4 * q + 2], cmul(wq, w2));
+        xch[(4 * q + 3) * XPAD + c] = cmul(a[4 * q + 3], cmul(wq, w3));
+    }
+}
 // pass 2 (after a group-wide sync): thread c now plays k1 = c; loads A[c][n2], transforms
 // over n2; on return a[k2] = Z[c + 16*k2].
 template <class T>

@@ -103,6 +103,34 @@ __device__ __forceinline__ float group_sum16(float v) {
     return v;
 }
 
+// real-input split without shared memory.  After pass 2 thread c holds Z[c + 16 k2] in a[k2].
+// X[k] for k = c + 16 j (j < 8) needs Z[k] = a[j] and Z[256-k], which thread (16-c)%16 holds at
+// index 15-j (thread 0 pairs with itself at index 16-j).  Same arithmetic as rfft_split.
+__device__ __forceinline__ void rfft_split_shfl(const cpx<float> (&a)[16], int c, const cpx<float> *twsplit, cpx<float> (&lo)[8],
+                                                cpx<float> (&hi)[8], cpx<float> &mid) {
+    const unsigned m = 0xffffu << (threadIdx.x & 16);
+    const int src = (16 - c) & 15;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        cpx<float> Z;
+        Z.x = __shfl_sync(m, a[15 - j].x, src, 16);
+        Z.y = __shfl_sync(m, a[15 - j].y, src, 16);
+        if (c == 0 && j >= 1) Z = a[j >= 1 ? 16 - j : 0];
+        const cpx<float> A = a[j];
+        if (j == 0 && c == 0) {
+            lo[j] = mk<float>(A.x + A.y, 0.f);
+            hi[j] = mk<float>(A.x - A.y, 0.f);
+        } else {
+            const cpx<float> B = conj(Z);
+            const cpx<float> E = mk<float>(0.5f * (A.x + B.x), 0.5f * (A.y + B.y));
+            const cpx<float> Tt = cmul(twsplit[c + 16 * j], A - B);
+            lo[j] = E + Tt;
+            hi[j] = conj(E - Tt);
+        }
+    }
+    mid = conj(a[8]);   // X[128], meaningful for c == 0
+}
+
 // shared-memory carve-up (floats)
 struct SmemLayout {
     int oP, oY, oD, oW, oX, oTw, oTs, oR, total;
@@ -110,15 +138,14 @@ struct SmemLayout {
 __host__ __device__ inline SmemLayout smem_layout(int window, int wshift, int nb) {
     SmemLayout L;
     int o = 0;
-    L.oP = o; o += TILE_F * LDP;
-    L.oY = o; o += TILE_F * (MAXB + 1);
+    L.oP = o; o += (TILE_F * LDP + 3) & ~3;
     L.oD = o; o += ((TILE_F - 1) * wshift + window + 3) & ~3;
     L.oW = o; o += (window + 3) & ~3;
-    L.oX = o; o += (CTA_THREADS / GROUP) * XPAD * 16 * 2;      // one 16x17 complex tile per group
+    L.oX = o;                                                  // one 16x17 complex tile per group ...
+    L.oY = o; o += (CTA_THREADS / GROUP) * XPAD * 16 * 2;      // ... re-used for the band tile once the transforms are done
     L.oTw = o; o += 256 * 2;
     L.oTs = o; o += 130 * 2;
-    o = (o + 1) & ~1;
-    L.oR = o; o += 2 * TILE_F * (MAXR + 1);                    // doubles: autocorrelation lags
+    L.oR = o;
     L.total = o;
     (void)nb;
     return L;
@@ -213,16 +240,13 @@ __device__ __forceinline__ void phase_fft(const FrameParams &P, const int16_t *_
                     if (i0 + 1 < w) a[n1].y -= mean;
                 }
             }
-            fft256_pass1(a, c, sTw, xch);
+            fft256_pass1_rec(a, c, sTw, xch);
         }
         __syncwarp();
-        if (active) fft256_pass2(a, c, xch);
-        __syncwarp();
-        if (active) fft256_store_linear(a, c, xch);
-        __syncwarp();
         if (active) {
+            fft256_pass2(a, c, xch);
             cpx<float> lo[8], hi[8], mid;
-            rfft_split(xch, c, sTs, lo, hi, mid);
+            rfft_split_shfl(a, c, sTs, lo, hi, mid);
             float *row = sP + f * LDP;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -275,6 +299,11 @@ __device__ __forceinline__ void phase_fb(const FrameParams &P, float *sm, const 
         }
         sY[lane * (MAXB + 1) + b] = y;
     }
+    // pad columns of the band tile (read by the 4-wide second-stage loop) must be finite
+    for (int i = threadIdx.x; i < TILE_F * (P.nbp - P.nb); i += CTA_THREADS) {
+        const int f = i / (P.nbp - P.nb), b = P.nb + i - f * (P.nbp - P.nb);
+        sY[f * (MAXB + 1) + b] = 0.f;
+    }
     __syncthreads();
 }
 
@@ -302,61 +331,6 @@ __device__ __forceinline__ void phase_fea(const FrameParams &P, float *sm, const
             }
             sO[lane * od + i] = acc;
         }
-    } else {  // LPA / LPC
-        double *sR = reinterpret_cast<double *>(sm + L.oR);      // [TILE_F][MAXR+1]
-        const int p = P.lporder;
-        // power spectrum -> autocorrelation (src/fea/fea_impl.cc:181-198); the cos table,
-        // the 1/2 end weights and the 2/N factor are folded into m2 on the host
-        for (int k = wv; k <= p; k += CTA_THREADS / 32) {
-            const float *m = P.m2 + k * P.nbp;
-            double acc = 0.0;
-            for (int n = 0; n < P.nb; n++) {
-                float v = y[n];
-                if (P.lpa_square) v = v * v;
-                acc += (double)v * (double)m[n];
-            }
-            sR[lane * (MAXR + 1) + k] = acc;
-        }
-        __syncthreads();
-        if (wv == 0) {
-            // Levinson-Durbin in fp64, one lane per frame (src/fea/fea_impl.cc:200-222)
-            const double *R = sR + lane * (MAXR + 1);
-            double a[MAXR], aa[MAXR];
-            double Pe = R[0];
-            double rc = -R[1] / R[0];
-            Pe = Pe * (1 - rc * rc);
-            a[0] = aa[0] = 1.0;
-            a[1] = aa[1] = rc;
-            for (int ik = 2; ik <= p; ik++) {
-                double dm = R[ik];
-                for (int n = 1; n <= ik - 1; n++) dm += aa[n] * R[ik - n];
-                rc = -dm / Pe;
-                a[ik] = rc;
-                for (int n = 1; n <= ik - 1; n++) a[n] = aa[n] + rc * aa[ik - n];
-                for (int n = 1; n <= ik; n++) aa[n] = a[n];
-                Pe = Pe * (1 - rc * rc);
-            }
-            if (KIND == KIND_LPA) {
-                for (int i = 1; i <= p; i++) sO[lane * od + i - 1] = (float)a[i];   // a0 is not written
-            } else {
-                // LPC -> cepstrum (src/fea/fea_impl.cc:266-284), lifter, writer order
-                double cc[MAXR];
-                const int N = P.ncep;
-                cc[0] = log(Pe);
-                for (int n = 1; n <= N; n++) {
-                    double sum = 0;
-                    if (n <= p) {
-                        for (int k = 1; k <= n - 1; k++) sum += (n - k) * cc[n - k] * a[k];
-                        cc[n] = -a[n] - sum / n;
-                    } else {
-                        for (int k = 1; k <= p; k++) sum += (n - k) * cc[n - k] * a[k];
-                        cc[n] = -sum / n;
-                    }
-                }
-                for (int n = 1; n <= N; n++) sO[lane * od + n - 1] = (float)(cc[n] * (double)P.lift[n]);
-                if (P.c0_last) sO[lane * od + N] = (float)cc[0];
-            }
-        }
     }
     __syncthreads();
 }
@@ -376,11 +350,6 @@ k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, cons
     const int64_t row0 = bd.row_off[u] + t0;
     const int tid = threadIdx.x;
 
-    if (DST != DST_SPEC) {
-        // pad columns of the band tile (read by the 4-wide second-stage loops) must be finite
-        float *sY = sm + L.oY;
-        for (int i = tid; i < TILE_F * (MAXB + 1); i += CTA_THREADS) sY[i] = 0.f;
-    }
     if (SRC == SRC_PCM) {
         phase_fft<WT>(P, pcm, bd.pcm_off[u] + (int64_t)t0 * P.wshift, t0 == 0, nf, tb, sm, L);
     } else if (SRC == SRC_SPEC) {
@@ -396,6 +365,10 @@ k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, cons
             float v = g[i];
             if (KIND == KIND_DCTC || KIND == KIND_LOGSPEC || KIND == KIND_TRAPLOG) v = logf(v);
             sY[f * (MAXB + 1) + b] = v;
+        }
+        for (int i = tid; i < TILE_F * (P.nbp - P.nb); i += CTA_THREADS) {
+            const int f = i / (P.nbp - P.nb), b = P.nb + i - f * (P.nbp - P.nb);
+            sY[f * (MAXB + 1) + b] = 0.f;
         }
         __syncthreads();
     }

@@ -7,5 +7,6 @@ name=$1; kre=$2; skip=$3; cnt=$4; shift 4
 ncu --set full --clock-control none --import-source on -k "regex:$kre" -s $skip -c $cnt -f -o /tmp/prof_$name "$@" > gpurun_out/ncu_$name.log 2>&1
 ncu -i /tmp/prof_$name.ncu-rep --page raw --csv > gpurun_out/raw_$name.csv 2>/dev/null
 ncu -i /tmp/prof_$name.ncu-rep --page source --csv > gpurun_out/src_$name.csv 2>/dev/null
+ncu -i /tmp/prof_$name.ncu-rep --page source --print-source cuda,sass --csv > gpurun_out/srccu_$name.csv 2>/dev/null
 ls -la /tmp/prof_$name.ncu-rep gpurun_out/raw_$name.csv gpurun_out/src_$name.csv
 rm -f /tmp/prof_$name.ncu-rep
