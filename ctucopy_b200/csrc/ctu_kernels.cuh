@@ -106,29 +106,65 @@ __device__ __forceinline__ float group_sum16(float v) {
 // real-input split without shared memory.  After pass 2 thread c holds Z[c + 16 k2] in a[k2].
 // X[k] for k = c + 16 j (j < 8) needs Z[k] = a[j] and Z[256-k], which thread (16-c)%16 holds at
 // index 15-j (thread 0 pairs with itself at index 16-j).  Same arithmetic as rfft_split.
-__device__ __forceinline__ void rfft_split_shfl(const cpx<float> (&a)[16], int c, const cpx<float> *twsplit, cpx<float> (&lo)[8],
-                                                cpx<float> (&hi)[8], cpx<float> &mid) {
+template <class T>
+__device__ __forceinline__ void rfft_split_shfl(const cpx<T> (&a)[16], int c, const cpx<T> *twsplit, cpx<T> (&lo)[8], cpx<T> (&hi)[8],
+                                                cpx<T> &mid) {
     const unsigned m = 0xffffu << (threadIdx.x & 16);
     const int src = (16 - c) & 15;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        cpx<float> Z;
+        cpx<T> Z;
         Z.x = __shfl_sync(m, a[15 - j].x, src, 16);
         Z.y = __shfl_sync(m, a[15 - j].y, src, 16);
         if (c == 0 && j >= 1) Z = a[j >= 1 ? 16 - j : 0];
-        const cpx<float> A = a[j];
+        const cpx<T> A = a[j];
         if (j == 0 && c == 0) {
-            lo[j] = mk<float>(A.x + A.y, 0.f);
-            hi[j] = mk<float>(A.x - A.y, 0.f);
+            lo[j] = mk<T>(A.x + A.y, (T)0);
+            hi[j] = mk<T>(A.x - A.y, (T)0);
         } else {
-            const cpx<float> B = conj(Z);
-            const cpx<float> E = mk<float>(0.5f * (A.x + B.x), 0.5f * (A.y + B.y));
-            const cpx<float> Tt = cmul(twsplit[c + 16 * j], A - B);
+            const cpx<T> B = conj(Z);
+            const cpx<T> E = mk<T>((T)0.5 * (A.x + B.x), (T)0.5 * (A.y + B.y));
+            const cpx<T> Tt = cmul(twsplit[c + 16 * j], A - B);
             lo[j] = E + Tt;
             hi[j] = conj(E - Tt);
         }
     }
     mid = conj(a[8]);   // X[128], meaningful for c == 0
+}
+
+// inverse counterpart: half-complex bins (lo[j] = X[k], hi[j] = X[256-k] for k = c + 16 j, mid =
+// X[128] on thread 0) -> the column a[n1] = conj(Zc[16 n1 + c]) that the first inverse pass
+// wants, again by swapping with thread (16-c)%16 instead of going through shared memory.
+// Same arithmetic as irfft_presplit + fft256_load_column.
+template <class T>
+__device__ __forceinline__ void irfft_presplit_shfl(cpx<T> (&a)[16], int c, const cpx<T> *twinv, const cpx<T> (&lo)[8], const cpx<T> (&hi)[8],
+                                                    cpx<T> mid) {
+    const unsigned m = 0xffffu << (threadIdx.x & 16);
+    const int src = (16 - c) & 15;
+    cpx<T> zn[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (j == 0 && c == 0) {
+            a[0] = conj(mk<T>(lo[0].x + hi[0].x, lo[0].x - hi[0].x));
+            zn[0] = mk<T>((T)0, (T)0);
+        } else {
+            const cpx<T> S = lo[j] + conj(hi[j]);
+            const cpx<T> U = cmul(lo[j] - conj(hi[j]), twinv[c + 16 * j]);
+            a[j] = conj(mk<T>(S.x - U.y, S.y + U.x));           // conj(Zc[k])
+            zn[j] = conj(mk<T>(S.x + U.y, -S.y + U.x));         // conj(Zc[256-k])
+        }
+    }
+    // Zc[128] pairs with itself (thread 0): S = 2 Re(mid), U = 2i Im(mid) * twinv[128]
+    const cpx<T> Um = cmul(mk<T>((T)0, (T)2 * mid.y), twinv[128]);
+    const cpx<T> z128 = conj(mk<T>((T)2 * mid.x - Um.y, Um.x));
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        cpx<T> v;
+        v.x = __shfl_sync(m, zn[r].x, src, 16);
+        v.y = __shfl_sync(m, zn[r].y, src, 16);
+        if (c == 0) v = (r == 7) ? z128 : zn[r < 7 ? r + 1 : 0];
+        a[15 - r] = v;
+    }
 }
 
 // shared-memory carve-up (floats)
@@ -519,15 +555,17 @@ k_delta(const __grid_constant__ DeltaParams D, BatchDesc bd, int tile_rows, E *_
     const int nr = min(tile_rows, T - t0);
     const int64_t row0 = bd.row_off[u];
     const int blk = D.blk;
+    // thread = (column cx of 16, row ry of 16): no divisions in the loops
+    const int cx = threadIdx.x & 15, ry = threadIdx.x >> 4;
     int halo = 0;
     for (int k = 0; k < D.n_order; k++) halo += D.win[k];
     const int span = nr + 2 * halo;                       // rows t0-halo .. t0+nr+halo-1 (clamped)
     E *cur = sm;                                          // [span][blk]
     E *nxt = sm + D.span_max * blk;
-    for (int i = threadIdx.x; i < span * blk; i += blockDim.x) {
-        int r = i / blk, col = i - r * blk;
-        int t = min(max(t0 - halo + r, 0), T - 1);
-        cur[i] = fea[(row0 + t) * D.stride + col];
+    for (int r = ry; r < span; r += 16) {
+        const int t = min(max(t0 - halo + r, 0), T - 1);
+        const E *g = fea + (row0 + t) * D.stride;
+        for (int col = cx; col < blk; col += 16) cur[r * blk + col] = g[col];
     }
     __syncthreads();
     int h = halo;                                         // halo still valid around `cur`
@@ -535,20 +573,23 @@ k_delta(const __grid_constant__ DeltaParams D, BatchDesc bd, int tile_rows, E *_
         const int W = D.win[k];
         const int hn = h - W;                             // halo of the next block
         const int rows_n = nr + 2 * hn;
-        for (int i = threadIdx.x; i < rows_n * blk; i += blockDim.x) {
-            int r = i / blk, col = i - r * blk;           // r: index into next (offset hn)
-            int t = t0 - hn + r;                          // absolute row of this output
-            int tc = min(max(t, 0), T - 1);               // replicated edge: value of the clamped row
-            // window rows around tc, each clamped to [0, T-1]; position in `cur` = row - (t0 - h)
-            E acc = 0;
-            for (int j = 1; j <= W; j++) {
-                int tp = min(tc + j, T - 1), tm = max(tc - j, 0);
-                acc += (E)j * (cur[(tp - (t0 - h)) * blk + col] - cur[(tm - (t0 - h)) * blk + col]);
+        const E scale = (sizeof(E) == 8) ? (E)D.inv_den64[k] : (E)D.inv_den[k];
+        for (int r = ry; r < rows_n; r += 16) {           // r: index into next (offset hn)
+            const int t = t0 - hn + r;                    // absolute row of this output
+            const int tc = min(max(t, 0), T - 1);         // replicated edge: value of the clamped row
+            const bool own = (t >= t0 && t < t0 + nr);
+            for (int col = cx; col < blk; col += 16) {
+                // window rows around tc, each clamped to [0, T-1]; position in `cur` = row - (t0 - h)
+                E acc = 0;
+                for (int j = 1; j <= W; j++) {
+                    const int tp = min(tc + j, T - 1), tm = max(tc - j, 0);
+                    acc += (E)j * (cur[(tp - (t0 - h)) * blk + col] - cur[(tm - (t0 - h)) * blk + col]);
+                }
+                E v = acc * scale;
+                if (W == 1 && tc == T - 1) v = 0;         // reference quirk for win == 1 (see oracle)
+                nxt[r * blk + col] = v;
+                if (own) fea[(row0 + t) * D.stride + (k + 1) * blk + col] = v;
             }
-            E v = acc * (sizeof(E) == 8 ? (E)D.inv_den64[k] : (E)D.inv_den[k]);
-            if (W == 1 && tc == T - 1) v = 0;           // reference quirk for win == 1 (see oracle)
-            nxt[i] = v;
-            if (t >= t0 && t < t0 + nr) fea[(row0 + t) * D.stride + (k + 1) * blk + col] = v;
         }
         __syncthreads();
         E *tmp = cur; cur = nxt; nxt = tmp;
@@ -611,11 +652,17 @@ k_trapdct(const __grid_constant__ TrapParams Tp, BatchDesc bd, int tile_rows, co
             const float *v = sm + r * nb + b;
             const float ref = v[(h - 1) * nb];
             if (LT && NT) {
+                // Hamming x DCT-II rows are symmetric (even k) or antisymmetric (odd k) about the
+                // centre of the odd-length trajectory, and removing the mean keeps that: fold
+                // x[j] +- x[L-1-j] first, half the multiplies.  The centre sample is `ref`, so its
+                // own term is zero.
+                constexpr int LH = (LT ? LT : 1) / 2;
 #pragma unroll
-                for (int j = 0; j < (LT ? LT : 1); j++) {
-                    const float x = v[j * nb] - ref;
+                for (int j = 0; j < LH; j++) {
+                    const float xa = v[j * nb] - ref, xb = v[((LT ? LT : 1) - 1 - j) * nb] - ref;
+                    const float sj = xa + xb, dj = xa - xb;
 #pragma unroll
-                    for (int k = 0; k < NA; k++) acc[k] = fmaf(x, Tp.m[k * (LT ? LT : 1) + j], acc[k]);
+                    for (int k = 0; k < NA; k++) acc[k] = fmaf((k & 1) ? sj : dj, Tp.m[k * (LT ? LT : 1) + j], acc[k]);   // row k holds DCT index k+1
                 }
             } else {
                 for (int j = 0; j < L; j++) {

@@ -288,8 +288,8 @@ __device__ __forceinline__ double shfl16d(double v, int src) {
     return __shfl_sync(m, v, src, 16);
 }
 
-template <int CH, bool EXACT>
-__global__ void __launch_bounds__(BURG_THREADS)
+template <int CH, bool EXACT, int MINB>
+__global__ void __launch_bounds__(BURG_THREADS, MINB)
 k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const int16_t *__restrict__ pcm, const float *__restrict__ spec,
        double *__restrict__ ceps, const double2 *__restrict__ g_tw256, const double2 *__restrict__ g_twsplit,
        const double2 *__restrict__ g_twinv, const double *__restrict__ g_win, const double *__restrict__ g_hann) {
@@ -370,12 +370,9 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const i
                 fft256_pass1(a, c, sTw, xch);
             }
             __syncwarp();
-            if (active) fft256_pass2(a, c, xch);
-            __syncwarp();
-            if (active) fft256_store_linear(a, c, xch);
-            __syncwarp();
             if (active) {
-                rfft_split(xch, c, sTs, lo, hi, mid);
+                fft256_pass2(a, c, xch);
+                rfft_split_shfl(a, c, sTs, lo, hi, mid);
                 // (|X|^a or the post-NR spectrum) with the phase of X: every bin is scaled by
                 // E/|X| -- what Xa*cos(phi), Xa*sin(phi) amount to (src/nr/nr.cc:281-292,
                 // src/vad/vad.cc:222-233) -- with the reference's conventions for bin 0
@@ -408,12 +405,9 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const i
                     hi[j] = scale_bin(hi[j], NC - k);
                 }
                 mid = scale_bin(mid, 128);
+                irfft_presplit_shfl(a, c, sTi, lo, hi, mid);
             }
-            __syncwarp();
-            if (active) irfft_presplit(xch, c, sTi, lo, hi, mid);
-            __syncwarp();
-            if (active) fft256_load_column(a, c, xch);
-            __syncwarp();
+            __syncwarp();                                             // pass-2 reads of the exchange tile are done
             if (active) fft256_pass1(a, c, sTw, xch);
             __syncwarp();
             if (active) fft256_pass2(a, c, xch);
@@ -448,14 +442,19 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const i
                 if (ik < ncoef) {
                     double below = shfl16d(eb[CH - 1], (c + 15) & 15);
                     if (c == 0) below = 0.0;
-                    double num = 0, den = 0;
+                    // three independent chains per parity: the sums are latency-bound otherwise
+                    double nu[2] = {0, 0}, df[2] = {0, 0}, db[2] = {0, 0};
 #pragma unroll
                     for (int j = 0; j < CH; j++) {
                         const double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
-                        if (EXACT || c * CH + j < w) { den += ef[j] * ef[j] + pv * pv; num += ef[j] * pv; }
+                        if (EXACT || c * CH + j < w) {
+                            df[j & 1] = fma(ef[j], ef[j], df[j & 1]);
+                            db[j & 1] = fma(pv, pv, db[j & 1]);
+                            nu[j & 1] = fma(ef[j], pv, nu[j & 1]);
+                        }
                     }
-                    num = group_sum16d(num) * 2.0;
-                    den = group_sum16d(den);
+                    const double num = group_sum16d(nu[0] + nu[1]) * 2.0;
+                    const double den = group_sum16d((df[0] + df[1]) + (db[0] + db[1]));
                     const double rc = -num / den;
                     alpha *= 1 - rc * rc;
 #pragma unroll
@@ -508,13 +507,14 @@ static inline int launch_burg(const BurgParams &B, int src_mode, const BatchDesc
     if (bytes > 227 * 1024) { err = "CTU: window shift too large for the Burg detector kernel"; return CTU_ERR_UNSUPPORTED; }
     cudaError_t e;
     lc->begin("k_burg", s);
-#define CTU_BURG_LAUNCH(CH, EX)                                                                                        \
-    e = cudaFuncSetAttribute(k_burg<CH, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);                 \
-    if (e == cudaSuccess) k_burg<CH, EX><<<(unsigned)ntiles, BURG_THREADS, bytes, s>>>(B, src_mode, bd, pcm, spec, ceps, tw, ts, ti, win, hann)
-    if (B.window == 400) { CTU_BURG_LAUNCH(25, true); }
-    else if (B.window == 512) { CTU_BURG_LAUNCH(32, true); }
-    else if (B.window <= 400) { CTU_BURG_LAUNCH(25, false); }
-    else { CTU_BURG_LAUNCH(32, false); }
+#define CTU_BURG_LAUNCH(CH, EX, MB)                                                                                    \
+    e = cudaFuncSetAttribute(k_burg<CH, EX, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);             \
+    if (e == cudaSuccess) k_burg<CH, EX, MB><<<(unsigned)ntiles, BURG_THREADS, bytes, s>>>(B, src_mode, bd, pcm, spec, ceps, tw, ts, ti, win, hann)
+    // two CTAs per SM: capping registers for a third one spills the lattice state and gains nothing (measured)
+    if (B.window == 400) { CTU_BURG_LAUNCH(25, true, 2); }
+    else if (B.window == 512) { CTU_BURG_LAUNCH(32, true, 2); }
+    else if (B.window <= 400) { CTU_BURG_LAUNCH(25, false, 2); }
+    else { CTU_BURG_LAUNCH(32, false, 2); }
 #undef CTU_BURG_LAUNCH
     lc->end(s);
     if (e == cudaSuccess) e = cudaGetLastError();
@@ -716,10 +716,11 @@ k_vad_compact(const int *__restrict__ nframes, const int64_t *__restrict__ row_o
 constexpr int SYN_THREADS = 256;
 constexpr int SYN_GROUPS = SYN_THREADS / GROUP;
 
-// frames a synthesis tile may hold: two passes of SYN_GROUPS frames.  A tile of the plan's
-// synthesis tile list covers SYN_FRAMES - hh new hops, so that together with the hh frames
-// before it that still overlap its first sample no pass runs partly empty.
-constexpr int SYN_FRAMES = 2 * SYN_GROUPS;
+// frames a synthesis tile holds: one per group, a single pass.  A tile of the plan's synthesis
+// tile list covers SYN_FRAMES - hh new hops, so that together with the hh frames before it
+// that still overlap its first sample every group is busy.  (Two passes per CTA needed 140 KB
+// of shared memory = one CTA per SM; one pass needs 91 KB = two.)
+constexpr int SYN_FRAMES = SYN_GROUPS;
 
 // WT / ST: window and shift known at compile time (0 = runtime) -- turns the divisions of the
 // overlap-add index arithmetic into shifts / multiplies and prunes the zero padding.
@@ -755,14 +756,12 @@ k_synth(const __grid_constant__ SynthParams S, int window, int wshift, float pre
     const int c = tid & (GROUP - 1), grp = tid / GROUP;
     cpx<float> *xch = sX + grp * (XPAD * 16);
     const float inv_w = 1.0f / (float)w;
-    const int npass = (nfr + SYN_GROUPS - 1) / SYN_GROUPS;
-#pragma unroll 1
-    for (int pass = 0; pass < npass; pass++) {
-        const int f = pass * SYN_GROUPS + grp;
+    {
+        const int f = grp;
         const bool active = f < nfr;
-        cpx<float> a[16], lo[8], hi[8], mid;
-        float Alo[8], Ahi[8], Amid = 0.f;
         if (active) {
+            cpx<float> a[16], lo[8], hi[8], mid;
+            float Alo[8], Ahi[8], Amid = 0.f;
             // enhanced magnitudes of this frame: issued first so that their HBM latency hides
             // behind the forward transform
             const float *srow = spec + (bd.row_off[u] + tfirst + f) * NBIN;
@@ -788,15 +787,11 @@ k_synth(const __grid_constant__ SynthParams S, int window, int wshift, float pre
                     if (i0 + 1 < w) a[n1].y -= mean;
                 }
             }
-            fft256_pass1(a, c, sTw, xch);
-        }
-        __syncwarp();
-        if (active) fft256_pass2(a, c, xch);
-        __syncwarp();
-        if (active) fft256_store_linear(a, c, xch);
-        __syncwarp();
-        if (active) {
-            rfft_split(xch, c, sTs, lo, hi, mid);
+            const unsigned hm = 0xffffu << (tid & 16);
+            fft256_pass1_rec(a, c, sTw, xch);
+            __syncwarp(hm);
+            fft256_pass2(a, c, xch);
+            rfft_split_shfl(a, c, sTs, lo, hi, mid);
             // enhanced magnitude with the ORIGINAL phase: scale X by |X|enh / (|X| nfft);
             // bin 0 has phase 0, the Nyquist bin is always written non-negative
             // (src/io/out.cc:417-424)
@@ -816,15 +811,10 @@ k_synth(const __grid_constant__ SynthParams S, int window, int wshift, float pre
                 hi[j] = scale_bin(hi[j], Ahi[j], edge);
             }
             mid = scale_bin(mid, Amid, false);
-        }
-        __syncwarp();
-        if (active) irfft_presplit(xch, c, sTi, lo, hi, mid);
-        __syncwarp();
-        if (active) fft256_load_column(a, c, xch);
-        __syncwarp();
-        if (active) fft256_pass1(a, c, sTw, xch);
-        __syncwarp();
-        if (active) {
+            irfft_presplit_shfl(a, c, sTi, lo, hi, mid);
+            __syncwarp(hm);                                     // pass-2 reads of the exchange tile are done
+            fft256_pass1_rec(a, c, sTw, xch);
+            __syncwarp(hm);
             fft256_pass2(a, c, xch);
             float *yt = sYt + f * w;
 #pragma unroll
@@ -834,7 +824,6 @@ k_synth(const __grid_constant__ SynthParams S, int window, int wshift, float pre
                 else if (2 * n < w) yt[2 * n] = a[k2].x;
             }
         }
-        __syncwarp();
     }
     __syncthreads();
     // overlap-add in frame order (fp64 accumulator like the reference's cbuffer), quantise:
