@@ -834,16 +834,25 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
         CK(cudaGetLastError());
     }
     if (h->dp.n_order > 0 && r.t64_n > 0) {
-        size_t bytes = (size_t)2 * h->dp.span_max * h->dp.blk * sizeof(float);
-        CK(cudaFuncSetAttribute(k_delta<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        const bool fast = (h->dp.n_order == 2 && h->dp.win[0] == 2 && h->dp.win[1] == 2 && h->dp.blk <= 16);
+        size_t bytes = fast ? (size_t)(DELTA_ROWS + 8) * h->dp.blk * sizeof(float) : (size_t)2 * h->dp.span_max * h->dp.blk * sizeof(float);
         h->lc.begin("k_delta", s);
-        k_delta<float><<<(unsigned)r.t64_n, 256, bytes, s>>>(h->dp, bd64, DELTA_ROWS, d_fea);
+        if (fast) {
+            k_delta22<float><<<(unsigned)r.t64_n, 256, bytes, s>>>(h->dp, bd64, d_fea);
+        } else {
+            CK(cudaFuncSetAttribute(k_delta<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            k_delta<float><<<(unsigned)r.t64_n, 256, bytes, s>>>(h->dp, bd64, DELTA_ROWS, d_fea);
+        }
         h->lc.end(s);
         CK(cudaGetLastError());
         if (p->d_fea64) {
-            CK(cudaFuncSetAttribute(k_delta<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * bytes)));
             h->lc.begin("k_delta64", s);
-            k_delta<double><<<(unsigned)r.t64_n, 256, 2 * bytes, s>>>(h->dp, bd64, DELTA_ROWS, p->d_fea64);
+            if (fast) {
+                k_delta22<double><<<(unsigned)r.t64_n, 256, 2 * bytes, s>>>(h->dp, bd64, p->d_fea64);
+            } else {
+                CK(cudaFuncSetAttribute(k_delta<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * bytes)));
+                k_delta<double><<<(unsigned)r.t64_n, 256, 2 * bytes, s>>>(h->dp, bd64, DELTA_ROWS, p->d_fea64);
+            }
             h->lc.end(s);
             CK(cudaGetLastError());
         }

@@ -316,16 +316,17 @@ __device__ __forceinline__ void phase_fb(const FrameParams &P, float *sm, const 
         const int lo = P.lo[b], n = P.hi[b] - lo + 1, n4 = n & ~3;
         const float *wq = P.w + P.woff[b];
         const float *r = row + lo;
-        float acc = 0.f;
+        float acc = 0.f, acc1 = 0.f;                 // two chains: the FMA latency is otherwise exposed
         int k = 0;
-        for (; k < n4; k += 4) {                     // same summation order as the reference loop
+        for (; k < n4; k += 4) {
             const float4 wv4 = *reinterpret_cast<const float4 *>(wq + k);
             acc = fmaf(r[k], wv4.x, acc);
-            acc = fmaf(r[k + 1], wv4.y, acc);
+            acc1 = fmaf(r[k + 1], wv4.y, acc1);
             acc = fmaf(r[k + 2], wv4.z, acc);
-            acc = fmaf(r[k + 3], wv4.w, acc);
+            acc1 = fmaf(r[k + 3], wv4.w, acc1);
         }
         for (; k < n; k++) acc = fmaf(r[k], wq[k], acc);
+        acc += acc1;
         float y;
         if (P.inld) {
             y = powf(acc, 0.33f) * P.inld_scale;
@@ -357,15 +358,15 @@ __device__ __forceinline__ void phase_fea(const FrameParams &P, float *sm, const
     } else if (KIND == KIND_DCTC) {
         for (int i = wv; i < P.nrows; i += CTA_THREADS / 32) {
             const float *m = P.m2 + i * P.nbp;
-            float acc = 0.f;
+            float acc = 0.f, acc1 = 0.f;
             for (int k = 0; k < P.nbp; k += 4) {     // pad taps are zero, pad y entries are zeroed
                 const float4 m4 = *reinterpret_cast<const float4 *>(m + k);
                 acc = fmaf(y[k], m4.x, acc);
-                acc = fmaf(y[k + 1], m4.y, acc);
+                acc1 = fmaf(y[k + 1], m4.y, acc1);
                 acc = fmaf(y[k + 2], m4.z, acc);
-                acc = fmaf(y[k + 3], m4.w, acc);
+                acc1 = fmaf(y[k + 3], m4.w, acc1);
             }
-            sO[lane * od + i] = acc;
+            sO[lane * od + i] = acc + acc1;
         }
     }
     __syncthreads();
@@ -594,6 +595,53 @@ k_delta(const __grid_constant__ DeltaParams D, BatchDesc bd, int tile_rows, E *_
         __syncthreads();
         E *tmp = cur; cur = nxt; nxt = tmp;
         h = hn;
+    }
+}
+
+// Fast path for the standard configuration (delta + acceleration, both windows 2, at most 16
+// columns per block): a thread owns one column and four consecutive rows of a 64-row tile and
+// keeps the whole chain in registers.  Replicated edges: the staged tile already holds c at
+// clamped rows, and a delta "at" a row outside the file is the delta of the clamped row
+// (src/fea/fea_delta.cc:70-130, 178-206).
+template <class E>
+__global__ void __launch_bounds__(256)
+k_delta22(const __grid_constant__ DeltaParams D, BatchDesc bd, E *__restrict__ fea) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    E *cur = reinterpret_cast<E *>(sm_raw);               // [DELTA_ROWS + 8][blk]
+    const int2 tile = bd.tiles[blockIdx.x];
+    const int u = tile.x, t0 = tile.y;
+    const int T = bd.nframes[u];
+    const int nr = min(DELTA_ROWS, T - t0);
+    const int64_t row0 = bd.row_off[u];
+    const int blk = D.blk;
+    const int cx = threadIdx.x & 15, seg = threadIdx.x >> 4;
+    const int span = nr + 8;                              // rows t0-4 .. t0+nr+3 (clamped)
+    if (cx < blk)
+        for (int r = seg; r < span; r += 16) {
+            const int t = min(max(t0 - 4 + r, 0), T - 1);
+            cur[r * blk + cx] = fea[(row0 + t) * D.stride + cx];
+        }
+    __syncthreads();
+    const int r0 = seg * 4;                               // first of this thread's rows, relative to t0
+    if (cx >= blk || r0 >= nr) return;
+    const E s1 = (sizeof(E) == 8) ? (E)D.inv_den64[0] : (E)D.inv_den[0];
+    const E s2 = (sizeof(E) == 8) ? (E)D.inv_den64[1] : (E)D.inv_den[1];
+    // delta at rows t0+r0-2 .. t0+r0+5, each taken at the clamped row
+    E d[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int tc = min(max(t0 + r0 - 2 + i, 0), T - 1);
+        const E *c = cur + (tc - (t0 - 4)) * blk + cx;    // position of row tc in the staged tile
+        d[i] = ((c[blk] - c[-blk]) + (E)2 * (c[2 * blk] - c[-2 * blk])) * s1;     // same order as the reference sum
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int t = t0 + r0 + i;
+        if (t >= t0 + nr) break;
+        const E a = ((d[i + 3] - d[i + 1]) + (E)2 * (d[i + 4] - d[i])) * s2;
+        E *o = fea + (row0 + t) * D.stride + cx;
+        o[blk] = d[i + 2];
+        o[2 * blk] = a;
     }
 }
 
