@@ -32,21 +32,36 @@ sys.path.insert(0, ROOT)
 
 B = ["-fs", "16000", "-format_in", "raw", "-dither", "0"]
 WORKLOADS = {
-    # name: (args, algorithmic bytes per frame of the whole step, of the dominant kernel, ~flops per frame, dominant kernel)
+    # name: (args, algorithmic bytes per frame of the whole step, ~flops per frame)
+    # mfcc_exten is the headline: MFCC_0_D_A features at the metric's 10 ms hop with extended spectral subtraction on
+    # the linear spectrum in front (north_star target "MFCC+exten ... pipelines"; BASELINE configs[1]'s algorithm, configs[0]'s
+    # feature kind).  configs[1] verbatim (exten -> waveform, 16 ms hop, no features) is the "exten" workload.
+    "mfcc_exten": (B + ["-preset", "mfcc", "-preem", "0.97", "-nr_mode", "exten", "-format_out", "htk", "-fea_delta", "d_a"], 476, 19000),
     "mfcc_d_a": (B + ["-format_out", "htk", "-w", "25", "-s", "10", "-preem", "0.97", "-fb_scale", "mel", "-fb_shape", "triang",
                       "-fb_power", "on", "-fb_definition", "30filters", "-nr_mode", "none", "-fb_eqld", "off", "-fb_inld", "off",
                       "-fea_kind", "dctc", "-fea_ncepcoefs", "12", "-fea_c0", "on", "-fea_E", "off", "-fea_lifter", "22",
-                      "-fea_rawenergy", "off", "-fea_delta", "d_a", "-d_win", "2", "-a_win", "2", "-t_win", "2"],
-                 476, 372, 18000, "k_frames<pcm,fea>"),
-    "plp": (B + ["-preset", "plpc", "-format_out", "ark=out.ark"], 372, 372, 19000, "k_frames<pcm,fea>"),
+                      "-fea_rawenergy", "off", "-fea_delta", "d_a", "-d_win", "2", "-a_win", "2", "-t_win", "2"], 476, 18000),
+    "plp": (B + ["-preset", "plpc", "-format_out", "ark=out.ark"], 372, 19000),
     "trapdct": (B + ["-format_out", "htk", "-fb_definition", "23filters", "-fb_eqld", "off", "-fb_inld", "off", "-preem", "0.97",
-                     "-fea_kind", "trapdct,51,8"], 1056, 828, 40000, "k_trapdct"),
-    "exten": (B + ["-preset", "exten", "-format_out", "raw"], 1024, 2056, 30000, "k_nr_scan"),
-    "mfcc_exten": (B + ["-preset", "mfcc", "-preem", "0.97", "-nr_mode", "exten", "-format_out", "htk", "-fea_delta", "d_a"],
-                   476, 2056, 19000, "k_nr_scan"),
+                     "-fea_kind", "trapdct,51,8"], 1056, 40000),
+    "exten": (B + ["-preset", "exten", "-format_out", "raw"], 1024, 30000),
     "fwss_burg": (B + ["-preset", "mfcc", "-preem", "0.97", "-nr_mode", "fwss", "-vad", "burg", "-nr_when", "beforeFB",
-                       "-format_out", "pfile=out.pfile"], 380, 416, 70000, "k_burg"),
+                       "-format_out", "pfile=out.pfile"], 380, 70000),
 }
+DEFAULT_WORKLOAD = "mfcc_exten"
+
+
+def kernel_alg_bytes(name, hop, dim, nb):
+    """ALGORITHMIC bytes one frame costs in each kernel: what the kernel must read and write once."""
+    pcm = 2 * hop
+    return {
+        "k_frames<pcm,fea>": pcm + 4 * dim, "k_frames<pcm,spec>": pcm + 4 * 257, "k_frames<pcm,fb>": pcm + 4 * nb,
+        "k_frames<spec,fea>": 4 * 257 + 4 * dim, "k_frames<spec,fb>": 4 * 257 + 4 * nb,
+        "k_nr_scan": 2 * 4 * 257, "k_delta": 4 * dim + 8 * dim, "k_lpc": 4 * nb + 4 * dim, "k_trapdct": 4 * nb + 4 * dim,
+        "k_synth": pcm + 4 * 257 + pcm, "k_burg": pcm + 8 * 16, "k_cepdet": 8 * 16 + 1,
+    }.get(name)
+
+
 METRIC = "feature frames/sec (16 kHz, 10 ms hop)"
 
 
@@ -189,7 +204,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="mfcc_d_a", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
     ap.add_argument("--utts", type=int, default=10000, help="utterances of 10 s per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -229,7 +244,7 @@ def main():
         return float(t.item())
 
     def measure(workload, steps, warmup, e2e_steps, with_clocks):
-        args, bytes_step, bytes_kernel, flops, dom = WORKLOADS[workload]
+        args, bytes_step, flops = WORKLOADS[workload]
         hd = cb.Handle(args, device=local)
         # each rank's shard: its own slice of the utterance list (weak scaling: a.utts per rank)
         uniq = 16
@@ -277,12 +292,23 @@ def main():
         hd.profile(False)
         clocks = sampler.stop() if sampler else None
         ms = max_over_ranks(ms)
-        # dominant kernel: average duration over the timed region
+        # per-kernel average duration over the timed region; the dominant kernel is the one with the largest share
         by = {}
         for n, t in recs:
             by.setdefault(n, []).append(t)
         kern_ms = {n: sum(v) / steps for n, v in by.items()}
-        dom_ms = statistics.mean(by[dom]) if dom in by else None
+        dom = max(kern_ms, key=kern_ms.get) if kern_ms else None
+        dom_ms = kern_ms.get(dom)
+        hop = 256 if workload == "exten" else 160
+        sdim = dim // 3 if ("-fea_delta" in args and dim % 3 == 0) else dim      # static block of a _D_A vector
+        kinfo = {}
+        for n, ms_k in kern_ms.items():
+            d = {"k_delta": sdim, "k_frames<pcm,fea>": sdim if workload != "trapdct" else hd.num_bands,
+                 "k_frames<spec,fea>": sdim, "k_lpc": sdim}.get(n, dim)
+            ab = kernel_alg_bytes(n, hop, d, hd.num_bands)
+            if ab:
+                gbs = frames * ab / (ms_k / 1000.0) / 1e9
+                kinfo[n] = {"ms": ms_k, "alg_bytes_per_frame": ab, "achieved_gbs": gbs}
         # ---- end to end through the public host-buffer call
         e2e = None
         if e2e_steps > 0:
@@ -299,7 +325,7 @@ def main():
             e2e = {"value": world * frames * e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": int(h_pcm.numel() * 2),
                    "d2h_bytes_per_step": int(h_out.numel() * h_out.element_size()), "ms_per_step": 1000 * dt / e2e_steps}
         res = dict(frames=frames, ms=ms, launches=launches, kern_ms=kern_ms, dom=dom, dom_ms=dom_ms, clocks=clocks, e2e=e2e,
-                   bytes_step=bytes_step, bytes_kernel=bytes_kernel, flops=flops, dim=dim, args=args)
+                   bytes_step=bytes_step, kinfo=kinfo, flops=flops, dim=dim, args=args)
         plan.close(); hd.close()
         del d_pcm, d_out, h_pcm, h_out
         torch.cuda.empty_cache()
@@ -309,18 +335,25 @@ def main():
     hbm, peak_src = peaks()
     value = world * r["frames"] * a.steps / (r["ms"] / 1000.0)
     roof = None
-    if r["dom_ms"]:
-        ach = r["frames"] * r["bytes_kernel"] / (r["dom_ms"] / 1000.0) / 1e9
+    for k in r["kinfo"].values():
+        k["frac"] = k["achieved_gbs"] / hbm
+    if r["dom"] in r["kinfo"]:
+        ki = r["kinfo"][r["dom"]]
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(a.workload + ":" + r["dom"])
-        roof = {"bound": "hbm", "kernel": r["dom"], "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
-                "peak_source": peak_src, "kernel_ms": r["dom_ms"], "alg_bytes_per_frame": r["bytes_kernel"],
+            t = json.load(open(tp)).get(a.workload + ":" + r["dom"])
+            if t:   # measured DRAM bytes per frame (ncu --set full) x frames of this launch
+                traffic = t["dram_bytes_per_frame"] * r["frames"]
+        roof = {"bound": "hbm", "kernel": r["dom"], "achieved": ki["achieved_gbs"], "peak": hbm, "unit": "GB/s", "frac": ki["frac"],
+                "traffic": traffic, "peak_source": peak_src, "kernel_ms": ki["ms"], "alg_bytes_per_frame": ki["alg_bytes_per_frame"],
+                "alg_bytes_per_launch": ki["alg_bytes_per_frame"] * r["frames"],
                 "step_alg_bytes_per_frame": r["bytes_step"],
                 "step_hbm_frac": (value / world) * r["bytes_step"] / 1e9 / hbm,
                 "fp32_frac_of_74TF": (value / world) * r["flops"] / 74e12,
-                "note": "front end is FP32/shared-memory bound (FFT), not HBM bound: see DESIGN.md"}
+                "kernels": r["kinfo"],
+                "note": "dominant kernel = largest share of the step; the FFT front end is FP32 / shared-memory-pipe bound, not HBM "
+                        "bound (DESIGN.md 3); k_nr_scan is the HBM-bound kernel of this path"}
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": r["ms"] / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -357,7 +390,7 @@ def main():
                              "kernel_ms_per_step": x["kern_ms"], "e2e": x["e2e"],
                              "step_hbm_frac": (v / world) * x["bytes_step"] / 1e9 / hbm,
                              "dominant": x["dom"],
-                             "dominant_hbm_frac": (x["frames"] * x["bytes_kernel"] / (x["dom_ms"] / 1000.0) / 1e9 / hbm) if x["dom_ms"] else None}
+                             "kernels": {n: dict(k, frac=k["achieved_gbs"] / hbm) for n, k in x["kinfo"].items()}}
             except Exception as e:
                 others[w] = {"error": str(e)}
         line["workloads"] = others

@@ -209,6 +209,10 @@ class Handle:
         return bool(self.L.ctu_is_signal_output(self.h))
 
     @property
+    def num_bands(self) -> int:
+        return int(self.L.ctu_num_bands(self.h))
+
+    @property
     def launch_count(self) -> int:
         return int(self.L.ctu_launch_count(self.h))
 

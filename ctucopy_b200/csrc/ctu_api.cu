@@ -24,7 +24,7 @@ using namespace ctu;
 // ------------------------------------------------------------------------------------------
 struct ctu_handle {
     ctu_config cfg;
-    int device = 0;
+    int device = 0, num_sms = 148;
     std::string err;
     LaunchCtx lc;
     CtuFbDesign fb;
@@ -489,6 +489,7 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
         return bail(CTU_ERR_CUDA);
     }
     if (cudaSetDevice(device) != cudaSuccess) { h->err = "CUDA: cudaSetDevice failed"; return bail(CTU_ERR_CUDA); }
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     if ((st = build_fft_tables(h))) return bail(st);
     if ((st = build_tables2(h))) return bail(st);
     if (h->nr_mode != NR_NONE && h->cfg.nr_when == 1 && !h->signal_out) h->precise = true;   // subtraction on band values
@@ -682,14 +683,17 @@ static int launch_frames_w(ctu_handle *h, const FrameParams &P, const ctu_plan *
         h->lc.end(s);
     } else {
         if (ft.n32 <= 0) return CTU_OK;
-        SmemLayout L = smem_layout(P.window, P.wshift, P.nb);
+        SmemLayout L = smem_layout(P.window, P.wshift, P.nb, SRC == SRC_PCM);
         size_t bytes = (size_t)L.total * sizeof(float);
         auto kern = k_frames<SRC, DST, KIND, WT>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         FftTables tb{h->d_tw256, h->d_twsplit, h->d_twinv, h->d_win};
         BatchDesc bd{p->d_pcm_off, p->d_nframes, p->d_row_off, ft.t32};
+        // from PCM: persistent CTAs, two per SM (shared-memory bound), each walks the tile list with stride
+        // gridDim.x and prefetches its next tile; other sources: one tile per CTA, the hardware scheduler overlaps them
+        const unsigned grid = (SRC == SRC_PCM) ? (unsigned)std::min<int64_t>(ft.n32, 2 * (int64_t)h->num_sms) : (unsigned)ft.n32;
         h->lc.begin(names[SRC][DST], s);
-        kern<<<(unsigned)ft.n32, CTA_THREADS, bytes, s>>>(P, bd, tb, pcm, src, dst);
+        kern<<<grid, CTA_THREADS, bytes, s>>>(P, bd, tb, pcm, src, dst, (int)ft.n32);
         h->lc.end(s);
     }
     CK(cudaGetLastError());
@@ -701,8 +705,10 @@ static int launch_frames_t(ctu_handle *h, const FrameParams &P, const ctu_plan *
                            const float *src, float *dst, cudaStream_t s) {
     // the PCM front end is specialised for the two standard window lengths (25 ms and 32 ms
     // at 16 kHz); every other length takes the generic instantiation
-    if (SRC == SRC_PCM && P.window == 400) return launch_frames_w<SRC, DST, KIND, 400>(h, P, p, ft, pcm, src, dst, s);
-    if (SRC == SRC_PCM && P.window == 512) return launch_frames_w<SRC, DST, KIND, 512>(h, P, p, ft, pcm, src, dst, s);
+    if constexpr (SRC == SRC_PCM) {
+        if (P.window == 400) return launch_frames_w<SRC, DST, KIND, 400>(h, P, p, ft, pcm, src, dst, s);
+        if (P.window == 512) return launch_frames_w<SRC, DST, KIND, 512>(h, P, p, ft, pcm, src, dst, s);
+    }
     return launch_frames_w<SRC, DST, KIND, 0>(h, P, p, ft, pcm, src, dst, s);
 }
 

@@ -169,19 +169,26 @@ __device__ __forceinline__ void irfft_presplit_shfl(cpx<T> (&a)[16], int c, cons
 
 // shared-memory carve-up (floats)
 struct SmemLayout {
-    int oP, oY, oD, oW, oX, oTw, oTs, oR, total;
+    int oP, oY, oD, oW, oX, oTw, oTs, oRaw, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int window, int wshift, int nb) {
+__host__ __device__ inline SmemLayout smem_layout(int window, int wshift, int nb, bool from_pcm = true) {
     SmemLayout L;
     int o = 0;
     L.oP = o; o += (TILE_F * LDP + 3) & ~3;
-    L.oD = o; o += ((TILE_F - 1) * wshift + window + 3) & ~3;
+    if (!from_pcm) {
+        // spectrum / band-value sources need the two tiles only: five CTAs per SM instead of two
+        L.oY = o; o += TILE_F * (MAXB + 1);
+        L.oD = L.oW = L.oX = L.oTw = L.oTs = L.oRaw = o;
+        L.total = o;
+        return L;
+    }
+    L.oD = o; o += ((TILE_F - 1) * wshift + window + 7) & ~7;   // staged in runs of 8
     L.oW = o; o += (window + 3) & ~3;
     L.oX = o;                                                  // one 16x17 complex tile per group ...
     L.oY = o; o += (CTA_THREADS / GROUP) * XPAD * 16 * 2;      // ... re-used for the band tile once the transforms are done
     L.oTw = o; o += 256 * 2;
     L.oTs = o; o += 130 * 2;
-    L.oR = o;
+    L.oRaw = o; o += (((TILE_F - 1) * wshift + window + 1 + 8 + 7) / 8) * 4;   // int16 prefetch buffer: 8-sample chunks
     L.total = o;
     (void)nb;
     return L;
@@ -238,12 +245,7 @@ __device__ __forceinline__ void phase_fft(const FrameParams &P, const int16_t *_
     cpx<float> *sTw = reinterpret_cast<cpx<float> *>(sm + L.oTw);
     cpx<float> *sTs = reinterpret_cast<cpx<float> *>(sm + L.oTs);
     const int w = WT ? WT : P.window, s = P.wshift;
-    const int nsamp = (nf - 1) * s + w;
-    stage_preem<CTA_THREADS>(sD, pcm + g0, nsamp, first_tile, P.preem);
-    for (int i = tid; i < w; i += CTA_THREADS) sW[i] = tb.win[i];
-    for (int i = tid; i < 256; i += CTA_THREADS) sTw[i] = mk<float>(tb.tw256[i].x, tb.tw256[i].y);
-    for (int i = tid; i < 129; i += CTA_THREADS) sTs[i] = mk<float>(tb.twsplit[i].x, tb.twsplit[i].y);
-    __syncthreads();
+    (void)pcm; (void)g0; (void)first_tile; (void)tb;
 
     const int c = tid & (GROUP - 1);
     const int grp = tid / GROUP;                          // 0..15
@@ -375,66 +377,167 @@ __device__ __forceinline__ void phase_fea(const FrameParams &P, float *sm, const
 // ------------------------------------------------------------------------------------------
 // the fused frame kernel
 // ------------------------------------------------------------------------------------------
+// ---- PCM prefetch: the next tile's samples travel HBM -> shared memory with cp.async while the
+// current tile is being transformed (the CTAs are persistent).  The raw int16 buffer keeps the
+// 16-byte phase of the source address so that whole 16-byte chunks can be copied; the (at most
+// two) partial chunks at the ends go through a register.
+struct TileMeta { int u, t0, nf; int64_t row0, g0; };
+
+__device__ __forceinline__ TileMeta load_tile_meta(const BatchDesc &bd, int tile, int wshift) {
+    TileMeta m;
+    const int2 t = bd.tiles[tile];
+    m.u = t.x; m.t0 = t.y;
+    m.nf = min(TILE_F, bd.nframes[m.u] - m.t0);
+    m.row0 = bd.row_off[m.u] + m.t0;
+    m.g0 = bd.pcm_off[m.u] + (int64_t)m.t0 * wshift;
+    return m;
+}
+
+// element k of the tile's sample run is sample (k - 1): k = 0 is the sample before the tile
+// (pre-emphasis memory), valid only when the tile is not at the start of its utterance
+__device__ __forceinline__ void prefetch_pcm(int16_t *raw, const int16_t *__restrict__ pcm, const TileMeta &m, int n, int &edge) {
+    const int16_t *S0 = pcm + m.g0 - 1;
+    const int phase = (int)((reinterpret_cast<uintptr_t>(S0) & 15) >> 1);
+    const int kmin = (m.t0 == 0) ? 1 : 0;
+    const int nchunks = (phase + n + 7) >> 3;
+    for (int j = threadIdx.x; j < nchunks; j += CTA_THREADS) {
+        const int k0 = 8 * j - phase;
+        if (k0 >= kmin && k0 + 8 <= n) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(raw + 8 * j);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(S0 + k0) : "memory");
+        }
+    }
+    // partial chunks: the first one (j = 0) and the last one; thread t < 8 takes element t of the
+    // first, thread 8 + t element t of the last
+    edge = 0;
+    if (threadIdx.x < 16) {
+        const int j = (threadIdx.x < 8) ? 0 : nchunks - 1;
+        const int k0 = 8 * j - phase, k = k0 + (threadIdx.x & 7);
+        const bool partial = !(k0 >= kmin && k0 + 8 <= n) && (threadIdx.x < 8 || nchunks > 1);
+        if (partial && k >= kmin && k < n) edge = (int)S0[k];
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// after the copies have landed: partial-chunk elements from the registers, then raw -> float with
+// pre-emphasis (src/io/in.cc:364-372), every sample converted once for all the frames it is in
+__device__ __forceinline__ void finish_pcm(int16_t *raw, float *__restrict__ sD, const int16_t *__restrict__ pcm, const TileMeta &m, int n,
+                                           int edge, float alpha) {
+    const int16_t *S0 = pcm + m.g0 - 1;
+    const int phase = (int)((reinterpret_cast<uintptr_t>(S0) & 15) >> 1);
+    const int kmin = (m.t0 == 0) ? 1 : 0;
+    const int nchunks = (phase + n + 7) >> 3;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (threadIdx.x < 16) {
+        const int j = (threadIdx.x < 8) ? 0 : nchunks - 1;
+        const int k0 = 8 * j - phase, k = k0 + (threadIdx.x & 7);
+        const bool partial = !(k0 >= kmin && k0 + 8 <= n) && (threadIdx.x < 8 || nchunks > 1);
+        if (partial && k >= 0 && k < n) raw[phase + k] = (k >= kmin) ? (int16_t)edge : (int16_t)0;
+    }
+    __syncthreads();
+    const int16_t *x = raw + phase;                       // x[k]: element k
+    const int nsamp = n - 1;
+    for (int i0 = threadIdx.x * 8; i0 < nsamp; i0 += CTA_THREADS * 8) {
+        float prev = s16_to_f32((int)x[i0]);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float xi = (i0 + j < nsamp) ? s16_to_f32((int)x[i0 + j + 1]) : 0.f;
+            v[j] = fmaf(-alpha, prev, xi);
+            prev = xi;
+        }
+        *reinterpret_cast<float4 *>(sD + i0) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(sD + i0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the fused frame kernel: persistent CTAs walk the tile list with stride gridDim.x
+// ------------------------------------------------------------------------------------------
 template <int SRC, int DST, int KIND, int WT>
-__global__ void __launch_bounds__(CTA_THREADS, 2)
+__global__ void __launch_bounds__(CTA_THREADS, SRC == SRC_PCM ? 2 : 4)
 k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, const int16_t *__restrict__ pcm,
-         const float *__restrict__ src, float *__restrict__ dst) {
+         const float *__restrict__ src, float *__restrict__ dst, int ntiles) {
     extern __shared__ __align__(16) float sm[];
-    const SmemLayout L = smem_layout(P.window, P.wshift, P.nb);
-    const int2 tile = bd.tiles[blockIdx.x];
-    const int u = tile.x, t0 = tile.y;
-    const int nf = min(TILE_F, bd.nframes[u] - t0);
-    const int64_t row0 = bd.row_off[u] + t0;
+    const SmemLayout L = smem_layout(P.window, P.wshift, P.nb, SRC == SRC_PCM);
     const int tid = threadIdx.x;
-
+    const int w = WT ? WT : P.window;
+    int16_t *raw = reinterpret_cast<int16_t *>(sm + L.oRaw);
+    int tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    TileMeta cur = load_tile_meta(bd, tile, P.wshift);
+    int edge = 0;
     if (SRC == SRC_PCM) {
-        phase_fft<WT>(P, pcm, bd.pcm_off[u] + (int64_t)t0 * P.wshift, t0 == 0, nf, tb, sm, L);
-    } else if (SRC == SRC_SPEC) {
-        const float *g = src + row0 * NBIN;
-        float *sP = sm + L.oP;
-        for (int i = tid; i < nf * NBIN; i += CTA_THREADS) sP[i] = g[i];
-        __syncthreads();
-    } else {  // SRC_FB: band values (true scale, post ^0.33) straight into sY
-        const float *g = src + row0 * P.nb;
-        float *sY = sm + L.oY;
-        for (int i = tid; i < nf * P.nb; i += CTA_THREADS) {
-            int f = i / P.nb, b = i - f * P.nb;
-            float v = g[i];
-            if (KIND == KIND_DCTC || KIND == KIND_LOGSPEC || KIND == KIND_TRAPLOG) v = logf(v);
-            sY[f * (MAXB + 1) + b] = v;
-        }
-        for (int i = tid; i < TILE_F * (P.nbp - P.nb); i += CTA_THREADS) {
-            const int f = i / (P.nbp - P.nb), b = P.nb + i - f * (P.nbp - P.nb);
-            sY[f * (MAXB + 1) + b] = 0.f;
-        }
-        __syncthreads();
+        prefetch_pcm(raw, pcm, cur, (cur.nf - 1) * P.wshift + w + 1, edge);
+        float *sW = sm + L.oW;
+        cpx<float> *sTw = reinterpret_cast<cpx<float> *>(sm + L.oTw);
+        cpx<float> *sTs = reinterpret_cast<cpx<float> *>(sm + L.oTs);
+        for (int i = tid; i < w; i += CTA_THREADS) sW[i] = tb.win[i];
+        for (int i = tid; i < 256; i += CTA_THREADS) sTw[i] = mk<float>(tb.tw256[i].x, tb.tw256[i].y);
+        for (int i = tid; i < 129; i += CTA_THREADS) sTs[i] = mk<float>(tb.twsplit[i].x, tb.twsplit[i].y);
     }
+#pragma unroll 1
+    for (; tile < ntiles; tile += gridDim.x) {
+        const int next = tile + gridDim.x;
+        TileMeta nxt = cur;
+        if (next < ntiles) nxt = load_tile_meta(bd, next, P.wshift);   // consumed at the end of this iteration
+        const int nf = cur.nf;
+        const int64_t row0 = cur.row0;
 
-    if (DST == DST_SPEC) {
-        float *g = dst + row0 * NBIN;
-        const float *sP = sm + L.oP;
-        for (int i = tid; i < nf * NBIN; i += CTA_THREADS) g[i] = sP[i];
-        return;
-    }
-    if (SRC != SRC_FB) {
-        const bool want_log = (DST == DST_FEA) && (KIND == KIND_DCTC || KIND == KIND_LOGSPEC || KIND == KIND_TRAPLOG);
-        phase_fb(P, sm, L, want_log);
-    }
-    if (DST == DST_FB) {
-        float *g = dst + row0 * P.nb;
-        const float *sY = sm + L.oY;
-        for (int i = tid; i < nf * P.nb; i += CTA_THREADS) {
-            int f = i / P.nb, b = i - f * P.nb;
-            g[i] = sY[f * (MAXB + 1) + b];
+        if (SRC == SRC_PCM) {
+            finish_pcm(raw, sm + L.oD, pcm, cur, (nf - 1) * P.wshift + w + 1, edge, P.preem);
+            __syncthreads();                              // samples staged; the raw buffer is free again
+            if (next < ntiles) prefetch_pcm(raw, pcm, nxt, (nxt.nf - 1) * P.wshift + w + 1, edge);
+            phase_fft<WT>(P, pcm, cur.g0, cur.t0 == 0, nf, tb, sm, L);
+        } else if (SRC == SRC_SPEC) {
+            const float *g = src + row0 * NBIN;
+            float *sP = sm + L.oP;
+            for (int i = tid; i < nf * NBIN; i += CTA_THREADS) sP[i] = g[i];
+            __syncthreads();
+        } else {  // SRC_FB: band values (true scale, post ^0.33) straight into sY
+            const float *g = src + row0 * P.nb;
+            float *sY = sm + L.oY;
+            for (int i = tid; i < nf * P.nb; i += CTA_THREADS) {
+                int f = i / P.nb, b = i - f * P.nb;
+                float v = g[i];
+                if (KIND == KIND_DCTC || KIND == KIND_LOGSPEC || KIND == KIND_TRAPLOG) v = logf(v);
+                sY[f * (MAXB + 1) + b] = v;
+            }
+            for (int i = tid; i < TILE_F * (P.nbp - P.nb); i += CTA_THREADS) {
+                const int f = i / (P.nbp - P.nb), b = P.nb + i - f * (P.nbp - P.nb);
+                sY[f * (MAXB + 1) + b] = 0.f;
+            }
+            __syncthreads();
         }
-        return;
-    }
-    phase_fea<KIND>(P, sm, L);
-    const float *sO = sm + L.oP;
-    const int od = P.out_dim;
-    for (int i = tid; i < nf * od; i += CTA_THREADS) {
-        int f = i / od, col = i - f * od;
-        dst[(row0 + f) * P.out_stride + col] = sO[i];
+
+        if (DST == DST_SPEC) {
+            float *g = dst + row0 * NBIN;
+            const float *sP = sm + L.oP;
+            for (int i = tid; i < nf * NBIN; i += CTA_THREADS) g[i] = sP[i];
+        } else {
+            if (SRC != SRC_FB) {
+                const bool want_log = (DST == DST_FEA) && (KIND == KIND_DCTC || KIND == KIND_LOGSPEC || KIND == KIND_TRAPLOG);
+                phase_fb(P, sm, L, want_log);
+            }
+            if (DST == DST_FB) {
+                float *g = dst + row0 * P.nb;
+                const float *sY = sm + L.oY;
+                for (int i = tid; i < nf * P.nb; i += CTA_THREADS) {
+                    int f = i / P.nb, b = i - f * P.nb;
+                    g[i] = sY[f * (MAXB + 1) + b];
+                }
+            } else {
+                phase_fea<KIND>(P, sm, L);
+                const float *sO = sm + L.oP;
+                const int od = P.out_dim;
+                for (int i = tid; i < nf * od; i += CTA_THREADS) {
+                    int f = i / od, col = i - f * od;
+                    dst[(row0 + f) * P.out_stride + col] = sO[i];
+                }
+            }
+        }
+        __syncthreads();                                  // the tiles in shared memory are re-used by the next iteration
+        cur = nxt;
     }
 }
 
