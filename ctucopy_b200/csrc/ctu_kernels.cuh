@@ -174,7 +174,7 @@ struct SmemLayout {
 __host__ __device__ inline SmemLayout smem_layout(int window, int wshift, int nb, bool from_pcm = true) {
     SmemLayout L;
     int o = 0;
-    L.oP = o; o += (TILE_F * LDP + 3) & ~3;
+    L.oP = o; o += ((TILE_F * LDP + 3) & ~3) + (from_pcm ? 0 : 4);    // +4: the tile keeps the 16-byte phase of its HBM address
     if (!from_pcm) {
         // spectrum / band-value sources need the two tiles only: five CTAs per SM instead of two
         L.oY = o; o += TILE_F * (MAXB + 1);
@@ -483,6 +483,10 @@ k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, cons
         if (next < ntiles) nxt = load_tile_meta(bd, next, P.wshift);   // consumed at the end of this iteration
         const int nf = cur.nf;
         const int64_t row0 = cur.row0;
+        // spectrum source: position of the tile inside its 16-byte line (floats); shifts the tile in shared memory
+        const int spec_phase = (SRC == SRC_SPEC) ? (int)((reinterpret_cast<uintptr_t>(src + row0 * NBIN) >> 2) & 3) : 0;
+        SmemLayout Lt = L;
+        Lt.oP += spec_phase;
 
         if (SRC == SRC_PCM) {
             finish_pcm(raw, sm + L.oD, pcm, cur, (nf - 1) * P.wshift + w + 1, edge, P.preem);
@@ -490,9 +494,21 @@ k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, cons
             if (next < ntiles) prefetch_pcm(raw, pcm, nxt, (nxt.nf - 1) * P.wshift + w + 1, edge);
             phase_fft<WT>(P, pcm, cur.g0, cur.t0 == 0, nf, tb, sm, L);
         } else if (SRC == SRC_SPEC) {
+            // the tile is one contiguous run of nf*257 floats: 16-byte cp.async for the aligned body (all of
+            // a thread's copies are in flight at once), scalar loads for the ragged ends
             const float *g = src + row0 * NBIN;
-            float *sP = sm + L.oP;
-            for (int i = tid; i < nf * NBIN; i += CTA_THREADS) sP[i] = g[i];
+            float *sP = sm + L.oP + spec_phase;
+            const int n = nf * NBIN;
+            const int head = min(n, (4 - spec_phase) & 3);            // floats before the first 16-byte boundary
+            const int body = (n - head) & ~3;
+            for (int i = tid * 4; i < body; i += CTA_THREADS * 4) {
+                const unsigned d = (unsigned)__cvta_generic_to_shared(sP + head + i);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g + head + i) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (tid < head) sP[tid] = g[tid];
+            if (tid >= 32 && tid - 32 < n - head - body) sP[head + body + tid - 32] = g[head + body + tid - 32];
+            asm volatile("cp.async.wait_all;" ::: "memory");
             __syncthreads();
         } else {  // SRC_FB: band values (true scale, post ^0.33) straight into sY
             const float *g = src + row0 * P.nb;
@@ -512,12 +528,12 @@ k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, cons
 
         if (DST == DST_SPEC) {
             float *g = dst + row0 * NBIN;
-            const float *sP = sm + L.oP;
+            const float *sP = sm + Lt.oP;
             for (int i = tid; i < nf * NBIN; i += CTA_THREADS) g[i] = sP[i];
         } else {
             if (SRC != SRC_FB) {
                 const bool want_log = (DST == DST_FEA) && (KIND == KIND_DCTC || KIND == KIND_LOGSPEC || KIND == KIND_TRAPLOG);
-                phase_fb(P, sm, L, want_log);
+                phase_fb(P, sm, Lt, want_log);
             }
             if (DST == DST_FB) {
                 float *g = dst + row0 * P.nb;
