@@ -32,6 +32,7 @@ struct ctu_handle {
     bool signal_out = false, do_vad = false, vad_drop = false;
     int vad_cri = VCRI_ENERGY, vad_thr = VTHR_PERC;
     int static_dim = 0, feature_dim = 0;
+    int energy_mode = 0, energy_latency = 0;   // optional _E column (last column of every row)
     FrameParams fp;      // filter bank + second stage tables
     DeltaParams dp;
     TrapParams tp;
@@ -75,6 +76,7 @@ struct ctu_plan {
     float *d_spec = nullptr, *d_fb = nullptr, *d_log = nullptr;
     double *d_fb64 = nullptr;            // band values of the precise path
     double *d_fea64 = nullptr;           // fp64 copy of the feature matrix (feature-vector VAD criterion)
+    float *d_E = nullptr;                // log energy per frame (-fea_E)
     double *d_ceps = nullptr;            // Burg cepstra [frames x ncoef]
     double *d_cri = nullptr;             // VAD criterion per frame
     uint8_t *d_flags = nullptr;          // NR-internal detector decisions
@@ -372,7 +374,7 @@ static int build_delta_trap_params(ctu_handle *h) {
     if (n_order > 0 && !c.fea_c0)
         return fail(h, CTU_ERR_UNSUPPORTED, "CTU: deltas with -fea_c0 off (the reference writes uninitialised columns there, src/io/out.cc:189-201)");
     D.blk = h->static_dim;
-    h->feature_dim = h->static_dim * (n_order + 1);
+    h->feature_dim = h->static_dim * (n_order + 1) + (c.fea_E ? 1 : 0);
     D.stride = h->feature_dim;
     D.span_max = DELTA_ROWS + 2 * halo;
     if (h->fea_kind == FEA_TRAPDCT) {
@@ -397,7 +399,20 @@ static int build_delta_trap_params(ctu_handle *h) {
         h->feature_dim = h->fb.nb * n;
         T.out_stride = h->feature_dim;
     }
-    if (c.fea_E) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_E on (energy column) is not built yet");
+    if (c.fea_E) {
+        // which stage's E the writer points at: BATCH::init_out (src/io/batch.cc:98-118)
+        if (h->fea_kind == FEA_TRAPDCT) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_E with trapdct (the reference never sets that energy)");
+        if (!std::strcmp(c.format_out, "pfile")) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_E with pfile output (the reference declares the pfile without the energy column, src/io/out.cc:252)");
+        if (c.fea_rawenergy) h->energy_mode = EN_RAW;
+        else if (h->fea_kind == FEA_DCTC) h->energy_mode = (c.nr_when == 1) ? EN_IN : EN_NR;
+        else if (h->fea_kind == FEA_LPA || h->fea_kind == FEA_LPC) h->energy_mode = EN_LPC;
+        else h->energy_mode = EN_BANDS;
+        // the row is written `latency` frames after its energy was current (deltas, VAD majority filter)
+        int lat = 0;
+        for (int k = 0; k < n_order; k++) lat += wins[k];
+        if (h->do_vad) lat += (c.vad_filter_order - 1) / 2;
+        h->energy_latency = lat;
+    }
     return CTU_OK;
 }
 
@@ -476,6 +491,7 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     if ((st = build_delta_trap_params(h))) return bail(st);
     if ((st = build_nr_params(h->cfg, h->nr_mode, h->vad_src, h->signal_out, h->fb.nb, h->nrp, h->sp, h->bp, h->vp, h->err))) return bail(st);
     h->vp.cri = h->vad_cri; h->vp.thr = h->vad_thr; h->vp.drop = h->vad_drop;
+    h->vp.has_E = h->energy_mode ? 1 : 0;
     // the reference's vector is in internal order (c0 first, a0 first); rows here are in writer order
     if (h->fea_kind == FEA_DCTC || h->fea_kind == FEA_LPC) h->vp.fea_skip = h->cfg.fea_c0 ? h->static_dim - 1 : -1;
     else if (h->fea_kind == FEA_LPA) h->vp.fea_skip = -1;
@@ -595,6 +611,7 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     if (need_fb && !h->precise && (st = dev_alloc(h, p, &p->d_fb, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     if (need_fb && h->precise && (st = dev_alloc(h, p, &p->d_fb64, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     if (h->do_vad && h->vad_cri == VCRI_CEPDIST_FEA && (st = dev_alloc(h, p, &p->d_fea64, (size_t)rows * h->feature_dim))) { ctu_plan_destroy(p); return st; }
+    if (h->energy_mode && (st = dev_alloc(h, p, &p->d_E, (size_t)rows))) { ctu_plan_destroy(p); return st; }
     if (h->fea_kind == FEA_TRAPDCT && (st = dev_alloc(h, p, &p->d_log, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     const bool burg_nr = h->nr_mode >= NR_HWSS && h->vad_src == VADSRC_BURG;
     const bool burg_vad = h->do_vad && h->vad_cri == VCRI_CEPDIST_LPC;
@@ -613,7 +630,7 @@ void ctu_plan_destroy(ctu_plan *p) {
     cudaSetDevice(p->h->device);
     cudaFree(p->d_pcm_off); cudaFree(p->d_row_off); cudaFree(p->d_osamp_off); cudaFree(p->d_t32_off); cudaFree(p->d_t64_off);
     cudaFree(p->d_nframes); cudaFree(p->d_tiles32); cudaFree(p->d_tiles64); cudaFree(p->d_tilesS); cudaFree(p->d_tS_off); cudaFree(p->d_tilesF); cudaFree(p->d_tF_off);
-    cudaFree(p->d_spec); cudaFree(p->d_fb); cudaFree(p->d_fb64); cudaFree(p->d_fea64); cudaFree(p->d_log); cudaFree(p->d_ceps); cudaFree(p->d_cri);
+    cudaFree(p->d_spec); cudaFree(p->d_fb); cudaFree(p->d_fb64); cudaFree(p->d_fea64); cudaFree(p->d_E); cudaFree(p->d_log); cudaFree(p->d_ceps); cudaFree(p->d_cri);
     cudaFree(p->d_flags); cudaFree(p->d_keep); cudaFree(p->d_vad0); cudaFree(p->d_rows);
     cudaFree(p->d_pcm); cudaFree(p->d_wave); cudaFree(p->d_fea); cudaFree(p->d_ext); cudaFree(p->d_vadnr_out); cudaFree(p->d_vad_out);
     delete p;
@@ -796,6 +813,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     int od = h->static_dim, ostride = h->feature_dim;
     if (kind == KIND_TRAPLOG) { fea_dst = p->d_log; od = h->fb.nb; ostride = h->fb.nb; }
     P = h->fp; P.out_dim = od; P.out_stride = ostride;
+    P.energy_mode = h->energy_mode; P.energy = p->d_E;
     if (h->precise) {
         // fp64 path (ctu_precise.cuh): band-domain noise reduction / ill-conditioned LPC /
         // features that feed VAD decisions
@@ -816,7 +834,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
         }
     } else if (kind == KIND_LPA || kind == KIND_LPC) {
         // band values to HBM (76 B per frame for PLP), then one thread per frame for the recursion
-        FrameParams Pf = h->fp; Pf.out_dim = h->fb.nb; Pf.out_stride = h->fb.nb;
+        FrameParams Pf = h->fp; Pf.out_dim = h->fb.nb; Pf.out_stride = h->fb.nb;   // (its energy comes from k_lpc: log R0)
         if (need_spec) { if ((st = launch_frames_t<SRC_SPEC, DST_FB, KIND_SPEC>(h, Pf, p, ft, nullptr, p->d_spec, p->d_fb, s))) return st; }
         else if ((st = launch_frames_t<SRC_PCM, DST_FB, KIND_SPEC>(h, Pf, p, ft, d_pcm, nullptr, p->d_fb, s))) return st;
         if ((st = launch_lpc(h, P, kind == KIND_LPC, r.row0, r.nrows, p->d_fb, fea_dst, s))) return st;
@@ -862,6 +880,17 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
             h->lc.end(s);
             CK(cudaGetLastError());
         }
+    }
+    if (h->energy_mode && r.t64_n > 0) {
+        if (h->energy_mode == EN_RAW) {
+            h->lc.begin("k_rawenergy", s);
+            k_rawenergy<<<(unsigned)r.t64_n, 256, 0, s>>>(bd64, h->cfg.window, h->cfg.wshift, d_pcm, p->d_E);
+            h->lc.end(s);
+        }
+        h->lc.begin("k_place_energy", s);
+        k_place_energy<<<(unsigned)r.t64_n, 256, 0, s>>>(bd64, h->energy_latency, h->feature_dim, p->d_E, d_fea);
+        h->lc.end(s);
+        CK(cudaGetLastError());
     }
     // ---- stage 4: VAD module -----------------------------------------------------------------
     if (h->do_vad) {

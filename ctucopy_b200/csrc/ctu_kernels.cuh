@@ -46,6 +46,7 @@ constexpr int MAXB = 64;          // filter-bank bands
 constexpr int MAXW = 2560;        // packed filter-bank taps
 constexpr int MAXR = 40;          // rows of the second-stage matrix (cepstra / autocorrelation lags)
 constexpr int MAXM2 = 2048;       // second-stage matrix entries (rows x nb)
+constexpr int DELTA_ROWS_C = 64;   // rows per tile of the 64-row tile list (= DELTA_ROWS)
 constexpr int LDP = NBIN;         // pitch of the spectrum tile (257: odd -> lane==frame reads are conflict free)
 
 enum Src { SRC_PCM = 0, SRC_SPEC = 1, SRC_FB = 2 };
@@ -78,6 +79,18 @@ struct FrameParams {
     // output geometry
     int out_dim;           // values this kernel writes per row
     int out_stride;        // floats per row of the destination matrix
+    // optional _E column: which stage's energy the writer points at
+    // (BATCH::init_out, src/io/batch.cc:98-118); written per frame into `energy`
+    int energy_mode;       // EnergyMode
+    float *energy;         // [total frames] log energies (device), nullptr when unused
+};
+enum EnergyMode {
+    EN_NONE = 0,
+    EN_NR = 1,             // _NR::compute_E (src/nr/nr.cc:36-45): sum of SQUARES of the spectrum handed to the filter bank
+    EN_IN = 2,             // rawIN::get_frame (src/io/in.cc:403-413): sum of the POWER spectrum
+    EN_BANDS = 3,          // specFEA / logspecFEA (src/fea/fea_impl.cc:45-50, 69-74): sum of squares of the band values
+    EN_LPC = 4,            // lpaFEA (src/fea/fea_impl.cc:177): log R0
+    EN_RAW = 5             // raw energy (src/io/in.cc:353-361), own kernel
 };
 
 struct BatchDesc {
@@ -164,6 +177,34 @@ __device__ __forceinline__ void irfft_presplit_shfl(cpx<T> (&a)[16], int c, cons
         v.y = __shfl_sync(m, zn[r].y, src, 16);
         if (c == 0) v = (r == 7) ? z128 : zn[r < 7 ? r + 1 : 0];
         a[15 - r] = v;
+    }
+}
+
+
+// E = log(2 * (t_0/2 + t_last/2 + sum of the inner terms)) over one row of n values, term = v or
+// v*v; one warp per row, `lane` strided.  The reference's formula for the energy of a
+// half spectrum (src/io/in.cc:403-413, src/nr/nr.cc:36-45).
+__device__ __forceinline__ float half_spectrum_energy(const float *row, int n, bool square) {
+    const int lane = threadIdx.x & 31;
+    float acc = 0.f;
+    for (int k = lane; k < n; k += 32) {
+        float v = row[k];
+        if (square) v *= v;
+        if (k == 0 || k == n - 1) v *= 0.5f;
+        acc += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return logf(acc * 2.f);
+}
+
+// frames of the spectrum tile dealt to the warps: energy of each (modes EN_NR / EN_IN)
+__device__ __forceinline__ void tile_energy(const FrameParams &P, const float *sP, int nf, int64_t row0) {
+    if (P.energy_mode != EN_NR && P.energy_mode != EN_IN) return;
+    const bool square = (P.energy_mode == EN_NR) || P.take_sqrt;      // EN_IN sums power: squares of a magnitude tile
+    for (int f = threadIdx.x >> 5; f < nf; f += CTA_THREADS / 32) {
+        const float e = half_spectrum_energy(sP + f * LDP, NBIN, square);
+        if ((threadIdx.x & 31) == 0) P.energy[row0 + f] = e;
     }
 }
 
@@ -350,13 +391,21 @@ __device__ __forceinline__ void phase_fb(const FrameParams &P, float *sm, const 
 // phase C variants: sY -> output tile (re-using the spectrum tile area as staging)
 // ------------------------------------------------------------------------------------------
 template <int KIND>
-__device__ __forceinline__ void phase_fea(const FrameParams &P, float *sm, const SmemLayout &L) {
+__device__ __forceinline__ void phase_fea(const FrameParams &P, float *sm, const SmemLayout &L, int nf, int64_t row0) {
     const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
     const float *y = sm + L.oY + lane * (MAXB + 1);
     float *sO = sm + L.oP;                      // [TILE_F][out_dim], spectrum tile is dead by now
     const int od = P.out_dim;
     if (KIND == KIND_SPEC || KIND == KIND_LOGSPEC || KIND == KIND_TRAPLOG) {
-        for (int b = wv; b < P.nb; b += CTA_THREADS / 32) sO[lane * od + b] = y[b];
+        // with the energy of the band values wanted, logspec arrives here in true scale (see k_frames)
+        const bool late_log = (KIND == KIND_LOGSPEC && P.energy_mode == EN_BANDS);
+        for (int b = wv; b < P.nb; b += CTA_THREADS / 32) sO[lane * od + b] = late_log ? logf(y[b]) : y[b];
+        if (P.energy_mode == EN_BANDS && wv == 0 && lane < nf) {
+            float acc = 0.5f * y[0] * y[0];
+            for (int b = 1; b < P.nb - 1; b++) acc += y[b] * y[b];
+            acc += 0.5f * y[P.nb - 1] * y[P.nb - 1];
+            P.energy[row0 + lane] = logf(acc * 2.f);
+        }
     } else if (KIND == KIND_DCTC) {
         for (int i = wv; i < P.nrows; i += CTA_THREADS / 32) {
             const float *m = P.m2 + i * P.nbp;
@@ -526,13 +575,15 @@ k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, cons
             __syncthreads();
         }
 
+        if (SRC != SRC_FB && DST != DST_SPEC) tile_energy(P, sm + Lt.oP, nf, row0);
         if (DST == DST_SPEC) {
             float *g = dst + row0 * NBIN;
             const float *sP = sm + Lt.oP;
             for (int i = tid; i < nf * NBIN; i += CTA_THREADS) g[i] = sP[i];
         } else {
             if (SRC != SRC_FB) {
-                const bool want_log = (DST == DST_FEA) && (KIND == KIND_DCTC || KIND == KIND_LOGSPEC || KIND == KIND_TRAPLOG);
+                const bool want_log = (DST == DST_FEA) && (KIND == KIND_DCTC || KIND == KIND_TRAPLOG ||
+                                                           (KIND == KIND_LOGSPEC && P.energy_mode != EN_BANDS));
                 phase_fb(P, sm, Lt, want_log);
             }
             if (DST == DST_FB) {
@@ -543,7 +594,7 @@ k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, cons
                     g[i] = sY[f * (MAXB + 1) + b];
                 }
             } else {
-                phase_fea<KIND>(P, sm, L);
+                phase_fea<KIND>(P, sm, L, nf, row0);
                 const float *sO = sm + L.oP;
                 const int od = P.out_dim;
                 for (int i = tid; i < nf * od; i += CTA_THREADS) {
@@ -555,6 +606,38 @@ k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, cons
         __syncthreads();                                  // the tiles in shared memory are re-used by the next iteration
         cur = nxt;
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// raw energy (src/io/in.cc:353-361): log of the sum of squares of the frame's raw samples 1..w-1
+// (the first one is skipped).  One warp per frame.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_rawenergy(BatchDesc bd, int window, int wshift, const int16_t *__restrict__ pcm, float *__restrict__ energy) {
+    const int2 tile = bd.tiles[blockIdx.x];
+    const int u = tile.x, t0 = tile.y;
+    const int nf = min(DELTA_ROWS_C, bd.nframes[u] - t0);
+    const int lane = threadIdx.x & 31;
+    for (int f = threadIdx.x >> 5; f < nf; f += 8) {
+        const int16_t *x = pcm + bd.pcm_off[u] + (int64_t)(t0 + f) * wshift;
+        double acc = 0;
+        for (int i = 1 + lane; i < window; i += 32) { const double v = (double)x[i]; acc += v * v; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) energy[bd.row_off[u] + t0 + f] = (float)log(acc);
+    }
+}
+
+// The writer reads *E when a row leaves the delta / VAD delay lines (src/io/out.cc:183-202), so
+// row t carries the energy of frame min(t + latency, T-1): last column of the feature matrix.
+__global__ void __launch_bounds__(256)
+k_place_energy(BatchDesc bd, int latency, int stride, const float *__restrict__ energy, float *__restrict__ fea) {
+    const int2 tile = bd.tiles[blockIdx.x];
+    const int u = tile.x, t0 = tile.y;
+    const int T = bd.nframes[u];
+    const int64_t row0 = bd.row_off[u];
+    for (int t = t0 + threadIdx.x; t < min(t0 + DELTA_ROWS_C, T); t += blockDim.x)
+        fea[(row0 + t) * stride + stride - 1] = energy[row0 + min(t + latency, T - 1)];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -595,6 +678,7 @@ k_lpc(const __grid_constant__ FrameParams P, int64_t row0, int64_t nrows, const 
             R[k] = acc;
         }
     }
+    if (P.energy_mode == EN_LPC) P.energy[r0 + threadIdx.x] = (float)log(R[0]);
     double Pe = R[0];
     double rc = -R[1] / R[0];
     Pe = Pe * (1 - rc * rc);

@@ -64,6 +64,7 @@ struct VadParams {
     int latency;         // rows between a feature row and the spectrum frame the VAD sees
     int order;           // majority filter length
     int cep_n;           // length of the cepstral vector (lpc: vad_lpc_coefs, fea: feature dim)
+    int has_E;           // last column of the feature rows is the _E column
     int fea_skip;        // fea criterion: WRITER column holding the reference's internal element 0 (left out of the
                          // distance, src/vad/vad.cc:262-272), or -1 when that element is not written at all
     int cep_init; double cep_p;
@@ -592,7 +593,7 @@ __global__ void k_vad_energy(const __grid_constant__ VadParams V, const float *_
 // thresholds + background update + majority filter, one thread per utterance
 __global__ void k_vad_scan(const __grid_constant__ VadParams V, const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int u0,
                            int n_utts, const double *__restrict__ cri_frame, const double *__restrict__ ceps,
-                           const double *__restrict__ fea, int fea_dim, uint8_t *__restrict__ vad0_tmp, uint8_t *__restrict__ vad_out,
+                           const double *__restrict__ fea, int fea_dim /* row pitch */, uint8_t *__restrict__ vad0_tmp, uint8_t *__restrict__ vad_out,
                            uint8_t *__restrict__ keep) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_utts) return;
@@ -897,7 +898,7 @@ static inline int launch_vad_module(VadParams V, const BurgParams &B, const Batc
         int st = launch_burg(B, BURG_SRC_VAD, bd32, nt32, d_pcm, d_spec, d_ceps, tw, ts, ti, win, nullptr, s, lc, err);
         if (st) return st;
     } else {
-        V.cep_n = fea_dim;
+        V.cep_n = fea_dim - V.has_E;      // the reference's vector does not hold the energy
         if (!d_fea64) { err = "CTU: internal: fp64 feature matrix missing for the cepstral-distance VAD"; return CTU_ERR_CONFIG; }
     }
     if (V.cep_n > 64) { err = "CTU: cepstral-distance VAD supports vectors of up to 64 values"; return CTU_ERR_UNSUPPORTED; }

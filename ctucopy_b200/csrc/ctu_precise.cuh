@@ -123,6 +123,19 @@ k_frames64(const __grid_constant__ FrameParams P, BatchDesc bd, Tables64 tb, con
             }
             __syncwarp();
         }
+        if ((SRC == SRC64_PCM || SRC == SRC64_SPEC) && (P.energy_mode == EN_NR || P.energy_mode == EN_IN)) {
+            // energy of the half spectrum (src/nr/nr.cc:36-45 squares the stored values; src/io/in.cc:403-413 sums power)
+            const bool square = (P.energy_mode == EN_NR) || P.take_sqrt;
+            double acc = 0;
+            if (active) for (int k = c; k < NBIN; k += GROUP) {
+                double v = pr[k];
+                if (square) v *= v;
+                if (k == 0 || k == NBIN - 1) v *= 0.5;
+                acc += v;
+            }
+            acc = group_sum16d(acc);
+            if (active && c == 0) P.energy[row0 + f] = (float)log(acc * 2.0);
+        }
         if (SRC == SRC64_PCM || SRC == SRC64_SPEC) {
             // filter bank: bands dealt round-robin to the group's threads, sequential sum
             // over the taps in the reference's order (src/fea/fb.cc:76-83)
@@ -149,6 +162,12 @@ k_frames64(const __grid_constant__ FrameParams P, BatchDesc bd, Tables64 tb, con
         float *orow = dst + (row0 + f) * P.out_stride;
         double *orow64 = dst64 ? dst64 + (row0 + f) * P.out_stride : nullptr;
         if (KIND == KIND_SPEC || KIND == KIND_LOGSPEC || KIND == KIND_TRAPLOG) {
+            if (P.energy_mode == EN_BANDS && active && c == 0) {
+                double acc = 0.5 * sY[0] * sY[0];
+                for (int b = 1; b < nb - 1; b++) acc += sY[b] * sY[b];
+                acc += 0.5 * sY[nb - 1] * sY[nb - 1];
+                P.energy[row0 + f] = (float)log(acc * 2.0);
+            }
             if (active) for (int b = c; b < nb; b += GROUP) {
                 double v = (KIND == KIND_SPEC) ? sY[b] : log(sY[b]);
                 orow[b] = (float)v;
@@ -176,6 +195,7 @@ k_frames64(const __grid_constant__ FrameParams P, BatchDesc bd, Tables64 tb, con
             }
             __syncwarp();
             if (active && c == 0) {
+                if (P.energy_mode == EN_LPC) P.energy[row0 + f] = (float)log(sR[0]);
                 double a[MAXR], aa[MAXR];
                 double Pe = sR[0];
                 double rc = -sR[1] / sR[0];

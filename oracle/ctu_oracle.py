@@ -1247,6 +1247,40 @@ def writer_order(F: np.ndarray, o: Opts) -> np.ndarray:
     return F[:, cols]
 
 
+def energy_column(o: Opts, fe: "FrontEnd", Xs: np.ndarray, Y: np.ndarray, kind: str, inld: bool, lat: int) -> np.ndarray:
+    """The optional _E column.  Which stage's E the writer points at is decided in
+    BATCH::init_out (src/io/batch.cc:98-118): raw energy -> IN (src/io/in.cc:353-361); dctc ->
+    NR::compute_E on the spectrum handed to the filter bank (src/nr/nr.cc:36-45; it squares X
+    again even when X is already power) or, with NR after the FB, IN's power-domain energy
+    (src/io/in.cc:403-413); lpc/lpa -> log R0 (src/fea/fea_impl.cc:177); spec/logspec -> the
+    same half-spectrum formula applied to the BAND values (src/fea/fea_impl.cc:45-50, 69-74).
+    htkOUT::save_frame reads *E when a (possibly delayed) row is written (src/io/out.cc:183-202),
+    so row r carries the energy of input frame min(r + latency, T-1)."""
+    T = Xs.shape[0]
+
+    def half_spectrum_energy(X):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.array([math.log(_seq_sum(X[t, 1:-1] * X[t, 1:-1], X[t, 0] * X[t, 0] / 2.0 + X[t, -1] * X[t, -1] / 2.0) * 2.0)
+                             if True else 0.0 for t in range(X.shape[0])])
+
+    if o.fea_rawenergy:
+        E = fe.E
+    elif kind == "dctc":
+        E = fe.E if o.nr_when == "afterFB" else half_spectrum_energy(Xs)
+    elif kind in ("lpa", "lpc"):
+        X = Y if inld else Y * Y
+        Nin = X.shape[1]; Nf = (Nin - 1) * 2
+        R0 = np.array([(_seq_sum(X[t, 1:Nin - 1], X[t, 0] / 2.0) + X[t, Nin - 1] / 2.0) / (float(Nf) / 2) for t in range(T)])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            E = np.log(R0)
+    elif kind in ("spec", "logspec"):
+        E = half_spectrum_energy(Y)
+    else:
+        raise ValueError("CTU: -fea_E with -fea_kind %s: the reference never sets that energy" % kind)
+    idx = np.minimum(np.arange(T) + lat, T - 1)
+    return np.asarray(E, dtype=np.float64)[idx]
+
+
 def run_pipeline(pcm: np.ndarray, o: Opts, ext_vad: Optional[np.ndarray] = None) -> Result:
     """One utterance through the chain BATCH builds (src/io/batch.cc:24-69, 205-296)."""
     fe = front_end(pcm, o)
@@ -1282,16 +1316,21 @@ def run_pipeline(pcm: np.ndarray, o: Opts, ext_vad: Optional[np.ndarray] = None)
     if o.n_order > 0 and k in ("dctc", "lpc"):
         F = add_deltas(F, o)
     out = writer_order(F, o) if k != "lpa" else F[:, 1:]
+    lat = 0
+    if k in ("dctc", "lpc"):
+        lat = sum([o.d_win, o.a_win, o.t_win][: o.n_order])
+    if k == "trapdct":
+        lat = (o.fea_trapdct_traplen + 1) // 2 - 1
+    do_vad = o.vad_apply_mode != "none" or o.vad_out_mode != "none"
+    if o.fea_E:
+        # rows also wait in the VAD module's majority filter, (order-1)/2 frames (src/vad/vad.h:126-175)
+        elat = lat + ((o.vad_filter_order - 1) // 2 if do_vad else 0)
+        out = np.concatenate([out, energy_column(o, fe, Xs, Y, k, fb.inld, elat)[:, None]], axis=1)
     res = Result(T, features=out.astype(np.float32), vad_nr=vnr, fb_out=Y, spectrum=Xs, internal=internal)
     if o.vad_apply_mode != "none" or o.vad_out_mode != "none":
         # BATCH::save_frame (src/io/batch.cc:230-241) runs when a feature row leaves the
         # delta / TRAP-DCT delay lines, so the VAD criterion sees in->_Xsabs of the frame
         # that is `latency` frames AHEAD of the row (and the last frame during flush).
-        lat = 0
-        if k in ("dctc", "lpc"):
-            lat = sum([o.d_win, o.a_win, o.t_win][: o.n_order])
-        if k == "trapdct":
-            lat = (o.fea_trapdct_traplen + 1) // 2 - 1
         idx = np.minimum(np.arange(F.shape[0]) + lat, T - 1)
         res.vad = vad_module(o, Xs[idx], fe.Xph[idx] if fe.Xph is not None else None, F)
         res.features = res.features[res.vad.keep]

@@ -85,6 +85,14 @@ CASES = {
                                   "-vad_filter_order", "1"], "htk", {"vad_out": True}),
     "vad_perc_d_a_drop": (B + MF + ["-format_out", "htk", "-vad_out_mode", "vad", "-fea_delta", "d_a", "-vad_apply_mode", "drop"],
                           "htk", {"vad_out": True}),
+    # the optional _E column: every source BATCH::init_out can pick (src/io/batch.cc:98-118)
+    "mfcc_E_d_a": (B + MF + ["-fea_E", "on", "-fea_delta", "d_a", "-format_out", "htk"], "htk", {}),
+    "mfcc_rawE": (B + MF + ["-fea_E", "on", "-fea_rawenergy", "on", "-format_out", "htk"], "htk", {}),
+    "mfcc_E_noc0": (B + MF + ["-fea_E", "on", "-fea_c0", "off", "-format_out", "htk"], "htk", {}),
+    "plp_E": (B + ["-preset", "plpc", "-fea_E", "on", "-format_out", "htk"], "htk", {}),
+    "logspec_E": (B + MF + ["-fea_kind", "logspec", "-fea_E", "on", "-format_out", "htk"], "htk", {}),
+    "mfcc_exten_E": (B + MF + ["-nr_mode", "exten", "-fea_E", "on", "-format_out", "htk"], "htk", {}),
+    "mfcc_exten_afterFB_E": (B + MF + ["-nr_mode", "exten", "-nr_when", "afterFB", "-fea_E", "on", "-format_out", "htk"], "htk", {}),
 }
 
 
@@ -101,7 +109,12 @@ def inputs():
 
 def main():
     utts = inputs()
-    np.savez_compressed(os.path.join(OUT, "inputs.npz"), **{"in%d" % i: u for i, u in enumerate(utts)})
+    if not sys.argv[1:] or not os.path.exists(os.path.join(OUT, "inputs.npz")):
+        np.savez_compressed(os.path.join(OUT, "inputs.npz"), **{"in%d" % i: u for i, u in enumerate(utts)})
+    else:   # adding cases: the committed inputs must be the ones generated here
+        z = np.load(os.path.join(OUT, "inputs.npz"))
+        assert all(np.array_equal(z["in%d" % i], u) for i, u in enumerate(utts)), "inputs.npz differs from inputs()"
+
     rng = np.random.default_rng(7)
     names = sys.argv[1:] or list(CASES)
     for name in names:
@@ -136,6 +149,8 @@ def main():
                 d["extvad%d" % i] = flags_all[i]
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
         print(name, "ok", sum(len(o) for o in outs), "bytes")
+    if sys.argv[1:]:
+        return       # only the named cases were asked for
     # filter-bank design goldens via the undocumented -fb_printself (src/fea/fb.cc:449-456)
     fbd = {}
     for nm, a in {

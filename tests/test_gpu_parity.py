@@ -178,3 +178,16 @@ def test_spectrum_tap_matches_numpy_fft():
     rowmax = want.max(axis=1, keepdims=True)
     assert np.all(np.abs(got - want) <= 1e-4 * want + 2e-6 * rowmax)
     plan.close(); hd.close()
+
+
+def test_energy_column_with_vad_delay_matches_oracle():
+    """-fea_E rows written through the VAD module carry the energy of the frame that is
+    (delta latency + majority-filter delay) ahead (checked against the reference binary when
+    the oracle was extended; here CUDA vs oracle)."""
+    args = B + ["-preset", "mfcc", "-preem", "0.97", "-fea_E", "on", "-fea_delta", "d_a", "-format_out", "htk",
+                "-vad_out_mode", "vad", "-vad_filter_order", "5"]
+    o = co.parse_args(args)
+    res = cb.extract(args, PARITY_SET[:4])
+    for j, u in enumerate(PARITY_SET[:4]):
+        ref = co.run_pipeline(u, o)
+        check_features("mfcc_E_vad", j, res.utt_features(j), ref.features, "dctc")
