@@ -73,7 +73,9 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region: sampled every 20 ms from before
+    the warm-up; stop(t0, t1) keeps the samples whose timestamps fall inside the timed window (all
+    samples under load if the window is too short to hold two)."""
 
     def __init__(self, index):
         self.index = index
@@ -81,11 +83,11 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -95,30 +97,35 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
+            if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        window = "timed region"
+        sel = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        if len(sel) < 2:
+            sel, window = rows, "warm-up + timed region (timed region shorter than two samples)"
+        sm = [r[1] for r in sel]
+        reasons = sorted({n for r in sel for n in r[3]})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(r[2] for r in sel) if sel else None,
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def cpu_reference_run(workload, utt_files, per_proc, cores, tmp, opt="O2"):
@@ -202,7 +209,7 @@ def run_reference_arm(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
     ap.add_argument("--utts", type=int, default=10000, help="utterances of 10 s per GPU")
@@ -272,12 +279,15 @@ def main():
             else:
                 plan.run_device(d_pcm.data_ptr(), d_features=d_out.data_ptr(), stream=stream)
 
-        for _ in range(warmup):
-            step()
-        barrier()
         sampler = ClockSampler(local) if with_clocks else None
         if sampler:
             sampler.start()
+            step(); torch.cuda.synchronize()
+            time.sleep(0.25)                               # nvidia-smi needs a moment before its first sample
+        for _ in range(warmup):
+            step()
+        barrier()
+        t_begin = time.time()
         l0 = hd.launch_count
         hd.profile(True)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -286,11 +296,12 @@ def main():
             step()
         ev1.record()
         barrier()
+        t_end = time.time()
         ms = ev0.elapsed_time(ev1)
         launches = hd.launch_count - l0
         recs = hd.profile_records()
         hd.profile(False)
-        clocks = sampler.stop() if sampler else None
+        clocks = sampler.stop(t_begin, t_end) if sampler else None
         ms = max_over_ranks(ms)
         # per-kernel average duration over the timed region; the dominant kernel is the one with the largest share
         by = {}

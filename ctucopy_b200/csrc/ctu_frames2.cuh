@@ -127,6 +127,8 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, Tables2 tb, const
             cpx<float> lo[8], hi[8], mid;
             rfft_split_shfl(a, c, sTs, lo, hi, mid);
             __syncwarp(hm);                                     // every lane holds its bins: the area can be overwritten
+            // PCM -> spectrum: the row goes from the registers straight to HBM (each store covers 64 contiguous bytes)
+            float *grow = (DST == DST_SPEC) ? dst + (row0 + f) * NBIN : sPr;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int k = c + 16 * j;
@@ -134,13 +136,14 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, Tables2 tb, const
                 float ph = hi[j].x * hi[j].x + hi[j].y * hi[j].y;
                 if (k == 0 && P.remove_dc) pl = 1e-10f;       // fixed floor (src/io/in.cc:390)
                 if (P.take_sqrt) { pl = sqrtf(pl); ph = sqrtf(ph); }
-                sPr[k] = pl;
-                sPr[NC - k] = ph;
+                grow[k] = pl;
+                grow[NC - k] = ph;
             }
             if (c == 0) {
                 const float pm = mid.x * mid.x + mid.y * mid.y;
-                sPr[128] = P.take_sqrt ? sqrtf(pm) : pm;
+                grow[128] = P.take_sqrt ? sqrtf(pm) : pm;
             }
+            if (DST == DST_SPEC) continue;
         } else if (SRC == SRC_SPEC) {
             const float *g = src + (row0 + f) * NBIN;
 #pragma unroll

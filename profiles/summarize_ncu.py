@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Turns an .ncu-rep (brought back in gpurun_out/) into the short per-kernel text summary
-committed under profiles/.   usage: python profiles/summarize_ncu.py <rep> [frames_per_launch]"""
+"""Turns an .ncu-rep, or the `--page raw --csv` export of one (tools/gpu_jobs/ncu_cap.sh writes
+those on the GPU box), into the short per-kernel text summary committed under profiles/.
+usage: python profiles/summarize_ncu.py <rep | raw.csv> [frames_per_launch]"""
 import csv
 import subprocess
 import sys
@@ -21,6 +22,7 @@ WANT = [
     ("launch__occupancy_limit_shared_mem", "blocks/SM (smem)"),
     ("launch__grid_size", "grid"),
     ("sm__inst_executed.sum", "warp instructions"),
+    ("l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "LSU data-pipe wavefronts % of peak"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
     ("sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active", "FMA pipe %"),
@@ -33,7 +35,10 @@ STALLS = "smsp__pcsamp_warps_issue_stalled_"
 def main():
     rep = sys.argv[1]
     frames = float(sys.argv[2]) if len(sys.argv) > 2 else None
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
