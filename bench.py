@@ -413,4 +413,12 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    # ONE JSON line on stdout: libraries that write to file descriptor 1 from native code (NCCL prints its
+    # version banner there) are sent to stderr; only our own print() reaches the real stdout
+    sys.stdout.flush()
+    _real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real
+    rc = main()
+    _real.flush()
+    sys.exit(rc)
