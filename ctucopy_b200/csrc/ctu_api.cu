@@ -43,10 +43,6 @@ struct ctu_handle {
     // device tables
     float2 *d_tw256 = nullptr, *d_twsplit = nullptr, *d_twinv = nullptr;
     float *d_win = nullptr;
-    // tables of the group-local frame kernel (ctu_frames2.cuh)
-    float *d_fbw = nullptr, *d_m2p = nullptr;
-    int4 *d_slots = nullptr;
-    Tables2 t2{};
     double2 *d_tw256d = nullptr, *d_twsplitd = nullptr, *d_twinvd = nullptr;
     double *d_wind = nullptr, *d_hann = nullptr;
     // fp64 tables of the precise path (ctu_precise.cuh)
@@ -319,40 +315,6 @@ static int build_frame_params(ctu_handle *h) {
 }
 
 
-// tables of k_frames2: packed taps, band slots (widest band first, dealt to the 16 lanes in
-// snake order so every lane gets about the same number of taps), second-stage matrix with an
-// odd row pitch
-static int build_tables2(ctu_handle *h) {
-    const FrameParams &P = h->fp;
-    Tables2 &T = h->t2;
-    std::memset(&T, 0, sizeof(T));
-    T.tw256 = h->d_tw256; T.twsplit = h->d_twsplit; T.win = h->d_win;
-    if (h->signal_out) return CTU_OK;
-    const int nb = P.nb;
-    int ntaps = 0;
-    for (int b = 0; b < nb; b++) ntaps = std::max(ntaps, P.woff[b] + (P.hi[b] - P.lo[b] + 1));
-    std::vector<float> fbw(P.w, P.w + ntaps);
-    std::vector<int> order(nb);
-    for (int b = 0; b < nb; b++) order[b] = b;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return (P.hi[a] - P.lo[a]) > (P.hi[b] - P.lo[b]); });
-    const int rounds = (nb + GROUP - 1) / GROUP;
-    std::vector<int4> slots((size_t)rounds * GROUP, make_int4(-1, 0, 0, 0));
-    for (int i = 0; i < nb; i++) {
-        const int r = i / GROUP, pos = i % GROUP, lane = (r & 1) ? GROUP - 1 - pos : pos;
-        const int b = order[i];
-        slots[(size_t)r * GROUP + lane] = make_int4(b, P.lo[b], P.hi[b] - P.lo[b] + 1, P.woff[b]);
-    }
-    const int pitch = P.nbp | 1;
-    std::vector<float> m2((size_t)std::max(1, P.nrows) * pitch, 0.f);
-    for (int r = 0; r < P.nrows; r++)
-        for (int k = 0; k < P.nbp; k++) m2[(size_t)r * pitch + k] = P.m2[r * P.nbp + k];
-    int st;
-    if ((st = upload(h, &h->d_fbw, fbw)) || (st = upload(h, &h->d_slots, slots)) || (st = upload(h, &h->d_m2p, m2))) return st;
-    T.fbw = h->d_fbw; T.slots = h->d_slots; T.m2 = h->d_m2p;
-    T.ntaps_total = ntaps; T.nslots = (int)slots.size(); T.m2_pitch = pitch; T.m2_rows = (h->fea_kind == FEA_DCTC) ? P.nrows : 0;
-    return CTU_OK;
-}
-
 static int build_delta_trap_params(ctu_handle *h) {
     const ctu_config &c = h->cfg;
     DeltaParams &D = h->dp;
@@ -507,7 +469,6 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     if (cudaSetDevice(device) != cudaSuccess) { h->err = "CUDA: cudaSetDevice failed"; return bail(CTU_ERR_CUDA); }
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     if ((st = build_fft_tables(h))) return bail(st);
-    if ((st = build_tables2(h))) return bail(st);
     if (h->nr_mode != NR_NONE && h->cfg.nr_when == 1 && !h->signal_out) h->precise = true;   // subtraction on band values
     // VAD criterion = distance between feature vectors, fed to threshold state machines whose
     // decisions must match the reference bit for bit: features in fp64 like the reference's
@@ -524,7 +485,6 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
 void ctu_destroy(ctu_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaFree(h->d_fbw); cudaFree(h->d_m2p); cudaFree(h->d_slots);
     cudaFree(h->d_tw256); cudaFree(h->d_twsplit); cudaFree(h->d_twinv); cudaFree(h->d_win);
     cudaFree(h->d_w64); cudaFree(h->d_m264); cudaFree(h->d_lift64);
     cudaFree(h->d_tw256d); cudaFree(h->d_twsplitd); cudaFree(h->d_twinvd); cudaFree(h->d_wind); cudaFree(h->d_hann);
@@ -687,16 +647,20 @@ static int launch_frames_w(ctu_handle *h, const FrameParams &P, const ctu_plan *
     static const char *const names[3][3] = {{"k_frames<pcm,spec>", "k_frames<pcm,fb>", "k_frames<pcm,fea>"},
                                             {"k_frames<spec,spec>", "k_frames<spec,fb>", "k_frames<spec,fea>"},
                                             {"k_frames<fb,spec>", "k_frames<fb,fb>", "k_frames<fb,fea>"}};
-    if constexpr (DST == DST_SPEC) {
+    if constexpr (SRC == SRC_PCM && DST == DST_SPEC) {
         if (ft.n16 <= 0) return CTU_OK;
-        const Tables2 &T = h->t2;
-        Smem2 L = smem2_layout(P.window, P.wshift, T.ntaps_total, T.nslots, T.m2_pitch, T.m2_rows);
+        Smem2 L = smem2_layout(P.window, P.wshift);
         size_t bytes = (size_t)L.total * sizeof(float);
-        auto kern = k_frames2<SRC, DST, KIND, WT>;
+        auto kern = k_frames2<WT>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        FftTables tb{h->d_tw256, h->d_twsplit, h->d_twinv, h->d_win};
         BatchDesc bd{p->d_pcm_off, p->d_nframes, p->d_row_off, ft.t16};
+        // persistent CTAs: exactly as many as are resident at once (five per SM at 25/10 ms, four at 32/16 ms)
+        int per_sm = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, F2_THREADS, bytes));
+        const unsigned grid = (unsigned)std::min<int64_t>(ft.n16, std::max(per_sm, 1) * (int64_t)h->num_sms);
         h->lc.begin(names[SRC][DST], s);
-        kern<<<(unsigned)ft.n16, F2_THREADS, bytes, s>>>(P, bd, T, pcm, src, dst);
+        kern<<<grid, F2_THREADS, bytes, s>>>(P, bd, tb, pcm, dst, (int)ft.n16);
         h->lc.end(s);
     } else {
         if (ft.n32 <= 0) return CTU_OK;
@@ -708,7 +672,9 @@ static int launch_frames_w(ctu_handle *h, const FrameParams &P, const ctu_plan *
         BatchDesc bd{p->d_pcm_off, p->d_nframes, p->d_row_off, ft.t32};
         // from PCM: persistent CTAs, two per SM (shared-memory bound), each walks the tile list with stride
         // gridDim.x and prefetches its next tile; other sources: one tile per CTA, the hardware scheduler overlaps them
-        const unsigned grid = (SRC == SRC_PCM) ? (unsigned)std::min<int64_t>(ft.n32, 2 * (int64_t)h->num_sms) : (unsigned)ft.n32;
+        int per_sm = 2;
+        if (SRC == SRC_PCM) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA_THREADS, bytes));
+        const unsigned grid = (SRC == SRC_PCM) ? (unsigned)std::min<int64_t>(ft.n32, std::max(per_sm, 1) * (int64_t)h->num_sms) : (unsigned)ft.n32;
         h->lc.begin(names[SRC][DST], s);
         kern<<<grid, CTA_THREADS, bytes, s>>>(P, bd, tb, pcm, src, dst, (int)ft.n32);
         h->lc.end(s);

@@ -432,11 +432,11 @@ __device__ __forceinline__ void phase_fea(const FrameParams &P, float *sm, const
 // two) partial chunks at the ends go through a register.
 struct TileMeta { int u, t0, nf; int64_t row0, g0; };
 
-__device__ __forceinline__ TileMeta load_tile_meta(const BatchDesc &bd, int tile, int wshift) {
+__device__ __forceinline__ TileMeta load_tile_meta(const BatchDesc &bd, int tile, int wshift, int tile_frames = TILE_F) {
     TileMeta m;
     const int2 t = bd.tiles[tile];
     m.u = t.x; m.t0 = t.y;
-    m.nf = min(TILE_F, bd.nframes[m.u] - m.t0);
+    m.nf = min(tile_frames, bd.nframes[m.u] - m.t0);
     m.row0 = bd.row_off[m.u] + m.t0;
     m.g0 = bd.pcm_off[m.u] + (int64_t)m.t0 * wshift;
     return m;
@@ -444,12 +444,13 @@ __device__ __forceinline__ TileMeta load_tile_meta(const BatchDesc &bd, int tile
 
 // element k of the tile's sample run is sample (k - 1): k = 0 is the sample before the tile
 // (pre-emphasis memory), valid only when the tile is not at the start of its utterance
+template <int NT>
 __device__ __forceinline__ void prefetch_pcm(int16_t *raw, const int16_t *__restrict__ pcm, const TileMeta &m, int n, int &edge) {
     const int16_t *S0 = pcm + m.g0 - 1;
     const int phase = (int)((reinterpret_cast<uintptr_t>(S0) & 15) >> 1);
     const int kmin = (m.t0 == 0) ? 1 : 0;
     const int nchunks = (phase + n + 7) >> 3;
-    for (int j = threadIdx.x; j < nchunks; j += CTA_THREADS) {
+    for (int j = threadIdx.x; j < nchunks; j += NT) {
         const int k0 = 8 * j - phase;
         if (k0 >= kmin && k0 + 8 <= n) {
             const unsigned dst = (unsigned)__cvta_generic_to_shared(raw + 8 * j);
@@ -470,6 +471,7 @@ __device__ __forceinline__ void prefetch_pcm(int16_t *raw, const int16_t *__rest
 
 // after the copies have landed: partial-chunk elements from the registers, then raw -> float with
 // pre-emphasis (src/io/in.cc:364-372), every sample converted once for all the frames it is in
+template <int NT>
 __device__ __forceinline__ void finish_pcm(int16_t *raw, float *__restrict__ sD, const int16_t *__restrict__ pcm, const TileMeta &m, int n,
                                            int edge, float alpha) {
     const int16_t *S0 = pcm + m.g0 - 1;
@@ -486,7 +488,7 @@ __device__ __forceinline__ void finish_pcm(int16_t *raw, float *__restrict__ sD,
     __syncthreads();
     const int16_t *x = raw + phase;                       // x[k]: element k
     const int nsamp = n - 1;
-    for (int i0 = threadIdx.x * 8; i0 < nsamp; i0 += CTA_THREADS * 8) {
+    for (int i0 = threadIdx.x * 8; i0 < nsamp; i0 += NT * 8) {
         float prev = s16_to_f32((int)x[i0]);
         float v[8];
 #pragma unroll
@@ -517,7 +519,7 @@ k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, cons
     TileMeta cur = load_tile_meta(bd, tile, P.wshift);
     int edge = 0;
     if (SRC == SRC_PCM) {
-        prefetch_pcm(raw, pcm, cur, (cur.nf - 1) * P.wshift + w + 1, edge);
+        prefetch_pcm<CTA_THREADS>(raw, pcm, cur, (cur.nf - 1) * P.wshift + w + 1, edge);
         float *sW = sm + L.oW;
         cpx<float> *sTw = reinterpret_cast<cpx<float> *>(sm + L.oTw);
         cpx<float> *sTs = reinterpret_cast<cpx<float> *>(sm + L.oTs);
@@ -538,9 +540,9 @@ k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, cons
         Lt.oP += spec_phase;
 
         if (SRC == SRC_PCM) {
-            finish_pcm(raw, sm + L.oD, pcm, cur, (nf - 1) * P.wshift + w + 1, edge, P.preem);
+            finish_pcm<CTA_THREADS>(raw, sm + L.oD, pcm, cur, (nf - 1) * P.wshift + w + 1, edge, P.preem);
             __syncthreads();                              // samples staged; the raw buffer is free again
-            if (next < ntiles) prefetch_pcm(raw, pcm, nxt, (nxt.nf - 1) * P.wshift + w + 1, edge);
+            if (next < ntiles) prefetch_pcm<CTA_THREADS>(raw, pcm, nxt, (nxt.nf - 1) * P.wshift + w + 1, edge);
             phase_fft<WT>(P, pcm, cur.g0, cur.t0 == 0, nf, tb, sm, L);
         } else if (SRC == SRC_SPEC) {
             // the tile is one contiguous run of nf*257 floats: 16-byte cp.async for the aligned body (all of

@@ -191,3 +191,25 @@ def test_energy_column_with_vad_delay_matches_oracle():
     for j, u in enumerate(PARITY_SET[:4]):
         ref = co.run_pipeline(u, o)
         check_features("mfcc_E_vad", j, res.utt_features(j), ref.features, "dctc")
+
+
+@pytest.mark.parametrize("name", ["mfcc_exten", "fwss_burg", "exten_raw", "plp", "trapdct"])
+def test_full_length_utterances_match_oracle(name):
+    """BASELINE's utterance size (10 s = 998 frames): the cross-frame recursions (noise estimates,
+    detector thresholds, overlap-add) run their full length; every detector decision must match."""
+    args = ORACLE_CASES[name]
+    o = co.parse_args(args)
+    utts = [synthetic.utterance(k, 10.0) for k in (3, 6)]
+    res = cb.extract(args, utts)
+    for j, u in enumerate(utts):
+        ref = co.run_pipeline(u, o)
+        if o.format_out == "raw":
+            d = np.abs(res.utt_waveform(j).astype(np.int32) - ref.waveform.astype(np.int32))
+            assert d.max() <= 1 and (d > 0).mean() < 0.02, (name, j, d.max(), (d > 0).mean())
+        else:
+            assert int(res.frames_per_utt[j]) == 998
+            check_features(name, j, res.utt_features(j), ref.features, o.fea_kind)
+        if ref.vad_nr is not None:
+            r0 = int(res.row_offsets[j])
+            got = res.vad_nr[r0: r0 + ref.nframes]
+            assert np.array_equal(got.astype(bool), ref.vad_nr), (name, j, int((got.astype(bool) != ref.vad_nr).sum()))
