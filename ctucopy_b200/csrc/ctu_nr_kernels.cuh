@@ -725,35 +725,57 @@ constexpr int SYN_FRAMES = SYN_GROUPS;
 
 // WT / ST: window and shift known at compile time (0 = runtime) -- turns the divisions of the
 // overlap-add index arithmetic into shifts / multiplies and prunes the zero padding.
+// one synthesis tile: utterance, hops [t0, t0+nf), frames [tfirst, t0+nf) to transform
+struct SynTile { int u, t0, T, nf, tfirst, nfr; TileMeta st; };
+__device__ __forceinline__ SynTile load_syn_tile(const BatchDesc &bd, int tile, int tile_frames, int hh, int s) {
+    SynTile m;
+    const int2 t = bd.tiles[tile];
+    m.u = t.x; m.t0 = t.y;
+    m.T = bd.nframes[m.u];
+    m.nf = min(tile_frames, m.T - m.t0);
+    m.tfirst = max(m.t0 - hh, 0);
+    m.nfr = m.t0 + m.nf - m.tfirst;
+    m.st.u = m.u; m.st.t0 = m.tfirst; m.st.nf = m.nfr; m.st.row0 = bd.row_off[m.u] + m.tfirst;
+    m.st.g0 = bd.pcm_off[m.u] + (int64_t)m.tfirst * s;
+    return m;
+}
+
 template <int WT, int ST>
-__global__ void __launch_bounds__(SYN_THREADS)
-k_synth(const __grid_constant__ SynthParams S, int window, int wshift, float preem, int remove_dc, BatchDesc bd, int tile_frames,
+__global__ void __launch_bounds__(SYN_THREADS, 2)
+k_synth(const __grid_constant__ SynthParams S, int window, int wshift, float preem, int remove_dc, BatchDesc bd, int tile_frames, int ntiles,
         const int64_t *__restrict__ osamp_off, const int16_t *__restrict__ pcm, const float *__restrict__ spec, int16_t *__restrict__ out,
         const float2 *__restrict__ g_tw256, const float2 *__restrict__ g_twsplit, const float2 *__restrict__ g_twinv,
         const float *__restrict__ g_win) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x;
     const int w = WT ? WT : window, s = ST ? ST : wshift, hh = S.hh;
-    const int2 tile = bd.tiles[blockIdx.x];
-    const int u = tile.x, t0 = tile.y;
-    const int T = bd.nframes[u];
-    const int nf = min(tile_frames, T - t0);
-    const int tfirst = max(t0 - hh, 0);
-    const int nfr = t0 + nf - tfirst;                     // frames to synthesise (<= SYN_FRAMES)
-    const int nsamp = (nfr - 1) * s + w;
     // carve-up
     cpx<float> *sTw = reinterpret_cast<cpx<float> *>(sm);                 // 256
     cpx<float> *sTs = sTw + 256;                                         // 130
     cpx<float> *sTi = sTs + 130;                                         // 130
     cpx<float> *sX = sTi + 130;                                          // SYN_GROUPS * 16*17
     float *sW = reinterpret_cast<float *>(sX + SYN_GROUPS * XPAD * 16);  // w (padded to 512)
-    float *sD = sW + NFFT;                                               // (SYN_FRAMES-1)*s + w  (padded)
-    float *sYt = sD + (((SYN_FRAMES - 1) * s + w + 3) & ~3);             // SYN_FRAMES * w
-    stage_preem<SYN_THREADS>(sD, pcm + bd.pcm_off[u] + (int64_t)tfirst * s, nsamp, tfirst == 0, preem);
+    float *sD = sW + NFFT;                                               // (SYN_FRAMES-1)*s + w  (padded to 8)
+    float *sYt = sD + (((SYN_FRAMES - 1) * s + w + 7) & ~7);             // SYN_FRAMES * w
+    int16_t *raw = reinterpret_cast<int16_t *>(sYt + SYN_FRAMES * w);    // prefetch buffer, 8-sample chunks
+    // persistent CTAs (two per SM): the next tile's PCM arrives by cp.async while this one is synthesised
+    int tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    SynTile cur = load_syn_tile(bd, tile, tile_frames, hh, s);
+    int edge = 0;
+    prefetch_pcm<SYN_THREADS>(raw, pcm, cur.st, (cur.nfr - 1) * s + w + 1, edge);
     for (int i = tid; i < 256; i += SYN_THREADS) sTw[i] = mk<float>(g_tw256[i].x, g_tw256[i].y);
     for (int i = tid; i < 129; i += SYN_THREADS) { sTs[i] = mk<float>(g_twsplit[i].x, g_twsplit[i].y); sTi[i] = mk<float>(g_twinv[i].x, g_twinv[i].y); }
     for (int i = tid; i < w; i += SYN_THREADS) sW[i] = g_win[i];
+#pragma unroll 1
+    for (; tile < ntiles; tile += gridDim.x) {
+    const int next = tile + gridDim.x;
+    SynTile nxt = cur;
+    if (next < ntiles) nxt = load_syn_tile(bd, next, tile_frames, hh, s);
+    const int u = cur.u, t0 = cur.t0, T = cur.T, nf = cur.nf, tfirst = cur.tfirst, nfr = cur.nfr;
+    finish_pcm<SYN_THREADS>(raw, sD, pcm, cur.st, (nfr - 1) * s + w + 1, edge, preem);
     __syncthreads();
+    if (next < ntiles) prefetch_pcm<SYN_THREADS>(raw, pcm, nxt.st, (nxt.nfr - 1) * s + w + 1, edge);
     const int c = tid & (GROUP - 1), grp = tid / GROUP;
     cpx<float> *xch = sX + grp * (XPAD * 16);
     const float inv_w = 1.0f / (float)w;
@@ -833,22 +855,25 @@ k_synth(const __grid_constant__ SynthParams S, int window, int wshift, float pre
     const int nout = nf * s + (last ? (w - s) : 0);
     int16_t *o = out + osamp_off[u] + (int64_t)t0 * s;
     const int base = (t0 - tfirst) * s;                     // position of the tile's first sample inside the synthesised span
-    const double corr = S.correction;
+    const double inv_corr = 1.0 / S.correction;           // floor(x * (1/c)) differs from floor(x / c) only within 1e-16 of an integer
     for (int i = tid; i < nout; i += SYN_THREADS) {
         const int pos = base + i;                           // sample index relative to frame `tfirst`
         const int fa = (pos < w) ? 0 : (pos - w) / s + 1;   // first frame with fa*s + w > pos
         const int fb = min(pos / s, nfr - 1);
         double acc = 0.0;
         for (int f = fa; f <= fb; f++) acc += (double)sYt[f * w + (pos - f * s)];
-        int v = (int)floor(acc / corr);
+        int v = (int)floor(acc * inv_corr);
         v = max(-32767, min(32767, v));
         o[i] = (int16_t)v;
+    }
+    __syncthreads();                                      // the slots and sD are re-used by the next tile
+    cur = nxt;
     }
 }
 
 static inline size_t synth_smem_bytes(int w, int s) {
-    size_t fl = 2 * (256 + 130 + 130 + SYN_GROUPS * XPAD * 16) + NFFT + (((SYN_FRAMES - 1) * s + w + 3) & ~3) + (size_t)SYN_FRAMES * w;
-    return fl * sizeof(float);
+    size_t fl = 2 * (256 + 130 + 130 + SYN_GROUPS * XPAD * 16) + NFFT + (((SYN_FRAMES - 1) * s + w + 7) & ~7) + (size_t)SYN_FRAMES * w;
+    return fl * sizeof(float) + (size_t)(((SYN_FRAMES - 1) * s + w + 1 + 8 + 7) / 8) * 16;
 }
 
 // tiles: the plan's synthesis tile list, tile_frames = SYN_FRAMES - hh hops per tile
@@ -859,12 +884,16 @@ static inline int launch_synth(const SynthParams &S, const FrameParams &F, const
     size_t bytes = synth_smem_bytes(F.window, F.wshift);
     if (bytes > 227 * 1024 || tile_frames < 1) { err = "CTU: window/shift combination needs too much shared memory for synthesis"; return CTU_ERR_UNSUPPORTED; }
     cudaError_t e;
+    int per_sm = 1, num_sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     lc->begin("k_synth", s);
 #define CTU_SYNTH_LAUNCH(WT, ST)                                                                                                   \
     e = cudaFuncSetAttribute(k_synth<WT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);                          \
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_synth<WT, ST>, SYN_THREADS, bytes);         \
     if (e == cudaSuccess)                                                                                                          \
-        k_synth<WT, ST><<<(unsigned)ntiles, SYN_THREADS, bytes, s>>>(S, F.window, F.wshift, F.preem, F.remove_dc, bd, tile_frames, \
-                                                                     d_osamp_off, pcm, spec, out, tw, ts, ti, win)
+        k_synth<WT, ST><<<(unsigned)std::min<int64_t>(ntiles, (int64_t)std::max(per_sm, 1) * num_sms), SYN_THREADS, bytes, s>>>(  \
+            S, F.window, F.wshift, F.preem, F.remove_dc, bd, tile_frames, (int)ntiles, d_osamp_off, pcm, spec, out, tw, ts, ti, win)
     if (F.window == 512 && F.wshift == 256) { CTU_SYNTH_LAUNCH(512, 256); }
     else if (F.window == 400 && F.wshift == 160) { CTU_SYNTH_LAUNCH(400, 160); }
     else { CTU_SYNTH_LAUNCH(0, 0); }
