@@ -117,6 +117,8 @@ def lib() -> C.CDLL:
     L.ctu_plan_run_host.argtypes = [vp, vp, vp, vp, vp, vp, vp]; L.ctu_plan_run_host.restype = C.c_int
     L.ctu_run.argtypes = [vp, vp, vp, i32, vp, vp, i64, vp, i64, vp, vp, vp, vp]; L.ctu_run.restype = C.c_int
     L.ctu_debug_spectrum.argtypes = [vp, vp, vp, vp]; L.ctu_debug_spectrum.restype = C.c_int
+    L.ctu_host_alloc.argtypes = [P(vp), C.c_uint64]; L.ctu_host_alloc.restype = C.c_int
+    L.ctu_host_free.argtypes = [vp]; L.ctu_host_free.restype = None
     _lib = L
     return L
 

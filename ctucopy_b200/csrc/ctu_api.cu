@@ -50,6 +50,10 @@ struct ctu_handle {
     std::vector<double> w64, m264, lift64;
     double *d_w64 = nullptr, *d_m264 = nullptr, *d_lift64 = nullptr;
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    // device blocks of destroyed plans, kept for the next plan: a list is processed as a sequence of plans of
+    // similar size, and cudaMalloc / cudaFree of gigabytes cost more than the kernels that use them
+    struct PoolBlock { void *p; size_t bytes; bool used; };
+    std::vector<PoolBlock> pool;
 };
 
 struct ctu_plan {
@@ -85,6 +89,7 @@ struct ctu_plan {
     float *d_fea = nullptr;
     uint8_t *d_ext = nullptr, *d_vadnr_out = nullptr, *d_vad_out = nullptr;
     bool host_bufs = false;
+    std::vector<void *> blocks;          // this plan's blocks of the handle's pool
 };
 
 static thread_local std::string g_create_err;
@@ -488,6 +493,7 @@ void ctu_destroy(ctu_handle *h) {
     cudaFree(h->d_tw256); cudaFree(h->d_twsplit); cudaFree(h->d_twinv); cudaFree(h->d_win);
     cudaFree(h->d_w64); cudaFree(h->d_m264); cudaFree(h->d_lift64);
     cudaFree(h->d_tw256d); cudaFree(h->d_twsplitd); cudaFree(h->d_twinvd); cudaFree(h->d_wind); cudaFree(h->d_hann);
+    for (auto &b : h->pool) cudaFree(b.p);
     for (int i = 0; i < 3; i++) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     h->lc.clear();
     delete h;
@@ -497,9 +503,30 @@ void ctu_destroy(ctu_handle *h) {
 // plan
 // ------------------------------------------------------------------------------------------
 template <class T> static int dev_alloc(ctu_handle *h, ctu_plan *p, T **ptr, size_t n) {
-    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
-    CK(cudaMalloc((void **)ptr, bytes));
+    const size_t bytes = (std::max<size_t>(n, 1) * sizeof(T) + 255) & ~size_t(255);
     p->workspace_bytes += (int64_t)bytes;
+    int best = -1;
+    for (int i = 0; i < (int)h->pool.size(); i++) {
+        const auto &b = h->pool[i];
+        if (!b.used && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096 && (best < 0 || b.bytes < h->pool[best].bytes)) best = i;
+    }
+    if (best >= 0) {
+        h->pool[best].used = true;
+        *ptr = (T *)h->pool[best].p;
+    } else {
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, bytes);
+        if (e != cudaSuccess) {
+            // out of memory: give the cached blocks back and try once more
+            for (auto &b : h->pool) if (!b.used) { cudaFree(b.p); b.p = nullptr; }
+            h->pool.erase(std::remove_if(h->pool.begin(), h->pool.end(), [](const ctu_handle::PoolBlock &b) { return b.p == nullptr; }), h->pool.end());
+            cudaGetLastError();
+            CK(cudaMalloc(&q, bytes));
+        }
+        h->pool.push_back({q, bytes, true});
+        *ptr = (T *)q;
+    }
+    p->blocks.push_back((void *)*ptr);
     return CTU_OK;
 }
 
@@ -588,11 +615,9 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
 void ctu_plan_destroy(ctu_plan *p) {
     if (!p) return;
     cudaSetDevice(p->h->device);
-    cudaFree(p->d_pcm_off); cudaFree(p->d_row_off); cudaFree(p->d_osamp_off); cudaFree(p->d_t32_off); cudaFree(p->d_t64_off);
-    cudaFree(p->d_nframes); cudaFree(p->d_tiles32); cudaFree(p->d_tiles64); cudaFree(p->d_tilesS); cudaFree(p->d_tS_off); cudaFree(p->d_tilesF); cudaFree(p->d_tF_off);
-    cudaFree(p->d_spec); cudaFree(p->d_fb); cudaFree(p->d_fb64); cudaFree(p->d_fea64); cudaFree(p->d_E); cudaFree(p->d_log); cudaFree(p->d_ceps); cudaFree(p->d_cri);
-    cudaFree(p->d_flags); cudaFree(p->d_keep); cudaFree(p->d_vad0); cudaFree(p->d_rows);
-    cudaFree(p->d_pcm); cudaFree(p->d_wave); cudaFree(p->d_fea); cudaFree(p->d_ext); cudaFree(p->d_vadnr_out); cudaFree(p->d_vad_out);
+    cudaDeviceSynchronize();                 // what cudaFree would have done: nothing of this plan is in flight any more
+    for (void *q : p->blocks)
+        for (auto &b : p->h->pool) if (b.p == q) { b.used = false; break; }
     delete p;
 }
 
@@ -914,7 +939,8 @@ int ctu_plan_run_host(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad, f
     }
     // chunks of utterances of roughly 64 MB of PCM, round-robin over three streams so that
     // H2D of chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap
-    const int64_t chunk_samples = 32ll << 20;
+    static const int64_t chunk_mb = getenv("CTU_CHUNK_MB") ? atoll(getenv("CTU_CHUNK_MB")) : 32;   // MB of PCM per pipeline chunk (e2e is flat between 16 and 64)
+    const int64_t chunk_samples = chunk_mb << 19;
     int u0 = 0, ci = 0;
     const int64_t base = p->offsets[0];
     while (u0 < p->n_utts) {
@@ -956,6 +982,15 @@ int ctu_run(ctu_handle *h, const int16_t *pcm, const int64_t *off, int32_t n, co
     ctu_plan_destroy(p);
     return st;
 }
+
+int ctu_host_alloc(void **ptr, uint64_t bytes) {
+    if (!ptr) return CTU_ERR_CONFIG;
+    *ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(ptr, (size_t)std::max<uint64_t>(bytes, 1), cudaHostAllocDefault);
+    if (e != cudaSuccess) { g_create_err = std::string("CUDA: ") + cudaGetErrorString(e) + " (cudaHostAlloc)"; return CTU_ERR_CUDA; }
+    return CTU_OK;
+}
+void ctu_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
 
 int ctu_debug_spectrum(ctu_plan *p, const int16_t *d_pcm, float *d_spec, void *stream) {
     if (!p) return CTU_ERR_CONFIG;

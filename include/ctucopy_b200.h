@@ -167,6 +167,12 @@ int ctu_run(ctu_handle *h, const int16_t *pcm, const int64_t *utt_offsets, int32
             float *features, int64_t features_capacity_rows, int16_t *waveform, int64_t waveform_capacity,
             uint8_t *vad_nr, uint8_t *vad_out, int64_t *frames_per_utt, int64_t *rows_per_utt);
 
+/* Page-locked host memory for the buffers handed to ctu_plan_run_host / ctu_run: pageable memory
+ * makes every chunk copy synchronous and several times slower.  (What rawIN's fread buffer and the
+ * writers' obuffer are to the reference, src/io/in.cc:434-460, src/io/out.cc:95-106.)            */
+int ctu_host_alloc(void **ptr, uint64_t bytes);
+void ctu_host_free(void *ptr);
+
 /* Debug / test taps (device-resident, synchronous): intermediate stages of one plan run. */
 int ctu_debug_spectrum(ctu_plan *p, const int16_t *d_pcm, float *d_spec /* [frames x wfftby2] */, void *stream);
 

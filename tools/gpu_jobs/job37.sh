@@ -1,0 +1,3 @@
+timeout 900 python -m pytest tests -m gpu -q --maxfail=10 -p no:cacheprovider 2>&1 | tail -15 > gpurun_out/t18.log
+tail -3 gpurun_out/t18.log
+python tools/cli_e2e.py 20000 2>&1 | grep -v "batch"
