@@ -17,7 +17,7 @@ import numpy as np
 
 CTU_STR = 40
 CTU_FBDEF = 1024
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class CtuError(RuntimeError):
@@ -66,6 +66,8 @@ class Config(C.Structure):
         ("vad_dyn_qmaxdec", C.c_double), ("vad_dyn_qmindec", C.c_double), ("vad_dyn_qmininc", C.c_double),
         ("vad_filter_order", C.c_int32),
         ("window", C.c_int32), ("wshift", C.c_int32), ("wfft", C.c_int32), ("wfftby2", C.c_int32), ("phase_needed", C.c_int32),
+        ("fea_Z_exp", C.c_float), ("fea_Z_block", C.c_float), ("cms_exp_coef", C.c_float),
+        ("stat_cmvn", C.c_int32), ("apply_cmvn", C.c_int32),
     ]
 
 
@@ -88,6 +90,9 @@ def lib() -> C.CDLL:
     L = C.CDLL(p)
     vp, i32, i64, cp = C.c_void_p, C.c_int32, C.c_int64, C.c_char_p
     P = C.POINTER
+    L.ctu_config_sizeof.argtypes = []; L.ctu_config_sizeof.restype = C.c_int
+    if L.ctu_config_sizeof() != C.sizeof(Config):
+        raise ImportError("ctucopy_b200.api.Config (%d bytes) does not mirror struct ctu_config of %s (%d bytes)" % (C.sizeof(Config), p, L.ctu_config_sizeof()))
     L.ctu_config_init.argtypes = [P(Config)]; L.ctu_config_init.restype = C.c_int
     L.ctu_config_set.argtypes = [P(Config), cp, cp]; L.ctu_config_set.restype = C.c_int
     L.ctu_config_parse.argtypes = [P(Config), C.c_int, P(cp)]; L.ctu_config_parse.restype = C.c_int

@@ -432,6 +432,16 @@ static int resolve_modes(ctu_handle *h) {
         if (c.vad_filter_order < 1 || c.vad_filter_order % 2 == 0)
             return fail(h, CTU_ERR_CONFIG, "medianFilter: filter order must be positive, odd number!");
     }
+    // post-processing
+    if (c.stat_cmvn || c.apply_cmvn)
+        return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -stat_cmvn / -apply_cmvn (per-speaker CMVN passes over the whole list) are not built yet");
+    if (c.fea_Z_block > 0)
+        return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_Z_block: the reference dies with SIGSEGV in this mode (ring of row pointers allocated with sizeof(float), src/fea/post_impl.cc:179); nothing to match");
+    if (c.cms_exp_coef > 0) {
+        if (h->signal_out || (h->fea_kind != FEA_DCTC && h->fea_kind != FEA_LPC))
+            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_Z_exp is built for cepstral features (dctc, lpc)");
+        if (h->do_vad) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_Z_exp together with the VAD module");
+    }
     if (c.dither != 0.0)
         return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -dither != 0 draws from glibc rand() in list order (src/io/in.cc:205,454); not reproducible on a parallel device. Use -dither 0.");
     if (c.remove_dc1) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -remove_dc1 on is not built yet");
@@ -871,6 +881,14 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
             h->lc.end(s);
             CK(cudaGetLastError());
         }
+    }
+    if (h->cfg.cms_exp_coef > 0 && r.nrows > 0) {
+        // static block in writer order: c1..cN [c0]; c0 is normalised in the reference even when it is not written
+        const int ncols = h->static_dim, n = (r.u1 - r.u0) * ncols;
+        h->lc.begin("k_cms_exp", s);
+        k_cms_exp<<<(n + 127) / 128, 128, 0, s>>>(p->d_nframes, p->d_row_off, r.u0, r.u1 - r.u0, ncols, h->feature_dim, h->cfg.cms_exp_coef, d_fea);
+        h->lc.end(s);
+        CK(cudaGetLastError());
     }
     if (h->energy_mode && r.t64_n > 0) {
         if (h->energy_mode == EN_RAW) {

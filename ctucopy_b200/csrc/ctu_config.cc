@@ -48,6 +48,7 @@ int ctu_config_init(ctu_config *c) {
     c->nr_when = 0;
     put(c->fea_kind, "lpc");
     c->fea_lporder = 12; c->fea_ncepcoefs = 12; c->fea_c0 = 1; c->fea_E = 0; c->fea_rawenergy = 0;
+    c->fea_Z_exp = -1.f; c->fea_Z_block = -1.f; c->cms_exp_coef = -1.f; c->stat_cmvn = 0; c->apply_cmvn = 0;   // src/io/opts.cc:86-91
     c->fea_lifter = 22;
     c->fea_trapdct_traplen = 0; c->fea_trapdct_ndct = 0;  // the reference leaves these uninitialised
     c->fea_delta = 0; c->n_order = 0; c->d_win = c->a_win = c->t_win = 2;
@@ -126,11 +127,11 @@ const Opt kOpts[] = {
     {"-vad_dyn_qmaxinc", K_DBL, O(vad_dyn_qmaxinc)}, {"-vad_dyn_qmaxdec", K_DBL, O(vad_dyn_qmaxdec)},
     {"-vad_dyn_qmindec", K_DBL, O(vad_dyn_qmindec)}, {"-vad_dyn_qmininc", K_DBL, O(vad_dyn_qmininc)},
     {"-vad_filter_order", K_INT, O(vad_filter_order)},
+    {"-fea_Z_exp", K_FLT, O(fea_Z_exp)}, {"-fea_Z_block", K_FLT, O(fea_Z_block)},
     // owned by the host CLI, not by the hot path: accepted, no effect here
     {"-S", K_IGNORE, 0}, {"-i", K_IGNORE, 0}, {"-o", K_IGNORE, 0}, {"-C", K_IGNORE, 0},
     {"-format_in", K_IGNORE, 0}, {"-endian_in", K_IGNORE, 0}, {"-endian_out", K_IGNORE, 0},
-    {"-vad_out", K_IGNORE, 0}, {"-stat_cmvn", K_IGNORE, 0}, {"-apply_cmvn", K_IGNORE, 0},
-    {"-fea_Z_exp", K_IGNORE, 0}, {"-fea_Z_block", K_IGNORE, 0}, {"-filters", K_IGNORE, 0},
+    {"-vad_out", K_IGNORE, 0}, {"-filters", K_IGNORE, 0},
     {"-nfeacoefs", K_IGNORE, 0}, {"-weight_of_td_iir_mfcc_bank", K_IGNORE, 0}, {"-nr_rasta", K_IGNORE, 0},
     {"-online_in", K_FLAG_IGNORE, 0}, {"-online_out", K_FLAG_IGNORE, 0}, {"-fb_printself", K_FLAG_IGNORE, 0},
     {"-verbose", K_FLAG_IGNORE, 0}, {"-v", K_FLAG_IGNORE, 0}, {"-quiet", K_FLAG_IGNORE, 0},
@@ -162,6 +163,8 @@ int ctu_config_set(ctu_config *c, const char *l, const char *r) {
         else return cfg_fail("OPTS: Syntax error in option -vad !");
         return CTU_OK;
     }
+    if (opt == "-stat_cmvn") { if (r) c->stat_cmvn = 1; return CTU_OK; }
+    if (opt == "-apply_cmvn") { if (r) c->apply_cmvn = 1; return CTU_OK; }
     if (opt == "-nr_when") {
         if (r && !std::strcmp(r, "beforeFB")) c->nr_when = 0;
         else if (r && !std::strcmp(r, "afterFB")) c->nr_when = 1;
@@ -219,6 +222,8 @@ int ctu_config_set(ctu_config *c, const char *l, const char *r) {
     return cfg_fail(msg);
 }
 
+int ctu_config_sizeof(void) { return (int)sizeof(ctu_config); }
+
 int ctu_config_finalize(ctu_config *c) {
     if (!c) return CTU_ERR_CONFIG;
     if (c->fs == 0) return cfg_fail("OPTS: Please specify sampling rate!");
@@ -235,6 +240,9 @@ int ctu_config_finalize(ctu_config *c) {
     if (c->preem >= 1.0f || c->preem < 0.0f) return cfg_fail("OPTS: Preemphasis not in range <0,1)!");
     if (sig && c->fb_power) c->fb_power = 0;  // src/io/opts.cc:312-316
     if (c->window <= 0 || c->wshift <= 0 || c->wfft == 0) return cfg_fail("OPTS: bad window / shift");
+    // exponential CMS: the time constant becomes the (float) smoothing coefficient (src/io/opts.cc:273-274);
+    // kept in its own field so that finalising twice is harmless
+    c->cms_exp_coef = (c->fea_Z_exp != -1.f) ? (float)(1.0 - (2 * c->wshift_ms) / (double)c->fea_Z_exp) : -1.f;
     return CTU_OK;
 }
 

@@ -611,6 +611,29 @@ k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, cons
 }
 
 // ------------------------------------------------------------------------------------------
+// Exponential cepstral mean subtraction (cms_POST::process_frame, src/fea/post_impl.cc:203-209):
+// per utterance and per static coefficient  m = m*Z + c*(1-Z);  c -= m  with a FLOAT running mean
+// and a float coefficient, applied to the finished rows (the deltas were taken from the
+// un-normalised statics, src/io/batch.cc:159-163).  One thread per (utterance, column).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_cms_exp(const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int u0, int n_utts, int ncols, int stride, float Z,
+          float *__restrict__ fea) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_utts * ncols) return;
+    const int u = u0 + gid / ncols, col = gid % ncols;
+    const int T = nframes[u];
+    float *x = fea + row_off[u] * stride + col;
+    const float omZ = 1.0f - Z;
+    float m = 0.f;
+    for (int t = 0; t < T; t++, x += stride) {
+        const double c = (double)*x;
+        m = (float)((double)(m * Z) + c * (double)omZ);
+        *x = (float)(c - (double)m);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // raw energy (src/io/in.cc:353-361): log of the sum of squares of the frame's raw samples 1..w-1
 // (the first one is skipped).  One warp per frame.
 // ------------------------------------------------------------------------------------------

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CTU_ABI_VERSION 1
+#define CTU_ABI_VERSION 2
 #define CTU_STR 40
 #define CTU_FBDEF 1024
 
@@ -85,6 +85,11 @@ typedef struct ctu_config {
     int32_t vad_filter_order;
     /* derived by ctu_config_finalize (opts::check_config, src/io/opts.cc:255-325) */
     int32_t window, wshift, wfft, wfftby2, phase_needed;
+    /* post-processing (src/fea/post_impl.cc): cepstral mean subtraction.  Time constants in ms, -1 = off
+     * (floats like the reference, src/io/opts.h); cms_exp_coef = 1 - 2*wshift_ms/fea_Z_exp is derived.   */
+    float   fea_Z_exp, fea_Z_block;
+    float   cms_exp_coef;
+    int32_t stat_cmvn, apply_cmvn;   /* CMVN passes: recognised, not built (CTU_ERR_UNSUPPORTED)       */
 } ctu_config;
 
 typedef struct ctu_handle ctu_handle;
@@ -92,6 +97,7 @@ typedef struct ctu_plan ctu_plan;
 
 /* ---- configuration (replaces opts::opts / set_preset / parse / check_config) ---------- */
 int ctu_config_init(ctu_config *cfg);                         /* defaults, src/io/opts.cc:34-146   */
+int ctu_config_sizeof(void);                                  /* sizeof(ctu_config) of this build: lets a binding check its mirror */
 /* One option exactly as opts::parse takes it (src/io/opts.cc:644-846): `value` may be NULL.
  * Options outside the hot path (-S -i -o -C -v ... -format_in -endian_*) are accepted and
  * ignored here; the host CLI owns them.  Unknown option -> CTU_ERR_CONFIG.               */

@@ -68,6 +68,10 @@ class Opts:
     fea_ncepcoefs: int = 12
     fea_c0: bool = True
     fea_E: bool = False
+    fea_Z_exp: float = -1.0            # stored as float (src/io/opts.h); check_config turns the time constant into the coefficient
+    fea_Z_block: float = -1.0
+    length_b: int = 0
+    cms_exp_coef: float = -1.0
     fea_rawenergy: bool = False
     fea_lifter: int = 22
     fea_trapdct_traplen: int = 0
@@ -217,6 +221,10 @@ def _parse_one(o: Opts, l: str, r: Optional[str]) -> None:
     elif l == "-fea_ncepcoefs": o.fea_ncepcoefs = int(r)
     elif l == "-fea_c0": o.fea_c0 = _onoff(r, o.fea_c0)
     elif l == "-fea_E": o.fea_E = _onoff(r, o.fea_E)
+    elif l == "-fea_Z_exp":
+        if r is not None: o.fea_Z_exp = float(np.float32(float(r)))
+    elif l == "-fea_Z_block":
+        if r is not None: o.fea_Z_block = float(np.float32(float(r)))
     elif l == "-fea_rawenergy": o.fea_rawenergy = _onoff(r, o.fea_rawenergy)
     elif l == "-fea_lifter": o.fea_lifter = int(r)
     elif l == "-vad_apply_mode": o.vad_apply_mode = r
@@ -259,6 +267,12 @@ def check_config(o: Opts) -> Opts:
             o.wfft = i * (1 + (1 if (o.window % i) != 0 else 0))
         i //= 2
     o.wfftby2 = o.wfft // 2 + 1
+    # CMS (src/io/opts.cc:270-274): block length in frames; the exp time constant becomes the (float) coefficient
+    o.cms_exp_coef = -1.0
+    if o.fea_Z_block != -1:
+        o.length_b = int(math.floor((o.fea_Z_block - o.window_ms) / o.wshift_ms)) + 1
+    if o.fea_Z_exp != -1:
+        o.cms_exp_coef = float(np.float32(1.0 - (2 * o.wshift_ms) / o.fea_Z_exp))
     o.phase_needed = o.format_out in ("raw", "wave")
     if o.vadmode == "burg":
         o.phase_needed = True
@@ -1247,6 +1261,27 @@ def writer_order(F: np.ndarray, o: Opts) -> np.ndarray:
     return F[:, cols]
 
 
+def cms(F: np.ndarray, o: Opts) -> np.ndarray:
+    """cms_POST::process_frame, exponential version (src/fea/post_impl.cc:203-209), on the finished
+    feature vector (after the deltas, src/io/batch.cc:159-163, 198-199): only the first ncep+1 elements
+    (internal order: c0..cN) are normalised.  `sumM` is float and so is the coefficient
+    (src/fea/post_impl.h, src/io/opts.h): sumM = sumM*Z + F*(1-Z); F -= sumM.
+    The block version (-fea_Z_block) is not restated: the reference binary dies with SIGSEGV on it (its
+    ring of row pointers is allocated with sizeof(float) per pointer, src/fea/post_impl.cc:179)."""
+    if o.fea_Z_block > 0:
+        raise ValueError("CTU: -fea_Z_block: the reference crashes in this mode (src/fea/post_impl.cc:179); nothing to match")
+    F = F.copy()
+    n = o.fea_ncepcoefs + 1
+    f32 = np.float32
+    Z = f32(o.cms_exp_coef)
+    omZ = f32(1) - Z
+    sumM = np.zeros(n, dtype=f32)
+    for t in range(F.shape[0]):
+        sumM = (np.float64(sumM * Z) + F[t, :n] * np.float64(omZ)).astype(f32)
+        F[t, :n] -= sumM.astype(np.float64)
+    return F
+
+
 def energy_column(o: Opts, fe: "FrontEnd", Xs: np.ndarray, Y: np.ndarray, kind: str, inld: bool, lat: int) -> np.ndarray:
     """The optional _E column.  Which stage's E the writer points at is decided in
     BATCH::init_out (src/io/batch.cc:98-118): raw energy -> IN (src/io/in.cc:353-361); dctc ->
@@ -1315,6 +1350,8 @@ def run_pipeline(pcm: np.ndarray, o: Opts, ext_vad: Optional[np.ndarray] = None)
     internal = F
     if o.n_order > 0 and k in ("dctc", "lpc"):
         F = add_deltas(F, o)
+    if o.cms_exp_coef > 0 or o.fea_Z_block > 0:
+        F = cms(F, o)
     out = writer_order(F, o) if k != "lpa" else F[:, 1:]
     lat = 0
     if k in ("dctc", "lpc"):

@@ -93,6 +93,9 @@ CASES = {
     "logspec_E": (B + MF + ["-fea_kind", "logspec", "-fea_E", "on", "-format_out", "htk"], "htk", {}),
     "mfcc_exten_E": (B + MF + ["-nr_mode", "exten", "-fea_E", "on", "-format_out", "htk"], "htk", {}),
     "mfcc_exten_afterFB_E": (B + MF + ["-nr_mode", "exten", "-nr_when", "afterFB", "-fea_E", "on", "-format_out", "htk"], "htk", {}),
+    # exponential cepstral mean subtraction (src/fea/post_impl.cc:203-209); the block version crashes the reference
+    "mfcc_cms_exp_d_a": (B + MF + ["-fea_Z_exp", "500", "-fea_delta", "d_a", "-format_out", "htk"], "htk", {}),
+    "plp_cms_exp": (B + ["-preset", "plpc", "-fea_Z_exp", "2000", "-format_out", "htk"], "htk", {}),
 }
 
 
