@@ -122,6 +122,11 @@ def lib() -> C.CDLL:
     L.ctu_plan_run_host.argtypes = [vp, vp, vp, vp, vp, vp, vp]; L.ctu_plan_run_host.restype = C.c_int
     L.ctu_run.argtypes = [vp, vp, vp, i32, vp, vp, i64, vp, i64, vp, vp, vp, vp]; L.ctu_run.restype = C.c_int
     L.ctu_debug_spectrum.argtypes = [vp, vp, vp, vp]; L.ctu_debug_spectrum.restype = C.c_int
+    L.ctu_plan_run_host_keep.argtypes = [vp, vp, vp]; L.ctu_plan_run_host_keep.restype = C.c_int
+    L.ctu_plan_fetch.argtypes = [vp, vp, vp, vp, vp]; L.ctu_plan_fetch.restype = C.c_int
+    L.ctu_cmvn_dim.argtypes = [vp]; L.ctu_cmvn_dim.restype = C.c_int
+    L.ctu_plan_colsums.argtypes = [vp, vp, vp]; L.ctu_plan_colsums.restype = C.c_int
+    L.ctu_plan_normalise.argtypes = [vp, vp, vp]; L.ctu_plan_normalise.restype = C.c_int
     L.ctu_host_alloc.argtypes = [P(vp), C.c_uint64]; L.ctu_host_alloc.restype = C.c_int
     L.ctu_host_free.argtypes = [vp]; L.ctu_host_free.restype = None
     _lib = L

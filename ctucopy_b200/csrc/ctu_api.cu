@@ -433,8 +433,14 @@ static int resolve_modes(ctu_handle *h) {
             return fail(h, CTU_ERR_CONFIG, "medianFilter: filter order must be positive, odd number!");
     }
     // post-processing
-    if (c.stat_cmvn || c.apply_cmvn)
-        return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -stat_cmvn / -apply_cmvn (per-speaker CMVN passes over the whole list) are not built yet");
+    if (c.stat_cmvn || c.apply_cmvn) {
+        // the host drives the passes (ctu_plan_colsums / ctu_plan_normalise); what the device half supports:
+        if (h->signal_out || h->do_vad || h->fea_kind == FEA_LPA || h->fea_kind == FEA_TRAPDCT ||
+            ((h->fea_kind == FEA_DCTC || h->fea_kind == FEA_LPC) && !c.fea_c0))
+            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: CMVN is built for dctc / lpc (with c0), spec and logspec features without the VAD module");
+        if (c.cms_exp_coef > 0 || c.fea_Z_block > 0)
+            return fail(h, CTU_ERR_CONFIG, "OPTS: CMN or CMVN can not be set together with CMS option (exp or block CMS normalisations)!");
+    }
     if (c.fea_Z_block > 0)
         return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_Z_block: the reference dies with SIGSEGV in this mode (ring of row pointers allocated with sizeof(float), src/fea/post_impl.cc:179); nothing to match");
     if (c.cms_exp_coef > 0) {
@@ -938,13 +944,13 @@ int ctu_plan_run_device(ctu_plan *p, const int16_t *d_pcm, const uint8_t *d_ext_
     return fetch_rows(p, s);
 }
 
-int ctu_plan_run_host(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad, float *features, int16_t *waveform, uint8_t *vad_nr,
-                      uint8_t *vad_out) {
+static int run_host_impl(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad, float *features, int16_t *waveform, uint8_t *vad_nr,
+                         uint8_t *vad_out, bool keep) {
     if (!p) return CTU_ERR_CONFIG;
     ctu_handle *h = p->h;
     CK(cudaSetDevice(h->device));
-    if (!h->signal_out && !features) return fail(h, CTU_ERR_CAPACITY, "CTU: features buffer is NULL");
-    if (h->signal_out && !waveform) return fail(h, CTU_ERR_CAPACITY, "CTU: waveform buffer is NULL");
+    if (!keep && !h->signal_out && !features) return fail(h, CTU_ERR_CAPACITY, "CTU: features buffer is NULL");
+    if (!keep && h->signal_out && !waveform) return fail(h, CTU_ERR_CAPACITY, "CTU: waveform buffer is NULL");
     int st;
     if (!p->host_bufs) {
         if ((st = dev_alloc(h, p, &p->d_pcm, (size_t)p->total_samples + 8))) return st;
@@ -971,6 +977,7 @@ int ctu_plan_run_host(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad, f
         if (ext_vad && r.nrows) CK(cudaMemcpyAsync(p->d_ext + r.row0, ext_vad + r.row0, r.nrows, cudaMemcpyHostToDevice, s));
         if (h->signal_out) CK(cudaMemsetAsync(p->d_wave + p->osamp_off[u0], 0, (size_t)(p->osamp_off[u1] - p->osamp_off[u0]) * sizeof(int16_t), s));
         if ((st = run_range(p, r, p->d_pcm - base, ext_vad ? p->d_ext : nullptr, p->d_fea, p->d_wave, p->d_vadnr_out, p->d_vad_out, s))) return st;
+        if (keep) { u0 = u1; ci++; continue; }             // results stay on the device (ctu_plan_fetch brings them back)
         if (!h->signal_out && r.nrows)
             CK(cudaMemcpyAsync(features + r.row0 * h->feature_dim, p->d_fea + r.row0 * h->feature_dim,
                                (size_t)r.nrows * h->feature_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -984,6 +991,78 @@ int ctu_plan_run_host(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad, f
     }
     for (int i = 0; i < 3; i++) CK(cudaStreamSynchronize(h->streams[i]));
     return fetch_rows(p, h->streams[0]);
+}
+
+int ctu_plan_run_host(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad, float *features, int16_t *waveform, uint8_t *vad_nr,
+                      uint8_t *vad_out) {
+    return run_host_impl(p, pcm, ext_vad, features, waveform, vad_nr, vad_out, false);
+}
+
+int ctu_plan_run_host_keep(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad) {
+    return run_host_impl(p, pcm, ext_vad, nullptr, nullptr, nullptr, nullptr, true);
+}
+
+int ctu_plan_fetch(ctu_plan *p, float *features, int16_t *waveform, uint8_t *vad_nr, uint8_t *vad_out) {
+    if (!p || !p->host_bufs) return CTU_ERR_CONFIG;
+    ctu_handle *h = p->h;
+    CK(cudaSetDevice(h->device));
+    if (features && p->d_fea) CK(cudaMemcpy(features, p->d_fea, (size_t)p->total_frames * h->feature_dim * sizeof(float), cudaMemcpyDeviceToHost));
+    if (waveform && p->d_wave) CK(cudaMemcpy(waveform, p->d_wave, (size_t)p->total_osamp * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    if (vad_nr) CK(cudaMemcpy(vad_nr, p->d_vadnr_out, (size_t)p->total_frames, cudaMemcpyDeviceToHost));
+    if (vad_out && h->do_vad) CK(cudaMemcpy(vad_out, p->d_vad_out, (size_t)p->total_frames, cudaMemcpyDeviceToHost));
+    return CTU_OK;
+}
+
+// ---- per-utterance column statistics and normalisation of the device-resident feature rows: the device
+// half of CMVN (cmvn_POST::sum_fea / sum_cv / process_frame, src/fea/post_impl.cc:52-118).  The host
+// groups utterances by speaker and owns the statistics file.
+int ctu_cmvn_dim(const ctu_handle *h) { return h ? h->feature_dim - (h->energy_mode ? 1 : 0) : 0; }
+
+int ctu_plan_colsums(ctu_plan *p, const double *center, double *sums) {
+    if (!p || !sums || !p->host_bufs || !p->d_fea) return CTU_ERR_CONFIG;
+    ctu_handle *h = p->h;
+    CK(cudaSetDevice(h->device));
+    const int dim = ctu_cmvn_dim(h);
+    const size_t n = (size_t)p->n_utts * dim;
+    if (n == 0) return CTU_OK;
+    double *d_c = nullptr, *d_s = nullptr;
+    int st;
+    if ((st = dev_alloc(h, p, &d_s, n))) return st;
+    if (center) {
+        if ((st = dev_alloc(h, p, &d_c, n))) return st;
+        CK(cudaMemcpy(d_c, center, n * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    h->lc.begin("k_colsums", h->streams[0]);
+    k_colsums<<<(unsigned)((n + 127) / 128), 128, 0, h->streams[0]>>>(p->d_nframes, p->d_row_off, p->n_utts, dim, h->feature_dim, p->d_fea, d_c, d_s);
+    h->lc.end(h->streams[0]);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(sums, d_s, n * sizeof(double), cudaMemcpyDeviceToHost, h->streams[0]));
+    CK(cudaStreamSynchronize(h->streams[0]));
+    return CTU_OK;
+}
+
+int ctu_plan_normalise(ctu_plan *p, const double *mean, const double *scale) {
+    if (!p || !mean || !scale || !p->host_bufs || !p->d_fea) return CTU_ERR_CONFIG;
+    ctu_handle *h = p->h;
+    CK(cudaSetDevice(h->device));
+    const int dim = ctu_cmvn_dim(h);
+    const size_t n = (size_t)p->n_utts * dim;
+    if (n == 0) return CTU_OK;
+    double *d_m = nullptr, *d_v = nullptr;
+    int st;
+    if ((st = dev_alloc(h, p, &d_m, n)) || (st = dev_alloc(h, p, &d_v, n))) return st;
+    CK(cudaMemcpy(d_m, mean, n * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_v, scale, n * sizeof(double), cudaMemcpyHostToDevice));
+    const int64_t t64 = p->tile64_off[p->n_utts];
+    if (t64 > 0) {
+        BatchDesc bd64{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tiles64};
+        h->lc.begin("k_normalise", h->streams[0]);
+        k_normalise<<<(unsigned)t64, 256, 0, h->streams[0]>>>(bd64, dim, h->feature_dim, d_m, d_v, p->d_fea);
+        h->lc.end(h->streams[0]);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(h->streams[0]));
+    return CTU_OK;
 }
 
 int ctu_run(ctu_handle *h, const int16_t *pcm, const int64_t *off, int32_t n, const uint8_t *ext_vad, float *features,

@@ -634,6 +634,41 @@ k_cms_exp(const int *__restrict__ nframes, const int64_t *__restrict__ row_off, 
 }
 
 // ------------------------------------------------------------------------------------------
+// CMVN, device half (cmvn_POST::sum_fea / sum_cv / process_frame, src/fea/post_impl.cc:52-118):
+// per-utterance column sums (of the values, or of squared deviations from a centre) in a fixed
+// order -- the host adds the utterances of a speaker in list order, so the statistics are
+// reproducible -- and the normalisation (F - mean) / var of every row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_colsums(const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int n_utts, int dim, int stride,
+          const float *__restrict__ fea, const double *__restrict__ center, double *__restrict__ sums) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_utts * dim) return;
+    const int u = gid / dim, col = gid - u * dim;
+    const int T = nframes[u];
+    const float *x = fea + row_off[u] * stride + col;
+    const double c = center ? center[gid] : 0.0;
+    double acc = 0.0;
+    if (center) for (int t = 0; t < T; t++, x += stride) { const double d = (double)*x - c; acc += d * d; }
+    else for (int t = 0; t < T; t++, x += stride) acc += (double)*x;
+    sums[gid] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+k_normalise(BatchDesc bd, int dim, int stride, const double *__restrict__ mean, const double *__restrict__ scale, float *__restrict__ fea) {
+    const int2 tile = bd.tiles[blockIdx.x];
+    const int u = tile.x, t0 = tile.y;
+    const int nr = min(DELTA_ROWS_C, bd.nframes[u] - t0);
+    float *base = fea + (bd.row_off[u] + t0) * stride;
+    const double *m = mean + (int64_t)u * dim, *v = scale + (int64_t)u * dim;
+    for (int i = threadIdx.x; i < nr * dim; i += blockDim.x) {
+        const int r = i / dim, col = i - r * dim;
+        float *x = base + r * stride + col;
+        *x = (float)(((double)*x - m[col]) / v[col]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // raw energy (src/io/in.cc:353-361): log of the sum of squares of the frame's raw samples 1..w-1
 // (the first one is skipped).  One warp per frame.
 // ------------------------------------------------------------------------------------------

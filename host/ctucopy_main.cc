@@ -39,6 +39,7 @@ struct HostOpts {
     int shard_r = 0, shard_n = 1; // -shard r/N : this process handles shard r of N (one process per GPU)
     int merge_n = 0;              // -merge N   : merge the pfile / ark+scp shards of N finished `-shard` runs
     int device = -1;              // -device d  : CUDA device (default: shard index modulo device count)
+    std::string stat_cmvn, apply_cmvn;   // CMVN statistics file to write / to apply (src/io/opts.cc:678-685)
     std::string ark_ref;          // ark path recorded in scp lines (the merged file's name)
 };
 
@@ -225,6 +226,8 @@ void take_host_option(HostOpts &o, const char *l, const char *r) {
     else if (opt == "-endian_out" && r) { if (val() == "big") o.big_out = true; else if (val() == "little") o.big_out = false; }
     else if (opt == "-vad" && r) { std::string v = val(); if (v.find("file=") != std::string::npos) o.filevad = v.substr(v.find('=') + 1); }
     else if (opt == "-vad_out" && r) o.vad_out = r;
+    else if (opt == "-stat_cmvn" && r) o.stat_cmvn = r;
+    else if (opt == "-apply_cmvn" && r) o.apply_cmvn = r;
     else if (opt == "-v" || opt == "-verbose") { o.verbose = true; o.quiet = false; }
     else if (opt == "-quiet") { o.quiet = true; o.verbose = false; }
     else if (opt == "-fb_printself") o.fb_printself = true;
@@ -577,6 +580,137 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
     tmark("whole range", t_start);
 }
 
+// ---- CMVN over the whole list (src/io/batch.cc:136-152, 339-420; src/fea/post_impl.cc:52-118) ------------
+// -stat_cmvn <f>: two passes, per-speaker mean and variance of every feature, written to <f>, no features.
+// -apply_cmvn <f> with <f> not there yet: the same two passes, <f> written, then a third pass that writes
+// (F - mean) / var.  (With an existing <f> the reference never finds its speakers again and writes +-inf;
+// that mode is refused.)  The device does the column sums and the normalisation; the host groups the
+// utterances by speaker in list order and owns the file.
+void process_cmvn(const HostOpts &ho, const ctu_config &cfg, const std::vector<ListEntry> &list, int device,
+                  const std::vector<unsigned char> &extvad) {
+    const bool apply = !ho.apply_cmvn.empty();
+    const std::string statfile = apply ? ho.apply_cmvn : ho.stat_cmvn;
+    if (apply) {
+        if (FILE *f = std::fopen(statfile.c_str(), "rb")) {
+            std::fclose(f);
+            die("CTU: -apply_cmvn with an existing statistics file: the reference does not find its speakers again and writes +-inf "
+                "(src/io/in.cc:743-770, src/fea/post_impl.cc:45); delete the file to compute and apply the statistics in one run");
+        }
+        std::cout << "IN: Cannot open stat. cmvn file!" << std::endl << "IN: Stat. cmvn file is being created: " << statfile << std::endl;
+    }
+    // speakers: third list column (second one for statistics-only lists of two columns)
+    std::vector<std::string> names;
+    std::vector<int> spk(list.size());
+    for (size_t i = 0; i < list.size(); i++) {
+        std::string id = list[i].spk;
+        if (id.empty()) {
+            if (apply) die(" Bad list format for applying cmvn!");
+            id = list[i].out;
+        }
+        size_t j = 0;
+        while (j < names.size() && names[j] != id) j++;
+        if (j == names.size()) names.push_back(id);
+        spk[i] = (int)j;
+    }
+    ctu_handle *h = nullptr;
+    if (ctu_create(&cfg, device, &h)) die(ctu_last_error(nullptr));
+    const int fdim = ctu_feature_dim(h), dim = ctu_cmvn_dim(h);
+    const bool use_ext = !std::strcmp(cfg.vadmode, "file");
+    std::vector<int64_t> nsamp(list.size());
+    parallel_for(list.size(), IO_THREADS, [&](size_t i) { nsamp[i] = count_samples(ho, list[i].in); });
+    std::vector<size_t> cuts{0};
+    {
+        int64_t acc = 0;
+        for (size_t i = 0; i < list.size(); i++) {
+            acc += nsamp[i];
+            if (acc >= (int64_t(1) << 26)) { cuts.push_back(i + 1); acc = 0; }
+        }
+        if (cuts.back() != list.size()) cuts.push_back(list.size());
+    }
+    const size_t ns = names.size();
+    std::vector<double> sum(ns * dim, 0.0), var(ns * dim, 0.0), cnt(ns, 0.0);
+    Pinned pcmbuf, feabuf;
+    Writers W(ho, cfg, fdim);
+    for (int pass = 0; pass < (apply ? 3 : 2); pass++) {
+        size_t fr_before = 0;
+        for (size_t k = 0; k + 1 < cuts.size(); k++) {
+            const size_t i0 = cuts[k], i1 = cuts[k + 1], n = i1 - i0;
+            std::vector<int64_t> off(n + 1, 0), frames(n);
+            int64_t total = 0;
+            for (size_t u = 0; u < n; u++) {
+                off[u + 1] = off[u] + nsamp[i0 + u];
+                frames[u] = ctu_num_frames(h, nsamp[i0 + u]);
+                if (frames[u] < 0) die("IO: Signal shorter than one frame!");
+                total += frames[u];
+            }
+            pcmbuf.reserve((uint64_t)(off[n] + 8) * 2);
+            int16_t *pcm = (int16_t *)pcmbuf.p;
+            parallel_for(n, IO_THREADS, [&](size_t u) { decode_into(ho, cfg.fs, list[i0 + u].in, pcm + off[u], off[u + 1] - off[u]); });
+            const uint8_t *ev = nullptr;
+            if (use_ext) {
+                if (fr_before + (size_t)total > extvad.size()) die("NR: Unexpected end of VAD file!");
+                ev = extvad.data() + fr_before;
+            }
+            fr_before += (size_t)total;
+            ctu_plan *p = nullptr;
+            if (ctu_plan_create(h, off.data(), (int)n, &p)) die(ctu_last_error(h));
+            if (ctu_plan_run_host_keep(p, pcm, ev)) die(ctu_last_error(h));
+            std::vector<double> a(n * dim), b(n * dim);
+            if (pass == 0) {
+                if (ctu_plan_colsums(p, nullptr, a.data())) die(ctu_last_error(h));
+                for (size_t u = 0; u < n; u++) {
+                    const int j = spk[i0 + u];
+                    for (int c = 0; c < dim; c++) sum[(size_t)j * dim + c] += a[u * dim + c];
+                    cnt[j] += (double)frames[u];
+                }
+            } else if (pass == 1) {
+                for (size_t u = 0; u < n; u++) std::copy(sum.begin() + (size_t)spk[i0 + u] * dim, sum.begin() + (size_t)(spk[i0 + u] + 1) * dim, a.begin() + u * dim);
+                if (ctu_plan_colsums(p, a.data(), b.data())) die(ctu_last_error(h));
+                for (size_t u = 0; u < n; u++)
+                    for (int c = 0; c < dim; c++) var[(size_t)spk[i0 + u] * dim + c] += b[u * dim + c];
+            } else {
+                for (size_t u = 0; u < n; u++) {
+                    std::copy(sum.begin() + (size_t)spk[i0 + u] * dim, sum.begin() + (size_t)(spk[i0 + u] + 1) * dim, a.begin() + u * dim);
+                    std::copy(var.begin() + (size_t)spk[i0 + u] * dim, var.begin() + (size_t)(spk[i0 + u] + 1) * dim, b.begin() + u * dim);
+                }
+                if (ctu_plan_normalise(p, a.data(), b.data())) die(ctu_last_error(h));
+                feabuf.reserve((uint64_t)total * fdim * 4);
+                if (ctu_plan_fetch(p, (float *)feabuf.p, nullptr, nullptr, nullptr)) die(ctu_last_error(h));
+                int64_t r0 = 0;
+                for (size_t u = 0; u < n; u++) { W.features(list[i0 + u], (const float *)feabuf.p + r0 * fdim, frames[u]); r0 += frames[u]; }
+            }
+            ctu_plan_destroy(p);
+        }
+        if (pass == 0) {
+            for (size_t j = 0; j < ns; j++) for (int c = 0; c < dim; c++) sum[j * dim + c] /= cnt[j];       // sum -> mean (stat_cm)
+        } else if (pass == 1) {
+            for (size_t j = 0; j < ns; j++) for (int c = 0; c < dim; c++) var[j * dim + c] /= (cnt[j] - 1);  // stat_cv
+            // statistics file (cmvnOUT::save_frame, src/io/out.cc:591-615) in the reference's order: the
+            // internal vector F[1..], then F[0] -- c0 of the static block goes last, everything else stays
+            const std::string kind(cfg.fea_kind);
+            const bool cep = (kind == "dctc" || kind == "lpc");
+            const int nblk = cfg.fea_ncepcoefs + 1;
+            std::vector<int> wcol(dim);            // statistics index -> writer column
+            for (int w = 0; w < dim; w++) {
+                int i = w;                         // internal index of writer column w
+                if (cep) { const int j = w / nblk, pw = w % nblk; i = j * nblk + (pw == nblk - 1 ? 0 : pw + 1); }
+                wcol[i == 0 ? dim - 1 : i - 1] = w;
+            }
+            FILE *f = std::fopen(statfile.c_str(), "wt");
+            if (!f) die("OUT: Cannot create output file with stat. of cmvn!");
+            for (size_t j = 0; j < ns; j++) {
+                std::fprintf(f, "%s\nmean\t", names[j].c_str());
+                for (int i = 0; i < dim; i++) std::fprintf(f, i + 1 < dim ? "%f " : "%f", sum[j * dim + wcol[i]]);
+                std::fprintf(f, "\nvar\t");
+                for (int i = 0; i < dim; i++) std::fprintf(f, i + 1 < dim ? "%f " : "%f\n", var[j * dim + wcol[i]]);
+            }
+            std::fclose(f);
+        }
+    }
+    W.close();
+    ctu_destroy(h);
+}
+
 int run(int argc, char **argv) {
     if (argc == 1) { std::cerr << "usage: ctucopy_b200 <ctucopy options> -S <list> [-gpus N | -shard r/N | -merge N]   (options: man/ctucopy4 of the reference)" << std::endl; die("OPTS: No command line options!"); }
     ctu_config cfg;
@@ -645,6 +779,11 @@ int run(int argc, char **argv) {
     std::vector<unsigned char> extvad;
     if (!std::strcmp(cfg.vadmode, "file")) extvad = slurp(ho.filevad, "NR: Unable to open VAD file!\n");
     const int nparts = ho.gpus > 1 ? ho.gpus : ho.shard_n;
+    if (!ho.stat_cmvn.empty() || !ho.apply_cmvn.empty()) {
+        if (nparts != 1) die("CTU: CMVN statistics span the whole list: run it in one process (no -gpus / -shard)");
+        process_cmvn(ho, cfg, list, ho.device < 0 ? 0 : ho.device, extvad);
+        return 0;
+    }
     if (nparts == 1) {
         process_range(ho, cfg, list, 0, list.size(), ho.device < 0 ? 0 : ho.device, extvad, 0);
         return 0;

@@ -168,6 +168,22 @@ int ctu_plan_run_device(ctu_plan *p, const int16_t *d_pcm, const uint8_t *d_ext_
 int ctu_plan_run_host(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad, float *features,
                       int16_t *waveform, uint8_t *vad_nr, uint8_t *vad_out);
 
+/* The same in steps, for callers that post-process on the device before fetching: run with the results
+ * left on the device, [ctu_plan_colsums / ctu_plan_normalise], then ctu_plan_fetch.                  */
+int ctu_plan_run_host_keep(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad);
+int ctu_plan_fetch(ctu_plan *p, float *features, int16_t *waveform, uint8_t *vad_nr, uint8_t *vad_out);
+
+/* CMVN, device half (cmvn_POST::sum_fea / sum_cv / process_frame, src/fea/post_impl.cc:52-118), on the
+ * feature rows ctu_plan_run_host_keep left on the device.  dim = ctu_cmvn_dim(): the row without the _E
+ * column, in WRITER column order.  Arrays are host arrays [n_utts x dim].
+ *   ctu_plan_colsums  : sums[u][c] = sum over the rows of utterance u of F[c]            (center == NULL)
+ *                                  = sum of (F[c] - center[u][c])^2                      (center != NULL)
+ *   ctu_plan_normalise: F[c] = (F[c] - mean[u][c]) / scale[u][c]   (the reference divides by the VARIANCE)
+ * The host groups utterances by speaker and owns the statistics file (src/io/out.cc:591-615).          */
+int ctu_cmvn_dim(const ctu_handle *h);
+int ctu_plan_colsums(ctu_plan *p, const double *center, double *sums);
+int ctu_plan_normalise(ctu_plan *p, const double *mean, const double *scale);
+
 /* Convenience: plan + run_host + destroy.  frames_per_utt/rows_per_utt may be NULL.     */
 int ctu_run(ctu_handle *h, const int16_t *pcm, const int64_t *utt_offsets, int32_t n_utts, const uint8_t *ext_vad,
             float *features, int64_t features_capacity_rows, int16_t *waveform, int64_t waveform_capacity,

@@ -72,6 +72,8 @@ class Opts:
     fea_Z_block: float = -1.0
     length_b: int = 0
     cms_exp_coef: float = -1.0
+    stat_cmvn: bool = False
+    apply_cmvn: bool = False
     fea_rawenergy: bool = False
     fea_lifter: int = 22
     fea_trapdct_traplen: int = 0
@@ -221,6 +223,10 @@ def _parse_one(o: Opts, l: str, r: Optional[str]) -> None:
     elif l == "-fea_ncepcoefs": o.fea_ncepcoefs = int(r)
     elif l == "-fea_c0": o.fea_c0 = _onoff(r, o.fea_c0)
     elif l == "-fea_E": o.fea_E = _onoff(r, o.fea_E)
+    elif l == "-stat_cmvn":
+        if r is not None: o.stat_cmvn = True
+    elif l == "-apply_cmvn":
+        if r is not None: o.apply_cmvn = True
     elif l == "-fea_Z_exp":
         if r is not None: o.fea_Z_exp = float(np.float32(float(r)))
     elif l == "-fea_Z_block":
@@ -1280,6 +1286,89 @@ def cms(F: np.ndarray, o: Opts) -> np.ndarray:
         sumM = (np.float64(sumM * Z) + F[t, :n] * np.float64(omZ)).astype(f32)
         F[t, :n] -= sumM.astype(np.float64)
     return F
+
+
+def cmvn_stat_order(F: np.ndarray) -> np.ndarray:
+    """Statistics are kept as F[1], ..., F[size-1], F[0] of the INTERNAL vector -- c0 of the static block
+    moves to the very end, everything else (deltas included) keeps its place (src/fea/post_impl.cc:60-64)."""
+    return np.concatenate([F[:, 1:], F[:, :1]], axis=1)
+
+
+def cmvn_stats(feats: List[np.ndarray], spk: List[str]):
+    """cmvn_POST::sum_fea / stat_cm / sum_cv / stat_cv (src/fea/post_impl.cc:52-104) driven as BATCH::process
+    does for -stat_cmvn (src/io/batch.cc:339-420): pass 0 sums every frame of a speaker's files (list order),
+    mean = sum / count; pass 1 sums squared deviations, var = sum / (count - 1).  feats: internal-order
+    feature matrices (after deltas), one per list line.  Returns (speaker names in order of first
+    appearance, mean [n_spk, size], var [n_spk, size]) in the statistics order of cmvn_stat_order."""
+    names: List[str] = []
+    for s_ in spk:
+        if s_ not in names:
+            names.append(s_)
+    size = feats[0].shape[1]
+    mean = np.zeros((len(names), size)); var = np.zeros((len(names), size)); cnt = np.zeros(len(names))
+    for F, s_ in zip(feats, spk):
+        j = names.index(s_)
+        G = cmvn_stat_order(F)
+        for t in range(G.shape[0]):
+            mean[j] += G[t]
+        cnt[j] += G.shape[0]
+    mean /= cnt[:, None]
+    for F, s_ in zip(feats, spk):
+        j = names.index(s_)
+        G = cmvn_stat_order(F)
+        for t in range(G.shape[0]):
+            d = G[t] - mean[j]
+            var[j] += d * d
+    var /= (cnt[:, None] - 1)
+    return names, mean, var
+
+
+def cmvn_stat_text(names: List[str], mean: np.ndarray, var: np.ndarray) -> str:
+    """cmvnOUT::save_frame, src/io/out.cc:591-615: "<id>\nmean\t%f %f ... %f\nvar\t%f ... %f\n" per speaker."""
+    out = ""
+    for j, n in enumerate(names):
+        out += "%s\nmean\t%s\nvar\t%s\n" % (n, " ".join("%f" % v for v in mean[j]), " ".join("%f" % v for v in var[j]))
+    return out
+
+
+def cmvn_apply(F: np.ndarray, mean: np.ndarray, var: np.ndarray) -> np.ndarray:
+    """cmvn_POST::process_frame, src/fea/post_impl.cc:106-118: (F - mean) / var -- the VARIANCE, not its root."""
+    G = (cmvn_stat_order(F) - mean) / var
+    return np.concatenate([G[:, -1:], G[:, :-1]], axis=1)
+
+
+def run_list_cmvn(pcms: List[np.ndarray], spk: List[str], o: Opts):
+    """A whole list through -stat_cmvn (statistics only) or -apply_cmvn with a statistics file that does not
+    exist yet (three passes: statistics, then normalised features; src/io/batch.cc:136-152, 339-420).
+    Returns (statistics text, per-utterance float32 feature matrices in writer order or None)."""
+    feats = []
+    for pcm in pcms:
+        fe = front_end(pcm, o)
+        fb = fb_design(o)
+        if o.nr_when == "afterFB":
+            Y, _ = apply_nr(fb_project(fe.Xabs, fb), o, None, None)
+        else:
+            Xs, _ = apply_nr(fe.Xabs, o, fe.Xph, None)
+            Y = fb_project(Xs, fb)
+        k = o.fea_kind
+        if k == "spec": F = Y.copy()
+        elif k == "logspec": F = np.log(Y)
+        elif k == "dctc": F = fea_dctc(Y, o)
+        elif k == "lpc": F = fea_lpc(Y, o, fb.inld)
+        else: raise ValueError("CTU: CMVN oracle covers spec, logspec, dctc and lpc")
+        if o.n_order > 0 and k in ("dctc", "lpc"):
+            F = add_deltas(F, o)
+        feats.append(F)
+    names, mean, var = cmvn_stats(feats, spk)
+    text = cmvn_stat_text(names, mean, var)
+    if not o.apply_cmvn:
+        return text, None
+    outs = []
+    for F, s_ in zip(feats, spk):
+        j = names.index(s_)
+        G = cmvn_apply(F, mean[j], var[j])
+        outs.append((writer_order(G, o)).astype(np.float32))
+    return text, outs
 
 
 def energy_column(o: Opts, fe: "FrontEnd", Xs: np.ndarray, Y: np.ndarray, kind: str, inld: bool, lat: int) -> np.ndarray:

@@ -99,6 +99,14 @@ CASES = {
 }
 
 
+CMVN_CASES = {
+    # -apply_cmvn with a statistics file that does not exist yet: statistics passes, file written, features normalised
+    "cmvn_3stage_d_a": (B + MF + ["-format_out", "htk", "-fea_delta", "d_a", "-apply_cmvn", "{STAT}"], [0, 1, 4, 5], ["spkA", "spkA", "spkB", "spkB"]),
+    # -stat_cmvn: statistics only
+    "cmvn_stat_plp": (B + ["-preset", "plpc", "-format_out", "htk", "-stat_cmvn", "{STAT}"], [0, 4, 1, 5, 2], ["s1", "s2", "s1", "s2", "s3"]),
+}
+
+
 def inputs():
     utts = [synthetic.utterance(k, 1.0) for k in (0, 1, 5, 13)]           # tone/chirp, noisy + clean
     utts.append(synthetic.utterance(2, 2.5))
@@ -119,7 +127,7 @@ def main():
         assert all(np.array_equal(z["in%d" % i], u) for i, u in enumerate(utts)), "inputs.npz differs from inputs()"
 
     rng = np.random.default_rng(7)
-    names = sys.argv[1:] or list(CASES)
+    names = [n for n in sys.argv[1:] if n in CASES] if sys.argv[1:] else list(CASES)
     for name in names:
         args, kind, extra = CASES[name]
         outs, vads, flags_all = [], [], []
@@ -152,6 +160,28 @@ def main():
                 d["extvad%d" % i] = flags_all[i]
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
         print(name, "ok", sum(len(o) for o in outs), "bytes")
+    # CMVN over a LIST with speakers: statistics file + normalised features, one reference process
+    for name, (args, idx, spk) in CMVN_CASES.items():
+        if sys.argv[1:] and name not in sys.argv[1:]:
+            continue
+        import subprocess, tempfile
+        with tempfile.TemporaryDirectory() as d:
+            for i in idx:
+                utts[i].astype("<i2").tofile(os.path.join(d, "u%d.raw" % i))
+            with open(os.path.join(d, "list.scp"), "w") as fh:
+                for i, sp in zip(idx, spk):
+                    fh.write("%s/u%d.raw %s/u%d.htk %s\n" % (d, i, d, i, sp))
+            a = [x.replace("{STAT}", os.path.join(d, "cmvn.stat")) for x in args]
+            pr = subprocess.run([rr.ref_binary("O0")] + a + ["-S", os.path.join(d, "list.scp")], capture_output=True, cwd=d)
+            assert pr.returncode == 0, (name, pr.stderr)
+            dd = {"args": np.array(json.dumps(args)), "idx": np.array(idx), "spk": np.array(json.dumps(spk)),
+                  "stat": np.frombuffer(open(os.path.join(d, "cmvn.stat"), "rb").read(), dtype=np.uint8)}
+            for i in idx:
+                pth = os.path.join(d, "u%d.htk" % i)
+                if os.path.exists(pth):
+                    dd["out%d" % i] = np.frombuffer(open(pth, "rb").read(), dtype=np.uint8)
+            np.savez_compressed(os.path.join(OUT, name + ".npz"), **dd)
+            print(name, "ok")
     if sys.argv[1:]:
         return       # only the named cases were asked for
     # filter-bank design goldens via the undocumented -fb_printself (src/fea/fb.cc:449-456)

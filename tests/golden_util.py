@@ -20,7 +20,15 @@ def inputs():
 
 
 def case_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("inputs.npz", "fb_design.npz"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("inputs.npz", "fb_design.npz") and not f.startswith("cmvn_"))
+
+
+def cmvn_case(name):
+    """A list-mode CMVN golden: (args with {STAT}, input indices, speakers, statistics text, {index: HTK bytes})."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    idx = [int(i) for i in z["idx"]]
+    outs = {i: z["out%d" % i].tobytes() for i in idx if ("out%d" % i) in z.files}
+    return json.loads(str(z["args"])), idx, json.loads(str(z["spk"])), z["stat"].tobytes().decode(), outs
 
 
 class Case:

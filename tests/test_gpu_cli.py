@@ -124,3 +124,46 @@ def test_cli_sharded_run_merges_to_the_single_process_files(tmp_path):
                 want = open(one / fn, "rb").read().replace(str(one).encode(), b"@")
                 assert got == want, fn
         assert not [f for f in os.listdir(two) if f.startswith("shard")]
+
+
+def _stat_numbers(text):
+    names, vals = [], []
+    for ln in text.splitlines():
+        tok = ln.split()
+        if tok and tok[0] in ("mean", "var"):
+            vals.append([float(x) for x in tok[1:]])
+        elif tok:
+            names.append(tok[0])
+    return names, np.array(vals)
+
+
+@pytest.mark.parametrize("name", ["cmvn_3stage_d_a", "cmvn_stat_plp"])
+def test_cli_cmvn_statistics_and_normalised_features(tmp_path, name):
+    """List-mode CMVN through the CLI against the reference binary's statistics file and feature files."""
+    args, idx, spk, stat, outs = gu.cmvn_case(name)
+    ins = gu.inputs()
+    for i in idx:
+        ins[i].astype("<i2").tofile(tmp_path / ("u%d.raw" % i))
+    with open(tmp_path / "list.scp", "w") as fh:
+        for i, sp in zip(idx, spk):
+            fh.write("%s/u%d.raw %s/u%d.htk %s\n" % (tmp_path, i, tmp_path, i, sp))
+    a = [x.replace("{STAT}", str(tmp_path / "cmvn.stat")) for x in args]
+    pr = subprocess.run([EXE] + a + ["-S", str(tmp_path / "list.scp")], capture_output=True)
+    assert pr.returncode == 0, pr.stderr.decode()
+    names, vals = _stat_numbers(open(tmp_path / "cmvn.stat").read())
+    rnames, rvals = _stat_numbers(stat)
+    assert names == rnames and vals.shape == rvals.shape
+    np.testing.assert_allclose(vals, rvals, rtol=2e-4, atol=2e-4)
+    for i in idx:
+        if i in outs:
+            got = open(tmp_path / ("u%d.htk" % i), "rb").read()
+            assert got[:12] == outs[i][:12]
+            g, w = rr.parse_htk(got)[1], rr.parse_htk(outs[i])[1]
+            # north_star tolerance for log-domain features; the division by a small variance (deltas) scales absolute errors up
+            assert np.all(np.abs(g - w) <= 1e-4 * np.abs(w) + 1e-3), float(np.abs(g - w).max())
+        else:
+            assert not (tmp_path / ("u%d.htk" % i)).exists()
+    # applying from an existing statistics file is refused (the reference writes +-inf there)
+    if "-apply_cmvn" in args:
+        pr = subprocess.run([EXE] + a + ["-S", str(tmp_path / "list.scp")], capture_output=True)
+        assert pr.returncode == 255 and b"existing statistics file" in pr.stderr

@@ -92,3 +92,20 @@ def test_frame_count_edge_cases():
     assert co.num_frames(160000, o) == 998
     with pytest.raises(ValueError):
         co.num_frames(239, o)
+
+
+@pytest.mark.parametrize("name", ["cmvn_3stage_d_a", "cmvn_stat_plp"])
+def test_oracle_cmvn_matches_reference_binary(name):
+    """List-mode CMVN (src/fea/post_impl.cc:52-118, src/io/batch.cc:136-152, 339-420): statistics file text
+    and normalised features identical to the reference binary's."""
+    args, idx, spk, stat, outs = gu.cmvn_case(name)
+    o = co.parse_args([a.replace("{STAT}", "x.stat") for a in args])
+    ins = gu.inputs()
+    text, feats = co.run_list_cmvn([ins[i] for i in idx], spk, o)
+    assert text == stat
+    if o.apply_cmvn:
+        import ref_runner as rr
+        for j, i in enumerate(idx):
+            assert np.array_equal(feats[j], rr.parse_htk(outs[i])[1]), (name, i)
+    else:
+        assert not outs           # statistics only: no feature files
