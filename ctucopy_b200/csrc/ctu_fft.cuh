@@ -134,6 +134,63 @@ CTU_HD void rfft_split(const cpx<T> *zlin, int c, const cpx<T> *twsplit, cpx<T> 
     mid = conj(zlin[128]);   // only meaningful for c == 0
 }
 
+// ---- real-input split and its inverse WITHOUT shared memory ---------------------------------
+// After pass 2 thread c holds Z[c + 16 k2] in a[k2].  X[k] for k = c + 16 j (j < 8) needs Z[k] = a[j]
+// and Z[256-k], which thread (16-c)%16 holds at index 15-j (thread 0 pairs with itself at index
+// 16-j).  The kernels fetch Zp[j] = partner's a[15-j] with register shuffles (ctu_kernels.cuh);
+// the arithmetic lives here so that tests/emu can run it thread by thread.  Same maths as rfft_split.
+template <class T>
+CTU_HD void rfft_split_pairs(const cpx<T> (&a)[16], const cpx<T> (&Zp)[8], int c, const cpx<T> *twsplit, cpx<T> (&lo)[8], cpx<T> (&hi)[8],
+                             cpx<T> &mid) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        cpx<T> Z = Zp[j];
+        if (c == 0 && j >= 1) Z = a[j >= 1 ? 16 - j : 0];
+        const cpx<T> A = a[j];
+        if (j == 0 && c == 0) {
+            lo[j] = mk<T>(A.x + A.y, (T)0);
+            hi[j] = mk<T>(A.x - A.y, (T)0);
+        } else {
+            const cpx<T> B = conj(Z);
+            const cpx<T> E = mk<T>((T)0.5 * (A.x + B.x), (T)0.5 * (A.y + B.y));
+            const cpx<T> Tt = cmul(twsplit[c + 16 * j], A - B);
+            lo[j] = E + Tt;
+            hi[j] = conj(E - Tt);
+        }
+    }
+    mid = conj(a[8]);   // X[128], meaningful for c == 0
+}
+
+// inverse, step 1 (thread-local): from the half-complex bins of thread c (lo[j] = X[k], hi[j] = X[256-k],
+// k = c + 16 j; mid = X[128] on thread 0) the values conj(Zc[k]) -> a[j] and conj(Zc[256-k]) -> zn[j],
+// and conj(Zc[128]) -> z128.  Same maths as irfft_presplit.
+template <class T>
+CTU_HD void irfft_presplit_local(cpx<T> (&a)[16], cpx<T> (&zn)[8], cpx<T> &z128, int c, const cpx<T> *twinv, const cpx<T> (&lo)[8],
+                                 const cpx<T> (&hi)[8], cpx<T> mid) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (j == 0 && c == 0) {
+            a[0] = conj(mk<T>(lo[0].x + hi[0].x, lo[0].x - hi[0].x));
+            zn[0] = mk<T>((T)0, (T)0);
+        } else {
+            const cpx<T> S = lo[j] + conj(hi[j]);
+            const cpx<T> U = cmul(lo[j] - conj(hi[j]), twinv[c + 16 * j]);
+            a[j] = conj(mk<T>(S.x - U.y, S.y + U.x));           // conj(Zc[k])
+            zn[j] = conj(mk<T>(S.x + U.y, -S.y + U.x));         // conj(Zc[256-k])
+        }
+    }
+    // Zc[128] pairs with itself (thread 0): S = 2 Re(mid), U = 2i Im(mid) * twinv[128]
+    const cpx<T> Um = cmul(mk<T>((T)0, (T)2 * mid.y), twinv[128]);
+    z128 = conj(mk<T>((T)2 * mid.x - Um.y, Um.x));
+}
+// inverse, step 2: the column a[n1] = conj(Zc[16 n1 + c]) the first inverse pass wants.  n1 < 8 is local
+// (step 1); a[15-r] is the partner's zn[r] (thread (16-c)%16), thread 0 takes its own zn[r+1] and z128.
+template <class T>
+CTU_HD void irfft_presplit_place(cpx<T> (&a)[16], int c, const cpx<T> (&zn)[8], const cpx<T> (&znp)[8], cpx<T> z128) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) a[15 - r] = (c == 0) ? ((r == 7) ? z128 : zn[r < 7 ? r + 1 : 0]) : znp[r];
+}
+
 // ---- inverse: half-complex spectrum -> 512 real samples (unnormalised) ------------------
 // Thread c provides X[k] (lo[j]) and X[256-k] (hi[j]) for k = c + 16*j and, for c == 0,
 // X[128] in mid.  Writes conj(Zc) into zlin; after a sync run pass1 (loading column c of

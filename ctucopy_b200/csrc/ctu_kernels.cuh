@@ -116,70 +116,36 @@ __device__ __forceinline__ float group_sum16(float v) {
     return v;
 }
 
-// real-input split without shared memory.  After pass 2 thread c holds Z[c + 16 k2] in a[k2].
-// X[k] for k = c + 16 j (j < 8) needs Z[k] = a[j] and Z[256-k], which thread (16-c)%16 holds at
-// index 15-j (thread 0 pairs with itself at index 16-j).  Same arithmetic as rfft_split.
+// real-input split / inverse pre-split with the partner values fetched by register shuffles between
+// thread c and thread (16-c)%16 of the group (arithmetic: ctu_fft.cuh, emulated in tests/emu)
 template <class T>
 __device__ __forceinline__ void rfft_split_shfl(const cpx<T> (&a)[16], int c, const cpx<T> *twsplit, cpx<T> (&lo)[8], cpx<T> (&hi)[8],
                                                 cpx<T> &mid) {
     const unsigned m = 0xffffu << (threadIdx.x & 16);
     const int src = (16 - c) & 15;
+    cpx<T> Zp[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        cpx<T> Z;
-        Z.x = __shfl_sync(m, a[15 - j].x, src, 16);
-        Z.y = __shfl_sync(m, a[15 - j].y, src, 16);
-        if (c == 0 && j >= 1) Z = a[j >= 1 ? 16 - j : 0];
-        const cpx<T> A = a[j];
-        if (j == 0 && c == 0) {
-            lo[j] = mk<T>(A.x + A.y, (T)0);
-            hi[j] = mk<T>(A.x - A.y, (T)0);
-        } else {
-            const cpx<T> B = conj(Z);
-            const cpx<T> E = mk<T>((T)0.5 * (A.x + B.x), (T)0.5 * (A.y + B.y));
-            const cpx<T> Tt = cmul(twsplit[c + 16 * j], A - B);
-            lo[j] = E + Tt;
-            hi[j] = conj(E - Tt);
-        }
+        Zp[j].x = __shfl_sync(m, a[15 - j].x, src, 16);
+        Zp[j].y = __shfl_sync(m, a[15 - j].y, src, 16);
     }
-    mid = conj(a[8]);   // X[128], meaningful for c == 0
+    rfft_split_pairs(a, Zp, c, twsplit, lo, hi, mid);
 }
 
-// inverse counterpart: half-complex bins (lo[j] = X[k], hi[j] = X[256-k] for k = c + 16 j, mid =
-// X[128] on thread 0) -> the column a[n1] = conj(Zc[16 n1 + c]) that the first inverse pass
-// wants, again by swapping with thread (16-c)%16 instead of going through shared memory.
-// Same arithmetic as irfft_presplit + fft256_load_column.
 template <class T>
 __device__ __forceinline__ void irfft_presplit_shfl(cpx<T> (&a)[16], int c, const cpx<T> *twinv, const cpx<T> (&lo)[8], const cpx<T> (&hi)[8],
                                                     cpx<T> mid) {
     const unsigned m = 0xffffu << (threadIdx.x & 16);
     const int src = (16 - c) & 15;
-    cpx<T> zn[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        if (j == 0 && c == 0) {
-            a[0] = conj(mk<T>(lo[0].x + hi[0].x, lo[0].x - hi[0].x));
-            zn[0] = mk<T>((T)0, (T)0);
-        } else {
-            const cpx<T> S = lo[j] + conj(hi[j]);
-            const cpx<T> U = cmul(lo[j] - conj(hi[j]), twinv[c + 16 * j]);
-            a[j] = conj(mk<T>(S.x - U.y, S.y + U.x));           // conj(Zc[k])
-            zn[j] = conj(mk<T>(S.x + U.y, -S.y + U.x));         // conj(Zc[256-k])
-        }
-    }
-    // Zc[128] pairs with itself (thread 0): S = 2 Re(mid), U = 2i Im(mid) * twinv[128]
-    const cpx<T> Um = cmul(mk<T>((T)0, (T)2 * mid.y), twinv[128]);
-    const cpx<T> z128 = conj(mk<T>((T)2 * mid.x - Um.y, Um.x));
+    cpx<T> zn[8], znp[8], z128;
+    irfft_presplit_local(a, zn, z128, c, twinv, lo, hi, mid);
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-        cpx<T> v;
-        v.x = __shfl_sync(m, zn[r].x, src, 16);
-        v.y = __shfl_sync(m, zn[r].y, src, 16);
-        if (c == 0) v = (r == 7) ? z128 : zn[r < 7 ? r + 1 : 0];
-        a[15 - r] = v;
+        znp[r].x = __shfl_sync(m, zn[r].x, src, 16);
+        znp[r].y = __shfl_sync(m, zn[r].y, src, 16);
     }
+    irfft_presplit_place(a, c, zn, znp, z128);
 }
-
 
 // E = log(2 * (t_0/2 + t_last/2 + sum of the inner terms)) over one row of n values, term = v or
 // v*v; one warp per row, `lane` strided.  The reference's formula for the energy of a

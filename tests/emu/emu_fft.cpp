@@ -55,6 +55,40 @@ template <class T> int run(double tol) {
     }
     printf("inverse: max err %.3g (rel %.3g)\n", e2, e2 / 1000.0);
     bad |= (e2 / 1000.0 > tol);
+    // ---- the variants the kernels use now: on-the-fly twiddles in pass 1, and the split / inverse pre-split
+    // with the partner thread's registers instead of shared memory (shuffles are emulated by reading the
+    // partner's registers directly)
+    static cpx<T> r2[16][16], lo2[16][8], hi2[16][8], mid2[16];
+    for (int c = 0; c < 16; c++) for (int n1 = 0; n1 < 16; n1++) { int n = 16 * n1 + c; r2[c][n1] = mk<T>((T)x[2 * n], (T)x[2 * n + 1]); }
+    for (int c = 0; c < 16; c++) fft256_pass1_rec(r2[c], c, tw256.data(), xch.data());
+    for (int c = 0; c < 16; c++) fft256_pass2(r2[c], c, xch.data());
+    for (int c = 0; c < 16; c++) {
+        cpx<T> Zp[8];
+        for (int j = 0; j < 8; j++) Zp[j] = r2[(16 - c) & 15][15 - j];
+        rfft_split_pairs(r2[c], Zp, c, twsplit.data(), lo2[c], hi2[c], mid2[c]);
+    }
+    double e3 = 0;
+    for (int c = 0; c < 16; c++) for (int j = 0; j < 8; j++) {
+        int k = c + 16 * j;
+        e3 = fmax(e3, hypot(lo2[c][j].x - re[k], lo2[c][j].y - im[k]));
+        e3 = fmax(e3, hypot(hi2[c][j].x - re[256 - k], hi2[c][j].y - im[256 - k]));
+    }
+    e3 = fmax(e3, hypot(mid2[0].x - re[128], mid2[0].y - im[128]));
+    printf("forward (rec twiddles + register split): max err %.3g (rel %.3g)\n", e3, e3 / ref);
+    bad |= (e3 / ref > 2 * tol);
+    static cpx<T> zn[16][8], z128[16];
+    for (int c = 0; c < 16; c++) irfft_presplit_local(r2[c], zn[c], z128[c], c, twinv.data(), lo2[c], hi2[c], mid2[c]);
+    for (int c = 0; c < 16; c++) irfft_presplit_place(r2[c], c, zn[c], zn[(16 - c) & 15], z128[c]);
+    for (int c = 0; c < 16; c++) fft256_pass1_rec(r2[c], c, tw256.data(), xch.data());
+    for (int c = 0; c < 16; c++) fft256_pass2(r2[c], c, xch.data());
+    double e4 = 0;
+    for (int c = 0; c < 16; c++) for (int k2 = 0; k2 < 16; k2++) {
+        int n = c + 16 * k2;
+        e4 = fmax(e4, fabs(r2[c][k2].x / 512.0 - x[2 * n]));
+        e4 = fmax(e4, fabs(-r2[c][k2].y / 512.0 - x[2 * n + 1]));
+    }
+    printf("inverse (register pre-split): max err %.3g (rel %.3g)\n", e4, e4 / 1000.0);
+    bad |= (e4 / 1000.0 > 2 * tol);
     return bad;
 }
 int main() {

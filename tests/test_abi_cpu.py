@@ -96,3 +96,14 @@ def test_no_cpu_fallback():
     with pytest.raises(cb.CtuError) as e:
         cb.Handle(["-fs", "16000", "-preset", "mfcc", "-format_out", "htk"])
     assert e.value.status == 4 and "no CPU fallback" in e.value.message
+
+
+def test_fft_index_algebra_on_the_cpu(tmp_path):
+    """ctu_fft.cuh is __host__ __device__: the four-step 256-point FFT, the on-the-fly twiddles, the real split
+    and the inverse pre-split (shared-memory and register-exchange variants) run here thread by thread
+    against a naive DFT (tests/emu/emu_fft.cpp)."""
+    import subprocess
+    exe = str(tmp_path / "emu_fft")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "emu", "emu_fft.cpp")])
+    pr = subprocess.run([exe], capture_output=True, text=True)
+    assert pr.returncode == 0 and "OK" in pr.stdout, pr.stdout
