@@ -367,10 +367,11 @@ __device__ __forceinline__ void phase_fea(const FrameParams &P, float *sm, const
         const bool late_log = (KIND == KIND_LOGSPEC && P.energy_mode == EN_BANDS);
         for (int b = wv; b < P.nb; b += CTA_THREADS / 32) sO[lane * od + b] = late_log ? logf(y[b]) : y[b];
         if (P.energy_mode == EN_BANDS && wv == 0 && lane < nf) {
-            float acc = 0.5f * y[0] * y[0];
-            for (int b = 1; b < P.nb - 1; b++) acc += y[b] * y[b];
-            acc += 0.5f * y[P.nb - 1] * y[P.nb - 1];
-            P.energy[row0 + lane] = logf(acc * 2.f);
+            // fp64: with equal-loudness weights the band values are ~1e-20 and their squares leave the fp32 range
+            double acc = 0.5 * (double)y[0] * (double)y[0];
+            for (int b = 1; b < P.nb - 1; b++) acc += (double)y[b] * (double)y[b];
+            acc += 0.5 * (double)y[P.nb - 1] * (double)y[P.nb - 1];
+            P.energy[row0 + lane] = (float)log(acc * 2.0);
         }
     } else if (KIND == KIND_DCTC) {
         for (int i = wv; i < P.nrows; i += CTA_THREADS / 32) {

@@ -213,3 +213,34 @@ def test_full_length_utterances_match_oracle(name):
             r0 = int(res.row_offsets[j])
             got = res.vad_nr[r0: r0 + ref.nframes]
             assert np.array_equal(got.astype(bool), ref.vad_nr), (name, j, int((got.astype(bool) != ref.vad_nr).sum()))
+
+
+def test_randomised_option_sweep_matches_oracle():
+    """A fixed draw of 30 option sets from tools/parity_sweep.py (filter-bank scales / shapes, feature kinds,
+    orders, lifters, deltas, noise-reduction modes, energy, CMS), CUDA vs oracle at the north_star tolerance.
+    hwss is left out: half-wave rectification makes the reference irreproducible against itself."""
+    import random
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("parity_sweep", __import__("os").path.join(gu.GOLDEN, "..", "..", "tools", "parity_sweep.py"))
+    ps = importlib.util.module_from_spec(spec); spec.loader.exec_module(ps)
+    rng = random.Random(5)
+    ins = [gu.inputs()[i] for i in (0, 5)]
+    done = 0
+    while done < 30:
+        args = ps.draw(rng)
+        if "hwss" in args:
+            continue
+        o = co.parse_args(args)
+        try:
+            res = cb.extract(args, ins)
+        except cb.CtuError as e:
+            assert e.status == 3, (args, e.message)          # only "not built" refusals are acceptable
+            continue
+        for i, u in enumerate(ins):
+            ref = co.run_pipeline(u, o)
+            ok, why = ps.tol_ok(res.utt_features(i), ref.features, o.fea_kind)
+            assert ok, (why, " ".join(args))
+            if ref.vad_nr is not None:
+                r0 = int(res.row_offsets[i])
+                assert np.array_equal(res.vad_nr[r0: r0 + ref.nframes].astype(bool), ref.vad_nr), " ".join(args)
+        done += 1

@@ -1,0 +1,135 @@
+#!/usr/bin/env python
+"""Randomised option sweep.  Draws valid command lines from the hot-path option space and compares
+   cpu : the numpy oracle against the REFERENCE BINARY (oracle/_ref, needs /root/reference built here)
+   gpu : the CUDA path against the oracle
+on two short inputs.  usage: python tools/parity_sweep.py cpu|gpu [n] [seed]"""
+import os
+import random
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import ctu_oracle as co  # noqa: E402
+import golden_util as gu  # noqa: E402
+
+B = ["-fs", "16000", "-format_in", "raw", "-dither", "0", "-format_out", "htk"]
+
+
+def draw(rng):
+    a = list(B)
+    kind = rng.choice(["dctc", "dctc", "lpc", "lpc", "spec", "logspec", "lpa", "trapdct"])
+    scale = rng.choice(["mel", "bark", "lin", "expolog"])
+    shape = rng.choice(["triang", "triang", "rect", "trapez"])
+    a += ["-preem", rng.choice(["0", "0.95", "0.97"]), "-w", rng.choice(["25", "25", "20", "30", "32"]), "-s", rng.choice(["10", "10", "8", "16"])]
+    a += ["-remove_dc", rng.choice(["on", "on", "off"])]
+    if shape == "trapez":
+        a += ["-fb_shape", "trapez"]
+    else:
+        nb = rng.choice([15, 20, 23, 26, 30, 40])
+        a += ["-fb_scale", scale, "-fb_shape", shape, "-fb_definition", rng.choice(["%dfilters" % nb, "1-%d/%dfilters" % (nb - 2, nb)])]
+        a += ["-fb_norm", rng.choice(["on", "off"]), "-fb_eqld", rng.choice(["on", "off"]), "-fb_inld", rng.choice(["on", "off"])]
+    a += ["-fb_power", rng.choice(["on", "on", "off"])]
+    ncep = rng.choice([8, 12, 12, 13, 16])
+    if kind == "trapdct":
+        a += ["-fea_kind", "trapdct,%d,%d" % (rng.choice([11, 21, 31]), rng.choice([3, 6]))]
+    else:
+        a += ["-fea_kind", kind]
+    if kind in ("dctc", "lpc", "lpa"):
+        order = ncep if kind == "lpa" else rng.choice([ncep, ncep, 10, 14])
+        a += ["-fea_ncepcoefs", str(ncep), "-fea_lporder", str(order), "-fea_lifter", rng.choice(["22", "0", "1", "30"]), "-fea_c0", "on"]
+    if kind in ("dctc", "lpc") and rng.random() < 0.6:
+        a += ["-fea_delta", rng.choice(["d", "d_a", "d_a_t"]), "-d_win", rng.choice(["2", "3"]), "-a_win", rng.choice(["2", "1"]), "-t_win", "2"]
+    nr = rng.choice(["none", "none", "exten", "exten", "fwss", "hwss", "2fwss"])
+    if nr != "none":
+        a += ["-nr_mode", nr, "-nr_p", rng.choice(["0.95", "0.9"]), "-nr_a", rng.choice(["1", "2"]), "-nr_b", rng.choice(["1", "1.5"]),
+              "-nr_initsegs", rng.choice(["10", "5"])]
+        if nr != "exten":
+            a += ["-vad", "burg"]
+        elif rng.random() < 0.4:
+            a += ["-nr_when", "afterFB"]
+    if kind != "trapdct" and rng.random() < 0.25:
+        a += ["-fea_E", "on"] + (["-fea_rawenergy", "on"] if rng.random() < 0.3 else [])
+    if kind in ("dctc", "lpc") and rng.random() < 0.2 and "-fea_E" not in a:
+        a += ["-fea_Z_exp", rng.choice(["300", "1000"])]
+    return a
+
+
+def tol_ok(got, want, kind):
+    if got.shape != want.shape:
+        return False, "shape %s vs %s" % (got.shape, want.shape)
+    if not gu.same_nonfinite(got, want):
+        return False, "non-finite positions differ"
+    fin = np.isfinite(want)
+    err = np.abs(got - want)[fin]
+    if kind in ("dctc", "lpc", "logspec", "trapdct"):
+        tol = (1e-4 * np.abs(want) + 1e-3)[fin]
+    else:
+        rowmax = np.max(np.where(fin, np.abs(want), 0), axis=1, keepdims=True) * np.ones_like(want)
+        tol = (1e-4 * np.abs(want) + 1e-5 * rowmax)[fin]
+    bad = err > tol
+    return (not bad.any()), ("max err %.3g at %d entries (max |want| %.3g)" % (err.max() if err.size else 0, int(bad.sum()), np.abs(want[fin]).max() if fin.any() else 0))
+
+
+def main():
+    mode = sys.argv[1]
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+    rng = random.Random(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+    ins = [gu.inputs()[i] for i in (0, 5)]
+    nbad = nrun = nskip = 0
+    if mode == "cpu":
+        import ref_runner as rr
+    else:
+        import ctucopy_b200 as cb
+    for it in range(n):
+        args = draw(rng)
+        try:
+            o = co.parse_args(args)
+            refs = [co.run_pipeline(u, o) for u in ins]
+        except Exception as e:  # the option set is invalid for the reference too
+            nskip += 1
+            continue
+        if mode == "cpu":
+            r = rr.run_reference(args, ins, opt="O0", one_per_process=True)
+            if r["returncode"] != 0 or any(x is None for x in r["outputs"]):
+                print("REFERENCE FAILED rc=%s: %s\n   %s" % (r["returncode"], " ".join(args[7:]), r["stderr"].strip()[-120:]))
+                nskip += 1
+                continue
+            for i in range(len(ins)):
+                want = rr.parse_htk(r["outputs"][i])[1]
+                got = refs[i].features
+                ok = got.shape == want.shape and gu.same_nonfinite(got, want) and np.allclose(got[np.isfinite(want)], want[np.isfinite(want)], rtol=3e-6, atol=3e-6)
+                nrun += 1
+                if not ok:
+                    nbad += 1
+                    d = np.abs(got - want)[np.isfinite(want)].max() if got.shape == want.shape else -1
+                    print("ORACLE != REFERENCE (input %d, shape %s vs %s, max diff %.3g): %s" % (i, got.shape, want.shape, d, " ".join(args[7:])))
+        else:
+            try:
+                res = cb.extract(args, ins)
+            except cb.CtuError as e:
+                if e.status == 3:
+                    nskip += 1
+                    continue
+                print("CUDA PATH ERROR %s: %s" % (e.message[:80], " ".join(args[7:])))
+                nbad += 1
+                continue
+            for i in range(len(ins)):
+                ok, why = tol_ok(res.utt_features(i), refs[i].features, o.fea_kind)
+                nrun += 1
+                if refs[i].vad_nr is not None:
+                    r0 = int(res.row_offsets[i])
+                    gv = res.vad_nr[r0: r0 + refs[i].nframes].astype(bool)
+                    if not np.array_equal(gv, refs[i].vad_nr):
+                        ok, why = False, why + "; detector decisions differ at %d frames" % int((gv != refs[i].vad_nr).sum())
+                if not ok:
+                    nbad += 1
+                    print("CUDA != ORACLE (input %d): %s\n   %s" % (i, why, " ".join(args[7:])))
+    print("sweep %s: %d comparisons, %d mismatches, %d option sets skipped" % (mode, nrun, nbad, nskip))
+    return 1 if nbad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
