@@ -370,7 +370,12 @@ static int build_delta_trap_params(ctu_handle *h) {
         // which stage's E the writer points at: BATCH::init_out (src/io/batch.cc:98-118)
         if (h->fea_kind == FEA_TRAPDCT) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_E with trapdct (the reference never sets that energy)");
         if (!std::strcmp(c.format_out, "pfile")) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_E with pfile output (the reference declares the pfile without the energy column, src/io/out.cc:252)");
-        if (c.fea_rawenergy) h->energy_mode = EN_RAW;
+        const bool lp = (h->fea_kind == FEA_LPA || h->fea_kind == FEA_LPC);
+        // with the VAD module init_out never looks at fea_rawenergy (src/io/batch.cc:74-96): lpc/lpa still get log R0,
+        // dctc after the FB gets IN's (raw) energy, the other stages leave their E unset
+        if (c.fea_rawenergy && h->do_vad && !lp && !(h->fea_kind == FEA_DCTC && c.nr_when == 1))
+            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_rawenergy with the VAD module: the reference writes an energy that was never computed (src/io/batch.cc:74-96)");
+        if (c.fea_rawenergy && !(h->do_vad && lp)) h->energy_mode = EN_RAW;
         else if (h->fea_kind == FEA_DCTC) h->energy_mode = (c.nr_when == 1) ? EN_IN : EN_NR;
         else if (h->fea_kind == FEA_LPA || h->fea_kind == FEA_LPC) h->energy_mode = EN_LPC;
         else h->energy_mode = EN_BANDS;

@@ -1387,7 +1387,12 @@ def energy_column(o: Opts, fe: "FrontEnd", Xs: np.ndarray, Y: np.ndarray, kind: 
             return np.array([math.log(_seq_sum(X[t, 1:-1] * X[t, 1:-1], X[t, 0] * X[t, 0] / 2.0 + X[t, -1] * X[t, -1] / 2.0) * 2.0)
                              if True else 0.0 for t in range(X.shape[0])])
 
-    if o.fea_rawenergy:
+    do_vad = o.vad_apply_mode != "none" or o.vad_out_mode != "none"
+    if do_vad and o.fea_rawenergy and not (kind == "dctc" and o.nr_when == "afterFB") and kind not in ("lpa", "lpc"):
+        # with the VAD module BATCH::init_out never looks at fea_rawenergy (src/io/batch.cc:74-96): it points at
+        # nr->E / fea->E, which those stages leave unset when raw energy is asked for
+        raise ValueError("CTU: -fea_rawenergy with the VAD module: the reference writes an energy that was never computed")
+    if o.fea_rawenergy and not (do_vad and kind in ("lpa", "lpc")):
         E = fe.E
     elif kind == "dctc":
         E = fe.E if o.nr_when == "afterFB" else half_spectrum_energy(Xs)

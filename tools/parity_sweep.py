@@ -54,6 +54,19 @@ def draw(rng):
         a += ["-fea_E", "on"] + (["-fea_rawenergy", "on"] if rng.random() < 0.3 else [])
     if kind in ("dctc", "lpc") and rng.random() < 0.2 and "-fea_E" not in a:
         a += ["-fea_Z_exp", rng.choice(["300", "1000"])]
+    # VAD module (src/vad/vad.cc): criterion x threshold x majority filter x apply mode
+    if rng.random() < 0.35 and "-fea_Z_exp" not in a and kind != "trapdct":
+        cri = rng.choice(["energy", "energy", "cepdist"])
+        a += ["-vad_out_mode", "vad", "-vad_cri_mode", cri, "-vad_thr_mode", rng.choice(["absolute", "perc", "adapt", "dyn"]),
+              "-vad_filter_order", rng.choice(["1", "3", "5"]), "-vad_apply_mode", rng.choice(["none", "none", "drop", "silence"])]
+        if cri == "cepdist":
+            mode = rng.choice(["lpc", "fea"]) if kind in ("dctc", "lpc") else "lpc"
+            a += ["-vad_cepdist_mode", mode]
+            if mode == "lpc" and "-vad" not in a:
+                a += ["-vad", "burg"]
+        else:
+            a += ["-vad_energy_db", rng.choice(["on", "off"])]
+        a += ["-vad_absolute_thr", rng.choice(["60", "100"]), "-vad_perc_thr", rng.choice(["50", "30"])]
     return a
 
 
@@ -92,7 +105,8 @@ def main():
             nskip += 1
             continue
         if mode == "cpu":
-            r = rr.run_reference(args, ins, opt="O0", one_per_process=True)
+            do_vad = "-vad_out_mode" in args
+            r = rr.run_reference(args, ins, opt="O0", one_per_process=True, vad_out=do_vad)
             if r["returncode"] != 0 or any(x is None for x in r["outputs"]):
                 print("REFERENCE FAILED rc=%s: %s\n   %s" % (r["returncode"], " ".join(args[7:]), r["stderr"].strip()[-120:]))
                 nskip += 1
@@ -101,6 +115,9 @@ def main():
                 want = rr.parse_htk(r["outputs"][i])[1]
                 got = refs[i].features
                 ok = got.shape == want.shape and gu.same_nonfinite(got, want) and np.allclose(got[np.isfinite(want)], want[np.isfinite(want)], rtol=3e-6, atol=3e-6)
+                if do_vad and ok:
+                    v = np.frombuffer(r["vad"][i]["vad"], dtype=np.uint8) - 48
+                    ok = np.array_equal(v, refs[i].vad.vad.astype(np.uint8))
                 nrun += 1
                 if not ok:
                     nbad += 1
@@ -119,11 +136,15 @@ def main():
             for i in range(len(ins)):
                 ok, why = tol_ok(res.utt_features(i), refs[i].features, o.fea_kind)
                 nrun += 1
+                r0 = int(res.row_offsets[i])
                 if refs[i].vad_nr is not None:
-                    r0 = int(res.row_offsets[i])
                     gv = res.vad_nr[r0: r0 + refs[i].nframes].astype(bool)
                     if not np.array_equal(gv, refs[i].vad_nr):
                         ok, why = False, why + "; detector decisions differ at %d frames" % int((gv != refs[i].vad_nr).sum())
+                if refs[i].vad is not None:
+                    gv = res.vad_out[r0: r0 + refs[i].nframes].astype(bool)
+                    if not np.array_equal(gv, refs[i].vad.vad):
+                        ok, why = False, why + "; VAD-module decisions differ at %d frames" % int((gv != refs[i].vad.vad).sum())
                 if not ok:
                     nbad += 1
                     print("CUDA != ORACLE (input %d): %s\n   %s" % (i, why, " ".join(args[7:])))
