@@ -2,7 +2,7 @@
 """Randomised option sweep.  Draws valid command lines from the hot-path option space and compares
    cpu : the numpy oracle against the REFERENCE BINARY (oracle/_ref, needs /root/reference built here)
    gpu : the CUDA path against the oracle
-on two short inputs.  usage: python tools/parity_sweep.py cpu|gpu [n] [seed]"""
+on two short inputs.  usage: python tools/parity_sweep.py cpu|gpu [n] [seed] [share of waveform-output draws]"""
 import os
 import random
 import sys
@@ -16,9 +16,24 @@ import ctu_oracle as co  # noqa: E402
 import golden_util as gu  # noqa: E402
 
 B = ["-fs", "16000", "-format_in", "raw", "-dither", "0", "-format_out", "htk"]
+SIGNAL_SHARE = 0.0      # share of enhanced-waveform draws (set from the command line: 4th argument)
+
+
+def draw_signal(rng):
+    """enhanced-waveform command lines (src/io/out.cc:346-451): raw output, NR mode x window/shift"""
+    a = ["-fs", "16000", "-format_in", "raw", "-dither", "0", "-format_out", "raw"]
+    w, s_ = rng.choice([("32", "16"), ("32", "16"), ("25", "10"), ("32", "8"), ("20", "10"), ("30", "10"), ("25", "12.5")])
+    a += ["-w", w, "-s", s_, "-preem", rng.choice(["0", "0.97"]), "-remove_dc", rng.choice(["on", "off"])]
+    nr = rng.choice(["exten", "exten", "fwss", "2fwss", "none"])
+    a += ["-nr_mode", nr, "-nr_p", rng.choice(["0.95", "0.9"]), "-nr_a", rng.choice(["1", "2"]), "-nr_b", rng.choice(["1", "1.5"])]
+    if nr in ("fwss", "2fwss"):
+        a += ["-vad", "burg"]
+    return a
 
 
 def draw(rng):
+    if rng.random() < SIGNAL_SHARE:
+        return draw_signal(rng)
     a = list(B)
     kind = rng.choice(["dctc", "dctc", "lpc", "lpc", "spec", "logspec", "lpa", "trapdct"])
     scale = rng.choice(["mel", "bark", "lin", "expolog"])
@@ -90,6 +105,8 @@ def main():
     mode = sys.argv[1]
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
     rng = random.Random(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+    global SIGNAL_SHARE
+    SIGNAL_SHARE = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0
     ins = [gu.inputs()[i] for i in (0, 5)]
     nbad = nrun = nskip = 0
     if mode == "cpu":
@@ -112,6 +129,14 @@ def main():
                 nskip += 1
                 continue
             for i in range(len(ins)):
+                if o.format_out == "raw":
+                    want = np.frombuffer(r["outputs"][i], dtype="<i2")
+                    got = refs[i].waveform
+                    nrun += 1
+                    if got.shape != want.shape or not np.array_equal(got, want):
+                        nbad += 1
+                        print("ORACLE != REFERENCE waveform (input %d, %s vs %s, differing %s): %s" % (i, got.shape, want.shape, int((got != want).sum()) if got.shape == want.shape else -1, " ".join(args[7:])))
+                    continue
                 want = rr.parse_htk(r["outputs"][i])[1]
                 got = refs[i].features
                 ok = got.shape == want.shape and gu.same_nonfinite(got, want) and np.allclose(got[np.isfinite(want)], want[np.isfinite(want)], rtol=3e-6, atol=3e-6)
@@ -134,7 +159,12 @@ def main():
                 nbad += 1
                 continue
             for i in range(len(ins)):
-                ok, why = tol_ok(res.utt_features(i), refs[i].features, o.fea_kind)
+                if o.format_out == "raw":
+                    g, w_ = res.utt_waveform(i).astype(np.int32), refs[i].waveform.astype(np.int32)
+                    ok = g.shape == w_.shape and np.abs(g - w_).max() <= 1 and (g != w_).mean() < 0.02
+                    why = "waveform: shape %s vs %s, max |diff| %s, share differing %.4f" % (g.shape, w_.shape, np.abs(g - w_).max() if g.shape == w_.shape else -1, (g != w_).mean() if g.shape == w_.shape else 1)
+                else:
+                    ok, why = tol_ok(res.utt_features(i), refs[i].features, o.fea_kind)
                 nrun += 1
                 r0 = int(res.row_offsets[i])
                 if refs[i].vad_nr is not None:
