@@ -16,6 +16,7 @@
 #include "ctu_internal.h"
 #include "ctu_kernels.cuh"
 #include "ctu_frames2.cuh"
+#include "ctu_frames_any.cuh"
 #include "ctu_nr_kernels.cuh"
 #include "ctu_precise.cuh"
 
@@ -43,6 +44,14 @@ struct ctu_handle {
     // device tables
     float2 *d_tw256 = nullptr, *d_twsplit = nullptr, *d_twinv = nullptr;
     float *d_win = nullptr;
+    // FFT sizes other than 512 (ctu_frames_any.cuh)
+    bool generic = false;
+    int nbins = NBIN;
+    float2 *d_any_tw = nullptr, *d_any_ts = nullptr;
+    float *d_any_fbw = nullptr;
+    int4 *d_any_bands = nullptr;
+    std::vector<float> fbw_all;
+    std::vector<int4> bands_all;
     double2 *d_tw256d = nullptr, *d_twsplitd = nullptr, *d_twinvd = nullptr;
     double *d_wind = nullptr, *d_hann = nullptr;
     // fp64 tables of the precise path (ctu_precise.cuh)
@@ -241,13 +250,17 @@ static int build_frame_params(ctu_handle *h) {
     int off = 0;
     for (int b = 0; b < fb.nb; b++) {
         int n = fb.hi[b] - fb.lo[b] + 1;
-        if (off + n > MAXW) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: filter bank has too many taps");
+        if (!h->generic && off + n > MAXW) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: filter bank has too many taps");
         off = (off + 3) & ~3;
-        if (off + n > MAXW) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: filter bank has too many taps");
+        if (!h->generic && off + n > MAXW) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: filter bank has too many taps");
         P.lo[b] = (short)fb.lo[b]; P.hi[b] = (short)fb.hi[b]; P.woff[b] = off;
         h->w64.resize(off + n, 0.0);            // same (4-aligned) offsets as the fp32 copy
+        h->fbw_all.resize(off + n, 0.f);
+        h->bands_all.push_back(make_int4(fb.lo[b], n, off, 0));
         for (int k = 0; k < n; k++) {
-            P.w[off + k] = (float)(fb.mat[(size_t)b * fb.bins + fb.lo[b] + k] * S);
+            const float wv = (float)(fb.mat[(size_t)b * fb.bins + fb.lo[b] + k] * S);
+            if (off + k < MAXW) P.w[off + k] = wv;           // the general kernel reads its taps from global memory
+            h->fbw_all[off + k] = wv;
             h->w64[off + k] = fb.mat[(size_t)b * fb.bins + fb.lo[b] + k];
         }
         off += n;
@@ -456,7 +469,16 @@ static int resolve_modes(ctu_handle *h) {
     if (c.dither != 0.0)
         return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -dither != 0 draws from glibc rand() in list order (src/io/in.cc:205,454); not reproducible on a parallel device. Use -dither 0.");
     if (c.remove_dc1) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -remove_dc1 on is not built yet");
-    if (c.wfft != NFFT) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: only 512-point frames (window of 257..512 samples) are built so far");
+    h->generic = (c.wfft != NFFT);
+    h->nbins = c.wfftby2;
+    if (h->generic) {
+        // other sampling rates / window lengths: the general (slower) frame kernel; the specialised 512-point
+        // kernels of the Burg detector, the synthesis and the fp64 path are not generalised yet
+        if (c.wfft < 64 || c.wfft > ANY_MAX_NFFT) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: FFT sizes from 64 to 2048 points are built (window of 33..2048 samples)");
+        if (h->signal_out) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: waveform output is built for 512-point frames only (window of 257..512 samples)");
+        if (h->vad_src == VADSRC_BURG || (h->do_vad && h->vad_cri == VCRI_CEPDIST_LPC))
+            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: the Burg detector is built for 512-point frames only (window of 257..512 samples)");
+    }
     return CTU_OK;
 }
 
@@ -480,6 +502,7 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     if ((st = build_nr_params(h->cfg, h->nr_mode, h->vad_src, h->signal_out, h->fb.nb, h->nrp, h->sp, h->bp, h->vp, h->err))) return bail(st);
     h->vp.cri = h->vad_cri; h->vp.thr = h->vad_thr; h->vp.drop = h->vad_drop;
     h->vp.has_E = h->energy_mode ? 1 : 0;
+    h->vp.nbins = h->nbins;
     // the reference's vector is in internal order (c0 first, a0 first); rows here are in writer order
     if (h->fea_kind == FEA_DCTC || h->fea_kind == FEA_LPC) h->vp.fea_skip = h->cfg.fea_c0 ? h->static_dim - 1 : -1;
     else if (h->fea_kind == FEA_LPA) h->vp.fea_skip = -1;
@@ -495,6 +518,16 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     if (cudaSetDevice(device) != cudaSuccess) { h->err = "CUDA: cudaSetDevice failed"; return bail(CTU_ERR_CUDA); }
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     if ((st = build_fft_tables(h))) return bail(st);
+    if (h->generic) {
+        if (h->precise) { h->err = "CTU: this configuration needs the fp64 path (band-domain noise reduction, LPC without the cube-root law, feature-vector VAD), built for 512-point frames only"; return bail(CTU_ERR_UNSUPPORTED); }
+        const int N = h->cfg.wfft, M = N / 2;
+        const double PI = 3.14159265358979323846264338327950288;
+        std::vector<float2> tw(std::max(1, M / 2)), ts(M + 1);
+        for (int k = 0; k < M / 2; k++) tw[k] = make_float2((float)cos(-2 * PI * k / M), (float)sin(-2 * PI * k / M));
+        for (int k = 0; k <= M; k++) { const double th = 2 * PI * k / N; ts[k] = make_float2((float)(-sin(th) / 2), (float)(-cos(th) / 2)); }
+        if ((st = upload(h, &h->d_any_tw, tw)) || (st = upload(h, &h->d_any_ts, ts)) || (st = upload(h, &h->d_any_fbw, h->fbw_all)) ||
+            (st = upload(h, &h->d_any_bands, h->bands_all))) return bail(st);
+    }
     if (h->nr_mode != NR_NONE && h->cfg.nr_when == 1 && !h->signal_out) h->precise = true;   // subtraction on band values
     // VAD criterion = distance between feature vectors, fed to threshold state machines whose
     // decisions must match the reference bit for bit: features in fp64 like the reference's
@@ -514,6 +547,7 @@ void ctu_destroy(ctu_handle *h) {
     cudaFree(h->d_tw256); cudaFree(h->d_twsplit); cudaFree(h->d_twinv); cudaFree(h->d_win);
     cudaFree(h->d_w64); cudaFree(h->d_m264); cudaFree(h->d_lift64);
     cudaFree(h->d_tw256d); cudaFree(h->d_twsplitd); cudaFree(h->d_twinvd); cudaFree(h->d_wind); cudaFree(h->d_hann);
+    cudaFree(h->d_any_tw); cudaFree(h->d_any_ts); cudaFree(h->d_any_fbw); cudaFree(h->d_any_bands);
     for (auto &b : h->pool) cudaFree(b.p);
     for (int i = 0; i < 3; i++) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     h->lc.clear();
@@ -615,7 +649,7 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     const bool need_spec = h->signal_out || (nr_on && h->cfg.nr_when == 0) || (h->do_vad && h->vad_cri != VCRI_CEPDIST_FEA);
     const bool lpc_kind = (h->fea_kind == FEA_LPA || h->fea_kind == FEA_LPC);
     const bool need_fb = !h->signal_out && ((nr_on && h->cfg.nr_when == 1) || lpc_kind);
-    if (need_spec && (st = dev_alloc(h, p, &p->d_spec, (size_t)rows * NBIN))) { ctu_plan_destroy(p); return st; }
+    if (need_spec && (st = dev_alloc(h, p, &p->d_spec, (size_t)rows * h->nbins))) { ctu_plan_destroy(p); return st; }
     if (need_fb && !h->precise && (st = dev_alloc(h, p, &p->d_fb, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     if (need_fb && h->precise && (st = dev_alloc(h, p, &p->d_fb64, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     if (h->do_vad && h->vad_cri == VCRI_CEPDIST_FEA && (st = dev_alloc(h, p, &p->d_fea64, (size_t)rows * h->feature_dim))) { ctu_plan_destroy(p); return st; }
@@ -693,6 +727,21 @@ static int launch_frames_w(ctu_handle *h, const FrameParams &P, const ctu_plan *
     static const char *const names[3][3] = {{"k_frames<pcm,spec>", "k_frames<pcm,fb>", "k_frames<pcm,fea>"},
                                             {"k_frames<spec,spec>", "k_frames<spec,fb>", "k_frames<spec,fea>"},
                                             {"k_frames<fb,spec>", "k_frames<fb,fb>", "k_frames<fb,fea>"}};
+    if (h->generic) {
+        if (ft.n16 <= 0) return CTU_OK;
+        int log2m = 0;
+        while ((1 << (log2m + 1)) <= h->cfg.wfft / 2) log2m++;
+        AnyTables tb{h->d_any_tw, h->d_any_ts, h->d_win, h->d_any_fbw, h->d_any_bands, h->cfg.wfft, log2m};
+        size_t bytes = any_smem_floats_per_warp(h->cfg.wfft) * (ANY_THREADS / 32) * sizeof(float);
+        auto kern = k_frames_any<SRC, DST, KIND>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        BatchDesc bd{p->d_pcm_off, p->d_nframes, p->d_row_off, ft.t16};
+        h->lc.begin(names[SRC][DST], s);
+        kern<<<(unsigned)ft.n16, ANY_THREADS, bytes, s>>>(P, bd, tb, pcm, src, dst);
+        h->lc.end(s);
+        CK(cudaGetLastError());
+        return CTU_OK;
+    }
     if constexpr (SRC == SRC_PCM && DST == DST_SPEC) {
         if (ft.n16 <= 0) return CTU_OK;
         Smem2 L = smem2_layout(P.window, P.wshift);
@@ -799,7 +848,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     const bool need_spec = p->d_spec != nullptr;
     FrameParams P = h->fp;
     if (need_spec) {
-        P.out_dim = NBIN; P.out_stride = NBIN;
+        P.out_dim = h->nbins; P.out_stride = h->nbins;
         if ((st = launch_frames_t<SRC_PCM, DST_SPEC, KIND_SPEC>(h, P, p, ft, d_pcm, nullptr, p->d_spec, s))) return st;
     }
     if (nr_on && before) {
@@ -810,7 +859,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
         }
         const uint8_t *fl = (h->nr_mode >= NR_HWSS) ? (h->vad_src == VADSRC_FILE ? d_ext : flags) : nullptr;
         if (h->nr_mode >= NR_HWSS && !fl) return fail(h, CTU_ERR_INPUT, "NR: Unable to open VAD file!\n");
-        if ((st = launch_nr_scan(h->nrp, p->d_nframes, p->d_row_off, r.u0, r.u1, NBIN, p->d_spec, fl, s, &h->lc, h->err))) return st;
+        if ((st = launch_nr_scan(h->nrp, p->d_nframes, p->d_row_off, r.u0, r.u1, h->nbins, p->d_spec, fl, s, &h->lc, h->err))) return st;
         if (h->vad_src == VADSRC_FILE && d_vadnr && h->nr_mode >= NR_HWSS)
             CK(cudaMemcpyAsync(d_vadnr + r.row0, d_ext + r.row0, r.nrows, cudaMemcpyDeviceToDevice, s));
     }
@@ -1099,7 +1148,7 @@ int ctu_debug_spectrum(ctu_plan *p, const int16_t *d_pcm, float *d_spec, void *s
     ctu_handle *h = p->h;
     CK(cudaSetDevice(h->device));
     const FrameTiles ft{p->d_tiles32, p->tile32_off[p->n_utts], p->d_tilesF, p->tileF_off[p->n_utts]};
-    FrameParams P = h->fp; P.out_dim = NBIN; P.out_stride = NBIN;
+    FrameParams P = h->fp; P.out_dim = h->nbins; P.out_stride = h->nbins;
     int st = launch_frames_t<SRC_PCM, DST_SPEC, KIND_SPEC>(h, P, p, ft, d_pcm, nullptr, d_spec, (cudaStream_t)stream);
     if (st) return st;
     CK(cudaStreamSynchronize((cudaStream_t)stream));

@@ -64,6 +64,7 @@ struct VadParams {
     int latency;         // rows between a feature row and the spectrum frame the VAD sees
     int order;           // majority filter length
     int cep_n;           // length of the cepstral vector (lpc: vad_lpc_coefs, fea: feature dim)
+    int nbins;           // spectrum bins per frame (wfft/2 + 1)
     int has_E;           // last column of the feature rows is the _E column
     int fea_skip;        // fea criterion: WRITER column holding the reference's internal element 0 (left out of the
                          // distance, src/vad/vad.cc:262-272), or -1 when that element is not written at all
@@ -583,9 +584,9 @@ __global__ void k_vad_energy(const __grid_constant__ VadParams V, const float *_
     const int64_t r = row0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= row0 + nrows) return;
     const int lane = threadIdx.x & 31;
-    const float *x = spec + r * NBIN;
+    const float *x = spec + r * V.nbins;
     double e = 0;
-    for (int k = lane; k < NBIN; k += 32) { double v = (double)x[k]; e += v * v; }
+    for (int k = lane; k < V.nbins; k += 32) { double v = (double)x[k]; e += v * v; }
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if (lane == 0) cri[r] = V.energy_db ? 10.0 * log10(DBL_MIN + e) : e;
 }

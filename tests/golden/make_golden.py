@@ -96,6 +96,11 @@ CASES = {
     # exponential cepstral mean subtraction (src/fea/post_impl.cc:203-209); the block version crashes the reference
     "mfcc_cms_exp_d_a": (B + MF + ["-fea_Z_exp", "500", "-fea_delta", "d_a", "-format_out", "htk"], "htk", {}),
     "plp_cms_exp": (B + ["-preset", "plpc", "-fea_Z_exp", "2000", "-format_out", "htk"], "htk", {}),
+    # other sampling rates: 256-, 1024- and 2048-point frames (the same samples read at another rate)
+    "mfcc8k_d_a": (["-fs", "8000"] + B[2:] + MF + ["-fea_delta", "d_a", "-format_out", "htk"], "htk", {}),
+    "plp8k": (["-fs", "8000"] + B[2:] + ["-preset", "plpc", "-format_out", "htk"], "htk", {}),
+    "mfcc44k_exten_E": (["-fs", "44100"] + B[2:] + MF + ["-nr_mode", "exten", "-fea_E", "on", "-format_out", "htk"], "htk", {}),
+    "logspec32k_40": (["-fs", "32000"] + B[2:] + MF + ["-fea_kind", "logspec", "-fb_definition", "40filters", "-format_out", "htk"], "htk", {}),
 }
 
 
