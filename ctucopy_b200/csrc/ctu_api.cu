@@ -86,6 +86,7 @@ struct ctu_plan {
     double *d_fb64 = nullptr;            // band values of the precise path
     double *d_fea64 = nullptr;           // fp64 copy of the feature matrix (feature-vector VAD criterion)
     float *d_E = nullptr;                // log energy per frame (-fea_E)
+    double *d_dc1 = nullptr;             // ring means per frame (-remove_dc1)
     double *d_ceps = nullptr;            // Burg cepstra [frames x ncoef]
     double *d_cri = nullptr;             // VAD criterion per frame
     uint8_t *d_flags = nullptr;          // NR-internal detector decisions
@@ -468,16 +469,18 @@ static int resolve_modes(ctu_handle *h) {
     }
     if (c.dither != 0.0)
         return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -dither != 0 draws from glibc rand() in list order (src/io/in.cc:205,454); not reproducible on a parallel device. Use -dither 0.");
-    if (c.remove_dc1) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -remove_dc1 on is not built yet");
-    h->generic = (c.wfft != NFFT);
+    // -remove_dc1 needs per-frame ring offsets: only the general kernel applies them
+    h->generic = (c.wfft != NFFT) || c.remove_dc1;
     h->nbins = c.wfftby2;
+    if (c.remove_dc1 && c.window / c.wshift + 1 > ANY_DC1_MAX) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -remove_dc1 with a window longer than 17 shifts");
+    if (c.remove_dc1 && c.fea_E && c.fea_rawenergy) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -remove_dc1 together with -fea_rawenergy");
     if (h->generic) {
         // other sampling rates / window lengths: the general (slower) frame kernel; the specialised 512-point
         // kernels of the Burg detector, the synthesis and the fp64 path are not generalised yet
         if (c.wfft < 64 || c.wfft > ANY_MAX_NFFT) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: FFT sizes from 64 to 2048 points are built (window of 33..2048 samples)");
-        if (h->signal_out) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: waveform output is built for 512-point frames only (window of 257..512 samples)");
+        if (h->signal_out) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: waveform output is built for 512-point frames without -remove_dc1 only");
         if (h->vad_src == VADSRC_BURG || (h->do_vad && h->vad_cri == VCRI_CEPDIST_LPC))
-            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: the Burg detector is built for 512-point frames only (window of 257..512 samples)");
+            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: the Burg detector is built for 512-point frames without -remove_dc1 only");
     }
     return CTU_OK;
 }
@@ -654,6 +657,7 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     if (need_fb && h->precise && (st = dev_alloc(h, p, &p->d_fb64, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     if (h->do_vad && h->vad_cri == VCRI_CEPDIST_FEA && (st = dev_alloc(h, p, &p->d_fea64, (size_t)rows * h->feature_dim))) { ctu_plan_destroy(p); return st; }
     if (h->energy_mode && (st = dev_alloc(h, p, &p->d_E, (size_t)rows))) { ctu_plan_destroy(p); return st; }
+    if (h->cfg.remove_dc1 && (st = dev_alloc(h, p, &p->d_dc1, (size_t)rows))) { ctu_plan_destroy(p); return st; }
     if (h->fea_kind == FEA_TRAPDCT && (st = dev_alloc(h, p, &p->d_log, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     const bool burg_nr = h->nr_mode >= NR_HWSS && h->vad_src == VADSRC_BURG;
     const bool burg_vad = h->do_vad && h->vad_cri == VCRI_CEPDIST_LPC;
@@ -847,6 +851,14 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     const bool before = h->cfg.nr_when == 0 || h->signal_out;
     const bool need_spec = p->d_spec != nullptr;
     FrameParams P = h->fp;
+    if (p->d_dc1 && r.u1 > r.u0) {
+        h->lc.begin("k_dc1_means", s);
+        k_dc1_means<<<(unsigned)((r.u1 - r.u0 + 3) / 4), 128, 0, s>>>(p->d_nframes, p->d_row_off, p->d_pcm_off, r.u0, r.u1 - r.u0, h->cfg.window,
+                                                                    h->cfg.wshift, d_pcm, p->d_dc1);
+        h->lc.end(s);
+        CK(cudaGetLastError());
+        P.dc1 = p->d_dc1;
+    }
     if (need_spec) {
         P.out_dim = h->nbins; P.out_stride = h->nbins;
         if ((st = launch_frames_t<SRC_PCM, DST_SPEC, KIND_SPEC>(h, P, p, ft, d_pcm, nullptr, p->d_spec, s))) return st;
@@ -875,6 +887,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     if (kind == KIND_TRAPLOG) { fea_dst = p->d_log; od = h->fb.nb; ostride = h->fb.nb; }
     P = h->fp; P.out_dim = od; P.out_stride = ostride;
     P.energy_mode = h->energy_mode; P.energy = p->d_E;
+    P.dc1 = p->d_dc1;
     if (h->precise) {
         // fp64 path (ctu_precise.cuh): band-domain noise reduction / ill-conditioned LPC /
         // features that feed VAD decisions
@@ -896,6 +909,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     } else if (kind == KIND_LPA || kind == KIND_LPC) {
         // band values to HBM (76 B per frame for PLP), then one thread per frame for the recursion
         FrameParams Pf = h->fp; Pf.out_dim = h->fb.nb; Pf.out_stride = h->fb.nb;   // (its energy comes from k_lpc: log R0)
+        Pf.dc1 = p->d_dc1;
         if (need_spec) { if ((st = launch_frames_t<SRC_SPEC, DST_FB, KIND_SPEC>(h, Pf, p, ft, nullptr, p->d_spec, p->d_fb, s))) return st; }
         else if ((st = launch_frames_t<SRC_PCM, DST_FB, KIND_SPEC>(h, Pf, p, ft, d_pcm, nullptr, p->d_fb, s))) return st;
         if ((st = launch_lpc(h, P, kind == KIND_LPC, r.row0, r.nrows, p->d_fb, fea_dst, s))) return st;

@@ -16,6 +16,7 @@ namespace ctu {
 constexpr int ANY_THREADS = 256;              // 8 warps = 8 frames in flight
 constexpr int ANY_TILE = 16;                  // frames per CTA (the 16-frame tile list)
 constexpr int ANY_MAX_NFFT = 2048;
+constexpr int ANY_DC1_MAX = 18;               // frames a sample can be part of (+1), -remove_dc1
 
 struct AnyTables {
     const float2 *tw;        // e^{-2 pi i k / M}, k < M/2           (M = nfft/2)
@@ -27,6 +28,31 @@ struct AnyTables {
 };
 
 __host__ __device__ inline size_t any_smem_floats_per_warp(int nfft) { return (size_t)nfft /* M complex */ + (nfft / 2 + 4) /* bins */ + MAXB + 4; }
+
+// -remove_dc1 (src/io/in.cc:343-350): mean of the ring at frame t, m_t = mean(raw frame t) - sum_d m_{t-d} (w - d s) / w
+// (the overlap with frame t-d has already lost m_{t-d}).  One warp per utterance, frames in order, fp64.
+__global__ void __launch_bounds__(128)
+k_dc1_means(const int *__restrict__ nframes, const int64_t *__restrict__ row_off, const int64_t *__restrict__ pcm_off, int u0, int n_utts,
+            int w, int s, const int16_t *__restrict__ pcm, double *__restrict__ m) {
+    const int u = u0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (u >= u0 + n_utts) return;
+    const int lane = threadIdx.x & 31;
+    const int T = nframes[u];
+    const int16_t *x = pcm + pcm_off[u];
+    double *mu = m + row_off[u];
+    for (int t = 0; t < T; t++) {
+        int acc = 0;
+        for (int i = lane; i < w; i += 32) acc += (int)x[(int64_t)t * s + i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            double v = (double)acc / (double)w;
+            for (int d = 1; d * s < w && d <= t; d++) v -= mu[t - d] * (double)(w - d * s) / (double)w;
+            mu[t] = v;
+        }
+        __syncwarp();
+    }
+}
 
 template <int SRC, int DST, int KIND>
 __global__ void __launch_bounds__(ANY_THREADS)
@@ -52,11 +78,27 @@ k_frames_any(const __grid_constant__ FrameParams P, BatchDesc bd, AnyTables tb, 
             const bool at_start = (t0 + f) == 0;
             float *y = reinterpret_cast<float *>(z);                   // the frame as nfft reals, natural order first
             float sum = 0.f;
+            // -remove_dc1: frame t subtracts the mean of the whole ring from the ring, so a sample that is in frames
+            // t-d .. t has lost m[t-d] + .. + m[t] by the time frame t reads it (m from k_dc1_means)
+            float md[ANY_DC1_MAX];
+            const int nd = P.dc1 ? min(ANY_DC1_MAX, w / s + 1) : 0;
+            for (int d = 0; d < nd; d++) md[d] = (t0 + f - d >= 0) ? (float)P.dc1[row0 + f - d] : 0.f;
+            auto ring_off = [&](int i, int d0) {        // what sample i of the frame has lost, counting frames t-d0, t-d0-1, ...
+                float c = 0.f;
+                for (int d = d0; d < nd; d++) if (i + (d - d0) * s < w) c += md[d];
+                return c;
+            };
             for (int i = lane; i < nfft; i += 32) {
                 float v = 0.f;
                 if (i < w) {
-                    const float xi = (float)x[i];
-                    const float xp = (i == 0 && at_start) ? 0.f : (float)x[i - 1];
+                    float xi = (float)x[i];
+                    float xp = (i == 0 && at_start) ? 0.f : (float)x[i - 1];
+                    if (P.dc1) {
+                        xi -= ring_off(i, 0);
+                        // the sample before the frame was remembered at the end of frame t-1 (src/io/in.cc:384)
+                        if (i > 0) xp -= ring_off(i - 1, 0);
+                        else if (!at_start) xp -= ring_off(s - 1, 1);
+                    }
                     v = tb.win[i] * fmaf(-P.preem, xp, xi);
                 }
                 y[i] = v;

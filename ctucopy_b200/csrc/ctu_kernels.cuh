@@ -83,6 +83,8 @@ struct FrameParams {
     // (BATCH::init_out, src/io/batch.cc:98-118); written per frame into `energy`
     int energy_mode;       // EnergyMode
     float *energy;         // [total frames] log energies (device), nullptr when unused
+    // -remove_dc1 (src/io/in.cc:343-350): per-frame means of the repeatedly de-meaned sample ring, nullptr when off
+    const double *dc1;
 };
 enum EnergyMode {
     EN_NONE = 0,
