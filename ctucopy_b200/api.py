@@ -127,6 +127,7 @@ def lib() -> C.CDLL:
     L.ctu_cmvn_dim.argtypes = [vp]; L.ctu_cmvn_dim.restype = C.c_int
     L.ctu_plan_colsums.argtypes = [vp, vp, vp]; L.ctu_plan_colsums.restype = C.c_int
     L.ctu_plan_normalise.argtypes = [vp, vp, vp]; L.ctu_plan_normalise.restype = C.c_int
+    L.ctu_set_rand_offset.argtypes = [vp, C.c_uint64]; L.ctu_set_rand_offset.restype = C.c_int
     L.ctu_host_alloc.argtypes = [P(vp), C.c_uint64]; L.ctu_host_alloc.restype = C.c_int
     L.ctu_host_free.argtypes = [vp]; L.ctu_host_free.restype = None
     _lib = L

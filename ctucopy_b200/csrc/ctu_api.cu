@@ -61,6 +61,7 @@ struct ctu_handle {
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     // device blocks of destroyed plans, kept for the next plan: a list is processed as a sequence of plans of
     // similar size, and cudaMalloc / cudaFree of gigabytes cost more than the kernels that use them
+    uint64_t rand_pos = 0;               // -dither: values of the process-wide rand() stream drawn by earlier plans
     struct PoolBlock { void *p; size_t bytes; bool used; };
     std::vector<PoolBlock> pool;
 };
@@ -87,6 +88,9 @@ struct ctu_plan {
     double *d_fea64 = nullptr;           // fp64 copy of the feature matrix (feature-vector VAD criterion)
     float *d_E = nullptr;                // log energy per frame (-fea_E)
     double *d_dc1 = nullptr;             // ring means per frame (-remove_dc1)
+    float *d_dither = nullptr;           // dither noise per sample (-dither), generated on first use
+    uint64_t rand_base = 0;
+    bool dither_ready = false;
     double *d_ceps = nullptr;            // Burg cepstra [frames x ncoef]
     double *d_cri = nullptr;             // VAD criterion per frame
     uint8_t *d_flags = nullptr;          // NR-internal detector decisions
@@ -467,10 +471,12 @@ static int resolve_modes(ctu_handle *h) {
             return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_Z_exp is built for cepstral features (dctc, lpc)");
         if (h->do_vad) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_Z_exp together with the VAD module");
     }
-    if (c.dither != 0.0)
-        return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -dither != 0 draws from glibc rand() in list order (src/io/in.cc:205,454); not reproducible on a parallel device. Use -dither 0.");
     // -remove_dc1 needs per-frame ring offsets: only the general kernel applies them
-    h->generic = (c.wfft != NFFT) || c.remove_dc1;
+    // dither (src/io/in.cc:452-455): glibc's rand() stream restated on the host, one value per loaded sample in list
+    // order; applied by the general kernel
+    h->generic = (c.wfft != NFFT) || c.remove_dc1 || c.dither != 0.0;
+    if (c.dither != 0.0 && (c.remove_dc1 || (c.fea_E && c.fea_rawenergy)))
+        return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -dither together with -remove_dc1 or -fea_rawenergy");
     h->nbins = c.wfftby2;
     if (c.remove_dc1 && c.window / c.wshift + 1 > ANY_DC1_MAX) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -remove_dc1 with a window longer than 17 shifts");
     if (c.remove_dc1 && c.fea_E && c.fea_rawenergy) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -remove_dc1 together with -fea_rawenergy");
@@ -478,9 +484,9 @@ static int resolve_modes(ctu_handle *h) {
         // other sampling rates / window lengths: the general (slower) frame kernel; the specialised 512-point
         // kernels of the Burg detector, the synthesis and the fp64 path are not generalised yet
         if (c.wfft < 64 || c.wfft > ANY_MAX_NFFT) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: FFT sizes from 64 to 2048 points are built (window of 33..2048 samples)");
-        if (h->signal_out) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: waveform output is built for 512-point frames without -remove_dc1 only");
+        if (h->signal_out) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: waveform output is built for 512-point frames without -remove_dc1 / -dither only");
         if (h->vad_src == VADSRC_BURG || (h->do_vad && h->vad_cri == VCRI_CEPDIST_LPC))
-            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: the Burg detector is built for 512-point frames without -remove_dc1 only");
+            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: the Burg detector is built for 512-point frames without -remove_dc1 / -dither only");
     }
     return CTU_OK;
 }
@@ -622,6 +628,10 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
             if (T < mw + 2) { delete p; return fail(h, CTU_ERR_UNSUPPORTED, "CTU: utterance shorter than delta window + 2 frames"); }
         }
     }
+    if (h->cfg.dither != 0.0) {
+        p->rand_base = h->rand_pos;
+        h->rand_pos += (uint64_t)rows * (uint64_t)s + (uint64_t)n * (uint64_t)(w - s);     // one rand() per LOADED sample
+    }
     p->row_off[n] = rows; p->osamp_off[n] = osamp; p->tile32_off[n] = t32; p->tile64_off[n] = t64; p->tileS_off[n] = tS; p->tileF_off[n] = tF;
     p->total_frames = rows; p->total_osamp = osamp; p->total_samples = off[n] - off[0];
     int st = 0;
@@ -658,6 +668,7 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     if (h->do_vad && h->vad_cri == VCRI_CEPDIST_FEA && (st = dev_alloc(h, p, &p->d_fea64, (size_t)rows * h->feature_dim))) { ctu_plan_destroy(p); return st; }
     if (h->energy_mode && (st = dev_alloc(h, p, &p->d_E, (size_t)rows))) { ctu_plan_destroy(p); return st; }
     if (h->cfg.remove_dc1 && (st = dev_alloc(h, p, &p->d_dc1, (size_t)rows))) { ctu_plan_destroy(p); return st; }
+    if (h->cfg.dither != 0.0 && (st = dev_alloc(h, p, &p->d_dither, (size_t)p->total_samples + 8))) { ctu_plan_destroy(p); return st; }
     if (h->fea_kind == FEA_TRAPDCT && (st = dev_alloc(h, p, &p->d_log, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     const bool burg_nr = h->nr_mode >= NR_HWSS && h->vad_src == VADSRC_BURG;
     const bool burg_vad = h->do_vad && h->vad_cri == VCRI_CEPDIST_LPC;
@@ -833,6 +844,48 @@ static int kind_of(const ctu_handle *h) {
     return KIND_SPEC;
 }
 
+// glibc's rand() after srand(1) (random_r TYPE_3: r[i] = r[i-3] + r[i-31] mod 2^32, output r[i] >> 1, 310 values
+// discarded after seeding), which the reference draws once per loaded sample (src/io/in.cc:205, 452-455)
+struct GlibcRand {
+    uint32_t r[34];
+    int i = 0;
+    GlibcRand() {
+        int64_t v = 1;
+        uint32_t init[34];
+        init[0] = 1;
+        for (int k = 1; k < 31; k++) { v = (16807 * (int64_t)init[k - 1]) % 2147483647; if (v < 0) v += 2147483647; init[k] = (uint32_t)v; }
+        for (int k = 31; k < 34; k++) init[k] = init[k - 31];
+        for (int k = 0; k < 34; k++) r[k] = init[k];
+        i = 0;                                   // r[(i + k) % 34] holds element (count + k) of the sequence, k < 34
+        for (int k = 0; k < 310; k++) step();
+    }
+    inline uint32_t step() {                      // element n = element n-31 + element n-3; the window holds n-34 .. n-1
+        const uint32_t v = r[(i + 3) % 34] + r[(i + 31) % 34];
+        r[i] = v;
+        i = (i + 1) % 34;
+        return v;
+    }
+    inline uint32_t next() { return step() >> 1; }
+};
+
+static int prepare_dither(ctu_plan *p) {
+    ctu_handle *h = p->h;
+    if (!p->d_dither || p->dither_ready) return CTU_OK;
+    const int w = h->cfg.window, s = h->cfg.wshift;
+    std::vector<float> noise((size_t)p->total_samples + 8, 0.f);
+    GlibcRand g;
+    for (uint64_t k = 0; k < p->rand_base; k++) g.step();
+    const double d = h->cfg.dither;
+    for (int u = 0; u < p->n_utts; u++) {
+        const int64_t o = p->offsets[u] - p->offsets[0];
+        const int64_t nloaded = (int64_t)p->nframes[u] * s + (w - s);
+        for (int64_t k = 0; k < nloaded; k++) noise[(size_t)(o + k)] = (float)((2. * (double)g.next() / 2147483647. - 1.) * d);
+    }
+    CK(cudaMemcpy(p->d_dither, noise.data(), noise.size() * sizeof(float), cudaMemcpyHostToDevice));
+    p->dither_ready = true;
+    return CTU_OK;
+}
+
 // Runs utterances [u0,u1) of the plan on stream s.  All pointers are whole-batch device
 // buffers (rows / samples are addressed through the plan's global offsets).
 static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const uint8_t *d_ext, float *d_fea, int16_t *d_wave,
@@ -859,6 +912,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
         CK(cudaGetLastError());
         P.dc1 = p->d_dc1;
     }
+    P.dither = p->d_dither ? p->d_dither - p->offsets[0] : nullptr;
     if (need_spec) {
         P.out_dim = h->nbins; P.out_stride = h->nbins;
         if ((st = launch_frames_t<SRC_PCM, DST_SPEC, KIND_SPEC>(h, P, p, ft, d_pcm, nullptr, p->d_spec, s))) return st;
@@ -888,6 +942,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     P = h->fp; P.out_dim = od; P.out_stride = ostride;
     P.energy_mode = h->energy_mode; P.energy = p->d_E;
     P.dc1 = p->d_dc1;
+    P.dither = p->d_dither ? p->d_dither - p->offsets[0] : nullptr;
     if (h->precise) {
         // fp64 path (ctu_precise.cuh): band-domain noise reduction / ill-conditioned LPC /
         // features that feed VAD decisions
@@ -909,7 +964,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     } else if (kind == KIND_LPA || kind == KIND_LPC) {
         // band values to HBM (76 B per frame for PLP), then one thread per frame for the recursion
         FrameParams Pf = h->fp; Pf.out_dim = h->fb.nb; Pf.out_stride = h->fb.nb;   // (its energy comes from k_lpc: log R0)
-        Pf.dc1 = p->d_dc1;
+        Pf.dc1 = p->d_dc1; Pf.dither = P.dither;
         if (need_spec) { if ((st = launch_frames_t<SRC_SPEC, DST_FB, KIND_SPEC>(h, Pf, p, ft, nullptr, p->d_spec, p->d_fb, s))) return st; }
         else if ((st = launch_frames_t<SRC_PCM, DST_FB, KIND_SPEC>(h, Pf, p, ft, d_pcm, nullptr, p->d_fb, s))) return st;
         if ((st = launch_lpc(h, P, kind == KIND_LPC, r.row0, r.nrows, p->d_fb, fea_dst, s))) return st;
@@ -1005,6 +1060,7 @@ int ctu_plan_run_device(ctu_plan *p, const int16_t *d_pcm, const uint8_t *d_ext_
     if (!h->signal_out && !d_features) return fail(h, CTU_ERR_CAPACITY, "CTU: features buffer is NULL");
     if (h->signal_out && !d_waveform) return fail(h, CTU_ERR_CAPACITY, "CTU: waveform buffer is NULL");
     cudaStream_t s = (cudaStream_t)stream;
+    { int st0 = prepare_dither(p); if (st0) return st0; }
     Range r = make_range(p, 0, p->n_utts);
     if (h->signal_out) CK(cudaMemsetAsync(d_waveform, 0, (size_t)p->total_osamp * sizeof(int16_t), s));
     int st = run_range(p, r, d_pcm, d_ext_vad, d_features, d_waveform, d_vad_nr, d_vad_out, s);
@@ -1020,6 +1076,7 @@ static int run_host_impl(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad
     if (!keep && !h->signal_out && !features) return fail(h, CTU_ERR_CAPACITY, "CTU: features buffer is NULL");
     if (!keep && h->signal_out && !waveform) return fail(h, CTU_ERR_CAPACITY, "CTU: waveform buffer is NULL");
     int st;
+    if ((st = prepare_dither(p))) return st;
     if (!p->host_bufs) {
         if ((st = dev_alloc(h, p, &p->d_pcm, (size_t)p->total_samples + 8))) return st;
         if (!h->signal_out && (st = dev_alloc(h, p, &p->d_fea, (size_t)p->total_frames * h->feature_dim))) return st;
@@ -1146,6 +1203,12 @@ int ctu_run(ctu_handle *h, const int16_t *pcm, const int64_t *off, int32_t n, co
     if (!st && rows_per_utt) ctu_plan_rows_per_utt(p, rows_per_utt);
     ctu_plan_destroy(p);
     return st;
+}
+
+int ctu_set_rand_offset(ctu_handle *h, uint64_t drawn) {
+    if (!h) return CTU_ERR_CONFIG;
+    h->rand_pos = drawn;
+    return CTU_OK;
 }
 
 int ctu_host_alloc(void **ptr, uint64_t bytes) {

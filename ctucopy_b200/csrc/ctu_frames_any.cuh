@@ -75,6 +75,7 @@ k_frames_any(const __grid_constant__ FrameParams P, BatchDesc bd, AnyTables tb, 
         // ---- A: frame -> spectrum row ------------------------------------------------------------
         if (SRC == SRC_PCM) {
             const int16_t *x = pcm + bd.pcm_off[u] + (int64_t)(t0 + f) * s;
+            const float *dn = P.dither ? P.dither + bd.pcm_off[u] + (int64_t)(t0 + f) * s : nullptr;
             const bool at_start = (t0 + f) == 0;
             float *y = reinterpret_cast<float *>(z);                   // the frame as nfft reals, natural order first
             float sum = 0.f;
@@ -93,6 +94,7 @@ k_frames_any(const __grid_constant__ FrameParams P, BatchDesc bd, AnyTables tb, 
                 if (i < w) {
                     float xi = (float)x[i];
                     float xp = (i == 0 && at_start) ? 0.f : (float)x[i - 1];
+                    if (dn) { xi += dn[i]; if (!(i == 0 && at_start)) xp += dn[i - 1]; }
                     if (P.dc1) {
                         xi -= ring_off(i, 0);
                         // the sample before the frame was remembered at the end of frame t-1 (src/io/in.cc:384)

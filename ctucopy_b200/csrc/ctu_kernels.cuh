@@ -85,6 +85,8 @@ struct FrameParams {
     float *energy;         // [total frames] log energies (device), nullptr when unused
     // -remove_dc1 (src/io/in.cc:343-350): per-frame means of the repeatedly de-meaned sample ring, nullptr when off
     const double *dc1;
+    // -dither: (2*rand()/RAND_MAX - 1)*dither per loaded sample, same indexing as the PCM buffer, nullptr when off
+    const float *dither;
 };
 enum EnergyMode {
     EN_NONE = 0,

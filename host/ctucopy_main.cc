@@ -454,7 +454,7 @@ struct Batch {
 };
 
 void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<ListEntry> &list, size_t r0, size_t r1, int device,
-                   const std::vector<unsigned char> &extvad, size_t frame0) {
+                   const std::vector<unsigned char> &extvad, size_t frame0, uint64_t rand0 = 0) {
     const bool do_vad = std::strcmp(cfg.vad_apply_mode, "none") || std::strcmp(cfg.vad_out_mode, "none");
     const bool vad_file = std::strcmp(cfg.vad_out_mode, "none") != 0;
     const bool use_ext = !std::strcmp(cfg.vadmode, "file");
@@ -462,6 +462,7 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
     ctu_handle *h = nullptr;
     if (ctu_create(&cfg, device, &h)) die(ctu_last_error(nullptr));
     tmark("ctu_create (CUDA init)", t_start);
+    ctu_set_rand_offset(h, rand0);            // -dither: rand() values the list lines before this range have drawn
     const int dim = ctu_feature_dim(h);
     const bool sig = ctu_is_signal_output(h);
     const std::string fo(cfg.format_out);
@@ -791,10 +792,12 @@ int run(int argc, char **argv) {
     // ---- utterance sharding: contiguous list ranges balanced by sample count, no exchange between shards
     std::vector<int64_t> samples(list.size());
     std::vector<size_t> frames_before(list.size() + 1, 0);
+    std::vector<uint64_t> drawn_before(list.size() + 1, 0);      // -dither: one rand() per loaded sample (src/io/in.cc:452-455)
     for (size_t i = 0; i < list.size(); i++) {
         samples[i] = count_samples(ho, list[i].in);
         int64_t T = samples[i] < cfg.window - cfg.wshift ? 0 : (samples[i] - (cfg.window - cfg.wshift)) / cfg.wshift;
         frames_before[i + 1] = frames_before[i] + (size_t)T;
+        drawn_before[i + 1] = drawn_before[i] + (uint64_t)T * cfg.wshift + (cfg.window - cfg.wshift);
     }
     const std::vector<size_t> cut = partition(samples, nparts);
     auto shard_opts = [&](int r) {
@@ -805,14 +808,14 @@ int run(int argc, char **argv) {
     };
     if (ho.gpus <= 1) {                          // one process per GPU (e.g. under torchrun): this is shard r
         process_range(shard_opts(ho.shard_r), cfg, list, cut[ho.shard_r], cut[ho.shard_r + 1], ho.device < 0 ? ho.shard_r : ho.device, extvad,
-                      frames_before[cut[ho.shard_r]]);
+                      frames_before[cut[ho.shard_r]], drawn_before[cut[ho.shard_r]]);
         return 0;
     }
     std::vector<std::string> errs(nparts);
     std::vector<std::thread> th;
     for (int r = 0; r < nparts; r++)
         th.emplace_back([&, r]() {
-            try { process_range(shard_opts(r), cfg, list, cut[r], cut[r + 1], r, extvad, frames_before[cut[r]]); }
+            try { process_range(shard_opts(r), cfg, list, cut[r], cut[r + 1], r, extvad, frames_before[cut[r]], drawn_before[cut[r]]); }
             catch (const std::exception &e) { errs[r] = e.what(); if (errs[r].empty()) errs[r] = "unknown error"; }
         });
     for (auto &t : th) t.join();

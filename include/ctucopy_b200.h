@@ -48,7 +48,7 @@ typedef struct ctu_config {
     char    format_out[CTU_STR];     /* htk|pfile|ark -> features; raw|wave -> enhanced waveform  */
     int32_t fs;
     float   preem;                   /* stored as float like the reference (src/io/opts.h:47)     */
-    double  dither;                  /* must be 0: see DESIGN.md                                  */
+    double  dither;                  /* amplitude of the uniform dither (code default 0, src/io/opts.cc:38) */
     int32_t remove_dc, remove_dc1;
     double  window_ms, wshift_ms;
     /* filter bank */
@@ -188,6 +188,12 @@ int ctu_plan_normalise(ctu_plan *p, const double *mean, const double *scale);
 int ctu_run(ctu_handle *h, const int16_t *pcm, const int64_t *utt_offsets, int32_t n_utts, const uint8_t *ext_vad,
             float *features, int64_t features_capacity_rows, int16_t *waveform, int64_t waveform_capacity,
             uint8_t *vad_nr, uint8_t *vad_out, int64_t *frames_per_utt, int64_t *rows_per_utt);
+
+/* -dither draws one value of the process-wide glibc rand() stream (srand(1), src/io/in.cc:205, 452-455) per loaded
+ * sample, in list order.  A handle continues the stream from plan to plan like the reference process does from file to
+ * file; a shard that starts in the middle of a list sets how many values the files before it have drawn
+ * ((window - wshift) + frames * wshift per file).                                                                  */
+int ctu_set_rand_offset(ctu_handle *h, uint64_t values_drawn);
 
 /* Page-locked host memory for the buffers handed to ctu_plan_run_host / ctu_run: pageable memory
  * makes every chunk copy synchronous and several times slower.  (What rawIN's fread buffer and the

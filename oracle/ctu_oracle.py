@@ -349,13 +349,41 @@ class FrontEnd:
     spec: np.ndarray                  # complex [T, wfftby2] raw DFT (for tests)
 
 
-def front_end(pcm: np.ndarray, o: Opts) -> FrontEnd:
-    """rawIN::get_frame, src/io/in.cc:305-419 (dither == 0 only; dither draws from glibc
-    rand() in list order, src/io/in.cc:205,454, which no sharded run can reproduce)."""
-    assert o.dither == 0.0, "oracle restates the dither-free path only"
+def glibc_rand(n: int, skip: int = 0, seed: int = 1) -> np.ndarray:
+    """The first skip+n values of glibc's rand() after srand(seed), values [skip:] (TYPE_3 additive feedback
+    generator of random_r: r[i] = r[i-3] + r[i-31] mod 2^32, output r[i] >> 1, 310 values discarded after
+    seeding).  The reference seeds it once per process (src/io/in.cc:205) and draws one value per loaded
+    sample (src/io/in.cc:452-455); tests/test_oracle_vs_golden.py checks this against libc itself."""
+    tot = skip + n
+    r = np.zeros(tot + 344, dtype=np.uint64)
+    r[0] = seed
+    for i in range(1, 31):
+        r[i] = (16807 * int(r[i - 1])) % 2147483647
+    for i in range(31, 34):
+        r[i] = r[i - 31]
+    rl = [int(v) for v in r[:34]] + [0] * (tot + 310)
+    for i in range(34, tot + 344):
+        rl[i] = (rl[i - 31] + rl[i - 3]) & 0xFFFFFFFF
+    return np.array([v >> 1 for v in rl[344 + skip: 344 + tot]], dtype=np.int64)
+
+
+def dither_noise(nloaded: int, o: Opts, rand_offset: int = 0) -> np.ndarray:
+    """(2*rand()/RAND_MAX - 1) * dither for the nloaded samples the reference reads of one file
+    (src/io/in.cc:452-455); rand_offset = values the process has drawn for earlier files."""
+    rv = glibc_rand(nloaded, rand_offset).astype(np.float64)
+    return (2.0 * rv / 2147483647.0 - 1.0) * o.dither
+
+
+def front_end(pcm: np.ndarray, o: Opts, rand_offset: int = 0) -> FrontEnd:
+    """rawIN::get_frame, src/io/in.cc:305-419.  Dither draws from glibc rand() in list order
+    (src/io/in.cc:205,454): rand_offset places this file in the process-wide stream."""
     w, s, nfft = o.window, o.wshift, o.wfft
     x = np.asarray(pcm, dtype=np.float64)
     T = num_frames(len(x), o)
+    if o.dither != 0.0:
+        nloaded = (w - s) + T * s                      # samples the reference actually loads (one rand() each)
+        x = x.copy()
+        x[:nloaded] += dither_noise(nloaded, o, rand_offset)
     W = hamming(w)
     alpha = float(np.float32(o.preem))
     Xabs = np.empty((T, o.wfftby2))
@@ -1410,9 +1438,9 @@ def energy_column(o: Opts, fe: "FrontEnd", Xs: np.ndarray, Y: np.ndarray, kind: 
     return np.asarray(E, dtype=np.float64)[idx]
 
 
-def run_pipeline(pcm: np.ndarray, o: Opts, ext_vad: Optional[np.ndarray] = None) -> Result:
+def run_pipeline(pcm: np.ndarray, o: Opts, ext_vad: Optional[np.ndarray] = None, rand_offset: int = 0) -> Result:
     """One utterance through the chain BATCH builds (src/io/batch.cc:24-69, 205-296)."""
-    fe = front_end(pcm, o)
+    fe = front_end(pcm, o, rand_offset)
     T = fe.Xabs.shape[0]
     signal_out = o.format_out in ("raw", "wave")
     if signal_out:

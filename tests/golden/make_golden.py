@@ -100,6 +100,9 @@ CASES = {
     "mfcc8k_d_a": (["-fs", "8000"] + B[2:] + MF + ["-fea_delta", "d_a", "-format_out", "htk"], "htk", {}),
     "plp8k": (["-fs", "8000"] + B[2:] + ["-preset", "plpc", "-format_out", "htk"], "htk", {}),
     "mfcc44k_exten_E": (["-fs", "44100"] + B[2:] + MF + ["-nr_mode", "exten", "-fea_E", "on", "-format_out", "htk"], "htk", {}),
+    # -dither: one glibc rand() per loaded sample (src/io/in.cc:452-455); every golden process starts its stream at srand(1)
+    "mfcc_dither1_d_a": (["-fs", "16000", "-format_in", "raw", "-dither", "1.0"] + MF + ["-fea_delta", "d_a", "-format_out", "htk"], "htk", {}),
+    "plp_dither4": (["-fs", "16000", "-format_in", "raw", "-dither", "4"] + ["-preset", "plpc", "-format_out", "htk"], "htk", {}),
     # -remove_dc1: the sample ring is de-meaned in place by every frame (src/io/in.cc:343-350)
     "mfcc_dc1": (B + MF + ["-remove_dc1", "on", "-format_out", "htk"], "htk", {}),
     "mfcc_dc1_w32s8": (B + ["-preset", "mfcc", "-preem", "0", "-remove_dc1", "on", "-remove_dc", "off", "-w", "32", "-s", "8", "-nr_mode", "exten",

@@ -66,6 +66,10 @@ def test_cuda_matches_reference_golden(name):
     ev = [c.extvad[i] for i in idx] if c.extvad[idx[0]] is not None else None
     res = cb.extract(args, [ins[i] for i in idx], ev)
     for j, i in enumerate(idx):
+        if o.dither != 0.0:
+            # the goldens are one reference process per utterance: every file starts the rand() stream afresh,
+            # while a batch continues it from utterance to utterance (test_dither_stream_continues_through_a_list)
+            res, j = cb.extract(args, [ins[i]]), 0
         want = c.payload(i)
         if c.kind in ("raw", "wave"):
             got = res.utt_waveform(j)
@@ -244,3 +248,17 @@ def test_randomised_option_sweep_matches_oracle():
                 r0 = int(res.row_offsets[i])
                 assert np.array_equal(res.vad_nr[r0: r0 + ref.nframes].astype(bool), ref.vad_nr), " ".join(args)
         done += 1
+
+
+def test_dither_stream_continues_through_a_list():
+    """-dither: the second and third utterances of a batch take their noise from where the first one stopped in the
+    process-wide rand() stream, exactly like the files of a reference list (src/io/in.cc:205, 452-455)."""
+    args = ["-fs", "16000", "-format_in", "raw", "-dither", "1.0", "-preset", "mfcc", "-preem", "0.97", "-fea_delta", "d_a", "-format_out", "htk"]
+    o = co.parse_args(args)
+    utts = [PARITY_SET[0], PARITY_SET[1], PARITY_SET[2]]
+    res = cb.extract(args, utts)
+    off = 0
+    for j, u in enumerate(utts):
+        ref = co.run_pipeline(u, o, rand_offset=off)
+        off += (o.window - o.wshift) + ref.nframes * o.wshift
+        check_features("dither", j, res.utt_features(j), ref.features, "dctc")

@@ -109,3 +109,17 @@ def test_oracle_cmvn_matches_reference_binary(name):
             assert np.array_equal(feats[j], rr.parse_htk(outs[i])[1]), (name, i)
     else:
         assert not outs           # statistics only: no feature files
+
+
+def test_glibc_rand_restatement_matches_libc():
+    """-dither draws from glibc's rand() after srand(1) (src/io/in.cc:205, 454); the oracle (and the library) restate
+    the generator, checked here against libc itself, including the skip used for later files of a list."""
+    import ctypes
+    try:
+        libc = ctypes.CDLL("libc.so.6")
+    except OSError:
+        pytest.skip("no glibc")
+    libc.srand(1)
+    ref = np.array([libc.rand() for _ in range(5000)], dtype=np.int64)
+    assert np.array_equal(co.glibc_rand(5000), ref)
+    assert np.array_equal(co.glibc_rand(1000, skip=4000), ref[4000:])
