@@ -459,17 +459,12 @@ __device__ __forceinline__ void finish_pcm(int16_t *raw, float *__restrict__ sD,
     __syncthreads();
     const int16_t *x = raw + phase;                       // x[k]: element k
     const int nsamp = n - 1;
-    for (int i0 = threadIdx.x * 8; i0 < nsamp; i0 += NT * 8) {
-        float prev = s16_to_f32((int)x[i0]);
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const float xi = (i0 + j < nsamp) ? s16_to_f32((int)x[i0 + j + 1]) : 0.f;
-            v[j] = fmaf(-alpha, prev, xi);
-            prev = xi;
-        }
-        *reinterpret_cast<float4 *>(sD + i0) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4 *>(sD + i0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    // consecutive threads take consecutive samples: 2-byte reads and 4-byte writes at unit stride are free of bank
+    // conflicts (the 8-samples-per-thread layout cost four wavefronts per load: ncu, profiles/)
+    for (int i = threadIdx.x; i < nsamp; i += NT) {
+        const float prev = s16_to_f32((int)x[i]);
+        const float xi = s16_to_f32((int)x[i + 1]);
+        sD[i] = fmaf(-alpha, prev, xi);
     }
 }
 
