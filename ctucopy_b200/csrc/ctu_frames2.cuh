@@ -42,7 +42,7 @@ __host__ __device__ inline Smem2 smem2_layout(int window, int wshift) {
 }
 
 template <int WT>
-__global__ void __launch_bounds__(F2_THREADS, 5)
+__global__ void __launch_bounds__(F2_THREADS, 4)
 k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, const int16_t *__restrict__ pcm, float *__restrict__ dst,
           int ntiles) {
     extern __shared__ __align__(16) float sm[];
@@ -67,6 +67,16 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, con
     const unsigned hm = 0xffffu << (tid & 16);                // the two groups of a warp run independently
     cpx<float> *xch = reinterpret_cast<cpx<float> *>(sm + L.oX + grp * F2_ROWF);
     const float inv_w = 1.0f / (float)w;
+    // a thread windows the same 2 x 16 sample positions of every frame it ever sees: its window values live in
+    // registers for the whole (persistent) kernel instead of being re-read from shared memory per frame
+    __syncthreads();
+    float wr[32];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) {
+        const int i0 = 32 * n1 + 2 * c;
+        wr[2 * n1] = (i0 < w) ? sW[i0] : 0.f;
+        wr[2 * n1 + 1] = (i0 + 1 < w) ? sW[i0 + 1] : 0.f;
+    }
 #pragma unroll 1
     for (; tile < ntiles; tile += gridDim.x) {
     const int next = tile + gridDim.x;
@@ -85,8 +95,8 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, con
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) {
             const int i0 = 32 * n1 + 2 * c;
-            float y0 = (i0 < w) ? sW[i0] * d[i0] : 0.f;
-            float y1 = (i0 + 1 < w) ? sW[i0 + 1] * d[i0 + 1] : 0.f;
+            float y0 = (i0 < w) ? wr[2 * n1] * d[i0] : 0.f;
+            float y1 = (i0 + 1 < w) ? wr[2 * n1 + 1] * d[i0 + 1] : 0.f;
             a[n1] = mk<float>(y0, y1);
             sum += y0 + y1;
         }
