@@ -15,7 +15,9 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 
 def label(kernel):
-    m = re.match(r"void k_frames2?<(\d+), (\d+)", kernel)
+    if "k_frames2<" in kernel:
+        return "k_frames<pcm,spec>"
+    m = re.match(r"void k_frames<(\d+), (\d+)", kernel)
     if m:
         return "k_frames<%s,%s>" % (SRC[int(m.group(1))], DST[int(m.group(2))])
     m = re.match(r"void (k_[a-z_]+?)(22|64)?<|void (k_[a-z_]+)\(|(k_[a-z_]+)\(", kernel)
