@@ -528,41 +528,62 @@ static inline int launch_burg(const BurgParams &B, int src_mode, const BatchDesc
 }
 
 // ------------------------------------------------------------------------------------------
-// K5: cepstral detector, one thread per utterance
+// K5: cepstral detector (src/vdet/CepstralDet.h:134-194), sequential per utterance
 // ------------------------------------------------------------------------------------------
-__global__ void k_cepdet(const __grid_constant__ BurgParams B, const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int u0,
-                         int n_utts, const double *__restrict__ ceps, uint8_t *__restrict__ flags) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per utterance: the warp stages blocks of 32 frames of cepstra in shared memory (coalesced, all loads
+// in flight at once) and lane 0 runs the sequential state machine out of shared memory.  With one thread per
+// utterance every frame waited for its own HBM / L2 round trip (2 ms per launch whatever the batch size, which
+// dominated the chunked host path).
+constexpr int CEPDET_WARPS = 4;
+__global__ void __launch_bounds__(32 * CEPDET_WARPS)
+k_cepdet(const __grid_constant__ BurgParams B, const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int u0,
+         int n_utts, const double *__restrict__ ceps, uint8_t *__restrict__ flags) {
+    __shared__ double stage[CEPDET_WARPS][32 * BURG_MAXC];
+    __shared__ uint8_t sflag[CEPDET_WARPS][32];
+    const int wv = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * CEPDET_WARPS + wv;
     if (i >= n_utts) return;
     const int u = u0 + i;
     const int T = nframes[u];
     const int nc = B.ncoef_nr;
-    const double *cp = ceps + row_off[u] * BURG_MAXC;
+    const double *cp0 = ceps + row_off[u] * BURG_MAXC;
     uint8_t *fl = flags + row_off[u];
     double c0[BURG_MAXC];
     double dMean = 0, dMean2 = 0, dVar = 0, thr = 0;
-    for (int t = 0; t < T; t++, cp += BURG_MAXC) {
-        bool res = false;
-        if (t == 0) {
-            for (int k = 0; k < nc; k++) c0[k] = cp[k];
-        } else {
-            if (t == 1) for (int k = 0; k < nc; k++) c0[k] = (c0[k] + cp[k]) / 2.0;
-            double sum = 0;
-            for (int k = 1; k < nc; k++) { double d = cp[k] - c0[k]; sum += d * d; }
-            const double dist = 4.3429 * sqrt(2 * sum);
-            if (t == 1) { dMean = dist; dMean2 = dist * dist; thr = dMean; }
-            else {
-                res = (t > B.ninit) && (dist >= thr);
-                if (!res) {
-                    for (int k = 0; k < nc; k++) c0[k] = B.P * c0[k] + (1 - B.P) * cp[k];
-                    dMean = B.Q * dMean + (1 - B.Q) * dist;
-                    dMean2 = B.Q * dMean2 + (1 - B.Q) * dist * dist;
-                    dVar = dMean2 - dMean * dMean;
-                    thr = dMean + 2.0 * sqrt(dVar);
+    for (int tb = 0; tb < T; tb += 32) {
+        const int nb = min(32, T - tb);
+        for (int k = lane; k < nb * BURG_MAXC; k += 32) stage[wv][k] = cp0[(int64_t)tb * BURG_MAXC + k];
+        __syncwarp();
+        if (lane == 0) {
+            for (int j = 0; j < nb; j++) {
+                const int t = tb + j;
+                const double *cp = stage[wv] + j * BURG_MAXC;
+                bool res = false;
+                if (t == 0) {
+                    for (int k = 0; k < nc; k++) c0[k] = cp[k];
+                } else {
+                    if (t == 1) for (int k = 0; k < nc; k++) c0[k] = (c0[k] + cp[k]) / 2.0;
+                    double sum = 0;
+                    for (int k = 1; k < nc; k++) { double d = cp[k] - c0[k]; sum += d * d; }
+                    const double dist = 4.3429 * sqrt(2 * sum);
+                    if (t == 1) { dMean = dist; dMean2 = dist * dist; thr = dMean; }
+                    else {
+                        res = (t > B.ninit) && (dist >= thr);
+                        if (!res) {
+                            for (int k = 0; k < nc; k++) c0[k] = B.P * c0[k] + (1 - B.P) * cp[k];
+                            dMean = B.Q * dMean + (1 - B.Q) * dist;
+                            dMean2 = B.Q * dMean2 + (1 - B.Q) * dist * dist;
+                            dVar = dMean2 - dMean * dMean;
+                            thr = dMean + 2.0 * sqrt(dVar);
+                        }
+                    }
                 }
+                sflag[wv][j] = res ? 1 : 0;
             }
         }
-        fl[t] = res ? 1 : 0;
+        __syncwarp();
+        if (lane < nb) fl[tb + lane] = sflag[wv][lane];
+        __syncwarp();
     }
 }
 
@@ -571,7 +592,7 @@ static inline int launch_cepdet(const BurgParams &B, const int *d_nframes, const
     int n = u1 - u0;
     if (n <= 0) return CTU_OK;
     lc->begin("k_cepdet", s);
-    k_cepdet<<<(n + 63) / 64, 64, 0, s>>>(B, d_nframes, d_row_off, u0, n, ceps, flags);
+    k_cepdet<<<(n + CEPDET_WARPS - 1) / CEPDET_WARPS, 32 * CEPDET_WARPS, 0, s>>>(B, d_nframes, d_row_off, u0, n, ceps, flags);
     lc->end(s);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e) + " (k_cepdet)"; return CTU_ERR_CUDA; }
