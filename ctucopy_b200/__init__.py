@@ -14,9 +14,10 @@ from .api import (  # noqa: F401
     Result,
     design_filter_bank,
     extract,
+    extract_features,
     lib,
     lib_path,
     parse_config,
 )
 
-__all__ = ["Config", "CtuError", "Handle", "Plan", "Result", "design_filter_bank", "extract", "lib", "lib_path", "parse_config"]
+__all__ = ["Config", "CtuError", "Handle", "Plan", "Result", "design_filter_bank", "extract", "extract_features", "lib", "lib_path", "parse_config"]

@@ -17,7 +17,7 @@ import numpy as np
 
 CTU_STR = 40
 CTU_FBDEF = 1024
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class CtuError(RuntimeError):
@@ -68,6 +68,7 @@ class Config(C.Structure):
         ("window", C.c_int32), ("wshift", C.c_int32), ("wfft", C.c_int32), ("wfftby2", C.c_int32), ("phase_needed", C.c_int32),
         ("fea_Z_exp", C.c_float), ("fea_Z_block", C.c_float), ("cms_exp_coef", C.c_float),
         ("stat_cmvn", C.c_int32), ("apply_cmvn", C.c_int32),
+        ("fea_trap", C.c_int32), ("trap_win", C.c_int32), ("fea_in", C.c_int32), ("nfeacoefs", C.c_int32),
     ]
 
 
@@ -103,6 +104,9 @@ def lib() -> C.CDLL:
     L.ctu_last_error.argtypes = [vp]; L.ctu_last_error.restype = cp
     L.ctu_design_filter_bank.argtypes = [P(Config), vp, vp, vp, P(i32)]; L.ctu_design_filter_bank.restype = C.c_int
     L.ctu_feature_dim.argtypes = [vp]; L.ctu_feature_dim.restype = C.c_int
+    L.ctu_input_dim.argtypes = [vp]; L.ctu_input_dim.restype = C.c_int
+    L.ctu_plan_run_device_fea.argtypes = [vp, vp, vp, vp]; L.ctu_plan_run_device_fea.restype = C.c_int
+    L.ctu_plan_run_host_fea.argtypes = [vp, vp, vp]; L.ctu_plan_run_host_fea.restype = C.c_int
     L.ctu_is_signal_output.argtypes = [vp]; L.ctu_is_signal_output.restype = C.c_int
     L.ctu_num_bands.argtypes = [vp]; L.ctu_num_bands.restype = C.c_int
     L.ctu_fb_matrix.argtypes = [vp, vp, vp, vp]; L.ctu_fb_matrix.restype = C.c_int
@@ -250,6 +254,10 @@ class Handle:
         self._check(self.L.ctu_fb_matrix(self.h, mat.ctypes.data, lo.ctypes.data, hi.ctypes.data))
         return mat, lo, hi
 
+    @property
+    def input_dim(self) -> int:
+        return int(self.L.ctu_input_dim(self.h))
+
     def plan(self, lengths: Sequence[int]) -> "Plan":
         return Plan(self, lengths)
 
@@ -300,6 +308,18 @@ class Plan:
         """All arguments are raw device addresses (e.g. torch.Tensor.data_ptr()); enqueues on `stream`."""
         self.hd._check(self.L.ctu_plan_run_device(self.p, d_pcm, d_ext_vad, d_features, d_waveform, d_vad_nr, d_vad_out, stream))
 
+    def run_host_fea(self, fea_in: np.ndarray, *, features: Optional[np.ndarray] = None) -> Result:
+        """Feature-file input (-format_in htk): rows of Handle.input_dim floats in, rows of feature_dim floats out."""
+        hd = self.hd
+        assert fea_in.dtype == np.float32 and fea_in.flags.c_contiguous and fea_in.shape == (int(self.offsets[-1]), hd.input_dim)
+        if features is None:
+            features = np.empty((self.total_frames, hd.feature_dim), dtype=np.float32)
+        hd._check(self.L.ctu_plan_run_host_fea(self.p, _ptr(fea_in), _ptr(features)))
+        return Result(self.frames_per_utt.copy(), self.rows_per_utt(), self.row_offsets, features)
+
+    def run_device_fea(self, d_fea_in: int, d_features: int, stream: int = 0):
+        self.hd._check(self.L.ctu_plan_run_device_fea(self.p, d_fea_in, d_features, stream))
+
     def run_host(self, pcm: np.ndarray, ext_vad: Optional[np.ndarray] = None, *, features: Optional[np.ndarray] = None,
                  waveform: Optional[np.ndarray] = None, want_vad: bool = True) -> Result:
         """End to end with host buffers (numpy, ideally pinned): H2D + kernels + D2H."""
@@ -330,6 +350,21 @@ def extract(argv: Sequence[str], utterances: List[np.ndarray], ext_vad: Optional
             pcm = np.ascontiguousarray(np.concatenate(utterances).astype(np.int16)) if utterances else np.zeros(0, np.int16)
             ev = np.concatenate(ext_vad).astype(np.uint8) if ext_vad is not None else None
             return plan.run_host(pcm, ev)
+        finally:
+            plan.close()
+    finally:
+        hd.close()
+
+
+def extract_features(argv: Sequence[str], matrices: List[np.ndarray], device: int = 0) -> Result:
+    """`ctucopy -format_in htk <argv> -S list` for the listed feature matrices (each its own file): deltas, context
+    stacking, CMS on existing features.  Every matrix must have Handle.input_dim (= -nfeacoefs) columns."""
+    hd = Handle(argv, device)
+    try:
+        plan = hd.plan([m.shape[0] for m in matrices])
+        try:
+            x = np.ascontiguousarray(np.concatenate(matrices, axis=0).astype(np.float32))
+            return plan.run_host_fea(x)
         finally:
             plan.close()
     finally:

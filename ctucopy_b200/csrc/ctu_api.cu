@@ -34,13 +34,20 @@ struct ctu_handle {
     int vad_cri = VCRI_ENERGY, vad_thr = VTHR_PERC;
     int static_dim = 0, feature_dim = 0;
     int energy_mode = 0, energy_latency = 0;   // optional _E column (last column of every row)
+    // context stacking / deltas of non-cepstral vectors / feature-file input: the static block is gathered from a
+    // separate matrix by k_stack (the frame kernels' output, or the caller's feature rows)
+    bool gather = false, fea_in = false;
+    StackParams skp;
+    int in_dim = 0;                            // floats per input row (feature input)
+    int work_dim = 0;                          // row width the chain computes (= feature_dim + columns the writer cuts)
+    int cms_cols = 0;                          // leading columns -fea_Z_exp normalises
     FrameParams fp;      // filter bank + second stage tables
     DeltaParams dp;
     TrapParams tp;
-    NrParams nrp;
-    SynthParams sp;
-    BurgParams bp;
-    VadParams vp;
+    NrParams nrp{};
+    SynthParams sp{};
+    BurgParams bp{};
+    VadParams vp{};
     // device tables
     float2 *d_tw256 = nullptr, *d_twsplit = nullptr, *d_twinv = nullptr;
     float *d_win = nullptr;
@@ -84,6 +91,9 @@ struct ctu_plan {
     int64_t *d_tS_off = nullptr, *d_tF_off = nullptr;
     // workspaces (whole batch)
     float *d_spec = nullptr, *d_fb = nullptr, *d_log = nullptr;
+    float *d_static = nullptr;           // static block before k_stack (gather modes)
+    float *d_work = nullptr;             // full-width rows when the writer cuts the last column (feature input)
+    float *d_in = nullptr;               // feature input rows (host entry point)
     double *d_fb64 = nullptr;            // band values of the precise path
     double *d_fea64 = nullptr;           // fp64 copy of the feature matrix (feature-vector VAD criterion)
     float *d_E = nullptr;                // log energy per frame (-fea_E)
@@ -124,6 +134,7 @@ static int fail(ctu_handle *h, int code, const std::string &m) {
 
 const char *ctu_last_error(const ctu_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 int ctu_feature_dim(const ctu_handle *h) { return h ? h->feature_dim : 0; }
+int ctu_input_dim(const ctu_handle *h) { return (h && h->fea_in) ? h->in_dim : 0; }
 int ctu_is_signal_output(const ctu_handle *h) { return h && h->signal_out; }
 int ctu_num_bands(const ctu_handle *h) { return h ? h->fb.nb : 0; }
 uint64_t ctu_launch_count(const ctu_handle *h) { return h ? h->lc.launches : 0; }
@@ -166,6 +177,7 @@ int ctu_fb_matrix(const ctu_handle *h, double *mat, int32_t *lo, int32_t *hi) {
 }
 
 int64_t ctu_num_frames(const ctu_handle *h, int64_t n) {
+    if (h->fea_in) return n;                        // feature input: a row is a frame
     const int w = h->cfg.window, s = h->cfg.wshift;
     if (n < w - s) return -1;                       // "IO: Signal shorter than one frame!"
     return (n - (w - s)) / s;
@@ -174,6 +186,7 @@ int64_t ctu_num_frames(const ctu_handle *h, int64_t n) {
 int64_t ctu_num_output_samples(const ctu_handle *h, int64_t n) {
     int64_t T = ctu_num_frames(h, n);
     if (T < 0) return -1;
+    if (h->fea_in) return 0;
     return T * h->cfg.wshift + (h->cfg.window - h->cfg.wshift);
 }
 
@@ -236,7 +249,7 @@ static int build_frame_params(ctu_handle *h) {
     P.remove_dc = c.remove_dc;
     P.take_sqrt = !c.fb_power;
     P.inld_scale = 1.f; P.lin_scale = 1.f; P.log_offset = 0.f;
-    if (h->signal_out) return CTU_OK;
+    if (h->signal_out || h->fea_in) return CTU_OK;
     const CtuFbDesign &fb = h->fb;
     if (fb.nb > MAXB) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: more than 64 filter-bank bands");
     P.nb = fb.nb;
@@ -341,9 +354,47 @@ static int build_frame_params(ctu_handle *h) {
 static int build_delta_trap_params(ctu_handle *h) {
     const ctu_config &c = h->cfg;
     DeltaParams &D = h->dp;
+    StackParams &S = h->skp;
     std::memset(&D, 0, sizeof(D));
-    int n_order = 0;
-    if ((h->fea_kind == FEA_DCTC || h->fea_kind == FEA_LPC) && c.fea_delta) n_order = c.n_order;
+    std::memset(&S, 0, sizeof(S));
+    S.L = 1;
+    // deltaFEA works on the first fea_ncepcoefs+1 elements of whatever vector it is given (src/fea/fea_delta.cc:23, 31);
+    // -fea_trap reuses its first stage as a context window (src/io/opts.cc:694-704)
+    const int fea_c = c.fea_ncepcoefs + 1;
+    const bool chain = c.fea_delta && c.n_order > 0;
+    const bool trap = chain && c.fea_trap;
+    const bool cepstral = (h->fea_kind == FEA_DCTC || h->fea_kind == FEA_LPC);
+    int n_order = (chain && !trap) ? c.n_order : 0;
+    int blk = h->static_dim;
+    if (h->fea_in) {
+        h->in_dim = c.nfeacoefs;
+        if (h->in_dim < 1) return fail(h, CTU_ERR_CONFIG, "IN: -nfeacoefs must be positive");
+        if (chain && h->in_dim < fea_c) return fail(h, CTU_ERR_CONFIG, "IN: -nfeacoefs is smaller than fea_ncepcoefs+1, the columns the delta chain reads");
+        h->gather = true;
+        blk = chain ? fea_c : h->in_dim;
+        S.fea_c = blk; S.rot = 0; S.src_stride = h->in_dim;
+        h->static_dim = blk;
+    } else if (chain) {
+        if (h->fea_kind == FEA_LPA) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: deltas / stacking with -fea_kind lpa (the reference's delta chain and writer disagree on the vector layout)");
+        if (h->fea_kind == FEA_TRAPDCT) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: deltas / stacking with trapdct (the reference never flushes the TRAP ring then, src/io/batch.cc:253: the last rows are lost)");
+        if (cepstral && !c.fea_c0)
+            return fail(h, CTU_ERR_UNSUPPORTED, trap ? "CTU: -fea_trap with -fea_c0 off (the reference writes past its output buffer, src/io/out.cc:184)"
+                                                     : "CTU: deltas with -fea_c0 off (the reference writes uninitialised columns there, src/io/out.cc:189-201)");
+        if (!cepstral && h->fb.nb < fea_c) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: deltas / stacking read fea_ncepcoefs+1 elements, more than the filter bank has bands");
+        if (!cepstral || trap) {
+            h->gather = true;
+            blk = fea_c;
+            S.fea_c = fea_c; S.rot = cepstral ? 1 : 0; S.src_stride = h->static_dim;
+        }
+    }
+    if (trap) {
+        if (c.d_win < 1) return fail(h, CTU_ERR_CONFIG, "FEA: Trap window size must be >= 3!");
+        S.win = c.d_win; S.L = 2 * c.d_win + 1;
+    }
+    if (h->gather && h->do_vad && h->vad_cri == VCRI_CEPDIST_FEA)
+        return fail(h, CTU_ERR_UNSUPPORTED, "CTU: the feature-vector VAD criterion together with stacking / deltas of spectral vectors");
+    if (h->gather && (c.stat_cmvn || c.apply_cmvn))
+        return fail(h, CTU_ERR_UNSUPPORTED, "CTU: CMVN together with stacking / deltas of spectral vectors / feature-file input");
     D.n_order = n_order;
     int wins[3] = {c.d_win, c.a_win, c.t_win};
     int halo = 0;
@@ -356,12 +407,21 @@ static int build_delta_trap_params(ctu_handle *h) {
         D.inv_den64[k] = 1.0 / (2 * den);
         halo += wins[k];
     }
-    if (n_order > 0 && !c.fea_c0)
-        return fail(h, CTU_ERR_UNSUPPORTED, "CTU: deltas with -fea_c0 off (the reference writes uninitialised columns there, src/io/out.cc:189-201)");
-    D.blk = h->static_dim;
-    h->feature_dim = h->static_dim * (n_order + 1) + (c.fea_E ? 1 : 0);
-    D.stride = h->feature_dim;
+    D.blk = blk;
+    h->work_dim = (trap ? blk * S.L : blk * (n_order + 1)) + (c.fea_E ? 1 : 0);
+    h->feature_dim = h->work_dim;
+    if (h->fea_in) {
+        // htkOUT::get_fea_size (src/io/out.cc:95-112) cuts one element for lpa, and for lpc / dctc without c0; the
+        // writer then copies the first fea_size elements as they come (src/io/out.cc:177-179)
+        if (h->fea_kind == FEA_LPA || (cepstral && !c.fea_c0)) h->feature_dim = h->work_dim - 1;
+        if (h->feature_dim < 1) return fail(h, CTU_ERR_CONFIG, "OUT: empty feature vector");
+    }
+    D.stride = h->work_dim;
+    S.dst_stride = h->work_dim;
     D.span_max = DELTA_ROWS + 2 * halo;
+    // -fea_Z_exp normalises the first fea_ncepcoefs+1 elements of the finished vector (src/fea/post_impl.cc:203-209): the
+    // whole static block of cepstral rows (c0 included, wherever the writer puts it), the leading columns otherwise
+    h->cms_cols = h->gather ? ((h->fea_in && !chain) ? 0 : fea_c) : h->static_dim;
     if (h->fea_kind == FEA_TRAPDCT) {
         TrapParams &T = h->tp;
         std::memset(&T, 0, sizeof(T));
@@ -381,7 +441,7 @@ static int build_delta_trap_params(ctu_handle *h) {
             }
             for (int j = 0; j < L; j++) T.m[(k - 1) * L + j] = (float)(row[j] - sum / L);
         }
-        h->feature_dim = h->fb.nb * n;
+        h->feature_dim = h->work_dim = h->fb.nb * n;
         T.out_stride = h->feature_dim;
     }
     if (c.fea_E) {
@@ -398,7 +458,7 @@ static int build_delta_trap_params(ctu_handle *h) {
         else if (h->fea_kind == FEA_LPA || h->fea_kind == FEA_LPC) h->energy_mode = EN_LPC;
         else h->energy_mode = EN_BANDS;
         // the row is written `latency` frames after its energy was current (deltas, VAD majority filter)
-        int lat = 0;
+        int lat = trap ? c.d_win : 0;
         for (int k = 0; k < n_order; k++) lat += wins[k];
         if (h->do_vad) lat += (c.vad_filter_order - 1) / 2;
         h->energy_latency = lat;
@@ -432,8 +492,19 @@ static int resolve_modes(ctu_handle *h) {
         if (h->vad_src == VADSRC_BURG && c.nr_when == 1 && !h->signal_out)
             return fail(h, CTU_ERR_CONFIG, "NR: Cannot use Burg detector after filter bank!");
     }
+    h->fea_in = c.fea_in != 0;
+    if (h->fea_in) {
+        // BATCH::BATCH, src/io/batch.cc:55-60: no IN spectrum, no NR, no FB, no FEA -- only deltaFEA / POST / OUT
+        if (h->signal_out) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: feature-file input with waveform output");
+        if (c.fea_E) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_E with feature-file input (no energy is ever computed; the reference reads past its vector, src/io/out.cc:177-179)");
+        if (h->fea_kind == FEA_DCTC && !c.fea_rawenergy)
+            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: feature-file input with -fea_kind dctc needs -fea_rawenergy on (the reference dereferences a null NR otherwise, src/io/batch.cc:108)");
+        if (h->fea_kind == FEA_TRAPDCT) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: feature-file input with -fea_kind trapdct");
+        h->nr_mode = NR_NONE; h->vad_src = VADSRC_NONE;
+    }
     std::string am(c.vad_apply_mode), om(c.vad_out_mode);
     h->do_vad = (am != "none" || om != "none");
+    if (h->do_vad && h->fea_in) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: the VAD module with feature-file input (there is no spectrum to decide on)");
     h->vad_drop = (am == "drop");
     if (h->do_vad && h->signal_out)
         return fail(h, CTU_ERR_UNSUPPORTED, "CTU: the VAD module with waveform output (the reference dereferences an uninitialised pointer there, src/io/batch.cc:63-65,230-241)");
@@ -467,14 +538,16 @@ static int resolve_modes(ctu_handle *h) {
     if (c.fea_Z_block > 0)
         return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_Z_block: the reference dies with SIGSEGV in this mode (ring of row pointers allocated with sizeof(float), src/fea/post_impl.cc:179); nothing to match");
     if (c.cms_exp_coef > 0) {
-        if (h->signal_out || (h->fea_kind != FEA_DCTC && h->fea_kind != FEA_LPC))
-            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_Z_exp is built for cepstral features (dctc, lpc)");
+        const bool chain = c.fea_delta && c.n_order > 0;
+        if (h->signal_out || (h->fea_kind != FEA_DCTC && h->fea_kind != FEA_LPC && !chain && !h->fea_in))
+            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_Z_exp is built for cepstral features (dctc, lpc) and for delta / stacking chains");
         if (h->do_vad) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -fea_Z_exp together with the VAD module");
     }
     // -remove_dc1 needs per-frame ring offsets: only the general kernel applies them
     // dither (src/io/in.cc:452-455): glibc's rand() stream restated on the host, one value per loaded sample in list
     // order; applied by the general kernel
-    h->generic = (c.wfft != NFFT) || c.remove_dc1 || c.dither != 0.0;
+    h->generic = !h->fea_in && ((c.wfft != NFFT) || c.remove_dc1 || c.dither != 0.0);
+    if (h->fea_in) { h->nbins = c.wfftby2; return CTU_OK; }
     if (c.dither != 0.0 && (c.remove_dc1 || (c.fea_E && c.fea_rawenergy)))
         return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -dither together with -remove_dc1 or -fea_rawenergy");
     h->nbins = c.wfftby2;
@@ -502,13 +575,13 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     int st = ctu_config_finalize(&h->cfg);
     if (st) { h->err = ctu_config_error(); return bail(st); }
     if ((st = resolve_modes(h))) return bail(st);
-    if (!h->signal_out) {
+    if (!h->signal_out && !h->fea_in) {
         std::string e = ctu_design_fb(h->cfg, h->fb);
         if (!e.empty()) { h->err = e; return bail(CTU_ERR_CONFIG); }
     }
     if ((st = build_frame_params(h))) return bail(st);
     if ((st = build_delta_trap_params(h))) return bail(st);
-    if ((st = build_nr_params(h->cfg, h->nr_mode, h->vad_src, h->signal_out, h->fb.nb, h->nrp, h->sp, h->bp, h->vp, h->err))) return bail(st);
+    if (!h->fea_in && (st = build_nr_params(h->cfg, h->nr_mode, h->vad_src, h->signal_out, h->fb.nb, h->nrp, h->sp, h->bp, h->vp, h->err))) return bail(st);
     h->vp.cri = h->vad_cri; h->vp.thr = h->vad_thr; h->vp.drop = h->vad_drop;
     h->vp.has_E = h->energy_mode ? 1 : 0;
     h->vp.nbins = h->nbins;
@@ -526,7 +599,7 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     }
     if (cudaSetDevice(device) != cudaSuccess) { h->err = "CUDA: cudaSetDevice failed"; return bail(CTU_ERR_CUDA); }
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
-    if ((st = build_fft_tables(h))) return bail(st);
+    if (!h->fea_in && (st = build_fft_tables(h))) return bail(st);
     if (h->generic) {
         if (h->precise) { h->err = "CTU: this configuration needs the fp64 path (band-domain noise reduction, LPC without the cube-root law, feature-vector VAD), built for 512-point frames only"; return bail(CTU_ERR_UNSUPPORTED); }
         const int N = h->cfg.wfft, M = N / 2;
@@ -610,8 +683,8 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     int64_t rows = 0, osamp = 0, t32 = 0, t64 = 0, tS = 0, tF = 0;
     for (int u = 0; u < n; u++) {
         int64_t N = off[u + 1] - off[u];
-        if (N < w - s) { delete p; return fail(h, CTU_ERR_INPUT, "IO: Signal shorter than one frame!"); }
-        int64_t T = (N - (w - s)) / s;
+        if (!h->fea_in && N < w - s) { delete p; return fail(h, CTU_ERR_INPUT, "IO: Signal shorter than one frame!"); }
+        int64_t T = h->fea_in ? N : (N - (w - s)) / s;                 // feature input: one row = one frame
         if (T > 0x7fffffff) { delete p; return fail(h, CTU_ERR_INPUT, "CTU: utterance too long"); }
         p->nframes[u] = (int)T;
         p->row_off[u] = rows; p->osamp_off[u] = osamp; p->tile32_off[u] = t32; p->tile64_off[u] = t64; p->tileS_off[u] = tS; p->tileF_off[u] = tF;
@@ -627,8 +700,9 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
             for (int k = 0; k < h->dp.n_order; k++) mw = std::max(mw, h->dp.win[k]);
             if (T < mw + 2) { delete p; return fail(h, CTU_ERR_UNSUPPORTED, "CTU: utterance shorter than delta window + 2 frames"); }
         }
+        if (h->skp.L > 1 && T < h->skp.win + 2) { delete p; return fail(h, CTU_ERR_UNSUPPORTED, "CTU: utterance shorter than half the stacking window + 2 frames"); }
     }
-    if (h->cfg.dither != 0.0) {
+    if (h->cfg.dither != 0.0 && !h->fea_in) {
         p->rand_base = h->rand_pos;
         h->rand_pos += (uint64_t)rows * (uint64_t)s + (uint64_t)n * (uint64_t)(w - s);     // one rand() per LOADED sample
     }
@@ -658,6 +732,9 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
         CK(cudaDeviceSynchronize());
     }
     // workspaces by configuration
+    if (h->gather && !h->fea_in && (st = dev_alloc(h, p, &p->d_static, (size_t)rows * h->static_dim))) { ctu_plan_destroy(p); return st; }
+    if (h->work_dim != h->feature_dim && (st = dev_alloc(h, p, &p->d_work, (size_t)rows * h->work_dim))) { ctu_plan_destroy(p); return st; }
+    if (h->fea_in) { *out = p; return CTU_OK; }
     const bool nr_on = h->nr_mode != NR_NONE;
     const bool need_spec = h->signal_out || (nr_on && h->cfg.nr_when == 0) || (h->do_vad && h->vad_cri != VCRI_CEPDIST_FEA);
     const bool lpc_kind = (h->fea_kind == FEA_LPA || h->fea_kind == FEA_LPC);
@@ -888,6 +965,63 @@ static int prepare_dither(ctu_plan *p) {
 
 // Runs utterances [u0,u1) of the plan on stream s.  All pointers are whole-batch device
 // buffers (rows / samples are addressed through the plan's global offsets).
+// ---- the delta / stacking / CMS chain on rows of work_dim floats (deltaFEA src/fea/fea_delta.cc:70-206, cms_POST
+// src/fea/post_impl.cc:203-209); `src` = the matrix k_stack gathers the static block from (gather modes)
+static int run_chain(ctu_plan *p, const Range &r, const BatchDesc &bd64, const float *src, float *d_fea, cudaStream_t s) {
+    ctu_handle *h = p->h;
+    // deltas of a plain column gather (feature-file input, spectral vectors): the delta kernel reads the static block from
+    // the source itself; only stacking and the plain copy need k_stack
+    const bool fused = h->gather && h->dp.n_order > 0 && h->skp.L == 1 && !h->skp.rot;
+    if (h->gather && !fused && r.t64_n > 0) {
+        const StackParams &S = h->skp;
+        const size_t bytes = (size_t)(DELTA_ROWS + 2 * S.win + 1) * S.src_stride * sizeof(float);
+        h->lc.begin("k_stack", s);
+        if (bytes <= 96 * 1024) {
+            CK(cudaFuncSetAttribute(k_stack<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            k_stack<true><<<(unsigned)r.t64_n, 256, bytes, s>>>(S, bd64, DELTA_ROWS, src, d_fea);
+        } else {
+            k_stack<false><<<(unsigned)r.t64_n, 256, 0, s>>>(S, bd64, DELTA_ROWS, src, d_fea);
+        }
+        h->lc.end(s);
+        CK(cudaGetLastError());
+    }
+    const float *dsrc = fused ? src : nullptr;
+    const int dss = fused ? h->skp.src_stride : 0;
+    if (h->dp.n_order > 0 && r.t64_n > 0) {
+        const bool fast = (h->dp.n_order == 2 && h->dp.win[0] == 2 && h->dp.win[1] == 2 && h->dp.blk <= 16);
+        size_t bytes = fast ? (size_t)(DELTA_ROWS + 8) * h->dp.blk * sizeof(float) : (size_t)2 * h->dp.span_max * h->dp.blk * sizeof(float);
+        h->lc.begin("k_delta", s);
+        if (fast) {
+            k_delta22<float><<<(unsigned)r.t64_n, 256, bytes, s>>>(h->dp, bd64, d_fea, dsrc, dss);
+        } else {
+            CK(cudaFuncSetAttribute(k_delta<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            k_delta<float><<<(unsigned)r.t64_n, 256, bytes, s>>>(h->dp, bd64, DELTA_ROWS, d_fea, dsrc, dss);
+        }
+        h->lc.end(s);
+        CK(cudaGetLastError());
+        if (p->d_fea64) {
+            h->lc.begin("k_delta64", s);
+            if (fast) {
+                k_delta22<double><<<(unsigned)r.t64_n, 256, 2 * bytes, s>>>(h->dp, bd64, p->d_fea64);
+            } else {
+                CK(cudaFuncSetAttribute(k_delta<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * bytes)));
+                k_delta<double><<<(unsigned)r.t64_n, 256, 2 * bytes, s>>>(h->dp, bd64, DELTA_ROWS, p->d_fea64);
+            }
+            h->lc.end(s);
+            CK(cudaGetLastError());
+        }
+    }
+    if (h->cfg.cms_exp_coef > 0 && h->cms_cols > 0 && r.nrows > 0) {
+        // static block in writer order: c1..cN [c0]; c0 is normalised in the reference even when it is not written
+        const int ncols = h->cms_cols, n = (r.u1 - r.u0) * ncols;
+        h->lc.begin("k_cms_exp", s);
+        k_cms_exp<<<(n + 127) / 128, 128, 0, s>>>(p->d_nframes, p->d_row_off, r.u0, r.u1 - r.u0, ncols, h->work_dim, h->cfg.cms_exp_coef, d_fea);
+        h->lc.end(s);
+        CK(cudaGetLastError());
+    }
+    return CTU_OK;
+}
+
 static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const uint8_t *d_ext, float *d_fea, int16_t *d_wave,
                      uint8_t *d_vadnr, uint8_t *d_vadout, cudaStream_t s) {
     ctu_handle *h = p->h;
@@ -939,6 +1073,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     float *fea_dst = d_fea;
     int od = h->static_dim, ostride = h->feature_dim;
     if (kind == KIND_TRAPLOG) { fea_dst = p->d_log; od = h->fb.nb; ostride = h->fb.nb; }
+    if (h->gather) { fea_dst = p->d_static; ostride = h->static_dim; }        // k_stack builds the rows from it
     P = h->fp; P.out_dim = od; P.out_stride = ostride;
     P.energy_mode = h->energy_mode; P.energy = p->d_E;
     P.dc1 = p->d_dc1;
@@ -987,38 +1122,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
         h->lc.end(s);
         CK(cudaGetLastError());
     }
-    if (h->dp.n_order > 0 && r.t64_n > 0) {
-        const bool fast = (h->dp.n_order == 2 && h->dp.win[0] == 2 && h->dp.win[1] == 2 && h->dp.blk <= 16);
-        size_t bytes = fast ? (size_t)(DELTA_ROWS + 8) * h->dp.blk * sizeof(float) : (size_t)2 * h->dp.span_max * h->dp.blk * sizeof(float);
-        h->lc.begin("k_delta", s);
-        if (fast) {
-            k_delta22<float><<<(unsigned)r.t64_n, 256, bytes, s>>>(h->dp, bd64, d_fea);
-        } else {
-            CK(cudaFuncSetAttribute(k_delta<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-            k_delta<float><<<(unsigned)r.t64_n, 256, bytes, s>>>(h->dp, bd64, DELTA_ROWS, d_fea);
-        }
-        h->lc.end(s);
-        CK(cudaGetLastError());
-        if (p->d_fea64) {
-            h->lc.begin("k_delta64", s);
-            if (fast) {
-                k_delta22<double><<<(unsigned)r.t64_n, 256, 2 * bytes, s>>>(h->dp, bd64, p->d_fea64);
-            } else {
-                CK(cudaFuncSetAttribute(k_delta<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * bytes)));
-                k_delta<double><<<(unsigned)r.t64_n, 256, 2 * bytes, s>>>(h->dp, bd64, DELTA_ROWS, p->d_fea64);
-            }
-            h->lc.end(s);
-            CK(cudaGetLastError());
-        }
-    }
-    if (h->cfg.cms_exp_coef > 0 && r.nrows > 0) {
-        // static block in writer order: c1..cN [c0]; c0 is normalised in the reference even when it is not written
-        const int ncols = h->static_dim, n = (r.u1 - r.u0) * ncols;
-        h->lc.begin("k_cms_exp", s);
-        k_cms_exp<<<(n + 127) / 128, 128, 0, s>>>(p->d_nframes, p->d_row_off, r.u0, r.u1 - r.u0, ncols, h->feature_dim, h->cfg.cms_exp_coef, d_fea);
-        h->lc.end(s);
-        CK(cudaGetLastError());
-    }
+    if ((st = run_chain(p, r, bd64, p->d_static, d_fea, s))) return st;
     if (h->energy_mode && r.t64_n > 0) {
         if (h->energy_mode == EN_RAW) {
             h->lc.begin("k_rawenergy", s);
@@ -1057,6 +1161,7 @@ int ctu_plan_run_device(ctu_plan *p, const int16_t *d_pcm, const uint8_t *d_ext_
     if (!p) return CTU_ERR_CONFIG;
     ctu_handle *h = p->h;
     CK(cudaSetDevice(h->device));
+    if (h->fea_in) return fail(h, CTU_ERR_CONFIG, "CTU: this handle takes feature rows (-format_in htk): use ctu_plan_run_device_fea / ctu_plan_run_host_fea");
     if (!h->signal_out && !d_features) return fail(h, CTU_ERR_CAPACITY, "CTU: features buffer is NULL");
     if (h->signal_out && !d_waveform) return fail(h, CTU_ERR_CAPACITY, "CTU: waveform buffer is NULL");
     cudaStream_t s = (cudaStream_t)stream;
@@ -1073,6 +1178,7 @@ static int run_host_impl(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad
     if (!p) return CTU_ERR_CONFIG;
     ctu_handle *h = p->h;
     CK(cudaSetDevice(h->device));
+    if (h->fea_in) return fail(h, CTU_ERR_CONFIG, "CTU: this handle takes feature rows (-format_in htk): use ctu_plan_run_device_fea / ctu_plan_run_host_fea");
     if (!keep && !h->signal_out && !features) return fail(h, CTU_ERR_CAPACITY, "CTU: features buffer is NULL");
     if (!keep && h->signal_out && !waveform) return fail(h, CTU_ERR_CAPACITY, "CTU: waveform buffer is NULL");
     int st;
@@ -1133,9 +1239,68 @@ int ctu_plan_fetch(ctu_plan *p, float *features, int16_t *waveform, uint8_t *vad
     CK(cudaSetDevice(h->device));
     if (features && p->d_fea) CK(cudaMemcpy(features, p->d_fea, (size_t)p->total_frames * h->feature_dim * sizeof(float), cudaMemcpyDeviceToHost));
     if (waveform && p->d_wave) CK(cudaMemcpy(waveform, p->d_wave, (size_t)p->total_osamp * sizeof(int16_t), cudaMemcpyDeviceToHost));
-    if (vad_nr) CK(cudaMemcpy(vad_nr, p->d_vadnr_out, (size_t)p->total_frames, cudaMemcpyDeviceToHost));
+    if (vad_nr && p->d_vadnr_out) CK(cudaMemcpy(vad_nr, p->d_vadnr_out, (size_t)p->total_frames, cudaMemcpyDeviceToHost));
     if (vad_out && h->do_vad) CK(cudaMemcpy(vad_out, p->d_vad_out, (size_t)p->total_frames, cudaMemcpyDeviceToHost));
     return CTU_OK;
+}
+
+// ---- feature-file input: rows in, rows out (htkIN -> deltaFEA -> cms_POST -> OUT, src/io/batch.cc:55-60, 217-218) -----
+static int run_range_fea(ctu_plan *p, const Range &r, const float *d_in, float *d_fea, cudaStream_t s) {
+    ctu_handle *h = p->h;
+    if (r.nrows <= 0) return CTU_OK;
+    BatchDesc bd64{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tiles64 + r.t64_0};
+    float *work = p->d_work ? p->d_work : d_fea;
+    int st = run_chain(p, r, bd64, d_in, work, s);
+    if (st) return st;
+    if (p->d_work)      // the writer drops the last element of every row (htkOUT::get_fea_size, src/io/out.cc:95-112)
+        CK(cudaMemcpy2DAsync(d_fea + r.row0 * h->feature_dim, (size_t)h->feature_dim * sizeof(float), work + r.row0 * h->work_dim,
+                             (size_t)h->work_dim * sizeof(float), (size_t)h->feature_dim * sizeof(float), (size_t)r.nrows, cudaMemcpyDeviceToDevice, s));
+    return CTU_OK;
+}
+
+int ctu_plan_run_device_fea(ctu_plan *p, const float *d_fea_in, float *d_features, void *stream) {
+    if (!p) return CTU_ERR_CONFIG;
+    ctu_handle *h = p->h;
+    CK(cudaSetDevice(h->device));
+    if (!h->fea_in) return fail(h, CTU_ERR_CONFIG, "CTU: this handle takes PCM: use ctu_plan_run_device / ctu_plan_run_host");
+    if (!d_fea_in || !d_features) return fail(h, CTU_ERR_CAPACITY, "CTU: feature buffer is NULL");
+    int st = run_range_fea(p, make_range(p, 0, p->n_utts), d_fea_in + p->offsets[0] * h->in_dim, d_features, (cudaStream_t)stream);
+    if (st) return st;
+    return fetch_rows(p, (cudaStream_t)stream);
+}
+
+int ctu_plan_run_host_fea(ctu_plan *p, const float *fea_in, float *features) {
+    if (!p) return CTU_ERR_CONFIG;
+    ctu_handle *h = p->h;
+    CK(cudaSetDevice(h->device));
+    if (!h->fea_in) return fail(h, CTU_ERR_CONFIG, "CTU: this handle takes PCM: use ctu_plan_run_device / ctu_plan_run_host");
+    if (!fea_in) return fail(h, CTU_ERR_CAPACITY, "CTU: feature buffer is NULL");
+    int st;
+    if (!p->host_bufs) {
+        if ((st = dev_alloc(h, p, &p->d_in, (size_t)p->total_frames * h->in_dim + 8))) return st;
+        if ((st = dev_alloc(h, p, &p->d_fea, (size_t)p->total_frames * h->feature_dim + 8))) return st;
+        p->host_bufs = true;
+    }
+    // the same three-stream pipeline as the PCM entry point: chunks of utterances of about 32 MB of input
+    const int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)32 << 20) / ((int64_t)h->in_dim * (int64_t)sizeof(float)));
+    const float *in0 = fea_in + p->offsets[0] * h->in_dim;
+    int u0 = 0, ci = 0;
+    while (u0 < p->n_utts) {
+        int u1 = u0 + 1;
+        while (u1 < p->n_utts && p->row_off[u1 + 1] - p->row_off[u0] <= chunk_rows) u1++;
+        cudaStream_t s = h->streams[ci % 3];
+        Range r = make_range(p, u0, u1);
+        if (r.nrows) {
+            CK(cudaMemcpyAsync(p->d_in + r.row0 * h->in_dim, in0 + r.row0 * h->in_dim, (size_t)r.nrows * h->in_dim * sizeof(float), cudaMemcpyHostToDevice, s));
+            if ((st = run_range_fea(p, r, p->d_in, p->d_fea, s))) return st;
+            if (features)
+                CK(cudaMemcpyAsync(features + r.row0 * h->feature_dim, p->d_fea + r.row0 * h->feature_dim,
+                                   (size_t)r.nrows * h->feature_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+        }
+        u0 = u1; ci++;
+    }
+    for (int i = 0; i < 3; i++) CK(cudaStreamSynchronize(h->streams[i]));
+    return fetch_rows(p, h->streams[0]);
 }
 
 // ---- per-utterance column statistics and normalisation of the device-resident feature rows: the device

@@ -52,6 +52,7 @@ int ctu_config_init(ctu_config *c) {
     c->fea_lifter = 22;
     c->fea_trapdct_traplen = 0; c->fea_trapdct_ndct = 0;  // the reference leaves these uninitialised
     c->fea_delta = 0; c->n_order = 0; c->d_win = c->a_win = c->t_win = 2;
+    c->fea_trap = 0; c->trap_win = 5; c->fea_in = 0; c->nfeacoefs = 13;      // src/io/opts.cc:97-99
     put(c->vad_apply_mode, "none");
     put(c->vad_out_mode, "none");
     put(c->vad_cri_mode, "energy");
@@ -130,9 +131,9 @@ const Opt kOpts[] = {
     {"-fea_Z_exp", K_FLT, O(fea_Z_exp)}, {"-fea_Z_block", K_FLT, O(fea_Z_block)},
     // owned by the host CLI, not by the hot path: accepted, no effect here
     {"-S", K_IGNORE, 0}, {"-i", K_IGNORE, 0}, {"-o", K_IGNORE, 0}, {"-C", K_IGNORE, 0},
-    {"-format_in", K_IGNORE, 0}, {"-endian_in", K_IGNORE, 0}, {"-endian_out", K_IGNORE, 0},
+    {"-endian_in", K_IGNORE, 0}, {"-endian_out", K_IGNORE, 0},
     {"-vad_out", K_IGNORE, 0}, {"-filters", K_IGNORE, 0},
-    {"-nfeacoefs", K_IGNORE, 0}, {"-weight_of_td_iir_mfcc_bank", K_IGNORE, 0}, {"-nr_rasta", K_IGNORE, 0},
+    {"-weight_of_td_iir_mfcc_bank", K_IGNORE, 0}, {"-nr_rasta", K_IGNORE, 0},
     {"-online_in", K_FLAG_IGNORE, 0}, {"-online_out", K_FLAG_IGNORE, 0}, {"-fb_printself", K_FLAG_IGNORE, 0},
     {"-verbose", K_FLAG_IGNORE, 0}, {"-v", K_FLAG_IGNORE, 0}, {"-quiet", K_FLAG_IGNORE, 0},
     {"-info", K_FLAG_IGNORE, 0}, {"-h", K_FLAG_IGNORE, 0}, {"--help", K_FLAG_IGNORE, 0},
@@ -191,6 +192,7 @@ int ctu_config_set(ctu_config *c, const char *l, const char *r) {
     if (opt == "-fea_delta") {
         if (!r) return CTU_OK;
         c->fea_delta = 1;
+        c->fea_trap = 0;
         if (!std::strcmp(r, "d")) c->n_order = 1;
         else if (!std::strcmp(r, "d_a")) c->n_order = 2;
         else if (!std::strcmp(r, "d_a_t")) c->n_order = 3;
@@ -198,9 +200,22 @@ int ctu_config_set(ctu_config *c, const char *l, const char *r) {
         return CTU_OK;
     }
     if (opt == "-fea_trap") {
-        if (r) return cfg_fail("CTU: -fea_trap context stacking is not part of this hot path (SURVEY 8f.3)");
+        // src/io/opts.cc:694-704: ignored after -fea_delta; reuses the first delta stage with window (N-1)/2
+        if (r && !c->fea_delta) {
+            c->fea_trap = 1;
+            c->trap_win = std::atoi(r);
+            c->fea_delta = 1;
+            c->n_order = 1;
+            c->d_win = (c->trap_win - 1) / 2;
+        }
         return CTU_OK;
     }
+    if (opt == "-format_in") {
+        // the sample decoders (raw, alaw, mulaw, wave) belong to the host; "htk" switches the library to feature input
+        if (r) c->fea_in = !std::strcmp(r, "htk");
+        return CTU_OK;
+    }
+    if (opt == "-nfeacoefs") { if (r) c->nfeacoefs = std::atoi(r); return CTU_OK; }
     for (const Opt &o : kOpts) {
         if (opt != o.name) continue;
         if (o.kind == K_FLAG_IGNORE || o.kind == K_IGNORE) return CTU_OK;

@@ -592,7 +592,20 @@ k_cms_exp(const int *__restrict__ nframes, const int64_t *__restrict__ row_off, 
     float *x = fea + row_off[u] * stride + col;
     const float omZ = 1.0f - Z;
     float m = 0.f;
-    for (int t = 0; t < T; t++, x += stride) {
+    // the recurrence is serial in t but its loads are not: eight rows are fetched before the chain advances
+    int t = 0;
+    for (; t + 8 <= T; t += 8, x += 8 * (int64_t)stride) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = x[(int64_t)i * stride];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const double c = (double)v[i];
+            m = (float)((double)(m * Z) + c * (double)omZ);
+            x[(int64_t)i * stride] = (float)(c - (double)m);
+        }
+    }
+    for (; t < T; t++, x += stride) {
         const double c = (double)*x;
         m = (float)((double)(m * Z) + c * (double)omZ);
         *x = (float)(c - (double)m);
@@ -776,7 +789,8 @@ constexpr int DELTA_ROWS = 64;
 
 template <class E>
 __global__ void __launch_bounds__(256)
-k_delta(const __grid_constant__ DeltaParams D, BatchDesc bd, int tile_rows, E *__restrict__ fea) {
+k_delta(const __grid_constant__ DeltaParams D, BatchDesc bd, int tile_rows, E *__restrict__ fea, const E *__restrict__ src = nullptr,
+        int src_stride = 0) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     E *sm = reinterpret_cast<E *>(sm_raw);
     const int2 tile = bd.tiles[blockIdx.x];
@@ -792,10 +806,17 @@ k_delta(const __grid_constant__ DeltaParams D, BatchDesc bd, int tile_rows, E *_
     const int span = nr + 2 * halo;                       // rows t0-halo .. t0+nr+halo-1 (clamped)
     E *cur = sm;                                          // [span][blk]
     E *nxt = sm + D.span_max * blk;
+    // src != nullptr: the static block comes from another matrix (the first blk columns of its rows: feature-file input,
+    // spectral vectors) and is written to the output rows here as well -- gather and deltas in one pass
     for (int r = ry; r < span; r += 16) {
-        const int t = min(max(t0 - halo + r, 0), T - 1);
-        const E *g = fea + (row0 + t) * D.stride;
-        for (int col = cx; col < blk; col += 16) cur[r * blk + col] = g[col];
+        const int ta = t0 - halo + r, t = min(max(ta, 0), T - 1);
+        const E *g = src ? src + (row0 + t) * src_stride : fea + (row0 + t) * D.stride;
+        const bool own = src && ta >= t0 && ta < t0 + nr;
+        for (int col = cx; col < blk; col += 16) {
+            const E v = g[col];
+            cur[r * blk + col] = v;
+            if (own) fea[(row0 + t) * D.stride + col] = v;
+        }
     }
     __syncthreads();
     int h = halo;                                         // halo still valid around `cur`
@@ -834,7 +855,7 @@ k_delta(const __grid_constant__ DeltaParams D, BatchDesc bd, int tile_rows, E *_
 // (src/fea/fea_delta.cc:70-130, 178-206).
 template <class E>
 __global__ void __launch_bounds__(256)
-k_delta22(const __grid_constant__ DeltaParams D, BatchDesc bd, E *__restrict__ fea) {
+k_delta22(const __grid_constant__ DeltaParams D, BatchDesc bd, E *__restrict__ fea, const E *__restrict__ src = nullptr, int src_stride = 0) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     E *cur = reinterpret_cast<E *>(sm_raw);               // [DELTA_ROWS + 8][blk]
     const int2 tile = bd.tiles[blockIdx.x];
@@ -848,7 +869,7 @@ k_delta22(const __grid_constant__ DeltaParams D, BatchDesc bd, E *__restrict__ f
     if (cx < blk)
         for (int r = seg; r < span; r += 16) {
             const int t = min(max(t0 - 4 + r, 0), T - 1);
-            cur[r * blk + cx] = fea[(row0 + t) * D.stride + cx];
+            cur[r * blk + cx] = src ? src[(row0 + t) * src_stride + cx] : fea[(row0 + t) * D.stride + cx];
         }
     __syncthreads();
     const int r0 = seg * 4;                               // first of this thread's rows, relative to t0
@@ -869,6 +890,7 @@ k_delta22(const __grid_constant__ DeltaParams D, BatchDesc bd, E *__restrict__ f
         if (t >= t0 + nr) break;
         const E a = ((d[i + 3] - d[i + 1]) + (E)2 * (d[i + 4] - d[i])) * s2;
         E *o = fea + (row0 + t) * D.stride + cx;
+        if (src) o[0] = cur[(r0 + i + 4) * blk + cx];     // static block from the external source (see k_delta)
         o[blk] = d[i + 2];
         o[2 * blk] = a;
     }
@@ -965,6 +987,72 @@ k_trapdct(const __grid_constant__ TrapParams Tp, BatchDesc bd, int tile_rows, co
 #pragma unroll
         for (int k = 0; k < NA; k++)
             if (k < ND) o[k] = acc[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K9: column gather / context stacking.  Three uses, one kernel:
+//   * `-fea_trap N` (deltaFEA::trap, src/fea/fea_delta.cc:166-176): out[t][i*L + j] = C[t + j - win][i], L = N = 2 win + 1,
+//     rows clamped to the utterance, with the reference's start-up and flush behaviour (closed form and its derivation:
+//     oracle/ctu_oracle.py trap_stack_closed_form -- first row stacks rows 0 x win, 1, 1, 2, .., win; with win == 1 the last
+//     row stacks row T-1 three times; the first row and the last `win` rows then carry C[t][0..fea_c) in their first fea_c
+//     elements, src/fea/fea_delta.cc:88-90, 197-199);
+//   * deltas of spec / logspec vectors: the delta chain works on the first fea_ncepcoefs+1 elements (L = 1);
+//   * feature-file input (htkIN, src/io/in.cc:682-690): the first fea_c columns of the input rows (L = 1).
+// C is in the reference's INTERNAL order; `rot` says the source block is stored in writer order (c1..cN, c0).
+// One CTA per tile of DELTA_ROWS rows; consecutive threads write consecutive output elements.
+// ------------------------------------------------------------------------------------------
+struct StackParams {
+    int L, win;          // context length (1 = plain gather) and half width
+    int fea_c;           // coefficients taken from every source row
+    int rot;             // source column of internal coefficient i: rot ? (i == 0 ? fea_c-1 : i-1) : i
+    int src_stride, dst_stride;
+};
+
+// STAGE: the tile's source rows t0-win .. t0+nr-1+win (all src_stride columns: one contiguous block of memory) are copied to
+// shared memory with coalesced loads, and the tile's output -- also one contiguous block -- is written element by element in
+// memory order.  Without STAGE (rows too wide for shared memory) the gather reads global memory directly.
+template <bool STAGE>
+__global__ void __launch_bounds__(256)
+k_stack(const StackParams S, BatchDesc bd, int tile_rows, const float *__restrict__ src, float *__restrict__ dst) {
+    extern __shared__ __align__(16) float sm_stack[];
+    const int2 tile = bd.tiles[blockIdx.x];
+    const int u = tile.x, t0 = tile.y;
+    const int T = bd.nframes[u];
+    const int nr = min(tile_rows, T - t0);
+    const int64_t row0 = bd.row_off[u];
+    const int L = S.L, win = S.win, fc = S.fea_c;
+    const int W = fc * L, ss = S.src_stride, ds = S.dst_stride;
+    // staged rows: [lo, hi]; the first row of a file also reads row 1 (start-up priming), the last one row T-1
+    const int lo = max(t0 - win, 0), hi = min(max(t0 + nr - 1 + win, L > 1 ? 1 : 0), T - 1);
+    if (STAGE) {
+        const float *g = src + (row0 + lo) * ss;
+        const int n = (hi - lo + 1) * ss;
+        for (int i = threadIdx.x; i < n; i += 256) sm_stack[i] = __ldg(g + i);
+        __syncthreads();
+    }
+    float *o = dst + (row0 + t0) * ds;
+    // a thread owns one output column e (a few when a row has more than 256 of them) and walks down the rows of its row
+    // group: the column's (coefficient, context position) pair is worked out once, and consecutive threads write
+    // consecutive floats of a row
+    const int RG = (W >= 256) ? 1 : 256 / W;
+    const int rg = (W >= 256) ? 0 : threadIdx.x / W;
+    if (rg >= RG) return;
+    for (int e = threadIdx.x - rg * W; e < W; e += 256) {
+        const int i = e / L, j = e - i * L;
+        const int col = S.rot ? (i == 0 ? fc - 1 : i - 1) : i;
+        const int col_own = S.rot ? (e == 0 ? fc - 1 : e - 1) : e;        // column e of the row itself (edge rows, e < fc)
+        for (int f = rg; f < nr; f += RG) {
+            const int t = t0 + f;
+            int k = t + j - win, c = col;
+            if (L > 1 && (t < win || t > T - 1 - win)) {                 // start-up / flush rows
+                if (t == 0) k = (j < win) ? 0 : (j <= win + 1 ? 1 : j - win);
+                k = min(max(k, 0), T - 1);
+                if (win == 1 && t == T - 1) k = T - 1;
+                if ((t == 0 || t >= T - win) && e < fc) { k = t; c = col_own; }
+            }
+            o[(int64_t)f * ds + e] = STAGE ? sm_stack[(k - lo) * ss + c] : __ldg(src + (row0 + k) * ss + c);
+        }
     }
 }
 

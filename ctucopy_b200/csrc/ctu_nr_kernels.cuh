@@ -115,7 +115,7 @@ static inline int build_nr_params(const ctu_config &c, int nr_mode, int vad_src,
     // latency of the feature chain as BATCH::save_frame sees it (src/io/batch.cc:172-204)
     V.latency = 0;
     std::string kind(c.fea_kind);
-    if ((kind == "dctc" || kind == "lpc") && c.fea_delta) {
+    if (kind != "trapdct" && kind != "lpa" && c.fea_delta) {      // deltas, or one stage used as the -fea_trap window
         int wins[3] = {c.d_win, c.a_win, c.t_win};
         for (int k = 0; k < c.n_order; k++) V.latency += wins[k];
     }

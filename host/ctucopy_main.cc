@@ -115,24 +115,29 @@ struct Writers {
             if (!scp) die("Cannot open output scp file for writing!");
         }
     }
-    int parmkind() const {
+    // htkOUT::new_file, src/io/out.cc:145-158.  Two reference quirks are part of the header: the "T bit" is the DECIMAL
+    // constant 100000 cut to 16 bits (:158), and with -fea_trap on sample input the first written row renames the kind
+    // to "spec" (:182), so every file after the first of the list carries base kind 8.
+    int parmkind(size_t list_index) const {
         std::string k(c.fea_kind);
+        if (c.fea_trap && !c.fea_in && list_index > 0) k = "spec";
         int kind = k == "lpc" ? 11 : k == "dctc" ? 6 : k == "trapdct" ? 9 : k == "spec" ? 8 : k == "logspec" ? 7 : 9;
-        bool c0 = c.fea_c0 && !(k == "lpa" || k == "spec" || k == "logspec");
+        std::string k0(c.fea_kind);
+        bool c0 = c.fea_c0 && !(k0 == "lpa" || k0 == "spec" || k0 == "logspec");
         if (c0) kind |= 020000;
         if (c.fea_E) kind |= 000100;
         if (c.fea_delta && c.n_order >= 1) kind |= 000400;
         if (c.fea_delta && c.n_order >= 2) kind |= 001000;
-        if (c.fea_delta && c.n_order == 3) kind |= 0100000;
+        if (c.fea_delta && c.n_order == 3) kind = (kind | 100000) & 0xffff;
         return kind;
     }
-    void features(const ListEntry &e, const float *rows, int64_t n) {
+    void features(const ListEntry &e, const float *rows, int64_t n, size_t list_index) {
         std::string fo(c.format_out);
         if (fo == "htk") {
             FILE *f = std::fopen(e.out.c_str(), "wb");
             if (!f) die("OUT: Cannot create output file!");
             uint32_t frames = (uint32_t)n, period = (uint32_t)std::floor(.5 + 10000000. * c.wshift / (double)c.fs);
-            uint16_t size = (uint16_t)(4 * dim), kind = (uint16_t)parmkind();
+            uint16_t size = (uint16_t)(4 * dim), kind = (uint16_t)parmkind(list_index);
             if (o.big_out) { frames = bswap32(frames); period = bswap32(period); size = bswap16(size); kind = bswap16(kind); }
             std::fwrite(&frames, 4, 1, f); std::fwrite(&period, 4, 1, f); std::fwrite(&size, 2, 1, f); std::fwrite(&kind, 2, 1, f);
             if (o.big_out) {
@@ -246,11 +251,25 @@ bool is_host_extension(const char *opt) {
 
 // samples a file will decode to, from its size / header only (used to balance shards and to
 // place each shard inside a list-wide external VAD file)
+// HTK parameter file header (htkIN::new_file, src/io/in.cc:630-650): only the vector size is used
+int htk_width(FILE *f, bool big) {
+    unsigned char b[12];
+    std::fseek(f, 0, SEEK_SET);
+    if (std::fread(b, 1, 12, f) != 12) return -1;
+    const int bytes = big ? ((b[8] << 8) | b[9]) : (b[8] | (b[9] << 8));
+    return bytes / 4;
+}
+
 int64_t count_samples(const HostOpts &o, const std::string &path) {
     FILE *f = std::fopen(path.c_str(), "rb");
     if (!f) die(o.format_in == "wave" ? "IN: Cannot open file!" : "IN: Cannot open data file!");
     std::fseek(f, 0, SEEK_END);
     int64_t size = (int64_t)std::ftell(f), n = 0;
+    if (o.format_in == "htk") {                  // rows: the reference reads whole vectors until the file ends
+        const int wd = htk_width(f, o.big_in);
+        if (wd <= 0) { std::fclose(f); die("IN: Cannot read the HTK header of " + path); }
+        n = (size - 12) / ((int64_t)wd * 4);
+    } else
     if (o.format_in == "raw") n = size / 2;
     else if (o.format_in == "alaw" || o.format_in == "mulaw") n = size;
     else if (o.format_in == "wave") {
@@ -433,6 +452,28 @@ void decode_into(const HostOpts &o, int fs, const std::string &path, int16_t *ds
     std::fclose(f);
 }
 
+// one HTK parameter file into dst[n rows x in_dim]: the first `width` floats of a row come from the file, the rest is 0.
+// The library takes rows of -nfeacoefs floats; the delta chain reads the first fea_ncepcoefs+1 of them.
+void read_features_into(const HostOpts &o, const ctu_config &cfg, const std::string &path, float *dst, int64_t n) {
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) die("IN: Cannot open data file!");
+    const int wd = htk_width(f, o.big_in), in_dim = cfg.nfeacoefs;
+    const bool chain = cfg.fea_delta && cfg.n_order > 0;
+    if (wd > in_dim) { std::fclose(f); die("IN: " + path + " has more columns than -nfeacoefs (the reference overruns its vector)"); }
+    if (chain ? wd < cfg.fea_ncepcoefs + 1 : wd != in_dim) {
+        std::fclose(f);
+        die("IN: " + path + (chain ? " has fewer than fea_ncepcoefs+1 columns" : " does not have -nfeacoefs columns"));
+    }
+    std::vector<uint32_t> row((size_t)wd);
+    for (int64_t t = 0; t < n; t++) {
+        if (std::fread(row.data(), 4, (size_t)wd, f) != (size_t)wd) { std::fclose(f); die("IN: Error reading input file!"); }
+        if (o.big_in) for (auto &v : row) v = bswap32(v);
+        std::memcpy(dst + t * in_dim, row.data(), (size_t)wd * 4);
+        for (int i = wd; i < in_dim; i++) dst[t * in_dim + i] = 0.f;
+    }
+    std::fclose(f);
+}
+
 struct Pinned {
     void *p = nullptr; uint64_t cap = 0;
     void reserve(uint64_t bytes) {
@@ -465,6 +506,8 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
     ctu_set_rand_offset(h, rand0);            // -dither: rand() values the list lines before this range have drawn
     const int dim = ctu_feature_dim(h);
     const bool sig = ctu_is_signal_output(h);
+    const int in_dim = ctu_input_dim(h);          // > 0: the list names feature files (-format_in htk), offsets count rows
+    const bool fea_in = in_dim > 0;
     const std::string fo(cfg.format_out);
     const bool per_file = (fo == "htk" || sig);
     Writers W(ho, cfg, dim);
@@ -478,7 +521,7 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
     {
         int64_t acc = 0;
         for (size_t i = 0; i < nfiles; i++) {
-            acc += nsamp[i];
+            acc += fea_in ? nsamp[i] * in_dim * 2 : nsamp[i];     // the same bytes per batch either way
             if (acc >= (int64_t(1) << 26) || (int64_t)(r0 + i + 1 - cuts.back()) >= (1 << 20)) { cuts.push_back(r0 + i + 1); acc = 0; }
         }
         if (cuts.back() != r1) cuts.push_back(r1);
@@ -511,10 +554,14 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
                 }
                 B.ext_pos = fr_before;
                 fr_before += (size_t)B.total;
-                B.pcm.reserve((uint64_t)(B.off[n] + 8) * 2);
+                B.pcm.reserve(fea_in ? (uint64_t)(B.off[n] + 1) * in_dim * 4 : (uint64_t)(B.off[n] + 8) * 2);
                 int16_t *pcm = (int16_t *)B.pcm.p;
+                float *fin = (float *)B.pcm.p;
                 double tr = now_s();
-                parallel_for(n, IO_THREADS, [&](size_t u) { decode_into(ho, cfg.fs, list[B.i0 + u].in, pcm + B.off[u], B.off[u + 1] - B.off[u]); });
+                parallel_for(n, IO_THREADS, [&](size_t u) {
+                    if (fea_in) read_features_into(ho, cfg, list[B.i0 + u].in, fin + B.off[u] * in_dim, B.off[u + 1] - B.off[u]);
+                    else decode_into(ho, cfg.fs, list[B.i0 + u].in, pcm + B.off[u], B.off[u + 1] - B.off[u]);
+                });
                 tmark("batch read+decode", tr);
                 { std::lock_guard<std::mutex> l(mu); B.state = 1; }
                 cv.notify_all();
@@ -536,7 +583,7 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
                 auto one = [&](size_t u) {
                     const ListEntry &e = list[B.i0 + u];
                     if (sig) W.waveform(e, wav + s0[u], s0[u + 1] - s0[u]);
-                    else W.features(e, fea + row0[u] * dim, B.rows[u]);
+                    else W.features(e, fea + row0[u] * dim, B.rows[u], B.i0 + u);
                     if (do_vad && vad_file) W.vad(e, vout + row0[u], B.frames[u]);
                 };
                 double tw = now_s();
@@ -565,6 +612,14 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
                 ev = extvad.data() + B.ext_pos;
             }
             double tg = now_s();
+            if (fea_in) {
+                ctu_plan *pl = nullptr;
+                if (ctu_plan_create(h, B.off.data(), n, &pl)) die(ctu_last_error(h));
+                if (ctu_plan_run_host_fea(pl, (const float *)B.pcm.p, (float *)B.fea.p)) { ctu_plan_destroy(pl); die(ctu_last_error(h)); }
+                ctu_plan_frames_per_utt(pl, B.frames.data());
+                ctu_plan_rows_per_utt(pl, B.rows.data());
+                ctu_plan_destroy(pl);
+            } else
             if (ctu_run(h, (const int16_t *)B.pcm.p, B.off.data(), n, ev, sig ? nullptr : (float *)B.fea.p, B.total, sig ? (int16_t *)B.wav.p : nullptr,
                         B.total_os, (uint8_t *)B.vnr.p, (uint8_t *)B.vout.p, B.frames.data(), B.rows.data()))
                 die(ctu_last_error(h));
@@ -678,7 +733,7 @@ void process_cmvn(const HostOpts &ho, const ctu_config &cfg, const std::vector<L
                 feabuf.reserve((uint64_t)total * fdim * 4);
                 if (ctu_plan_fetch(p, (float *)feabuf.p, nullptr, nullptr, nullptr)) die(ctu_last_error(h));
                 int64_t r0 = 0;
-                for (size_t u = 0; u < n; u++) { W.features(list[i0 + u], (const float *)feabuf.p + r0 * fdim, frames[u]); r0 += frames[u]; }
+                for (size_t u = 0; u < n; u++) { W.features(list[i0 + u], (const float *)feabuf.p + r0 * fdim, frames[u], i0 + u); r0 += frames[u]; }
             }
             ctu_plan_destroy(p);
         }

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CTU_ABI_VERSION 2
+#define CTU_ABI_VERSION 3
 #define CTU_STR 40
 #define CTU_FBDEF 1024
 
@@ -89,7 +89,11 @@ typedef struct ctu_config {
      * (floats like the reference, src/io/opts.h); cms_exp_coef = 1 - 2*wshift_ms/fea_Z_exp is derived.   */
     float   fea_Z_exp, fea_Z_block;
     float   cms_exp_coef;
-    int32_t stat_cmvn, apply_cmvn;   /* CMVN passes: recognised, not built (CTU_ERR_UNSUPPORTED)       */
+    int32_t stat_cmvn, apply_cmvn;   /* CMVN passes: the host drives them (ctu_plan_colsums / _normalise)  */
+    /* context stacking and feature-file input (src/io/opts.cc:694-704, 786; src/io/in.cc:623-690)         */
+    int32_t fea_trap, trap_win;      /* -fea_trap N: rows t-(N-1)/2 .. t+(N-1)/2 stacked per coefficient     */
+    int32_t fea_in;                  /* 1 = -format_in htk: the input is a feature matrix, not PCM           */
+    int32_t nfeacoefs;               /* -nfeacoefs: floats per input feature row                             */
 } ctu_config;
 
 typedef struct ctu_handle ctu_handle;
@@ -119,6 +123,7 @@ const char *ctu_last_error(const ctu_handle *h);              /* h may be NULL: 
 int ctu_design_filter_bank(const ctu_config *cfg, double *mat, int32_t *lo, int32_t *hi, int32_t *nb);
 
 int ctu_feature_dim(const ctu_handle *h);      /* floats per output row, writer order (0 in waveform mode) */
+int ctu_input_dim(const ctu_handle *h);        /* floats per INPUT row of a feature-input handle (-format_in htk), else 0 */
 int ctu_is_signal_output(const ctu_handle *h); /* 1 when format_out is raw|wave                             */
 int ctu_num_bands(const ctu_handle *h);        /* FB::size                                                  */
 /* FB::mat as designed (src/fea/fb.cc:255-457): mat[nb*wfftby2] row-major, lo/hi[nb].     */
@@ -136,7 +141,8 @@ int ctu_profile_enable(ctu_handle *h, int on);     /* also clears previous recor
 int ctu_profile_count(const ctu_handle *h);
 int ctu_profile_get(ctu_handle *h, int idx, const char **name, float *ms);
 
-/* ---- plan: a list of utterances (sample offsets into one concatenated PCM buffer) ----- */
+/* ---- plan: a list of utterances (sample offsets into one concatenated PCM buffer; for a
+ * feature-input handle, ROW offsets into one concatenated [rows x ctu_input_dim] matrix) ---- */
 int ctu_plan_create(ctu_handle *h, const int64_t *utt_offsets /* n_utts+1 */, int32_t n_utts, ctu_plan **out);
 void ctu_plan_destroy(ctu_plan *p);
 int64_t ctu_plan_total_frames(const ctu_plan *p);   /* sum of T_u                                 */
@@ -167,6 +173,13 @@ int ctu_plan_run_device(ctu_plan *p, const int16_t *d_pcm, const uint8_t *d_ext_
  * utterances on internal streams; returns when the outputs are complete.               */
 int ctu_plan_run_host(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad, float *features,
                       int16_t *waveform, uint8_t *vad_nr, uint8_t *vad_out);
+
+/* Feature-file input (-format_in htk; htkIN::get_frame src/io/in.cc:682-690 -> deltaFEA src/fea/fea_delta.cc:70-206
+ * -> cms_POST src/fea/post_impl.cc:203-209 -> htkOUT::save_frame src/io/out.cc:177-179): rows of ctu_input_dim()
+ * floats in, rows of ctu_feature_dim() floats out (file column order, no reordering).  Device / host variants as
+ * above; `keep` leaves the result on the device for ctu_plan_colsums / _normalise / _fetch.                       */
+int ctu_plan_run_device_fea(ctu_plan *p, const float *d_fea_in, float *d_features, void *stream);
+int ctu_plan_run_host_fea(ctu_plan *p, const float *fea_in, float *features /* NULL = keep on the device */);
 
 /* The same in steps, for callers that post-process on the device before fetching: run with the results
  * left on the device, [ctu_plan_colsums / ctu_plan_normalise], then ctu_plan_fetch.                  */

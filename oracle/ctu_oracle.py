@@ -84,6 +84,7 @@ class Opts:
     fea_delta: bool = False
     n_order: int = 0
     fea_trap: bool = False
+    nfeacoefs: int = 13
     trap_win: int = 5
     vad_apply_mode: str = "none"
     vad_out_mode: str = "none"
@@ -183,6 +184,7 @@ def _parse_one(o: Opts, l: str, r: Optional[str]) -> None:
         if not o.fea_delta:
             o.fea_trap, o.trap_win, o.fea_delta, o.n_order = True, int(r), True, 1
             o.d_win = (o.trap_win - 1) // 2
+    elif l == "-nfeacoefs": o.nfeacoefs = int(r)
     elif l == "-fs": o.fs = int(r)
     elif l == "-dither": o.dither = f(r)
     elif l == "-remove_dc": o.remove_dc = _onoff(r, o.remove_dc)
@@ -786,13 +788,16 @@ class DeltaFEA:
     utterances shorter than win+2 rows, where the output depends on never-written ring
     rows (zeros in a fresh process: Mat zero-fills all but column 0, src/base/types.h:72)."""
 
-    def __init__(self, fea_c: int, n_order: int, delta_w: int):
+    def __init__(self, fea_c: int, n_order: int, delta_w: int, trap: bool = False):
         if delta_w < 1:
-            raise ValueError("FEA: Delta window size must be > 1!")
+            raise ValueError("FEA: Trap window size must be >= 3!" if trap else "FEA: Delta window size must be > 1!")
         self.fea_c, self.delta_w, self.dwlen, self.n_order = fea_c, delta_w, 2 * delta_w + 1, n_order
         self.nfea = fea_c * (n_order - 1)
+        self.trap = trap
+        if trap:                                   # src/fea/fea_delta.cc:40 (after nfea was taken from n_order = 2)
+            self.n_order = self.dwlen
         self.buf = np.zeros((self.dwlen, self.nfea))
-        self.fvec = np.zeros(fea_c * n_order)
+        self.fvec = np.zeros(fea_c * self.n_order)
         self.den = 2.0 * sum(i * i for i in range(1, delta_w + 1))
         self.new_file()
 
@@ -811,6 +816,9 @@ class DeltaFEA:
 
     def _delta(self):
         d = self.buf[(self.start + np.arange(self.dwlen)) % self.dwlen]
+        if self.trap:                              # deltaFEA::trap, src/fea/fea_delta.cc:166-176: fvec[i*dwlen+j] = ring row j, column i
+            self.fvec[:] = d[:, : self.fea_c].T.reshape(-1)
+            return
         lo, hi = self.fea_c * (self.n_order - 2), self.fea_c * (self.n_order - 1)
         x = np.zeros(hi - lo)
         for i in range(1, self.delta_w + 1):
@@ -833,7 +841,8 @@ class DeltaFEA:
         fea_x = self.dwlen - 1 if self.start == 0 else self.start - 1
         self.buf[fea_x] = f[: self.nfea]
         self._delta()
-        self.fvec[: self.nfea] = self.buf[(fea_x - self.delta_w) % self.dwlen]
+        if not self.trap:                          # src/fea/fea_delta.cc:120-124; NOT guarded in the fill / flush branches
+            self.fvec[: self.nfea] = self.buf[(fea_x - self.delta_w) % self.dwlen]
         self.end = self.start
         self.start = (self.start + 1) % self.dwlen
         self.frame += 1
@@ -860,7 +869,7 @@ def add_deltas(C: np.ndarray, o: Opts) -> np.ndarray:
     wins = [o.d_win, o.a_win, o.t_win][: o.n_order]
     n = len(wins)
     fea_c = C.shape[1]
-    st = [DeltaFEA(fea_c, k + 2, wins[k]) for k in range(n)]
+    st = [DeltaFEA(fea_c, k + 2, wins[k], trap=o.fea_trap) for k in range(n)]
     out = []
 
     def push(level, vec):
@@ -875,7 +884,32 @@ def add_deltas(C: np.ndarray, o: Opts) -> np.ndarray:
         src = (C[-1] if C.shape[0] else np.zeros(fea_c)) if level == 0 else st[level - 1].fvec
         while st[level].flush_frame(src):
             push(level + 1, st[level].fvec)
-    return np.array(out).reshape(len(out), fea_c * (n + 1))
+    return np.array(out).reshape(len(out), fea_c * (st[-1].n_order if o.fea_trap else n + 1))
+
+
+def trap_stack_closed_form(C: np.ndarray, win: int) -> np.ndarray:
+    """What the CUDA path computes for `-fea_trap 2*win+1` (deltaFEA in trap mode, T >= win + 2 rows):
+    out[t, i*L + j] = C[clip(t + j - win, 0, T-1), i], L = 2 win + 1, plus the reference's edge behaviour:
+      * the ring is primed with  row0 x win, row1 x 2, row2, ...  (src/fea/fea_delta.cc:73-77), so the FIRST output row
+        stacks rows [0]*win + [1, 1, 2, .., win] instead of [0]*(win+1) + [1, .., win];
+      * with win == 1 the flush replica lands on the slot of the last real row (`index=end`, :182-185): the LAST output
+        row stacks row T-1 three times;
+      * in the first row and in the `win` flush rows the first fea_c elements are then overwritten with that row's own
+        columns C[t, :] (the copies `ofvec[i] = b(...)` at :88-90 and :197-199 are not guarded by !fea_trap).
+    tests/test_oracle_vs_golden.py checks this against the state machine and the reference binary."""
+    T, fea_c = C.shape
+    L = 2 * win + 1
+    out = np.empty((T, fea_c * L))
+    for t in range(T):
+        idx = np.clip(t + np.arange(L) - win, 0, T - 1)
+        if t == 0:
+            idx = np.array(([0] * win + [1, 1] + list(range(2, win + 1)))[:L])
+        if win == 1 and t == T - 1:
+            idx[:] = T - 1
+        out[t] = C[idx].T.reshape(-1)
+        if t == 0 or t >= T - win:
+            out[t, :fea_c] = C[t]
+    return out
 
 
 def add_deltas_closed_form(C: np.ndarray, o: Opts) -> np.ndarray:
@@ -1284,7 +1318,7 @@ def writer_order(F: np.ndarray, o: Opts) -> np.ndarray:
     """htkOUT::save_frame column order, src/io/out.cc:183-202: spec/logspec/trapdct as is;
     lpc/dctc blocks are written c1..cN then c0.  (fea_E / fea_c0 off are handled by the
     caller: E appended last, see out_dim.)"""
-    if o.fea_kind in ("spec", "logspec", "trapdct"):
+    if o.fea_kind in ("spec", "logspec", "trapdct") or o.fea_trap:   # -fea_trap: kind forced to "spec", src/io/out.cc:182
         return F
     n = o.fea_ncepcoefs + 1
     cols = []
@@ -1470,16 +1504,23 @@ def run_pipeline(pcm: np.ndarray, o: Opts, ext_vad: Optional[np.ndarray] = None,
     else:
         raise ValueError("FEA: Unknown feature kind!")
     internal = F
-    if o.n_order > 0 and k in ("dctc", "lpc"):
-        F = add_deltas(F, o)
+    if o.fea_delta and o.n_order > 0:
+        # deltaFEA works on the first fea_ncepcoefs+1 elements of whatever vector FEA produced (src/fea/fea_delta.cc:23,
+        # 31) and the writer then sees a vector of (ncep+1)*(n_order+1) [or *(2 win + 1) when stacking] elements
+        fea_c = o.fea_ncepcoefs + 1
+        if k == "lpa" or F.shape[1] < fea_c:
+            raise ValueError("FEA: deltas / stacking read beyond the feature vector for this kind")
+        if k == "trapdct":
+            raise ValueError("CTU: trapdct with deltas: the reference never flushes the TRAP ring (src/io/batch.cc:253), the last rows are lost")
+        if o.fea_trap and k in ("dctc", "lpc") and not o.fea_c0:
+            raise ValueError("CTU: -fea_trap with -fea_c0 off: the reference writes past its output buffer (src/io/out.cc:184)")
+        F = add_deltas(F[:, :fea_c], o)
     if o.cms_exp_coef > 0 or o.fea_Z_block > 0:
         F = cms(F, o)
     out = writer_order(F, o) if k != "lpa" else F[:, 1:]
-    lat = 0
-    if k in ("dctc", "lpc"):
-        lat = sum([o.d_win, o.a_win, o.t_win][: o.n_order])
+    lat = sum([o.d_win, o.a_win, o.t_win][: o.n_order]) if o.fea_delta else 0
     if k == "trapdct":
-        lat = (o.fea_trapdct_traplen + 1) // 2 - 1
+        lat += (o.fea_trapdct_traplen + 1) // 2 - 1
     do_vad = o.vad_apply_mode != "none" or o.vad_out_mode != "none"
     if o.fea_E:
         # rows also wait in the VAD module's majority filter, (order-1)/2 frames (src/vad/vad.h:126-175)
@@ -1496,20 +1537,50 @@ def run_pipeline(pcm: np.ndarray, o: Opts, ext_vad: Optional[np.ndarray] = None,
     return res
 
 
+def run_features(Fin: np.ndarray, o: Opts) -> np.ndarray:
+    """`-format_in htk`: an existing feature file through deltas / stacking / CMS (BATCH::BATCH src/io/batch.cc:55-60,
+    process_frame :217-218, htkIN src/io/in.cc:623-690).  The reader's vector holds -nfeacoefs elements; deltaFEA
+    takes its first fea_ncepcoefs+1; the writer copies the result in the order it comes (src/io/out.cc:177-179) and
+    cuts it to get_fea_size() elements (src/io/out.cc:95-112)."""
+    if o.fea_E or o.vad_apply_mode != "none" or o.vad_out_mode != "none":
+        raise ValueError("CTU: no spectrum / energy exists for feature-file input")
+    if o.fea_kind == "dctc" and not o.fea_rawenergy:
+        raise ValueError("CTU: the reference dereferences a null NR here (src/io/batch.cc:108)")
+    F = np.asarray(Fin, dtype=np.float64)
+    if F.shape[1] > o.nfeacoefs:
+        raise ValueError("IN: feature file wider than -nfeacoefs")
+    if o.fea_delta and o.n_order > 0:
+        fea_c = o.fea_ncepcoefs + 1
+        if F.shape[1] < fea_c:
+            raise ValueError("IN: feature file narrower than fea_ncepcoefs+1")
+        F = add_deltas(F[:, :fea_c], o)
+    elif F.shape[1] != o.nfeacoefs:
+        raise ValueError("IN: feature file width differs from -nfeacoefs")
+    if (o.cms_exp_coef > 0 or o.fea_Z_block > 0) and o.fea_delta and o.n_order > 0:
+        F = cms(F, o)                                # the plain-copy branch never calls POST (src/io/batch.cc:223-227)
+    size = F.shape[1]
+    if o.fea_kind == "lpa" or (o.fea_kind in ("lpc", "dctc") and not o.fea_c0):
+        size -= 1
+    return F[:, :size].astype(np.float32)
+
+
 # --------------------------------------------------------------------------------------
 # file formats  (src/io/out.cc, src/io/pfile.cc) -- byte-exact writers used by the tests
 # --------------------------------------------------------------------------------------
 
 
-def htk_parmkind(o: Opts) -> int:
-    """htkOUT::new_file, src/io/out.cc:145-158."""
+def htk_parmkind(o: Opts, file_index: int = 0) -> int:
+    """htkOUT::new_file, src/io/out.cc:145-158.  With -fea_trap (raw input) the first written row renames the kind to
+    "spec" (src/io/out.cc:182), so every file after the first of a process carries base kind 8."""
     kind = {"lpc": 11, "dctc": 6, "trapdct": 9, "spec": 8, "logspec": 7}.get(o.fea_kind, 9)
+    if o.fea_trap and file_index > 0 and o.format_in != "htk":
+        kind = 8
     c0 = o.fea_c0 and o.fea_kind not in ("lpa", "spec", "logspec")
     if c0: kind |= 0o20000
     if o.fea_E: kind |= 0o100
     if o.fea_delta and o.n_order >= 1: kind |= 0o400
     if o.fea_delta and o.n_order >= 2: kind |= 0o1000
-    if o.fea_delta and o.n_order == 3: kind |= 0o100000
+    if o.fea_delta and o.n_order == 3: kind = (kind | 100000) & 0xFFFF   # DECIMAL 100000 in the reference (src/io/out.cc:158), cut to 16 bits
     return kind
 
 

@@ -76,7 +76,15 @@ def run_reference(args: Sequence[str], pcms: List[np.ndarray], *, opt: str = "O0
     with tempfile.TemporaryDirectory() as d:
         groups = [[i] for i in range(len(pcms))] if one_per_process else [list(range(len(pcms)))]
         for i, p in enumerate(pcms):
-            np.asarray(p).astype(endian_in + "i2").tofile(os.path.join(d, "u%d.raw" % i))
+            p = np.asarray(p)
+            if p.dtype.kind == "f":
+                # a feature matrix: written as an HTK parameter file (input of `-format_in htk`, src/io/in.cc:630-680;
+                # only the vector size of the header is used by the reader)
+                with open(os.path.join(d, "u%d.raw" % i), "wb") as fh:
+                    fh.write(struct.pack(endian_in + "IIHH", p.shape[0], 100000, 4 * p.shape[1], 6))
+                    fh.write(p.astype(endian_in + "f4").tobytes())
+                continue
+            p.astype(endian_in + "i2").tofile(os.path.join(d, "u%d.raw" % i))
         if ext_vad_bytes is not None:
             open(os.path.join(d, "vadin.bin"), "wb").write(ext_vad_bytes)
         for gi, g in enumerate(groups):

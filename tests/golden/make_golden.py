@@ -107,6 +107,16 @@ CASES = {
     "mfcc_dc1": (B + MF + ["-remove_dc1", "on", "-format_out", "htk"], "htk", {}),
     "mfcc_dc1_w32s8": (B + ["-preset", "mfcc", "-preem", "0", "-remove_dc1", "on", "-remove_dc", "off", "-w", "32", "-s", "8", "-nr_mode", "exten",
                            "-format_out", "htk"], "htk", {}),
+    # context stacking (-fea_trap N, src/fea/fea_delta.cc:166-176) and deltas of non-cepstral vectors: deltaFEA takes the first
+    # fea_ncepcoefs+1 elements of whatever FEA produced
+    "mfcc_trap5": (B + MF + ["-fea_trap", "5", "-format_out", "htk"], "htk", {}),
+    "mfcc_trap3_E": (B + MF + ["-fea_trap", "3", "-fea_E", "on", "-format_out", "htk"], "htk", {}),
+    "logspec_trap7": (B + MF + ["-fea_kind", "logspec", "-fea_trap", "7", "-format_out", "htk"], "htk", {}),
+    "logspec_d_a": (B + MF + ["-fea_kind", "logspec", "-fea_delta", "d_a", "-format_out", "htk"], "htk", {}),
+    "spec22_d": (B + MF + ["-fea_kind", "spec", "-fea_ncepcoefs", "22", "-fea_delta", "d", "-format_out", "htk"], "htk", {}),
+    "plp_trap5_cms": (B + ["-preset", "plpc", "-fea_trap", "5", "-fea_Z_exp", "500", "-format_out", "htk"], "htk", {}),
+    "mfcc_trap5_vad_drop": (B + MF + ["-fea_trap", "5", "-format_out", "htk", "-vad_out_mode", "vad", "-vad_apply_mode", "drop"],
+                            "htk", {"vad_out": True}),
     "logspec32k_40": (["-fs", "32000"] + B[2:] + MF + ["-fea_kind", "logspec", "-fb_definition", "40filters", "-format_out", "htk"], "htk", {}),
 }
 
@@ -116,6 +126,21 @@ CMVN_CASES = {
     "cmvn_3stage_d_a": (B + MF + ["-format_out", "htk", "-fea_delta", "d_a", "-apply_cmvn", "{STAT}"], [0, 1, 4, 5], ["spkA", "spkA", "spkB", "spkB"]),
     # -stat_cmvn: statistics only
     "cmvn_stat_plp": (B + ["-preset", "plpc", "-format_out", "htk", "-stat_cmvn", "{STAT}"], [0, 4, 1, 5, 2], ["s1", "s2", "s1", "s2", "s3"]),
+}
+
+
+# feature-file input (-format_in htk, src/io/in.cc:623-690; BATCH::BATCH src/io/batch.cc:55-60): the input of every case is
+# the committed golden "mfcc30_static" (13 columns: c1..c12, c0), one file per reference process
+BH = ["-fs", "16000", "-format_in", "htk", "-fea_ncepcoefs", "12"]
+FEAIN_SOURCE = "mfcc30_static"
+FEAIN_CASES = {
+    "feain_copy": BH + ["-fea_kind", "lpc", "-format_out", "htk"],
+    "feain_lpc_d_a": BH + ["-fea_kind", "lpc", "-fea_delta", "d_a", "-format_out", "htk"],
+    "feain_dctc_d_a_t_noc0": BH + ["-fea_kind", "dctc", "-fea_rawenergy", "on", "-fea_delta", "d_a_t", "-fea_c0", "off", "-format_out", "htk"],
+    "feain_spec_trap5": BH + ["-fea_kind", "spec", "-fea_trap", "5", "-format_out", "htk"],
+    "feain_lpc_d_cms": BH + ["-fea_kind", "lpc", "-fea_delta", "d", "-fea_Z_exp", "400", "-format_out", "htk"],
+    "feain_lpa_d8": BH + ["-fea_kind", "lpa", "-fea_ncepcoefs", "8", "-fea_delta", "d", "-d_win", "3", "-format_out", "htk"],
+    "feain_trap3_be": BH + ["-fea_kind", "logspec", "-fea_trap", "3", "-format_out", "htk", "-endian_out", "big"],
 }
 
 
@@ -194,6 +219,20 @@ def main():
                     dd["out%d" % i] = np.frombuffer(open(pth, "rb").read(), dtype=np.uint8)
             np.savez_compressed(os.path.join(OUT, name + ".npz"), **dd)
             print(name, "ok")
+    # feature-file input
+    for name, args in FEAIN_CASES.items():
+        if sys.argv[1:] and name not in sys.argv[1:]:
+            continue
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import golden_util as gu
+        src = gu.Case(FEAIN_SOURCE)
+        d = {"args": np.array(json.dumps(args)), "kind": np.array("htk_be" if "big" in args else "htk"), "source": np.array(FEAIN_SOURCE)}
+        for i in range(len(utts)):
+            r = rr.run_reference(args, [src.payload(i).astype(np.float32)])
+            assert r["returncode"] == 0 and r["outputs"][0] is not None, (name, i, r["stderr"])
+            d["out%d" % i] = np.frombuffer(r["outputs"][0], dtype=np.uint8)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+        print(name, "ok")
     if sys.argv[1:]:
         return       # only the named cases were asked for
     # filter-bank design goldens via the undocumented -fb_printself (src/fea/fb.cc:449-456)

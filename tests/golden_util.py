@@ -20,7 +20,12 @@ def inputs():
 
 
 def case_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("inputs.npz", "fb_design.npz") and not f.startswith("cmvn_"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("inputs.npz", "fb_design.npz") and not f.startswith("cmvn_") and not f.startswith("feain_"))
+
+
+def feain_case_names():
+    """Feature-file input goldens (-format_in htk): Case(name).source names the golden whose payloads are the inputs."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.startswith("feain_") and f.endswith(".npz"))
 
 
 def cmvn_case(name):
@@ -37,6 +42,7 @@ class Case:
         self.name = name
         self.args = json.loads(str(z["args"]))
         self.kind = str(z["kind"])
+        self.source = str(z["source"]) if "source" in z.files else None
         self.n = len(inputs())
         self.raw = [z["out%d" % i].tobytes() for i in range(self.n)]
         self.aux = [z["aux%d" % i].tobytes() if ("aux%d" % i) in z.files else None for i in range(self.n)]

@@ -167,3 +167,41 @@ def test_cli_cmvn_statistics_and_normalised_features(tmp_path, name):
     if "-apply_cmvn" in args:
         pr = subprocess.run([EXE] + a + ["-S", str(tmp_path / "list.scp")], capture_output=True)
         assert pr.returncode == 255 and b"existing statistics file" in pr.stderr
+
+
+def test_cli_feature_file_input_and_stacking_headers(tmp_path):
+    """-format_in htk through the command line: stacked rows byte-identical to the reference's files (a pure gather), delta
+    rows within tolerance with byte-exact headers -- including the reference's parmKind quirks (the decimal "T bit", and
+    "spec" as the kind of every file after the first with -fea_trap on sample input)."""
+    tmp = str(tmp_path)
+    for name in ("feain_spec_trap5", "feain_trap3_be", "feain_copy", "feain_dctc_d_a_t_noc0", "feain_lpc_d_cms"):
+        c = gu.Case(name)
+        src = gu.Case(c.source)
+        idx = [0, 4, 5]
+        with open(os.path.join(tmp, "list.scp"), "w") as fh:
+            for j, i in enumerate(idx):
+                open(os.path.join(tmp, "f%d.htk" % j), "wb").write(src.raw[i])
+                fh.write("%s/f%d.htk %s/g%d.htk\n" % (tmp, j, tmp, j))
+        pr = subprocess.run([EXE] + c.args + ["-S", os.path.join(tmp, "list.scp")], capture_output=True, cwd=tmp)
+        assert pr.returncode == 0, pr.stderr.decode()
+        be = ">" if c.kind == "htk_be" else "<"
+        for j, i in enumerate(idx):
+            got, want = open(os.path.join(tmp, "g%d.htk" % j), "rb").read(), c.raw[i]
+            assert len(got) == len(want) and got[:12] == want[:12], (name, i)
+            if "trap" in name or name == "feain_copy":
+                assert got == want, (name, i)
+            else:
+                a, b = rr.parse_htk(got, be)[1], rr.parse_htk(want, be)[1]
+                assert np.all(np.abs(a - b) <= 1e-4 * np.abs(b) + 1e-3), (name, i)
+    # sample input + stacking, several files in one list: compare with the reference run on the same list
+    if rr.ref_binary("O0") is None:
+        return
+    c = gu.Case("mfcc_trap5")
+    utts = [gu.inputs()[i] for i in (0, 4, 5)]
+    run_cli(tmp, c.args, utts)
+    ref = rr.run_reference(c.args, utts)
+    for j in range(3):
+        got, want = open(os.path.join(tmp, "u%d.out" % j), "rb").read(), ref["outputs"][j]
+        assert got[:12] == want[:12], ("parmKind of file %d" % j, got[:12], want[:12])
+        a, b = rr.parse_htk(got)[1], rr.parse_htk(want)[1]
+        assert np.all(np.abs(a - b) <= 1e-4 * np.abs(b) + 1e-3)

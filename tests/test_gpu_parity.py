@@ -262,3 +262,72 @@ def test_dither_stream_continues_through_a_list():
         ref = co.run_pipeline(u, o, rand_offset=off)
         off += (o.window - o.wshift) + ref.nframes * o.wshift
         check_features("dither", j, res.utt_features(j), ref.features, "dctc")
+
+
+# ---- context stacking, deltas of spectral vectors, feature-file input ---------------------------------------
+
+@pytest.mark.parametrize("name", gu.feain_case_names())
+def test_cuda_feature_input_matches_reference_golden(name):
+    """-format_in htk: rows of an existing feature file through deltas / stacking / CMS (ctu_plan_run_host_fea).  Gathers
+    (copy, stacking) are bit-exact; the delta regression is fp32 on the device, fp64 in the reference."""
+    c = gu.Case(name)
+    args = c.oracle_args()
+    o = co.parse_args(args)
+    src = gu.Case(c.source)
+    mats = [np.ascontiguousarray(src.payload(i), dtype=np.float32) for i in range(len(gu.inputs()))]
+    idx = list(range(len(mats)))
+    if o.fea_delta and o.n_order > 0:
+        mw = max([o.d_win, o.a_win, o.t_win][: o.n_order])
+        short = [i for i in idx if mats[i].shape[0] < mw + 2]
+        for i in short:
+            with pytest.raises(cb.CtuError):
+                cb.extract_features(args, [mats[i]])
+        idx = [i for i in idx if i not in short]
+    res = cb.extract_features(args, [mats[i] for i in idx])
+    exact = o.fea_trap or not o.fea_delta
+    for j, i in enumerate(idx):
+        got, want = res.utt_features(j), c.payload(i)
+        if exact and not (o.cms_exp_coef > 0):
+            assert got.shape == want.shape and np.array_equal(got, want), (name, i)
+        else:
+            check_features(name, i, got, want, "dctc")
+
+
+def test_stacking_large_batch_matches_closed_form_bit_exactly():
+    """-fea_trap on feature input, 300 ragged utterances in one plan, windows from 3 to 31 rows: a pure gather, so the
+    device result must equal the oracle's closed form (= the reference's state machine) bit for bit.  Also through the
+    device-resident entry point."""
+    import torch
+    rng = np.random.default_rng(5)
+    for N, dim in ((3, 13), (9, 13), (31, 20)):
+        w = (N - 1) // 2
+        mats = [rng.standard_normal((int(rng.integers(w + 2, 400)), dim)).astype(np.float32) for _ in range(300)]
+        args = ["-fs", "16000", "-format_in", "htk", "-nfeacoefs", str(dim), "-fea_ncepcoefs", str(dim - 1), "-fea_kind", "spec",
+                "-fea_trap", str(N), "-format_out", "htk"]
+        res = cb.extract_features(args, mats)
+        for j, m in enumerate(mats):
+            want = co.trap_stack_closed_form(m.astype(np.float64), w).astype(np.float32)
+            assert np.array_equal(res.utt_features(j), want), (N, j)
+        hd = cb.Handle(args)
+        plan = hd.plan([m.shape[0] for m in mats])
+        x = torch.from_numpy(np.concatenate(mats)).cuda()
+        y = torch.empty((plan.total_frames, hd.feature_dim), dtype=torch.float32, device="cuda")
+        plan.run_device_fea(x.data_ptr(), y.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(y.cpu().numpy(), res.features)
+        plan.close(); hd.close()
+
+
+def test_feature_input_refusals():
+    """Configurations in which the reference crashes or reads memory it never wrote are refused, not imitated."""
+    B_ = ["-fs", "16000", "-format_in", "htk", "-format_out", "htk"]
+    for extra in (["-fea_kind", "dctc"],                                   # null NR dereferenced, src/io/batch.cc:108
+                  ["-fea_kind", "lpc", "-fea_E", "on"],                    # no energy exists
+                  ["-fea_kind", "lpc", "-vad_out_mode", "vad"],            # no spectrum for the VAD module
+                  ["-fea_kind", "lpc", "-fea_delta", "d", "-fea_ncepcoefs", "20"]):   # the chain reads 21 of 13 columns
+        with pytest.raises(cb.CtuError):
+            cb.Handle(B_ + extra)
+    with pytest.raises(cb.CtuError):
+        cb.Handle(B[:2] + ["-format_in", "raw", "-preset", "mfcc", "-fea_kind", "trapdct,11,3", "-fea_delta", "d", "-format_out", "htk"])
+    with pytest.raises(cb.CtuError):
+        cb.Handle(B + ["-preset", "mfcc", "-fea_trap", "5", "-fea_c0", "off", "-format_out", "htk"])

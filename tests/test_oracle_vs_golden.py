@@ -86,6 +86,43 @@ def test_delta_closed_form_equals_state_machine():
             np.testing.assert_allclose(a, b, rtol=0, atol=1e-13)
 
 
+def test_stacking_closed_form_equals_state_machine():
+    """-fea_trap N: the closed form the CUDA kernel implements (first-row priming, win == 1 flush quirk, the un-guarded
+    copies over the first fea_c elements of the first and the flush rows) equals the reference's state machine."""
+    rng = np.random.default_rng(1)
+    for N in (3, 5, 7, 9, 11, 15):
+        w = (N - 1) // 2
+        for T in list(range(w + 2, w + 14)) + [61]:
+            for fc in (1, 3, 13):
+                C = rng.standard_normal((T, fc))
+                o = co.parse_args(["-fs", "16000", "-preset", "mfcc", "-fea_trap", str(N)])
+                a = co.add_deltas(C, o); b = co.trap_stack_closed_form(C, w)
+                assert a.shape == b.shape == (T, fc * N) and np.array_equal(a, b), (N, T, fc)
+
+
+@pytest.mark.parametrize("name", gu.feain_case_names())
+def test_oracle_feature_input_matches_reference_binary(name):
+    """-format_in htk (deltas / stacking / CMS on existing feature files): bit-identical float32 rows and header."""
+    c = gu.Case(name)
+    o = co.parse_args(c.oracle_args())
+    src = gu.Case(c.source)
+    for i in range(len(gu.inputs())):
+        got = co.run_features(src.payload(i), o)
+        want = c.payload(i)
+        assert got.shape == want.shape, (name, i, got.shape, want.shape)
+        assert np.array_equal(got, want), (name, i, float(np.abs(got - want).max()))
+        assert co.write_htk(got, o) == c.raw[i], (name, i, "HTK header / payload bytes differ")
+
+
+def test_htk_header_quirks():
+    """parmKind as the reference writes it: the T bit is the decimal constant 100000 cut to 16 bits (src/io/out.cc:158), and
+    with -fea_trap every file after the first of a process is labelled "spec" (src/io/out.cc:182)."""
+    c = gu.Case("mfcc26_d_a_t_win3"); o = co.parse_args(c.oracle_args())
+    assert co.write_htk(co.run_pipeline(gu.inputs()[0], o).features, o) == c.raw[0]
+    o = co.parse_args(gu.Case("mfcc_trap5").oracle_args())
+    assert co.htk_parmkind(o, 0) == 0o20000 + 0o400 + 6 and co.htk_parmkind(o, 1) == 0o20000 + 0o400 + 8
+
+
 def test_frame_count_edge_cases():
     o = co.parse_args(["-fs", "16000", "-preset", "mfcc", "-format_out", "htk"])
     assert co.num_frames(400, o) == 1 and co.num_frames(399, o) == 0 and co.num_frames(240, o) == 0
