@@ -55,8 +55,17 @@ def draw(rng):
     if kind in ("dctc", "lpc", "lpa"):
         order = ncep if kind == "lpa" else rng.choice([ncep, ncep, 10, 14])
         a += ["-fea_ncepcoefs", str(ncep), "-fea_lporder", str(order), "-fea_lifter", rng.choice(["22", "0", "1", "30"]), "-fea_c0", "on"]
-    if kind in ("dctc", "lpc") and rng.random() < 0.6:
-        a += ["-fea_delta", rng.choice(["d", "d_a", "d_a_t"]), "-d_win", rng.choice(["2", "3"]), "-a_win", rng.choice(["2", "1"]), "-t_win", "2"]
+    if kind in ("spec", "logspec") and rng.random() < 0.5:
+        # the delta chain / context stacking take the first ncep+1 bands
+        a += ["-fea_ncepcoefs", str(rng.choice([8, 12, 14]))]
+        kind_chain = True
+    else:
+        kind_chain = kind in ("dctc", "lpc")
+    if kind_chain and rng.random() < 0.6:
+        if rng.random() < 0.35:
+            a += ["-fea_trap", rng.choice(["3", "5", "7", "11"])]
+        else:
+            a += ["-fea_delta", rng.choice(["d", "d_a", "d_a_t"]), "-d_win", rng.choice(["2", "3"]), "-a_win", rng.choice(["2", "1"]), "-t_win", "2"]
     nr = rng.choice(["none", "none", "exten", "exten", "fwss", "hwss", "2fwss"])
     if nr != "none":
         a += ["-nr_mode", nr, "-nr_p", rng.choice(["0.95", "0.9"]), "-nr_a", rng.choice(["1", "2"]), "-nr_b", rng.choice(["1", "1.5"]),
@@ -67,7 +76,7 @@ def draw(rng):
             a += ["-nr_when", "afterFB"]
     if kind != "trapdct" and rng.random() < 0.25:
         a += ["-fea_E", "on"] + (["-fea_rawenergy", "on"] if rng.random() < 0.3 else [])
-    if kind in ("dctc", "lpc") and rng.random() < 0.2 and "-fea_E" not in a:
+    if (kind in ("dctc", "lpc") or "-fea_trap" in a or "-fea_delta" in a) and rng.random() < 0.2 and "-fea_E" not in a:
         a += ["-fea_Z_exp", rng.choice(["300", "1000"])]
     # VAD module (src/vad/vad.cc): criterion x threshold x majority filter x apply mode
     if rng.random() < 0.35 and "-fea_Z_exp" not in a and kind != "trapdct":
