@@ -393,8 +393,6 @@ static int build_delta_trap_params(ctu_handle *h) {
     }
     if (h->gather && h->do_vad && h->vad_cri == VCRI_CEPDIST_FEA)
         return fail(h, CTU_ERR_UNSUPPORTED, "CTU: the feature-vector VAD criterion together with stacking / deltas of spectral vectors");
-    if (h->gather && (c.stat_cmvn || c.apply_cmvn))
-        return fail(h, CTU_ERR_UNSUPPORTED, "CTU: CMVN together with stacking / deltas of spectral vectors / feature-file input");
     D.n_order = n_order;
     int wins[3] = {c.d_win, c.a_win, c.t_win};
     int halo = 0;
@@ -416,6 +414,8 @@ static int build_delta_trap_params(ctu_handle *h) {
         if (h->fea_kind == FEA_LPA || (cepstral && !c.fea_c0)) h->feature_dim = h->work_dim - 1;
         if (h->feature_dim < 1) return fail(h, CTU_ERR_CONFIG, "OUT: empty feature vector");
     }
+    if ((c.stat_cmvn || c.apply_cmvn) && h->work_dim != h->feature_dim)
+        return fail(h, CTU_ERR_UNSUPPORTED, "CTU: CMVN on feature files whose last column the writer cuts (lpa, lpc / dctc without c0)");
     D.stride = h->work_dim;
     S.dst_stride = h->work_dim;
     D.span_max = DELTA_ROWS + 2 * halo;

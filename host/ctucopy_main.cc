@@ -671,6 +671,8 @@ void process_cmvn(const HostOpts &ho, const ctu_config &cfg, const std::vector<L
     ctu_handle *h = nullptr;
     if (ctu_create(&cfg, device, &h)) die(ctu_last_error(nullptr));
     const int fdim = ctu_feature_dim(h), dim = ctu_cmvn_dim(h);
+    const int in_dim = ctu_input_dim(h);          // > 0: feature files in (-format_in htk)
+    const bool fea_in = in_dim > 0;
     const bool use_ext = !std::strcmp(cfg.vadmode, "file");
     std::vector<int64_t> nsamp(list.size());
     parallel_for(list.size(), IO_THREADS, [&](size_t i) { nsamp[i] = count_samples(ho, list[i].in); });
@@ -678,7 +680,7 @@ void process_cmvn(const HostOpts &ho, const ctu_config &cfg, const std::vector<L
     {
         int64_t acc = 0;
         for (size_t i = 0; i < list.size(); i++) {
-            acc += nsamp[i];
+            acc += fea_in ? nsamp[i] * in_dim * 2 : nsamp[i];
             if (acc >= (int64_t(1) << 26)) { cuts.push_back(i + 1); acc = 0; }
         }
         if (cuts.back() != list.size()) cuts.push_back(list.size());
@@ -699,9 +701,13 @@ void process_cmvn(const HostOpts &ho, const ctu_config &cfg, const std::vector<L
                 if (frames[u] < 0) die("IO: Signal shorter than one frame!");
                 total += frames[u];
             }
-            pcmbuf.reserve((uint64_t)(off[n] + 8) * 2);
+            pcmbuf.reserve(fea_in ? (uint64_t)(off[n] + 1) * in_dim * 4 : (uint64_t)(off[n] + 8) * 2);
             int16_t *pcm = (int16_t *)pcmbuf.p;
-            parallel_for(n, IO_THREADS, [&](size_t u) { decode_into(ho, cfg.fs, list[i0 + u].in, pcm + off[u], off[u + 1] - off[u]); });
+            float *fin = (float *)pcmbuf.p;
+            parallel_for(n, IO_THREADS, [&](size_t u) {
+                if (fea_in) read_features_into(ho, cfg, list[i0 + u].in, fin + off[u] * in_dim, off[u + 1] - off[u]);
+                else decode_into(ho, cfg.fs, list[i0 + u].in, pcm + off[u], off[u + 1] - off[u]);
+            });
             const uint8_t *ev = nullptr;
             if (use_ext) {
                 if (fr_before + (size_t)total > extvad.size()) die("NR: Unexpected end of VAD file!");
@@ -710,7 +716,7 @@ void process_cmvn(const HostOpts &ho, const ctu_config &cfg, const std::vector<L
             fr_before += (size_t)total;
             ctu_plan *p = nullptr;
             if (ctu_plan_create(h, off.data(), (int)n, &p)) die(ctu_last_error(h));
-            if (ctu_plan_run_host_keep(p, pcm, ev)) die(ctu_last_error(h));
+            if (fea_in ? ctu_plan_run_host_fea(p, fin, nullptr) : ctu_plan_run_host_keep(p, pcm, ev)) die(ctu_last_error(h));
             std::vector<double> a(n * dim), b(n * dim);
             if (pass == 0) {
                 if (ctu_plan_colsums(p, nullptr, a.data())) die(ctu_last_error(h));
@@ -742,9 +748,11 @@ void process_cmvn(const HostOpts &ho, const ctu_config &cfg, const std::vector<L
         } else if (pass == 1) {
             for (size_t j = 0; j < ns; j++) for (int c = 0; c < dim; c++) var[j * dim + c] /= (cnt[j] - 1);  // stat_cv
             // statistics file (cmvnOUT::save_frame, src/io/out.cc:591-615) in the reference's order: the
-            // internal vector F[1..], then F[0] -- c0 of the static block goes last, everything else stays
+            // internal vector F[1..], then F[0] -- c0 of the static block goes last, everything else stays.  Stacked rows
+            // (-fea_trap) are written as they are, so the vector the statistics see is the written one; with feature-file
+            // input nothing is skipped or rotated at all (src/fea/post_impl.cc:56-58)
             const std::string kind(cfg.fea_kind);
-            const bool cep = (kind == "dctc" || kind == "lpc");
+            const bool cep = (kind == "dctc" || kind == "lpc") && !cfg.fea_trap;
             const int nblk = cfg.fea_ncepcoefs + 1;
             std::vector<int> wcol(dim);            // statistics index -> writer column
             for (int w = 0; w < dim; w++) {
@@ -752,6 +760,7 @@ void process_cmvn(const HostOpts &ho, const ctu_config &cfg, const std::vector<L
                 if (cep) { const int j = w / nblk, pw = w % nblk; i = j * nblk + (pw == nblk - 1 ? 0 : pw + 1); }
                 wcol[i == 0 ? dim - 1 : i - 1] = w;
             }
+            if (fea_in) for (int w = 0; w < dim; w++) wcol[w] = w;
             FILE *f = std::fopen(statfile.c_str(), "wt");
             if (!f) die("OUT: Cannot create output file with stat. of cmvn!");
             for (size_t j = 0; j < ns; j++) {

@@ -1418,8 +1418,10 @@ def run_list_cmvn(pcms: List[np.ndarray], spk: List[str], o: Opts):
         elif k == "dctc": F = fea_dctc(Y, o)
         elif k == "lpc": F = fea_lpc(Y, o, fb.inld)
         else: raise ValueError("CTU: CMVN oracle covers spec, logspec, dctc and lpc")
-        if o.n_order > 0 and k in ("dctc", "lpc"):
-            F = add_deltas(F, o)
+        if o.fea_delta and o.n_order > 0:
+            if F.shape[1] < o.fea_ncepcoefs + 1:
+                raise ValueError("FEA: deltas / stacking read beyond the feature vector for this kind")
+            F = add_deltas(F[:, : o.fea_ncepcoefs + 1], o)
         feats.append(F)
     names, mean, var = cmvn_stats(feats, spk)
     text = cmvn_stat_text(names, mean, var)
@@ -1430,6 +1432,28 @@ def run_list_cmvn(pcms: List[np.ndarray], spk: List[str], o: Opts):
         j = names.index(s_)
         G = cmvn_apply(F, mean[j], var[j])
         outs.append((writer_order(G, o)).astype(np.float32))
+    return text, outs
+
+
+def run_list_cmvn_features(mats: List[np.ndarray], spk: List[str], o: Opts):
+    """run_list_cmvn for `-format_in htk`: the statistics cover the whole vector the chain produced, in the order it
+    comes -- with feature-file input POST neither skips nor rotates element 0 (the `format_in == "htk"` branches of
+    cmvn_POST::sum_fea / sum_cv / process_frame, src/fea/post_impl.cc:56-58, 83-85, 111-113)."""
+    feats = []
+    for M in mats:
+        F = np.asarray(M, dtype=np.float64)
+        if o.fea_delta and o.n_order > 0:
+            F = add_deltas(F[:, : o.fea_ncepcoefs + 1], o)
+        feats.append(np.concatenate([F[:, -1:], F[:, :-1]], axis=1))      # undo cmvn_stat_order's rotation: identity order
+    names, mean, var = cmvn_stats(feats, spk)
+    text = cmvn_stat_text(names, mean, var)
+    if not o.apply_cmvn:
+        return text, None
+    outs = []
+    for F, s_ in zip(feats, spk):
+        j = names.index(s_)
+        G = cmvn_apply(F, mean[j], var[j])
+        outs.append(np.concatenate([G[:, 1:], G[:, :1]], axis=1).astype(np.float32))
     return text, outs
 
 

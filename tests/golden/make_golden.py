@@ -124,6 +124,9 @@ CASES = {
 CMVN_CASES = {
     # -apply_cmvn with a statistics file that does not exist yet: statistics passes, file written, features normalised
     "cmvn_3stage_d_a": (B + MF + ["-format_out", "htk", "-fea_delta", "d_a", "-apply_cmvn", "{STAT}"], [0, 1, 4, 5], ["spkA", "spkA", "spkB", "spkB"]),
+    # stacked rows / deltas of spectral vectors through the three passes (statistics order: F[1..], F[0] of the vector as written)
+    "cmvn_3stage_trap3": (B + MF + ["-format_out", "htk", "-fea_trap", "3", "-apply_cmvn", "{STAT}"], [0, 4, 5], ["spkA", "spkB", "spkA"]),
+    "cmvn_3stage_logspec_d": (B + MF + ["-format_out", "htk", "-fea_kind", "logspec", "-fea_delta", "d", "-apply_cmvn", "{STAT}"], [0, 4, 1], ["s1", "s2", "s2"]),
     # -stat_cmvn: statistics only
     "cmvn_stat_plp": (B + ["-preset", "plpc", "-format_out", "htk", "-stat_cmvn", "{STAT}"], [0, 4, 1, 5, 2], ["s1", "s2", "s1", "s2", "s3"]),
 }
@@ -141,6 +144,14 @@ FEAIN_CASES = {
     "feain_lpc_d_cms": BH + ["-fea_kind", "lpc", "-fea_delta", "d", "-fea_Z_exp", "400", "-format_out", "htk"],
     "feain_lpa_d8": BH + ["-fea_kind", "lpa", "-fea_ncepcoefs", "8", "-fea_delta", "d", "-d_win", "3", "-format_out", "htk"],
     "feain_trap3_be": BH + ["-fea_kind", "logspec", "-fea_trap", "3", "-format_out", "htk", "-endian_out", "big"],
+}
+
+
+# CMVN over a list of feature files (three passes / statistics only), same layout as CMVN_CASES
+FEAIN_CMVN_CASES = {
+    "cmvnfea_3stage_d": (BH + ["-fea_kind", "lpc", "-fea_delta", "d", "-format_out", "htk", "-apply_cmvn", "{STAT}"], [0, 1, 4, 5], ["spkA", "spkA", "spkB", "spkB"]),
+    "cmvnfea_3stage_copy": (BH + ["-fea_kind", "lpc", "-format_out", "htk", "-apply_cmvn", "{STAT}"], [0, 4, 1], ["s1", "s2", "s1"]),
+    "cmvnfea_stat_trap3": (BH + ["-fea_kind", "spec", "-fea_trap", "3", "-format_out", "htk", "-stat_cmvn", "{STAT}"], [0, 4, 5], ["a", "b", "a"]),
 }
 
 
@@ -233,6 +244,30 @@ def main():
             d["out%d" % i] = np.frombuffer(r["outputs"][0], dtype=np.uint8)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
         print(name, "ok")
+    for name, (args, idx, spk) in FEAIN_CMVN_CASES.items():
+        if sys.argv[1:] and name not in sys.argv[1:]:
+            continue
+        import struct, subprocess, tempfile
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import golden_util as gu
+        src = gu.Case(FEAIN_SOURCE)
+        with tempfile.TemporaryDirectory() as d:
+            for i in idx:
+                open(os.path.join(d, "f%d.htk" % i), "wb").write(src.raw[i])
+            with open(os.path.join(d, "list.scp"), "w") as fh:
+                for i, sp in zip(idx, spk):
+                    fh.write("%s/f%d.htk %s/g%d.htk %s\n" % (d, i, d, i, sp))
+            a = [x.replace("{STAT}", os.path.join(d, "cmvn.stat")) for x in args]
+            pr = subprocess.run([rr.ref_binary("O0")] + a + ["-S", os.path.join(d, "list.scp")], capture_output=True, cwd=d)
+            assert pr.returncode == 0, (name, pr.stderr)
+            dd = {"args": np.array(json.dumps(args)), "idx": np.array(idx), "spk": np.array(json.dumps(spk)), "source": np.array(FEAIN_SOURCE),
+                  "stat": np.frombuffer(open(os.path.join(d, "cmvn.stat"), "rb").read(), dtype=np.uint8)}
+            for i in idx:
+                pth = os.path.join(d, "g%d.htk" % i)
+                if os.path.exists(pth):
+                    dd["out%d" % i] = np.frombuffer(open(pth, "rb").read(), dtype=np.uint8)
+            np.savez_compressed(os.path.join(OUT, name + ".npz"), **dd)
+            print(name, "ok", sorted(k for k in dd if k.startswith("out")))
     if sys.argv[1:]:
         return       # only the named cases were asked for
     # filter-bank design goldens via the undocumented -fb_printself (src/fea/fb.cc:449-456)

@@ -20,7 +20,7 @@ def inputs():
 
 
 def case_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("inputs.npz", "fb_design.npz") and not f.startswith("cmvn_") and not f.startswith("feain_"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("inputs.npz", "fb_design.npz") and not f.startswith("cmvn") and not f.startswith("feain_"))
 
 
 def feain_case_names():

@@ -137,13 +137,19 @@ def _stat_numbers(text):
     return names, np.array(vals)
 
 
-@pytest.mark.parametrize("name", ["cmvn_3stage_d_a", "cmvn_stat_plp"])
+@pytest.mark.parametrize("name", ["cmvn_3stage_d_a", "cmvn_stat_plp", "cmvn_3stage_trap3", "cmvn_3stage_logspec_d",
+                                  "cmvnfea_3stage_d", "cmvnfea_3stage_copy", "cmvnfea_stat_trap3"])
 def test_cli_cmvn_statistics_and_normalised_features(tmp_path, name):
-    """List-mode CMVN through the CLI against the reference binary's statistics file and feature files."""
+    """List-mode CMVN through the CLI against the reference binary's statistics file and feature files (sample input, and
+    HTK feature files in: the cmvnfea_* cases)."""
     args, idx, spk, stat, outs = gu.cmvn_case(name)
     ins = gu.inputs()
+    src = gu.Case("mfcc30_static") if name.startswith("cmvnfea") else None
     for i in idx:
-        ins[i].astype("<i2").tofile(tmp_path / ("u%d.raw" % i))
+        if src is not None:
+            open(tmp_path / ("u%d.raw" % i), "wb").write(src.raw[i])      # an HTK parameter file, whatever its name
+        else:
+            ins[i].astype("<i2").tofile(tmp_path / ("u%d.raw" % i))
     with open(tmp_path / "list.scp", "w") as fh:
         for i, sp in zip(idx, spk):
             fh.write("%s/u%d.raw %s/u%d.htk %s\n" % (tmp_path, i, tmp_path, i, sp))

@@ -131,7 +131,7 @@ def test_frame_count_edge_cases():
         co.num_frames(239, o)
 
 
-@pytest.mark.parametrize("name", ["cmvn_3stage_d_a", "cmvn_stat_plp"])
+@pytest.mark.parametrize("name", ["cmvn_3stage_d_a", "cmvn_stat_plp", "cmvn_3stage_trap3", "cmvn_3stage_logspec_d"])
 def test_oracle_cmvn_matches_reference_binary(name):
     """List-mode CMVN (src/fea/post_impl.cc:52-118, src/io/batch.cc:136-152, 339-420): statistics file text
     and normalised features identical to the reference binary's."""
@@ -160,3 +160,20 @@ def test_glibc_rand_restatement_matches_libc():
     ref = np.array([libc.rand() for _ in range(5000)], dtype=np.int64)
     assert np.array_equal(co.glibc_rand(5000), ref)
     assert np.array_equal(co.glibc_rand(1000, skip=4000), ref[4000:])
+
+
+@pytest.mark.parametrize("name", ["cmvnfea_3stage_d", "cmvnfea_3stage_copy", "cmvnfea_stat_trap3"])
+def test_oracle_cmvn_on_feature_files_matches_reference_binary(name):
+    """CMVN over a list of HTK feature files (the `format_in == "htk"` branches of cmvn_POST, src/fea/post_impl.cc:56-58,
+    83-85, 111-113): statistics text and normalised rows identical to the reference binary's."""
+    import ref_runner as rr
+    args, idx, spk, stat, outs = gu.cmvn_case(name)
+    o = co.parse_args([a.replace("{STAT}", "x.stat") for a in args])
+    src = gu.Case("mfcc30_static")
+    text, feats = co.run_list_cmvn_features([src.payload(i) for i in idx], spk, o)
+    assert text == stat
+    if o.apply_cmvn:
+        for j, i in enumerate(idx):
+            assert np.array_equal(feats[j], rr.parse_htk(outs[i])[1]), (name, i)
+    else:
+        assert not outs
