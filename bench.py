@@ -47,6 +47,8 @@ WORKLOADS = {
     "exten": (B + ["-preset", "exten", "-format_out", "raw"], 1024, 30000),
     "fwss_burg": (B + ["-preset", "mfcc", "-preem", "0.97", "-nr_mode", "fwss", "-vad", "burg", "-nr_when", "beforeFB",
                        "-format_out", "pfile=out.pfile"], 380, 70000),
+    # MFCC_0 with +-2 frames of context stacked per coefficient (13 -> 65 columns)
+    "mfcc_trap5": (B + ["-preset", "mfcc", "-preem", "0.97", "-fea_trap", "5", "-format_out", "htk"], 320 + 260, 18000),
 }
 DEFAULT_WORKLOAD = "mfcc_exten"
 
@@ -59,6 +61,7 @@ def kernel_alg_bytes(name, hop, dim, nb):
         "k_frames<spec,fea>": 4 * 257 + 4 * dim, "k_frames<spec,fb>": 4 * 257 + 4 * nb,
         "k_nr_scan": 2 * 4 * 257, "k_delta": 4 * dim + 8 * dim, "k_lpc": 4 * nb + 4 * dim, "k_trapdct": 4 * nb + 4 * dim,
         "k_synth": pcm + 4 * 257 + pcm, "k_burg": pcm + 8 * 16, "k_cepdet": 8 * 16 + 1,
+        "k_stack": 4 * 13 + 4 * dim,          # static block read once, stacked row written once
     }.get(name)
 
 
@@ -314,6 +317,8 @@ def main():
         sdim = dim // 3 if ("-fea_delta" in args and dim % 3 == 0) else dim      # static block of a _D_A vector
         kinfo = {}
         for n, ms_k in kern_ms.items():
+            if workload == "mfcc_trap5":
+                sdim = 13
             d = {"k_delta": sdim, "k_frames<pcm,fea>": sdim if workload != "trapdct" else hd.num_bands,
                  "k_frames<spec,fea>": sdim, "k_lpc": sdim}.get(n, dim)
             ab = kernel_alg_bytes(n, hop, d, hd.num_bands)

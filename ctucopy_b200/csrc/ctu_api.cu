@@ -19,6 +19,7 @@
 #include "ctu_frames_any.cuh"
 #include "ctu_nr_kernels.cuh"
 #include "ctu_precise.cuh"
+#include "ctu_synth_any.cuh"
 
 using namespace ctu;
 
@@ -55,6 +56,7 @@ struct ctu_handle {
     bool generic = false;
     int nbins = NBIN;
     float2 *d_any_tw = nullptr, *d_any_ts = nullptr;
+    double2 *d_any_tw64 = nullptr, *d_any_ts64 = nullptr;     // fp64 copies for the general synthesis (ctu_synth_any.cuh)
     float *d_any_fbw = nullptr;
     int4 *d_any_bands = nullptr;
     std::vector<float> fbw_all;
@@ -94,6 +96,7 @@ struct ctu_plan {
     float *d_static = nullptr;           // static block before k_stack (gather modes)
     float *d_work = nullptr;             // full-width rows when the writer cuts the last column (feature input)
     float *d_in = nullptr;               // feature input rows (host entry point)
+    double *d_yt = nullptr;              // synthesised frames [frames x window] of the general synthesis
     double *d_fb64 = nullptr;            // band values of the precise path
     double *d_fea64 = nullptr;           // fp64 copy of the feature matrix (feature-vector VAD criterion)
     float *d_E = nullptr;                // log energy per frame (-fea_E)
@@ -557,7 +560,8 @@ static int resolve_modes(ctu_handle *h) {
         // other sampling rates / window lengths: the general (slower) frame kernel; the specialised 512-point
         // kernels of the Burg detector, the synthesis and the fp64 path are not generalised yet
         if (c.wfft < 64 || c.wfft > ANY_MAX_NFFT) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: FFT sizes from 64 to 2048 points are built (window of 33..2048 samples)");
-        if (h->signal_out) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: waveform output is built for 512-point frames without -remove_dc1 / -dither only");
+        if (h->signal_out && (c.remove_dc1 || c.dither != 0.0))
+            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: waveform output together with -remove_dc1 / -dither");
         if (h->vad_src == VADSRC_BURG || (h->do_vad && h->vad_cri == VCRI_CEPDIST_LPC))
             return fail(h, CTU_ERR_UNSUPPORTED, "CTU: the Burg detector is built for 512-point frames without -remove_dc1 / -dither only");
     }
@@ -607,6 +611,12 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
         std::vector<float2> tw(std::max(1, M / 2)), ts(M + 1);
         for (int k = 0; k < M / 2; k++) tw[k] = make_float2((float)cos(-2 * PI * k / M), (float)sin(-2 * PI * k / M));
         for (int k = 0; k <= M; k++) { const double th = 2 * PI * k / N; ts[k] = make_float2((float)(-sin(th) / 2), (float)(-cos(th) / 2)); }
+        if (h->signal_out) {
+            std::vector<double2> twd(std::max(1, M / 2)), tsd(M + 1);
+            for (int k = 0; k < M / 2; k++) twd[k] = make_double2(cos(-2 * PI * k / M), sin(-2 * PI * k / M));
+            for (int k = 0; k <= M; k++) { const double th = 2 * PI * k / N; tsd[k] = make_double2(-sin(th) / 2, -cos(th) / 2); }
+            if ((st = upload(h, &h->d_any_tw64, twd)) || (st = upload(h, &h->d_any_ts64, tsd))) return bail(st);
+        }
         if ((st = upload(h, &h->d_any_tw, tw)) || (st = upload(h, &h->d_any_ts, ts)) || (st = upload(h, &h->d_any_fbw, h->fbw_all)) ||
             (st = upload(h, &h->d_any_bands, h->bands_all))) return bail(st);
     }
@@ -629,6 +639,7 @@ void ctu_destroy(ctu_handle *h) {
     cudaFree(h->d_tw256); cudaFree(h->d_twsplit); cudaFree(h->d_twinv); cudaFree(h->d_win);
     cudaFree(h->d_w64); cudaFree(h->d_m264); cudaFree(h->d_lift64);
     cudaFree(h->d_tw256d); cudaFree(h->d_twsplitd); cudaFree(h->d_twinvd); cudaFree(h->d_wind); cudaFree(h->d_hann);
+    cudaFree(h->d_any_tw64); cudaFree(h->d_any_ts64);
     cudaFree(h->d_any_tw); cudaFree(h->d_any_ts); cudaFree(h->d_any_fbw); cudaFree(h->d_any_bands);
     for (auto &b : h->pool) cudaFree(b.p);
     for (int i = 0; i < 3; i++) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
@@ -677,7 +688,7 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     p->nframes.resize(n); p->row_off.resize(n + 1); p->osamp_off.resize(n + 1);
     p->tile32_off.resize(n + 1); p->tile64_off.resize(n + 1); p->tileS_off.resize(n + 1); p->tileF_off.resize(n + 1);
     p->syn_tile = std::max(1, SYN_FRAMES - h->sp.hh);
-    if (h->signal_out && h->sp.hh >= SYN_FRAMES) { delete p; return fail(h, CTU_ERR_UNSUPPORTED, "CTU: window / shift ratio too large for synthesis"); }
+    if (h->signal_out && !h->generic && h->sp.hh >= SYN_FRAMES) { delete p; return fail(h, CTU_ERR_UNSUPPORTED, "CTU: window / shift ratio too large for synthesis"); }
     p->rows_per_utt.assign(n, 0);
     const int w = h->cfg.window, s = h->cfg.wshift;
     int64_t rows = 0, osamp = 0, t32 = 0, t64 = 0, tS = 0, tF = 0;
@@ -740,6 +751,7 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     const bool lpc_kind = (h->fea_kind == FEA_LPA || h->fea_kind == FEA_LPC);
     const bool need_fb = !h->signal_out && ((nr_on && h->cfg.nr_when == 1) || lpc_kind);
     if (need_spec && (st = dev_alloc(h, p, &p->d_spec, (size_t)rows * h->nbins))) { ctu_plan_destroy(p); return st; }
+    if (h->signal_out && h->generic && (st = dev_alloc(h, p, &p->d_yt, (size_t)rows * h->cfg.window))) { ctu_plan_destroy(p); return st; }
     if (need_fb && !h->precise && (st = dev_alloc(h, p, &p->d_fb, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     if (need_fb && h->precise && (st = dev_alloc(h, p, &p->d_fb64, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     if (h->do_vad && h->vad_cri == VCRI_CEPDIST_FEA && (st = dev_alloc(h, p, &p->d_fea64, (size_t)rows * h->feature_dim))) { ctu_plan_destroy(p); return st; }
@@ -1062,6 +1074,27 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
         if ((st = launch_nr_scan(h->nrp, p->d_nframes, p->d_row_off, r.u0, r.u1, h->nbins, p->d_spec, fl, s, &h->lc, h->err))) return st;
         if (h->vad_src == VADSRC_FILE && d_vadnr && h->nr_mode >= NR_HWSS)
             CK(cudaMemcpyAsync(d_vadnr + r.row0, d_ext + r.row0, r.nrows, cudaMemcpyDeviceToDevice, s));
+    }
+    if (h->signal_out && h->generic) {
+        // other FFT sizes: frames -> segments (fp64, one warp per frame), then overlap-add per 16-hop tile
+        if (r.tF_n <= 0) return CTU_OK;
+        BatchDesc bdF{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tilesF + r.tF_0};
+        const int N = h->cfg.wfft, M = N / 2;
+        int lg = 0;
+        while ((1 << lg) < M) lg++;
+        AnyTables64 tb{h->d_any_tw64, h->d_any_ts64, h->d_wind, N, lg};
+        const size_t bytes = (size_t)(SYNANY_THREADS / 32) * (4 * M + 4) * sizeof(double);
+        CK(cudaFuncSetAttribute(k_synth_frames_any, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        h->lc.begin("k_synth_frames_any", s);
+        k_synth_frames_any<<<(unsigned)r.tF_n, SYNANY_THREADS, bytes, s>>>(h->cfg.window, h->cfg.wshift, (double)h->cfg.preem, h->cfg.remove_dc, bdF, tb, d_pcm,
+                                                                          p->d_spec, p->d_yt);
+        h->lc.end(s);
+        CK(cudaGetLastError());
+        h->lc.begin("k_ola_any", s);
+        k_ola_any<<<(unsigned)r.tF_n, 256, 0, s>>>(h->cfg.window, h->cfg.wshift, 1.0 / h->sp.correction, bdF, p->d_osamp_off, p->d_yt, d_wave);
+        h->lc.end(s);
+        CK(cudaGetLastError());
+        return CTU_OK;
     }
     if (h->signal_out) {
         BatchDesc bdS{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tilesS + r.tS_0};

@@ -117,6 +117,11 @@ CASES = {
     "plp_trap5_cms": (B + ["-preset", "plpc", "-fea_trap", "5", "-fea_Z_exp", "500", "-format_out", "htk"], "htk", {}),
     "mfcc_trap5_vad_drop": (B + MF + ["-fea_trap", "5", "-format_out", "htk", "-vad_out_mode", "vad", "-vad_apply_mode", "drop"],
                             "htk", {"vad_out": True}),
+    # enhanced waveforms at other sampling rates: 256-, 1024- and 2048-point synthesis (the same samples read at another rate)
+    "exten_raw_8k": (["-fs", "8000"] + B[2:] + ["-preset", "exten", "-format_out", "raw"], "raw", {}),
+    "exten_raw_8k_2510": (["-fs", "8000"] + B[2:] + ["-preset", "exten", "-nr_a", "2", "-w", "25", "-s", "10", "-preem", "0.97", "-format_out", "raw"], "raw", {}),
+    "exten_wave_44k": (["-fs", "44100"] + B[2:] + ["-preset", "exten", "-format_out", "wave"], "wave", {}),
+    "resynth_raw_22k": (["-fs", "22050"] + B[2:] + ["-nr_mode", "none", "-w", "25", "-s", "10", "-preem", "0.97", "-remove_dc", "off", "-format_out", "raw"], "raw", {}),
     "logspec32k_40": (["-fs", "32000"] + B[2:] + MF + ["-fea_kind", "logspec", "-fb_definition", "40filters", "-format_out", "htk"], "htk", {}),
 }
 
