@@ -1,0 +1,101 @@
+// fp64 building blocks of the GENERAL kernels (FFT sizes other than 512): one warp owns a frame, the transform is an
+// in-place radix-2 FFT of nfft/2 complex points in shared memory.  Used by the general synthesis (ctu_synth_any.cuh) and
+// by the general Burg front end below.  Speed is secondary here (every BASELINE configuration takes the 512-point
+// kernels); the arithmetic conventions are those of k_synth / k_burg, restated from the same reference lines.
+#ifndef CTU_ANY64_CUH
+#define CTU_ANY64_CUH
+
+#include "ctu_kernels.cuh"
+
+namespace ctu {
+
+struct AnyTables64 {
+    const double2 *tw;       // e^{-2 pi i k / M}, k < M/2           (M = nfft/2)
+    const double2 *twsplit;  // -i/2 e^{-2 pi i k / nfft}, k <= M
+    const double *win;       // analysis window [window]
+    int nfft, log2m;
+};
+
+constexpr int ANY64_THREADS = 128;            // 4 warps per CTA
+
+// in-place radix-2 decimation-in-time FFT of M complex points held by one warp in shared memory
+__device__ __forceinline__ void warp_fft_radix2(cpx<double> *z, int M, int log2m, const double2 *__restrict__ tw, int lane) {
+    for (int n = lane; n < M; n += 32) {
+        const int r = (int)(__brev((unsigned)n) >> (32 - log2m));
+        if (r > n) { const cpx<double> t = z[n]; z[n] = z[r]; z[r] = t; }
+    }
+    __syncwarp();
+    for (int len = 2, shift = log2m - 1; len <= M; len <<= 1, shift--) {
+        const int half = len >> 1;
+        for (int b = lane; b < (M >> 1); b += 32) {
+            const int j0 = b & (half - 1), i0 = ((b - j0) << 1) + j0, i1 = i0 + half;
+            const double2 w = __ldg(tw + ((size_t)j0 << shift));
+            const cpx<double> t = cmul(z[i1], mk<double>(w.x, w.y));
+            const cpx<double> a = z[i0];
+            z[i0] = a + t;
+            z[i1] = a - t;
+        }
+        __syncwarp();
+    }
+}
+
+// the frame exactly as rawIN::get_frame builds it (pre-emphasis, window, mean of the windowed frame removed inside the
+// window, src/io/in.cc:362-388), transformed: z holds FFT_M of the even/odd packed frame afterwards
+__device__ __forceinline__ void any64_analysis(cpx<double> *z, const AnyTables64 &tb, const int16_t *__restrict__ x, bool at_start, int w,
+                                               double preem, int remove_dc, int lane) {
+    const int nfft = tb.nfft;
+    double *y = reinterpret_cast<double *>(z);
+    double sum = 0.0;
+    for (int i = lane; i < nfft; i += 32) {
+        double v = 0.0;
+        if (i < w) {
+            const double xi = (double)x[i];
+            const double xp = (i == 0 && at_start) ? 0.0 : (double)x[i - 1];
+            v = tb.win[i] * (xi - preem * xp);
+        }
+        y[i] = v;
+        sum += v;
+    }
+    if (remove_dc) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const double mean = sum / (double)w;
+        __syncwarp();
+        for (int i = lane; i < w; i += 32) y[i] -= mean;
+    }
+    __syncwarp();
+    warp_fft_radix2(z, nfft >> 1, tb.log2m, tb.tw, lane);
+}
+
+// bin k of the real-input spectrum from the packed transform
+__device__ __forceinline__ cpx<double> any64_bin(const cpx<double> *z, const AnyTables64 &tb, int k) {
+    const int M = tb.nfft >> 1;
+    const cpx<double> a = z[k == M ? 0 : k], b = conj(z[k == 0 ? 0 : M - k]);
+    const double2 ts = __ldg(tb.twsplit + k);
+    return mk<double>(0.5 * (a.x + b.x), 0.5 * (a.y + b.y)) + cmul(mk<double>(ts.x, ts.y), a - b);
+}
+
+// UNNORMALISED inverse real transform (what FFTW's HC2R gives, src/io/out.cc:425, src/nr/nr.cc:291, src/vad/vad.cc:232) of
+// the half spectrum Y[0..M] into the nfft reals that alias z:  Z[k] = E[k] + i O[k], E = (Y[k] + conj Y[M-k]) / 2,
+// O = e^{+2 pi i k / nfft} (Y[k] - conj Y[M-k]) / 2;  z[n] = 2 sum_k Z[k] e^{+2 pi i k n / M} = 2 conj(FFT_M(conj Z))[n];
+// y[2n] = Re z[n], y[2n+1] = Im z[n].
+__device__ __forceinline__ void any64_inverse(cpx<double> *z, const cpx<double> *Y, const AnyTables64 &tb, int lane) {
+    const int M = tb.nfft >> 1;
+    for (int k = lane; k < M; k += 32) {
+        const cpx<double> a = Y[k], b = conj(Y[M - k]);
+        const double2 ts = __ldg(tb.twsplit + k);                      // (-sin/2, -cos/2)  ->  e^{+i th}/2 = (-ts.y, -ts.x)
+        const cpx<double> E = mk<double>(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
+        const cpx<double> O = cmul(mk<double>(-ts.y, -ts.x), a - b);
+        z[k] = mk<double>(E.x - O.y, -(E.y + O.x));                    // conj(Z[k])
+    }
+    __syncwarp();
+    warp_fft_radix2(z, M, tb.log2m, tb.tw, lane);
+    for (int n = lane; n < M; n += 32) {                               // in place: z[n] occupies reals 2n, 2n+1
+        const cpx<double> v = z[n];
+        z[n] = mk<double>(2.0 * v.x, -2.0 * v.y);
+    }
+    __syncwarp();
+}
+
+}  // namespace ctu
+#endif

@@ -469,6 +469,9 @@ static int build_delta_trap_params(ctu_handle *h) {
     return CTU_OK;
 }
 
+// FFT size other than the specialised 512 points (the fp64 Burg / synthesis kernels then take their general form)
+static bool c_wfft_is_general(const ctu_handle *h) { return h->cfg.wfft != NFFT; }
+
 static int resolve_modes(ctu_handle *h) {
     const ctu_config &c = h->cfg;
     std::string fo(c.format_out), kind(c.fea_kind), nr(c.nr_mode), vm(c.vadmode);
@@ -562,8 +565,8 @@ static int resolve_modes(ctu_handle *h) {
         if (c.wfft < 64 || c.wfft > ANY_MAX_NFFT) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: FFT sizes from 64 to 2048 points are built (window of 33..2048 samples)");
         if (h->signal_out && (c.remove_dc1 || c.dither != 0.0))
             return fail(h, CTU_ERR_UNSUPPORTED, "CTU: waveform output together with -remove_dc1 / -dither");
-        if (h->vad_src == VADSRC_BURG || (h->do_vad && h->vad_cri == VCRI_CEPDIST_LPC))
-            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: the Burg detector is built for 512-point frames without -remove_dc1 / -dither only");
+        if ((h->vad_src == VADSRC_BURG || (h->do_vad && h->vad_cri == VCRI_CEPDIST_LPC)) && (c.remove_dc1 || c.dither != 0.0))
+            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: the Burg detector together with -remove_dc1 / -dither");
     }
     return CTU_OK;
 }
@@ -611,11 +614,17 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
         std::vector<float2> tw(std::max(1, M / 2)), ts(M + 1);
         for (int k = 0; k < M / 2; k++) tw[k] = make_float2((float)cos(-2 * PI * k / M), (float)sin(-2 * PI * k / M));
         for (int k = 0; k <= M; k++) { const double th = 2 * PI * k / N; ts[k] = make_float2((float)(-sin(th) / 2), (float)(-cos(th) / 2)); }
-        if (h->signal_out) {
+        const bool burg = h->vad_src == VADSRC_BURG || (h->do_vad && h->vad_cri == VCRI_CEPDIST_LPC);
+        if (h->signal_out || burg) {
             std::vector<double2> twd(std::max(1, M / 2)), tsd(M + 1);
             for (int k = 0; k < M / 2; k++) twd[k] = make_double2(cos(-2 * PI * k / M), sin(-2 * PI * k / M));
             for (int k = 0; k <= M; k++) { const double th = 2 * PI * k / N; tsd[k] = make_double2(-sin(th) / 2, -cos(th) / 2); }
             if ((st = upload(h, &h->d_any_tw64, twd)) || (st = upload(h, &h->d_any_ts64, tsd))) return bail(st);
+            if (c_wfft_is_general(h)) {
+                int lg = 0;
+                while ((1 << lg) < M) lg++;
+                h->bp.nfft = N; h->bp.log2m = lg; h->bp.any_tw = h->d_any_tw64; h->bp.any_ts = h->d_any_ts64;
+            }
         }
         if ((st = upload(h, &h->d_any_tw, tw)) || (st = upload(h, &h->d_any_ts, ts)) || (st = upload(h, &h->d_any_fbw, h->fbw_all)) ||
             (st = upload(h, &h->d_any_bands, h->bands_all))) return bail(st);

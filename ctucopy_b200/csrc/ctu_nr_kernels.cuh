@@ -27,6 +27,7 @@
 
 #include "ctu_internal.h"
 #include "ctu_kernels.cuh"
+#include "ctu_any64.cuh"
 
 namespace ctu {
 
@@ -56,6 +57,9 @@ struct BurgParams {
     int ncoef_vad;       // vad_lpc_coefs
     int ninit; double P, Q;   // detector options <- (nr_initsegs, nr_p, nr_q)
     int use_spec_gain;   // VAD source: post-NR spectrum present (gain from d_spec) else own spectrum
+    // FFT sizes other than 512: the general kernel k_burg_any (nfft == 0: the specialised k_burg)
+    int nfft, log2m;
+    const double2 *any_tw, *any_ts;
 };
 
 struct VadParams {
@@ -499,6 +503,113 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const i
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K4g: the Burg front end for FFT sizes other than 512 (fwss / hwss / 2fwss and the LPC cepstral-distance criterion at
+// 8 kHz, 22-48 kHz).  Same arithmetic as k_burg, one WARP per frame, everything in shared memory:
+//   frame -> FFT -> per-bin gain (|X|^a or the post-NR magnitude, on the phase of X) -> unnormalised inverse -> first
+//   `window` samples [x Hann for the NR detector] -> Burg lattice (src/vdet/Burg.h:49-95) -> cepstrum (:141-152).
+// The lattice keeps ef (aliasing the time signal) and eb in shared memory; a stage updates them in chunks of 32 samples
+// from the END of the frame, so that eb[i-1] is still the old value when sample i is updated.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ANY64_THREADS)
+k_burg_any(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, AnyTables64 tb, const int16_t *__restrict__ pcm,
+           const float *__restrict__ spec, double *__restrict__ ceps, const double *__restrict__ g_hann) {
+    extern __shared__ __align__(16) double smd[];
+    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+    const int nfft = tb.nfft, M = nfft >> 1, nbins = M + 1;
+    cpx<double> *z = reinterpret_cast<cpx<double> *>(smd + (size_t)wv * (6 * M + 4));   // M complex = nfft reals
+    cpx<double> *Y = z + M;                                                             // M + 1 complex (+ pad)
+    double *eb = reinterpret_cast<double *>(Y + M + 2);                                 // nfft reals
+    double *ef = reinterpret_cast<double *>(z);
+    const int2 tile = bd.tiles[blockIdx.x];
+    const int u = tile.x, t0 = tile.y;
+    const int nf = min(TILE_F, bd.nframes[u] - t0);
+    const int64_t row0 = bd.row_off[u] + t0;
+    const int w = B.window, s = B.wshift;
+    const int ncoef = (src_mode == BURG_SRC_NR) ? B.ncoef_nr : B.ncoef_vad;
+    for (int f = wv; f < nf; f += ANY64_THREADS / 32) {
+        any64_analysis(z, tb, pcm + bd.pcm_off[u] + (int64_t)(t0 + f) * s, (t0 + f) == 0, w, B.preem, B.remove_dc, lane);
+        // (|X|^a or the post-NR spectrum) with the phase of X -- see k_burg for the conventions (bin 0: phase 0 and the fixed
+        // 1e-10 floor under -remove_dc, src/io/in.cc:390-398; Nyquist real; atan(0/0) = -pi/2)
+        const float *srow = (src_mode == BURG_SRC_VAD && B.use_spec_gain) ? spec + (row0 + f) * nbins : nullptr;
+        const bool expand = (src_mode == BURG_SRC_NR && B.expand);
+        for (int k = lane; k <= M; k += 32) {
+            cpx<double> X = any64_bin(z, tb, k);
+            double m2 = X.x * X.x + X.y * X.y;
+            const bool edge = (k == 0 || k == M);
+            if (k == 0) { if (B.remove_dc) m2 = 1e-10; X = mk<double>(sqrt(m2), 0.0); }
+            const double rm = (m2 > 0.0) ? rsqrt(m2) : 0.0;
+            const double m = m2 * rm;
+            double E, g;
+            if (srow) { E = (double)srow[k]; g = E * rm; }
+            else {
+                const int ak = expand ? B.a_kind : 1;
+                if (ak == 0) { E = pow(B.fb_power ? m2 : m, B.a); g = E * rm; }
+                else if (B.fb_power) { E = (ak == 2) ? m2 * m2 : m2; g = (ak == 2) ? m2 * m : m; }
+                else { E = (ak == 2) ? m2 : m; g = (ak == 2) ? m : 1.0; }
+            }
+            Y[k] = (m2 == 0.0) ? (edge ? mk<double>(E, 0.0) : mk<double>(0.0, -E)) : mk<double>(X.x * g, edge ? 0.0 : X.y * g);
+        }
+        __syncwarp();
+        any64_inverse(z, Y, tb, lane);
+        // ---- Burg lattice on the first w samples ------------------------------------------------------------------
+        double en = 0.0;
+        for (int i = lane; i < w; i += 32) {
+            const double v = ef[i] * ((src_mode == BURG_SRC_NR) ? g_hann[i] : 1.0);
+            ef[i] = v; eb[i] = v;
+            en += v * v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) en += __shfl_xor_sync(0xffffffffu, en, o);
+        double alpha = en / (double)w;
+        __syncwarp();
+        double a_c = (lane == 0) ? 1.0 : 0.0, aa_c = a_c;              // lane i holds a_i
+#pragma unroll 1
+        for (int ik = 1; ik < ncoef; ik++) {
+            double num = 0.0, den = 0.0;
+            for (int i = ik + lane; i < w; i += 32) {
+                const double e1 = ef[i], e2 = eb[i - 1];
+                num = fma(e1, e2, num);
+                den += e1 * e1 + e2 * e2;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { num += __shfl_xor_sync(0xffffffffu, num, o); den += __shfl_xor_sync(0xffffffffu, den, o); }
+            const double rc = -(2.0 * num) / den;
+            alpha *= 1 - rc * rc;
+            for (int base = (w - 1) & ~31; base >= 0; base -= 32) {
+                const int i = base + lane;
+                const bool ok = i >= 1 && i < w;
+                double e0 = 0.0, pv = 0.0;
+                if (ok) { e0 = ef[i]; pv = eb[i - 1]; }
+                __syncwarp();
+                if (ok) { ef[i] = e0 + rc * pv; eb[i] = pv + rc * e0; }
+                __syncwarp();
+            }
+            const double other = __shfl_sync(0xffffffffu, aa_c, (ik - lane) & 31);
+            if (lane == ik) a_c = rc;
+            else if (lane >= 1 && lane < ik) a_c = aa_c + rc * other;
+            aa_c = a_c;
+        }
+        double av[BURG_MAXC];
+#pragma unroll
+        for (int k = 0; k < BURG_MAXC; k++) av[k] = __shfl_sync(0xffffffffu, a_c, k);
+        if (lane == 0) {
+            double cc[BURG_MAXC];
+            double *o = ceps + (row0 + f) * BURG_MAXC;
+#pragma unroll
+            for (int n = 1; n < BURG_MAXC; n++) {
+                double sum = 0;
+#pragma unroll
+                for (int k = 1; k < BURG_MAXC; k++) if (k < n) sum += (double)(n - k) * cc[(n - k) & (BURG_MAXC - 1)] * av[k];
+                cc[n] = -av[n] - sum / n;
+                if (n < ncoef) o[n] = cc[n];
+            }
+            o[0] = log(alpha);
+        }
+        __syncwarp();
+    }
+}
+
 static inline size_t burg_smem_bytes(int w, int s) {
     return sizeof(double) * (2 * (256 + 130 + 130 + BURG_GROUPS * XPAD * 16) + 2 * NFFT) + sizeof(int16_t) * (size_t)(8 + (TILE_F - 1) * s + w + 1 + 8 + 8);
 }
@@ -507,6 +618,18 @@ static inline int launch_burg(const BurgParams &B, int src_mode, const BatchDesc
                               double *ceps, const double2 *tw, const double2 *ts, const double2 *ti, const double *win, const double *hann,
                               cudaStream_t s, LaunchCtx *lc, std::string &err) {
     if (ntiles <= 0) return CTU_OK;
+    if (B.nfft) {                                        // FFT sizes other than 512: the general kernel
+        const int M = B.nfft / 2;
+        const size_t bytes_any = (size_t)(ANY64_THREADS / 32) * (6 * M + 4) * sizeof(double);
+        AnyTables64 tb{B.any_tw, B.any_ts, win, B.nfft, B.log2m};
+        cudaError_t e2 = cudaFuncSetAttribute(k_burg_any, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_any);
+        lc->begin("k_burg_any", s);
+        if (e2 == cudaSuccess) k_burg_any<<<(unsigned)ntiles, ANY64_THREADS, bytes_any, s>>>(B, src_mode, bd, tb, pcm, spec, ceps, hann);
+        lc->end(s);
+        if (e2 == cudaSuccess) e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e2) + " (k_burg_any)"; return CTU_ERR_CUDA; }
+        return CTU_OK;
+    }
     if (B.window & 1) { err = "CTU: the Burg detector path needs an even window length"; return CTU_ERR_UNSUPPORTED; }
     size_t bytes = burg_smem_bytes(B.window, B.wshift);
     if (bytes > 227 * 1024) { err = "CTU: window shift too large for the Burg detector kernel"; return CTU_ERR_UNSUPPORTED; }

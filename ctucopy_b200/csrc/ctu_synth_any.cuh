@@ -9,38 +9,11 @@
 #define CTU_SYNTH_ANY_CUH
 
 #include "ctu_frames_any.cuh"
+#include "ctu_any64.cuh"
 
 namespace ctu {
 
-struct AnyTables64 {
-    const double2 *tw;       // e^{-2 pi i k / M}, k < M/2           (M = nfft/2)
-    const double2 *twsplit;  // -i/2 e^{-2 pi i k / nfft}, k <= M
-    const double *win;       // analysis window [window]
-    int nfft, log2m;
-};
-
-// in-place radix-2 decimation-in-time FFT of M complex points held by one warp in shared memory
-__device__ __forceinline__ void warp_fft_radix2(cpx<double> *z, int M, int log2m, const double2 *__restrict__ tw, int lane) {
-    for (int n = lane; n < M; n += 32) {
-        const int r = (int)(__brev((unsigned)n) >> (32 - log2m));
-        if (r > n) { const cpx<double> t = z[n]; z[n] = z[r]; z[r] = t; }
-    }
-    __syncwarp();
-    for (int len = 2, shift = log2m - 1; len <= M; len <<= 1, shift--) {
-        const int half = len >> 1;
-        for (int b = lane; b < (M >> 1); b += 32) {
-            const int j0 = b & (half - 1), i0 = ((b - j0) << 1) + j0, i1 = i0 + half;
-            const double2 w = __ldg(tw + ((size_t)j0 << shift));
-            const cpx<double> t = cmul(z[i1], mk<double>(w.x, w.y));
-            const cpx<double> a = z[i0];
-            z[i0] = a + t;
-            z[i1] = a - t;
-        }
-        __syncwarp();
-    }
-}
-
-constexpr int SYNANY_THREADS = 128;           // 4 warps: 4 x (4M + 4) doubles of shared memory, 131 KB at 2048 points
+constexpr int SYNANY_THREADS = ANY64_THREADS;  // 4 warps: 4 x (4M + 4) doubles of shared memory, 131 KB at 2048 points
 
 __global__ void __launch_bounds__(SYNANY_THREADS)
 k_synth_frames_any(int window, int wshift, double preem, int remove_dc, BatchDesc bd, AnyTables64 tb, const int16_t *__restrict__ pcm,
@@ -56,37 +29,12 @@ k_synth_frames_any(int window, int wshift, double preem, int remove_dc, BatchDes
     const int64_t row0 = bd.row_off[u] + t0;
     const int w = window, s = wshift;
     for (int f = wv; f < nf; f += SYNANY_THREADS / 32) {
-        // ---- analysis: the frame exactly as rawIN::get_frame builds it (src/io/in.cc:362-388) ---------------------
-        const int16_t *x = pcm + bd.pcm_off[u] + (int64_t)(t0 + f) * s;
-        const bool at_start = (t0 + f) == 0;
-        double *y = reinterpret_cast<double *>(z);
-        double sum = 0.0;
-        for (int i = lane; i < nfft; i += 32) {
-            double v = 0.0;
-            if (i < w) {
-                const double xi = (double)x[i];
-                const double xp = (i == 0 && at_start) ? 0.0 : (double)x[i - 1];
-                v = tb.win[i] * (xi - preem * xp);
-            }
-            y[i] = v;
-            sum += v;
-        }
-        if (remove_dc) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            const double mean = sum / (double)w;
-            __syncwarp();
-            for (int i = lane; i < w; i += 32) y[i] -= mean;
-        }
-        __syncwarp();
-        warp_fft_radix2(z, M, tb.log2m, tb.tw, lane);
+        any64_analysis(z, tb, pcm + bd.pcm_off[u] + (int64_t)(t0 + f) * s, (t0 + f) == 0, w, preem, remove_dc, lane);
         // ---- real-input split; enhanced magnitude on the original phase, scaled by 1/nfft (src/io/out.cc:417-424) ---
         const float *A = spec + (row0 + f) * nbins;
         const double invn = 1.0 / (double)nfft;
         for (int k = lane; k <= M; k += 32) {
-            const cpx<double> a = z[k == M ? 0 : k], b = conj(z[k == 0 ? 0 : M - k]);
-            const double2 ts = __ldg(tb.twsplit + k);
-            const cpx<double> X = mk<double>(0.5 * (a.x + b.x), 0.5 * (a.y + b.y)) + cmul(mk<double>(ts.x, ts.y), a - b);
+            const cpx<double> X = any64_bin(z, tb, k);
             const double mag = (double)__ldg(A + k) * invn;
             cpx<double> Yk;
             if (k == 0 || k == M) Yk = mk<double>(mag, 0.0);            // bin 0: phase 0; Nyquist: written non-negative
@@ -98,23 +46,10 @@ k_synth_frames_any(int window, int wshift, double preem, int remove_dc, BatchDes
             Y[k] = Yk;
         }
         __syncwarp();
-        // ---- inverse: Z[k] = E[k] + i O[k], E = (Y[k] + conj Y[M-k]) / 2, O = e^{+2 pi i k/nfft} (Y[k] - conj Y[M-k]) / 2;
-        //      z[n] = 2 sum_k Z[k] e^{+2 pi i k n / M} = 2 conj(FFT_M(conj Z))[n]; y[2n] = Re z[n], y[2n+1] = Im z[n] ----------
-        for (int k = lane; k < M; k += 32) {
-            const cpx<double> a = Y[k], b = conj(Y[M - k]);
-            const double2 ts = __ldg(tb.twsplit + k);                  // (-sin/2, -cos/2)  ->  e^{+i th}/2 = (-ts.y, -ts.x)
-            const cpx<double> E = mk<double>(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
-            const cpx<double> O = cmul(mk<double>(-ts.y, -ts.x), a - b);
-            z[k] = mk<double>(E.x - O.y, -(E.y + O.x));                // conj(Z[k])
-        }
-        __syncwarp();
-        warp_fft_radix2(z, M, tb.log2m, tb.tw, lane);
+        any64_inverse(z, Y, tb, lane);
+        const double *yv = reinterpret_cast<const double *>(z);
         double *o = yt + (row0 + f) * w;
-        for (int n = lane; n < M; n += 32) {
-            const cpx<double> v = z[n];
-            if (2 * n < w) o[2 * n] = 2.0 * v.x;
-            if (2 * n + 1 < w) o[2 * n + 1] = -2.0 * v.y;
-        }
+        for (int i = lane; i < w; i += 32) o[i] = yv[i];
         __syncwarp();
     }
 }

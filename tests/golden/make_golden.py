@@ -122,6 +122,12 @@ CASES = {
     "exten_raw_8k_2510": (["-fs", "8000"] + B[2:] + ["-preset", "exten", "-nr_a", "2", "-w", "25", "-s", "10", "-preem", "0.97", "-format_out", "raw"], "raw", {}),
     "exten_wave_44k": (["-fs", "44100"] + B[2:] + ["-preset", "exten", "-format_out", "wave"], "wave", {}),
     "resynth_raw_22k": (["-fs", "22050"] + B[2:] + ["-nr_mode", "none", "-w", "25", "-s", "10", "-preem", "0.97", "-remove_dc", "off", "-format_out", "raw"], "raw", {}),
+    # the Burg detector (spectral subtraction with its own VAD, LPC cepstral-distance criterion) at other FFT sizes
+    "fwss_burg_8k": (["-fs", "8000"] + B[2:] + MF + ["-nr_mode", "fwss", "-vad", "burg", "-format_out", "htk"], "htk", {}),
+    "fwss_burg_raw_8k": (["-fs", "8000"] + B[2:] + ["-w", "32", "-s", "16", "-nr_mode", "fwss", "-nr_b", "1.5", "-vad", "burg", "-format_out", "raw"], "raw", {}),
+    "2fwss_burg_44k": (["-fs", "44100"] + B[2:] + MF + ["-nr_mode", "2fwss", "-vad", "burg", "-nr_initsegs", "5", "-format_out", "htk"], "htk", {}),
+    "vad_cepdist_lpc_8k": (["-fs", "8000"] + B[2:] + MF + ["-format_out", "htk", "-vad_out_mode", "vad", "-vad_thr_mode", "adapt", "-vad_cri_mode", "cepdist",
+                                                          "-vad_cepdist_mode", "lpc", "-vad", "burg"], "htk", {"vad_out": True}),
     "logspec32k_40": (["-fs", "32000"] + B[2:] + MF + ["-fea_kind", "logspec", "-fb_definition", "40filters", "-format_out", "htk"], "htk", {}),
 }
 
