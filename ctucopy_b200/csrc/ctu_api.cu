@@ -607,15 +607,22 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     if (cudaSetDevice(device) != cudaSuccess) { h->err = "CUDA: cudaSetDevice failed"; return bail(CTU_ERR_CUDA); }
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (!h->fea_in && (st = build_fft_tables(h))) return bail(st);
+    if (h->nr_mode != NR_NONE && h->cfg.nr_when == 1 && !h->signal_out) h->precise = true;   // subtraction on band values
+    // VAD criterion = distance between feature vectors, fed to threshold state machines whose
+    // decisions must match the reference bit for bit: features in fp64 like the reference's
+    if (h->do_vad && h->vad_cri == VCRI_CEPDIST_FEA) h->precise = true;
     if (h->generic) {
-        if (h->precise) { h->err = "CTU: this configuration needs the fp64 path (band-domain noise reduction, LPC without the cube-root law, feature-vector VAD), built for 512-point frames only"; return bail(CTU_ERR_UNSUPPORTED); }
+        if (h->precise && (h->cfg.remove_dc1 || h->cfg.dither != 0.0)) {
+            h->err = "CTU: -remove_dc1 / -dither together with a configuration that needs the fp64 path (band-domain noise reduction, LPC without the cube-root law, feature-vector VAD)";
+            return bail(CTU_ERR_UNSUPPORTED);
+        }
         const int N = h->cfg.wfft, M = N / 2;
         const double PI = 3.14159265358979323846264338327950288;
         std::vector<float2> tw(std::max(1, M / 2)), ts(M + 1);
         for (int k = 0; k < M / 2; k++) tw[k] = make_float2((float)cos(-2 * PI * k / M), (float)sin(-2 * PI * k / M));
         for (int k = 0; k <= M; k++) { const double th = 2 * PI * k / N; ts[k] = make_float2((float)(-sin(th) / 2), (float)(-cos(th) / 2)); }
         const bool burg = h->vad_src == VADSRC_BURG || (h->do_vad && h->vad_cri == VCRI_CEPDIST_LPC);
-        if (h->signal_out || burg) {
+        if (h->signal_out || burg || h->precise) {
             std::vector<double2> twd(std::max(1, M / 2)), tsd(M + 1);
             for (int k = 0; k < M / 2; k++) twd[k] = make_double2(cos(-2 * PI * k / M), sin(-2 * PI * k / M));
             for (int k = 0; k <= M; k++) { const double th = 2 * PI * k / N; tsd[k] = make_double2(-sin(th) / 2, -cos(th) / 2); }
@@ -629,10 +636,6 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
         if ((st = upload(h, &h->d_any_tw, tw)) || (st = upload(h, &h->d_any_ts, ts)) || (st = upload(h, &h->d_any_fbw, h->fbw_all)) ||
             (st = upload(h, &h->d_any_bands, h->bands_all))) return bail(st);
     }
-    if (h->nr_mode != NR_NONE && h->cfg.nr_when == 1 && !h->signal_out) h->precise = true;   // subtraction on band values
-    // VAD criterion = distance between feature vectors, fed to threshold state machines whose
-    // decisions must match the reference bit for bit: features in fp64 like the reference's
-    if (h->do_vad && h->vad_cri == VCRI_CEPDIST_FEA) h->precise = true;
     if (h->precise) {
         if ((st = upload(h, &h->d_w64, h->w64)) || (st = upload(h, &h->d_m264, h->m264)) || (st = upload(h, &h->d_lift64, h->lift64))) return bail(st);
     }
@@ -1123,7 +1126,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     if (h->precise) {
         // fp64 path (ctu_precise.cuh): band-domain noise reduction / ill-conditioned LPC /
         // features that feed VAD decisions
-        Tables64 t64{h->d_tw256d, h->d_twsplitd, h->d_wind, h->d_w64, h->d_m264, h->d_lift64};
+        Tables64 t64{h->d_tw256d, h->d_twsplitd, h->d_wind, h->d_w64, h->d_m264, h->d_lift64, h->bp.nfft, h->bp.log2m, h->bp.any_tw, h->bp.any_ts};
         double *f64 = (kind == KIND_TRAPLOG) ? nullptr : p->d_fea64;
         if (nr_on && !before) {
             const uint8_t *fl = (h->nr_mode >= NR_HWSS) ? d_ext : nullptr;

@@ -29,7 +29,135 @@ struct Tables64 {
     const double *w;       // packed filter-bank taps (true scale)
     const double *m2;      // second-stage matrix [nrows][nb]
     const double *lift;    // lpc lifter [ncep+1]
+    // FFT sizes other than 512: k_frames64_any (nfft == 0: the specialised kernel)
+    int nfft, log2m;
+    const double2 *any_tw, *any_ts;
 };
+
+template <int LANES> __device__ __forceinline__ double lanes_sum_d(double v) {
+    if (LANES == 16) return group_sum16d(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Everything after the spectrum row (energies, filter bank, features) for one frame held by LANES threads: shared by the
+// 512-point kernel (16 threads per frame) and the general one (a warp per frame).  pr: spectrum row [nbins] (fp64).
+template <int SRC, int DST, int KIND, int LANES>
+__device__ __forceinline__ void frames64_tail(const FrameParams &P, const Tables64 &tb, int nbins, const double *pr, double *sY, double *sR, int c,
+                                              bool active, int64_t row, const double *__restrict__ src, double *__restrict__ dst64,
+                                              float *__restrict__ dst) {
+    const int nb = P.nb;
+    if ((SRC == SRC64_PCM || SRC == SRC64_SPEC) && (P.energy_mode == EN_NR || P.energy_mode == EN_IN)) {
+        // energy of the half spectrum (src/nr/nr.cc:36-45 squares the stored values; src/io/in.cc:403-413 sums power)
+        const bool square = (P.energy_mode == EN_NR) || P.take_sqrt;
+        double acc = 0;
+        if (active) for (int k = c; k < nbins; k += LANES) {
+            double v = pr[k];
+            if (square) v *= v;
+            if (k == 0 || k == nbins - 1) v *= 0.5;
+            acc += v;
+        }
+        acc = lanes_sum_d<LANES>(acc);
+        if (active && c == 0) P.energy[row] = (float)log(acc * 2.0);
+    }
+    if (SRC == SRC64_PCM || SRC == SRC64_SPEC) {
+        // filter bank: bands dealt round-robin to the group's threads, sequential sum
+        // over the taps in the reference's order (src/fea/fb.cc:76-83)
+        if (active) {
+            for (int b = c; b < nb; b += LANES) {
+                const int lo_ = P.lo[b], hi_ = P.hi[b];
+                const double *wp = tb.w + P.woff[b] - lo_;
+                double acc = 0;
+                for (int k = lo_; k <= hi_; k++) acc += pr[k] * wp[k];
+                if (P.inld) acc = pow(acc, 0.33);
+                sY[b] = acc;
+            }
+        }
+    } else {
+        if (active) for (int b = c; b < nb; b += LANES) sY[b] = src[row * nb + b];
+    }
+    __syncwarp();
+    if (DST == DST64_FB) {
+        if (active) for (int b = c; b < nb; b += LANES) dst64[row * nb + b] = sY[b];
+        __syncwarp();
+        return;
+    }
+    // ---- features --------------------------------------------------------------------------
+    float *orow = dst + row * P.out_stride;
+    double *orow64 = dst64 ? dst64 + row * P.out_stride : nullptr;
+    if (KIND == KIND_SPEC || KIND == KIND_LOGSPEC || KIND == KIND_TRAPLOG) {
+        if (P.energy_mode == EN_BANDS && active && c == 0) {
+            double acc = 0.5 * sY[0] * sY[0];
+            for (int b = 1; b < nb - 1; b++) acc += sY[b] * sY[b];
+            acc += 0.5 * sY[nb - 1] * sY[nb - 1];
+            P.energy[row] = (float)log(acc * 2.0);
+        }
+        if (active) for (int b = c; b < nb; b += LANES) {
+            double v = (KIND == KIND_SPEC) ? sY[b] : log(sY[b]);
+            orow[b] = (float)v;
+            if (orow64) orow64[b] = v;
+        }
+    } else if (KIND == KIND_DCTC) {
+        if (active) for (int b = c; b < nb; b += LANES) sY[b] = log(sY[b]);
+        __syncwarp();
+        if (active) for (int i = c; i < P.nrows; i += LANES) {
+            const double *m = tb.m2 + i * nb;
+            double acc = 0;
+            for (int k = 0; k < nb; k++) acc += sY[k] * m[k];
+            orow[i] = (float)acc;
+            if (orow64) orow64[i] = acc;
+        }
+    } else {
+        const int p = P.lporder;
+        if (active && P.lpa_square) for (int b = c; b < nb; b += LANES) sY[b] = sY[b] * sY[b];
+        __syncwarp();
+        if (active) for (int k = c; k <= p; k += LANES) {
+            const double *m = tb.m2 + k * nb;
+            double acc = 0;
+            for (int n = 0; n < nb; n++) acc += sY[n] * m[n];
+            sR[k] = acc;
+        }
+        __syncwarp();
+        if (active && c == 0) {
+            if (P.energy_mode == EN_LPC) P.energy[row] = (float)log(sR[0]);
+            double a[MAXR], aa[MAXR];
+            double Pe = sR[0];
+            double rc = -sR[1] / sR[0];
+            Pe = Pe * (1 - rc * rc);
+            a[0] = aa[0] = 1.0; a[1] = aa[1] = rc;
+            for (int ik = 2; ik <= p; ik++) {
+                double dm = sR[ik];
+                for (int n = 1; n <= ik - 1; n++) dm += aa[n] * sR[ik - n];
+                rc = -dm / Pe;
+                a[ik] = rc;
+                for (int n = 1; n <= ik - 1; n++) a[n] = aa[n] + rc * aa[ik - n];
+                for (int n = 1; n <= ik; n++) aa[n] = a[n];
+                Pe = Pe * (1 - rc * rc);
+            }
+            if (KIND == KIND_LPA) {
+                for (int i = 1; i <= p; i++) { orow[i - 1] = (float)a[i]; if (orow64) orow64[i - 1] = a[i]; }
+            } else {
+                double cc[MAXR];
+                const int N = P.ncep;
+                cc[0] = log(Pe);
+                for (int n = 1; n <= N; n++) {
+                    double sum = 0;
+                    if (n <= p) {
+                        for (int k = 1; k <= n - 1; k++) sum += (n - k) * cc[n - k] * a[k];
+                        cc[n] = -a[n] - sum / n;
+                    } else {
+                        for (int k = 1; k <= p; k++) sum += (n - k) * cc[n - k] * a[k];
+                        cc[n] = -sum / n;
+                    }
+                }
+                for (int n = 1; n <= N; n++) { double v = cc[n] * tb.lift[n]; orow[n - 1] = (float)v; if (orow64) orow64[n - 1] = v; }
+                if (P.c0_last) { orow[N] = (float)cc[0]; if (orow64) orow64[N] = cc[0]; }
+            }
+        }
+    }
+    __syncwarp();
+}
 
 template <int SRC, int DST, int KIND>
 __global__ void __launch_bounds__(P64_THREADS)
@@ -123,115 +251,44 @@ k_frames64(const __grid_constant__ FrameParams P, BatchDesc bd, Tables64 tb, con
             }
             __syncwarp();
         }
-        if ((SRC == SRC64_PCM || SRC == SRC64_SPEC) && (P.energy_mode == EN_NR || P.energy_mode == EN_IN)) {
-            // energy of the half spectrum (src/nr/nr.cc:36-45 squares the stored values; src/io/in.cc:403-413 sums power)
-            const bool square = (P.energy_mode == EN_NR) || P.take_sqrt;
-            double acc = 0;
-            if (active) for (int k = c; k < NBIN; k += GROUP) {
-                double v = pr[k];
-                if (square) v *= v;
-                if (k == 0 || k == NBIN - 1) v *= 0.5;
-                acc += v;
-            }
-            acc = group_sum16d(acc);
-            if (active && c == 0) P.energy[row0 + f] = (float)log(acc * 2.0);
-        }
-        if (SRC == SRC64_PCM || SRC == SRC64_SPEC) {
-            // filter bank: bands dealt round-robin to the group's threads, sequential sum
-            // over the taps in the reference's order (src/fea/fb.cc:76-83)
-            if (active) {
-                for (int b = c; b < nb; b += GROUP) {
-                    const int lo_ = P.lo[b], hi_ = P.hi[b];
-                    const double *wp = tb.w + P.woff[b] - lo_;
-                    double acc = 0;
-                    for (int k = lo_; k <= hi_; k++) acc += pr[k] * wp[k];
-                    if (P.inld) acc = pow(acc, 0.33);
-                    sY[b] = acc;
-                }
-            }
-        } else {
-            if (active) for (int b = c; b < nb; b += GROUP) sY[b] = src[(row0 + f) * nb + b];
-        }
-        __syncwarp();
-        if (DST == DST64_FB) {
-            if (active) for (int b = c; b < nb; b += GROUP) dst64[(row0 + f) * nb + b] = sY[b];
+        frames64_tail<SRC, DST, KIND, GROUP>(P, tb, NBIN, pr, sY, sR, c, active, row0 + f, src, dst64, dst);
+    }
+}
+
+// The same chain for FFT sizes other than 512: one warp per frame, front end from ctu_any64.cuh.
+template <int SRC, int DST, int KIND>
+__global__ void __launch_bounds__(ANY64_THREADS)
+k_frames64_any(const __grid_constant__ FrameParams P, BatchDesc bd, Tables64 tb, const int16_t *__restrict__ pcm, const double *__restrict__ src,
+               const float *__restrict__ spec, double *__restrict__ dst64, float *__restrict__ dst) {
+    extern __shared__ __align__(16) double smd[];
+    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+    const int nfft = tb.nfft, M = nfft >> 1, nbins = M + 1;
+    double *base = smd + (size_t)wv * (nfft + (M + 4) + 64 + 64);
+    cpx<double> *z = reinterpret_cast<cpx<double> *>(base);
+    double *pr = base + nfft;
+    double *sY = pr + (M + 4);
+    double *sR = sY + 64;
+    const AnyTables64 at{tb.any_tw, tb.any_ts, tb.win, nfft, tb.log2m};
+    const int2 tile = bd.tiles[blockIdx.x];
+    const int u = tile.x, t0 = tile.y;
+    const int nf = min(TILE_F, bd.nframes[u] - t0);
+    const int64_t row0 = bd.row_off[u] + t0;
+    for (int f = wv; f < nf; f += ANY64_THREADS / 32) {
+        if (SRC == SRC64_SPEC) {
+            for (int k = lane; k < nbins; k += 32) pr[k] = (double)spec[(row0 + f) * nbins + k];
             __syncwarp();
-            continue;
         }
-        // ---- features --------------------------------------------------------------------------
-        float *orow = dst + (row0 + f) * P.out_stride;
-        double *orow64 = dst64 ? dst64 + (row0 + f) * P.out_stride : nullptr;
-        if (KIND == KIND_SPEC || KIND == KIND_LOGSPEC || KIND == KIND_TRAPLOG) {
-            if (P.energy_mode == EN_BANDS && active && c == 0) {
-                double acc = 0.5 * sY[0] * sY[0];
-                for (int b = 1; b < nb - 1; b++) acc += sY[b] * sY[b];
-                acc += 0.5 * sY[nb - 1] * sY[nb - 1];
-                P.energy[row0 + f] = (float)log(acc * 2.0);
-            }
-            if (active) for (int b = c; b < nb; b += GROUP) {
-                double v = (KIND == KIND_SPEC) ? sY[b] : log(sY[b]);
-                orow[b] = (float)v;
-                if (orow64) orow64[b] = v;
-            }
-        } else if (KIND == KIND_DCTC) {
-            if (active) for (int b = c; b < nb; b += GROUP) sY[b] = log(sY[b]);
-            __syncwarp();
-            if (active) for (int i = c; i < P.nrows; i += GROUP) {
-                const double *m = tb.m2 + i * nb;
-                double acc = 0;
-                for (int k = 0; k < nb; k++) acc += sY[k] * m[k];
-                orow[i] = (float)acc;
-                if (orow64) orow64[i] = acc;
-            }
-        } else {
-            const int p = P.lporder;
-            if (active && P.lpa_square) for (int b = c; b < nb; b += GROUP) sY[b] = sY[b] * sY[b];
-            __syncwarp();
-            if (active) for (int k = c; k <= p; k += GROUP) {
-                const double *m = tb.m2 + k * nb;
-                double acc = 0;
-                for (int n = 0; n < nb; n++) acc += sY[n] * m[n];
-                sR[k] = acc;
+        if (SRC == SRC64_PCM) {
+            any64_analysis(z, at, pcm + bd.pcm_off[u] + (int64_t)(t0 + f) * P.wshift, (t0 + f) == 0, P.window, (double)P.preem, P.remove_dc, lane);
+            for (int k = lane; k <= M; k += 32) {
+                const cpx<double> X = any64_bin(z, at, k);
+                double pw = X.x * X.x + X.y * X.y;
+                if (k == 0 && P.remove_dc) pw = 1e-10;                 // fixed floor (src/io/in.cc:390)
+                pr[k] = P.take_sqrt ? sqrt(pw) : pw;
             }
             __syncwarp();
-            if (active && c == 0) {
-                if (P.energy_mode == EN_LPC) P.energy[row0 + f] = (float)log(sR[0]);
-                double a[MAXR], aa[MAXR];
-                double Pe = sR[0];
-                double rc = -sR[1] / sR[0];
-                Pe = Pe * (1 - rc * rc);
-                a[0] = aa[0] = 1.0; a[1] = aa[1] = rc;
-                for (int ik = 2; ik <= p; ik++) {
-                    double dm = sR[ik];
-                    for (int n = 1; n <= ik - 1; n++) dm += aa[n] * sR[ik - n];
-                    rc = -dm / Pe;
-                    a[ik] = rc;
-                    for (int n = 1; n <= ik - 1; n++) a[n] = aa[n] + rc * aa[ik - n];
-                    for (int n = 1; n <= ik; n++) aa[n] = a[n];
-                    Pe = Pe * (1 - rc * rc);
-                }
-                if (KIND == KIND_LPA) {
-                    for (int i = 1; i <= p; i++) { orow[i - 1] = (float)a[i]; if (orow64) orow64[i - 1] = a[i]; }
-                } else {
-                    double cc[MAXR];
-                    const int N = P.ncep;
-                    cc[0] = log(Pe);
-                    for (int n = 1; n <= N; n++) {
-                        double sum = 0;
-                        if (n <= p) {
-                            for (int k = 1; k <= n - 1; k++) sum += (n - k) * cc[n - k] * a[k];
-                            cc[n] = -a[n] - sum / n;
-                        } else {
-                            for (int k = 1; k <= p; k++) sum += (n - k) * cc[n - k] * a[k];
-                            cc[n] = -sum / n;
-                        }
-                    }
-                    for (int n = 1; n <= N; n++) { double v = cc[n] * tb.lift[n]; orow[n - 1] = (float)v; if (orow64) orow64[n - 1] = v; }
-                    if (P.c0_last) { orow[N] = (float)cc[0]; if (orow64) orow64[N] = cc[0]; }
-                }
-            }
         }
-        __syncwarp();
+        frames64_tail<SRC, DST, KIND, 32>(P, tb, nbins, pr, sY, sR, lane, true, row0 + f, src, dst64, dst);
     }
 }
 
@@ -244,6 +301,20 @@ static int launch_frames64_t(const FrameParams &P, const BatchDesc &bd, const Ta
                              const double *src, const float *spec, double *dst64, float *dst, cudaStream_t s, LaunchCtx *lc,
                              std::string &err) {
     if (ntiles <= 0) return CTU_OK;
+    if (tb.nfft) {
+        const size_t bytes_any = (size_t)(ANY64_THREADS / 32) * (tb.nfft + tb.nfft / 2 + 4 + 128) * sizeof(double);
+        auto ka = k_frames64_any<SRC, DST, KIND>;
+        cudaError_t e2 = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_any);
+        if (e2 == cudaSuccess) {
+            lc->begin(SRC == SRC64_PCM ? (DST == DST64_FB ? "k_frames64_any<pcm,fb>" : "k_frames64_any<pcm,fea>")
+                      : SRC == SRC64_SPEC ? (DST == DST64_FB ? "k_frames64_any<spec,fb>" : "k_frames64_any<spec,fea>") : "k_frames64_any<fb,fea>", s);
+            ka<<<(unsigned)ntiles, ANY64_THREADS, bytes_any, s>>>(P, bd, tb, pcm, src, spec, dst64, dst);
+            lc->end(s);
+            e2 = cudaGetLastError();
+        }
+        if (e2 != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e2) + " (k_frames64_any)"; return CTU_ERR_CUDA; }
+        return CTU_OK;
+    }
     size_t bytes = p64_smem_bytes();
     auto kern = k_frames64<SRC, DST, KIND>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

@@ -128,6 +128,12 @@ CASES = {
     "2fwss_burg_44k": (["-fs", "44100"] + B[2:] + MF + ["-nr_mode", "2fwss", "-vad", "burg", "-nr_initsegs", "5", "-format_out", "htk"], "htk", {}),
     "vad_cepdist_lpc_8k": (["-fs", "8000"] + B[2:] + MF + ["-format_out", "htk", "-vad_out_mode", "vad", "-vad_thr_mode", "adapt", "-vad_cri_mode", "cepdist",
                                                           "-vad_cepdist_mode", "lpc", "-vad", "burg"], "htk", {"vad_out": True}),
+    # the fp64 band path (noise reduction after the filter bank, LPC on a mel bank, feature-vector VAD criterion) at other FFT sizes
+    "mfcc_exten_afterFB_8k": (["-fs", "8000"] + B[2:] + MF + ["-nr_mode", "exten", "-nr_when", "afterFB", "-nr_a", "2", "-fea_E", "on", "-format_out", "htk"], "htk", {}),
+    "lpc_mel_inld_44k": (["-fs", "44100"] + B[2:] + MF + ["-fea_kind", "lpc", "-fb_inld", "on", "-fb_eqld", "on", "-fea_ncepcoefs", "16", "-nr_mode", "exten", "-nr_when", "afterFB",
+                                                         "-format_out", "htk"], "htk", {}),
+    "vad_cepdist_fea_8k": (["-fs", "8000"] + B[2:] + MF + ["-format_out", "htk", "-vad_out_mode", "vad", "-vad_thr_mode", "adapt", "-vad_cri_mode", "cepdist",
+                                                          "-vad_cepdist_mode", "fea", "-fea_delta", "d"], "htk", {"vad_out": True}),
     "logspec32k_40": (["-fs", "32000"] + B[2:] + MF + ["-fea_kind", "logspec", "-fb_definition", "40filters", "-format_out", "htk"], "htk", {}),
 }
 
