@@ -611,30 +611,33 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     // VAD criterion = distance between feature vectors, fed to threshold state machines whose
     // decisions must match the reference bit for bit: features in fp64 like the reference's
     if (h->do_vad && h->vad_cri == VCRI_CEPDIST_FEA) h->precise = true;
-    if (h->generic) {
-        if (h->precise && (h->cfg.remove_dc1 || h->cfg.dither != 0.0)) {
+    // the fp64 general kernels (ctu_any64.cuh) also take the 512-point frames whose window length is odd (e.g. 32 ms at
+    // 11.025 kHz = 353 samples): the specialised synthesis / Burg kernels pair samples two by two
+    const bool any64 = c_wfft_is_general(h) || (h->cfg.window & 1);
+    if (h->generic || any64) {
+        if (h->generic && h->precise && (h->cfg.remove_dc1 || h->cfg.dither != 0.0)) {
             h->err = "CTU: -remove_dc1 / -dither together with a configuration that needs the fp64 path (band-domain noise reduction, LPC without the cube-root law, feature-vector VAD)";
             return bail(CTU_ERR_UNSUPPORTED);
         }
         const int N = h->cfg.wfft, M = N / 2;
         const double PI = 3.14159265358979323846264338327950288;
-        std::vector<float2> tw(std::max(1, M / 2)), ts(M + 1);
-        for (int k = 0; k < M / 2; k++) tw[k] = make_float2((float)cos(-2 * PI * k / M), (float)sin(-2 * PI * k / M));
-        for (int k = 0; k <= M; k++) { const double th = 2 * PI * k / N; ts[k] = make_float2((float)(-sin(th) / 2), (float)(-cos(th) / 2)); }
         const bool burg = h->vad_src == VADSRC_BURG || (h->do_vad && h->vad_cri == VCRI_CEPDIST_LPC);
-        if (h->signal_out || burg || h->precise) {
+        if (any64 && (h->signal_out || burg || h->precise)) {
             std::vector<double2> twd(std::max(1, M / 2)), tsd(M + 1);
             for (int k = 0; k < M / 2; k++) twd[k] = make_double2(cos(-2 * PI * k / M), sin(-2 * PI * k / M));
             for (int k = 0; k <= M; k++) { const double th = 2 * PI * k / N; tsd[k] = make_double2(-sin(th) / 2, -cos(th) / 2); }
             if ((st = upload(h, &h->d_any_tw64, twd)) || (st = upload(h, &h->d_any_ts64, tsd))) return bail(st);
-            if (c_wfft_is_general(h)) {
-                int lg = 0;
-                while ((1 << lg) < M) lg++;
-                h->bp.nfft = N; h->bp.log2m = lg; h->bp.any_tw = h->d_any_tw64; h->bp.any_ts = h->d_any_ts64;
-            }
+            int lg = 0;
+            while ((1 << lg) < M) lg++;
+            h->bp.nfft = N; h->bp.log2m = lg; h->bp.any_tw = h->d_any_tw64; h->bp.any_ts = h->d_any_ts64;
         }
-        if ((st = upload(h, &h->d_any_tw, tw)) || (st = upload(h, &h->d_any_ts, ts)) || (st = upload(h, &h->d_any_fbw, h->fbw_all)) ||
-            (st = upload(h, &h->d_any_bands, h->bands_all))) return bail(st);
+        if (h->generic) {
+            std::vector<float2> tw(std::max(1, M / 2)), ts(M + 1);
+            for (int k = 0; k < M / 2; k++) tw[k] = make_float2((float)cos(-2 * PI * k / M), (float)sin(-2 * PI * k / M));
+            for (int k = 0; k <= M; k++) { const double th = 2 * PI * k / N; ts[k] = make_float2((float)(-sin(th) / 2), (float)(-cos(th) / 2)); }
+            if ((st = upload(h, &h->d_any_tw, tw)) || (st = upload(h, &h->d_any_ts, ts)) || (st = upload(h, &h->d_any_fbw, h->fbw_all)) ||
+                (st = upload(h, &h->d_any_bands, h->bands_all))) return bail(st);
+        }
     }
     if (h->precise) {
         if ((st = upload(h, &h->d_w64, h->w64)) || (st = upload(h, &h->d_m264, h->m264)) || (st = upload(h, &h->d_lift64, h->lift64))) return bail(st);
@@ -700,7 +703,7 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     p->nframes.resize(n); p->row_off.resize(n + 1); p->osamp_off.resize(n + 1);
     p->tile32_off.resize(n + 1); p->tile64_off.resize(n + 1); p->tileS_off.resize(n + 1); p->tileF_off.resize(n + 1);
     p->syn_tile = std::max(1, SYN_FRAMES - h->sp.hh);
-    if (h->signal_out && !h->generic && h->sp.hh >= SYN_FRAMES) { delete p; return fail(h, CTU_ERR_UNSUPPORTED, "CTU: window / shift ratio too large for synthesis"); }
+    if (h->signal_out && !h->bp.nfft && h->sp.hh >= SYN_FRAMES) { delete p; return fail(h, CTU_ERR_UNSUPPORTED, "CTU: window / shift ratio too large for synthesis"); }
     p->rows_per_utt.assign(n, 0);
     const int w = h->cfg.window, s = h->cfg.wshift;
     int64_t rows = 0, osamp = 0, t32 = 0, t64 = 0, tS = 0, tF = 0;
@@ -763,7 +766,7 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     const bool lpc_kind = (h->fea_kind == FEA_LPA || h->fea_kind == FEA_LPC);
     const bool need_fb = !h->signal_out && ((nr_on && h->cfg.nr_when == 1) || lpc_kind);
     if (need_spec && (st = dev_alloc(h, p, &p->d_spec, (size_t)rows * h->nbins))) { ctu_plan_destroy(p); return st; }
-    if (h->signal_out && h->generic && (st = dev_alloc(h, p, &p->d_yt, (size_t)rows * h->cfg.window))) { ctu_plan_destroy(p); return st; }
+    if (h->signal_out && h->bp.nfft && (st = dev_alloc(h, p, &p->d_yt, (size_t)rows * h->cfg.window))) { ctu_plan_destroy(p); return st; }
     if (need_fb && !h->precise && (st = dev_alloc(h, p, &p->d_fb, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     if (need_fb && h->precise && (st = dev_alloc(h, p, &p->d_fb64, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     if (h->do_vad && h->vad_cri == VCRI_CEPDIST_FEA && (st = dev_alloc(h, p, &p->d_fea64, (size_t)rows * h->feature_dim))) { ctu_plan_destroy(p); return st; }
@@ -1087,8 +1090,8 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
         if (h->vad_src == VADSRC_FILE && d_vadnr && h->nr_mode >= NR_HWSS)
             CK(cudaMemcpyAsync(d_vadnr + r.row0, d_ext + r.row0, r.nrows, cudaMemcpyDeviceToDevice, s));
     }
-    if (h->signal_out && h->generic) {
-        // other FFT sizes: frames -> segments (fp64, one warp per frame), then overlap-add per 16-hop tile
+    if (h->signal_out && h->bp.nfft) {
+        // other FFT sizes / odd window lengths: frames -> segments (fp64, one warp per frame), then overlap-add per 16-hop tile
         if (r.tF_n <= 0) return CTU_OK;
         BatchDesc bdF{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tilesF + r.tF_0};
         const int N = h->cfg.wfft, M = N / 2;

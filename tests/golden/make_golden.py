@@ -134,6 +134,9 @@ CASES = {
                                                          "-format_out", "htk"], "htk", {}),
     "vad_cepdist_fea_8k": (["-fs", "8000"] + B[2:] + MF + ["-format_out", "htk", "-vad_out_mode", "vad", "-vad_thr_mode", "adapt", "-vad_cri_mode", "cepdist",
                                                           "-vad_cepdist_mode", "fea", "-fea_delta", "d"], "htk", {"vad_out": True}),
+    # odd window lengths inside 512-point frames (32 ms at 11.025 kHz = 353 samples): synthesis and the Burg detector
+    "exten_raw_11k": (["-fs", "11025"] + B[2:] + ["-preset", "exten", "-format_out", "raw"], "raw", {}),
+    "fwss_burg_11k": (["-fs", "11025"] + B[2:] + MF + ["-w", "32", "-s", "16", "-nr_mode", "fwss", "-vad", "burg", "-format_out", "htk"], "htk", {}),
     "logspec32k_40": (["-fs", "32000"] + B[2:] + MF + ["-fea_kind", "logspec", "-fb_definition", "40filters", "-format_out", "htk"], "htk", {}),
 }
 

@@ -2,7 +2,7 @@
 """Randomised option sweep.  Draws valid command lines from the hot-path option space and compares
    cpu : the numpy oracle against the REFERENCE BINARY (oracle/_ref, needs /root/reference built here)
    gpu : the CUDA path against the oracle
-on two short inputs.  usage: python tools/parity_sweep.py cpu|gpu [n] [seed] [share of waveform-output draws]"""
+on two short inputs.  usage: python tools/parity_sweep.py cpu|gpu [n] [seed] [share of waveform-output draws] [share of draws at other sampling rates]"""
 import os
 import random
 import sys
@@ -32,6 +32,17 @@ def draw_signal(rng):
 
 
 def draw(rng):
+    a = draw16(rng)
+    # other sampling rates: the same samples read at another rate -> 256- to 2048-point frames (general kernels)
+    if rng.random() < OTHER_FS_SHARE:
+        a[1] = rng.choice(["8000", "8000", "11025", "22050", "44100"])
+    return a
+
+
+OTHER_FS_SHARE = 0.0    # 5th command-line argument
+
+
+def draw16(rng):
     if rng.random() < SIGNAL_SHARE:
         return draw_signal(rng)
     a = list(B)
@@ -116,6 +127,8 @@ def main():
     rng = random.Random(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
     global SIGNAL_SHARE
     SIGNAL_SHARE = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0
+    global OTHER_FS_SHARE
+    OTHER_FS_SHARE = float(sys.argv[5]) if len(sys.argv) > 5 else 0.0
     ins = [gu.inputs()[i] for i in (0, 5)]
     nbad = nrun = nskip = 0
     if mode == "cpu":
@@ -134,7 +147,7 @@ def main():
             do_vad = "-vad_out_mode" in args
             r = rr.run_reference(args, ins, opt="O0", one_per_process=True, vad_out=do_vad)
             if r["returncode"] != 0 or any(x is None for x in r["outputs"]):
-                print("REFERENCE FAILED rc=%s: %s\n   %s" % (r["returncode"], " ".join(args[7:]), r["stderr"].strip()[-120:]))
+                print("REFERENCE FAILED rc=%s: %s\n   %s" % (r["returncode"], ("-fs %s " % args[1]) + " ".join(args[7:]), r["stderr"].strip()[-120:]))
                 nskip += 1
                 continue
             for i in range(len(ins)):
@@ -144,7 +157,7 @@ def main():
                     nrun += 1
                     if got.shape != want.shape or not np.array_equal(got, want):
                         nbad += 1
-                        print("ORACLE != REFERENCE waveform (input %d, %s vs %s, differing %s): %s" % (i, got.shape, want.shape, int((got != want).sum()) if got.shape == want.shape else -1, " ".join(args[7:])))
+                        print("ORACLE != REFERENCE waveform (input %d, %s vs %s, differing %s): %s" % (i, got.shape, want.shape, int((got != want).sum()) if got.shape == want.shape else -1, ("-fs %s " % args[1]) + " ".join(args[7:])))
                     continue
                 want = rr.parse_htk(r["outputs"][i])[1]
                 got = refs[i].features
@@ -156,7 +169,7 @@ def main():
                 if not ok:
                     nbad += 1
                     d = np.abs(got - want)[np.isfinite(want)].max() if got.shape == want.shape else -1
-                    print("ORACLE != REFERENCE (input %d, shape %s vs %s, max diff %.3g): %s" % (i, got.shape, want.shape, d, " ".join(args[7:])))
+                    print("ORACLE != REFERENCE (input %d, shape %s vs %s, max diff %.3g): %s" % (i, got.shape, want.shape, d, ("-fs %s " % args[1]) + " ".join(args[7:])))
         else:
             try:
                 res = cb.extract(args, ins)
@@ -164,7 +177,7 @@ def main():
                 if e.status == 3:
                     nskip += 1
                     continue
-                print("CUDA PATH ERROR %s: %s" % (e.message[:80], " ".join(args[7:])))
+                print("CUDA PATH ERROR %s: %s" % (e.message[:80], ("-fs %s " % args[1]) + " ".join(args[7:])))
                 nbad += 1
                 continue
             for i in range(len(ins)):
@@ -186,7 +199,7 @@ def main():
                         ok, why = False, why + "; VAD-module decisions differ at %d frames" % int((gv != refs[i].vad.vad).sum())
                 if not ok:
                     nbad += 1
-                    print("CUDA != ORACLE (input %d): %s\n   %s" % (i, why, " ".join(args[7:])))
+                    print("CUDA != ORACLE (input %d): %s\n   %s" % (i, why, ("-fs %s " % args[1]) + " ".join(args[7:])))
     print("sweep %s: %d comparisons, %d mismatches, %d option sets skipped" % (mode, nrun, nbad, nskip))
     return 1 if nbad else 0
 
