@@ -738,84 +738,110 @@ __global__ void k_vad_energy(const __grid_constant__ VadParams V, const float *_
     if (lane == 0) cri[r] = V.energy_db ? 10.0 * log10(DBL_MIN + e) : e;
 }
 
-// thresholds + background update + majority filter, one thread per utterance
-__global__ void k_vad_scan(const __grid_constant__ VadParams V, const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int u0,
-                           int n_utts, const double *__restrict__ cri_frame, const double *__restrict__ ceps,
-                           const double *__restrict__ fea, int fea_dim /* row pitch */, uint8_t *__restrict__ vad0_tmp, uint8_t *__restrict__ vad_out,
-                           uint8_t *__restrict__ keep) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+// thresholds + background update + majority filter (src/vad/vad.cc:249-276, 300-420, src/vad/vad.h:126-175).
+// One WARP per utterance, like k_cepdet: the warp stages the criterion inputs of 32 frames in shared memory (coalesced, all
+// loads in flight at once), lane 0 runs the sequential state machines out of shared memory -- same operations in the same
+// order as before -- and the majority filter runs one row per lane.  With one thread per utterance every frame waited for
+// its own memory round trip: 1-3 ms per launch whatever the batch size, which the chunked host path paid per chunk.
+constexpr int VADSCAN_WARPS = 4;
+__global__ void __launch_bounds__(VADSCAN_WARPS * 32)
+k_vad_scan(const __grid_constant__ VadParams V, const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int u0,
+           int n_utts, const double *__restrict__ cri_frame, const double *__restrict__ ceps,
+           const double *__restrict__ fea, int fea_dim /* row pitch */, uint8_t *__restrict__ vad0_tmp, uint8_t *__restrict__ vad_out,
+           uint8_t *__restrict__ keep) {
+    extern __shared__ __align__(16) double sm_vs[];
+    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+    const int i = blockIdx.x * VADSCAN_WARPS + wv;
     if (i >= n_utts) return;
     const int u = u0 + i;
     const int T = nframes[u];
     const int64_t R0 = row_off[u];
-    double c0[64];
+    const int cn = (V.cri == VCRI_ENERGY) ? 1 : V.cep_n;
+    double *sc = sm_vs + (size_t)wv * (32 * cn + 64 + 4);      // [32][cn] staged criterion inputs
+    double *c0 = sc + 32 * cn;                                // [64] running background (cepstral criteria)
+    uint8_t *sv = reinterpret_cast<uint8_t *>(c0 + 64);       // [32] decisions of the block
     double s_min = 0, s_max = 0, mean = 0, mean2 = 0, var = 0, dmin = 0, dmax = 0, dyn = 0;
-    const int cn = V.cep_n;
-    for (int r = 0; r < T; r++) {
-        const int64_t fidx = R0 + min(r + V.latency, T - 1);   // spectrum frame this row is paired with
-        double c;
+    for (int base = 0; base < T; base += 32) {
+        const int n = min(32, T - base);
         if (V.cri == VCRI_ENERGY) {
-            c = cri_frame[fidx];
+            if (lane < n) sc[lane] = cri_frame[R0 + min(base + lane + V.latency, T - 1)];
         } else {
-            // cepstral distance to the running background c0 (src/vad/vad.cc:249-276)
-            double sum = 0;
-            if (r == 0) {
-                for (int k = 0; k < cn; k++) c0[k] = (V.cri == VCRI_CEPDIST_LPC) ? ceps[fidx * BURG_MAXC + k] : fea[(R0 + r) * fea_dim + k];
-                c = 0.0;
-            } else {
-                for (int k = 0; k < cn; k++) {
-                    double ci = (V.cri == VCRI_CEPDIST_LPC) ? ceps[fidx * BURG_MAXC + k] : fea[(R0 + r) * fea_dim + k];
-                    if (r == 1) c0[k] = (c0[k] + ci) / 2.0;
-                    if ((V.cri == VCRI_CEPDIST_LPC) ? (k >= 1) : (k != V.fea_skip)) { double d = ci - c0[k]; sum += d * d; }
+            for (int idx = lane; idx < n * cn; idx += 32) {
+                const int j = idx / cn, k = idx - j * cn;
+                const int64_t fidx = R0 + min(base + j + V.latency, T - 1);   // spectrum frame this row is paired with
+                sc[idx] = (V.cri == VCRI_CEPDIST_LPC) ? ceps[fidx * BURG_MAXC + k] : fea[(R0 + base + j) * fea_dim + k];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (int j = 0; j < n; j++) {
+                const int r = base + j;
+                const double *ci_row = sc + j * cn;
+                double c;
+                if (V.cri == VCRI_ENERGY) {
+                    c = ci_row[0];
+                } else {
+                    // cepstral distance to the running background c0 (src/vad/vad.cc:249-276)
+                    double sum = 0;
+                    if (r == 0) {
+                        for (int k = 0; k < cn; k++) c0[k] = ci_row[k];
+                        c = 0.0;
+                    } else {
+                        for (int k = 0; k < cn; k++) {
+                            const double ci = ci_row[k];
+                            if (r == 1) c0[k] = (c0[k] + ci) / 2.0;
+                            if ((V.cri == VCRI_CEPDIST_LPC) ? (k >= 1) : (k != V.fea_skip)) { double d = ci - c0[k]; sum += d * d; }
+                        }
+                        c = 4.3429 * sqrt(2 * sum);
+                    }
                 }
-                c = 4.3429 * sqrt(2 * sum);
+                bool v;
+                if (V.thr == VTHR_ABSOLUTE) {
+                    v = c >= V.abs_thr;
+                } else if (V.thr == VTHR_PERC) {
+                    if (r == 0 || (double)r < (double)V.perc_init) { s_min = c; s_max = c; }
+                    else { s_min = (c < s_min) ? c : s_min; s_max = (c > s_max) ? c : s_max; }
+                    double th = s_min + (V.perc_thr / 100.0) * (s_max - s_min);
+                    v = c >= th;
+                } else if (V.thr == VTHR_ADAPT) {
+                    if (r == 0) { mean = c; mean2 = c * c; var = 0.0; v = false; }
+                    else {
+                        double th = mean + V.adapt_za * sqrt(var);
+                        if ((c < th) || (r <= V.adapt_init)) {
+                            mean = V.adapt_q * mean + (1.0 - V.adapt_q) * c;
+                            mean2 = V.adapt_q * mean2 + (1.0 - V.adapt_q) * c * c;
+                            var = mean2 - mean * mean;
+                            v = false;
+                        } else v = true;
+                    }
+                } else {
+                    const int i0 = max(1, V.dyn_init);
+                    if (r < i0) { dmax = c; dmin = c; dyn = 0.0; v = false; }
+                    else if (r == i0) {
+                        dmax = fmax(dmax, c) + V.dyn_min / 10.0;
+                        dmin = fmin(dmin, c) - V.dyn_min / 10.0;
+                        dyn = dmax - dmin; v = false;
+                    } else {
+                        if (dmax < c) dmax = V.qmaxinc * dmax + (1.0 - V.qmaxinc) * c; else dmax = V.qmaxdec * dmax + (1.0 - V.qmaxdec) * c;
+                        if (dmin > c) dmin = V.qmindec * dmin + (1.0 - V.qmindec) * c; else dmin = V.qmininc * dmin + (1.0 - V.qmininc) * c;
+                        dyn = dmax - dmin;
+                        double th = dmin + (V.dyn_perc / 100.0) * dyn;
+                        v = (c > th) && (dyn > V.dyn_min);
+                    }
+                }
+                sv[j] = v ? 1 : 0;
+                if (V.cri != VCRI_ENERGY && !(v && r > V.cep_init)) {
+                    for (int k = 0; k < cn; k++) c0[k] = V.cep_p * c0[k] + (1.0 - V.cep_p) * ci_row[k];
+                }
             }
         }
-        bool v;
-        if (V.thr == VTHR_ABSOLUTE) {
-            v = c >= V.abs_thr;
-        } else if (V.thr == VTHR_PERC) {
-            if (r == 0 || (double)r < (double)V.perc_init) { s_min = c; s_max = c; }
-            else { s_min = (c < s_min) ? c : s_min; s_max = (c > s_max) ? c : s_max; }
-            double th = s_min + (V.perc_thr / 100.0) * (s_max - s_min);
-            v = c >= th;
-        } else if (V.thr == VTHR_ADAPT) {
-            if (r == 0) { mean = c; mean2 = c * c; var = 0.0; v = false; }
-            else {
-                double th = mean + V.adapt_za * sqrt(var);
-                if ((c < th) || (r <= V.adapt_init)) {
-                    mean = V.adapt_q * mean + (1.0 - V.adapt_q) * c;
-                    mean2 = V.adapt_q * mean2 + (1.0 - V.adapt_q) * c * c;
-                    var = mean2 - mean * mean;
-                    v = false;
-                } else v = true;
-            }
-        } else {
-            const int i0 = max(1, V.dyn_init);
-            if (r < i0) { dmax = c; dmin = c; dyn = 0.0; v = false; }
-            else if (r == i0) {
-                dmax = fmax(dmax, c) + V.dyn_min / 10.0;
-                dmin = fmin(dmin, c) - V.dyn_min / 10.0;
-                dyn = dmax - dmin; v = false;
-            } else {
-                if (dmax < c) dmax = V.qmaxinc * dmax + (1.0 - V.qmaxinc) * c; else dmax = V.qmaxdec * dmax + (1.0 - V.qmaxdec) * c;
-                if (dmin > c) dmin = V.qmindec * dmin + (1.0 - V.qmindec) * c; else dmin = V.qmininc * dmin + (1.0 - V.qmininc) * c;
-                dyn = dmax - dmin;
-                double th = dmin + (V.dyn_perc / 100.0) * dyn;
-                v = (c > th) && (dyn > V.dyn_min);
-            }
-        }
-        vad0_tmp[R0 + r] = v ? 1 : 0;
-        if (V.cri != VCRI_ENERGY && !(v && r > V.cep_init)) {
-            for (int k = 0; k < cn; k++) {
-                double ci = (V.cri == VCRI_CEPDIST_LPC) ? ceps[fidx * BURG_MAXC + k] : fea[(R0 + r) * fea_dim + k];
-                c0[k] = V.cep_p * c0[k] + (1.0 - V.cep_p) * ci;
-            }
-        }
+        __syncwarp();
+        if (lane < n) vad0_tmp[R0 + base + lane] = sv[lane];
+        __syncwarp();
     }
     // majority vote over `order` decisions centred on the row; zeros beyond both ends
     const int h = (V.order - 1) / 2;
-    for (int r = 0; r < T; r++) {
+    for (int r = lane; r < T; r += 32) {
         int sum = 0;
         for (int q = r + h - V.order + 1; q <= r + h; q++)
             if (q >= 0 && q < T) sum += vad0_tmp[R0 + q];
@@ -1081,7 +1107,10 @@ static inline int launch_vad_module(VadParams V, const BurgParams &B, const Batc
     if (V.cep_n > 64) { err = "CTU: cepstral-distance VAD supports vectors of up to 64 values"; return CTU_ERR_UNSUPPORTED; }
     if (e == cudaSuccess) {
         lc->begin("k_vad_scan", s);
-        k_vad_scan<<<(n + 63) / 64, 64, 0, s>>>(V, d_nframes, d_row_off, u0, n, d_cri, d_ceps, d_fea64, fea_dim, d_vad0, d_vadout, d_keep);
+        const int cn_s = (V.cri == VCRI_ENERGY) ? 1 : V.cep_n;
+        const size_t vs_bytes = (size_t)VADSCAN_WARPS * (32 * cn_s + 64 + 4) * sizeof(double);
+        e = cudaFuncSetAttribute(k_vad_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs_bytes);
+        k_vad_scan<<<(n + VADSCAN_WARPS - 1) / VADSCAN_WARPS, VADSCAN_WARPS * 32, vs_bytes, s>>>(V, d_nframes, d_row_off, u0, n, d_cri, d_ceps, d_fea64, fea_dim, d_vad0, d_vadout, d_keep);
         lc->end(s);
         e = cudaGetLastError();
     }
