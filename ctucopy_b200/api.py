@@ -107,6 +107,8 @@ def lib() -> C.CDLL:
     L.ctu_input_dim.argtypes = [vp]; L.ctu_input_dim.restype = C.c_int
     L.ctu_plan_run_device_fea.argtypes = [vp, vp, vp, vp]; L.ctu_plan_run_device_fea.restype = C.c_int
     L.ctu_plan_run_host_fea.argtypes = [vp, vp, vp]; L.ctu_plan_run_host_fea.restype = C.c_int
+    L.ctu_g711_table.argtypes = [C.c_int, vp]; L.ctu_g711_table.restype = C.c_int
+    L.ctu_plan_run_host_g711.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]; L.ctu_plan_run_host_g711.restype = C.c_int
     L.ctu_is_signal_output.argtypes = [vp]; L.ctu_is_signal_output.restype = C.c_int
     L.ctu_num_bands.argtypes = [vp]; L.ctu_num_bands.restype = C.c_int
     L.ctu_fb_matrix.argtypes = [vp, vp, vp, vp]; L.ctu_fb_matrix.restype = C.c_int
@@ -321,10 +323,11 @@ class Plan:
         self.hd._check(self.L.ctu_plan_run_device_fea(self.p, d_fea_in, d_features, stream))
 
     def run_host(self, pcm: np.ndarray, ext_vad: Optional[np.ndarray] = None, *, features: Optional[np.ndarray] = None,
-                 waveform: Optional[np.ndarray] = None, want_vad: bool = True) -> Result:
-        """End to end with host buffers (numpy, ideally pinned): H2D + kernels + D2H."""
+                 waveform: Optional[np.ndarray] = None, want_vad: bool = True, g711: Optional[str] = None) -> Result:
+        """End to end with host buffers (numpy, ideally pinned): H2D + kernels + D2H.  g711 = "alaw" | "mulaw": `pcm` holds
+        the 8-bit codes of the files, expanded on the device (ctu_plan_run_host_g711)."""
         hd = self.hd
-        assert pcm.dtype == np.int16 and pcm.flags.c_contiguous and len(pcm) == int(self.offsets[-1])
+        assert pcm.dtype == (np.uint8 if g711 else np.int16) and pcm.flags.c_contiguous and len(pcm) == int(self.offsets[-1])
         dim = hd.feature_dim
         if hd.signal_output:
             if waveform is None:
@@ -336,7 +339,11 @@ class Plan:
         if ext_vad is not None:
             ext_vad = np.ascontiguousarray(ext_vad, dtype=np.uint8)
             assert len(ext_vad) == self.total_frames
-        hd._check(self.L.ctu_plan_run_host(self.p, _ptr(pcm), _ptr(ext_vad), _ptr(features), _ptr(waveform), _ptr(vnr), _ptr(vout)))
+        if g711:
+            hd._check(self.L.ctu_plan_run_host_g711(self.p, _ptr(pcm), 1 if g711 == "alaw" else 0, _ptr(ext_vad), _ptr(features), _ptr(waveform),
+                                                    _ptr(vnr), _ptr(vout)))
+        else:
+            hd._check(self.L.ctu_plan_run_host(self.p, _ptr(pcm), _ptr(ext_vad), _ptr(features), _ptr(waveform), _ptr(vnr), _ptr(vout)))
         return Result(self.frames_per_utt.copy(), self.rows_per_utt(), self.row_offsets, features, waveform, self.wave_offsets, vnr, vout)
 
 
@@ -350,6 +357,26 @@ def extract(argv: Sequence[str], utterances: List[np.ndarray], ext_vad: Optional
             pcm = np.ascontiguousarray(np.concatenate(utterances).astype(np.int16)) if utterances else np.zeros(0, np.int16)
             ev = np.concatenate(ext_vad).astype(np.uint8) if ext_vad is not None else None
             return plan.run_host(pcm, ev)
+        finally:
+            plan.close()
+    finally:
+        hd.close()
+
+
+def g711_table(alaw: bool) -> np.ndarray:
+    """The 256 expansion values the library uses (host-only call, no GPU needed)."""
+    t = np.zeros(256, dtype=np.int16)
+    lib().ctu_g711_table(1 if alaw else 0, t.ctypes.data)
+    return t
+
+
+def extract_g711(argv: Sequence[str], code_streams: List[np.ndarray], alaw: bool, device: int = 0) -> Result:
+    """`ctucopy -format_in alaw|mulaw <argv> -S list`: the 8-bit codes go to the GPU as they are."""
+    hd = Handle(argv, device)
+    try:
+        plan = hd.plan([len(u) for u in code_streams])
+        try:
+            return plan.run_host(np.ascontiguousarray(np.concatenate(code_streams).astype(np.uint8)), g711="alaw" if alaw else "mulaw")
         finally:
             plan.close()
     finally:

@@ -70,6 +70,7 @@ struct ctu_handle {
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     // device blocks of destroyed plans, kept for the next plan: a list is processed as a sequence of plans of
     // similar size, and cudaMalloc / cudaFree of gigabytes cost more than the kernels that use them
+    int16_t *d_g711[2] = {nullptr, nullptr};   // expansion tables (mu-law, A-law), uploaded on first use
     uint64_t rand_pos = 0;               // -dither: values of the process-wide rand() stream drawn by earlier plans
     struct PoolBlock { void *p; size_t bytes; bool used; };
     std::vector<PoolBlock> pool;
@@ -113,6 +114,7 @@ struct ctu_plan {
     int64_t workspace_bytes = 0;
     // buffers owned for the host entry point
     int16_t *d_pcm = nullptr, *d_wave = nullptr;
+    uint8_t *d_codes = nullptr;          // G.711 codes as uploaded (ctu_plan_run_host_g711)
     float *d_fea = nullptr;
     uint8_t *d_ext = nullptr, *d_vadnr_out = nullptr, *d_vad_out = nullptr;
     bool host_bufs = false;
@@ -655,6 +657,7 @@ void ctu_destroy(ctu_handle *h) {
     cudaFree(h->d_w64); cudaFree(h->d_m264); cudaFree(h->d_lift64);
     cudaFree(h->d_tw256d); cudaFree(h->d_twsplitd); cudaFree(h->d_twinvd); cudaFree(h->d_wind); cudaFree(h->d_hann);
     cudaFree(h->d_any_tw64); cudaFree(h->d_any_ts64);
+    cudaFree(h->d_g711[0]); cudaFree(h->d_g711[1]);
     cudaFree(h->d_any_tw); cudaFree(h->d_any_ts); cudaFree(h->d_any_fbw); cudaFree(h->d_any_bands);
     for (auto &b : h->pool) cudaFree(b.p);
     for (int i = 0; i < 3; i++) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
@@ -1221,8 +1224,31 @@ int ctu_plan_run_device(ctu_plan *p, const int16_t *d_pcm, const uint8_t *d_ext_
     return fetch_rows(p, s);
 }
 
+// G.711 expansion values, 16-bit (ITU-T G.711 tables scaled to 16 bits, which is what alaw2lin computes bit by bit,
+// src/io/amulaw.h:19-56): segment number in bits 4-6, step in bits 0-3, sign in bit 7 (set = positive).
+int ctu_g711_table(int alaw, int16_t *t) {
+    if (!t) return CTU_ERR_CONFIG;
+    for (int code = 0; code < 256; code++) {
+        int v;
+        if (alaw) {
+            const int a = code ^ 0x55;                      // even bits are inverted on the line
+            const int seg = (a >> 4) & 7, step = a & 15;
+            v = (step << 4) + 8;                            // segment 0: linear, 16 per step
+            if (seg >= 1) v = ((step << 4) + 0x108) << (seg - 1);
+            if (!(a & 0x80)) v = -v;
+        } else {
+            const int u = ~code & 0xff;                     // mu-law codes are stored inverted
+            const int seg = (u >> 4) & 7, step = u & 15;
+            v = (((step << 3) + 0x84) << seg) - 0x84;
+            if (u & 0x80) v = -v;
+        }
+        t[code] = (int16_t)v;
+    }
+    return CTU_OK;
+}
+
 static int run_host_impl(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad, float *features, int16_t *waveform, uint8_t *vad_nr,
-                         uint8_t *vad_out, bool keep) {
+                         uint8_t *vad_out, bool keep, const uint8_t *codes = nullptr, int alaw = 0) {
     if (!p) return CTU_ERR_CONFIG;
     ctu_handle *h = p->h;
     CK(cudaSetDevice(h->device));
@@ -1240,6 +1266,15 @@ static int run_host_impl(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad
         if ((st = dev_alloc(h, p, &p->d_vad_out, (size_t)p->total_frames))) return st;
         p->host_bufs = true;
     }
+    if (codes) {
+        if (!p->d_codes && (st = dev_alloc(h, p, &p->d_codes, (size_t)p->total_samples + 16))) return st;
+        int16_t *&tab = h->d_g711[alaw ? 1 : 0];
+        if (!tab) {
+            std::vector<int16_t> t(256);
+            ctu_g711_table(alaw, t.data());
+            if ((st = upload(h, &tab, t))) return st;
+        }
+    }
     // chunks of utterances of roughly 64 MB of PCM, round-robin over three streams so that
     // H2D of chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap
     static const int64_t chunk_mb = getenv("CTU_CHUNK_MB") ? atoll(getenv("CTU_CHUNK_MB")) : 32;   // MB of PCM per pipeline chunk (e2e is flat between 16 and 64)
@@ -1252,7 +1287,18 @@ static int run_host_impl(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad
         cudaStream_t s = h->streams[ci % 3];
         Range r = make_range(p, u0, u1);
         int64_t so = p->offsets[u0] - base, sn = p->offsets[u1] - p->offsets[u0];
-        CK(cudaMemcpyAsync(p->d_pcm + so, pcm + p->offsets[u0], sn * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+        if (codes) {
+            // one byte per sample over PCIe; expanded next to the PCM buffer's own indexing
+            CK(cudaMemcpyAsync(p->d_codes + so, codes + p->offsets[u0], (size_t)sn, cudaMemcpyHostToDevice, s));
+            if (sn > 0) {
+                h->lc.begin("k_g711_expand", s);
+                k_g711_expand<<<(unsigned)std::min<int64_t>((sn / 8 + 256) / 256, 148 * 8), 256, 0, s>>>(p->d_codes, p->d_pcm, so, sn, h->d_g711[alaw ? 1 : 0]);
+                h->lc.end(s);
+                CK(cudaGetLastError());
+            }
+        } else {
+            CK(cudaMemcpyAsync(p->d_pcm + so, pcm + p->offsets[u0], sn * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+        }
         if (ext_vad && r.nrows) CK(cudaMemcpyAsync(p->d_ext + r.row0, ext_vad + r.row0, r.nrows, cudaMemcpyHostToDevice, s));
         if (h->signal_out) CK(cudaMemsetAsync(p->d_wave + p->osamp_off[u0], 0, (size_t)(p->osamp_off[u1] - p->osamp_off[u0]) * sizeof(int16_t), s));
         if ((st = run_range(p, r, p->d_pcm - base, ext_vad ? p->d_ext : nullptr, p->d_fea, p->d_wave, p->d_vadnr_out, p->d_vad_out, s))) return st;
@@ -1275,6 +1321,12 @@ static int run_host_impl(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad
 int ctu_plan_run_host(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad, float *features, int16_t *waveform, uint8_t *vad_nr,
                       uint8_t *vad_out) {
     return run_host_impl(p, pcm, ext_vad, features, waveform, vad_nr, vad_out, false);
+}
+
+int ctu_plan_run_host_g711(ctu_plan *p, const uint8_t *codes, int alaw, const uint8_t *ext_vad, float *features, int16_t *waveform,
+                           uint8_t *vad_nr, uint8_t *vad_out) {
+    if (!codes) return CTU_ERR_CONFIG;
+    return run_host_impl(p, nullptr, ext_vad, features, waveform, vad_nr, vad_out, false, codes, alaw);
 }
 
 int ctu_plan_run_host_keep(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad) {

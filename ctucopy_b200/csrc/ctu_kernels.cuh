@@ -1065,5 +1065,32 @@ k_stack(const StackParams S, BatchDesc bd, int tile_rows, const float *__restric
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// G.711 expansion on the device (alaw2lin, src/io/amulaw.h): 8-bit codes -> int16 PCM through a 256-entry table.
+// Both buffers are indexed by the same absolute sample index and allocated 256-byte aligned, so a thread takes the
+// 8 samples [8i, 8i+8) of the range rounded down to a multiple of 8: one 8-byte load, one 16-byte store.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_g711_expand(const uint8_t *__restrict__ codes, int16_t *__restrict__ pcm, int64_t first, int64_t count, const int16_t *__restrict__ table) {
+    __shared__ int16_t lut[256];
+    lut[threadIdx.x] = table[threadIdx.x];
+    __syncthreads();
+    const int64_t a0 = first & ~(int64_t)7;
+    const int64_t end = first + count;
+    for (int64_t i = a0 + 8 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); i < end; i += 8 * (int64_t)gridDim.x * blockDim.x) {
+        if (i >= first && i + 8 <= end) {
+            const uint2 c = *reinterpret_cast<const uint2 *>(codes + i);
+            int4 o;
+            o.x = (int)(uint16_t)lut[c.x & 255] | ((int)(uint16_t)lut[(c.x >> 8) & 255] << 16);
+            o.y = (int)(uint16_t)lut[(c.x >> 16) & 255] | ((int)(uint16_t)lut[c.x >> 24] << 16);
+            o.z = (int)(uint16_t)lut[c.y & 255] | ((int)(uint16_t)lut[(c.y >> 8) & 255] << 16);
+            o.w = (int)(uint16_t)lut[(c.y >> 16) & 255] | ((int)(uint16_t)lut[c.y >> 24] << 16);
+            *reinterpret_cast<int4 *>(pcm + i) = o;
+        } else {
+            for (int64_t k = max(i, first); k < min(i + 8, end); k++) pcm[k] = lut[codes[k]];
+        }
+    }
+}
+
 }  // namespace ctu
 #endif

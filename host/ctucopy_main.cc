@@ -50,26 +50,6 @@ struct ListEntry { std::string in, out, spk, vadout; };
 uint32_t bswap32(uint32_t x) { return ((x & 0xFFu) << 24) | ((x & 0xFF00u) << 8) | ((x & 0xFF0000u) >> 8) | ((x & 0xFF000000u) >> 24); }
 uint16_t bswap16(uint16_t x) { return (uint16_t)((x >> 8) | (x << 8)); }
 
-// G.711 expansion exactly as the reference does it (mode 1 = A-law, 0 = mu-law)
-int16_t g711(signed char a, int alaw) {
-    int chord, step, mag;
-    int sgn = (~(a >> 7)) & 1;
-    if (!alaw) {
-        chord = (~(a >> 4)) & 7;
-        step = (~(a)) & 0xf;
-        mag = (((2 * step) + 33) << chord) - 33;
-    } else {
-        chord = ((a ^ 0x55) >> 4) & 7;
-        step = ((a ^ 0x55)) & 0xf;
-        mag = (step << 1) + 1;
-        if (chord > 0) mag += 32; else chord = 1;
-        mag = mag << chord;
-    }
-    int v = ((1 - (2 * sgn)) * mag) & 0xffff;
-    v = (v << 2) & 0xffff;
-    return (int16_t)(uint16_t)v;
-}
-
 std::vector<unsigned char> slurp(const std::string &path, const char *err) {
     FILE *f = std::fopen(path.c_str(), "rb");
     if (!f) die(err);
@@ -430,10 +410,13 @@ void decode_into(const HostOpts &o, int fs, const std::string &path, int16_t *ds
         rd(dst, (size_t)n * 2);
         if (o.big_in) for (int64_t i = 0; i < n; i++) dst[i] = (int16_t)bswap16((uint16_t)dst[i]);
     } else if (fmt == "alaw" || fmt == "mulaw") {
-        std::vector<signed char> b((size_t)n);
+        // (the batch pipeline ships the codes to the GPU as they are, ctu_plan_run_host_g711; this host-side expansion
+        // serves the CMVN passes)
+        std::vector<unsigned char> b((size_t)n);
         rd(b.data(), (size_t)n);
-        const int alaw = fmt == "alaw";
-        for (int64_t i = 0; i < n; i++) dst[i] = g711(b[(size_t)i], alaw);
+        int16_t table[256];
+        ctu_g711_table(fmt == "alaw", table);
+        for (int64_t i = 0; i < n; i++) dst[i] = table[b[(size_t)i]];
     } else if (fmt == "wave") {
         unsigned char b[44];
         if (std::fread(b, 1, 44, f) != 44 || std::memcmp(b, "RIFF", 4)) { std::fclose(f); die("IN: No RIFF header in file!"); }
@@ -474,6 +457,14 @@ void read_features_into(const HostOpts &o, const ctu_config &cfg, const std::str
     std::fclose(f);
 }
 
+// a file's bytes as they are (G.711 codes: expanded on the GPU)
+void read_bytes_into(const std::string &path, unsigned char *dst, int64_t n) {
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) die("IN: Cannot open data file!");
+    if (n && std::fread(dst, 1, (size_t)n, f) != (size_t)n) { std::fclose(f); die("IN: Error reading input file!"); }
+    std::fclose(f);
+}
+
 struct Pinned {
     void *p = nullptr; uint64_t cap = 0;
     void reserve(uint64_t bytes) {
@@ -508,6 +499,7 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
     const bool sig = ctu_is_signal_output(h);
     const int in_dim = ctu_input_dim(h);          // > 0: the list names feature files (-format_in htk), offsets count rows
     const bool fea_in = in_dim > 0;
+    const bool g711 = (ho.format_in == "alaw" || ho.format_in == "mulaw");   // 8-bit codes go to the GPU as they are
     const std::string fo(cfg.format_out);
     const bool per_file = (fo == "htk" || sig);
     Writers W(ho, cfg, dim);
@@ -560,6 +552,7 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
                 double tr = now_s();
                 parallel_for(n, IO_THREADS, [&](size_t u) {
                     if (fea_in) read_features_into(ho, cfg, list[B.i0 + u].in, fin + B.off[u] * in_dim, B.off[u + 1] - B.off[u]);
+                    else if (g711) read_bytes_into(list[B.i0 + u].in, (unsigned char *)B.pcm.p + B.off[u], B.off[u + 1] - B.off[u]);
                     else decode_into(ho, cfg.fs, list[B.i0 + u].in, pcm + B.off[u], B.off[u + 1] - B.off[u]);
                 });
                 tmark("batch read+decode", tr);
@@ -612,10 +605,13 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
                 ev = extvad.data() + B.ext_pos;
             }
             double tg = now_s();
-            if (fea_in) {
+            if (fea_in || g711) {
                 ctu_plan *pl = nullptr;
                 if (ctu_plan_create(h, B.off.data(), n, &pl)) die(ctu_last_error(h));
-                if (ctu_plan_run_host_fea(pl, (const float *)B.pcm.p, (float *)B.fea.p)) { ctu_plan_destroy(pl); die(ctu_last_error(h)); }
+                const int st = fea_in ? ctu_plan_run_host_fea(pl, (const float *)B.pcm.p, (float *)B.fea.p)
+                                      : ctu_plan_run_host_g711(pl, (const uint8_t *)B.pcm.p, ho.format_in == "alaw", ev, sig ? nullptr : (float *)B.fea.p,
+                                                               sig ? (int16_t *)B.wav.p : nullptr, (uint8_t *)B.vnr.p, (uint8_t *)B.vout.p);
+                if (st) { ctu_plan_destroy(pl); die(ctu_last_error(h)); }
                 ctu_plan_frames_per_utt(pl, B.frames.data());
                 ctu_plan_rows_per_utt(pl, B.rows.data());
                 ctu_plan_destroy(pl);

@@ -181,6 +181,15 @@ int ctu_plan_run_host(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad, f
 int ctu_plan_run_device_fea(ctu_plan *p, const float *d_fea_in, float *d_features, void *stream);
 int ctu_plan_run_host_fea(ctu_plan *p, const float *fea_in, float *features /* NULL = keep on the device */);
 
+/* G.711 input (-format_in alaw | mulaw; rawIN::loadframe + alaw2lin, src/io/in.cc:470-500, src/io/amulaw.h): the caller
+ * hands over the 8-bit codes as they are in the file and the expansion to 16-bit PCM runs on the device, so only ONE byte
+ * per sample crosses PCIe (the end-to-end rate of this path is bound by the host-to-device copy).  Offsets of the plan
+ * count samples = bytes.  ctu_g711_table gives the 256 expansion values (law: 1 = A-law, 0 = mu-law) for hosts that
+ * decode themselves.                                                                                                   */
+int ctu_g711_table(int alaw, int16_t *table /* 256 */);
+int ctu_plan_run_host_g711(ctu_plan *p, const uint8_t *codes, int alaw, const uint8_t *ext_vad, float *features,
+                           int16_t *waveform, uint8_t *vad_nr, uint8_t *vad_out);
+
 /* The same in steps, for callers that post-process on the device before fetching: run with the results
  * left on the device, [ctu_plan_colsums / ctu_plan_normalise], then ctu_plan_fetch.                  */
 int ctu_plan_run_host_keep(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad);

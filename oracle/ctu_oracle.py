@@ -376,6 +376,29 @@ def dither_noise(nloaded: int, o: Opts, rand_offset: int = 0) -> np.ndarray:
     return (2.0 * rv / 2147483647.0 - 1.0) * o.dither
 
 
+def g711_expand(codes: np.ndarray, alaw: bool) -> np.ndarray:
+    """alaw2lin, src/io/amulaw.h:19-56 (mode 1 = A-law, 0 = mu-law), as rawIN::loadframe applies it to every byte of an
+    `-format_in alaw | mulaw` file (src/io/in.cc:470-500): bit-level restatement on signed chars, 16-bit result."""
+    a = np.asarray(codes, dtype=np.uint8).astype(np.int8).astype(np.int64)       # `char` is signed: >> is arithmetic
+    sgn = (~(a >> 7)) & 1
+    if not alaw:
+        chord = (~(a >> 4)) & 7
+        step = (~a) & 0xF
+        mag = (((2 * step) + 33) << chord) - 33
+    else:
+        x = a ^ 0x55
+        chord = (x >> 4) & 7
+        step = x & 0xF
+        mag = (step << 1) + 1
+        mag = np.where(chord > 0, mag + 32, mag)
+        chord = np.where(chord > 0, chord, 1)
+        mag = mag << chord
+    out = ((1 - 2 * sgn) * mag) & 0xFFFF
+    out = (out << 2) & 0xFFFF
+    out = np.where(out & 0x8000, out - 65536, out)
+    return out.astype(np.int16)
+
+
 def front_end(pcm: np.ndarray, o: Opts, rand_offset: int = 0) -> FrontEnd:
     """rawIN::get_frame, src/io/in.cc:305-419.  Dither draws from glibc rand() in list order
     (src/io/in.cc:205,454): rand_offset places this file in the process-wide stream."""

@@ -84,6 +84,9 @@ def run_reference(args: Sequence[str], pcms: List[np.ndarray], *, opt: str = "O0
                     fh.write(struct.pack(endian_in + "IIHH", p.shape[0], 100000, 4 * p.shape[1], 6))
                     fh.write(p.astype(endian_in + "f4").tobytes())
                 continue
+            if p.dtype == np.uint8:                 # 8-bit G.711 codes (-format_in alaw | mulaw): the file is the byte stream
+                p.tofile(os.path.join(d, "u%d.raw" % i))
+                continue
             p.astype(endian_in + "i2").tofile(os.path.join(d, "u%d.raw" % i))
         if ext_vad_bytes is not None:
             open(os.path.join(d, "vadin.bin"), "wb").write(ext_vad_bytes)

@@ -175,6 +175,26 @@ FEAIN_CMVN_CASES = {
 }
 
 
+# 8-bit G.711 input (-format_in alaw | mulaw): the codes are the standard inputs encoded to the nearest table value
+G711_CASES = {
+    "g711_alaw_mfcc_8k": ["-fs", "8000", "-format_in", "alaw", "-dither", "0"] + MF + ["-fea_delta", "d_a", "-format_out", "htk"],
+    "g711_mulaw_exten_raw_8k": ["-fs", "8000", "-format_in", "mulaw", "-dither", "0", "-preset", "exten", "-format_out", "raw"],
+    "g711_alaw_plp_16k": ["-fs", "16000", "-format_in", "alaw", "-dither", "0", "-preset", "plpc", "-format_out", "htk"],
+}
+
+
+def g711_encode(pcm, alaw):
+    """nearest code of the expansion table (ties: the smaller code); only used to make realistic test inputs"""
+    import ctu_oracle as co
+    table = co.g711_expand(np.arange(256, dtype=np.uint8), alaw).astype(np.int64)
+    order = np.argsort(table, kind="stable")
+    tv = table[order]
+    x = np.asarray(pcm, dtype=np.int64)
+    j = np.clip(np.searchsorted(tv, x), 1, 255)
+    pick = np.where(np.abs(tv[j - 1] - x) <= np.abs(tv[j] - x), j - 1, j)
+    return order[pick].astype(np.uint8)
+
+
 def inputs():
     utts = [synthetic.utterance(k, 1.0) for k in (0, 1, 5, 13)]           # tone/chirp, noisy + clean
     utts.append(synthetic.utterance(2, 2.5))
@@ -288,6 +308,19 @@ def main():
                     dd["out%d" % i] = np.frombuffer(open(pth, "rb").read(), dtype=np.uint8)
             np.savez_compressed(os.path.join(OUT, name + ".npz"), **dd)
             print(name, "ok", sorted(k for k in dd if k.startswith("out")))
+    for name, args in G711_CASES.items():
+        if sys.argv[1:] and name not in sys.argv[1:]:
+            continue
+        alaw = "alaw" in args
+        d = {"args": np.array(json.dumps(args)), "kind": np.array("raw" if args[-1] == "raw" else "htk"), "law": np.array("alaw" if alaw else "mulaw")}
+        for i, u in enumerate(utts):
+            codes = g711_encode(u, alaw)
+            r = rr.run_reference(args, [codes])
+            assert r["returncode"] == 0 and r["outputs"][0] is not None, (name, i, r["stderr"])
+            d["codes%d" % i] = codes
+            d["out%d" % i] = np.frombuffer(r["outputs"][0], dtype=np.uint8)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+        print(name, "ok")
     if sys.argv[1:]:
         return       # only the named cases were asked for
     # filter-bank design goldens via the undocumented -fb_printself (src/fea/fb.cc:449-456)

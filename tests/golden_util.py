@@ -20,7 +20,14 @@ def inputs():
 
 
 def case_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("inputs.npz", "fb_design.npz") and not f.startswith("cmvn") and not f.startswith("feain_"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("inputs.npz", "fb_design.npz") and not f.startswith("cmvn") and not f.startswith("feain_") and not f.startswith("g711_"))
+
+
+def g711_case(name):
+    """8-bit input golden: (args, law, [codes per input], Case-like payload access through Case(name))."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    n = len(inputs())
+    return json.loads(str(z["args"])), str(z["law"]) == "alaw", [z["codes%d" % i] for i in range(n)]
 
 
 def feain_case_names():

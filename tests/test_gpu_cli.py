@@ -211,3 +211,28 @@ def test_cli_feature_file_input_and_stacking_headers(tmp_path):
         assert got[:12] == want[:12], ("parmKind of file %d" % j, got[:12], want[:12])
         a, b = rr.parse_htk(got)[1], rr.parse_htk(want)[1]
         assert np.all(np.abs(a - b) <= 1e-4 * np.abs(b) + 1e-3)
+
+
+def test_cli_g711_files(tmp_path):
+    """-format_in alaw / mulaw through the command line (codes expanded on the GPU) against the reference's files."""
+    tmp = str(tmp_path)
+    for name in ("g711_alaw_mfcc_8k", "g711_mulaw_exten_raw_8k"):
+        args, alaw, codes = gu.g711_case(name)
+        c = gu.Case(name)
+        idx = [0, 4, 5]
+        with open(os.path.join(tmp, "list.scp"), "w") as fh:
+            for j, i in enumerate(idx):
+                codes[i].tofile(os.path.join(tmp, "c%d.al" % j))
+                fh.write("%s/c%d.al %s/c%d.out\n" % (tmp, j, tmp, j))
+        pr = subprocess.run([EXE] + args + ["-S", os.path.join(tmp, "list.scp")], capture_output=True, cwd=tmp)
+        assert pr.returncode == 0, pr.stderr.decode()
+        for j, i in enumerate(idx):
+            got, want = open(os.path.join(tmp, "c%d.out" % j), "rb").read(), c.raw[i]
+            assert len(got) == len(want), (name, i)
+            if c.kind == "raw":
+                d = np.abs(np.frombuffer(got, "<i2").astype(np.int32) - np.frombuffer(want, "<i2").astype(np.int32))
+                assert d.max() <= 1
+            else:
+                assert got[:12] == want[:12]
+                a, b = rr.parse_htk(got)[1], rr.parse_htk(want)[1]
+                assert np.all(np.abs(a - b) <= 1e-4 * np.abs(b) + 1e-3)

@@ -331,3 +331,22 @@ def test_feature_input_refusals():
         cb.Handle(B[:2] + ["-format_in", "raw", "-preset", "mfcc", "-fea_kind", "trapdct,11,3", "-fea_delta", "d", "-format_out", "htk"])
     with pytest.raises(cb.CtuError):
         cb.Handle(B + ["-preset", "mfcc", "-fea_trap", "5", "-fea_c0", "off", "-format_out", "htk"])
+
+
+@pytest.mark.parametrize("name", ["g711_alaw_mfcc_8k", "g711_mulaw_exten_raw_8k", "g711_alaw_plp_16k"])
+def test_cuda_g711_input_matches_reference_golden(name):
+    """8-bit A-law / mu-law files: the codes are uploaded as they are (one byte per sample over PCIe) and expanded on the
+    device (k_g711_expand); results against the reference binary run on the same files."""
+    args, alaw, codes = gu.g711_case(name)
+    c = gu.Case(name)
+    o = co.parse_args(args)
+    idx = [i for i in range(len(codes)) if co.num_frames(len(codes[i]), o) >= (4 if o.n_order else 0)]
+    res = cb.extract_g711(args, [codes[i] for i in idx], alaw)
+    for j, i in enumerate(idx):
+        want = c.payload(i)
+        if c.kind == "raw":
+            got = res.utt_waveform(j)
+            d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+            assert got.shape == want.shape and d.max() <= 1 and (d > 0).mean() < 0.02, (name, i)
+        else:
+            check_features(name, i, res.utt_features(j), want, o.fea_kind)

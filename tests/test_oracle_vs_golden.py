@@ -177,3 +177,23 @@ def test_oracle_cmvn_on_feature_files_matches_reference_binary(name):
             assert np.array_equal(feats[j], rr.parse_htk(outs[i])[1]), (name, i)
     else:
         assert not outs
+
+
+@pytest.mark.parametrize("name", ["g711_alaw_mfcc_8k", "g711_mulaw_exten_raw_8k", "g711_alaw_plp_16k"])
+def test_oracle_g711_input_matches_reference_binary(name):
+    """-format_in alaw | mulaw: expansion (src/io/amulaw.h) + pipeline against the reference binary on 8-bit files; and
+    the library's own 256-entry table (ctu_g711_table, host-only) equals the restated bit manipulation."""
+    import ctucopy_b200 as cb
+    args, alaw, codes = gu.g711_case(name)
+    c = gu.Case(name)
+    o = co.parse_args(args)
+    assert np.array_equal(cb.g711_table(alaw), co.g711_expand(np.arange(256, dtype=np.uint8), alaw))
+    for i, cd in enumerate(codes):
+        res = co.run_pipeline(co.g711_expand(cd, alaw), o)
+        want = c.payload(i)
+        got = res.waveform if c.kind == "raw" else res.features
+        assert got.shape == want.shape, (name, i)
+        if c.kind == "raw":
+            assert np.array_equal(got, want), (name, i)
+        else:
+            np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-6)
