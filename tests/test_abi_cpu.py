@@ -35,10 +35,11 @@ FIELDS = ["fs", "preem", "dither", "remove_dc", "remove_dc1", "window_ms", "wshi
           "vad_apply_mode", "vad_out_mode", "vad_cri_mode", "vad_thr_mode", "vad_energy_db", "vad_cepdist_mode", "vad_cepdist_p",
           "vad_cepdist_init", "vad_lpc_coefs", "vad_absolute_thr", "vad_perc_init", "vad_perc_thr", "vad_adapt_init", "vad_adapt_q",
           "vad_adapt_za", "vad_dyn_init", "vad_dyn_perc", "vad_dyn_min", "vad_dyn_qmaxinc", "vad_dyn_qmaxdec", "vad_dyn_qmindec",
-          "vad_dyn_qmininc", "vad_filter_order", "window", "wshift", "wfft", "wfftby2", "phase_needed", "format_out"]
+          "vad_dyn_qmininc", "vad_filter_order", "window", "wshift", "wfft", "wfftby2", "phase_needed", "format_out",
+          "fea_delta", "fea_trap", "trap_win", "nfeacoefs"]
 
 
-@pytest.mark.parametrize("name", gu.case_names())
+@pytest.mark.parametrize("name", gu.case_names() + gu.feain_case_names())
 def test_config_parser_agrees_with_oracle_parser(name):
     c = gu.Case(name)
     args = c.oracle_args()
@@ -52,6 +53,7 @@ def test_config_parser_agrees_with_oracle_parser(name):
             a = int(a)
         assert a == b, (name, f, a, b)
     assert (o.nr_when == "afterFB") == bool(g.nr_when)
+    assert (o.format_in == "htk") == bool(g.fea_in)
     if o.fea_kind == "trapdct":
         assert (o.fea_trapdct_traplen, o.fea_trapdct_ndct) == (g.fea_trapdct_traplen, g.fea_trapdct_ndct)
 
