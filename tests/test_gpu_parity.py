@@ -350,3 +350,43 @@ def test_cuda_g711_input_matches_reference_golden(name):
             assert got.shape == want.shape and d.max() <= 1 and (d > 0).mean() < 0.02, (name, i)
         else:
             check_features(name, i, res.utt_features(j), want, o.fea_kind)
+
+
+def test_feature_input_random_chains_match_oracle():
+    """Random delta / stacking / CMS chains on random feature matrices (dims 5..40, windows 1..4, stacking 3..15 rows, with
+    and without the writer's column cut), ragged row counts, 40 option sets: the device against the oracle's state machine."""
+    rng = np.random.default_rng(11)
+    for it in range(40):
+        dim = int(rng.integers(5, 41))
+        ncep = int(rng.integers(2, dim))                       # the chain reads ncep+1 <= dim columns
+        kind = ["lpc", "spec", "logspec", "lpa"][int(rng.integers(0, 4))]
+        args = ["-fs", "16000", "-format_in", "htk", "-nfeacoefs", str(dim), "-fea_ncepcoefs", str(ncep), "-fea_kind", kind, "-format_out", "htk"]
+        mode = int(rng.integers(0, 4))
+        need = 1
+        if mode == 1:
+            order = ["d", "d_a", "d_a_t"][int(rng.integers(0, 3))]
+            wins = [int(rng.integers(1, 5)) for _ in range(3)]
+            args += ["-fea_delta", order, "-d_win", str(wins[0]), "-a_win", str(wins[1]), "-t_win", str(wins[2])]
+            need = max(wins[: len(order.split("_"))]) + 2
+        elif mode == 2:
+            N = int(rng.choice([3, 5, 7, 9, 11, 15]))
+            args += ["-fea_trap", str(N)]
+            need = (N - 1) // 2 + 2
+        elif mode == 3:
+            args += ["-fea_delta", "d_a"]
+            need = 4
+        if mode in (1, 3) and rng.random() < 0.4:
+            args += ["-fea_Z_exp", str(int(rng.choice([200, 500, 1500])))]
+        if kind == "lpc" and rng.random() < 0.3:
+            args += ["-fea_c0", "off"]
+        o = co.parse_args(args)
+        mats = [rng.standard_normal((int(rng.integers(need, need + 200)), dim)).astype(np.float32) * 3 for _ in range(int(rng.integers(1, 12)))]
+        res = cb.extract_features(args, mats)
+        for j, m in enumerate(mats):
+            want = co.run_features(m, o)
+            got = res.utt_features(j)
+            assert got.shape == want.shape, (args, j, got.shape, want.shape)
+            if mode in (0, 2):
+                assert np.array_equal(got, want), (args, j)
+            else:
+                assert np.all(np.abs(got - want) <= 1e-4 * np.abs(want) + 1e-3), (args, j, float(np.abs(got - want).max()))
