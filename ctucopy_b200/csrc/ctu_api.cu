@@ -562,8 +562,8 @@ static int resolve_modes(ctu_handle *h) {
     if (c.remove_dc1 && c.window / c.wshift + 1 > ANY_DC1_MAX) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -remove_dc1 with a window longer than 17 shifts");
     if (c.remove_dc1 && c.fea_E && c.fea_rawenergy) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -remove_dc1 together with -fea_rawenergy");
     if (h->generic) {
-        // other sampling rates / window lengths: the general (slower) frame kernel; the specialised 512-point
-        // kernels of the Burg detector, the synthesis and the fp64 path are not generalised yet
+        // other sampling rates / window lengths, -remove_dc1, -dither: the general (slower) frame kernel; synthesis, the Burg
+        // detector and the fp64 path have general siblings too (ctu_any64.cuh), but those do not apply ring offsets / dither
         if (c.wfft < 64 || c.wfft > ANY_MAX_NFFT) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: FFT sizes from 64 to 2048 points are built (window of 33..2048 samples)");
         if (h->signal_out && (c.remove_dc1 || c.dither != 0.0))
             return fail(h, CTU_ERR_UNSUPPORTED, "CTU: waveform output together with -remove_dc1 / -dither");

@@ -35,7 +35,7 @@ typedef enum ctu_status {
     CTU_OK = 0,
     CTU_ERR_CONFIG = 1,      /* option error (the reference throws "OPTS: ...", "FB: ...", "NR: ...") */
     CTU_ERR_INPUT = 2,       /* e.g. "IO: Signal shorter than one frame!" (src/io/in.cc:277)          */
-    CTU_ERR_UNSUPPORTED = 3, /* valid for the reference, not built here yet (message says what)      */
+    CTU_ERR_UNSUPPORTED = 3, /* not built here, or undefined behaviour in the reference (message says) */
     CTU_ERR_CUDA = 4,        /* CUDA runtime failure, or no usable device: there is NO CPU fallback   */
     CTU_ERR_CAPACITY = 5     /* caller's output buffer too small                                      */
 } ctu_status;
