@@ -97,6 +97,7 @@ struct ctu_plan {
     float *d_static = nullptr;           // static block before k_stack (gather modes)
     float *d_work = nullptr;             // full-width rows when the writer cuts the last column (feature input)
     float *d_in = nullptr;               // feature input rows (host entry point)
+    float2 *d_cspec = nullptr;           // complex spectrum kept for the synthesis (k_synth_c)
     double *d_yt = nullptr;              // synthesised frames [frames x window] of the general synthesis
     double *d_fb64 = nullptr;            // band values of the precise path
     double *d_fea64 = nullptr;           // fp64 copy of the feature matrix (feature-vector VAD criterion)
@@ -770,6 +771,8 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     const bool need_fb = !h->signal_out && ((nr_on && h->cfg.nr_when == 1) || lpc_kind);
     if (need_spec && (st = dev_alloc(h, p, &p->d_spec, (size_t)rows * h->nbins))) { ctu_plan_destroy(p); return st; }
     if (h->signal_out && h->bp.nfft && (st = dev_alloc(h, p, &p->d_yt, (size_t)rows * h->cfg.window))) { ctu_plan_destroy(p); return st; }
+    static const int want_cspec = getenv("CTU_SYNTH_FROM_PCM") ? 0 : 1;
+    if (h->signal_out && !h->bp.nfft && want_cspec && (st = dev_alloc(h, p, &p->d_cspec, (size_t)rows * NBIN))) { ctu_plan_destroy(p); return st; }
     if (need_fb && !h->precise && (st = dev_alloc(h, p, &p->d_fb, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     if (need_fb && h->precise && (st = dev_alloc(h, p, &p->d_fb64, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     if (h->do_vad && h->vad_cri == VCRI_CEPDIST_FEA && (st = dev_alloc(h, p, &p->d_fea64, (size_t)rows * h->feature_dim))) { ctu_plan_destroy(p); return st; }
@@ -837,6 +840,7 @@ struct Range;
 struct FrameTiles {
     const int2 *t32; int64_t n32;     // 32-frame tiles (k_frames)
     const int2 *t16; int64_t n16;     // 16-frame tiles (k_frames2)
+    float2 *cplx = nullptr;           // PCM -> spectrum: also store the complex spectrum here (synthesis)
 };
 
 // Two generations of the fused frame kernel are kept because they bind on different things
@@ -868,7 +872,7 @@ static int launch_frames_w(ctu_handle *h, const FrameParams &P, const ctu_plan *
         if (ft.n16 <= 0) return CTU_OK;
         Smem2 L = smem2_layout(P.window, P.wshift);
         size_t bytes = (size_t)L.total * sizeof(float);
-        auto kern = k_frames2<WT>;
+        auto kern = ft.cplx ? k_frames2<WT, true> : k_frames2<WT, false>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         FftTables tb{h->d_tw256, h->d_twsplit, h->d_twinv, h->d_win};
         BatchDesc bd{p->d_pcm_off, p->d_nframes, p->d_row_off, ft.t16};
@@ -877,7 +881,7 @@ static int launch_frames_w(ctu_handle *h, const FrameParams &P, const ctu_plan *
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, F2_THREADS, bytes));
         const unsigned grid = (unsigned)std::min<int64_t>(ft.n16, std::max(per_sm, 1) * (int64_t)h->num_sms);
         h->lc.begin(names[SRC][DST], s);
-        kern<<<grid, F2_THREADS, bytes, s>>>(P, bd, tb, pcm, dst, (int)ft.n16);
+        kern<<<grid, F2_THREADS, bytes, s>>>(P, bd, tb, pcm, dst, (int)ft.n16, ft.cplx);
         h->lc.end(s);
     } else {
         if (ft.n32 <= 0) return CTU_OK;
@@ -1058,7 +1062,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     if (r.nrows <= 0 && !h->signal_out) return CTU_OK;
     BatchDesc bd32{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tiles32 + r.t32_0};
     BatchDesc bd64{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tiles64 + r.t64_0};
-    const FrameTiles ft{p->d_tiles32 + r.t32_0, r.t32_n, p->d_tilesF + r.tF_0, r.tF_n};
+    FrameTiles ft{p->d_tiles32 + r.t32_0, r.t32_n, p->d_tilesF + r.tF_0, r.tF_n};
     int st;
     const int kind = kind_of(h);
     uint8_t *flags = d_vadnr ? d_vadnr : p->d_flags;
@@ -1079,7 +1083,9 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     P.dither = p->d_dither ? p->d_dither - p->offsets[0] : nullptr;
     if (need_spec) {
         P.out_dim = h->nbins; P.out_stride = h->nbins;
+        ft.cplx = p->d_cspec;                 // waveform output: X itself is kept for the synthesis
         if ((st = launch_frames_t<SRC_PCM, DST_SPEC, KIND_SPEC>(h, P, p, ft, d_pcm, nullptr, p->d_spec, s))) return st;
+        ft.cplx = nullptr;
     }
     if (nr_on && before) {
         if (h->nr_mode >= NR_HWSS && h->vad_src == VADSRC_BURG) {
@@ -1113,6 +1119,10 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
         h->lc.end(s);
         CK(cudaGetLastError());
         return CTU_OK;
+    }
+    if (h->signal_out && p->d_cspec) {
+        BatchDesc bdS{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tilesS + r.tS_0};
+        return launch_synth_c(h->sp, h->fp, bdS, p->syn_tile, r.tS_n, p->d_osamp_off, p->d_cspec, p->d_spec, d_wave, h->d_tw256, h->d_twinv, s, &h->lc, h->err);
     }
     if (h->signal_out) {
         BatchDesc bdS{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tilesS + r.tS_0};

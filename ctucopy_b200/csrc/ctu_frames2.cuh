@@ -41,10 +41,12 @@ __host__ __device__ inline Smem2 smem2_layout(int window, int wshift) {
     return L;
 }
 
-template <int WT>
+// CPLX: also store the complex spectrum X (float2 per bin) for the synthesis (k_synth_c): the phase then never has to be
+// recomputed from the samples.
+template <int WT, bool CPLX = false>
 __global__ void __launch_bounds__(F2_THREADS, 4)
 k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, const int16_t *__restrict__ pcm, float *__restrict__ dst,
-          int ntiles) {
+          int ntiles, float2 *__restrict__ cdst = nullptr) {
     extern __shared__ __align__(16) float sm[];
     const Smem2 L = smem2_layout(P.window, P.wshift);
     const int tid = threadIdx.x;
@@ -117,6 +119,15 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, con
         rfft_split_shfl(a, c, sTs, lo, hi, mid);
         __syncwarp(hm);                                       // all reads of the exchange tile are done
         float *g = dst + (row0 + f) * NBIN;
+        if (CPLX) {
+            float2 *gc = cdst + (row0 + f) * NBIN;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                gc[c + 16 * j] = make_float2(lo[j].x, lo[j].y);
+                gc[NC - c - 16 * j] = make_float2(hi[j].x, hi[j].y);
+            }
+            if (c == 0) gc[128] = make_float2(mid.x, mid.y);
+        }
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int k = c + 16 * j;

@@ -1078,6 +1078,148 @@ static inline int launch_synth(const SynthParams &S, const FrameParams &F, const
     return CTU_OK;
 }
 
+// K9c: synthesis from a STORED complex spectrum.  k_frames2 can write X (float2 per bin) next to |X|; the synthesis then
+// needs no second forward transform of the frame -- no PCM staging, no window, no forward FFT -- only the enhanced
+// magnitude on the stored phase, the inverse transform and the overlap-add.  Same arithmetic as k_synth from scale_bin on
+// (the stored X is the very value k_synth would recompute), so the waveforms are bit-identical; it trades 2 x 2056 B of
+// HBM traffic per frame (write + read of X) for about 40 % of the synthesis kernel's instructions.
+template <int WT, int ST>
+__global__ void __launch_bounds__(SYN_THREADS, 3)
+k_synth_c(const __grid_constant__ SynthParams S, int window, int wshift, BatchDesc bd, int tile_frames, int ntiles,
+          const int64_t *__restrict__ osamp_off, const float2 *__restrict__ cspec, const float *__restrict__ spec, int16_t *__restrict__ out,
+          const float2 *__restrict__ g_tw256, const float2 *__restrict__ g_twinv) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x;
+    const int w = WT ? WT : window, s = ST ? ST : wshift, hh = S.hh;
+    cpx<float> *sTw = reinterpret_cast<cpx<float> *>(sm);                 // 256
+    cpx<float> *sTi = sTw + 256;                                         // 130
+    cpx<float> *sX = sTi + 130;                                          // SYN_GROUPS * 16*17
+    float *sYt = reinterpret_cast<float *>(sX + SYN_GROUPS * XPAD * 16); // SYN_FRAMES * w
+    for (int i = tid; i < 256; i += SYN_THREADS) sTw[i] = mk<float>(g_tw256[i].x, g_tw256[i].y);
+    for (int i = tid; i < 129; i += SYN_THREADS) sTi[i] = mk<float>(g_twinv[i].x, g_twinv[i].y);
+    __syncthreads();
+    const int c = tid & (GROUP - 1), grp = tid / GROUP;
+    const unsigned hm = 0xffffu << (tid & 16);
+    cpx<float> *xch = sX + grp * (XPAD * 16);
+    // (fetching a tile's inputs one tile ahead, before the overlap-add of the current one, was tried: 11.0 ms at two CTAs
+    // per SM against 10.8 ms with three and no prefetch -- the kernel is bound by the transform and the overlap-add)
+    struct SynMeta { int u, t0, T, nf, tfirst, nfr; };
+    auto meta_of = [&](int tile) {
+        SynMeta m;
+        const int2 tl = bd.tiles[tile];
+        m.u = tl.x; m.t0 = tl.y; m.T = bd.nframes[m.u];
+        m.nf = min(tile_frames, m.T - m.t0); m.tfirst = max(m.t0 - hh, 0); m.nfr = m.t0 + m.nf - m.tfirst;
+        return m;
+    };
+    cpx<float> lo[8], hi[8], mid;
+    float Alo[8], Ahi[8], Amid = 0.f;
+    auto fetch = [&](const SynMeta &m) {
+        if (grp < m.nfr) {
+            const int64_t row = bd.row_off[m.u] + m.tfirst + grp;
+            const float *srow = spec + row * NBIN;
+            const float2 *xrow = cspec + row * NBIN;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                Alo[j] = __ldg(srow + c + 16 * j); Ahi[j] = __ldg(srow + NC - c - 16 * j);
+                const float2 xl = __ldg(xrow + c + 16 * j), xh = __ldg(xrow + NC - c - 16 * j);
+                lo[j] = mk<float>(xl.x, xl.y); hi[j] = mk<float>(xh.x, xh.y);
+            }
+            Amid = __ldg(srow + 128);
+            const float2 xm = __ldg(xrow + 128);
+            mid = mk<float>(xm.x, xm.y);
+        }
+    };
+    int tile = blockIdx.x;
+    if (tile >= ntiles) return;
+#pragma unroll 1
+    for (; tile < ntiles; tile += gridDim.x) {
+        const SynMeta cur = meta_of(tile);
+        fetch(cur);
+        const int u = cur.u, t0 = cur.t0, T = cur.T, nf = cur.nf, tfirst = cur.tfirst, nfr = cur.nfr;
+        if (grp < nfr) {
+            const int f = grp;
+            cpx<float> a[16];
+            // enhanced magnitude with the ORIGINAL phase: scale X by |X|enh / (|X| nfft); bin 0 has phase 0, the Nyquist
+            // bin is always written non-negative (src/io/out.cc:417-424)
+            const float invn = 1.0f / (float)NFFT;
+            auto scale_bin = [&](cpx<float> X, float A, bool edge) -> cpx<float> {
+                A *= invn;
+                if (edge) return mk<float>(A, 0.f);
+                float m2 = X.x * X.x + X.y * X.y;
+                if (m2 == 0.f) return mk<float>(0.f, -A);
+                float g = A * rsqrtf(m2);
+                return mk<float>(X.x * g, X.y * g);
+            };
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool edge = (c == 0 && j == 0);               // k == 0 pairs with k == 256
+                lo[j] = scale_bin(lo[j], Alo[j], edge);
+                hi[j] = scale_bin(hi[j], Ahi[j], edge);
+            }
+            mid = scale_bin(mid, Amid, false);
+            irfft_presplit_shfl(a, c, sTi, lo, hi, mid);
+            fft256_pass1_rec(a, c, sTw, xch);
+            __syncwarp(hm);
+            fft256_pass2(a, c, xch);
+            __syncwarp(hm);
+            float *yt = sYt + f * w;
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++) {
+                int n = c + 16 * k2;
+                if (2 * n + 1 < w) *reinterpret_cast<float2 *>(yt + 2 * n) = make_float2(a[k2].x, -a[k2].y);
+                else if (2 * n < w) yt[2 * n] = a[k2].x;
+            }
+        }
+        __syncthreads();
+        // overlap-add in frame order (fp64 accumulator like the reference's cbuffer), floor(x / correction), clip
+        // (src/io/out.cc:427-451)
+        const bool last = (t0 + nf == T);
+        const int nout = nf * s + (last ? (w - s) : 0);
+        int16_t *o = out + osamp_off[u] + (int64_t)t0 * s;
+        const int base = (t0 - tfirst) * s;
+        const double inv_corr = 1.0 / S.correction;
+        for (int i = tid; i < nout; i += SYN_THREADS) {
+            const int pos = base + i;
+            const int fa = (pos < w) ? 0 : (pos - w) / s + 1;
+            const int fb = min(pos / s, nfr - 1);
+            double acc = 0.0;
+            for (int f = fa; f <= fb; f++) acc += (double)sYt[f * w + (pos - f * s)];
+            int v = (int)floor(acc * inv_corr);
+            v = max(-32767, min(32767, v));
+            o[i] = (int16_t)v;
+        }
+        __syncthreads();                                      // the slots are re-used by the next tile
+    }
+}
+
+static inline int launch_synth_c(const SynthParams &S, const FrameParams &F, const BatchDesc &bd, int tile_frames, int64_t ntiles,
+                                 const int64_t *d_osamp_off, const float2 *cspec, const float *spec, int16_t *out, const float2 *tw,
+                                 const float2 *ti, cudaStream_t s, LaunchCtx *lc, std::string &err) {
+    if (ntiles <= 0) return CTU_OK;
+    if (F.window & 1) { err = "CTU: synthesis needs an even window length"; return CTU_ERR_UNSUPPORTED; }
+    const size_t bytes = sizeof(float) * (2 * (256 + 130 + SYN_GROUPS * XPAD * 16) + (size_t)SYN_FRAMES * F.window);
+    if (bytes > 227 * 1024 || tile_frames < 1) { err = "CTU: window/shift combination needs too much shared memory for synthesis"; return CTU_ERR_UNSUPPORTED; }
+    cudaError_t e;
+    int per_sm = 1, num_sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    lc->begin("k_synth_c", s);
+#define CTU_SYNTHC_LAUNCH(WT, ST)                                                                                                    \
+    e = cudaFuncSetAttribute(k_synth_c<WT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);                          \
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_synth_c<WT, ST>, SYN_THREADS, bytes);         \
+    if (e == cudaSuccess)                                                                                                            \
+        k_synth_c<WT, ST><<<(unsigned)std::min<int64_t>(ntiles, (int64_t)std::max(per_sm, 1) * num_sms), SYN_THREADS, bytes, s>>>(  \
+            S, F.window, F.wshift, bd, tile_frames, (int)ntiles, d_osamp_off, cspec, spec, out, tw, ti)
+    if (F.window == 512 && F.wshift == 256) { CTU_SYNTHC_LAUNCH(512, 256); }
+    else if (F.window == 400 && F.wshift == 160) { CTU_SYNTHC_LAUNCH(400, 160); }
+    else { CTU_SYNTHC_LAUNCH(0, 0); }
+#undef CTU_SYNTHC_LAUNCH
+    lc->end(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e) + " (k_synth_c)"; return CTU_ERR_CUDA; }
+    return CTU_OK;
+}
+
 static inline int launch_vad_module(VadParams V, const BurgParams &B, const BatchDesc &bd32, int64_t nt32, const int *d_nframes,
                                     const int64_t *d_row_off, int u0, int u1, int64_t row0, int64_t nrows, const int16_t *d_pcm,
                                     const float *d_spec, float *d_fea, const double *d_fea64, int fea_dim, double *d_ceps, double *d_cri,
