@@ -766,7 +766,12 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     if (h->work_dim != h->feature_dim && (st = dev_alloc(h, p, &p->d_work, (size_t)rows * h->work_dim))) { ctu_plan_destroy(p); return st; }
     if (h->fea_in) { *out = p; return CTU_OK; }
     const bool nr_on = h->nr_mode != NR_NONE;
-    const bool need_spec = h->signal_out || (nr_on && h->cfg.nr_when == 0) || (h->do_vad && h->vad_cri != VCRI_CEPDIST_FEA);
+    // PCM -> spectrum (k_frames2, 4-5 CTAs per SM) followed by spectrum -> features is faster than the single fused kernel
+    // (2 CTAs per SM) even though the spectrum then makes a round trip through HBM -- measured 12.4 -> 11.4 ms (MFCC_0_D_A),
+    // 12.6 -> 11.8 (PLP), 14.9 -> 14.1 (TRAP-DCT) per 9.98 M frames; CTU_SPLIT_FRONT=0 restores the fused kernel
+    static const int split_front = getenv("CTU_SPLIT_FRONT") ? atoi(getenv("CTU_SPLIT_FRONT")) : 1;
+    const bool need_spec = h->signal_out || (nr_on && h->cfg.nr_when == 0) || (h->do_vad && h->vad_cri != VCRI_CEPDIST_FEA) ||
+                           (split_front && !h->precise && !h->generic && h->fea_kind != FEA_NONE);
     const bool lpc_kind = (h->fea_kind == FEA_LPA || h->fea_kind == FEA_LPC);
     const bool need_fb = !h->signal_out && ((nr_on && h->cfg.nr_when == 1) || lpc_kind);
     if (need_spec && (st = dev_alloc(h, p, &p->d_spec, (size_t)rows * h->nbins))) { ctu_plan_destroy(p); return st; }
