@@ -62,6 +62,7 @@ def kernel_alg_bytes(name, hop, dim, nb):
         "k_nr_scan": 2 * 4 * 257, "k_delta": 4 * dim + 8 * dim, "k_lpc": 4 * nb + 4 * dim, "k_trapdct": 4 * nb + 4 * dim,
         "k_synth": pcm + 4 * 257 + pcm, "k_burg": pcm + 8 * 16, "k_cepdet": 8 * 16 + 1,
         "k_stack": 4 * 13 + 4 * dim,          # static block read once, stacked row written once
+        "k_synth_c": 8 * 257 + 4 * 257 + pcm,  # stored complex spectrum + enhanced magnitudes in, one hop of int16 out
     }.get(name)
 
 
