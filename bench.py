@@ -239,7 +239,21 @@ def main():
         print(json.dumps({"error": "no CUDA device: the CtuCopy hot path has no CPU fallback"}))
         return 1
     torch.cuda.set_device(local)
+    numa = None
     if world > 1:
+        # one process per GPU: run on (and, by first touch, allocate the pinned buffers from) the CPU cores next to this
+        # rank's GPU -- the end-to-end number is bound by host <-> device copies, which cross the socket link otherwise
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+            cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1} & os.sched_getaffinity(0)
+            if cpus and os.environ.get("CTU_BENCH_NO_AFFINITY") is None:
+                os.sched_setaffinity(0, cpus)
+                numa = "%d cpus next to GPU %d" % (len(cpus), local)
+        except Exception as e:      # affinity is an optimisation, never fatal
+            numa = "unavailable (%s)" % type(e).__name__
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -377,7 +391,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": a.workload, "utterances_per_gpu": a.utts, "seconds_per_utt": 10.0, "frames_per_gpu": r["frames"],
                    "feature_dim": r["dim"], "args": " ".join(r["args"]), "l2": "inputs (3.2 GB PCM per GPU) exceed L2; no flush needed",
-                   "sharding": "utterances by rank, no collective"},
+                   "sharding": "utterances by rank, no collective", "cpu_affinity": numa},
         "gpu_launches": r["launches"], "kernel_ms_per_step": r["kern_ms"], "clocks": r["clocks"], "e2e": r["e2e"], "roofline": roof,
     }
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
