@@ -10,7 +10,14 @@ A "step" is one pass of the hot path over one batch of synthetic 16 kHz utteranc
           launching stream, max over ranks)
   e2e   : the same metric through the public C-ABI call with HOST (pinned) buffers:
           H2D of the PCM and D2H of the features inside the timed region
+          e2e.copy_only_ms = the same chunk schedule with the kernels left out (control: what the
+          host <-> device copies alone cost on this box at this N); e2e.frac_of_copy_only = copy_only_ms / ms_per_step
   roofline / cpu_baseline : see DESIGN.md "Measurement"
+  workloads : the other BASELINE configs (PLP, MFCC_0_D_A, exten -> waveform, TRAP-DCT, fwss + Burg) measured the
+          same way with fewer steps, each with its own roofline / e2e / selfcheck
+  selfcheck : after the timed region the output of the LAST utterance of the batch is compared bit for bit with
+          the output of the identical utterance near the start of the batch (past 2^31 elements in between), and
+          with the CPU oracle within the parity tolerance
 Multi-GPU: one process per GPU (torchrun), utterances sharded by rank, no collective on the
 data path (weak scaling: every rank gets its own 10 000 utterances).
 """
@@ -210,6 +217,48 @@ def run_reference_arm(a):
     return 0
 
 
+def selfcheck(workload, args, plan, hd, d_out, lens, uniq, first, sig):
+    """Correctness at bench scale, outside the timed region: (1) utterance n-1 holds the same samples as utterance
+    (n-1) % uniq, so their outputs must be bit-identical although they sit at opposite ends of the batch (2.56e9
+    spectrum elements apart: 64-bit indexing, tile lists, persistent-CTA strides); (2) that utterance against the CPU
+    oracle (test infrastructure, the checker only) within the parity tolerance of tests/test_gpu_parity.py."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ctu_oracle as co
+    from ctucopy_b200 import synthetic
+    n = len(lens)
+    a_i, b_i = n - 1, (n - 1) % uniq
+    if sig:
+        off = plan.wave_offsets
+        ya = d_out[int(off[a_i]): int(off[a_i + 1])].cpu().numpy()
+        yb = d_out[int(off[b_i]): int(off[b_i + 1])].cpu().numpy()
+    else:
+        ro = plan.row_offsets
+        ya = d_out[int(ro[a_i]): int(ro[a_i + 1])].cpu().numpy()
+        yb = d_out[int(ro[b_i]): int(ro[b_i + 1])].cpu().numpy()
+    out = {"identical_utts": [a_i, b_i]}
+    if ya.shape != yb.shape or ya.tobytes() != yb.tobytes():
+        out["status"] = "FAILED: outputs of identical utterances %d and %d differ" % (a_i, b_i)
+        return out
+    o = co.parse_args([x for x in args])
+    ref = co.run_pipeline(synthetic.utterance(first + b_i, 10.0), o)
+    if sig:
+        d = np.abs(ya.astype(np.int32) - ref.waveform.astype(np.int32))
+        out["oracle_max_lsb"] = int(d.max())
+        out["oracle_frac_off_by_one"] = float((d > 0).mean())
+        ok = d.max() <= 1 and (d > 0).mean() < 0.005
+    else:
+        fin = np.isfinite(ref.features)
+        same_nf = np.array_equal(np.isfinite(ya), fin)
+        err = np.abs(ya - ref.features)[fin]
+        tol = (1e-4 * np.abs(ref.features) + 1e-3)[fin]
+        out["oracle_max_err_over_tol"] = float((err / tol).max()) if err.size else 0.0
+        ok = same_nf and bool((err <= tol).all())
+    out["tolerance"] = "waveform: <= 1 LSB on < 0.5 % of samples" if sig else "1e-4 relative + 1e-3 absolute (log-domain features)"
+    out["status"] = "ok" if ok else "FAILED: differs from the oracle beyond the parity tolerance"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -221,7 +270,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-seconds", type=float, default=4.0, help="CPU work per core per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--others", action="store_true", help="also run the other workloads (shorter) and report them under 'workloads'")
+    ap.add_argument("--others", default="auto", choices=["auto", "all", "none"],
+                    help="the other BASELINE configs under 'workloads': auto = all of them on one GPU, PLP only under torchrun")
+    ap.add_argument("--no-selfcheck", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
@@ -268,19 +319,23 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def measure(workload, steps, warmup, e2e_steps, with_clocks):
+    # each rank's shard of the utterance list (weak scaling: a.utts per rank): 16 distinct utterances tiled, and every
+    # rank synthesises its OWN 16 (utterance numbers 16*rank .. 16*rank+15), so no two ranks hold the same samples
+    uniq = min(16, a.utts)
+    first = uniq * rank
+    pcm_np, lens = synthetic.batch(a.utts, 10.0, unique=uniq, first=first)
+    h_pcm = torch.empty(len(pcm_np), dtype=torch.int16).pin_memory()
+    h_pcm.numpy()[:] = pcm_np
+    del pcm_np
+    d_pcm = h_pcm.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def measure(workload, steps, warmup, e2e_steps, with_clocks, check):
         args, bytes_step, flops = WORKLOADS[workload]
         hd = cb.Handle(args, device=local)
-        # each rank's shard: its own slice of the utterance list (weak scaling: a.utts per rank)
-        uniq = 16
-        pcm_np, lens = synthetic.batch(a.utts, 10.0, unique=uniq)
-        # rotate by rank so ranks do not hold identical data
         plan = hd.plan(lens)
         frames = plan.total_frames
-        h_pcm = torch.empty(len(pcm_np), dtype=torch.int16).pin_memory()
-        h_pcm.numpy()[:] = pcm_np
-        del pcm_np
-        d_pcm = h_pcm.cuda(non_blocking=True)
         dim = hd.feature_dim
         sig = hd.signal_output
         if sig:
@@ -289,7 +344,6 @@ def main():
         else:
             d_out = torch.empty((frames, dim), dtype=torch.float32, device="cuda")
             h_out = torch.empty((frames, dim), dtype=torch.float32).pin_memory()
-        stream = torch.cuda.current_stream().cuda_stream
 
         def step():
             if sig:
@@ -327,7 +381,6 @@ def main():
             by.setdefault(n, []).append(t)
         kern_ms = {n: sum(v) / steps for n, v in by.items()}
         dom = max(kern_ms, key=kern_ms.get) if kern_ms else None
-        dom_ms = kern_ms.get(dom)
         hop = 256 if workload == "exten" else 160
         sdim = dim // 3 if ("-fea_delta" in args and dim % 3 == 0) else dim      # static block of a _D_A vector
         kinfo = {}
@@ -340,59 +393,84 @@ def main():
             if ab:
                 gbs = frames * ab / (ms_k / 1000.0) / 1e9
                 kinfo[n] = {"ms": ms_k, "alg_bytes_per_frame": ab, "achieved_gbs": gbs}
-        # ---- end to end through the public host-buffer call
+        chk = None
+        if check:
+            try:
+                chk = selfcheck(workload, args, plan, hd, d_out, lens, uniq, first, sig)
+            except Exception as e:      # a broken checker must not hide the measurement; it is reported as such
+                chk = {"status": "FAILED: selfcheck raised %s: %s" % (type(e).__name__, e)}
+        # ---- end to end through the public host-buffer call, and the same chunk schedule with the kernels left out
         e2e = None
         if e2e_steps > 0:
             pcm_host = h_pcm.numpy()
             out_host = h_out.numpy()
             kw = {"waveform": out_host} if sig else {"features": out_host}
-            plan.run_host(pcm_host, want_vad=False, **kw)       # warm-up (allocates the plan's device buffers)
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                plan.run_host(pcm_host, want_vad=False, **kw)
-            torch.cuda.synchronize()
-            dt = max_over_ranks(time.perf_counter() - t0)
-            e2e = {"value": world * frames * e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": int(h_pcm.numel() * 2),
-                   "d2h_bytes_per_step": int(h_out.numel() * h_out.element_size()), "ms_per_step": 1000 * dt / e2e_steps}
-        res = dict(frames=frames, ms=ms, launches=launches, kern_ms=kern_ms, dom=dom, dom_ms=dom_ms, clocks=clocks, e2e=e2e,
-                   bytes_step=bytes_step, kinfo=kinfo, flops=flops, dim=dim, args=args)
+
+            def timed(nsteps):
+                plan.run_host(pcm_host, want_vad=False, **kw)       # warm-up (the first call allocates the plan's device buffers)
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(nsteps):
+                    plan.run_host(pcm_host, want_vad=False, **kw)
+                torch.cuda.synchronize()
+                return max_over_ranks(time.perf_counter() - t0)
+
+            dt = timed(e2e_steps)
+            hd.set_option("copy_only", 1)
+            dtc = timed(e2e_steps)
+            hd.set_option("copy_only", 0)
+            h2d, d2h = int(h_pcm.numel() * 2), int(h_out.numel() * h_out.element_size())
+            e2e = {"value": world * frames * e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": 1000 * dt / e2e_steps, "copy_only_ms": 1000 * dtc / e2e_steps, "frac_of_copy_only": dtc / dt,
+                   "copy_only_gbs_per_gpu": (h2d + d2h) / 1e9 / (dtc / e2e_steps),
+                   "note": "copy_only = the same ctu_plan_run_host chunk schedule (32 MB of PCM per chunk, three streams) with every kernel "
+                           "skipped: frac_of_copy_only close to 1 means the end-to-end time IS the host <-> device copy time of this box at this N"}
+        res = dict(frames=frames, ms=ms, launches=launches, kern_ms=kern_ms, dom=dom, clocks=clocks, e2e=e2e,
+                   bytes_step=bytes_step, kinfo=kinfo, flops=flops, dim=dim, args=args, selfcheck=chk)
         plan.close(); hd.close()
-        del d_pcm, d_out, h_pcm, h_out
+        del d_out, h_out
         torch.cuda.empty_cache()
         return res
 
-    r = measure(a.workload, a.steps, a.warmup, a.e2e_steps, True)
     hbm, peak_src = peaks()
-    value = world * r["frames"] * a.steps / (r["ms"] / 1000.0)
-    roof = None
-    for k in r["kinfo"].values():
-        k["frac"] = k["achieved_gbs"] / hbm
-    if r["dom"] in r["kinfo"]:
+
+    def roofline_of(workload, r, value):
+        for k in r["kinfo"].values():
+            k["frac"] = k["achieved_gbs"] / hbm
+        if r["dom"] not in r["kinfo"]:
+            return None
         ki = r["kinfo"][r["dom"]]
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            t = json.load(open(tp)).get(a.workload + ":" + r["dom"])
+            t = json.load(open(tp)).get(workload + ":" + r["dom"])
             if t:   # measured DRAM bytes per frame (ncu --set full) x frames of this launch
                 traffic = t["dram_bytes_per_frame"] * r["frames"]
-        roof = {"bound": "hbm", "kernel": r["dom"], "achieved": ki["achieved_gbs"], "peak": hbm, "unit": "GB/s", "frac": ki["frac"],
+        return {"bound": "hbm", "kernel": r["dom"], "achieved": ki["achieved_gbs"], "peak": hbm, "unit": "GB/s", "frac": ki["frac"],
                 "traffic": traffic, "peak_source": peak_src, "kernel_ms": ki["ms"], "alg_bytes_per_frame": ki["alg_bytes_per_frame"],
                 "alg_bytes_per_launch": ki["alg_bytes_per_frame"] * r["frames"],
                 "step_alg_bytes_per_frame": r["bytes_step"],
                 "step_hbm_frac": (value / world) * r["bytes_step"] / 1e9 / hbm,
                 "fp32_frac_of_74TF": (value / world) * r["flops"] / 74e12,
-                "kernels": r["kinfo"],
-                "note": "dominant kernel = largest share of the step; the FFT front end is FP32 / shared-memory-pipe bound, not HBM "
-                        "bound (DESIGN.md 3); k_nr_scan is the HBM-bound kernel of this path"}
+                "kernels": r["kinfo"]}
+
+    check = not a.no_selfcheck
+    r = measure(a.workload, a.steps, a.warmup, a.e2e_steps, True, check)
+    value = world * r["frames"] * a.steps / (r["ms"] / 1000.0)
+    roof = roofline_of(a.workload, r, value)
+    if roof:
+        roof["note"] = ("dominant kernel = largest share of the step; the FFT front end is FP32 / shared-memory-pipe bound, not HBM "
+                        "bound (DESIGN.md 3); the noise-reduction scan is the HBM-bound piece of this path")
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": r["ms"] / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": a.workload, "utterances_per_gpu": a.utts, "seconds_per_utt": 10.0, "frames_per_gpu": r["frames"],
                    "feature_dim": r["dim"], "args": " ".join(r["args"]), "l2": "inputs (3.2 GB PCM per GPU) exceed L2; no flush needed",
-                   "sharding": "utterances by rank, no collective", "cpu_affinity": numa},
+                   "sharding": "utterances by rank (rank r holds synthetic utterances 16r .. 16r+15, tiled), no collective",
+                   "cpu_affinity": numa},
         "gpu_launches": r["launches"], "kernel_ms_per_step": r["kern_ms"], "clocks": r["clocks"], "e2e": r["e2e"], "roofline": roof,
+        "selfcheck": (r["selfcheck"] or {}).get("status", "skipped"), "selfcheck_detail": r["selfcheck"],
     }
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         tmp = tempfile.mkdtemp(prefix="ctu_cpu_")
@@ -409,21 +487,25 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
-    if a.others:
-        others = {}
-        for w in WORKLOADS:
-            if w == a.workload:
-                continue
-            try:
-                x = measure(w, max(2, a.steps // 2), 3, 1, False)
-                v = world * x["frames"] * max(2, a.steps // 2) / (x["ms"] / 1000.0)
-                others[w] = {"value": v, "frames_per_gpu": x["frames"], "ms_per_step": x["ms"] / max(2, a.steps // 2),
-                             "kernel_ms_per_step": x["kern_ms"], "e2e": x["e2e"],
-                             "step_hbm_frac": (v / world) * x["bytes_step"] / 1e9 / hbm,
-                             "dominant": x["dom"],
-                             "kernels": {n: dict(k, frac=k["achieved_gbs"] / hbm) for n, k in x["kinfo"].items()}}
-            except Exception as e:
-                others[w] = {"error": str(e)}
+    # ---- the other BASELINE configs, measured the same way with fewer steps (BASELINE.json configs 1, 2, 3, 4, 5)
+    names = []
+    if a.others == "all" or (a.others == "auto" and world == 1):
+        names = [w for w in ("plp", "mfcc_d_a", "exten", "trapdct", "fwss_burg") if w != a.workload]
+    elif a.others == "auto":
+        names = [w for w in ("plp",) if w != a.workload]
+    others = {}
+    for w in names:
+        try:
+            k = max(3, min(5, a.steps // 4))
+            x = measure(w, k, 3, 2, False, check)
+            v = world * x["frames"] * k / (x["ms"] / 1000.0)
+            others[w] = {"value": v, "unit": "frames/s", "steps": k, "warmup": 3, "frames_per_gpu": x["frames"], "ms_per_step": x["ms"] / k,
+                         "args": " ".join(x["args"]), "gpu_launches": x["launches"], "kernel_ms_per_step": x["kern_ms"], "e2e": x["e2e"],
+                         "roofline": roofline_of(w, x, v), "selfcheck": (x["selfcheck"] or {}).get("status", "skipped"),
+                         "selfcheck_detail": x["selfcheck"]}
+        except Exception as e:
+            others[w] = {"error": "%s: %s" % (type(e).__name__, e)}
+    if others:
         line["workloads"] = others
     if rank == 0:
         print(json.dumps(line))

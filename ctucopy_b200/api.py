@@ -134,6 +134,7 @@ def lib() -> C.CDLL:
     L.ctu_plan_colsums.argtypes = [vp, vp, vp]; L.ctu_plan_colsums.restype = C.c_int
     L.ctu_plan_normalise.argtypes = [vp, vp, vp]; L.ctu_plan_normalise.restype = C.c_int
     L.ctu_set_rand_offset.argtypes = [vp, C.c_uint64]; L.ctu_set_rand_offset.restype = C.c_int
+    L.ctu_set_option.argtypes = [vp, cp, i64]; L.ctu_set_option.restype = C.c_int
     L.ctu_host_alloc.argtypes = [P(vp), C.c_uint64]; L.ctu_host_alloc.restype = C.c_int
     L.ctu_host_free.argtypes = [vp]; L.ctu_host_free.restype = None
     _lib = L
@@ -234,6 +235,11 @@ class Handle:
     @property
     def launch_count(self) -> int:
         return int(self.L.ctu_launch_count(self.h))
+
+    def set_option(self, name: str, value: int):
+        """Run-time knobs outside the reference's option set (ctu_set_option): copy_only, chunk_mb, split_front,
+        synth_from_pcm."""
+        self._check(self.L.ctu_set_option(self.h, name.encode(), int(value)))
 
     def profile(self, on: bool):
         self._check(self.L.ctu_profile_enable(self.h, 1 if on else 0))
@@ -347,11 +353,14 @@ class Plan:
         return Result(self.frames_per_utt.copy(), self.rows_per_utt(), self.row_offsets, features, waveform, self.wave_offsets, vnr, vout)
 
 
-def extract(argv: Sequence[str], utterances: List[np.ndarray], ext_vad: Optional[List[np.ndarray]] = None, device: int = 0) -> Result:
+def extract(argv: Sequence[str], utterances: List[np.ndarray], ext_vad: Optional[List[np.ndarray]] = None, device: int = 0,
+            options: Optional[dict] = None) -> Result:
     """One-call convenience used by the parity tests: what `ctucopy <argv> -S list` computes
-    for the listed utterances (each processed as its own file)."""
+    for the listed utterances (each processed as its own file).  options: run-time knobs (Handle.set_option)."""
     hd = Handle(argv, device)
     try:
+        for k, v in (options or {}).items():
+            hd.set_option(k, v)
         plan = hd.plan([len(u) for u in utterances])
         try:
             pcm = np.ascontiguousarray(np.concatenate(utterances).astype(np.int16)) if utterances else np.zeros(0, np.int16)

@@ -23,6 +23,30 @@
 
 using namespace ctu;
 
+// glibc's rand() after srand(1) (random_r TYPE_3: r[i] = r[i-3] + r[i-31] mod 2^32, output r[i] >> 1, 310 values
+// discarded after seeding), which the reference draws once per loaded sample (src/io/in.cc:205, 452-455)
+struct GlibcRand {
+    uint32_t r[34];
+    int i = 0;
+    GlibcRand() {
+        int64_t v = 1;
+        uint32_t init[34];
+        init[0] = 1;
+        for (int k = 1; k < 31; k++) { v = (16807 * (int64_t)init[k - 1]) % 2147483647; if (v < 0) v += 2147483647; init[k] = (uint32_t)v; }
+        for (int k = 31; k < 34; k++) init[k] = init[k - 31];
+        for (int k = 0; k < 34; k++) r[k] = init[k];
+        i = 0;                                   // r[(i + k) % 34] holds element (count + k) of the sequence, k < 34
+        for (int k = 0; k < 310; k++) step();
+    }
+    inline uint32_t step() {                      // element n = element n-31 + element n-3; the window holds n-34 .. n-1
+        const uint32_t v = r[(i + 3) % 34] + r[(i + 31) % 34];
+        r[i] = v;
+        i = (i + 1) % 34;
+        return v;
+    }
+    inline uint32_t next() { return step() >> 1; }
+};
+
 // ------------------------------------------------------------------------------------------
 struct ctu_handle {
     ctu_config cfg;
@@ -72,6 +96,13 @@ struct ctu_handle {
     // similar size, and cudaMalloc / cudaFree of gigabytes cost more than the kernels that use them
     int16_t *d_g711[2] = {nullptr, nullptr};   // expansion tables (mu-law, A-law), uploaded on first use
     uint64_t rand_pos = 0;               // -dither: values of the process-wide rand() stream drawn by earlier plans
+    GlibcRand rand_gen;                  // generator state after rand_gen_pos values (a list is a sequence of plans: the next
+    uint64_t rand_gen_pos = 0;           // plan resumes here instead of stepping from the seed again)
+    // run-time knobs outside the reference's option set (ctu_set_option; the environment gives the defaults)
+    int copy_only = 0;                   // host entry points: copies only, kernels skipped (control measurement)
+    int chunk_mb = 32;                   // MB of PCM per pipeline chunk of the host entry points
+    int split_front = 1;                 // 1: PCM -> spectrum -> features as two kernels; 0: the single fused kernel
+    int synth_from_pcm = 0;              // 1: synthesis recomputes the forward transform instead of reading the stored X
     struct PoolBlock { void *p; size_t bytes; bool used; };
     std::vector<PoolBlock> pool;
 };
@@ -183,6 +214,7 @@ int ctu_fb_matrix(const ctu_handle *h, double *mat, int32_t *lo, int32_t *hi) {
 }
 
 int64_t ctu_num_frames(const ctu_handle *h, int64_t n) {
+    if (!h) return -1;
     if (h->fea_in) return n;                        // feature input: a row is a frame
     const int w = h->cfg.window, s = h->cfg.wshift;
     if (n < w - s) return -1;                       // "IO: Signal shorter than one frame!"
@@ -201,7 +233,9 @@ int64_t ctu_num_output_samples(const ctu_handle *h, int64_t n) {
 // ------------------------------------------------------------------------------------------
 template <class T> static int upload(ctu_handle *h, T **dst, const std::vector<T> &v) {
     CK(cudaMalloc((void **)dst, std::max<size_t>(1, v.size()) * sizeof(T)));
-    if (!v.empty()) CK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    // pageable source: cudaMemcpy may return once the data is staged, and the consumers run on cudaStreamNonBlocking
+    // streams that do not order against the legacy stream -- wait for the DMA itself
+    if (!v.empty()) { CK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice)); CK(cudaDeviceSynchronize()); }
     return CTU_OK;
 }
 
@@ -581,6 +615,9 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     ctu_handle *h = new ctu_handle;
     h->cfg = *cfg;
     h->device = device;
+    if (const char *e = getenv("CTU_SPLIT_FRONT")) h->split_front = atoi(e);
+    if (getenv("CTU_SYNTH_FROM_PCM")) h->synth_from_pcm = 1;
+    if (const char *e = getenv("CTU_CHUNK_MB")) h->chunk_mb = std::max(1, atoi(e));
     auto bail = [&](int st) { g_create_err = h->err; delete h; return st; };
     int st = ctu_config_finalize(&h->cfg);
     if (st) { h->err = ctu_config_error(); return bail(st); }
@@ -748,7 +785,16 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     if ((st = up64(&p->d_pcm_off, pcm_off)) || (st = up64(&p->d_row_off, p->row_off)) || (st = up64(&p->d_osamp_off, p->osamp_off)) ||
         (st = up64(&p->d_t32_off, p->tile32_off)) || (st = up64(&p->d_t64_off, p->tile64_off))) { ctu_plan_destroy(p); return st; }
     if ((st = dev_alloc(h, p, &p->d_nframes, n))) { ctu_plan_destroy(p); return st; }
-    if (n) CK(cudaMemcpy(p->d_nframes, p->nframes.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+#define CKP(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #call;                \
+            ctu_plan_destroy(p);                                                                   \
+            return CTU_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+    if (n) CKP(cudaMemcpy(p->d_nframes, p->nframes.data(), n * sizeof(int), cudaMemcpyHostToDevice));
     if ((st = dev_alloc(h, p, &p->d_tiles32, t32)) || (st = dev_alloc(h, p, &p->d_tiles64, t64))) { ctu_plan_destroy(p); return st; }
     if ((st = up64(&p->d_tF_off, p->tileF_off)) || (st = dev_alloc(h, p, &p->d_tilesF, tF))) { ctu_plan_destroy(p); return st; }
     if (h->signal_out && ((st = up64(&p->d_tS_off, p->tileS_off)) || (st = dev_alloc(h, p, &p->d_tilesS, tS)))) { ctu_plan_destroy(p); return st; }
@@ -758,9 +804,12 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
         k_build_tiles<<<(n + 127) / 128, 128>>>(p->d_nframes, p->d_tF_off, n, F2_TILE, p->d_tilesF);
         if (h->signal_out) k_build_tiles<<<(n + 127) / 128, 128>>>(p->d_nframes, p->d_tS_off, n, p->syn_tile, p->d_tilesS);
         h->lc.launches += h->signal_out ? 4 : 3;
-        CK(cudaGetLastError());
-        CK(cudaDeviceSynchronize());
+        CKP(cudaGetLastError());
     }
+    // the tables above came from pageable memory and the tile lists from the legacy stream; everything that consumes them
+    // runs on non-blocking streams, which do not order against either
+    CKP(cudaDeviceSynchronize());
+#undef CKP
     // workspaces by configuration
     if (h->gather && !h->fea_in && (st = dev_alloc(h, p, &p->d_static, (size_t)rows * h->static_dim))) { ctu_plan_destroy(p); return st; }
     if (h->work_dim != h->feature_dim && (st = dev_alloc(h, p, &p->d_work, (size_t)rows * h->work_dim))) { ctu_plan_destroy(p); return st; }
@@ -769,14 +818,14 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     // PCM -> spectrum (k_frames2, 4-5 CTAs per SM) followed by spectrum -> features is faster than the single fused kernel
     // (2 CTAs per SM) even though the spectrum then makes a round trip through HBM -- measured 12.4 -> 11.4 ms (MFCC_0_D_A),
     // 12.6 -> 11.8 (PLP), 14.9 -> 14.1 (TRAP-DCT) per 9.98 M frames; CTU_SPLIT_FRONT=0 restores the fused kernel
-    static const int split_front = getenv("CTU_SPLIT_FRONT") ? atoi(getenv("CTU_SPLIT_FRONT")) : 1;
+    const int split_front = h->split_front;
     const bool need_spec = h->signal_out || (nr_on && h->cfg.nr_when == 0) || (h->do_vad && h->vad_cri != VCRI_CEPDIST_FEA) ||
                            (split_front && !h->precise && !h->generic && h->fea_kind != FEA_NONE);
     const bool lpc_kind = (h->fea_kind == FEA_LPA || h->fea_kind == FEA_LPC);
     const bool need_fb = !h->signal_out && ((nr_on && h->cfg.nr_when == 1) || lpc_kind);
     if (need_spec && (st = dev_alloc(h, p, &p->d_spec, (size_t)rows * h->nbins))) { ctu_plan_destroy(p); return st; }
     if (h->signal_out && h->bp.nfft && (st = dev_alloc(h, p, &p->d_yt, (size_t)rows * h->cfg.window))) { ctu_plan_destroy(p); return st; }
-    static const int want_cspec = getenv("CTU_SYNTH_FROM_PCM") ? 0 : 1;
+    const int want_cspec = h->synth_from_pcm ? 0 : 1;
     if (h->signal_out && !h->bp.nfft && want_cspec && (st = dev_alloc(h, p, &p->d_cspec, (size_t)rows * NBIN))) { ctu_plan_destroy(p); return st; }
     if (need_fb && !h->precise && (st = dev_alloc(h, p, &p->d_fb, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
     if (need_fb && h->precise && (st = dev_alloc(h, p, &p->d_fb64, (size_t)rows * h->fb.nb))) { ctu_plan_destroy(p); return st; }
@@ -960,44 +1009,28 @@ static int kind_of(const ctu_handle *h) {
     return KIND_SPEC;
 }
 
-// glibc's rand() after srand(1) (random_r TYPE_3: r[i] = r[i-3] + r[i-31] mod 2^32, output r[i] >> 1, 310 values
-// discarded after seeding), which the reference draws once per loaded sample (src/io/in.cc:205, 452-455)
-struct GlibcRand {
-    uint32_t r[34];
-    int i = 0;
-    GlibcRand() {
-        int64_t v = 1;
-        uint32_t init[34];
-        init[0] = 1;
-        for (int k = 1; k < 31; k++) { v = (16807 * (int64_t)init[k - 1]) % 2147483647; if (v < 0) v += 2147483647; init[k] = (uint32_t)v; }
-        for (int k = 31; k < 34; k++) init[k] = init[k - 31];
-        for (int k = 0; k < 34; k++) r[k] = init[k];
-        i = 0;                                   // r[(i + k) % 34] holds element (count + k) of the sequence, k < 34
-        for (int k = 0; k < 310; k++) step();
-    }
-    inline uint32_t step() {                      // element n = element n-31 + element n-3; the window holds n-34 .. n-1
-        const uint32_t v = r[(i + 3) % 34] + r[(i + 31) % 34];
-        r[i] = v;
-        i = (i + 1) % 34;
-        return v;
-    }
-    inline uint32_t next() { return step() >> 1; }
-};
-
 static int prepare_dither(ctu_plan *p) {
     ctu_handle *h = p->h;
     if (!p->d_dither || p->dither_ready) return CTU_OK;
     const int w = h->cfg.window, s = h->cfg.wshift;
     std::vector<float> noise((size_t)p->total_samples + 8, 0.f);
-    GlibcRand g;
-    for (uint64_t k = 0; k < p->rand_base; k++) g.step();
+    // resume from the state the previous plan left (only a shard offset set behind it, ctu_set_rand_offset, or plans
+    // prepared out of order make the generator step from the seed)
+    if (p->rand_base < h->rand_gen_pos) { h->rand_gen = GlibcRand(); h->rand_gen_pos = 0; }
+    GlibcRand &g = h->rand_gen;
+    for (uint64_t k = h->rand_gen_pos; k < p->rand_base; k++) g.step();
+    uint64_t drawn = 0;
     const double d = h->cfg.dither;
     for (int u = 0; u < p->n_utts; u++) {
         const int64_t o = p->offsets[u] - p->offsets[0];
         const int64_t nloaded = (int64_t)p->nframes[u] * s + (w - s);
         for (int64_t k = 0; k < nloaded; k++) noise[(size_t)(o + k)] = (float)((2. * (double)g.next() / 2147483647. - 1.) * d);
+        drawn += (uint64_t)nloaded;
     }
+    h->rand_gen_pos = p->rand_base + drawn;
+    // pageable source, consumers on non-blocking streams: wait for the DMA itself (see upload())
     CK(cudaMemcpy(p->d_dither, noise.data(), noise.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaDeviceSynchronize());
     p->dither_ready = true;
     return CTU_OK;
 }
@@ -1290,12 +1323,25 @@ static int run_host_impl(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad
             if ((st = upload(h, &tab, t))) return st;
         }
     }
-    // chunks of utterances of roughly 64 MB of PCM, round-robin over three streams so that
+    // chunks of utterances of roughly 32 MB of PCM, round-robin over three streams so that
     // H2D of chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap
-    static const int64_t chunk_mb = getenv("CTU_CHUNK_MB") ? atoll(getenv("CTU_CHUNK_MB")) : 32;   // MB of PCM per pipeline chunk (e2e is flat between 16 and 64)
-    const int64_t chunk_samples = chunk_mb << 19;
+    const int64_t chunk_samples = (int64_t)h->chunk_mb << 19;
+    // the NR-internal detector's decisions exist only for hwss / fwss / 2fwss; otherwise the caller gets zeros
+    const bool have_vadnr = h->nr_mode >= NR_HWSS;
+    if (vad_nr && !have_vadnr && !keep) std::memset(vad_nr, 0, (size_t)p->total_frames);
     int u0 = 0, ci = 0;
     const int64_t base = p->offsets[0];
+    st = CTU_OK;
+    // an error in the middle of the loop must not return while copies into the caller's buffers are in flight
+#define CKL(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #call;                \
+            st = CTU_ERR_CUDA;                                                                     \
+            goto drain;                                                                            \
+        }                                                                                          \
+    } while (0)
     while (u0 < p->n_utts) {
         int u1 = u0 + 1;
         while (u1 < p->n_utts && p->offsets[u1 + 1] - p->offsets[u0] <= chunk_samples) u1++;
@@ -1304,32 +1350,42 @@ static int run_host_impl(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad
         int64_t so = p->offsets[u0] - base, sn = p->offsets[u1] - p->offsets[u0];
         if (codes) {
             // one byte per sample over PCIe; expanded next to the PCM buffer's own indexing
-            CK(cudaMemcpyAsync(p->d_codes + so, codes + p->offsets[u0], (size_t)sn, cudaMemcpyHostToDevice, s));
-            if (sn > 0) {
+            CKL(cudaMemcpyAsync(p->d_codes + so, codes + p->offsets[u0], (size_t)sn, cudaMemcpyHostToDevice, s));
+            if (sn > 0 && !h->copy_only) {
                 h->lc.begin("k_g711_expand", s);
                 k_g711_expand<<<(unsigned)std::min<int64_t>((sn / 8 + 256) / 256, 148 * 8), 256, 0, s>>>(p->d_codes, p->d_pcm, so, sn, h->d_g711[alaw ? 1 : 0]);
                 h->lc.end(s);
-                CK(cudaGetLastError());
+                CKL(cudaGetLastError());
             }
         } else {
-            CK(cudaMemcpyAsync(p->d_pcm + so, pcm + p->offsets[u0], sn * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+            CKL(cudaMemcpyAsync(p->d_pcm + so, pcm + p->offsets[u0], sn * sizeof(int16_t), cudaMemcpyHostToDevice, s));
         }
-        if (ext_vad && r.nrows) CK(cudaMemcpyAsync(p->d_ext + r.row0, ext_vad + r.row0, r.nrows, cudaMemcpyHostToDevice, s));
-        if (h->signal_out) CK(cudaMemsetAsync(p->d_wave + p->osamp_off[u0], 0, (size_t)(p->osamp_off[u1] - p->osamp_off[u0]) * sizeof(int16_t), s));
-        if ((st = run_range(p, r, p->d_pcm - base, ext_vad ? p->d_ext : nullptr, p->d_fea, p->d_wave, p->d_vadnr_out, p->d_vad_out, s))) return st;
+        if (ext_vad && r.nrows) CKL(cudaMemcpyAsync(p->d_ext + r.row0, ext_vad + r.row0, r.nrows, cudaMemcpyHostToDevice, s));
+        // copy_only (ctu_set_option): the same chunk schedule with the kernels left out -- the control measurement that
+        // says how much of the end-to-end time is the host <-> device copies themselves (bench.py e2e.copy_only_ms)
+        if (!h->copy_only) {
+            if (h->signal_out) CKL(cudaMemsetAsync(p->d_wave + p->osamp_off[u0], 0, (size_t)(p->osamp_off[u1] - p->osamp_off[u0]) * sizeof(int16_t), s));
+            if ((st = run_range(p, r, p->d_pcm - base, ext_vad ? p->d_ext : nullptr, p->d_fea, p->d_wave, p->d_vadnr_out, p->d_vad_out, s))) goto drain;
+        }
         if (keep) { u0 = u1; ci++; continue; }             // results stay on the device (ctu_plan_fetch brings them back)
         if (!h->signal_out && r.nrows)
-            CK(cudaMemcpyAsync(features + r.row0 * h->feature_dim, p->d_fea + r.row0 * h->feature_dim,
-                               (size_t)r.nrows * h->feature_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+            CKL(cudaMemcpyAsync(features + r.row0 * h->feature_dim, p->d_fea + r.row0 * h->feature_dim,
+                                (size_t)r.nrows * h->feature_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
         if (h->signal_out) {
             int64_t o0 = p->osamp_off[u0], on = p->osamp_off[u1] - o0;
-            CK(cudaMemcpyAsync(waveform + o0, p->d_wave + o0, on * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+            CKL(cudaMemcpyAsync(waveform + o0, p->d_wave + o0, on * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
         }
-        if (vad_nr && r.nrows) CK(cudaMemcpyAsync(vad_nr + r.row0, p->d_vadnr_out + r.row0, r.nrows, cudaMemcpyDeviceToHost, s));
-        if (vad_out && r.nrows && h->do_vad) CK(cudaMemcpyAsync(vad_out + r.row0, p->d_vad_out + r.row0, r.nrows, cudaMemcpyDeviceToHost, s));
+        if (vad_nr && r.nrows && have_vadnr) CKL(cudaMemcpyAsync(vad_nr + r.row0, p->d_vadnr_out + r.row0, r.nrows, cudaMemcpyDeviceToHost, s));
+        if (vad_out && r.nrows && h->do_vad) CKL(cudaMemcpyAsync(vad_out + r.row0, p->d_vad_out + r.row0, r.nrows, cudaMemcpyDeviceToHost, s));
         u0 = u1; ci++;
     }
-    for (int i = 0; i < 3; i++) CK(cudaStreamSynchronize(h->streams[i]));
+#undef CKL
+drain:
+    for (int i = 0; i < 3; i++) {
+        cudaError_t e = cudaStreamSynchronize(h->streams[i]);
+        if (e != cudaSuccess && st == CTU_OK) { h->err = std::string("CUDA: ") + cudaGetErrorString(e) + " (stream synchronize)"; st = CTU_ERR_CUDA; }
+    }
+    if (st) return st;
     return fetch_rows(p, h->streams[0]);
 }
 
@@ -1397,24 +1453,29 @@ int ctu_plan_run_host_fea(ctu_plan *p, const float *fea_in, float *features) {
         p->host_bufs = true;
     }
     // the same three-stream pipeline as the PCM entry point: chunks of utterances of about 32 MB of input
-    const int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)32 << 20) / ((int64_t)h->in_dim * (int64_t)sizeof(float)));
+    const int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)h->chunk_mb << 20) / ((int64_t)h->in_dim * (int64_t)sizeof(float)));
     const float *in0 = fea_in + p->offsets[0] * h->in_dim;
     int u0 = 0, ci = 0;
-    while (u0 < p->n_utts) {
+    st = CTU_OK;
+    cudaError_t ce = cudaSuccess;
+    while (u0 < p->n_utts && st == CTU_OK && ce == cudaSuccess) {
         int u1 = u0 + 1;
         while (u1 < p->n_utts && p->row_off[u1 + 1] - p->row_off[u0] <= chunk_rows) u1++;
         cudaStream_t s = h->streams[ci % 3];
         Range r = make_range(p, u0, u1);
         if (r.nrows) {
-            CK(cudaMemcpyAsync(p->d_in + r.row0 * h->in_dim, in0 + r.row0 * h->in_dim, (size_t)r.nrows * h->in_dim * sizeof(float), cudaMemcpyHostToDevice, s));
-            if ((st = run_range_fea(p, r, p->d_in, p->d_fea, s))) return st;
-            if (features)
-                CK(cudaMemcpyAsync(features + r.row0 * h->feature_dim, p->d_fea + r.row0 * h->feature_dim,
-                                   (size_t)r.nrows * h->feature_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+            ce = cudaMemcpyAsync(p->d_in + r.row0 * h->in_dim, in0 + r.row0 * h->in_dim, (size_t)r.nrows * h->in_dim * sizeof(float), cudaMemcpyHostToDevice, s);
+            if (ce == cudaSuccess && !h->copy_only) st = run_range_fea(p, r, p->d_in, p->d_fea, s);
+            if (ce == cudaSuccess && st == CTU_OK && features)
+                ce = cudaMemcpyAsync(features + r.row0 * h->feature_dim, p->d_fea + r.row0 * h->feature_dim,
+                                     (size_t)r.nrows * h->feature_dim * sizeof(float), cudaMemcpyDeviceToHost, s);
         }
         u0 = u1; ci++;
     }
-    for (int i = 0; i < 3; i++) CK(cudaStreamSynchronize(h->streams[i]));
+    // also on an error: nothing may still be copying into the caller's buffer when this returns
+    for (int i = 0; i < 3; i++) { cudaError_t e = cudaStreamSynchronize(h->streams[i]); if (ce == cudaSuccess) ce = e; }
+    if (st) return st;
+    CK(ce);
     return fetch_rows(p, h->streams[0]);
 }
 
@@ -1435,7 +1496,7 @@ int ctu_plan_colsums(ctu_plan *p, const double *center, double *sums) {
     if ((st = dev_alloc(h, p, &d_s, n))) return st;
     if (center) {
         if ((st = dev_alloc(h, p, &d_c, n))) return st;
-        CK(cudaMemcpy(d_c, center, n * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(d_c, center, n * sizeof(double), cudaMemcpyHostToDevice, h->streams[0]));
     }
     h->lc.begin("k_colsums", h->streams[0]);
     k_colsums<<<(unsigned)((n + 127) / 128), 128, 0, h->streams[0]>>>(p->d_nframes, p->d_row_off, p->n_utts, dim, h->feature_dim, p->d_fea, d_c, d_s);
@@ -1456,8 +1517,9 @@ int ctu_plan_normalise(ctu_plan *p, const double *mean, const double *scale) {
     double *d_m = nullptr, *d_v = nullptr;
     int st;
     if ((st = dev_alloc(h, p, &d_m, n)) || (st = dev_alloc(h, p, &d_v, n))) return st;
-    CK(cudaMemcpy(d_m, mean, n * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_v, scale, n * sizeof(double), cudaMemcpyHostToDevice));
+    // stream-ordered on the stream that runs k_normalise (a pageable source makes the call itself synchronous)
+    CK(cudaMemcpyAsync(d_m, mean, n * sizeof(double), cudaMemcpyHostToDevice, h->streams[0]));
+    CK(cudaMemcpyAsync(d_v, scale, n * sizeof(double), cudaMemcpyHostToDevice, h->streams[0]));
     const int64_t t64 = p->tile64_off[p->n_utts];
     if (t64 > 0) {
         BatchDesc bd64{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tiles64};
@@ -1483,6 +1545,17 @@ int ctu_run(ctu_handle *h, const int16_t *pcm, const int64_t *off, int32_t n, co
     if (!st && rows_per_utt) ctu_plan_rows_per_utt(p, rows_per_utt);
     ctu_plan_destroy(p);
     return st;
+}
+
+int ctu_set_option(ctu_handle *h, const char *name, int64_t value) {
+    if (!h || !name) return CTU_ERR_CONFIG;
+    const std::string n(name);
+    if (n == "copy_only") h->copy_only = value != 0;
+    else if (n == "chunk_mb") h->chunk_mb = (int)std::max<int64_t>(1, value);
+    else if (n == "split_front") h->split_front = value != 0;           // takes effect for plans created afterwards
+    else if (n == "synth_from_pcm") h->synth_from_pcm = value != 0;     // takes effect for plans created afterwards
+    else return fail(h, CTU_ERR_CONFIG, "CTU: unknown run-time option " + n);
+    return CTU_OK;
 }
 
 int ctu_set_rand_offset(ctu_handle *h, uint64_t drawn) {

@@ -98,6 +98,25 @@ CTU_HD void fft256_pass1_rec(cpx<T> (&a)[16], int c, const cpx<T> *tw256, cpx<T>
         xch[(4 * q + 3) * XPAD + c] = cmul(a[4 * q + 3], cmul(wq, w3));
     }
 }
+// the same with the six loaded twiddles handed in: they depend on the thread (c) only, so a persistent kernel loads them
+// once and keeps them in registers.  tw[0..2] = W^c, W^2c, W^3c; tw[3..5] = W^4c, W^8c, W^12c.  Bit-identical to
+// fft256_pass1_rec.
+template <class T>
+CTU_HD void fft256_pass1_reg(cpx<T> (&a)[16], int c, const cpx<T> (&tw)[6], cpx<T> *xch) {
+    dft16(a);
+    xch[c] = a[0];
+    xch[1 * XPAD + c] = cmul(a[1], tw[0]);
+    xch[2 * XPAD + c] = cmul(a[2], tw[1]);
+    xch[3 * XPAD + c] = cmul(a[3], tw[2]);
+#pragma unroll
+    for (int q = 1; q < 4; q++) {
+        const cpx<T> wq = tw[2 + q];
+        xch[(4 * q) * XPAD + c] = cmul(a[4 * q], wq);
+        xch[(4 * q + 1) * XPAD + c] = cmul(a[4 * q + 1], cmul(wq, tw[0]));
+        xch[(4 * q + 2) * XPAD + c] = cmul(a[4 * q + 2], cmul(wq, tw[1]));
+        xch[(4 * q + 3) * XPAD + c] = cmul(a[4 * q + 3], cmul(wq, tw[2]));
+    }
+}
 // pass 2 (after a group-wide sync): thread c now plays k1 = c; loads A[c][n2], transforms
 // over n2; on return a[k2] = Z[c + 16*k2].
 template <class T>
@@ -154,6 +173,37 @@ CTU_HD void rfft_split_pairs(const cpx<T> (&a)[16], const cpx<T> (&Zp)[8], int c
             const cpx<T> B = conj(Z);
             const cpx<T> E = mk<T>((T)0.5 * (A.x + B.x), (T)0.5 * (A.y + B.y));
             const cpx<T> Tt = cmul(twsplit[c + 16 * j], A - B);
+            lo[j] = E + Tt;
+            hi[j] = conj(E - Tt);
+        }
+    }
+    mid = conj(a[8]);   // X[128], meaningful for c == 0
+}
+
+// The split twiddles of thread c are twsplit[c + 16 j] = twsplit[c] * e^{-i pi j/16}: one thread-constant value (kept in
+// a register by the persistent kernels) times eight compile-time constants, instead of eight shared-memory loads per
+// frame.  The product is rounded once more than the table value (<= 1.5 ulp instead of 0.5 ulp on the twiddle).
+template <class T>
+CTU_HD void rfft_split_pairs_rec(const cpx<T> (&a)[16], const cpx<T> (&Zp)[8], int c, cpx<T> ts_c, cpx<T> (&lo)[8], cpx<T> (&hi)[8],
+                                 cpx<T> &mid) {
+    // cos(pi j/16), -sin(pi j/16), j = 0..7
+    const T rc[8] = {(T)1.0, (T)0.98078528040323044913, (T)0.92387953251128675613, (T)0.83146961230254523708,
+                     (T)0.70710678118654752440, (T)0.55557023301960222474, (T)0.38268343236508977173, (T)0.19509032201612826785};
+    const T rs[8] = {(T)0.0, (T)-0.19509032201612826785, (T)-0.38268343236508977173, (T)-0.55557023301960222474,
+                     (T)-0.70710678118654752440, (T)-0.83146961230254523708, (T)-0.92387953251128675613, (T)-0.98078528040323044913};
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        cpx<T> Z = Zp[j];
+        if (c == 0 && j >= 1) Z = a[j >= 1 ? 16 - j : 0];
+        const cpx<T> A = a[j];
+        if (j == 0 && c == 0) {
+            lo[j] = mk<T>(A.x + A.y, (T)0);
+            hi[j] = mk<T>(A.x - A.y, (T)0);
+        } else {
+            const cpx<T> B = conj(Z);
+            const cpx<T> E = mk<T>((T)0.5 * (A.x + B.x), (T)0.5 * (A.y + B.y));
+            const cpx<T> tw = (j == 0) ? ts_c : cmul(ts_c, mk<T>(rc[j], rs[j]));
+            const cpx<T> Tt = cmul(tw, A - B);
             lo[j] = E + Tt;
             hi[j] = conj(E - Tt);
         }

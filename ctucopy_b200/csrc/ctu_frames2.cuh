@@ -79,6 +79,12 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, con
         wr[2 * n1] = (i0 < w) ? sW[i0] : 0.f;
         wr[2 * n1 + 1] = (i0 + 1 < w) ? sW[i0 + 1] : 0.f;
     }
+    // so do its twiddles: the six inter-pass ones it used to load per frame, and twsplit[c] (the other seven split
+    // twiddles are that value times compile-time constants) -- 14 shared-memory loads per frame off the LSU pipe
+    cpx<float> twr[6];
+    twr[0] = sTw[16 + c]; twr[1] = sTw[32 + c]; twr[2] = sTw[48 + c];
+    twr[3] = sTw[64 + c]; twr[4] = sTw[128 + c]; twr[5] = sTw[192 + c];
+    const cpx<float> ts_c = sTs[c];
 #pragma unroll 1
     for (; tile < ntiles; tile += gridDim.x) {
     const int next = tile + gridDim.x;
@@ -92,13 +98,23 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, con
 #pragma unroll 1
     for (int f = grp; f < nf; f += F2_GROUPS) {
         cpx<float> a[16];
+        // sample pairs as 8-byte loads: a half warp covers 128 contiguous bytes, so the two frames of a warp (whose rows
+        // start on the same bank when the shift is a multiple of 32 samples) no longer collide (ncu: 16 of the 105
+        // wavefronts per frame were these conflicts).  Needs an even shift; odd shifts take scalar loads.
         const float *d = sD + f * s;
+        const bool pair = (s & 1) == 0;
         float sum = 0.f;
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) {
             const int i0 = 32 * n1 + 2 * c;
-            float y0 = (i0 < w) ? wr[2 * n1] * d[i0] : 0.f;
-            float y1 = (i0 + 1 < w) ? wr[2 * n1 + 1] * d[i0 + 1] : 0.f;
+            float y0 = 0.f, y1 = 0.f;
+            if (i0 + 1 < w && pair) {
+                const float2 dd = *reinterpret_cast<const float2 *>(d + i0);
+                y0 = wr[2 * n1] * dd.x; y1 = wr[2 * n1 + 1] * dd.y;
+            } else {
+                if (i0 < w) y0 = wr[2 * n1] * d[i0];
+                if (i0 + 1 < w) y1 = wr[2 * n1 + 1] * d[i0 + 1];
+            }
             a[n1] = mk<float>(y0, y1);
             sum += y0 + y1;
         }
@@ -112,11 +128,11 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, con
                 if (i0 + 1 < w) a[n1].y -= mean;
             }
         }
-        fft256_pass1_rec(a, c, sTw, xch);
+        fft256_pass1_reg(a, c, twr, xch);
         __syncwarp(hm);
         fft256_pass2(a, c, xch);
         cpx<float> lo[8], hi[8], mid;
-        rfft_split_shfl(a, c, sTs, lo, hi, mid);
+        rfft_split_shfl_rec(a, c, ts_c, lo, hi, mid);
         __syncwarp(hm);                                       // all reads of the exchange tile are done
         float *g = dst + (row0 + f) * NBIN;
         if (CPLX) {

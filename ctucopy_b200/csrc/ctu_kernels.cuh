@@ -136,6 +136,20 @@ __device__ __forceinline__ void rfft_split_shfl(const cpx<T> (&a)[16], int c, co
     rfft_split_pairs(a, Zp, c, twsplit, lo, hi, mid);
 }
 
+// the same with the split twiddles formed from the thread-constant twsplit[c] (rfft_split_pairs_rec)
+template <class T>
+__device__ __forceinline__ void rfft_split_shfl_rec(const cpx<T> (&a)[16], int c, cpx<T> ts_c, cpx<T> (&lo)[8], cpx<T> (&hi)[8], cpx<T> &mid) {
+    const unsigned m = 0xffffu << (threadIdx.x & 16);
+    const int src = (16 - c) & 15;
+    cpx<T> Zp[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        Zp[j].x = __shfl_sync(m, a[15 - j].x, src, 16);
+        Zp[j].y = __shfl_sync(m, a[15 - j].y, src, 16);
+    }
+    rfft_split_pairs_rec(a, Zp, c, ts_c, lo, hi, mid);
+}
+
 template <class T>
 __device__ __forceinline__ void irfft_presplit_shfl(cpx<T> (&a)[16], int c, const cpx<T> *twinv, const cpx<T> (&lo)[8], const cpx<T> (&hi)[8],
                                                     cpx<T> mid) {

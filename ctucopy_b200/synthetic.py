@@ -60,12 +60,13 @@ def utterance(k: int, seconds: float = 10.0, fs: int = 16000) -> np.ndarray:
     return x.astype(np.int16)
 
 
-def batch(n_utts: int, seconds: float = 10.0, fs: int = 16000, unique: int = 0):
+def batch(n_utts: int, seconds: float = 10.0, fs: int = 16000, unique: int = 0, first: int = 0):
     """Returns (pcm int16 [sum N], lengths int64 [n_utts]).  With unique > 0 only that many
     distinct utterances are synthesised and tiled (the throughput set: 10 000 x 10 s would
-    otherwise take minutes of host time to generate)."""
+    otherwise take minutes of host time to generate).  `first`: number of the first utterance
+    synthesised (a shard of a larger list: rank r of the benchmark starts at 16 r)."""
     u = n_utts if unique <= 0 else min(unique, n_utts)
-    base = [utterance(k, seconds, fs) for k in range(u)]
+    base = [utterance(first + k, seconds, fs) for k in range(u)]
     pcm = np.concatenate([base[i % u] for i in range(n_utts)]) if n_utts else np.zeros(0, np.int16)
     lens = np.array([len(base[i % u]) for i in range(n_utts)], dtype=np.int64)
     return pcm, lens

@@ -89,6 +89,32 @@ template <class T> int run(double tol) {
     }
     printf("inverse (register pre-split): max err %.3g (rel %.3g)\n", e4, e4 / 1000.0);
     bad |= (e4 / 1000.0 > 2 * tol);
+    // ---- the persistent PCM -> spectrum kernel's form: pass-1 twiddles handed in as six thread constants (must be
+    // bit-identical to fft256_pass1_rec) and the split twiddles formed from twsplit[c] times compile-time constants
+    static cpx<T> r3[16][16], lo3[16][8], hi3[16][8], mid3[16];
+    std::vector<cpx<T>> xch3(16 * XPAD);
+    for (int c = 0; c < 16; c++) for (int n1 = 0; n1 < 16; n1++) { int n = 16 * n1 + c; r3[c][n1] = mk<T>((T)x[2 * n], (T)x[2 * n + 1]); r2[c][n1] = r3[c][n1]; }
+    for (int c = 0; c < 16; c++) {
+        cpx<T> tw[6] = {tw256[16 + c], tw256[32 + c], tw256[48 + c], tw256[64 + c], tw256[128 + c], tw256[192 + c]};
+        fft256_pass1_reg(r3[c], c, tw, xch3.data());
+        fft256_pass1_rec(r2[c], c, tw256.data(), xch.data());
+    }
+    for (int i = 0; i < 16 * XPAD; i++) if (i % XPAD < 16) bad |= (xch[i].x != xch3[i].x || xch[i].y != xch3[i].y);
+    for (int c = 0; c < 16; c++) fft256_pass2(r3[c], c, xch3.data());
+    for (int c = 0; c < 16; c++) {
+        cpx<T> Zp[8];
+        for (int j = 0; j < 8; j++) Zp[j] = r3[(16 - c) & 15][15 - j];
+        rfft_split_pairs_rec(r3[c], Zp, c, twsplit[c], lo3[c], hi3[c], mid3[c]);
+    }
+    double e5 = 0;
+    for (int c = 0; c < 16; c++) for (int j = 0; j < 8; j++) {
+        int k = c + 16 * j;
+        e5 = fmax(e5, hypot(lo3[c][j].x - re[k], lo3[c][j].y - im[k]));
+        e5 = fmax(e5, hypot(hi3[c][j].x - re[256 - k], hi3[c][j].y - im[256 - k]));
+    }
+    e5 = fmax(e5, hypot(mid3[0].x - re[128], mid3[0].y - im[128]));
+    printf("forward (register twiddles + composed split twiddles): max err %.3g (rel %.3g)\n", e5, e5 / ref);
+    bad |= (e5 / ref > 2 * tol);
     return bad;
 }
 int main() {
