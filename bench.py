@@ -66,6 +66,9 @@ def kernel_alg_bytes(name, hop, dim, nb):
     return {
         "k_frames<pcm,fea>": pcm + 4 * dim, "k_frames<pcm,spec>": pcm + 4 * 257, "k_frames<pcm,fb>": pcm + 4 * nb,
         "k_frames<spec,fea>": 4 * 257 + 4 * dim, "k_frames<spec,fb>": 4 * 257 + 4 * nb,
+        # k_bank: one spectrum row in (257 bins; the three pad floats per row are overhead, not algorithmic bytes), one
+        # feature / band row out; with the scan fused nothing else moves
+        "k_bank<fea>": 4 * 257 + 4 * dim, "k_bank<nr,fea>": 4 * 257 + 4 * dim, "k_bank<fb>": 4 * 257 + 4 * nb, "k_bank<nr,fb>": 4 * 257 + 4 * nb,
         "k_nr_scan": 2 * 4 * 257, "k_delta": 4 * dim + 8 * dim, "k_lpc": 4 * nb + 4 * dim, "k_trapdct": 4 * nb + 4 * dim,
         "k_synth": pcm + 4 * 257 + pcm, "k_burg": pcm + 8 * 16, "k_cepdet": 8 * 16 + 1,
         "k_stack": 4 * 13 + 4 * dim,          # static block read once, stacked row written once
@@ -388,7 +391,9 @@ def main():
             if workload == "mfcc_trap5":
                 sdim = 13
             d = {"k_delta": sdim, "k_frames<pcm,fea>": sdim if workload != "trapdct" else hd.num_bands,
-                 "k_frames<spec,fea>": sdim, "k_lpc": sdim}.get(n, dim)
+                 "k_frames<spec,fea>": sdim, "k_lpc": sdim,
+                 "k_bank<fea>": sdim if workload != "trapdct" else hd.num_bands,
+                 "k_bank<nr,fea>": sdim if workload != "trapdct" else hd.num_bands}.get(n, dim)
             ab = kernel_alg_bytes(n, hop, d, hd.num_bands)
             if ab:
                 gbs = frames * ab / (ms_k / 1000.0) / 1e9

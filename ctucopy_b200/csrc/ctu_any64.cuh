@@ -14,6 +14,7 @@ struct AnyTables64 {
     const double2 *twsplit;  // -i/2 e^{-2 pi i k / nfft}, k <= M
     const double *win;       // analysis window [window]
     int nfft, log2m;
+    int spitch;              // floats per row of the fp32 spectrum matrix
 };
 
 constexpr int ANY64_THREADS = 128;            // 4 warps per CTA

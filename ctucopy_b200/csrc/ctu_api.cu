@@ -17,8 +17,9 @@
 #include "ctu_kernels.cuh"
 #include "ctu_frames2.cuh"
 #include "ctu_frames_any.cuh"
-#include "ctu_nr_kernels.cuh"
+#include "ctu_nr_params.cuh"
 #include "ctu_precise.cuh"
+#include "ctu_bank.cuh"
 #include "ctu_synth_any.cuh"
 
 using namespace ctu;
@@ -79,6 +80,9 @@ struct ctu_handle {
     // FFT sizes other than 512 (ctu_frames_any.cuh)
     bool generic = false;
     int nbins = NBIN;
+    int spitch = SPITCH;                       // floats per row of the spectrum matrix (general FFT sizes: = nbins)
+    BankTables bank;                           // k_bank's packed filter bank (512-point feature chains)
+    BankParams bkp{};
     float2 *d_any_tw = nullptr, *d_any_ts = nullptr;
     double2 *d_any_tw64 = nullptr, *d_any_ts64 = nullptr;     // fp64 copies for the general synthesis (ctu_synth_any.cuh)
     float *d_any_fbw = nullptr;
@@ -103,6 +107,7 @@ struct ctu_handle {
     int chunk_mb = 32;                   // MB of PCM per pipeline chunk of the host entry points
     int split_front = 1;                 // 1: PCM -> spectrum -> features as two kernels; 0: the single fused kernel
     int synth_from_pcm = 0;              // 1: synthesis recomputes the forward transform instead of reading the stored X
+    int fuse_nr = 1;                     // 1: the noise-reduction scan runs inside k_bank (tile in shared memory) where it can
     struct PoolBlock { void *p; size_t bytes; bool used; };
     std::vector<PoolBlock> pool;
 };
@@ -590,10 +595,11 @@ static int resolve_modes(ctu_handle *h) {
     // dither (src/io/in.cc:452-455): glibc's rand() stream restated on the host, one value per loaded sample in list
     // order; applied by the general kernel
     h->generic = !h->fea_in && ((c.wfft != NFFT) || c.remove_dc1 || c.dither != 0.0);
-    if (h->fea_in) { h->nbins = c.wfftby2; return CTU_OK; }
+    if (h->fea_in) { h->nbins = c.wfftby2; h->spitch = h->nbins; return CTU_OK; }
     if (c.dither != 0.0 && (c.remove_dc1 || (c.fea_E && c.fea_rawenergy)))
         return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -dither together with -remove_dc1 or -fea_rawenergy");
     h->nbins = c.wfftby2;
+    h->spitch = h->generic ? h->nbins : SPITCH;      // 512-point path: rows padded to 260 floats (16-byte aligned)
     if (c.remove_dc1 && c.window / c.wshift + 1 > ANY_DC1_MAX) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -remove_dc1 with a window longer than 17 shifts");
     if (c.remove_dc1 && c.fea_E && c.fea_rawenergy) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: -remove_dc1 together with -fea_rawenergy");
     if (h->generic) {
@@ -617,6 +623,7 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     h->device = device;
     if (const char *e = getenv("CTU_SPLIT_FRONT")) h->split_front = atoi(e);
     if (getenv("CTU_SYNTH_FROM_PCM")) h->synth_from_pcm = 1;
+    if (const char *e = getenv("CTU_FUSE_NR")) h->fuse_nr = atoi(e);
     if (const char *e = getenv("CTU_CHUNK_MB")) h->chunk_mb = std::max(1, atoi(e));
     auto bail = [&](int st) { g_create_err = h->err; delete h; return st; };
     int st = ctu_config_finalize(&h->cfg);
@@ -631,7 +638,7 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     if (!h->fea_in && (st = build_nr_params(h->cfg, h->nr_mode, h->vad_src, h->signal_out, h->fb.nb, h->nrp, h->sp, h->bp, h->vp, h->err))) return bail(st);
     h->vp.cri = h->vad_cri; h->vp.thr = h->vad_thr; h->vp.drop = h->vad_drop;
     h->vp.has_E = h->energy_mode ? 1 : 0;
-    h->vp.nbins = h->nbins;
+    h->vp.nbins = h->nbins; h->vp.spitch = h->spitch; h->bp.spitch = h->spitch;
     // the reference's vector is in internal order (c0 first, a0 first); rows here are in writer order
     if (h->fea_kind == FEA_DCTC || h->fea_kind == FEA_LPC) h->vp.fea_skip = h->cfg.fea_c0 ? h->static_dim - 1 : -1;
     else if (h->fea_kind == FEA_LPA) h->vp.fea_skip = -1;
@@ -682,6 +689,25 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     if (h->precise) {
         if ((st = upload(h, &h->d_w64, h->w64)) || (st = upload(h, &h->d_m264, h->m264)) || (st = upload(h, &h->d_lift64, h->lift64))) return bail(st);
     }
+    if (!h->generic && !h->fea_in && !h->signal_out && !h->precise && h->fea_kind != FEA_NONE) {
+        // k_bank's copy of the filter bank: bands aligned to groups of four bins, second-stage matrix, geometry
+        std::vector<int4> bands; std::vector<float> w;
+        bank_pack(h->fp, bands, w);
+        std::vector<float4> w4(w.size() / 4);
+        for (size_t i = 0; i < w4.size(); i++) w4[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        std::vector<float> m2((size_t)std::max(1, h->fp.nrows * h->fp.nbp));
+        if (h->fea_kind == FEA_DCTC) for (int i = 0; i < h->fp.nrows * h->fp.nbp; i++) m2[i] = h->fp.m2[i];
+        if ((st = upload(h, &h->bank.d_bands, bands)) || (st = upload(h, &h->bank.d_w4, w4)) || (st = upload(h, &h->bank.d_m2, m2))) return bail(st);
+        h->bank.wtot4 = (int)w4.size();
+        h->bank.ypitch = ((h->fp.nbp + 31) / 32) * 32 + 4;
+        BankParams &B = h->bkp;
+        B.nb = h->fp.nb; B.nbp = h->fp.nbp; B.ypitch = h->bank.ypitch;
+        B.inld = h->fp.inld; B.inld_scale = h->fp.inld_scale; B.lin_scale = h->fp.lin_scale; B.log_offset = h->fp.log_offset;
+        B.nrows = (h->fea_kind == FEA_DCTC) ? h->fp.nrows : 0;
+        B.take_sqrt = h->fp.take_sqrt;
+        B.wtot4 = h->bank.wtot4; B.bands = h->bank.d_bands; B.w4 = h->bank.d_w4; B.m2 = h->bank.d_m2;
+        B.nr = h->nrp;
+    }
     for (int i = 0; i < 3; i++)
         if (cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking) != cudaSuccess) { h->err = "CUDA: stream creation failed"; return bail(CTU_ERR_CUDA); }
     *out = h;
@@ -697,6 +723,7 @@ void ctu_destroy(ctu_handle *h) {
     cudaFree(h->d_any_tw64); cudaFree(h->d_any_ts64);
     cudaFree(h->d_g711[0]); cudaFree(h->d_g711[1]);
     cudaFree(h->d_any_tw); cudaFree(h->d_any_ts); cudaFree(h->d_any_fbw); cudaFree(h->d_any_bands);
+    cudaFree(h->bank.d_bands); cudaFree(h->bank.d_w4); cudaFree(h->bank.d_m2);
     for (auto &b : h->pool) cudaFree(b.p);
     for (int i = 0; i < 3; i++) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     h->lc.clear();
@@ -823,7 +850,7 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
                            (split_front && !h->precise && !h->generic && h->fea_kind != FEA_NONE);
     const bool lpc_kind = (h->fea_kind == FEA_LPA || h->fea_kind == FEA_LPC);
     const bool need_fb = !h->signal_out && ((nr_on && h->cfg.nr_when == 1) || lpc_kind);
-    if (need_spec && (st = dev_alloc(h, p, &p->d_spec, (size_t)rows * h->nbins))) { ctu_plan_destroy(p); return st; }
+    if (need_spec && (st = dev_alloc(h, p, &p->d_spec, (size_t)rows * h->spitch))) { ctu_plan_destroy(p); return st; }
     if (h->signal_out && h->bp.nfft && (st = dev_alloc(h, p, &p->d_yt, (size_t)rows * h->cfg.window))) { ctu_plan_destroy(p); return st; }
     const int want_cspec = h->synth_from_pcm ? 0 : 1;
     if (h->signal_out && !h->bp.nfft && want_cspec && (st = dev_alloc(h, p, &p->d_cspec, (size_t)rows * NBIN))) { ctu_plan_destroy(p); return st; }
@@ -937,6 +964,9 @@ static int launch_frames_w(ctu_handle *h, const FrameParams &P, const ctu_plan *
         h->lc.begin(names[SRC][DST], s);
         kern<<<grid, F2_THREADS, bytes, s>>>(P, bd, tb, pcm, dst, (int)ft.n16, ft.cplx);
         h->lc.end(s);
+    } else if constexpr (SRC == SRC_SPEC) {
+        // 512-point spectra (rows of SPITCH floats) are consumed by k_bank (ctu_bank.cuh)
+        return fail(h, CTU_ERR_CONFIG, "CTU: internal: spectrum source outside k_bank");
     } else {
         if (ft.n32 <= 0) return CTU_OK;
         SmemLayout L = smem_layout(P.window, P.wshift, P.nb, SRC == SRC_PCM);
@@ -1125,6 +1155,10 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
         if ((st = launch_frames_t<SRC_PCM, DST_SPEC, KIND_SPEC>(h, P, p, ft, d_pcm, nullptr, p->d_spec, s))) return st;
         ft.cplx = nullptr;
     }
+    // the scan runs inside k_bank, on the tile in shared memory, whenever nothing but the filter bank consumes the enhanced
+    // spectrum (the enhanced spectrum then never exists in HBM)
+    const bool bank_path = need_spec && !h->generic && !h->precise && !h->signal_out && h->fea_kind != FEA_NONE;
+    const bool fuse_scan = bank_path && nr_on && before && h->fuse_nr && !h->do_vad && h->nrp.a_kind != 0;
     if (nr_on && before) {
         if (h->nr_mode >= NR_HWSS && h->vad_src == VADSRC_BURG) {
             if ((st = launch_burg(h->bp, BURG_SRC_NR, bd32, r.t32_n, d_pcm, nullptr, p->d_ceps, h->d_tw256d, h->d_twsplitd, h->d_twinvd, h->d_wind,
@@ -1133,7 +1167,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
         }
         const uint8_t *fl = (h->nr_mode >= NR_HWSS) ? (h->vad_src == VADSRC_FILE ? d_ext : flags) : nullptr;
         if (h->nr_mode >= NR_HWSS && !fl) return fail(h, CTU_ERR_INPUT, "NR: Unable to open VAD file!\n");
-        if ((st = launch_nr_scan(h->nrp, p->d_nframes, p->d_row_off, r.u0, r.u1, h->nbins, p->d_spec, fl, s, &h->lc, h->err))) return st;
+        if (!fuse_scan && (st = launch_nr_scan(h->nrp, p->d_nframes, p->d_row_off, r.u0, r.u1, h->nbins, h->spitch, p->d_spec, fl, s, &h->lc, h->err))) return st;
         if (h->vad_src == VADSRC_FILE && d_vadnr && h->nr_mode >= NR_HWSS)
             CK(cudaMemcpyAsync(d_vadnr + r.row0, d_ext + r.row0, r.nrows, cudaMemcpyDeviceToDevice, s));
     }
@@ -1144,7 +1178,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
         const int N = h->cfg.wfft, M = N / 2;
         int lg = 0;
         while ((1 << lg) < M) lg++;
-        AnyTables64 tb{h->d_any_tw64, h->d_any_ts64, h->d_wind, N, lg};
+        AnyTables64 tb{h->d_any_tw64, h->d_any_ts64, h->d_wind, N, lg, h->spitch};
         const size_t bytes = (size_t)(SYNANY_THREADS / 32) * (4 * M + 4) * sizeof(double);
         CK(cudaFuncSetAttribute(k_synth_frames_any, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         h->lc.begin("k_synth_frames_any", s);
@@ -1177,31 +1211,40 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     P.energy_mode = h->energy_mode; P.energy = p->d_E;
     P.dc1 = p->d_dc1;
     P.dither = p->d_dither ? p->d_dither - p->offsets[0] : nullptr;
+    BankParams BK = h->bkp;
+    BK.energy_mode = h->energy_mode; BK.energy = p->d_E;
+    BK.flags = (h->nr_mode >= NR_HWSS) ? (h->vad_src == VADSRC_FILE ? d_ext : flags) : nullptr;
     if (h->precise) {
         // fp64 path (ctu_precise.cuh): band-domain noise reduction / ill-conditioned LPC /
         // features that feed VAD decisions
-        Tables64 t64{h->d_tw256d, h->d_twsplitd, h->d_wind, h->d_w64, h->d_m264, h->d_lift64, h->bp.nfft, h->bp.log2m, h->bp.any_tw, h->bp.any_ts};
+        Tables64 t64{h->d_tw256d, h->d_twsplitd, h->d_wind, h->d_w64, h->d_m264, h->d_lift64, h->bp.nfft, h->bp.log2m, h->bp.any_tw, h->bp.any_ts, h->spitch};
         double *f64 = (kind == KIND_TRAPLOG) ? nullptr : p->d_fea64;
         if (nr_on && !before) {
             const uint8_t *fl = (h->nr_mode >= NR_HWSS) ? d_ext : nullptr;
             if (h->nr_mode >= NR_HWSS && !fl) return fail(h, CTU_ERR_INPUT, "NR: Unable to open VAD file!\n");
-            if ((st = launch_frames64_t<SRC64_PCM, DST64_FB, KIND_SPEC>(P, bd32, t64, r.t32_n, d_pcm, nullptr, nullptr, p->d_fb64, nullptr, s, &h->lc, h->err))) return st;
+            if ((st = launch_frames64(SRC64_PCM, DST64_FB, KIND_SPEC, P, bd32, t64, r.t32_n, d_pcm, nullptr, nullptr, p->d_fb64, nullptr, s, &h->lc, h->err))) return st;
             if ((st = launch_nr_scan64(h->nrp, p->d_nframes, p->d_row_off, r.u0, r.u1, h->fb.nb, p->d_fb64, fl, s, &h->lc, h->err))) return st;
             if (d_vadnr && fl) CK(cudaMemcpyAsync(d_vadnr + r.row0, d_ext + r.row0, r.nrows, cudaMemcpyDeviceToDevice, s));
-            if ((st = launch_frames64_k<SRC64_FB, DST64_FEA>(kind, P, bd32, t64, r.t32_n, nullptr, p->d_fb64, nullptr, f64, fea_dst, s, &h->lc, h->err))) return st;
+            if ((st = launch_frames64(SRC64_FB, DST64_FEA, kind, P, bd32, t64, r.t32_n, nullptr, p->d_fb64, nullptr, f64, fea_dst, s, &h->lc, h->err))) return st;
         } else if (nr_on && before) {
             // noise-reduced fp32 spectrum (stage 1) is the source
-            if ((st = launch_frames64_k<SRC64_SPEC, DST64_FEA>(kind, P, bd32, t64, r.t32_n, nullptr, nullptr, p->d_spec, f64, fea_dst, s, &h->lc, h->err))) return st;
+            if ((st = launch_frames64(SRC64_SPEC, DST64_FEA, kind, P, bd32, t64, r.t32_n, nullptr, nullptr, p->d_spec, f64, fea_dst, s, &h->lc, h->err))) return st;
         } else {
-            if ((st = launch_frames64_k<SRC64_PCM, DST64_FEA>(kind, P, bd32, t64, r.t32_n, d_pcm, nullptr, nullptr, f64, fea_dst, s, &h->lc, h->err))) return st;
+            if ((st = launch_frames64(SRC64_PCM, DST64_FEA, kind, P, bd32, t64, r.t32_n, d_pcm, nullptr, nullptr, f64, fea_dst, s, &h->lc, h->err))) return st;
         }
     } else if (kind == KIND_LPA || kind == KIND_LPC) {
         // band values to HBM (76 B per frame for PLP), then one thread per frame for the recursion
         FrameParams Pf = h->fp; Pf.out_dim = h->fb.nb; Pf.out_stride = h->fb.nb;   // (its energy comes from k_lpc: log R0)
         Pf.dc1 = p->d_dc1; Pf.dither = P.dither;
-        if (need_spec) { if ((st = launch_frames_t<SRC_SPEC, DST_FB, KIND_SPEC>(h, Pf, p, ft, nullptr, p->d_spec, p->d_fb, s))) return st; }
+        if (bank_path) {
+            BK.out_dim = h->fb.nb; BK.out_stride = h->fb.nb; BK.energy_mode = EN_NONE;      // (log R0 comes from k_lpc)
+            if ((st = launch_bank(BK, kind, true, fuse_scan, bd32, r.t32_n, r.u0, r.u1 - r.u0, h->num_sms, p->d_spec, p->d_fb, s, &h->lc, h->err))) return st;
+        } else if (need_spec) { if ((st = launch_frames_t<SRC_SPEC, DST_FB, KIND_SPEC>(h, Pf, p, ft, nullptr, p->d_spec, p->d_fb, s))) return st; }
         else if ((st = launch_frames_t<SRC_PCM, DST_FB, KIND_SPEC>(h, Pf, p, ft, d_pcm, nullptr, p->d_fb, s))) return st;
         if ((st = launch_lpc(h, P, kind == KIND_LPC, r.row0, r.nrows, p->d_fb, fea_dst, s))) return st;
+    } else if (bank_path) {
+        BK.out_dim = od; BK.out_stride = ostride;
+        if ((st = launch_bank(BK, kind, false, fuse_scan, bd32, r.t32_n, r.u0, r.u1 - r.u0, h->num_sms, p->d_spec, fea_dst, s, &h->lc, h->err))) return st;
     } else if (need_spec) {
         if ((st = launch_frames_k<SRC_SPEC, DST_FEA>(h, kind, P, p, ft, nullptr, p->d_spec, fea_dst, s))) return st;
     } else {
@@ -1554,6 +1597,7 @@ int ctu_set_option(ctu_handle *h, const char *name, int64_t value) {
     else if (n == "chunk_mb") h->chunk_mb = (int)std::max<int64_t>(1, value);
     else if (n == "split_front") h->split_front = value != 0;           // takes effect for plans created afterwards
     else if (n == "synth_from_pcm") h->synth_from_pcm = value != 0;     // takes effect for plans created afterwards
+    else if (n == "fuse_nr") h->fuse_nr = value != 0;
     else return fail(h, CTU_ERR_CONFIG, "CTU: unknown run-time option " + n);
     return CTU_OK;
 }
@@ -1579,8 +1623,19 @@ int ctu_debug_spectrum(ctu_plan *p, const int16_t *d_pcm, float *d_spec, void *s
     CK(cudaSetDevice(h->device));
     const FrameTiles ft{p->d_tiles32, p->tile32_off[p->n_utts], p->d_tilesF, p->tileF_off[p->n_utts]};
     FrameParams P = h->fp; P.out_dim = h->nbins; P.out_stride = h->nbins;
-    int st = launch_frames_t<SRC_PCM, DST_SPEC, KIND_SPEC>(h, P, p, ft, d_pcm, nullptr, d_spec, (cudaStream_t)stream);
+    // the kernels write rows of h->spitch floats (260 on the 512-point path); the tap hands out compact rows
+    float *tmp = d_spec;
+    int st;
+    if (h->spitch != h->nbins) {
+        tmp = p->d_spec;
+        if (!tmp && (st = dev_alloc(h, p, &p->d_spec, (size_t)p->total_frames * h->spitch))) return st;
+        tmp = p->d_spec;
+    }
+    st = launch_frames_t<SRC_PCM, DST_SPEC, KIND_SPEC>(h, P, p, ft, d_pcm, nullptr, tmp, (cudaStream_t)stream);
     if (st) return st;
+    if (tmp != d_spec && p->total_frames > 0)
+        CK(cudaMemcpy2DAsync(d_spec, (size_t)h->nbins * sizeof(float), tmp, (size_t)h->spitch * sizeof(float), (size_t)h->nbins * sizeof(float),
+                             (size_t)p->total_frames, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return CTU_OK;
 }

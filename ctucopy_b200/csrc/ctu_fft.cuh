@@ -22,6 +22,7 @@ namespace ctu {
 constexpr int NFFT = 512;   // real transform length handled by the fast path
 constexpr int NC = 256;     // complex length
 constexpr int NBIN = 257;   // NFFT/2 + 1
+constexpr int SPITCH = 260; // floats per spectrum row in HBM (512-point path): 16-byte aligned rows, three zero pad columns
 constexpr int GROUP = 16;   // threads per frame
 constexpr int XPAD = 17;    // row pitch (in complex elements) of the 16x16 exchange tile
 

@@ -134,7 +134,7 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, con
         cpx<float> lo[8], hi[8], mid;
         rfft_split_shfl_rec(a, c, ts_c, lo, hi, mid);
         __syncwarp(hm);                                       // all reads of the exchange tile are done
-        float *g = dst + (row0 + f) * NBIN;
+        float *g = dst + (row0 + f) * SPITCH;
         if (CPLX) {
             float2 *gc = cdst + (row0 + f) * NBIN;
 #pragma unroll
@@ -157,6 +157,8 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, con
         if (c == 0) {
             const float pm = mid.x * mid.x + mid.y * mid.y;
             g[128] = P.take_sqrt ? sqrtf(pm) : pm;
+        } else if (c <= SPITCH - NBIN) {
+            g[NBIN - 1 + c] = 0.f;                             // pad columns: read (times zero weights) by the 16-byte loads of k_bank
         }
     }
     __syncthreads();                                          // sD is re-staged by the next iteration

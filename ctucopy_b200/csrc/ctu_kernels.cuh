@@ -596,7 +596,7 @@ k_frames(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, cons
 // and a float coefficient, applied to the finished rows (the deltas were taken from the
 // un-normalised statics, src/io/batch.cc:159-163).  One thread per (utterance, column).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_cms_exp(const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int u0, int n_utts, int ncols, int stride, float Z,
           float *__restrict__ fea) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -632,7 +632,7 @@ k_cms_exp(const int *__restrict__ nframes, const int64_t *__restrict__ row_off, 
 // order -- the host adds the utterances of a speaker in list order, so the statistics are
 // reproducible -- and the normalisation (F - mean) / var of every row.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_colsums(const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int n_utts, int dim, int stride,
           const float *__restrict__ fea, const double *__restrict__ center, double *__restrict__ sums) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -647,7 +647,7 @@ k_colsums(const int *__restrict__ nframes, const int64_t *__restrict__ row_off, 
     sums[gid] = acc;
 }
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_normalise(BatchDesc bd, int dim, int stride, const double *__restrict__ mean, const double *__restrict__ scale, float *__restrict__ fea) {
     const int2 tile = bd.tiles[blockIdx.x];
     const int u = tile.x, t0 = tile.y;
@@ -665,7 +665,7 @@ k_normalise(BatchDesc bd, int dim, int stride, const double *__restrict__ mean, 
 // raw energy (src/io/in.cc:353-361): log of the sum of squares of the frame's raw samples 1..w-1
 // (the first one is skipped).  One warp per frame.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_rawenergy(BatchDesc bd, int window, int wshift, const int16_t *__restrict__ pcm, float *__restrict__ energy) {
     const int2 tile = bd.tiles[blockIdx.x];
     const int u = tile.x, t0 = tile.y;
@@ -683,7 +683,7 @@ k_rawenergy(BatchDesc bd, int window, int wshift, const int16_t *__restrict__ pc
 
 // The writer reads *E when a row leaves the delta / VAD delay lines (src/io/out.cc:183-202), so
 // row t carries the energy of frame min(t + latency, T-1): last column of the feature matrix.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_place_energy(BatchDesc bd, int latency, int stride, const float *__restrict__ energy, float *__restrict__ fea) {
     const int2 tile = bd.tiles[blockIdx.x];
     const int u = tile.x, t0 = tile.y;
@@ -775,7 +775,8 @@ k_lpc(const __grid_constant__ FrameParams P, int64_t row0, int64_t nrows, const 
 }
 
 // one thread per utterance writes that utterance's tile descriptors
-__global__ void k_build_tiles(const int *__restrict__ nframes, const int64_t *__restrict__ tile_off, int n_utts, int tile_f,
+// (the non-template kernels of this header are `static`: it is included by several translation units)
+static __global__ void k_build_tiles(const int *__restrict__ nframes, const int64_t *__restrict__ tile_off, int n_utts, int tile_f,
                               int2 *__restrict__ tiles) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_utts) return;
@@ -1084,7 +1085,7 @@ k_stack(const StackParams S, BatchDesc bd, int tile_rows, const float *__restric
 // Both buffers are indexed by the same absolute sample index and allocated 256-byte aligned, so a thread takes the
 // 8 samples [8i, 8i+8) of the range rounded down to a multiple of 8: one 8-byte load, one 16-byte store.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_g711_expand(const uint8_t *__restrict__ codes, int16_t *__restrict__ pcm, int64_t first, int64_t count, const int16_t *__restrict__ table) {
     __shared__ int16_t lut[256];
     lut[threadIdx.x] = table[threadIdx.x];

@@ -13,7 +13,7 @@
 #define CTU_PRECISE_CUH
 
 #include "ctu_kernels.cuh"
-#include "ctu_nr_kernels.cuh"
+#include "ctu_nr_params.cuh"
 
 namespace ctu {
 
@@ -32,8 +32,16 @@ struct Tables64 {
     // FFT sizes other than 512: k_frames64_any (nfft == 0: the specialised kernel)
     int nfft, log2m;
     const double2 *any_tw, *any_ts;
+    int spitch;            // floats per row of the fp32 spectrum matrix (SRC64_SPEC)
 };
 
+// non-template entry points (defined in ctu_precise.cu, where the kernels below are compiled)
+int launch_frames64(int src_kind, int dst_kind, int kind, const FrameParams &P, const BatchDesc &bd, const Tables64 &tb, int64_t ntiles, const int16_t *pcm,
+                    const double *src64, const float *spec, double *dst64, float *dst, cudaStream_t stream, LaunchCtx *lc, std::string &err);
+int launch_nr_scan64(const NrParams &N, const int *d_nframes, const int64_t *d_row_off, int u0, int u1, int size, double *X,
+                     const uint8_t *flags, cudaStream_t s, LaunchCtx *lc, std::string &err);
+
+#ifdef CTU_PRECISE_IMPL
 template <int LANES> __device__ __forceinline__ double lanes_sum_d(double v) {
     if (LANES == 16) return group_sum16d(v);
 #pragma unroll
@@ -193,7 +201,7 @@ k_frames64(const __grid_constant__ FrameParams P, BatchDesc bd, Tables64 tb, con
         const bool active = f < nf;
         if (SRC == SRC64_SPEC) {
             // (noise-reduced) fp32 spectrum from HBM, widened
-            if (active) for (int k = c; k < NBIN; k += GROUP) pr[k] = (double)spec[(row0 + f) * NBIN + k];
+            if (active) for (int k = c; k < NBIN; k += GROUP) pr[k] = (double)spec[(row0 + f) * tb.spitch + k];
             __syncwarp();
         }
         if (SRC == SRC64_PCM) {
@@ -275,7 +283,7 @@ k_frames64_any(const __grid_constant__ FrameParams P, BatchDesc bd, Tables64 tb,
     const int64_t row0 = bd.row_off[u] + t0;
     for (int f = wv; f < nf; f += ANY64_THREADS / 32) {
         if (SRC == SRC64_SPEC) {
-            for (int k = lane; k < nbins; k += 32) pr[k] = (double)spec[(row0 + f) * nbins + k];
+            for (int k = lane; k < nbins; k += 32) pr[k] = (double)spec[(row0 + f) * tb.spitch + k];
             __syncwarp();
         }
         if (SRC == SRC64_PCM) {
@@ -389,7 +397,7 @@ k_nr_scan64(const __grid_constant__ NrParams N, const int *__restrict__ nframes,
     }
 }
 
-static inline int launch_nr_scan64(const NrParams &N, const int *d_nframes, const int64_t *d_row_off, int u0, int u1, int size, double *X,
+int launch_nr_scan64(const NrParams &N, const int *d_nframes, const int64_t *d_row_off, int u0, int u1, int size, double *X,
                                    const uint8_t *flags, cudaStream_t s, LaunchCtx *lc, std::string &err) {
     int64_t n = (int64_t)(u1 - u0) * size;
     if (n <= 0) return CTU_OK;
@@ -400,6 +408,18 @@ static inline int launch_nr_scan64(const NrParams &N, const int *d_nframes, cons
     if (e != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e) + " (k_nr_scan64)"; return CTU_ERR_CUDA; }
     return CTU_OK;
 }
+
+int launch_frames64(int src_kind, int dst_kind, int kind, const FrameParams &P, const BatchDesc &bd, const Tables64 &tb, int64_t nt, const int16_t *pcm,
+                    const double *src64, const float *spec, double *dst64, float *dst, cudaStream_t s, LaunchCtx *lc, std::string &err) {
+    const int src = src_kind, dst_k = dst_kind;
+    if (src == SRC64_PCM && dst_k == DST64_FB) return launch_frames64_t<SRC64_PCM, DST64_FB, KIND_SPEC>(P, bd, tb, nt, pcm, src64, spec, dst64, dst, s, lc, err);
+    if (src == SRC64_FB && dst_k == DST64_FEA) return launch_frames64_k<SRC64_FB, DST64_FEA>(kind, P, bd, tb, nt, pcm, src64, spec, dst64, dst, s, lc, err);
+    if (src == SRC64_SPEC && dst_k == DST64_FEA) return launch_frames64_k<SRC64_SPEC, DST64_FEA>(kind, P, bd, tb, nt, pcm, src64, spec, dst64, dst, s, lc, err);
+    if (src == SRC64_PCM && dst_k == DST64_FEA) return launch_frames64_k<SRC64_PCM, DST64_FEA>(kind, P, bd, tb, nt, pcm, src64, spec, dst64, dst, s, lc, err);
+    err = "CTU: internal: unsupported fp64 chain";
+    return CTU_ERR_CONFIG;
+}
+#endif  // CTU_PRECISE_IMPL
 
 }  // namespace ctu
 #endif

@@ -31,7 +31,7 @@ k_synth_frames_any(int window, int wshift, double preem, int remove_dc, BatchDes
     for (int f = wv; f < nf; f += SYNANY_THREADS / 32) {
         any64_analysis(z, tb, pcm + bd.pcm_off[u] + (int64_t)(t0 + f) * s, (t0 + f) == 0, w, preem, remove_dc, lane);
         // ---- real-input split; enhanced magnitude on the original phase, scaled by 1/nfft (src/io/out.cc:417-424) ---
-        const float *A = spec + (row0 + f) * nbins;
+        const float *A = spec + (row0 + f) * tb.spitch;
         const double invn = 1.0 / (double)nfft;
         for (int k = lane; k <= M; k += 32) {
             const cpx<double> X = any64_bin(z, tb, k);
