@@ -11,10 +11,14 @@
 // and writes each frame's result once.
 //
 // Work unit: a tile of 32 consecutive frames of one utterance = ONE contiguous run of nf * 1040 bytes, fetched by a
-// single bulk asynchronous copy (cp.async.bulk + mbarrier: no load instructions, no LSU traffic, no registers), double
-// buffered: tile i+1 is in flight while tile i is processed.  CTAs are persistent.  Without a scan they stride over the
-// plan's 32-frame tile list; with a scan each CTA owns whole utterances (u = blockIdx.x, += gridDim.x) and walks their
-// tiles in time order with the recursion state of its 257 bins in registers.
+// single bulk asynchronous copy (cp.async.bulk + mbarrier: no load instructions, no LSU traffic, no registers).  A CTA
+// holds ONE tile (44 KB of shared memory in all, 64 registers: four CTAs = 32 warps per SM) and asks for its next tile
+// as soon as the filter bank has consumed the current one, so the copy overlaps its own second stage and store and the
+// other three CTAs' work.  (First version: two tile buffers per CTA, two CTAs per SM -- every phase between two
+// barriers then had 16 warps to hide its latencies with, and the fused scan, a 32-step dependent chain per bin, ran at a
+// third of the speed of the standalone scan kernel.)  CTAs are persistent.  Without a scan they stride over the plan's
+// 32-frame tile list; with a scan each CTA owns whole utterances (u = blockIdx.x, += gridDim.x) and walks their tiles
+// in time order with the recursion state of its 257 bins in registers.
 //
 // Filter bank: lane == frame.  A lane reads its frame's row with 16-byte loads (row pitch 260 floats = 4 mod 32 banks:
 // the eight lanes of a quarter warp cover all 32 banks, so a 128-bit load costs its minimum of four wavefronts) and the
@@ -50,17 +54,18 @@ struct BankParams {
     const uint8_t *flags;      // detector decisions per frame (hwss / fwss / 2fwss)
 };
 
-struct BankSmem { int oTile, oY, oW, oM, oBands, oFlags, oBar, total; };     // float offsets
-__host__ __device__ inline BankSmem bank_smem(int nb, int nbp, int ypitch, int wtot4, int nrows) {
+struct BankSmem { int oTile, oY, oO, oW, oM, oBands, oFlags, oBar, total; };     // float offsets
+__host__ __device__ inline BankSmem bank_smem(int nb, int nbp, int ypitch, int wtot4, int nrows, int out_dim) {
     BankSmem L;
     int o = 0;
-    L.oTile = o; o += 2 * BANK_TILE_FLOATS;
+    L.oTile = o; o += BANK_TILE_FLOATS;
     L.oY = o; o += TILE_F * ypitch;
+    L.oO = o; o += (TILE_F * out_dim + 3) & ~3;            // output staging (the tile itself is being refilled by then)
     L.oW = o; o += 4 * wtot4;
     L.oM = o; o += (nrows * nbp + 3) & ~3;
     L.oBands = o; o += 4 * nb;
     L.oFlags = o; o += TILE_F / 4 * 2;                     // 32 bytes + pad
-    L.oBar = o; o += 4;                                    // two 8-byte mbarriers
+    L.oBar = o; o += 2;                                    // one 8-byte mbarrier
     L.total = o;
     return L;
 }
@@ -132,21 +137,35 @@ template <int MODE, int AKIND>
 __device__ __forceinline__ void bank_scan_tile(const NrParams &N, ScanState &S, ScanState &S2, float *tile, const uint8_t *fl, int nf, int t0) {
     const int tid = threadIdx.x;
     float *x = tile + tid;
-#pragma unroll 4
-    for (int f = 0; f < nf; f++) {
-        const uint8_t g = (MODE != NR_EXTEN) ? fl[f] : 0;
-        x[f * SPITCH] = nr_step<MODE, AKIND>(N, S, x[f * SPITCH], t0 + f, g);
-        // bin 256 rides along on thread 0: a second, independent chain in the same loop
-        if (tid == 0) x[f * SPITCH + 256] = nr_step<MODE, AKIND>(N, S2, x[f * SPITCH + 256], t0 + f, g);
+    // the bin's 32 values come into registers first (independent loads, all in flight at once); in place, every step would
+    // wait for its own shared-memory load behind the previous step's store
+    float v[TILE_F];
+#pragma unroll
+    for (int f = 0; f < TILE_F; f++) v[f] = x[f * SPITCH];
+    // bin 256 is thread 0's second bin: its chain runs in the same unrolled loop, in place in shared memory, so that its
+    // loads and arithmetic fill the gaps of the first chain instead of doubling warp 0's time
+    const bool two = (tid == 0);
+#pragma unroll
+    for (int f = 0; f < TILE_F; f++) {
+        if (f < nf) {
+            const uint8_t g = (MODE != NR_EXTEN) ? fl[f] : 0;
+            float b = 0.f;
+            if (two) b = x[f * SPITCH + 256];
+            v[f] = nr_step<MODE, AKIND>(N, S, v[f], t0 + f, g);
+            if (two) x[f * SPITCH + 256] = nr_step<MODE, AKIND>(N, S2, b, t0 + f, g);
+        }
     }
+#pragma unroll
+    for (int f = 0; f < TILE_F; f++) x[f * SPITCH] = v[f];
 }
 
 template <int KIND, int DST, bool NR>
-__global__ void __launch_bounds__(BANK_THREADS, 2)
+__global__ void __launch_bounds__(BANK_THREADS, 4)
 k_bank(const __grid_constant__ BankParams B, BatchDesc bd, int ntiles, int u0, int n_utts, const float *__restrict__ spec, float *__restrict__ dst) {
     extern __shared__ __align__(16) float sm[];
-    const BankSmem L = bank_smem(B.nb, B.nbp, B.ypitch, B.wtot4, B.nrows);
+    const BankSmem L = bank_smem(B.nb, B.nbp, B.ypitch, B.wtot4, B.nrows, B.out_dim);
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    float *tile = sm + L.oTile, *sO = sm + L.oO;
     float *sY = sm + L.oY;
     float4 *sW4 = reinterpret_cast<float4 *>(sm + L.oW);
     float *sM = sm + L.oM;
@@ -157,7 +176,7 @@ k_bank(const __grid_constant__ BankParams B, BatchDesc bd, int ntiles, int u0, i
     BankWalk cur = bank_first<NR>(bd, ntiles, u0, n_utts);
     if (!cur.valid) return;
     if (tid == 0) {
-        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < B.wtot4; i += BANK_THREADS) sW4[i] = B.w4[i];
@@ -166,32 +185,22 @@ k_bank(const __grid_constant__ BankParams B, BatchDesc bd, int ntiles, int u0, i
     // pad columns of the band tile (read by the 4-wide second-stage loop) stay zero for the whole kernel
     for (int i = tid; i < TILE_F * B.ypitch; i += BANK_THREADS) sY[i] = 0.f;
     __syncthreads();
-    // tile i lives in buffer i & 1; its mbarrier completes phase (i >> 1) & 1
+    // the i-th tile of this CTA completes phase i & 1 of the mbarrier
     if (tid == 0) {
         const int nf = min(TILE_F, cur.T - cur.t0);
         const unsigned bytes = (unsigned)nf * SPITCH * sizeof(float);
-        mbar_expect_tx(&bar[0], bytes);
-        bulk_g2s(sm + L.oTile, spec + (cur.row0 + cur.t0) * SPITCH, bytes, &bar[0]);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(tile, spec + (cur.row0 + cur.t0) * SPITCH, bytes, bar);
     }
     ScanState S, S2;
     S.Navg = S2.Navg = 0.f; S.Yavg = S2.Yavg = 0.f; S.Nravg = S2.Nravg = 0.f; S.Nd = S2.Nd = 0.0; S.Yd = S2.Yd = 0.0;
 #pragma unroll 1
     for (int it = 0; cur.valid; it++) {
-        const int buf = it & 1;
-        float *tile = sm + L.oTile + buf * BANK_TILE_FLOATS;
         const BankWalk nxt = bank_next<NR>(cur, bd, ntiles, u0, n_utts);
         const int nf = min(TILE_F, cur.T - cur.t0);
         const int64_t row0 = cur.row0 + cur.t0;
-        // the other buffer was released by the barrier that ended the previous iteration: fetch the next tile into it
-        if (tid == 0 && nxt.valid) {
-            const int nfn = min(TILE_F, nxt.T - nxt.t0);
-            const unsigned bytes = (unsigned)nfn * SPITCH * sizeof(float);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes to that buffer (scan, staging) before the async-proxy write
-            mbar_expect_tx(&bar[buf ^ 1], bytes);
-            bulk_g2s(sm + L.oTile + (buf ^ 1) * BANK_TILE_FLOATS, spec + (nxt.row0 + nxt.t0) * SPITCH, bytes, &bar[buf ^ 1]);
-        }
         if (NR && B.nr.mode != NR_EXTEN && tid < TILE_F) sFlags[tid] = (tid < nf) ? B.flags[row0 + tid] : 0;
-        mbar_wait(&bar[buf], (unsigned)(it >> 1) & 1u);
+        mbar_wait(bar, (unsigned)it & 1u);
         if (NR) {
             if (cur.t0 == 0) {
                 // exten: smoothed noise / speech start at 0.95 / 0.05 (src/nr/nr.cc:86-93); *ss: the noise estimate of a
@@ -246,7 +255,14 @@ k_bank(const __grid_constant__ BankParams B, BatchDesc bd, int ntiles, int u0, i
             }
         }
         __syncthreads();                                                       // band tile complete; the spectrum tile is dead
-        float *sO = tile;                                                      // output staging re-uses the spectrum tile
+        // ... so the next tile can come in while the second stage runs and the result is stored
+        if (tid == 0 && nxt.valid) {
+            const int nfn = min(TILE_F, nxt.T - nxt.t0);
+            const unsigned bytes = (unsigned)nfn * SPITCH * sizeof(float);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy accesses to the tile (scan) before the async-proxy write
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(tile, spec + (nxt.row0 + nxt.t0) * SPITCH, bytes, bar);
+        }
         const int od = B.out_dim;
         if (DST == DST_FB) {
             float *g = dst + row0 * B.nb;
@@ -291,7 +307,7 @@ k_bank(const __grid_constant__ BankParams B, BatchDesc bd, int ntiles, int u0, i
                 }
             }
         }
-        __syncthreads();                                                       // both tiles are free again
+        __syncthreads();                                                       // the band tile and the staging area are free again
         cur = nxt;
     }
 }
@@ -319,7 +335,7 @@ static inline void bank_pack(const FrameParams &P, std::vector<int4> &bands, std
 template <int KIND, int DST>
 static inline int launch_bank_t(const BankParams &B, bool nr, const BatchDesc &bd, int64_t ntiles, int u0, int n_utts, int num_sms, const float *spec,
                                 float *dst, cudaStream_t s, LaunchCtx *lc, std::string &err) {
-    const BankSmem L = bank_smem(B.nb, B.nbp, B.ypitch, B.wtot4, B.nrows);
+    const BankSmem L = bank_smem(B.nb, B.nbp, B.ypitch, B.wtot4, B.nrows, B.out_dim);
     const size_t bytes = (size_t)L.total * sizeof(float);
     const int64_t units = nr ? n_utts : ntiles;
     if (units <= 0) return CTU_OK;

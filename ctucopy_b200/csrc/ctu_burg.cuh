@@ -11,27 +11,39 @@ namespace ctu {
 
 // ------------------------------------------------------------------------------------------
 // K4: Burg cepstrum per frame (fp64 throughout so that detector decisions are reproducible)
-// 128 threads = 8 frames per pass, 4 passes per 32-frame tile.
-//   * the tile's PCM is staged once into shared memory as int16 (16-byte loads);
-//   * forward FFT -> per-bin gain (|X|^a or the post-NR magnitude, over |X|) -> inverse FFT;
-//     the time signal reuses the exchange tile's memory;
-//   * lattice: sample i = c*CH + j lives in thread c's registers.  All updates are
-//     unconditional; the elements the reference no longer reads (i < ik) are driven to exact
-//     zeros instead of being masked: thread 0 keeps ef[0] = 0 and takes `below` = 0, which
-//     makes eb[ik-1] come out 0 by itself, and ef[ik] is cleared after stage ik (a select
-//     chain over the first 16 registers, so every register index stays static);
+// 128 threads = 8 frames per pass; a CTA takes HALF of a 32-frame tile (two passes), so that its staged samples, the
+// tables and the eight exchange areas fit four CTAs per SM.
+//   * the half tile's PCM is staged once into shared memory as int16 (16-byte loads);
+//   * forward FFT -> per-bin gain (|X|^a or the post-NR magnitude, over |X|) -> inverse FFT.  Real split, gain and the
+//     inverse pre-split run IN PLACE on the 16 complex registers of a thread, pair by pair (bins k and 256-k): the
+//     partner's value arrives by shuffle, the rebuilt pair is written back over the registers it came from.  (Round 1
+//     materialised lo[8] / hi[8] / zn[8] next to a[16]: 236 registers, two CTAs per SM, FP64 pipe 41 % busy.)
+//   * lattice: sample i = c*CH + j lives in thread c's registers and every update is unconditional.  The reference's
+//     sums run over i >= ik (src/vdet/Burg.h:64-68): elements below ik can only belong to thread 0 (ik <= 15 < CH), so the
+//     accumulation of thread 0's first 16 samples is predicated on j >= ik.  Values of dropped elements never reach a
+//     live one (element i reads eb[i-1] of the previous stage, which was live then), so they need no clearing.
 //   * the predictor coefficients are distributed (thread i holds a_i; one shuffle per stage).
-// CH: samples per thread; EXACT: window == 16*CH (no tail masking in the energy sums).
+// CH: samples per thread; EXACT: window == 16*CH (no tail masking in the energy sums); GENA: the spectral exponent is not 1
+// or 2 (-nr_a): only that instantiation carries pow() -- inlined at the 17 bin sites of a thread it costs the common paths
+// registers and instruction-cache space for nothing.
 // ------------------------------------------------------------------------------------------
 constexpr int BURG_THREADS = 128;
 constexpr int BURG_GROUPS = BURG_THREADS / GROUP;
+constexpr int BURG_HALF = TILE_F / 2;                     // frames per CTA
 
-__device__ __forceinline__ double shfl16d(double v, int src) {
-    const unsigned m = 0xffffu << (threadIdx.x & 16);
-    return __shfl_sync(m, v, src, 16);
+// Shuffles inside a 16-lane group with the FULL member mask: both groups of a warp always execute them together (a group
+// without a frame of its own recomputes the tile's last frame and skips the stores).  With the per-group masks of round 1
+// every shuffle was wrapped in BSSY / WARPSYNC / ENDCOLLECTIVE / BSYNC: a fifth of the kernel's instructions.
+__device__ __forceinline__ double shfl16d(double v, int src) { return __shfl_sync(0xffffffffu, v, src, 16); }
+__device__ __forceinline__ double group_sum16d_all(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
 }
 
-template <int CH, bool EXACT, int MINB>
+template <int CH, bool EXACT, int MINB, bool GENA>
 __global__ void __launch_bounds__(BURG_THREADS, MINB)
 k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const int16_t *__restrict__ pcm, const float *__restrict__ spec,
        double *__restrict__ ceps, const double2 *__restrict__ g_tw256, const double2 *__restrict__ g_twsplit,
@@ -39,16 +51,18 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const i
     extern __shared__ __align__(16) double smd[];
     const int tid = threadIdx.x;
     const int w = EXACT ? 16 * CH : B.window, s = B.wshift;
+    const int wp = (w + 1) & ~1;
     cpx<double> *sTw = reinterpret_cast<cpx<double> *>(smd);            // 256
     cpx<double> *sTs = sTw + 256;                                      // 129 (+1 pad)
     cpx<double> *sTi = sTs + 130;                                      // 129 (+1 pad)
     cpx<double> *sX = sTi + 130;                                       // BURG_GROUPS * 16*17 (also the time signal)
-    double *sWin = reinterpret_cast<double *>(sX + BURG_GROUPS * XPAD * 16);   // 512: analysis window
-    double *sHann = sWin + NFFT;                                       // 512: detector's Hann (NR source)
-    int16_t *sPcm = reinterpret_cast<int16_t *>(sHann + NFFT);         // 8 + (TILE_F-1)*s + w + 1 + 8
-    const int2 tile = bd.tiles[blockIdx.x];
-    const int u = tile.x, t0 = tile.y;
-    const int nf = min(TILE_F, bd.nframes[u] - t0);
+    double *sWin = reinterpret_cast<double *>(sX + BURG_GROUPS * XPAD * 16);   // w: analysis window
+    double *sHann = sWin + wp;                                         // w: detector's Hann (NR source)
+    int16_t *sPcm = reinterpret_cast<int16_t *>(sHann + wp);           // 8 + (BURG_HALF-1)*s + w + 1 + 8
+    const int2 tile = bd.tiles[blockIdx.x >> 1];
+    const int u = tile.x, t0 = tile.y + (blockIdx.x & 1) * BURG_HALF;
+    const int nf = min(BURG_HALF, bd.nframes[u] - t0);
+    if (nf <= 0) return;
     const int64_t row0 = bd.row_off[u] + t0;
     // samples [first-1, first + nsamp): the one before the tile feeds the first pre-emphasis
     const int nsamp = (nf - 1) * s + w + 1;
@@ -69,24 +83,25 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const i
     }
     for (int i = tid; i < 256; i += BURG_THREADS) sTw[i] = mk<double>(g_tw256[i].x, g_tw256[i].y);
     for (int i = tid; i < 129; i += BURG_THREADS) { sTs[i] = mk<double>(g_twsplit[i].x, g_twsplit[i].y); sTi[i] = mk<double>(g_twinv[i].x, g_twinv[i].y); }
-    for (int i = tid; i < NFFT; i += BURG_THREADS) {
+    for (int i = tid; i < wp; i += BURG_THREADS) {
         sWin[i] = (i < w) ? g_win[i] : 0.0;
         sHann[i] = (i < w) ? ((src_mode == BURG_SRC_NR) ? g_hann[i] : 1.0) : 0.0;
     }
     __syncthreads();
     const int c = tid & (GROUP - 1), grp = tid / GROUP;
+    const int partner = (16 - c) & 15;
     cpx<double> *xch = sX + grp * (XPAD * 16);
     double *xt = reinterpret_cast<double *>(xch);
     const int ncoef = (src_mode == BURG_SRC_NR) ? B.ncoef_nr : B.ncoef_vad;
     const double inv_w = 1.0 / (double)w;
 #pragma unroll 1
-    for (int pass = 0; pass < TILE_F / BURG_GROUPS; pass++) {
-        const int f = pass * BURG_GROUPS + grp;
-        const bool active = f < nf;
+    for (int pass = 0; pass < BURG_HALF / BURG_GROUPS; pass++) {
+        // a group whose frame number is past the end of the tile recomputes the tile's last frame and stores nothing
+        const bool active = pass * BURG_GROUPS + grp < nf;
+        const int f = min(pass * BURG_GROUPS + grp, nf - 1);
         {
             cpx<double> a[16];
-            cpx<double> lo[8], hi[8], mid;
-            if (active) {
+            {
                 const int16_t *x = dpcm + f * s + 1;                  // x[-1] is the sample before the frame
                 double sum = 0;
 #pragma unroll
@@ -96,13 +111,13 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const i
                     if (i0 < w) {                                     // w is even for every supported window
                         const double xm = (double)x[i0 - 1], x0 = (double)x[i0], x1 = (double)x[i0 + 1];
                         y0 = sWin[i0] * (x0 - B.preem * xm);
-                        y1 = sWin[i0 + 1] * (x1 - B.preem * x0);      // sWin is 0 beyond the window
+                        y1 = sWin[i0 + 1] * (x1 - B.preem * x0);
                     }
                     a[n1] = mk<double>(y0, y1);
                     sum += y0 + y1;
                 }
                 if (B.remove_dc) {
-                    const double mean = group_sum16d(sum) * inv_w;
+                    const double mean = group_sum16d_all(sum) * inv_w;
 #pragma unroll
                     for (int n1 = 0; n1 < 16; n1++) {
                         const int i0 = 32 * n1 + 2 * c;
@@ -113,9 +128,8 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const i
                 fft256_pass1(a, c, sTw, xch);
             }
             __syncwarp();
-            if (active) {
+            {
                 fft256_pass2(a, c, xch);
-                rfft_split_shfl(a, c, sTs, lo, hi, mid);
                 // (|X|^a or the post-NR spectrum) with the phase of X: every bin is scaled by
                 // E/|X| -- what Xa*cos(phi), Xa*sin(phi) amount to (src/nr/nr.cc:281-292,
                 // src/vad/vad.cc:222-233) -- with the reference's conventions for bin 0
@@ -134,28 +148,67 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const i
                         // E = Xa^a with Xa = |X|^2 (fb_power) or |X|;  g = E/|X| without the division
                         // where the exponents are small integers
                         const int ak = expand ? B.a_kind : 1;
-                        if (ak == 0) { E = pow(B.fb_power ? m2 : m, B.a); g = E * rm; }
+                        if (GENA && ak == 0) { E = pow(B.fb_power ? m2 : m, B.a); g = E * rm; }
                         else if (B.fb_power) { E = (ak == 2) ? m2 * m2 : m2; g = (ak == 2) ? m2 * m : m; }
                         else { E = (ak == 2) ? m2 : m; g = (ak == 2) ? m : 1.0; }
                     }
                     if (m2 == 0.0) return edge ? mk<double>(E, 0.0) : mk<double>(0.0, -E);
                     return mk<double>(X.x * g, edge ? 0.0 : X.y * g);
                 };
+                // real split (rfft_split_pairs), gain, inverse pre-split (irfft_presplit_local / _place), one bin pair at a
+                // time and in place: thread c needs Z[256-k] = a[15-j] of thread 16-c (thread 0: its own a[16-j]) and hands
+                // conj(Zc[256-k]) back to the same thread, which stores it where the value it lent came from
+                const cpx<double> x128 = conj(a[8]);                       // X[128], meaningful for c == 0
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const int k = c + 16 * j;
-                    lo[j] = scale_bin(lo[j], k);
-                    hi[j] = scale_bin(hi[j], NC - k);
+                    const cpx<double> prov = (c == 0) ? a[(16 - j) & 15] : a[15 - j];
+                    cpx<double> Z;
+                    Z.x = __shfl_sync(0xffffffffu, prov.x, partner, 16);
+                    Z.y = __shfl_sync(0xffffffffu, prov.y, partner, 16);
+                    const cpx<double> A = a[j];
+                    cpx<double> lo, hi;
+                    if (j == 0 && c == 0) {
+                        lo = mk<double>(A.x + A.y, 0.0);
+                        hi = mk<double>(A.x - A.y, 0.0);
+                    } else {
+                        const cpx<double> Bc = conj(Z);
+                        const cpx<double> E = mk<double>(0.5 * (A.x + Bc.x), 0.5 * (A.y + Bc.y));
+                        const cpx<double> Tt = cmul(sTs[k], A - Bc);
+                        lo = E + Tt;
+                        hi = conj(E - Tt);
+                    }
+                    lo = scale_bin(lo, k);
+                    hi = scale_bin(hi, NC - k);
+                    cpx<double> zn;
+                    if (j == 0 && c == 0) {
+                        a[0] = conj(mk<double>(lo.x + hi.x, lo.x - hi.x));
+                        zn = mk<double>(0.0, 0.0);
+                    } else {
+                        const cpx<double> S = lo + conj(hi);
+                        const cpx<double> U = cmul(lo - conj(hi), sTi[k]);
+                        a[j] = conj(mk<double>(S.x - U.y, S.y + U.x));           // conj(Zc[k])
+                        zn = conj(mk<double>(S.x + U.y, -S.y + U.x));           // conj(Zc[256-k])
+                    }
+                    cpx<double> back;
+                    back.x = __shfl_sync(0xffffffffu, zn.x, partner, 16);
+                    back.y = __shfl_sync(0xffffffffu, zn.y, partner, 16);
+                    if (c == 0) { if (j >= 1) a[(16 - j) & 15] = back; }
+                    else a[15 - j] = back;
                 }
-                mid = scale_bin(mid, 128);
-                irfft_presplit_shfl(a, c, sTi, lo, hi, mid);
+                if (c == 0) {
+                    // Zc[128] pairs with itself: S = 2 Re(mid), U = 2i Im(mid) * twinv[128]
+                    const cpx<double> mid = scale_bin(x128, 128);
+                    const cpx<double> Um = cmul(mk<double>(0.0, 2.0 * mid.y), sTi[128]);
+                    a[8] = conj(mk<double>(2.0 * mid.x - Um.y, Um.x));
+                }
             }
             __syncwarp();                                             // pass-2 reads of the exchange tile are done
-            if (active) fft256_pass1(a, c, sTw, xch);
+            fft256_pass1(a, c, sTw, xch);
             __syncwarp();
-            if (active) fft256_pass2(a, c, xch);
+            fft256_pass2(a, c, xch);
             __syncwarp();                                             // xch is re-used for the time signal
-            if (active) {
+            {
 #pragma unroll
                 for (int k2 = 0; k2 < 16; k2++) {
                     const int n = c + 16 * k2;
@@ -165,64 +218,58 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const i
             }
             __syncwarp();
         }
-        if (active) {
+        {
             // ---- Burg lattice (src/vdet/Burg.h:49-95) on the first w samples ------------------
             double ef[CH], eb[CH];
             double en = 0;
 #pragma unroll
             for (int j = 0; j < CH; j++) {
                 const int i = c * CH + j;
-                double v = (EXACT || i < w) ? xt[i < NFFT ? i : 0] * sHann[i < NFFT ? i : 0] : 0.0;
+                double v = (EXACT || i < w) ? xt[i < NFFT ? i : 0] * sHann[i < w ? i : 0] : 0.0;
                 if (!EXACT && i >= w) v = 0.0;
                 ef[j] = eb[j] = v;
                 en += v * v;
             }
-            double alpha = group_sum16d(en) * inv_w;
-            if (c == 0) ef[0] = 0.0;                                  // never read by the reference
+            double alpha = group_sum16d_all(en) * inv_w;
             double a_c = (c == 0) ? 1.0 : 0.0, aa_c = a_c;            // thread i holds a_i
-            // the stage loop stays rolled: unrolled 15 times the kernel was 14 k instructions and stalled on instruction
-            // fetch (30.4 -> 27.5 ms on 4 M frames)
+            // the stage loop stays rolled: unrolled 15 times the kernel was 14 k instructions and stalled on instruction fetch
 #pragma unroll 1
             for (int ik = 1; ik < ncoef; ik++) {
-                {
-                    double below = shfl16d(eb[CH - 1], (c + 15) & 15);
-                    if (c == 0) below = 0.0;
-                    // three independent chains per parity: the sums are latency-bound otherwise
-                    double nu[2] = {0, 0}, df[2] = {0, 0}, db[2] = {0, 0};
+                const double below = shfl16d(eb[CH - 1], (c + 15) & 15);   // eb of sample i-1 across the thread boundary
+                const int dead = (c == 0) ? ik : 0;                        // thread 0: its samples j < ik have left the sums
+                // three independent chains per parity: the sums are latency-bound otherwise
+                double nu[2] = {0, 0}, df[2] = {0, 0}, db[2] = {0, 0};
 #pragma unroll
-                    for (int j = 0; j < CH; j++) {
-                        const double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
-                        if (EXACT || c * CH + j < w) {
-                            df[j & 1] = fma(ef[j], ef[j], df[j & 1]);
-                            db[j & 1] = fma(pv, pv, db[j & 1]);
-                            nu[j & 1] = fma(ef[j], pv, nu[j & 1]);
-                        }
+                for (int j = 0; j < CH; j++) {
+                    const double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
+                    if ((EXACT || c * CH + j < w) && (j >= BURG_MAXC || j >= dead)) {
+                        df[j & 1] = fma(ef[j], ef[j], df[j & 1]);
+                        db[j & 1] = fma(pv, pv, db[j & 1]);
+                        nu[j & 1] = fma(ef[j], pv, nu[j & 1]);
                     }
-                    const double num = group_sum16d(nu[0] + nu[1]) * 2.0;
-                    const double den = group_sum16d((df[0] + df[1]) + (db[0] + db[1]));
-                    const double rc = -num / den;
-                    alpha *= 1 - rc * rc;
-#pragma unroll
-                    for (int j = CH - 1; j >= 0; j--) {
-                        const double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
-                        const double e0 = ef[j];
-                        ef[j] = e0 + rc * pv;
-                        eb[j] = pv + rc * e0;
-                    }
-#pragma unroll
-                    for (int j = 1; j < BURG_MAXC && j < CH; j++) if (c == 0 && j == ik) ef[j] = 0.0;
-                    // a_i = aa_i + rc * aa_{ik-i} (0 < i < ik), a_ik = rc
-                    const double other = shfl16d(aa_c, (ik - c) & 15);
-                    if (c == ik) a_c = rc;
-                    else if (c >= 1 && c < ik) a_c = aa_c + rc * other;
-                    aa_c = a_c;
                 }
+                const double num = group_sum16d_all(nu[0] + nu[1]) * 2.0;
+                const double den = group_sum16d_all((df[0] + df[1]) + (db[0] + db[1]));
+                const double rc = -num / den;
+                alpha *= 1 - rc * rc;
+#pragma unroll
+                for (int j = CH - 1; j >= 0; j--) {
+                    const double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
+                    const double e0 = ef[j];
+                    ef[j] = e0 + rc * pv;
+                    eb[j] = pv + rc * e0;
+                }
+                // a_i = aa_i + rc * aa_{ik-i} (0 < i < ik), a_ik = rc
+                const double other = shfl16d(aa_c, (ik - c) & 15);
+                if (c == ik) a_c = rc;
+                else if (c >= 1 && c < ik) a_c = aa_c + rc * other;
+                aa_c = a_c;
             }
             // LPC -> cepstrum (src/vdet/Burg.h:141-152), thread 0 of the group
             double av[BURG_MAXC];
 #pragma unroll
             for (int k = 0; k < BURG_MAXC; k++) av[k] = shfl16d(a_c, k);
-            if (c == 0) {
+            if (c == 0 && active) {
                 double cc[BURG_MAXC];
                 double *o = ceps + (row0 + f) * BURG_MAXC;
 #pragma unroll
@@ -348,7 +395,7 @@ k_burg_any(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, Any
 }
 
 static inline size_t burg_smem_bytes(int w, int s) {
-    return sizeof(double) * (2 * (256 + 130 + 130 + BURG_GROUPS * XPAD * 16) + 2 * NFFT) + sizeof(int16_t) * (size_t)(8 + (TILE_F - 1) * s + w + 1 + 8 + 8);
+    return sizeof(double) * (2 * (256 + 130 + 130 + BURG_GROUPS * XPAD * 16) + 2 * ((w + 1) & ~1)) + sizeof(int16_t) * (size_t)(8 + (BURG_HALF - 1) * s + w + 1 + 8 + 8);
 }
 
 int launch_burg(const BurgParams &B, int src_mode, const BatchDesc &bd, int64_t ntiles, const int16_t *pcm, const float *spec,
@@ -372,14 +419,19 @@ int launch_burg(const BurgParams &B, int src_mode, const BatchDesc &bd, int64_t 
     if (bytes > 227 * 1024) { err = "CTU: window shift too large for the Burg detector kernel"; return CTU_ERR_UNSUPPORTED; }
     cudaError_t e;
     lc->begin("k_burg", s);
+#define CTU_BURG_LAUNCH2(CH, EX, MB, GA)                                                                               \
+    e = cudaFuncSetAttribute(k_burg<CH, EX, MB, GA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);           \
+    if (e == cudaSuccess) k_burg<CH, EX, MB, GA><<<(unsigned)(2 * ntiles), BURG_THREADS, bytes, s>>>(B, src_mode, bd, pcm, spec, ceps, tw, ts, ti, win, hann)
 #define CTU_BURG_LAUNCH(CH, EX, MB)                                                                                    \
-    e = cudaFuncSetAttribute(k_burg<CH, EX, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);             \
-    if (e == cudaSuccess) k_burg<CH, EX, MB><<<(unsigned)ntiles, BURG_THREADS, bytes, s>>>(B, src_mode, bd, pcm, spec, ceps, tw, ts, ti, win, hann)
-    // two CTAs per SM: capping registers for a third one spills the lattice state and gains nothing (measured)
-    if (B.window == 400) { CTU_BURG_LAUNCH(25, true, 2); }
+    if (gena) { CTU_BURG_LAUNCH2(CH, EX, 2, true); } else { CTU_BURG_LAUNCH2(CH, EX, MB, false); }
+    // the general exponent only matters where the detector's input is expanded (NR source, hwss / fwss)
+    const bool gena = (src_mode == BURG_SRC_NR && B.expand && B.a_kind == 0);
+    // 25 samples per thread: 128 registers = four CTAs per SM; 32 samples per thread (window up to 512): three
+    if (B.window == 400) { CTU_BURG_LAUNCH(25, true, 4); }
     else if (B.window == 512) { CTU_BURG_LAUNCH(32, true, 2); }
-    else if (B.window <= 400) { CTU_BURG_LAUNCH(25, false, 2); }
+    else if (B.window <= 400) { CTU_BURG_LAUNCH(25, false, 3); }
     else { CTU_BURG_LAUNCH(32, false, 2); }
+#undef CTU_BURG_LAUNCH2
 #undef CTU_BURG_LAUNCH
     lc->end(s);
     if (e == cudaSuccess) e = cudaGetLastError();

@@ -66,7 +66,6 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, con
     for (int i = tid; i < 129; i += F2_THREADS) sTs[i] = mk<float>(tb.twsplit[i].x, tb.twsplit[i].y);
 
     const int c = tid & (GROUP - 1), grp = tid / GROUP;
-    const unsigned hm = 0xffffu << (tid & 16);                // the two groups of a warp run independently
     cpx<float> *xch = reinterpret_cast<cpx<float> *>(sm + L.oX + grp * F2_ROWF);
     const float inv_w = 1.0f / (float)w;
     // a thread windows the same 2 x 16 sample positions of every frame it ever sees: its window values live in
@@ -95,8 +94,13 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, con
     finish_pcm<F2_THREADS>(raw, sD, pcm, cur, (nf - 1) * s + w + 1, edge, P.preem);
     __syncthreads();                                          // samples staged; the raw buffer is free again
     if (next < ntiles) prefetch_pcm<F2_THREADS>(raw, pcm, nxt, (nxt.nf - 1) * s + w + 1, edge);
+    // the two groups of a warp walk the tile in step (frames grp, grp + 8): with an odd number of frames the last group
+    // recomputes the tile's last frame and stores nothing -- every shuffle can then name the full warp (bare SHFL)
+    const int nf_even = (nf + 1) & ~1;
 #pragma unroll 1
-    for (int f = grp; f < nf; f += F2_GROUPS) {
+    for (int f0 = grp; f0 < nf_even; f0 += F2_GROUPS) {
+        const bool store = f0 < nf;
+        const int f = min(f0, nf - 1);
         cpx<float> a[16];
         // sample pairs as 8-byte loads: a half warp covers 128 contiguous bytes, so the two frames of a warp (whose rows
         // start on the same bank when the shift is a multiple of 32 samples) no longer collide (ncu: 16 of the 105
@@ -120,7 +124,7 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, con
         }
         if (P.remove_dc) {
             // mean of the WINDOWED frame, subtracted from the window's samples only (src/io/in.cc:375-382)
-            const float mean = group_sum16(sum) * inv_w;
+            const float mean = group_sum16_all(sum) * inv_w;
 #pragma unroll
             for (int n1 = 0; n1 < 16; n1++) {
                 const int i0 = 32 * n1 + 2 * c;
@@ -129,11 +133,12 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, con
             }
         }
         fft256_pass1_reg(a, c, twr, xch);
-        __syncwarp(hm);
+        __syncwarp();
         fft256_pass2(a, c, xch);
         cpx<float> lo[8], hi[8], mid;
         rfft_split_shfl_rec(a, c, ts_c, lo, hi, mid);
-        __syncwarp(hm);                                       // all reads of the exchange tile are done
+        __syncwarp();                                         // all reads of the exchange tile are done
+        if (!store) continue;
         float *g = dst + (row0 + f) * SPITCH;
         if (CPLX) {
             float2 *gc = cdst + (row0 + f) * NBIN;

@@ -120,6 +120,17 @@ __device__ __forceinline__ float group_sum16(float v) {
     return v;
 }
 
+// The same with the FULL member mask, for code in which both groups of a warp always arrive together.  A shuffle whose
+// mask is not a compile-time constant is wrapped in BSSY / WARPSYNC / ENDCOLLECTIVE / BSYNC by the compiler (four extra
+// instructions and a convergence barrier each); with 0xffffffff it is the bare SHFL.
+__device__ __forceinline__ float group_sum16_all(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
 // real-input split / inverse pre-split with the partner values fetched by register shuffles between
 // thread c and thread (16-c)%16 of the group (arithmetic: ctu_fft.cuh, emulated in tests/emu)
 template <class T>
@@ -136,10 +147,11 @@ __device__ __forceinline__ void rfft_split_shfl(const cpx<T> (&a)[16], int c, co
     rfft_split_pairs(a, Zp, c, twsplit, lo, hi, mid);
 }
 
-// the same with the split twiddles formed from the thread-constant twsplit[c] (rfft_split_pairs_rec)
+// the same with the split twiddles formed from the thread-constant twsplit[c] (rfft_split_pairs_rec); full member mask:
+// both groups of the warp call it together
 template <class T>
 __device__ __forceinline__ void rfft_split_shfl_rec(const cpx<T> (&a)[16], int c, cpx<T> ts_c, cpx<T> (&lo)[8], cpx<T> (&hi)[8], cpx<T> &mid) {
-    const unsigned m = 0xffffu << (threadIdx.x & 16);
+    const unsigned m = 0xffffffffu;
     const int src = (16 - c) & 15;
     cpx<T> Zp[8];
 #pragma unroll
