@@ -133,30 +133,39 @@ __device__ __forceinline__ BankWalk bank_next(const BankWalk &c, const BatchDesc
 }
 
 // one tile of the recursion for one bin: 32 frames in shared memory, in place
+constexpr int BANK_SCAN_CHUNK = 8;
 template <int MODE, int AKIND>
 __device__ __forceinline__ void bank_scan_tile(const NrParams &N, ScanState &S, ScanState &S2, float *tile, const uint8_t *fl, int nf, int t0) {
     const int tid = threadIdx.x;
     float *x = tile + tid;
-    // the bin's 32 values come into registers first (independent loads, all in flight at once); in place, every step would
-    // wait for its own shared-memory load behind the previous step's store
-    float v[TILE_F];
-#pragma unroll
-    for (int f = 0; f < TILE_F; f++) v[f] = x[f * SPITCH];
-    // bin 256 is thread 0's second bin: its chain runs in the same unrolled loop, in place in shared memory, so that its
-    // loads and arithmetic fill the gaps of the first chain instead of doubling warp 0's time
+    // bin 256 is thread 0's second bin: its chain runs in the same loop, so that its loads and arithmetic fill the gaps of
+    // the first chain instead of doubling warp 0's time
     const bool two = (tid == 0);
+    // eight frames at a time: the bin's values come into registers first (independent loads, all in flight at once) -- in
+    // place, every step would wait for its own shared-memory load behind the previous step's store -- and the loop over
+    // the chunks stays rolled (unrolled over all 32 frames, seven mode variants made the kernel 240 KB of code)
+#pragma unroll 1
+    for (int f0 = 0; f0 < nf; f0 += BANK_SCAN_CHUNK) {
+        float v[BANK_SCAN_CHUNK], b[BANK_SCAN_CHUNK];
 #pragma unroll
-    for (int f = 0; f < TILE_F; f++) {
-        if (f < nf) {
-            const uint8_t g = (MODE != NR_EXTEN) ? fl[f] : 0;
-            float b = 0.f;
-            if (two) b = x[f * SPITCH + 256];
-            v[f] = nr_step<MODE, AKIND>(N, S, v[f], t0 + f, g);
-            if (two) x[f * SPITCH + 256] = nr_step<MODE, AKIND>(N, S2, b, t0 + f, g);
+        for (int j = 0; j < BANK_SCAN_CHUNK; j++) {
+            v[j] = x[(f0 + j) * SPITCH];
+            b[j] = two ? x[(f0 + j) * SPITCH + 256] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < BANK_SCAN_CHUNK; j++) {
+            if (f0 + j < nf) {
+                const uint8_t g = (MODE != NR_EXTEN) ? fl[f0 + j] : 0;
+                v[j] = nr_step<MODE, AKIND>(N, S, v[j], t0 + f0 + j, g);
+                if (two) b[j] = nr_step<MODE, AKIND>(N, S2, b[j], t0 + f0 + j, g);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < BANK_SCAN_CHUNK; j++) {
+            x[(f0 + j) * SPITCH] = v[j];
+            if (two) x[(f0 + j) * SPITCH + 256] = b[j];
         }
     }
-#pragma unroll
-    for (int f = 0; f < TILE_F; f++) x[f * SPITCH] = v[f];
 }
 
 template <int KIND, int DST, bool NR>

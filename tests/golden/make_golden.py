@@ -43,6 +43,8 @@ CASES = {
     "plpc_ark": (B + ["-preset", "plpc", "-format_out", "ark={ARK}"], "ark", {}),
     "plpc_htk_d": (B + ["-preset", "plpc", "-format_out", "htk", "-fea_delta", "d"], "htk", {}),
     "lpa_mel": (B + MF + ["-fea_kind", "lpa", "-format_out", "htk"], "htk", {}),
+    # lpa on the PLP bank (cube-root compressed bands): the well-conditioned Levinson-Durbin case
+    "plpc_lpa": (B + ["-preset", "plpc", "-fea_kind", "lpa", "-format_out", "htk"], "htk", {}),
     "lpc_mel_inld": (B + MF + ["-fea_kind", "lpc", "-fb_inld", "on", "-fb_eqld", "on", "-fea_ncepcoefs", "16", "-format_out", "htk"], "htk", {}),
     # config 5
     "trapdct_51_8": (B + ["-format_out", "htk", "-fb_definition", "23filters", "-fb_eqld", "off", "-fb_inld", "off", "-preem", "0.97",
@@ -70,6 +72,11 @@ CASES = {
     "fwss_burg_pfile": (B + MF + ["-nr_mode", "fwss", "-vad", "burg", "-nr_when", "beforeFB", "-format_out", "pfile={PFILE}"], "pfile", {}),
     "hwss_burg_a2": (B + MF + ["-nr_mode", "hwss", "-nr_a", "2", "-fb_power", "off", "-vad", "burg", "-format_out", "htk"], "htk", {}),
     "2fwss_burg": (B + MF + ["-nr_mode", "2fwss", "-vad", "burg", "-nr_initsegs", "5", "-format_out", "htk"], "htk", {}),
+    # hwss in the LINEAR domain (band values of the half-wave rectified spectrum, magnitude and power): a bin that the
+    # subtraction takes to 0 +- rounding contributes (almost) nothing here, whereas its logarithm is -inf or finite by the
+    # sign of a rounding error -- this is where hwss can be held to the same tolerance as every other mode
+    "hwss_burg_spec_mag": (B + MF + ["-nr_mode", "hwss", "-vad", "burg", "-fb_power", "off", "-fea_kind", "spec", "-format_out", "htk"], "htk", {}),
+    "hwss_burg_spec_pow": (B + MF + ["-nr_mode", "hwss", "-nr_b", "1.5", "-vad", "burg", "-fea_kind", "spec", "-format_out", "htk"], "htk", {}),
     "fwss_file_afterFB_pfile": (B + MF + ["-nr_mode", "fwss", "-vad", "file={VADIN}", "-nr_when", "afterFB", "-format_out", "pfile={PFILE}"],
                                 "pfile", {"ext_vad": True}),
     "fwss_burg_raw": (B + ["-w", "32", "-s", "16", "-nr_mode", "fwss", "-nr_b", "1.5", "-vad", "burg", "-format_out", "raw"], "raw", {}),
