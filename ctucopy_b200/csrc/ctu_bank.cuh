@@ -134,36 +134,47 @@ __device__ __forceinline__ BankWalk bank_next(const BankWalk &c, const BatchDesc
 
 // one tile of the recursion for one bin: 32 frames in shared memory, in place
 constexpr int BANK_SCAN_CHUNK = 8;
+// TWO: the warp also carries bin 256 (the 257th bin of 256 threads): all its lanes run that second chain redundantly on
+// the same values -- no divergence, and the two chains of a lane overlap in the pipeline -- and one lane stores it
+template <int MODE, int AKIND, bool FULL, bool TWO>
+__device__ __forceinline__ void bank_scan_chunk(const NrParams &N, ScanState &S, ScanState &S2, float *tile, const uint8_t *fl, int f0, int nf, int t0) {
+    float *x = tile + threadIdx.x;
+    // the bin's values come into registers first (independent loads, all in flight at once); in place, every step would
+    // wait for its own shared-memory load behind the previous step's store
+    float v[BANK_SCAN_CHUNK], b[BANK_SCAN_CHUNK];
+#pragma unroll
+    for (int j = 0; j < BANK_SCAN_CHUNK; j++) {
+        v[j] = x[(f0 + j) * SPITCH];
+        if (TWO) b[j] = tile[(f0 + j) * SPITCH + 256];
+    }
+#pragma unroll
+    for (int j = 0; j < BANK_SCAN_CHUNK; j++)
+        if (FULL || f0 + j < nf) {
+            const uint8_t g = (MODE != NR_EXTEN) ? fl[f0 + j] : 0;
+            v[j] = nr_step<MODE, AKIND>(N, S, v[j], t0 + f0 + j, g);
+            if (TWO) b[j] = nr_step<MODE, AKIND>(N, S2, b[j], t0 + f0 + j, g);
+        }
+#pragma unroll
+    for (int j = 0; j < BANK_SCAN_CHUNK; j++) {
+        x[(f0 + j) * SPITCH] = v[j];
+        if (TWO && (threadIdx.x & 31) == 31) tile[(f0 + j) * SPITCH + 256] = b[j];
+    }
+}
+
 template <int MODE, int AKIND>
 __device__ __forceinline__ void bank_scan_tile(const NrParams &N, ScanState &S, ScanState &S2, float *tile, const uint8_t *fl, int nf, int t0) {
-    const int tid = threadIdx.x;
-    float *x = tile + tid;
-    // bin 256 is thread 0's second bin: its chain runs in the same loop, so that its loads and arithmetic fill the gaps of
-    // the first chain instead of doubling warp 0's time
-    const bool two = (tid == 0);
-    // eight frames at a time: the bin's values come into registers first (independent loads, all in flight at once) -- in
-    // place, every step would wait for its own shared-memory load behind the previous step's store -- and the loop over
-    // the chunks stays rolled (unrolled over all 32 frames, seven mode variants made the kernel 240 KB of code)
+    const bool last_warp = (threadIdx.x >> 5) == BANK_THREADS / 32 - 1;            // warp-uniform
+    // eight frames at a time; the loop over the chunks stays rolled (unrolled over all 32 frames, seven mode variants made
+    // the kernel 240 KB of code).  Whole chunks take the branch-free body.
 #pragma unroll 1
     for (int f0 = 0; f0 < nf; f0 += BANK_SCAN_CHUNK) {
-        float v[BANK_SCAN_CHUNK], b[BANK_SCAN_CHUNK];
-#pragma unroll
-        for (int j = 0; j < BANK_SCAN_CHUNK; j++) {
-            v[j] = x[(f0 + j) * SPITCH];
-            b[j] = two ? x[(f0 + j) * SPITCH + 256] : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < BANK_SCAN_CHUNK; j++) {
-            if (f0 + j < nf) {
-                const uint8_t g = (MODE != NR_EXTEN) ? fl[f0 + j] : 0;
-                v[j] = nr_step<MODE, AKIND>(N, S, v[j], t0 + f0 + j, g);
-                if (two) b[j] = nr_step<MODE, AKIND>(N, S2, b[j], t0 + f0 + j, g);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < BANK_SCAN_CHUNK; j++) {
-            x[(f0 + j) * SPITCH] = v[j];
-            if (two) x[(f0 + j) * SPITCH + 256] = b[j];
+        const bool full = f0 + BANK_SCAN_CHUNK <= nf;
+        if (last_warp) {
+            if (full) bank_scan_chunk<MODE, AKIND, true, true>(N, S, S2, tile, fl, f0, nf, t0);
+            else bank_scan_chunk<MODE, AKIND, false, true>(N, S, S2, tile, fl, f0, nf, t0);
+        } else {
+            if (full) bank_scan_chunk<MODE, AKIND, true, false>(N, S, S2, tile, fl, f0, nf, t0);
+            else bank_scan_chunk<MODE, AKIND, false, false>(N, S, S2, tile, fl, f0, nf, t0);
         }
     }
 }

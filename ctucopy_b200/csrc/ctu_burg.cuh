@@ -18,10 +18,9 @@ namespace ctu {
 //     inverse pre-split run IN PLACE on the 16 complex registers of a thread, pair by pair (bins k and 256-k): the
 //     partner's value arrives by shuffle, the rebuilt pair is written back over the registers it came from.  (Round 1
 //     materialised lo[8] / hi[8] / zn[8] next to a[16]: 236 registers, two CTAs per SM, FP64 pipe 41 % busy.)
-//   * lattice: sample i = c*CH + j lives in thread c's registers and every update is unconditional.  The reference's
-//     sums run over i >= ik (src/vdet/Burg.h:64-68): elements below ik can only belong to thread 0 (ik <= 15 < CH), so the
-//     accumulation of thread 0's first 16 samples is predicated on j >= ik.  Values of dropped elements never reach a
-//     live one (element i reads eb[i-1] of the previous stage, which was live then), so they need no clearing.
+//   * lattice: sample i = c*CH + j lives in thread c's registers.  All updates and sums are unconditional; the elements the
+//     reference no longer reads (i < ik, src/vdet/Burg.h:64-68) are driven to exact zeros instead of being masked (see the
+//     stage loop).
 //   * the predictor coefficients are distributed (thread i holds a_i; one shuffle per stage).
 // CH: samples per thread; EXACT: window == 16*CH (no tail masking in the energy sums); GENA: the spectral exponent is not 1
 // or 2 (-nr_a): only that instantiation carries pow() -- inlined at the 17 bin sites of a thread it costs the common paths
@@ -45,7 +44,7 @@ __device__ __forceinline__ double group_sum16d_all(double v) {
 
 template <int CH, bool EXACT, int MINB, bool GENA>
 __global__ void __launch_bounds__(BURG_THREADS, MINB)
-k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const int16_t *__restrict__ pcm, const float *__restrict__ spec,
+k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, int nhalf, const int16_t *__restrict__ pcm, const float *__restrict__ spec,
        double *__restrict__ ceps, const double2 *__restrict__ g_tw256, const double2 *__restrict__ g_twsplit,
        const double2 *__restrict__ g_twinv, const double *__restrict__ g_win, const double *__restrict__ g_hann) {
     extern __shared__ __align__(16) double smd[];
@@ -59,11 +58,21 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const i
     double *sWin = reinterpret_cast<double *>(sX + BURG_GROUPS * XPAD * 16);   // w: analysis window
     double *sHann = sWin + wp;                                         // w: detector's Hann (NR source)
     int16_t *sPcm = reinterpret_cast<int16_t *>(sHann + wp);           // 8 + (BURG_HALF-1)*s + w + 1 + 8
-    const int2 tile = bd.tiles[blockIdx.x >> 1];
-    const int u = tile.x, t0 = tile.y + (blockIdx.x & 1) * BURG_HALF;
+    for (int i = tid; i < 256; i += BURG_THREADS) sTw[i] = mk<double>(g_tw256[i].x, g_tw256[i].y);
+    for (int i = tid; i < 129; i += BURG_THREADS) { sTs[i] = mk<double>(g_twsplit[i].x, g_twsplit[i].y); sTi[i] = mk<double>(g_twinv[i].x, g_twinv[i].y); }
+    for (int i = tid; i < wp; i += BURG_THREADS) {
+        sWin[i] = (i < w) ? g_win[i] : 0.0;
+        sHann[i] = (i < w) ? ((src_mode == BURG_SRC_NR) ? g_hann[i] : 1.0) : 0.0;
+    }
+    // persistent CTAs: the tables above are staged once, the half tiles are walked with stride gridDim.x
+#pragma unroll 1
+    for (int ht = blockIdx.x; ht < nhalf; ht += gridDim.x) {
+    const int2 tile = bd.tiles[ht >> 1];
+    const int u = tile.x, t0 = tile.y + (ht & 1) * BURG_HALF;
     const int nf = min(BURG_HALF, bd.nframes[u] - t0);
-    if (nf <= 0) return;
+    if (nf <= 0) continue;                                   // (uniform over the CTA)
     const int64_t row0 = bd.row_off[u] + t0;
+    __syncthreads();                                          // the previous half tile's samples are no longer read
     // samples [first-1, first + nsamp): the one before the tile feeds the first pre-emphasis
     const int nsamp = (nf - 1) * s + w + 1;
     const bool at_start = (t0 == 0);
@@ -80,12 +89,6 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const i
                 if (k >= 0 && k < nsamp) dpcm[k] = (k == 0 && at_start) ? (int16_t)0 : src[k];
             }
         }
-    }
-    for (int i = tid; i < 256; i += BURG_THREADS) sTw[i] = mk<double>(g_tw256[i].x, g_tw256[i].y);
-    for (int i = tid; i < 129; i += BURG_THREADS) { sTs[i] = mk<double>(g_twsplit[i].x, g_twsplit[i].y); sTi[i] = mk<double>(g_twinv[i].x, g_twinv[i].y); }
-    for (int i = tid; i < wp; i += BURG_THREADS) {
-        sWin[i] = (i < w) ? g_win[i] : 0.0;
-        sHann[i] = (i < w) ? ((src_mode == BURG_SRC_NR) ? g_hann[i] : 1.0) : 0.0;
     }
     __syncthreads();
     const int c = tid & (GROUP - 1), grp = tid / GROUP;
@@ -231,18 +234,24 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const i
                 en += v * v;
             }
             double alpha = group_sum16d_all(en) * inv_w;
+            // The reference's sums run over i >= ik (src/vdet/Burg.h:64-68).  Elements below ik can only belong to thread 0
+            // (ik <= 15 < CH); they are kept at exact zeros instead of being masked out of the sums: thread 0 starts with
+            // ef[0] = 0 and takes `below` = 0, which makes eb[ik-1] come out 0 by itself, and ef[ik] is cleared after stage
+            // ik.  (Masking the 16 candidates in every stage's sums cost 96 selects per stage: 17 % of the kernel's
+            // instructions in the first ncu capture of this version.)
+            if (c == 0) ef[0] = 0.0;
             double a_c = (c == 0) ? 1.0 : 0.0, aa_c = a_c;            // thread i holds a_i
             // the stage loop stays rolled: unrolled 15 times the kernel was 14 k instructions and stalled on instruction fetch
 #pragma unroll 1
             for (int ik = 1; ik < ncoef; ik++) {
-                const double below = shfl16d(eb[CH - 1], (c + 15) & 15);   // eb of sample i-1 across the thread boundary
-                const int dead = (c == 0) ? ik : 0;                        // thread 0: its samples j < ik have left the sums
+                double below = shfl16d(eb[CH - 1], (c + 15) & 15);         // eb of sample i-1 across the thread boundary
+                if (c == 0) below = 0.0;
                 // three independent chains per parity: the sums are latency-bound otherwise
                 double nu[2] = {0, 0}, df[2] = {0, 0}, db[2] = {0, 0};
 #pragma unroll
                 for (int j = 0; j < CH; j++) {
                     const double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
-                    if ((EXACT || c * CH + j < w) && (j >= BURG_MAXC || j >= dead)) {
+                    if (EXACT || c * CH + j < w) {
                         df[j & 1] = fma(ef[j], ef[j], df[j & 1]);
                         db[j & 1] = fma(pv, pv, db[j & 1]);
                         nu[j & 1] = fma(ef[j], pv, nu[j & 1]);
@@ -258,6 +267,17 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const i
                     const double e0 = ef[j];
                     ef[j] = e0 + rc * pv;
                     eb[j] = pv + rc * e0;
+                }
+                // ef[ik] leaves the sums: a jump on the stage number keeps the register index static (a select chain over
+                // the 15 candidates costs 30 selects per stage)
+                if (c == 0) {
+                    switch (ik) {
+#define CTU_CLR(J) case J: if (J < CH) ef[J < CH ? J : 0] = 0.0; break;
+                        CTU_CLR(1) CTU_CLR(2) CTU_CLR(3) CTU_CLR(4) CTU_CLR(5) CTU_CLR(6) CTU_CLR(7) CTU_CLR(8)
+                        CTU_CLR(9) CTU_CLR(10) CTU_CLR(11) CTU_CLR(12) CTU_CLR(13) CTU_CLR(14) CTU_CLR(15)
+#undef CTU_CLR
+                        default: break;
+                    }
                 }
                 // a_i = aa_i + rc * aa_{ik-i} (0 < i < ik), a_ik = rc
                 const double other = shfl16d(aa_c, (ik - c) & 15);
@@ -285,6 +305,7 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, const i
         }
         __syncwarp();
     }
+    }   // half tiles
 }
 
 // ------------------------------------------------------------------------------------------
@@ -418,10 +439,16 @@ int launch_burg(const BurgParams &B, int src_mode, const BatchDesc &bd, int64_t 
     size_t bytes = burg_smem_bytes(B.window, B.wshift);
     if (bytes > 227 * 1024) { err = "CTU: window shift too large for the Burg detector kernel"; return CTU_ERR_UNSUPPORTED; }
     cudaError_t e;
+    int per_sm = 1, num_sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     lc->begin("k_burg", s);
 #define CTU_BURG_LAUNCH2(CH, EX, MB, GA)                                                                               \
     e = cudaFuncSetAttribute(k_burg<CH, EX, MB, GA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);           \
-    if (e == cudaSuccess) k_burg<CH, EX, MB, GA><<<(unsigned)(2 * ntiles), BURG_THREADS, bytes, s>>>(B, src_mode, bd, pcm, spec, ceps, tw, ts, ti, win, hann)
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_burg<CH, EX, MB, GA>, BURG_THREADS, bytes);                   \
+    if (e == cudaSuccess)                                                                                                  \
+        k_burg<CH, EX, MB, GA><<<(unsigned)std::min<int64_t>(2 * ntiles, (int64_t)std::max(per_sm, 1) * num_sms), BURG_THREADS, bytes, s>>>(       \
+            B, src_mode, bd, (int)(2 * ntiles), pcm, spec, ceps, tw, ts, ti, win, hann)
 #define CTU_BURG_LAUNCH(CH, EX, MB)                                                                                    \
     if (gena) { CTU_BURG_LAUNCH2(CH, EX, 2, true); } else { CTU_BURG_LAUNCH2(CH, EX, MB, false); }
     // the general exponent only matters where the detector's input is expanded (NR source, hwss / fwss)

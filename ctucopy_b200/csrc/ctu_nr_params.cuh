@@ -130,6 +130,9 @@ constexpr int SCAN_UNROLL = 16;
 
 struct ScanState { float Navg, Yavg, Nravg; double Nd, Yd; };
 
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 // one frame of the recursion for one bin
 template <int MODE, int AKIND>
 __device__ __forceinline__ float nr_step(const NrParams &N, ScanState &S, float xi, int t, uint8_t flag) {
@@ -143,16 +146,20 @@ __device__ __forceinline__ float nr_step(const NrParams &N, ScanState &S, float 
             return (float)(xd - Nn);
         }
         // H = Navg/(Navg+Yavg) (a=1) or Navg/hypot(Navg,Yavg) (a=2); the output X-H*X is formed
-        // as X*(1-H) with 1-H written without cancellation
+        // as X*(1-H) with 1-H written without cancellation.  Reciprocal and reciprocal square root are the hardware
+        // approximations (MUFU, <= 2 ulp): the IEEE-rounded forms wrap each of them in a range check, two fix-up FMAs and
+        // a slow-path branch -- 10 of the 25 instructions of a step in the fused scan (ncu, profiles/r02_*), which is issue
+        // bound -- and the recursion is a contraction (p < 1), so the extra ulp does not accumulate
         float H, omH;
         if (AKIND == 1) {
-            const float r = __frcp_rn(S.Navg + S.Yavg);
+            const float r = fast_rcp(S.Navg + S.Yavg);
             H = S.Navg * r; omH = S.Yavg * r;
         } else {
             const float h2 = fmaf(S.Navg, S.Navg, S.Yavg * S.Yavg);
-            const float hh = sqrtf(h2);
-            H = __fdiv_rn(S.Navg, hh);
-            omH = __fdiv_rn(S.Yavg * S.Yavg, hh * (hh + S.Navg));
+            const float ri = fast_rsqrt(h2);                  // 1 / hypot
+            const float hh = h2 * ri;                         // hypot
+            H = S.Navg * ri;
+            omH = S.Yavg * S.Yavg * fast_rcp(hh * (hh + S.Navg));
         }
         const float Nn = H * xi;
         S.Navg = fmaf(p, S.Navg, q * Nn);

@@ -1171,6 +1171,7 @@ class VadResult:
     cri: np.ndarray         # criterion per input frame                      [T]
     thr: np.ndarray         # threshold per input frame                      [T]
     keep: np.ndarray        # rows written to the feature file (drop mode)   [T] bool
+    debug: Optional[dict] = None   # -vad_out_mode debug: side file suffix -> array (float64 values / uint8 '0','1' chars)
 
 
 def vad_module(o: Opts, Xs: np.ndarray, Xph: Optional[np.ndarray], feat: np.ndarray) -> VadResult:
@@ -1186,6 +1187,7 @@ def vad_module(o: Opts, Xs: np.ndarray, Xph: Optional[np.ndarray], feat: np.ndar
     cri = np.zeros(T); thr = np.zeros(T); vad0 = np.zeros(T, dtype=bool)
     st = {}
     c0 = None
+    rec = {k: np.zeros(T) for k in ("a", "b", "c", "d")}     # threshold internals per step (debug side files)
     for t in range(T):
         # ---- criterion
         if o.vad_cri_mode == "energy":                      # src/vad/vad.cc:96-107
@@ -1257,6 +1259,12 @@ def vad_module(o: Opts, Xs: np.ndarray, Xph: Optional[np.ndarray], feat: np.ndar
         else:
             raise ValueError("VAD: unknown vad_thr_mode!")
         thr[t] = th; vad0[t] = v
+        if m == "perc":
+            rec["a"][t], rec["b"][t] = st["min"], st["max"]
+        elif m == "adapt":
+            rec["a"][t], rec["b"][t], rec["c"][t] = st["mean"], st["mean2"], st["var"]
+        elif m == "dyn":
+            rec["a"][t], rec["b"][t], rec["c"][t] = st["dmin"], st["dmax"], st["dyn"]
         # ---- consume_vad (cepdist background update, src/vad/vad.cc:289-294)
         if o.vad_cri_mode == "cepdist" and not (v and t > o.vad_cepdist_init):
             c0 = o.vad_cepdist_p * c0 + (1.0 - o.vad_cepdist_p) * ci
@@ -1274,7 +1282,32 @@ def vad_module(o: Opts, Xs: np.ndarray, Xph: Optional[np.ndarray], feat: np.ndar
         seg = ext[max(lo, 0): r + h + 1]
         vad[r] = (seg.sum() / float(order)) >= 0.5
     keep = vad | (o.vad_apply_mode != "drop")
-    return VadResult(vad0, vad, cri, thr, keep)
+    debug = None
+    if o.vad_out_mode == "debug" and T > h:
+        # VAD::save_frame (src/vad/vad.cc:710-725) runs once per written row, after process_frame has advanced the state:
+        # row i carries the filtered decision of frame i but the criterion / threshold state of step i+h, and the h rows
+        # written by flush_vad (src/io/batch.cc:243-249) repeat the state of the last step.  The *init flags compare the
+        # already incremented frame index (src/vad/vad.cc:703, 281-284, 498-501).
+        step = np.minimum(np.arange(T) + h, T - 1)
+        ch = lambda b: np.where(b, ord("1"), ord("0")).astype(np.uint8)
+        debug = {"vad0": ch(vad0[step])}
+        if o.vad_cri_mode == "energy":
+            debug["energy"] = cri[step].copy()
+        else:
+            debug["cepdist"] = cri[step].copy()
+            debug["c0init"] = ch((step + 1) <= o.vad_cepdist_init)
+        m = o.vad_thr_mode
+        if m == "absolute":
+            debug["thr"] = np.full(T, float(o.vad_absolute_thr))
+        elif m == "perc":
+            debug.update(crimin=rec["a"][step].copy(), crimax=rec["b"][step].copy(), thr=thr[step].copy())
+        elif m == "adapt":
+            debug.update(init=ch((step + 1) <= o.vad_adapt_init), crimean=rec["a"][step].copy(), crimean2=rec["b"][step].copy(),
+                         crivar=rec["c"][step].copy(), thr=thr[step].copy())
+        else:
+            debug.update(dmin=rec["a"][step].copy(), dmax=rec["b"][step].copy(), dyn=rec["c"][step].copy(),
+                         dynmin=np.full(T, float(o.vad_dyn_min)), thr=thr[step].copy())
+    return VadResult(vad0, vad, cri, thr, keep, debug)
 
 
 # --------------------------------------------------------------------------------------

@@ -92,6 +92,15 @@ CASES = {
                                   "-vad_filter_order", "1"], "htk", {"vad_out": True}),
     "vad_perc_d_a_drop": (B + MF + ["-format_out", "htk", "-vad_out_mode", "vad", "-fea_delta", "d_a", "-vad_apply_mode", "drop"],
                           "htk", {"vad_out": True}),
+    # -vad_out_mode debug: the side files <vadfile>_vad0, _energy | _cepdist + _c0init, _thr and the threshold's own
+    # (src/vad/vad.h:39-76, src/vad/vad.cc:91-94, 212-218, 375-382, 456-467, 565-576): native doubles / '0','1' characters
+    "vaddbg_perc": (B + MF + ["-format_out", "htk", "-vad_out_mode", "debug"], "htk", {"vad_out": True, "vad_debug": True}),
+    "vaddbg_dyn_drop_f5": (B + MF + ["-format_out", "htk", "-vad_out_mode", "debug", "-vad_thr_mode", "dyn", "-vad_apply_mode", "drop",
+                                     "-vad_filter_order", "5"], "htk", {"vad_out": True, "vad_debug": True}),
+    "vaddbg_adapt_cepdist_lpc": (B + MF + ["-format_out", "htk", "-vad_out_mode", "debug", "-vad_thr_mode", "adapt", "-vad_cri_mode", "cepdist",
+                                           "-vad_cepdist_mode", "lpc", "-vad", "burg"], "htk", {"vad_out": True, "vad_debug": True}),
+    "vaddbg_abs_f1_d_a": (B + MF + ["-format_out", "htk", "-vad_out_mode", "debug", "-vad_thr_mode", "absolute", "-vad_absolute_thr", "100",
+                                    "-vad_filter_order", "1", "-fea_delta", "d_a"], "htk", {"vad_out": True, "vad_debug": True}),
     # the optional _E column: every source BATCH::init_out can pick (src/io/batch.cc:98-118)
     "mfcc_E_d_a": (B + MF + ["-fea_E", "on", "-fea_delta", "d_a", "-format_out", "htk"], "htk", {}),
     "mfcc_rawE": (B + MF + ["-fea_E", "on", "-fea_rawenergy", "on", "-format_out", "htk"], "htk", {}),
@@ -225,7 +234,7 @@ def main():
     names = [n for n in sys.argv[1:] if n in CASES] if sys.argv[1:] else list(CASES)
     for name in names:
         args, kind, extra = CASES[name]
-        outs, vads, flags_all = [], [], []
+        outs, vads, flags_all, dbgs = [], [], [], []
         for u in utts:
             ev = None
             if extra.get("ext_vad"):
@@ -246,7 +255,12 @@ def main():
                 outs.append(np.frombuffer(r["outputs"][0], dtype=np.uint8))
             if extra.get("vad_out"):
                 vads.append(np.frombuffer(r["vad"][0]["vad"], dtype=np.uint8))
+            if extra.get("vad_debug"):
+                dbgs.append({k[len("vad_"):]: np.frombuffer(v, dtype=np.uint8) for k, v in r["vad"][0].items() if k != "vad"})
         d = {"args": np.array(json.dumps(args)), "kind": np.array(kind)}
+        for i, dd in enumerate(dbgs):
+            for k, v in dd.items():
+                d["dbg_%s_%d" % (k, i)] = v
         for i, u in enumerate(utts):
             d["out%d" % i] = outs[i]
             if vads:

@@ -54,6 +54,8 @@ class Case:
         self.raw = [z["out%d" % i].tobytes() for i in range(self.n)]
         self.aux = [z["aux%d" % i].tobytes() if ("aux%d" % i) in z.files else None for i in range(self.n)]
         self.extvad = [z["extvad%d" % i] if ("extvad%d" % i) in z.files else None for i in range(self.n)]
+        # -vad_out_mode debug side files: per input, suffix -> raw bytes (native doubles, or '0' / '1' characters)
+        self.debug = [{f[4:f.rindex("_")]: z[f].tobytes() for f in z.files if f.startswith("dbg_") and f.endswith("_%d" % i)} for i in range(self.n)]
 
     def oracle_args(self):
         """args as given to the reference, with container placeholders made harmless"""

@@ -3,7 +3,8 @@ outputs (tests/golden) and against the numpy oracle on fresh seeded inputs.
 
 Bars (BASELINE.json north_star): bit-exact frame counts, row counts and VAD decisions;
 payload within 1e-4 relative or 1e-3 absolute in the log domain; int16 waveforms within
-1 LSB; non-finite positions identical.
+1 LSB (on fewer than 0.5 % of the samples; measured 0.11 % on 10 s utterances: floor() boundaries,
+SURVEY App. C-16); non-finite positions identical.
 """
 import numpy as np
 import pytest
@@ -15,16 +16,23 @@ from ctucopy_b200 import synthetic
 
 pytestmark = pytest.mark.gpu
 
-# log-domain feature kinds compare with an absolute floor of 1e-3, linear ones relative to
-# the row maximum (a band 80 dB below the frame peak is not resolvable in fp32 arithmetic)
+# log-domain feature kinds compare with an absolute floor of 1e-3.  Linear ones (band values, LP coefficients) at 1e-4
+# relative plus 1e-5 of the row maximum: north_star's "1e-3 absolute in the log domain" is 1e-3 RELATIVE for the linear
+# value, so this is the tighter reading for every entry within 40 dB of the frame's peak, and the floor only matters for
+# bands 100 dB below it (a sum of fp32 products cannot resolve those: the reference carries them in fp64)
 LOG_KINDS = ("dctc", "lpc", "logspec", "trapdct")
-ILL_CONDITIONED = {"lpa_mel"}   # see tests/test_oracle_vs_golden.py
-# hwss zeroes bins by half-wave rectification: log(0) = -inf positions depend on the sign of
-# quantities that are 0 +- rounding, so only the finite entries that agree are compared
+ILL_CONDITIONED = {"lpa_mel"}   # lpa from SQUARED mel band powers: see tests/test_oracle_vs_golden.py; the well-conditioned
+                                # lpa case (PLP bank, cube-root compressed) is the golden plpc_lpa, held to the full bar
+# hwss zeroes bins by half-wave rectification.  In the LOG domain, log(0) = -inf positions depend on the sign of quantities
+# that are 0 +- rounding (the reference is not reproducible against itself across FFT libraries there): for this one golden
+# only the finite entries that agree are compared.  The mode itself is pinned at the full tolerance in the LINEAR domain by
+# the goldens hwss_burg_spec_mag / hwss_burg_spec_pow (below, through check_features' normal path), and its detector
+# decisions bit for bit.
 HALFWAVE = {"hwss_burg_a2"}
+WAVE_MAX_FRAC = 0.005           # share of samples allowed to differ by one LSB
 
 
-def check_features(name, i, got, want, kind):
+def check_features(name, i, got, want, kind, pre=None):
     assert got.shape == want.shape, (name, i, got.shape, want.shape)
     if name in HALFWAVE:
         both = np.isfinite(got) & np.isfinite(want)
@@ -42,9 +50,22 @@ def check_features(name, i, got, want, kind):
     else:
         rowmax = np.max(np.where(fin, np.abs(want), 0), axis=1, keepdims=True)
         err = np.abs(got - want)[fin]
-        tol = (1e-4 * np.abs(want) + 1e-5 * rowmax)[fin]
+        tol = 1e-4 * np.abs(want) + 1e-5 * rowmax
+        if pre is not None:
+            # spectral subtraction in front of a linear kind: the resolution of |X| - b N is set by the value BEFORE the
+            # subtraction (fp32 front end: 6e-8 relative), see tools/parity_sweep.py tol_ok
+            colmax = np.max(np.abs(pre), axis=0)
+            tol = tol + 1e-6 * np.tile(colmax, (want.shape[1] + len(colmax) - 1) // len(colmax))[: want.shape[1]][None, :]
+        tol = tol[fin]
     bad = err > tol
     assert not bad.any(), (name, i, "max err %.3g (tol %.3g) at %d entries" % (err.max(), tol[np.argmax(err)], bad.sum()))
+
+
+def _pre_subtraction(args, o, pcm):
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("parity_sweep", os.path.join(gu.GOLDEN, "..", "..", "tools", "parity_sweep.py"))
+    ps = importlib.util.module_from_spec(spec); spec.loader.exec_module(ps)
+    return ps.pre_subtraction(args, o, pcm)
 
 
 @pytest.mark.parametrize("name", gu.case_names())
@@ -76,11 +97,11 @@ def test_cuda_matches_reference_golden(name):
             assert got.shape == want.shape, (name, i)
             d = np.abs(got.astype(np.int32) - want.astype(np.int32))
             assert d.max() <= 1, (name, i, d.max())
-            assert (d > 0).mean() < 0.02, (name, i, (d > 0).mean())
+            assert (d > 0).mean() < WAVE_MAX_FRAC, (name, i, (d > 0).mean())
         else:
             got = res.utt_features(j)
             assert int(res.frames_per_utt[j]) == co.num_frames(len(ins[i]), o)
-            check_features(name, i, got, want, o.fea_kind)
+            check_features(name, i, got, want, o.fea_kind, _pre_subtraction(args, o, ins[i]))
         if c.aux[i] is not None and c.kind != "ark":
             v = np.frombuffer(c.aux[i], dtype=np.uint8) - 48
             r0 = int(res.row_offsets[j])
@@ -113,13 +134,46 @@ def test_cuda_matches_oracle_on_parity_set(name):
         ref = co.run_pipeline(u, o)
         if o.format_out == "raw":
             d = np.abs(res.utt_waveform(j).astype(np.int32) - ref.waveform.astype(np.int32))
-            assert d.max() <= 1 and (d > 0).mean() < 0.02, (name, j, d.max(), (d > 0).mean())
+            assert d.max() <= 1 and (d > 0).mean() < WAVE_MAX_FRAC, (name, j, d.max(), (d > 0).mean())
         else:
             check_features(name, j, res.utt_features(j), ref.features, o.fea_kind)
         if ref.vad_nr is not None:
             r0 = int(res.row_offsets[j])
             got = res.vad_nr[r0: r0 + ref.nframes]
             assert np.array_equal(got.astype(bool), ref.vad_nr), (name, j, "detector decisions differ at %d frames" % int((got.astype(bool) != ref.vad_nr).sum()))
+
+
+# every alternative kernel path of the BASELINE configurations (run-time options, ctu_set_option): the fused frame kernel
+# instead of PCM -> spectrum -> k_bank, the standalone scan instead of the one fused into k_bank, and the synthesis that
+# recomputes the forward transform instead of reading the stored spectrum
+ALT_PATHS = [("mfcc_d_a", {"split_front": 0}), ("plp", {"split_front": 0}), ("trapdct", {"split_front": 0}),
+             ("mfcc_exten", {"fuse_nr": 0}), ("mfcc_exten", {"fuse_nr": 1}), ("fwss_burg", {"fuse_nr": 0}), ("fwss_burg", {"fuse_nr": 1}),
+             ("exten_raw", {"synth_from_pcm": 1})]
+
+
+@pytest.mark.parametrize("name,options", ALT_PATHS, ids=["%s-%s" % (n, "+".join("%s=%d" % kv for kv in o.items())) for n, o in ALT_PATHS])
+def test_alternative_kernel_paths_match_oracle(name, options):
+    args = ORACLE_CASES[name]
+    o = co.parse_args(args)
+    res = cb.extract(args, PARITY_SET, options=options)
+    for j, u in enumerate(PARITY_SET):
+        ref = co.run_pipeline(u, o)
+        if o.format_out == "raw":
+            d = np.abs(res.utt_waveform(j).astype(np.int32) - ref.waveform.astype(np.int32))
+            assert d.max() <= 1 and (d > 0).mean() < WAVE_MAX_FRAC, (name, j, d.max(), (d > 0).mean())
+        else:
+            check_features(name, j, res.utt_features(j), ref.features, o.fea_kind)
+        if ref.vad_nr is not None:
+            r0 = int(res.row_offsets[j])
+            assert np.array_equal(res.vad_nr[r0: r0 + ref.nframes].astype(bool), ref.vad_nr), (name, j)
+
+
+def test_fused_and_standalone_scan_agree_bit_for_bit():
+    """k_bank's in-tile scan and the standalone k_nr_scan4 run the same recursion step (nr_step): identical features."""
+    for name in ("mfcc_exten", "fwss_burg"):
+        a = cb.extract(ORACLE_CASES[name], PARITY_SET, options={"fuse_nr": 1})
+        b = cb.extract(ORACLE_CASES[name], PARITY_SET, options={"fuse_nr": 0})
+        assert np.array_equal(a.features, b.features), name
 
 
 def test_batch_position_independence_and_ragged_lengths():
@@ -209,7 +263,7 @@ def test_full_length_utterances_match_oracle(name):
         ref = co.run_pipeline(u, o)
         if o.format_out == "raw":
             d = np.abs(res.utt_waveform(j).astype(np.int32) - ref.waveform.astype(np.int32))
-            assert d.max() <= 1 and (d > 0).mean() < 0.02, (name, j, d.max(), (d > 0).mean())
+            assert d.max() <= 1 and (d > 0).mean() < WAVE_MAX_FRAC, (name, j, d.max(), (d > 0).mean())
         else:
             assert int(res.frames_per_utt[j]) == 998
             check_features(name, j, res.utt_features(j), ref.features, o.fea_kind)
@@ -242,7 +296,7 @@ def test_randomised_option_sweep_matches_oracle():
             continue
         for i, u in enumerate(ins):
             ref = co.run_pipeline(u, o)
-            ok, why = ps.tol_ok(res.utt_features(i), ref.features, o.fea_kind)
+            ok, why = ps.tol_ok(res.utt_features(i), ref.features, o.fea_kind, ps.pre_subtraction(args, o, u))
             assert ok, (why, " ".join(args))
             if ref.vad_nr is not None:
                 r0 = int(res.row_offsets[i])

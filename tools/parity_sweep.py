@@ -105,7 +105,45 @@ def draw16(rng):
     return a
 
 
-def tol_ok(got, want, kind):
+def without_nr(args):
+    """The same option set with the noise reduction (and its detector) switched off: gives the band values BEFORE the
+    subtraction, which is what the resolution of a subtractive mode's output is relative to."""
+    out, skip = [], 0
+    for i, a in enumerate(args):
+        if skip:
+            skip -= 1
+            continue
+        if a == "-nr_mode":
+            out += ["-nr_mode", "none"]; skip = 1
+        elif a == "-vad" and i + 1 < len(args) and "-vad_out_mode" not in args and "-vad_cri_mode" not in args:
+            skip = 1
+        else:
+            out.append(a)
+    return out
+
+
+def pre_subtraction(args, o, pcm):
+    """Static block of the oracle's features for `args` with the noise reduction switched off (None when the configuration
+    has no spectral subtraction in front of a linear feature kind)."""
+    if o.nr_mode == "none" or o.fea_kind in ("dctc", "lpc", "logspec", "trapdct") or o.format_out in ("raw", "wave"):
+        return None
+    a = without_nr(args)
+    oo = co.parse_args(a)
+    f = co.run_pipeline(pcm, oo).features
+    if (oo.fea_delta and oo.n_order > 0) or oo.fea_trap:
+        f = f[:, : oo.fea_ncepcoefs + 1]
+    elif oo.fea_E:
+        f = f[:, :-1]
+    return f
+
+
+def tol_ok(got, want, kind, pre=None):
+    """north_star's bar: 1e-4 relative, or 1e-3 absolute in the log domain.  Linear kinds get a floor of 1e-5 of the row
+    maximum (= 100 dB below the frame's peak).  pre: the oracle's output of the same configuration WITHOUT the noise
+    reduction -- a spectral subtraction |X| - b N takes the difference of two numbers that the fp32 front end knows to
+    6e-8 relative each, so the resolution of its (linear) output is 1e-6 of the value before the subtraction, however small
+    the difference comes out; the column-wise maximum of |pre| over the utterance stands for that value (it also covers
+    delta columns, which mix neighbouring rows)."""
     if got.shape != want.shape:
         return False, "shape %s vs %s" % (got.shape, want.shape)
     if not gu.same_nonfinite(got, want):
@@ -116,7 +154,12 @@ def tol_ok(got, want, kind):
         tol = (1e-4 * np.abs(want) + 1e-3)[fin]
     else:
         rowmax = np.max(np.where(fin, np.abs(want), 0), axis=1, keepdims=True) * np.ones_like(want)
-        tol = (1e-4 * np.abs(want) + 1e-5 * rowmax)[fin]
+        tol = 1e-4 * np.abs(want) + 1e-5 * rowmax
+        if pre is not None and pre.size:
+            blk = pre.shape[1]
+            colmax = np.max(np.where(np.isfinite(pre), np.abs(pre), 0), axis=0)
+            tol = tol + 1e-6 * np.tile(colmax, (want.shape[1] + blk - 1) // blk)[: want.shape[1]][None, :]
+        tol = tol[fin]
     bad = err > tol
     return (not bad.any()), ("max err %.3g at %d entries (max |want| %.3g)" % (err.max() if err.size else 0, int(bad.sum()), np.abs(want[fin]).max() if fin.any() else 0))
 
@@ -186,7 +229,7 @@ def main():
                     ok = g.shape == w_.shape and np.abs(g - w_).max() <= 1 and (g != w_).mean() < 0.02
                     why = "waveform: shape %s vs %s, max |diff| %s, share differing %.4f" % (g.shape, w_.shape, np.abs(g - w_).max() if g.shape == w_.shape else -1, (g != w_).mean() if g.shape == w_.shape else 1)
                 else:
-                    ok, why = tol_ok(res.utt_features(i), refs[i].features, o.fea_kind)
+                    ok, why = tol_ok(res.utt_features(i), refs[i].features, o.fea_kind, pre_subtraction(args, o, ins[i]))
                 nrun += 1
                 r0 = int(res.row_offsets[i])
                 if refs[i].vad_nr is not None:
