@@ -20,6 +20,7 @@ from .api import (  # noqa: F401
     lib,
     lib_path,
     parse_config,
+    vad_debug_files,
 )
 
-__all__ = ["Config", "CtuError", "Handle", "Plan", "Result", "design_filter_bank", "extract", "extract_features", "extract_g711", "g711_table", "lib", "lib_path", "parse_config"]
+__all__ = ["Config", "CtuError", "Handle", "Plan", "Result", "design_filter_bank", "extract", "extract_features", "extract_g711", "g711_table", "lib", "lib_path", "parse_config", "vad_debug_files"]

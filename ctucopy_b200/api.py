@@ -135,6 +135,7 @@ def lib() -> C.CDLL:
     L.ctu_plan_normalise.argtypes = [vp, vp, vp]; L.ctu_plan_normalise.restype = C.c_int
     L.ctu_set_rand_offset.argtypes = [vp, C.c_uint64]; L.ctu_set_rand_offset.restype = C.c_int
     L.ctu_set_option.argtypes = [vp, cp, i64]; L.ctu_set_option.restype = C.c_int
+    L.ctu_plan_fetch_vad_debug.argtypes = [vp, vp, vp]; L.ctu_plan_fetch_vad_debug.restype = C.c_int
     L.ctu_host_alloc.argtypes = [P(vp), C.c_uint64]; L.ctu_host_alloc.restype = C.c_int
     L.ctu_host_free.argtypes = [vp]; L.ctu_host_free.restype = None
     _lib = L
@@ -310,6 +311,14 @@ class Plan:
         self.L.ctu_plan_rows_per_utt(self.p, r.ctypes.data)
         return r
 
+    def fetch_vad_debug(self):
+        """-vad_out_mode debug: (steps float64 [total_frames, 5], vad0 uint8 [total_frames]) of the last run
+        (ctu_plan_fetch_vad_debug); vad_debug_files() turns one utterance's slice into the reference's side files."""
+        steps = np.zeros((self.total_frames, 5), dtype=np.float64)
+        vad0 = np.zeros(self.total_frames, dtype=np.uint8)
+        self.hd._check(self.L.ctu_plan_fetch_vad_debug(self.p, steps.ctypes.data, vad0.ctypes.data))
+        return steps, vad0
+
     def run_device(self, d_pcm: int, d_features: Optional[int] = None, d_waveform: Optional[int] = None,
                    d_ext_vad: Optional[int] = None, d_vad_nr: Optional[int] = None, d_vad_out: Optional[int] = None,
                    stream: int = 0):
@@ -370,6 +379,36 @@ def extract(argv: Sequence[str], utterances: List[np.ndarray], ext_vad: Optional
             plan.close()
     finally:
         hd.close()
+
+
+def vad_debug_files(cfg: Config, steps: np.ndarray, vad0: np.ndarray) -> dict:
+    """The side files `-vad_out_mode debug` writes next to <vadfile> for ONE utterance, suffix -> bytes (native doubles, or
+    '0' / '1' characters), from that utterance's rows of Plan.fetch_vad_debug().  Same rule as host/ctucopy_main.cc: row i
+    holds VAD step min(i + (vad_filter_order - 1) / 2, T - 1) (VAD::save_frame runs after the state has advanced and the
+    flush rows repeat the last step, src/vad/vad.cc:710-725, src/io/batch.cc:243-249)."""
+    T = len(vad0)
+    h = (cfg.vad_filter_order - 1) // 2
+    if T <= h:
+        return {}
+    step = np.minimum(np.arange(T) + h, T - 1)
+    ch = lambda b: np.where(b, ord("1"), ord("0")).astype(np.uint8).tobytes()
+    col = lambda k: np.ascontiguousarray(steps[step, k], dtype="<f8").tobytes()
+    out = {"vad0": ch(vad0[step] != 0)}
+    if cfg.vad_cri_mode.decode() == "energy":
+        out["energy"] = col(0)
+    else:
+        out["cepdist"] = col(0)
+        out["c0init"] = ch((step + 1) <= cfg.vad_cepdist_init)
+    m = cfg.vad_thr_mode.decode()
+    if m == "absolute":
+        out["thr"] = np.full(T, cfg.vad_absolute_thr, dtype="<f8").tobytes()
+    elif m == "perc":
+        out.update(crimin=col(2), crimax=col(3), thr=col(1))
+    elif m == "adapt":
+        out.update(init=ch((step + 1) <= cfg.vad_adapt_init), crimean=col(2), crimean2=col(3), crivar=col(4), thr=col(1))
+    else:
+        out.update(dmin=col(2), dmax=col(3), dyn=col(4), dynmin=np.full(T, cfg.vad_dyn_min, dtype="<f8").tobytes(), thr=col(1))
+    return out
 
 
 def g711_table(alaw: bool) -> np.ndarray:

@@ -144,6 +144,7 @@ struct ctu_plan {
     bool dither_ready = false;
     double *d_ceps = nullptr;            // Burg cepstra [frames x ncoef]
     double *d_cri = nullptr;             // VAD criterion per frame
+    double *d_vdbg = nullptr;            // -vad_out_mode debug: VAD_DBG doubles per VAD step
     uint8_t *d_flags = nullptr;          // NR-internal detector decisions
     uint8_t *d_keep = nullptr;           // VAD module: row kept
     uint8_t *d_vad0 = nullptr;           // VAD module: unfiltered decisions
@@ -868,6 +869,7 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     if (h->do_vad) {
         if ((st = dev_alloc(h, p, &p->d_cri, (size_t)rows)) || (st = dev_alloc(h, p, &p->d_keep, (size_t)rows)) || (st = dev_alloc(h, p, &p->d_vad0, (size_t)rows)) ||
             (st = dev_alloc(h, p, &p->d_rows, (size_t)n))) { ctu_plan_destroy(p); return st; }
+        if (!std::strcmp(h->cfg.vad_out_mode, "debug") && (st = dev_alloc(h, p, &p->d_vdbg, (size_t)rows * VAD_DBG))) { ctu_plan_destroy(p); return st; }
     }
     *out = p;
     return CTU_OK;
@@ -1278,7 +1280,9 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     }
     // ---- stage 4: VAD module -----------------------------------------------------------------
     if (h->do_vad) {
-        if ((st = launch_vad_module(h->vp, h->bp, bd32, r.t32_n, p->d_nframes, p->d_row_off, r.u0, r.u1, r.row0, r.nrows, d_pcm, p->d_spec, d_fea,
+        VadParams VP = h->vp;
+        VP.dbg = p->d_vdbg;
+        if ((st = launch_vad_module(VP, h->bp, bd32, r.t32_n, p->d_nframes, p->d_row_off, r.u0, r.u1, r.row0, r.nrows, d_pcm, p->d_spec, d_fea,
                                     p->d_fea64, h->feature_dim, p->d_ceps, p->d_cri, p->d_vad0, d_vadout, p->d_keep, p->d_rows, h->d_tw256d, h->d_twsplitd,
                                     h->d_twinvd, h->d_wind, s, &h->lc, h->err))) return st;
     }
@@ -1588,6 +1592,17 @@ int ctu_run(ctu_handle *h, const int16_t *pcm, const int64_t *off, int32_t n, co
     if (!st && rows_per_utt) ctu_plan_rows_per_utt(p, rows_per_utt);
     ctu_plan_destroy(p);
     return st;
+}
+
+int ctu_plan_fetch_vad_debug(ctu_plan *p, double *steps, uint8_t *vad0) {
+    if (!p) return CTU_ERR_CONFIG;
+    ctu_handle *h = p->h;
+    if (!p->d_vdbg) return fail(h, CTU_ERR_CONFIG, "CTU: the handle was not created with -vad_out_mode debug");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    if (steps) CK(cudaMemcpy(steps, p->d_vdbg, (size_t)p->total_frames * VAD_DBG * sizeof(double), cudaMemcpyDeviceToHost));
+    if (vad0) CK(cudaMemcpy(vad0, p->d_vad0, (size_t)p->total_frames, cudaMemcpyDeviceToHost));
+    return CTU_OK;
 }
 
 int ctu_set_option(ctu_handle *h, const char *name, int64_t value) {

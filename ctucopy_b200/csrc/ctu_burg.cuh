@@ -42,7 +42,7 @@ __device__ __forceinline__ double group_sum16d_all(double v) {
     return v;
 }
 
-template <int CH, bool EXACT, int MINB, bool GENA>
+template <int CH, bool EXACT, int MINB, bool GENA, int CLR = 1, bool PERSIST = true>
 __global__ void __launch_bounds__(BURG_THREADS, MINB)
 k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, int nhalf, const int16_t *__restrict__ pcm, const float *__restrict__ spec,
        double *__restrict__ ceps, const double2 *__restrict__ g_tw256, const double2 *__restrict__ g_twsplit,
@@ -66,7 +66,7 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, int nha
     }
     // persistent CTAs: the tables above are staged once, the half tiles are walked with stride gridDim.x
 #pragma unroll 1
-    for (int ht = blockIdx.x; ht < nhalf; ht += gridDim.x) {
+    for (int ht = blockIdx.x; ht < nhalf; ht += (PERSIST ? gridDim.x : nhalf)) {
     const int2 tile = bd.tiles[ht >> 1];
     const int u = tile.x, t0 = tile.y + (ht & 1) * BURG_HALF;
     const int nf = min(BURG_HALF, bd.nframes[u] - t0);
@@ -239,19 +239,20 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, int nha
             // ef[0] = 0 and takes `below` = 0, which makes eb[ik-1] come out 0 by itself, and ef[ik] is cleared after stage
             // ik.  (Masking the 16 candidates in every stage's sums cost 96 selects per stage: 17 % of the kernel's
             // instructions in the first ncu capture of this version.)
-            if (c == 0) ef[0] = 0.0;
+            if (CLR != 0 && c == 0) ef[0] = 0.0;
             double a_c = (c == 0) ? 1.0 : 0.0, aa_c = a_c;            // thread i holds a_i
             // the stage loop stays rolled: unrolled 15 times the kernel was 14 k instructions and stalled on instruction fetch
 #pragma unroll 1
             for (int ik = 1; ik < ncoef; ik++) {
                 double below = shfl16d(eb[CH - 1], (c + 15) & 15);         // eb of sample i-1 across the thread boundary
-                if (c == 0) below = 0.0;
+                if (CLR != 0 && c == 0) below = 0.0;
+                const int dead = (CLR == 0 && c == 0) ? ik : 0;
                 // three independent chains per parity: the sums are latency-bound otherwise
                 double nu[2] = {0, 0}, df[2] = {0, 0}, db[2] = {0, 0};
 #pragma unroll
                 for (int j = 0; j < CH; j++) {
                     const double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
-                    if (EXACT || c * CH + j < w) {
+                    if ((EXACT || c * CH + j < w) && (CLR != 0 || j >= BURG_MAXC || j >= dead)) {
                         df[j & 1] = fma(ef[j], ef[j], df[j & 1]);
                         db[j & 1] = fma(pv, pv, db[j & 1]);
                         nu[j & 1] = fma(ef[j], pv, nu[j & 1]);
@@ -268,16 +269,20 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, int nha
                     ef[j] = e0 + rc * pv;
                     eb[j] = pv + rc * e0;
                 }
-                // ef[ik] leaves the sums: a jump on the stage number keeps the register index static (a select chain over
-                // the 15 candidates costs 30 selects per stage)
-                if (c == 0) {
-                    switch (ik) {
+                // ef[ik] leaves the sums
+                if (CLR == 1) {
+                    if (c == 0) {
+                        switch (ik) {
 #define CTU_CLR(J) case J: if (J < CH) ef[J < CH ? J : 0] = 0.0; break;
-                        CTU_CLR(1) CTU_CLR(2) CTU_CLR(3) CTU_CLR(4) CTU_CLR(5) CTU_CLR(6) CTU_CLR(7) CTU_CLR(8)
-                        CTU_CLR(9) CTU_CLR(10) CTU_CLR(11) CTU_CLR(12) CTU_CLR(13) CTU_CLR(14) CTU_CLR(15)
+                            CTU_CLR(1) CTU_CLR(2) CTU_CLR(3) CTU_CLR(4) CTU_CLR(5) CTU_CLR(6) CTU_CLR(7) CTU_CLR(8)
+                            CTU_CLR(9) CTU_CLR(10) CTU_CLR(11) CTU_CLR(12) CTU_CLR(13) CTU_CLR(14) CTU_CLR(15)
 #undef CTU_CLR
-                        default: break;
+                            default: break;
+                        }
                     }
+                } else if (CLR == 2) {
+#pragma unroll
+                    for (int j = 1; j < BURG_MAXC && j < CH; j++) if (c == 0 && j == ik) ef[j] = 0.0;
                 }
                 // a_i = aa_i + rc * aa_{ik-i} (0 < i < ik), a_ik = rc
                 const double other = shfl16d(aa_c, (ik - c) & 15);
@@ -449,8 +454,21 @@ int launch_burg(const BurgParams &B, int src_mode, const BatchDesc &bd, int64_t 
     if (e == cudaSuccess)                                                                                                  \
         k_burg<CH, EX, MB, GA><<<(unsigned)std::min<int64_t>(2 * ntiles, (int64_t)std::max(per_sm, 1) * num_sms), BURG_THREADS, bytes, s>>>(       \
             B, src_mode, bd, (int)(2 * ntiles), pcm, spec, ceps, tw, ts, ti, win, hann)
+#define CTU_BURG_LAUNCH3(CH, EX, MB, GA, CL, PE)                                                                       \
+    e = cudaFuncSetAttribute(k_burg<CH, EX, MB, GA, CL, PE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);   \
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_burg<CH, EX, MB, GA, CL, PE>, BURG_THREADS, bytes); \
+    if (e == cudaSuccess)                                                                                                  \
+        k_burg<CH, EX, MB, GA, CL, PE><<<(unsigned)(PE ? std::min<int64_t>(2 * ntiles, (int64_t)std::max(per_sm, 1) * num_sms) : 2 * ntiles), BURG_THREADS, bytes, s>>>( \
+            B, src_mode, bd, (int)(2 * ntiles), pcm, spec, ceps, tw, ts, ti, win, hann)
 #define CTU_BURG_LAUNCH(CH, EX, MB)                                                                                    \
-    if (gena) { CTU_BURG_LAUNCH2(CH, EX, 2, true); } else { CTU_BURG_LAUNCH2(CH, EX, MB, false); }
+    if (gena) { CTU_BURG_LAUNCH2(CH, EX, 2, true); }                                                                   \
+    else if (CH == 25 && EX && variant == 0) { CTU_BURG_LAUNCH3(25, true, MB, false, 0, false); }                      \
+    else if (CH == 25 && EX && variant == 1) { CTU_BURG_LAUNCH3(25, true, MB, false, 1, false); }                      \
+    else if (CH == 25 && EX && variant == 2) { CTU_BURG_LAUNCH3(25, true, MB, false, 2, false); }                      \
+    else if (CH == 25 && EX && variant == 10) { CTU_BURG_LAUNCH3(25, true, MB, false, 0, true); }                      \
+    else if (CH == 25 && EX && variant == 12) { CTU_BURG_LAUNCH3(25, true, MB, false, 2, true); }                      \
+    else { CTU_BURG_LAUNCH2(CH, EX, MB, false); }
+    static const int variant = getenv("CTU_BURG_VARIANT") ? atoi(getenv("CTU_BURG_VARIANT")) : 11;
     // the general exponent only matters where the detector's input is expanded (NR source, hwss / fwss)
     const bool gena = (src_mode == BURG_SRC_NR && B.expand && B.a_kind == 0);
     // 25 samples per thread: 128 registers = four CTAs per SM; 32 samples per thread (window up to 512): three

@@ -219,17 +219,19 @@ k_vad_scan(const __grid_constant__ VadParams V, const int *__restrict__ nframes,
                     }
                 }
                 bool v;
+                double th = 0.0;                     // the threshold as the reference's debug file holds it after this step
                 if (V.thr == VTHR_ABSOLUTE) {
+                    th = V.abs_thr;
                     v = c >= V.abs_thr;
                 } else if (V.thr == VTHR_PERC) {
                     if (r == 0 || (double)r < (double)V.perc_init) { s_min = c; s_max = c; }
                     else { s_min = (c < s_min) ? c : s_min; s_max = (c > s_max) ? c : s_max; }
-                    double th = s_min + (V.perc_thr / 100.0) * (s_max - s_min);
+                    th = s_min + (V.perc_thr / 100.0) * (s_max - s_min);
                     v = c >= th;
                 } else if (V.thr == VTHR_ADAPT) {
-                    if (r == 0) { mean = c; mean2 = c * c; var = 0.0; v = false; }
+                    if (r == 0) { mean = c; mean2 = c * c; var = 0.0; v = false; th = c; }
                     else {
-                        double th = mean + V.adapt_za * sqrt(var);
+                        th = mean + V.adapt_za * sqrt(var);
                         if ((c < th) || (r <= V.adapt_init)) {
                             mean = V.adapt_q * mean + (1.0 - V.adapt_q) * c;
                             mean2 = V.adapt_q * mean2 + (1.0 - V.adapt_q) * c * c;
@@ -239,20 +241,30 @@ k_vad_scan(const __grid_constant__ VadParams V, const int *__restrict__ nframes,
                     }
                 } else {
                     const int i0 = max(1, V.dyn_init);
-                    if (r < i0) { dmax = c; dmin = c; dyn = 0.0; v = false; }
+                    if (r < i0) { dmax = c; dmin = c; dyn = 0.0; v = false; th = c; }
                     else if (r == i0) {
                         dmax = fmax(dmax, c) + V.dyn_min / 10.0;
                         dmin = fmin(dmin, c) - V.dyn_min / 10.0;
-                        dyn = dmax - dmin; v = false;
+                        dyn = dmax - dmin; v = false; th = c;
                     } else {
                         if (dmax < c) dmax = V.qmaxinc * dmax + (1.0 - V.qmaxinc) * c; else dmax = V.qmaxdec * dmax + (1.0 - V.qmaxdec) * c;
                         if (dmin > c) dmin = V.qmindec * dmin + (1.0 - V.qmindec) * c; else dmin = V.qmininc * dmin + (1.0 - V.qmininc) * c;
                         dyn = dmax - dmin;
-                        double th = dmin + (V.dyn_perc / 100.0) * dyn;
+                        th = dmin + (V.dyn_perc / 100.0) * dyn;
                         v = (c > th) && (dyn > V.dyn_min);
                     }
                 }
                 sv[j] = v ? 1 : 0;
+                if (V.dbg) {
+                    // what VAD::save_frame would write after this step (src/vad/vad.cc:109-111, 278-286, 333-335, 400-404,
+                    // 497-508, 627-634); the host pairs row i with step min(i + (order-1)/2, T-1)
+                    double *d = V.dbg + (R0 + r) * VAD_DBG;
+                    d[0] = c; d[1] = th;
+                    if (V.thr == VTHR_PERC) { d[2] = s_min; d[3] = s_max; d[4] = 0.0; }
+                    else if (V.thr == VTHR_ADAPT) { d[2] = mean; d[3] = mean2; d[4] = var; }
+                    else if (V.thr == VTHR_DYN) { d[2] = dmin; d[3] = dmax; d[4] = dyn; }
+                    else { d[2] = d[3] = d[4] = 0.0; }
+                }
                 if (V.cri != VCRI_ENERGY && !(v && r > V.cep_init)) {
                     for (int k = 0; k < cn; k++) c0[k] = V.cep_p * c0[k] + (1.0 - V.cep_p) * ci_row[k];
                 }

@@ -67,7 +67,10 @@ struct VadParams {
     int perc_init; double perc_thr;
     int adapt_init; double adapt_q, adapt_za;
     int dyn_init; double dyn_perc, dyn_min, qmaxinc, qmaxdec, qmindec, qmininc;
+    // -vad_out_mode debug: per step VAD_DBG doubles (criterion, threshold, three values of the threshold's state), else null
+    double *dbg;
 };
+constexpr int VAD_DBG = 5;
 
 // ------------------------------------------------------------------------------------------
 static inline int build_nr_params(const ctu_config &c, int nr_mode, int vad_src, bool signal_out, int nb, NrParams &N, SynthParams &S,

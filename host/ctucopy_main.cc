@@ -180,6 +180,46 @@ struct Writers {
         for (int64_t i = 0; i < n; i++) std::fputc(v[i] ? '1' : '0', f);
         std::fclose(f);
     }
+    // -vad_out_mode debug: the side files of FileWriter(filename, suffix) (src/vad/vad.h:39-76) next to the decision file.
+    // steps: CTU_VAD_DEBUG_COLS doubles per VAD step (criterion, threshold, three state values), vad0: unfiltered decisions.
+    // VAD::save_frame (src/vad/vad.cc:710-725) runs after the state has advanced and only once the majority filter has a
+    // decision: row i holds step min(i + (order-1)/2, T-1); the *init flags compare the incremented frame index.
+    void vad_debug(const ListEntry &e, const double *steps, const uint8_t *vad0, int64_t T) {
+        const int64_t h = (c.vad_filter_order - 1) / 2;
+        auto open = [&](const char *suffix) {
+            FILE *f = std::fopen((e.vadout + "_" + suffix).c_str(), "wb");
+            if (!f) die("FileWriter: cannot open file!");
+            return f;
+        };
+        auto step = [&](int64_t i) { return std::min(i + h, T - 1); };
+        const int64_t rows = (T > h) ? T : 0;
+        auto doubles = [&](const char *suffix, int col) {
+            FILE *f = open(suffix);
+            std::vector<double> v((size_t)rows);
+            for (int64_t i = 0; i < rows; i++) v[(size_t)i] = steps[step(i) * CTU_VAD_DEBUG_COLS + col];
+            std::fwrite(v.data(), 8, v.size(), f);
+            std::fclose(f);
+        };
+        auto constant = [&](const char *suffix, double x) {
+            FILE *f = open(suffix);
+            std::vector<double> v((size_t)rows, x);
+            std::fwrite(v.data(), 8, v.size(), f);
+            std::fclose(f);
+        };
+        auto flags = [&](const char *suffix, int init) {       // '1' while the (incremented) frame index is <= init
+            FILE *f = open(suffix);
+            for (int64_t i = 0; i < rows; i++) std::fputc(step(i) + 1 <= init ? '1' : '0', f);
+            std::fclose(f);
+        };
+        { FILE *f = open("vad0"); for (int64_t i = 0; i < rows; i++) std::fputc(vad0[step(i)] ? '1' : '0', f); std::fclose(f); }
+        if (!std::strcmp(c.vad_cri_mode, "energy")) doubles("energy", 0);
+        else { doubles("cepdist", 0); flags("c0init", c.vad_cepdist_init); }
+        const std::string m(c.vad_thr_mode);
+        if (m == "absolute") constant("thr", c.vad_absolute_thr);
+        else if (m == "perc") { doubles("crimin", 2); doubles("crimax", 3); doubles("thr", 1); }
+        else if (m == "adapt") { flags("init", c.vad_adapt_init); doubles("crimean", 2); doubles("crimean2", 3); doubles("crivar", 4); doubles("thr", 1); }
+        else { doubles("dmin", 2); doubles("dmax", 3); doubles("dyn", 4); constant("dynmin", c.vad_dyn_min); doubles("thr", 1); }
+    }
     void close() {
         if (pf) {
             // sentence table right behind the data, then the ASCII header (src/io/pfile.cc:435-468, 573-592)
@@ -482,6 +522,8 @@ struct Batch {
     int64_t total = 0, total_os = 0;       // frames, output samples
     size_t ext_pos = 0;
     Pinned pcm, fea, wav, vout, vnr;
+    std::vector<double> vdbg;              // -vad_out_mode debug: per-step records and unfiltered decisions
+    std::vector<uint8_t> vad0;
     int state = 0;                         // 0 free, 1 read, 2 computed
 };
 
@@ -489,6 +531,7 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
                    const std::vector<unsigned char> &extvad, size_t frame0, uint64_t rand0 = 0) {
     const bool do_vad = std::strcmp(cfg.vad_apply_mode, "none") || std::strcmp(cfg.vad_out_mode, "none");
     const bool vad_file = std::strcmp(cfg.vad_out_mode, "none") != 0;
+    const bool vad_dbg = !std::strcmp(cfg.vad_out_mode, "debug");
     const bool use_ext = !std::strcmp(cfg.vadmode, "file");
     const double t_start = now_s();
     ctu_handle *h = nullptr;
@@ -578,6 +621,7 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
                     if (sig) W.waveform(e, wav + s0[u], s0[u + 1] - s0[u]);
                     else W.features(e, fea + row0[u] * dim, B.rows[u], B.i0 + u);
                     if (do_vad && vad_file) W.vad(e, vout + row0[u], B.frames[u]);
+                    if (vad_dbg) W.vad_debug(e, B.vdbg.data() + row0[u] * CTU_VAD_DEBUG_COLS, B.vad0.data() + row0[u], B.frames[u]);
                 };
                 double tw = now_s();
                 if (per_file) parallel_for(n, IO_THREADS, one);      // one file per utterance: any order
@@ -605,15 +649,21 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
                 ev = extvad.data() + B.ext_pos;
             }
             double tg = now_s();
-            if (fea_in || g711) {
+            if (fea_in || g711 || vad_dbg) {
                 ctu_plan *pl = nullptr;
                 if (ctu_plan_create(h, B.off.data(), n, &pl)) die(ctu_last_error(h));
                 const int st = fea_in ? ctu_plan_run_host_fea(pl, (const float *)B.pcm.p, (float *)B.fea.p)
-                                      : ctu_plan_run_host_g711(pl, (const uint8_t *)B.pcm.p, ho.format_in == "alaw", ev, sig ? nullptr : (float *)B.fea.p,
-                                                               sig ? (int16_t *)B.wav.p : nullptr, (uint8_t *)B.vnr.p, (uint8_t *)B.vout.p);
+                               : g711 ? ctu_plan_run_host_g711(pl, (const uint8_t *)B.pcm.p, ho.format_in == "alaw", ev, sig ? nullptr : (float *)B.fea.p,
+                                                               sig ? (int16_t *)B.wav.p : nullptr, (uint8_t *)B.vnr.p, (uint8_t *)B.vout.p)
+                                      : ctu_plan_run_host(pl, (const int16_t *)B.pcm.p, ev, sig ? nullptr : (float *)B.fea.p, sig ? (int16_t *)B.wav.p : nullptr,
+                                                          (uint8_t *)B.vnr.p, (uint8_t *)B.vout.p);
                 if (st) { ctu_plan_destroy(pl); die(ctu_last_error(h)); }
                 ctu_plan_frames_per_utt(pl, B.frames.data());
                 ctu_plan_rows_per_utt(pl, B.rows.data());
+                if (vad_dbg) {
+                    B.vdbg.resize((size_t)B.total * CTU_VAD_DEBUG_COLS); B.vad0.resize((size_t)B.total);
+                    if (ctu_plan_fetch_vad_debug(pl, B.vdbg.data(), B.vad0.data())) { ctu_plan_destroy(pl); die(ctu_last_error(h)); }
+                }
                 ctu_plan_destroy(pl);
             } else
             if (ctu_run(h, (const int16_t *)B.pcm.p, B.off.data(), n, ev, sig ? nullptr : (float *)B.fea.p, B.total, sig ? (int16_t *)B.wav.p : nullptr,

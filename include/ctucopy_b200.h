@@ -217,6 +217,18 @@ int ctu_run(ctu_handle *h, const int16_t *pcm, const int64_t *utt_offsets, int32
  * ((window - wshift) + frames * wshift per file).                                                                  */
 int ctu_set_rand_offset(ctu_handle *h, uint64_t values_drawn);
 
+/* -vad_out_mode debug (FileWriter and the save_frame members of the criterion / threshold classes, src/vad/vad.h:39-76,
+ * src/vad/vad.cc:91-111, 212-286, 324-335, 375-404, 456-508, 565-634): the values behind the reference's side files
+ * <vadfile>_vad0, _energy | _cepdist (+ _c0init), _thr and the threshold's own files.  Per VAD step of every utterance
+ * (= per frame, list order) CTU_VAD_DEBUG_COLS doubles -- criterion, threshold, then the threshold's state: perc crimin,
+ * crimax, -; adapt crimean, crimean2, crivar; dyn dmin, dmax, dyn; absolute -, -, - -- and the unfiltered decision vad0.
+ * The reference writes a row once the majority filter has decided it, AFTER the state has advanced: row i of a side file
+ * holds step min(i + (vad_filter_order - 1) / 2, T - 1) (the rows written by the flush repeat the last step), and its
+ * *init flag files compare that step + 1 with the init length.  Valid after a run of this plan; needs a handle created
+ * with -vad_out_mode debug.                                                                                          */
+#define CTU_VAD_DEBUG_COLS 5
+int ctu_plan_fetch_vad_debug(ctu_plan *p, double *steps /* [total_frames x CTU_VAD_DEBUG_COLS] */, uint8_t *vad0 /* [total_frames] */);
+
 /* Run-time knobs that are not reference options (the reference has no counterpart: it has one code path):
  *   "copy_only"      1 = the host entry points do their H2D / D2H copies with the kernels left out: the control
  *                        measurement behind bench.py's e2e.copy_only_ms

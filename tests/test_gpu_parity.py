@@ -176,6 +176,36 @@ def test_fused_and_standalone_scan_agree_bit_for_bit():
         assert np.array_equal(a.features, b.features), name
 
 
+@pytest.mark.parametrize("name", [n for n in gu.case_names() if n.startswith("vaddbg_")])
+def test_vad_debug_side_files_match_reference(name):
+    """-vad_out_mode debug: the side files next to the decision file (criterion, threshold and its state per written row,
+    init flags, unfiltered decisions), assembled from ctu_plan_fetch_vad_debug like the CLI does, against the files the
+    reference binary wrote.  Characters bit for bit; doubles to 1e-9 relative (the criterion of the energy mode is a sum
+    over an fp32 spectrum on the device, fp64 in the reference: 1e-6 of the undecibeled value; dB values ~1e-8)."""
+    c = gu.Case(name)
+    args = c.oracle_args()
+    ins = gu.inputs()
+    idx = [i for i in range(len(ins)) if c.debug[i]]
+    hd = cb.Handle(args)
+    plan = hd.plan([len(ins[i]) for i in idx])
+    res = plan.run_host(np.ascontiguousarray(np.concatenate([ins[i] for i in idx]).astype(np.int16)))
+    steps, vad0 = plan.fetch_vad_debug()
+    for j, i in enumerate(idx):
+        r0, r1 = int(res.row_offsets[j]), int(res.row_offsets[j + 1])
+        files = cb.vad_debug_files(hd.cfg, steps[r0:r1], vad0[r0:r1])
+        want = c.debug[i]
+        assert sorted(files) == sorted(want), (name, i, sorted(files), sorted(want))
+        for suf, wb in want.items():
+            gb = files[suf]
+            assert len(gb) == len(wb), (name, i, suf, len(gb), len(wb))
+            if suf in ("vad0", "c0init", "init"):
+                assert gb == wb, (name, i, suf, "flags differ")
+            else:
+                g, w_ = np.frombuffer(gb, dtype="<f8"), np.frombuffer(wb, dtype="<f8")
+                np.testing.assert_allclose(g, w_, rtol=2e-5, atol=1e-6, err_msg="%s input %d file _%s" % (name, i, suf))
+    plan.close(); hd.close()
+
+
 def test_batch_position_independence_and_ragged_lengths():
     """An utterance's output does not depend on where it sits in the list (what makes
     utterance sharding exact, SURVEY.md finding 4), including ragged lengths and a
