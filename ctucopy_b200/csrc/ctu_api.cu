@@ -156,6 +156,9 @@ struct ctu_plan {
     float *d_fea = nullptr;
     uint8_t *d_ext = nullptr, *d_vadnr_out = nullptr, *d_vad_out = nullptr;
     bool host_bufs = false;
+    int row_format = 0;                  // CTU_ROWS_*: layout of the rows the host entry points hand back
+    uint32_t sent0 = 0;                  // pfile rows: sentence number of the plan's first utterance
+    uint32_t *d_fmt = nullptr;           // pfile rows on the device [rows x (dim + 2)]
     std::vector<void *> blocks;          // this plan's blocks of the handle's pool
 };
 
@@ -1361,6 +1364,8 @@ static int run_host_impl(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad
         if ((st = dev_alloc(h, p, &p->d_vad_out, (size_t)p->total_frames))) return st;
         p->host_bufs = true;
     }
+    if (p->row_format == CTU_ROWS_PFILE && !p->d_fmt && !h->signal_out &&
+        (st = dev_alloc(h, p, &p->d_fmt, (size_t)p->total_frames * (h->feature_dim + 2) + 8))) return st;
     if (codes) {
         if (!p->d_codes && (st = dev_alloc(h, p, &p->d_codes, (size_t)p->total_samples + 16))) return st;
         int16_t *&tab = h->d_g711[alaw ? 1 : 0];
@@ -1415,9 +1420,21 @@ static int run_host_impl(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad
             if ((st = run_range(p, r, p->d_pcm - base, ext_vad ? p->d_ext : nullptr, p->d_fea, p->d_wave, p->d_vadnr_out, p->d_vad_out, s))) goto drain;
         }
         if (keep) { u0 = u1; ci++; continue; }             // results stay on the device (ctu_plan_fetch brings them back)
-        if (!h->signal_out && r.nrows)
-            CKL(cudaMemcpyAsync(features + r.row0 * h->feature_dim, p->d_fea + r.row0 * h->feature_dim,
-                                (size_t)r.nrows * h->feature_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (!h->signal_out && r.nrows) {
+            const void *srcp = p->d_fea + r.row0 * h->feature_dim;
+            size_t row_bytes = (size_t)h->feature_dim * sizeof(float);
+            if (p->row_format != CTU_ROWS_NATIVE && r.t64_n > 0 && !h->copy_only) {
+                // container rows formatted on the device: the host writer is left with one fwrite per utterance (or batch)
+                const bool pf = p->row_format == CTU_ROWS_PFILE;
+                BatchDesc bd64{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tiles64 + r.t64_0};
+                h->lc.begin("k_format_rows", s);
+                k_format_rows<<<(unsigned)r.t64_n, 256, 0, s>>>(bd64, h->feature_dim, pf ? 1 : 0, p->sent0, p->d_fea, pf ? p->d_fmt : reinterpret_cast<uint32_t *>(p->d_fea));
+                h->lc.end(s);
+                CKL(cudaGetLastError());
+            }
+            if (p->row_format == CTU_ROWS_PFILE) { row_bytes += 8; srcp = p->d_fmt + r.row0 * (h->feature_dim + 2); }
+            CKL(cudaMemcpyAsync(reinterpret_cast<char *>(features) + (size_t)r.row0 * row_bytes, srcp, (size_t)r.nrows * row_bytes, cudaMemcpyDeviceToHost, s));
+        }
         if (h->signal_out) {
             int64_t o0 = p->osamp_off[u0], on = p->osamp_off[u1] - o0;
             CKL(cudaMemcpyAsync(waveform + o0, p->d_wave + o0, on * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
@@ -1592,6 +1609,20 @@ int ctu_run(ctu_handle *h, const int16_t *pcm, const int64_t *off, int32_t n, co
     if (!st && rows_per_utt) ctu_plan_rows_per_utt(p, rows_per_utt);
     ctu_plan_destroy(p);
     return st;
+}
+
+int ctu_plan_set_row_format(ctu_plan *p, int format, uint32_t first_sentence) {
+    if (!p) return CTU_ERR_CONFIG;
+    ctu_handle *h = p->h;
+    if (format != CTU_ROWS_NATIVE && format != CTU_ROWS_BE && format != CTU_ROWS_PFILE) return fail(h, CTU_ERR_CONFIG, "CTU: unknown row format");
+    if (format != CTU_ROWS_NATIVE && (h->signal_out || h->fea_in)) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: row formats apply to feature output from sample input");
+    p->row_format = format;
+    p->sent0 = first_sentence;
+    return CTU_OK;
+}
+int64_t ctu_plan_row_bytes(const ctu_plan *p) {
+    if (!p) return 0;
+    return (int64_t)sizeof(float) * (p->h->feature_dim + (p->row_format == CTU_ROWS_PFILE ? 2 : 0));
 }
 
 int ctu_plan_fetch_vad_debug(ctu_plan *p, double *steps, uint8_t *vad0) {

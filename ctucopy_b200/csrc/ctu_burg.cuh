@@ -42,7 +42,7 @@ __device__ __forceinline__ double group_sum16d_all(double v) {
     return v;
 }
 
-template <int CH, bool EXACT, int MINB, bool GENA, int CLR = 1, bool PERSIST = true>
+template <int CH, bool EXACT, int MINB, bool GENA, int CLR = 2, bool PERSIST = false>
 __global__ void __launch_bounds__(BURG_THREADS, MINB)
 k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, int nhalf, const int16_t *__restrict__ pcm, const float *__restrict__ spec,
        double *__restrict__ ceps, const double2 *__restrict__ g_tw256, const double2 *__restrict__ g_twsplit,
@@ -237,8 +237,10 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, int nha
             // The reference's sums run over i >= ik (src/vdet/Burg.h:64-68).  Elements below ik can only belong to thread 0
             // (ik <= 15 < CH); they are kept at exact zeros instead of being masked out of the sums: thread 0 starts with
             // ef[0] = 0 and takes `below` = 0, which makes eb[ik-1] come out 0 by itself, and ef[ik] is cleared after stage
-            // ik.  (Masking the 16 candidates in every stage's sums cost 96 selects per stage: 17 % of the kernel's
-            // instructions in the first ncu capture of this version.)
+            // ik.  CLR selects how (measured on 3.99 M frames, B200, k_burg alone): 0 = mask the 16 candidates in every
+            // stage's sums instead (96 selects per stage) 20.5 ms; 1 = a jump on the stage number 22.6 ms (the indirect branch
+            // costs more than it saves and spills); 2 = a select chain over the 15 candidates 18.7 ms -- kept.  PERSIST
+            // (tables staged once per CTA, half tiles walked with stride gridDim.x) lost 2 ms in each case -- not kept.
             if (CLR != 0 && c == 0) ef[0] = 0.0;
             double a_c = (c == 0) ? 1.0 : 0.0, aa_c = a_c;            // thread i holds a_i
             // the stage loop stays rolled: unrolled 15 times the kernel was 14 k instructions and stalled on instruction fetch
@@ -444,31 +446,13 @@ int launch_burg(const BurgParams &B, int src_mode, const BatchDesc &bd, int64_t 
     size_t bytes = burg_smem_bytes(B.window, B.wshift);
     if (bytes > 227 * 1024) { err = "CTU: window shift too large for the Burg detector kernel"; return CTU_ERR_UNSUPPORTED; }
     cudaError_t e;
-    int per_sm = 1, num_sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     lc->begin("k_burg", s);
 #define CTU_BURG_LAUNCH2(CH, EX, MB, GA)                                                                               \
     e = cudaFuncSetAttribute(k_burg<CH, EX, MB, GA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);           \
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_burg<CH, EX, MB, GA>, BURG_THREADS, bytes);                   \
     if (e == cudaSuccess)                                                                                                  \
-        k_burg<CH, EX, MB, GA><<<(unsigned)std::min<int64_t>(2 * ntiles, (int64_t)std::max(per_sm, 1) * num_sms), BURG_THREADS, bytes, s>>>(       \
-            B, src_mode, bd, (int)(2 * ntiles), pcm, spec, ceps, tw, ts, ti, win, hann)
-#define CTU_BURG_LAUNCH3(CH, EX, MB, GA, CL, PE)                                                                       \
-    e = cudaFuncSetAttribute(k_burg<CH, EX, MB, GA, CL, PE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);   \
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_burg<CH, EX, MB, GA, CL, PE>, BURG_THREADS, bytes); \
-    if (e == cudaSuccess)                                                                                                  \
-        k_burg<CH, EX, MB, GA, CL, PE><<<(unsigned)(PE ? std::min<int64_t>(2 * ntiles, (int64_t)std::max(per_sm, 1) * num_sms) : 2 * ntiles), BURG_THREADS, bytes, s>>>( \
-            B, src_mode, bd, (int)(2 * ntiles), pcm, spec, ceps, tw, ts, ti, win, hann)
+        k_burg<CH, EX, MB, GA><<<(unsigned)(2 * ntiles), BURG_THREADS, bytes, s>>>(B, src_mode, bd, (int)(2 * ntiles), pcm, spec, ceps, tw, ts, ti, win, hann)
 #define CTU_BURG_LAUNCH(CH, EX, MB)                                                                                    \
-    if (gena) { CTU_BURG_LAUNCH2(CH, EX, 2, true); }                                                                   \
-    else if (CH == 25 && EX && variant == 0) { CTU_BURG_LAUNCH3(25, true, MB, false, 0, false); }                      \
-    else if (CH == 25 && EX && variant == 1) { CTU_BURG_LAUNCH3(25, true, MB, false, 1, false); }                      \
-    else if (CH == 25 && EX && variant == 2) { CTU_BURG_LAUNCH3(25, true, MB, false, 2, false); }                      \
-    else if (CH == 25 && EX && variant == 10) { CTU_BURG_LAUNCH3(25, true, MB, false, 0, true); }                      \
-    else if (CH == 25 && EX && variant == 12) { CTU_BURG_LAUNCH3(25, true, MB, false, 2, true); }                      \
-    else { CTU_BURG_LAUNCH2(CH, EX, MB, false); }
-    static const int variant = getenv("CTU_BURG_VARIANT") ? atoi(getenv("CTU_BURG_VARIANT")) : 11;
+    if (gena) { CTU_BURG_LAUNCH2(CH, EX, 2, true); } else { CTU_BURG_LAUNCH2(CH, EX, MB, false); }
     // the general exponent only matters where the detector's input is expanded (NR source, hwss / fwss)
     const bool gena = (src_mode == BURG_SRC_NR && B.expand && B.a_kind == 0);
     // 25 samples per thread: 128 registers = four CTAs per SM; 32 samples per thread (window up to 512): three

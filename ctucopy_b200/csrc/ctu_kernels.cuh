@@ -786,6 +786,29 @@ k_lpc(const __grid_constant__ FrameParams P, int64_t row0, int64_t nrows, const 
     if (P.c0_last) o[N] = (float)cc[0];
 }
 
+// Container rows on the device: what pfileOUT / htkOUT do per value on the host (src/io/pfile.cc:470-539:
+// rows of big-endian u32 sentence, u32 frame, float32 x dim; src/io/out.cc:189-213: byte-swapped floats for -endian_out
+// big).  One CTA per 64-row tile; `out` may alias `fea` when only the byte order changes (same row pitch).
+//   pfile != 0: out rows are dim + 2 words, sentence = sent0 + utterance index, frame = row index within the utterance
+static __global__ void __launch_bounds__(256)
+k_format_rows(BatchDesc bd, int dim, int pfile, uint32_t sent0, const float *fea, uint32_t *out) {
+    const int2 tile = bd.tiles[blockIdx.x];
+    const int u = tile.x, t0 = tile.y;
+    const int nr = min(DELTA_ROWS_C, bd.nframes[u] - t0);
+    const int64_t row0 = bd.row_off[u] + t0;
+    const int od = dim + (pfile ? 2 : 0);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(fea) + row0 * dim;
+    uint32_t *dst = out + row0 * od;
+    for (int i = threadIdx.x; i < nr * od; i += blockDim.x) {
+        const int r = i / od, col = i - r * od;
+        uint32_t v;
+        if (pfile && col == 0) v = sent0 + (uint32_t)u;
+        else if (pfile && col == 1) v = (uint32_t)(t0 + r);
+        else v = src[r * dim + col - (pfile ? 2 : 0)];
+        dst[i] = __byte_perm(v, 0, 0x0123);
+    }
+}
+
 // one thread per utterance writes that utterance's tile descriptors
 // (the non-template kernels of this header are `static`: it is included by several translation units)
 static __global__ void k_build_tiles(const int *__restrict__ nframes, const int64_t *__restrict__ tile_off, int n_utts, int tile_f,

@@ -79,6 +79,7 @@ struct Writers {
     const ctu_config &c;
     int dim;
     FILE *pf = nullptr, *ark = nullptr, *scp = nullptr;
+    bool rows_formatted = false;   // the rows arrive in container layout (ctu_plan_set_row_format): big-endian floats / pfile rows
     std::vector<uint32_t> sent_table{0};
     uint64_t pf_frames = 0;
     Writers(const HostOpts &o_, const ctu_config &c_, int dim_) : o(o_), c(c_), dim(dim_) {
@@ -120,7 +121,9 @@ struct Writers {
             uint16_t size = (uint16_t)(4 * dim), kind = (uint16_t)parmkind(list_index);
             if (o.big_out) { frames = bswap32(frames); period = bswap32(period); size = bswap16(size); kind = bswap16(kind); }
             std::fwrite(&frames, 4, 1, f); std::fwrite(&period, 4, 1, f); std::fwrite(&size, 2, 1, f); std::fwrite(&kind, 2, 1, f);
-            if (o.big_out) {
+            if (o.big_out && rows_formatted) {
+                std::fwrite(rows, 4, (size_t)n * dim, f);             // byte-swapped on the device
+            } else if (o.big_out) {
                 std::vector<uint32_t> t((size_t)n * dim);
                 std::memcpy(t.data(), rows, t.size() * 4);
                 for (auto &v : t) v = bswap32(v);
@@ -133,7 +136,8 @@ struct Writers {
             // rows: u32 sentence, u32 frame, float32 x dim, all big-endian (src/io/pfile.cc:470-539)
             std::vector<uint32_t> row(dim + 2);
             uint32_t sid = (uint32_t)sent_table.size() - 1;
-            for (int64_t t = 0; t < n; t++) {
+            if (rows_formatted) std::fwrite(rows, 4 * (size_t)(dim + 2), (size_t)n, pf);      // whole rows from the device
+            else for (int64_t t = 0; t < n; t++) {
                 row[0] = bswap32(sid); row[1] = bswap32((uint32_t)t);
                 std::memcpy(row.data() + 2, rows + t * dim, (size_t)dim * 4);
                 for (int i = 0; i < dim; i++) row[2 + i] = bswap32(row[2 + i]);
@@ -546,6 +550,10 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
     const std::string fo(cfg.format_out);
     const bool per_file = (fo == "htk" || sig);
     Writers W(ho, cfg, dim);
+    // pfile rows and byte-swapped HTK rows are laid out by the device; the writers then copy whole rows
+    const int row_fmt = (sig || fea_in) ? CTU_ROWS_NATIVE : (fo == "pfile") ? CTU_ROWS_PFILE : (fo == "htk" && ho.big_out) ? CTU_ROWS_BE : CTU_ROWS_NATIVE;
+    const int row_words = dim + (row_fmt == CTU_ROWS_PFILE ? 2 : 0);
+    W.rows_formatted = row_fmt != CTU_ROWS_NATIVE;
     // sizes first: batch boundaries and every file's offset are known before anything is read
     const size_t nfiles = r1 - r0;
     std::vector<int64_t> nsamp(nfiles);
@@ -619,7 +627,7 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
                 auto one = [&](size_t u) {
                     const ListEntry &e = list[B.i0 + u];
                     if (sig) W.waveform(e, wav + s0[u], s0[u + 1] - s0[u]);
-                    else W.features(e, fea + row0[u] * dim, B.rows[u], B.i0 + u);
+                    else W.features(e, fea + row0[u] * row_words, B.rows[u], B.i0 + u);
                     if (do_vad && vad_file) W.vad(e, vout + row0[u], B.frames[u]);
                     if (vad_dbg) W.vad_debug(e, B.vdbg.data() + row0[u] * CTU_VAD_DEBUG_COLS, B.vad0.data() + row0[u], B.frames[u]);
                 };
@@ -640,7 +648,7 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
             Batch &B = slots[k % 3];
             { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return B.state == 1 || !err.empty(); }); if (!err.empty()) break; }
             const int n = (int)(B.i1 - B.i0);
-            if (!sig) B.fea.reserve((uint64_t)B.total * dim * 4);
+            if (!sig) B.fea.reserve((uint64_t)B.total * row_words * 4);
             if (sig) B.wav.reserve((uint64_t)B.total_os * 2);
             B.vout.reserve((uint64_t)B.total + 1); B.vnr.reserve((uint64_t)B.total + 1);
             const uint8_t *ev = nullptr;
@@ -649,9 +657,10 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
                 ev = extvad.data() + B.ext_pos;
             }
             double tg = now_s();
-            if (fea_in || g711 || vad_dbg) {
+            if (fea_in || g711 || vad_dbg || row_fmt != CTU_ROWS_NATIVE) {
                 ctu_plan *pl = nullptr;
                 if (ctu_plan_create(h, B.off.data(), n, &pl)) die(ctu_last_error(h));
+                if (row_fmt != CTU_ROWS_NATIVE && ctu_plan_set_row_format(pl, row_fmt, (uint32_t)(B.i0 - r0))) { ctu_plan_destroy(pl); die(ctu_last_error(h)); }
                 const int st = fea_in ? ctu_plan_run_host_fea(pl, (const float *)B.pcm.p, (float *)B.fea.p)
                                : g711 ? ctu_plan_run_host_g711(pl, (const uint8_t *)B.pcm.p, ho.format_in == "alaw", ev, sig ? nullptr : (float *)B.fea.p,
                                                                sig ? (int16_t *)B.wav.p : nullptr, (uint8_t *)B.vnr.p, (uint8_t *)B.vout.p)

@@ -217,6 +217,20 @@ int ctu_run(ctu_handle *h, const int16_t *pcm, const int64_t *utt_offsets, int32
  * ((window - wshift) + frames * wshift per file).                                                                  */
 int ctu_set_rand_offset(ctu_handle *h, uint64_t values_drawn);
 
+/* Container rows formatted on the device: what the reference's writers do value by value on the host.
+ *   CTU_ROWS_NATIVE  float32 rows in host byte order (default)
+ *   CTU_ROWS_BE      byte-swapped float32 rows: HTK -endian_out big (src/io/out.cc:189-213)
+ *   CTU_ROWS_PFILE   pfile rows (src/io/pfile.cc:470-539): big-endian u32 sentence, u32 frame, float32 x dim; the sentence
+ *                    number of the plan's first utterance is first_sentence, frames count from 0 per utterance (rows kept
+ *                    by -vad_apply_mode drop are numbered as written)
+ * Applies to the `features` buffer of ctu_plan_run_host / _run_host_g711, which must then hold ctu_plan_max_rows() x
+ * ctu_plan_row_bytes() bytes; row r of utterance u starts at byte (first row of u + r) x row_bytes.                    */
+#define CTU_ROWS_NATIVE 0
+#define CTU_ROWS_BE 1
+#define CTU_ROWS_PFILE 2
+int ctu_plan_set_row_format(ctu_plan *p, int format, uint32_t first_sentence);
+int64_t ctu_plan_row_bytes(const ctu_plan *p);
+
 /* -vad_out_mode debug (FileWriter and the save_frame members of the criterion / threshold classes, src/vad/vad.h:39-76,
  * src/vad/vad.cc:91-111, 212-286, 324-335, 375-404, 456-508, 565-634): the values behind the reference's side files
  * <vadfile>_vad0, _energy | _cepdist (+ _c0init), _thr and the threshold's own files.  Per VAD step of every utterance

@@ -77,6 +77,29 @@ def test_cli_ark_scp_and_multi_sentence_pfile(tmp_path):
     assert "-num_sentences 3\n" in meta["header"] and ("-num_frames %d\n" % sum(T)) in meta["header"]
 
 
+def test_cli_vad_debug_side_files(tmp_path):
+    """-vad_out_mode debug through the CLI: the same set of side files as the reference binary (names = <vadfile>_<suffix>),
+    flag files byte-identical, doubles within the device's resolution."""
+    for name in ("vaddbg_perc", "vaddbg_adapt_cepdist_lpc"):
+        c = gu.Case(name)
+        idx = [0, 4, 5]
+        run_cli(str(tmp_path), c.args, [gu.inputs()[i] for i in idx], vad_out=True)
+        for j, i in enumerate(idx):
+            want = c.debug[i]
+            have = sorted(f[len("u%d.vad_" % j):] for f in os.listdir(tmp_path) if f.startswith("u%d.vad_" % j))
+            assert have == sorted(want), (name, i, have)
+            assert open(tmp_path / ("u%d.vad" % j), "rb").read() == c.aux[i], (name, i, "decision file")
+            for suf, wb in want.items():
+                gb = open(tmp_path / ("u%d.vad_%s" % (j, suf)), "rb").read()
+                assert len(gb) == len(wb), (name, i, suf)
+                if suf in ("vad0", "c0init", "init"):
+                    assert gb == wb, (name, i, suf)
+                else:
+                    np.testing.assert_allclose(np.frombuffer(gb, "<f8"), np.frombuffer(wb, "<f8"), rtol=2e-5, atol=1e-6)
+        for f in os.listdir(tmp_path):
+            os.remove(tmp_path / f)
+
+
 def test_cli_waveform_and_vad_files(tmp_path):
     for name in ("exten_raw", "exten_wave_a1"):
         c = gu.Case(name)
