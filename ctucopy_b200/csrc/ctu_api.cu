@@ -1662,6 +1662,7 @@ int ctu_host_alloc(void **ptr, uint64_t bytes) {
     return CTU_OK;
 }
 void ctu_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+int ctu_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
 
 int ctu_debug_spectrum(ctu_plan *p, const int16_t *d_pcm, float *d_spec, void *stream) {
     if (!p) return CTU_ERR_CONFIG;

@@ -698,7 +698,7 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
 // that mode is refused.)  The device does the column sums and the normalisation; the host groups the
 // utterances by speaker in list order and owns the file.
 void process_cmvn(const HostOpts &ho, const ctu_config &cfg, const std::vector<ListEntry> &list, int device,
-                  const std::vector<unsigned char> &extvad) {
+                  const std::vector<unsigned char> &extvad, int ngpus = 1) {
     const bool apply = !ho.apply_cmvn.empty();
     const std::string statfile = apply ? ho.apply_cmvn : ho.stat_cmvn;
     if (apply) {
@@ -723,8 +723,17 @@ void process_cmvn(const HostOpts &ho, const ctu_config &cfg, const std::vector<L
         if (j == names.size()) names.push_back(id);
         spk[i] = (int)j;
     }
-    ctu_handle *h = nullptr;
-    if (ctu_create(&cfg, device, &h)) die(ctu_last_error(nullptr));
+    // -gpus N: one handle and one worker thread per GPU; the batches of a pass are dealt to the workers.  What a batch
+    // contributes is kept PER UTTERANCE and added up on the host in list order after the pass, so the statistics (and the
+    // text of the statistics file) are the single-process ones bit for bit, whatever the number of GPUs or their timing:
+    // the one cross-GPU reduction of the path is a host-side sum of n_utts x dim doubles.
+    const int G = std::max(1, ngpus);
+    const std::string fo(cfg.format_out);
+    if (G > 1 && apply && fo != "htk") die("CTU: -apply_cmvn under -gpus N writes one HTK file per utterance; pfile / ark containers need one process");
+    std::vector<ctu_handle *> hs((size_t)G, nullptr);
+    for (int g = 0; g < G; g++)
+        if (ctu_create(&cfg, G > 1 ? g % std::max(1, ctu_device_count()) : device, &hs[(size_t)g])) die(ctu_last_error(nullptr));
+    ctu_handle *h = hs[0];
     const int fdim = ctu_feature_dim(h), dim = ctu_cmvn_dim(h);
     const int in_dim = ctu_input_dim(h);          // > 0: feature files in (-format_in htk)
     const bool fea_in = in_dim > 0;
@@ -732,75 +741,92 @@ void process_cmvn(const HostOpts &ho, const ctu_config &cfg, const std::vector<L
     std::vector<int64_t> nsamp(list.size());
     parallel_for(list.size(), IO_THREADS, [&](size_t i) { nsamp[i] = count_samples(ho, list[i].in); });
     std::vector<size_t> cuts{0};
+    // samples per batch (64 Mi by default; CTU_CMVN_BATCH_SAMPLES lets a test cut a short list into several batches)
+    const int64_t batch_samples = std::getenv("CTU_CMVN_BATCH_SAMPLES") ? std::max<long long>(1, std::atoll(std::getenv("CTU_CMVN_BATCH_SAMPLES"))) : (int64_t(1) << 26);
     {
         int64_t acc = 0;
         for (size_t i = 0; i < list.size(); i++) {
             acc += fea_in ? nsamp[i] * in_dim * 2 : nsamp[i];
-            if (acc >= (int64_t(1) << 26)) { cuts.push_back(i + 1); acc = 0; }
+            if (acc >= batch_samples) { cuts.push_back(i + 1); acc = 0; }
         }
         if (cuts.back() != list.size()) cuts.push_back(list.size());
     }
+    const size_t nbatch = cuts.size() - 1;
+    // frames of the batches before each batch (external VAD bytes are one list-wide stream)
+    std::vector<int64_t> nfr(list.size());
+    for (size_t i = 0; i < list.size(); i++) { nfr[i] = ctu_num_frames(h, nsamp[i]); if (nfr[i] < 0) die("IO: Signal shorter than one frame!"); }
+    std::vector<size_t> fr_before(nbatch + 1, 0);
+    for (size_t k = 0; k < nbatch; k++) { size_t t = 0; for (size_t i = cuts[k]; i < cuts[k + 1]; i++) t += (size_t)nfr[i]; fr_before[k + 1] = fr_before[k] + t; }
     const size_t ns = names.size();
     std::vector<double> sum(ns * dim, 0.0), var(ns * dim, 0.0), cnt(ns, 0.0);
-    Pinned pcmbuf, feabuf;
+    std::vector<double> per_utt(list.size() * (size_t)dim, 0.0);       // what each utterance adds in the current pass
     Writers W(ho, cfg, fdim);
     for (int pass = 0; pass < (apply ? 3 : 2); pass++) {
-        size_t fr_before = 0;
-        for (size_t k = 0; k + 1 < cuts.size(); k++) {
-            const size_t i0 = cuts[k], i1 = cuts[k + 1], n = i1 - i0;
-            std::vector<int64_t> off(n + 1, 0), frames(n);
-            int64_t total = 0;
-            for (size_t u = 0; u < n; u++) {
-                off[u + 1] = off[u] + nsamp[i0 + u];
-                frames[u] = ctu_num_frames(h, nsamp[i0 + u]);
-                if (frames[u] < 0) die("IO: Signal shorter than one frame!");
-                total += frames[u];
-            }
-            pcmbuf.reserve(fea_in ? (uint64_t)(off[n] + 1) * in_dim * 4 : (uint64_t)(off[n] + 8) * 2);
-            int16_t *pcm = (int16_t *)pcmbuf.p;
-            float *fin = (float *)pcmbuf.p;
-            parallel_for(n, IO_THREADS, [&](size_t u) {
-                if (fea_in) read_features_into(ho, cfg, list[i0 + u].in, fin + off[u] * in_dim, off[u + 1] - off[u]);
-                else decode_into(ho, cfg.fs, list[i0 + u].in, pcm + off[u], off[u + 1] - off[u]);
-            });
-            const uint8_t *ev = nullptr;
-            if (use_ext) {
-                if (fr_before + (size_t)total > extvad.size()) die("NR: Unexpected end of VAD file!");
-                ev = extvad.data() + fr_before;
-            }
-            fr_before += (size_t)total;
-            ctu_plan *p = nullptr;
-            if (ctu_plan_create(h, off.data(), (int)n, &p)) die(ctu_last_error(h));
-            if (fea_in ? ctu_plan_run_host_fea(p, fin, nullptr) : ctu_plan_run_host_keep(p, pcm, ev)) die(ctu_last_error(h));
-            std::vector<double> a(n * dim), b(n * dim);
-            if (pass == 0) {
-                if (ctu_plan_colsums(p, nullptr, a.data())) die(ctu_last_error(h));
-                for (size_t u = 0; u < n; u++) {
-                    const int j = spk[i0 + u];
-                    for (int c = 0; c < dim; c++) sum[(size_t)j * dim + c] += a[u * dim + c];
-                    cnt[j] += (double)frames[u];
+        std::atomic<size_t> next{0};
+        std::vector<std::string> errs((size_t)G);
+        auto worker = [&](int g) {
+            try {
+                ctu_handle *hg = hs[(size_t)g];
+                Pinned pcmbuf, feabuf;
+                for (size_t k; (k = next.fetch_add(1)) < nbatch;) {
+                    const size_t i0 = cuts[k], i1 = cuts[k + 1], n = i1 - i0;
+                    std::vector<int64_t> off(n + 1, 0), frames(n);
+                    int64_t total = 0;
+                    for (size_t u = 0; u < n; u++) { off[u + 1] = off[u] + nsamp[i0 + u]; frames[u] = nfr[i0 + u]; total += frames[u]; }
+                    pcmbuf.reserve(fea_in ? (uint64_t)(off[n] + 1) * in_dim * 4 : (uint64_t)(off[n] + 8) * 2);
+                    int16_t *pcm = (int16_t *)pcmbuf.p;
+                    float *fin = (float *)pcmbuf.p;
+                    parallel_for(n, std::max(1, IO_THREADS / G), [&](size_t u) {
+                        if (fea_in) read_features_into(ho, cfg, list[i0 + u].in, fin + off[u] * in_dim, off[u + 1] - off[u]);
+                        else decode_into(ho, cfg.fs, list[i0 + u].in, pcm + off[u], off[u + 1] - off[u]);
+                    });
+                    const uint8_t *ev = nullptr;
+                    if (use_ext) {
+                        if (fr_before[k] + (size_t)total > extvad.size()) die("NR: Unexpected end of VAD file!");
+                        ev = extvad.data() + fr_before[k];
+                    }
+                    ctu_plan *p = nullptr;
+                    if (ctu_plan_create(hg, off.data(), (int)n, &p)) die(ctu_last_error(hg));
+                    if (fea_in ? ctu_plan_run_host_fea(p, fin, nullptr) : ctu_plan_run_host_keep(p, pcm, ev)) die(ctu_last_error(hg));
+                    std::vector<double> a(n * dim), b(n * dim);
+                    if (pass == 0) {
+                        if (ctu_plan_colsums(p, nullptr, per_utt.data() + i0 * dim)) die(ctu_last_error(hg));
+                    } else if (pass == 1) {
+                        for (size_t u = 0; u < n; u++) std::copy(sum.begin() + (size_t)spk[i0 + u] * dim, sum.begin() + (size_t)(spk[i0 + u] + 1) * dim, a.begin() + u * dim);
+                        if (ctu_plan_colsums(p, a.data(), per_utt.data() + i0 * dim)) die(ctu_last_error(hg));
+                    } else {
+                        for (size_t u = 0; u < n; u++) {
+                            std::copy(sum.begin() + (size_t)spk[i0 + u] * dim, sum.begin() + (size_t)(spk[i0 + u] + 1) * dim, a.begin() + u * dim);
+                            std::copy(var.begin() + (size_t)spk[i0 + u] * dim, var.begin() + (size_t)(spk[i0 + u] + 1) * dim, b.begin() + u * dim);
+                        }
+                        if (ctu_plan_normalise(p, a.data(), b.data())) die(ctu_last_error(hg));
+                        feabuf.reserve((uint64_t)total * fdim * 4);
+                        if (ctu_plan_fetch(p, (float *)feabuf.p, nullptr, nullptr, nullptr)) die(ctu_last_error(hg));
+                        int64_t r0 = 0;
+                        for (size_t u = 0; u < n; u++) { W.features(list[i0 + u], (const float *)feabuf.p + r0 * fdim, frames[u], i0 + u); r0 += frames[u]; }
+                    }
+                    ctu_plan_destroy(p);
                 }
-            } else if (pass == 1) {
-                for (size_t u = 0; u < n; u++) std::copy(sum.begin() + (size_t)spk[i0 + u] * dim, sum.begin() + (size_t)(spk[i0 + u] + 1) * dim, a.begin() + u * dim);
-                if (ctu_plan_colsums(p, a.data(), b.data())) die(ctu_last_error(h));
-                for (size_t u = 0; u < n; u++)
-                    for (int c = 0; c < dim; c++) var[(size_t)spk[i0 + u] * dim + c] += b[u * dim + c];
-            } else {
-                for (size_t u = 0; u < n; u++) {
-                    std::copy(sum.begin() + (size_t)spk[i0 + u] * dim, sum.begin() + (size_t)(spk[i0 + u] + 1) * dim, a.begin() + u * dim);
-                    std::copy(var.begin() + (size_t)spk[i0 + u] * dim, var.begin() + (size_t)(spk[i0 + u] + 1) * dim, b.begin() + u * dim);
-                }
-                if (ctu_plan_normalise(p, a.data(), b.data())) die(ctu_last_error(h));
-                feabuf.reserve((uint64_t)total * fdim * 4);
-                if (ctu_plan_fetch(p, (float *)feabuf.p, nullptr, nullptr, nullptr)) die(ctu_last_error(h));
-                int64_t r0 = 0;
-                for (size_t u = 0; u < n; u++) { W.features(list[i0 + u], (const float *)feabuf.p + r0 * fdim, frames[u], i0 + u); r0 += frames[u]; }
-            }
-            ctu_plan_destroy(p);
+            } catch (const std::exception &e) { errs[(size_t)g] = e.what(); if (errs[(size_t)g].empty()) errs[(size_t)g] = "unknown error"; next = nbatch; }
+        };
+        if (G == 1) worker(0);
+        else {
+            std::vector<std::thread> th;
+            for (int g = 0; g < G; g++) th.emplace_back(worker, g);
+            for (auto &t : th) t.join();
         }
+        for (auto &e : errs) if (!e.empty()) die(e);
+        // the pass's sums, utterance by utterance in list order (cmvn_POST::sum_fea / sum_cv, src/fea/post_impl.cc:52-97)
         if (pass == 0) {
+            for (size_t i = 0; i < list.size(); i++) {
+                const int j = spk[i];
+                for (int c = 0; c < dim; c++) sum[(size_t)j * dim + c] += per_utt[i * dim + c];
+                cnt[j] += (double)nfr[i];
+            }
             for (size_t j = 0; j < ns; j++) for (int c = 0; c < dim; c++) sum[j * dim + c] /= cnt[j];       // sum -> mean (stat_cm)
         } else if (pass == 1) {
+            for (size_t i = 0; i < list.size(); i++)
+                for (int c = 0; c < dim; c++) var[(size_t)spk[i] * dim + c] += per_utt[i * dim + c];
             for (size_t j = 0; j < ns; j++) for (int c = 0; c < dim; c++) var[j * dim + c] /= (cnt[j] - 1);  // stat_cv
             // statistics file (cmvnOUT::save_frame, src/io/out.cc:591-615) in the reference's order: the
             // internal vector F[1..], then F[0] -- c0 of the static block goes last, everything else stays.  Stacked rows
@@ -828,7 +854,7 @@ void process_cmvn(const HostOpts &ho, const ctu_config &cfg, const std::vector<L
         }
     }
     W.close();
-    ctu_destroy(h);
+    for (auto *x : hs) ctu_destroy(x);
 }
 
 int run(int argc, char **argv) {
@@ -900,8 +926,8 @@ int run(int argc, char **argv) {
     if (!std::strcmp(cfg.vadmode, "file")) extvad = slurp(ho.filevad, "NR: Unable to open VAD file!\n");
     const int nparts = ho.gpus > 1 ? ho.gpus : ho.shard_n;
     if (!ho.stat_cmvn.empty() || !ho.apply_cmvn.empty()) {
-        if (nparts != 1) die("CTU: CMVN statistics span the whole list: run it in one process (no -gpus / -shard)");
-        process_cmvn(ho, cfg, list, ho.device < 0 ? 0 : ho.device, extvad);
+        if (ho.shard_n != 1) die("CTU: CMVN statistics span the whole list: run it in one process (-gpus N uses N GPUs from one process; -shard cannot)");
+        process_cmvn(ho, cfg, list, ho.device < 0 ? 0 : ho.device, extvad, ho.gpus);
         return 0;
     }
     if (nparts == 1) {
@@ -934,7 +960,7 @@ int run(int argc, char **argv) {
     std::vector<std::thread> th;
     for (int r = 0; r < nparts; r++)
         th.emplace_back([&, r]() {
-            try { process_range(shard_opts(r), cfg, list, cut[r], cut[r + 1], r, extvad, frames_before[cut[r]], drawn_before[cut[r]]); }
+            try { process_range(shard_opts(r), cfg, list, cut[r], cut[r + 1], r % std::max(1, ctu_device_count()), extvad, frames_before[cut[r]], drawn_before[cut[r]]); }
             catch (const std::exception &e) { errs[r] = e.what(); if (errs[r].empty()) errs[r] = "unknown error"; }
         });
     for (auto &t : th) t.join();

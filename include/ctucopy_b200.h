@@ -256,6 +256,7 @@ int ctu_set_option(ctu_handle *h, const char *name, int64_t value);
  * makes every chunk copy synchronous and several times slower.  (What rawIN's fread buffer and the
  * writers' obuffer are to the reference, src/io/in.cc:434-460, src/io/out.cc:95-106.)            */
 int ctu_host_alloc(void **ptr, uint64_t bytes);
+int ctu_device_count(void);                      /* CUDA devices visible to this process (0 = none: nothing can run)  */
 void ctu_host_free(void *ptr);
 
 /* Debug / test taps (device-resident, synchronous): intermediate stages of one plan run. */

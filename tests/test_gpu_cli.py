@@ -198,6 +198,30 @@ def test_cli_cmvn_statistics_and_normalised_features(tmp_path, name):
         assert pr.returncode == 255 and b"existing statistics file" in pr.stderr
 
 
+def test_cli_cmvn_under_gpus_is_the_single_process_result(tmp_path):
+    """CMVN with -gpus 2 (two worker threads and handles; both on device 0 when the box has one GPU): per-utterance column
+    sums are added on the host in list order, so the statistics file and the normalised feature files are BYTE-identical
+    to the one-GPU run, whatever the split."""
+    args, idx, spk, stat, outs = gu.cmvn_case("cmvn_3stage_d_a")
+    ins = gu.inputs()
+    many = idx * 6                                   # 24 utterances, 4 speakers' worth of repeats
+    res = {}
+    for g in (1, 2):
+        d = tmp_path / ("g%d" % g); d.mkdir()
+        for n, i in enumerate(many):
+            ins[i].astype("<i2").tofile(d / ("u%d.raw" % n))
+        with open(d / "list.scp", "w") as fh:
+            for n, i in enumerate(many):
+                fh.write("%s/u%d.raw %s/u%d.htk %s\n" % (d, n, d, n, spk[idx.index(i)] + str(n % 3)))
+        a = [x.replace("{STAT}", str(d / "cmvn.stat")) for x in args]
+        env = dict(os.environ, CTU_CMVN_BATCH_SAMPLES="60000")       # several batches, so that both workers get some
+        pr = subprocess.run([EXE] + a + ["-S", str(d / "list.scp")] + (["-gpus", "2"] if g == 2 else []), capture_output=True, env=env)
+        assert pr.returncode == 0, pr.stderr.decode()
+        res[g] = (open(d / "cmvn.stat", "rb").read(), [open(d / ("u%d.htk" % n), "rb").read() for n in range(len(many))])
+    assert res[1][0] == res[2][0], "statistics text differs between -gpus 1 and -gpus 2"
+    assert res[1][1] == res[2][1], "normalised features differ between -gpus 1 and -gpus 2"
+
+
 def test_cli_feature_file_input_and_stacking_headers(tmp_path):
     """-format_in htk through the command line: stacked rows byte-identical to the reference's files (a pure gather), delta
     rows within tolerance with byte-exact headers -- including the reference's parmKind quirks (the decimal "T bit", and
