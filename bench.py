@@ -220,6 +220,51 @@ def run_reference_arm(a):
     return 0
 
 
+def cli_run(workload, n_utts):
+    """File -> file through the command-line host (host/ctucopy_b200: decode -> pinned buffers -> library -> writers, three
+    overlapped stages) on /dev/shm: SURVEY 8f.1.  Returns the wall-clock rate of a whole process run (CUDA start-up
+    included), and the steady-state rate from the stage times the host prints under CTU_TIMING=1."""
+    import re
+    from ctucopy_b200 import synthetic
+    exe = os.path.join(ROOT, "host", "ctucopy_b200")
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    d = tempfile.mkdtemp(prefix="ctu_cli_", dir=base)
+    try:
+        os.makedirs(d + "/in"); os.makedirs(d + "/out")
+        uniq = [synthetic.utterance(k, 10.0).astype("<i2").tobytes() for k in range(16)]
+        for i in range(n_utts):
+            with open("%s/in/u%05d.raw" % (d, i), "wb") as fh:
+                fh.write(uniq[i % 16])
+        args = [a.replace("out.ark", d + "/o.ark").replace("out.pfile", d + "/o.pfile") for a in WORKLOADS[workload][0]]
+        with open(d + "/list.scp", "w") as fh:
+            for i in range(n_utts):
+                fh.write("%s/in/u%05d.raw %s/out/u%05d.out\n" % (d, i, d, i))
+        fpu = frames_per_utt(workload)
+        runs = []
+        for rep in range(2):
+            t0 = time.perf_counter()
+            pr = subprocess.run([exe] + args + ["-S", d + "/list.scp"], capture_output=True, text=True, env=dict(os.environ, CTU_TIMING="1"))
+            dt = time.perf_counter() - t0
+            if pr.returncode != 0:
+                return {"error": "CLI exit %d: %s" % (pr.returncode, pr.stderr.strip()[-200:])}
+            st = {}
+            for m in re.finditer(r"\[ctu timing\] (.+?)\s+([0-9.]+) s", pr.stderr):
+                st.setdefault(m.group(1).strip(), []).append(float(m.group(2)))
+            runs.append((dt, st))
+        dt, st = runs[-1]
+        nb = len(st.get("batch ctu_run", [])) or 1
+        # steady state: the slowest of the three overlapped stages, per batch (the first batch, which pays the allocations,
+        # left out when there are several)
+        per_stage = {k: (statistics.median(v[1:]) if len(v) > 2 else statistics.median(v)) for k, v in st.items() if k.startswith("batch")}
+        slow = max(per_stage.values()) if per_stage else None
+        return {"workload": workload, "files": n_utts, "frames": n_utts * fpu, "where": base, "wall_s": dt, "frames_per_s_whole_run": n_utts * fpu / dt,
+                "startup_s": (st.get("ctu_create (CUDA init)") or [None])[0], "batches": nb, "stage_s_per_batch": per_stage,
+                "frames_per_s_steady": (n_utts * fpu / nb) / slow if slow else None, "first_run_wall_s": runs[0][0],
+                "note": "second of two runs; steady = frames per batch / slowest overlapped stage (read+decode | library call | write)"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def selfcheck(workload, args, plan, hd, d_out, lens, uniq, first, sig):
     """Correctness at bench scale, outside the timed region: (1) utterance n-1 holds the same samples as utterance
     (n-1) % uniq, so their outputs must be bit-identical although they sit at opposite ends of the batch (2.56e9
@@ -276,6 +321,7 @@ def main():
     ap.add_argument("--others", default="auto", choices=["auto", "all", "none"],
                     help="the other BASELINE configs under 'workloads': auto = all of them on one GPU, PLP only under torchrun")
     ap.add_argument("--no-selfcheck", action="store_true")
+    ap.add_argument("--cli-utts", type=int, default=4000, help="10 s files for the file -> file run of the command-line host (0 = skip)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
@@ -492,6 +538,14 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
+    if rank == 0 and world == 1 and a.cli_utts > 0:
+        try:
+            line["cli"] = cli_run(a.workload, a.cli_utts)
+            cb_ = line.get("cpu_baseline") or {}
+            if cb_.get("value") and line["cli"].get("frames_per_s_whole_run"):
+                line["cli"]["vs_cpu_reference_whole_run"] = line["cli"]["frames_per_s_whole_run"] / cb_["value"]
+        except Exception as e:      # reported, never fatal for the headline
+            line["cli"] = {"error": "%s: %s" % (type(e).__name__, e)}
     # ---- the other BASELINE configs, measured the same way with fewer steps (BASELINE.json configs 1, 2, 3, 4, 5)
     names = []
     if a.others == "all" or (a.others == "auto" and world == 1):
