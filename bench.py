@@ -56,6 +56,10 @@ WORKLOADS = {
                        "-format_out", "pfile=out.pfile"], 380, 70000),
     # MFCC_0 with +-2 frames of context stacked per coefficient (13 -> 65 columns)
     "mfcc_trap5": (B + ["-preset", "mfcc", "-preem", "0.97", "-fea_trap", "5", "-format_out", "htk"], 320 + 260, 18000),
+    # SURVEY 8f.4 (egs/conf/20): 24 time-domain IIR band filters -> windowed band energies -> log -> DCT; 30 ms / 10 ms; the
+    # coefficient file is the committed test fixture (the reference ships none)
+    "tdiir": (B + ["-format_out", "htk", "-w", "30", "-s", "10", "-nr_mode", "none", "-fea_kind", "td-iir-mfcc",
+                   "-filters", os.path.join(ROOT, "tests", "golden", "tdiir_filters.asc"), "-fea_ncepcoefs", "12"], 320 + 52, 160 * 24 * 24),
 }
 DEFAULT_WORKLOAD = "mfcc_exten"
 
@@ -73,6 +77,7 @@ def kernel_alg_bytes(name, hop, dim, nb):
         "k_synth": pcm + 4 * 257 + pcm, "k_burg": pcm + 8 * 16, "k_cepdet": 8 * 16 + 1,
         "k_stack": 4 * 13 + 4 * dim,          # static block read once, stacked row written once
         "k_synth_c": 8 * 257 + 4 * 257 + pcm,  # stored complex spectrum + enhanced magnitudes in, one hop of int16 out
+        "k_tdiir_filter": pcm + 8 * 24, "k_tdiir_frames": 3 * 8 * 24 + 4 * dim,   # one segment of 24 band energies per hop (30 / 10 ms)
     }.get(name)
 
 
@@ -170,7 +175,7 @@ def cpu_reference_run(workload, utt_files, per_proc, cores, tmp, opt="O2"):
 
 
 def frames_per_utt(workload, nsamp=160000):
-    w, s = (512, 256) if workload == "exten" else (400, 160)
+    w, s = (512, 256) if workload == "exten" else (480, 160) if workload == "tdiir" else (400, 160)
     return (nsamp - (w - s)) // s
 
 
@@ -549,7 +554,7 @@ def main():
     # ---- the other BASELINE configs, measured the same way with fewer steps (BASELINE.json configs 1, 2, 3, 4, 5)
     names = []
     if a.others == "all" or (a.others == "auto" and world == 1):
-        names = [w for w in ("plp", "mfcc_d_a", "exten", "trapdct", "fwss_burg") if w != a.workload]
+        names = [w for w in ("plp", "mfcc_d_a", "exten", "trapdct", "fwss_burg", "tdiir") if w != a.workload]
     elif a.others == "auto":
         names = [w for w in ("plp",) if w != a.workload]
     others = {}

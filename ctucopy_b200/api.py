@@ -17,7 +17,7 @@ import numpy as np
 
 CTU_STR = 40
 CTU_FBDEF = 1024
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class CtuError(RuntimeError):
@@ -69,6 +69,7 @@ class Config(C.Structure):
         ("fea_Z_exp", C.c_float), ("fea_Z_block", C.c_float), ("cms_exp_coef", C.c_float),
         ("stat_cmvn", C.c_int32), ("apply_cmvn", C.c_int32),
         ("fea_trap", C.c_int32), ("trap_win", C.c_int32), ("fea_in", C.c_int32), ("nfeacoefs", C.c_int32),
+        ("filters", C.c_char * 1024), ("weight_of_td_iir_mfcc_bank", C.c_float),
     ]
 
 

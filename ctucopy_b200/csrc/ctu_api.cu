@@ -19,6 +19,7 @@
 #include "ctu_frames_any.cuh"
 #include "ctu_nr_params.cuh"
 #include "ctu_precise.cuh"
+#include "ctu_tdiir.cuh"
 #include "ctu_bank.cuh"
 #include "ctu_synth_any.cuh"
 
@@ -95,6 +96,9 @@ struct ctu_handle {
     bool precise = false;
     std::vector<double> w64, m264, lift64;
     double *d_w64 = nullptr, *d_m264 = nullptr, *d_lift64 = nullptr;
+    // -fea_kind td-iir-mfcc (ctu_tdiir.cuh)
+    TdiirParams tdp{};
+    double *d_td_coefs = nullptr, *d_td_win = nullptr, *d_td_dct = nullptr;
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     // device blocks of destroyed plans, kept for the next plan: a list is processed as a sequence of plans of
     // similar size, and cudaMalloc / cudaFree of gigabytes cost more than the kernels that use them
@@ -143,6 +147,7 @@ struct ctu_plan {
     uint64_t rand_base = 0;
     bool dither_ready = false;
     double *d_ceps = nullptr;            // Burg cepstra [frames x ncoef]
+    double *d_tdseg = nullptr;           // td-iir-mfcc: windowed band energies per segment of gcd(window, shift) samples
     double *d_cri = nullptr;             // VAD criterion per frame
     double *d_vdbg = nullptr;            // -vad_out_mode debug: VAD_DBG doubles per VAD step
     uint8_t *d_flags = nullptr;          // NR-internal detector decisions
@@ -530,8 +535,28 @@ static int resolve_modes(ctu_handle *h) {
     else if (kind == "lpa") h->fea_kind = FEA_LPA;
     else if (kind == "lpc") h->fea_kind = FEA_LPC;
     else if (kind == "trapdct") h->fea_kind = FEA_TRAPDCT;
-    else if (kind == "td-iir-mfcc") return fail(h, CTU_ERR_UNSUPPORTED, "CTU: td-iir-mfcc is outside this hot path (SURVEY 8f.4)");
+    else if (kind == "td-iir-mfcc") h->fea_kind = FEA_TDIIR;
     else return fail(h, CTU_ERR_CONFIG, "FEA: Unknown feature kind!");
+    if (kind == "td-iir-mfcc") {
+        // BATCH::BATCH, src/io/batch.cc:28, 61-62: no NR, no FB, no FEA, no deltaFEA, no POST, no VAD object -- IN's 13-element
+        // vector goes straight to the writer (process_frame :221-222).  What the reference does NOT survive is refused:
+        if (h->signal_out) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: td-iir-mfcc with waveform output (the reference hands its 13 cepstra to the synthesis)");
+        if (c.fea_in) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: td-iir-mfcc with feature-file input");
+        if (c.fea_ncepcoefs != 12)
+            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: td-iir-mfcc needs -fea_ncepcoefs 12 (the reference writes 13 coefficients into a vector of fea_ncepcoefs+1, src/io/in.cc:168-170, 328)");
+        if (!c.fea_c0) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: td-iir-mfcc with -fea_c0 off (the writer's last column is never set, src/io/out.cc:95-112, 189-200)");
+        if (c.fea_E) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: td-iir-mfcc with -fea_E (no energy is computed on this branch, src/io/in.cc:317-340)");
+        if (c.fea_delta && c.n_order > 0)
+            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: td-iir-mfcc with deltas / stacking (the reference calls a deltaFEA it never built, src/io/batch.cc:217-218)");
+        if (c.stat_cmvn || c.apply_cmvn) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: td-iir-mfcc with CMVN (no POST object exists on this branch)");
+        if (std::string(c.vad_apply_mode) != "none" || std::string(c.vad_out_mode) != "none")
+            return fail(h, CTU_ERR_UNSUPPORTED, "CTU: td-iir-mfcc with the VAD module (the reference dereferences a VAD it never built, src/io/batch.cc:230-232)");
+        if (c.window > 4096) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: td-iir-mfcc with a window longer than 4096 samples");
+        // noise reduction, dither, DC removal, pre-emphasis and CMS never run on this branch (src/io/in.cc:430-436): ignored
+        h->nr_mode = NR_NONE; h->vad_src = VADSRC_NONE; h->do_vad = false; h->fea_in = false;
+        h->nbins = c.wfftby2; h->spitch = h->nbins;
+        return CTU_OK;
+    }
     if (nr == "none") h->nr_mode = NR_NONE;
     else if (nr == "exten") h->nr_mode = NR_EXTEN;
     else if (nr == "hwss") h->nr_mode = NR_HWSS;
@@ -618,6 +643,50 @@ static int resolve_modes(ctu_handle *h) {
     return CTU_OK;
 }
 
+// rawIN::loadf_filters (src/io/in.cc:242-262): one filter per line, ten TAB-separated numbers parsed with atof; the
+// reference reads lines until the file ends (past its 24 rows when there are more) and hands strtok's NULL to atof when a
+// line is short -- both refused here.  Host tables of the td-iir-mfcc path (ctu_tdiir.cuh).
+static int build_tdiir(ctu_handle *h, std::vector<double> &coefs, std::vector<double> &win, std::vector<double> &dct) {
+    const ctu_config &c = h->cfg;
+    FILE *f = std::fopen(c.filters, "r");
+    if (!f) return fail(h, CTU_ERR_INPUT, std::string("IN: Cannot open the filter coefficient file '") + c.filters + "' (-filters)");
+    coefs.assign(TDIIR_BANDS * 10, 0.0);
+    char line[1000];
+    int nf = 0;
+    while (nf < TDIIR_BANDS && std::fgets(line, sizeof(line), f)) {
+        char *save = nullptr;
+        char *tok = strtok_r(line, "\t", &save);
+        for (int i = 0; i < 10; i++) {
+            if (!tok) { std::fclose(f); return fail(h, CTU_ERR_INPUT, "IN: a line of the filter coefficient file has fewer than 10 TAB-separated numbers"); }
+            coefs[nf * 10 + i] = std::atof(tok);
+            tok = strtok_r(nullptr, "\t", &save);
+        }
+        nf++;
+    }
+    std::fclose(f);
+    if (nf < TDIIR_BANDS) return fail(h, CTU_ERR_INPUT, "IN: the filter coefficient file holds fewer than 24 filters");
+    const int w = c.window, s = c.wshift;
+    win.resize(w);
+    const double pi = 2. * asin(1.);
+    for (int j = 0; j < w; j++) win[j] = 0.54 - (1 - 0.54) * cos(2 * pi * j / (w - 1.));       // src/io/in.cc:139-144
+    // wdct[i] = cos(pi i / 48), used at index (2k-1) i % 96 (src/io/in.cc:236-237, 330-333)
+    dct.resize(TDIIR_NCEP * TDIIR_BANDS);
+    for (int i = 0; i < TDIIR_NCEP; i++)
+        for (int k = 1; k <= TDIIR_BANDS; k++)
+            dct[i * TDIIR_BANDS + (k - 1)] = cos(3.14159265358979 * (double)(((2 * k - 1) * i) % (4 * TDIIR_BANDS)) / (2 * TDIIR_BANDS));
+    int a = w, b = s;
+    while (b) { const int t = a % b; a = b; b = t; }
+    TdiirParams &P = h->tdp;
+    P.window = w; P.wshift = s; P.seg = a; P.spf = w / a; P.sps = s / a;
+    // samples staged per step: the largest length up to TDIIR_CHUNK that is a multiple or a divisor of the segment
+    int L = TDIIR_CHUNK;
+    while (L > 1 && (L % a) != 0 && (a % L) != 0) L--;
+    P.chunk = L; P.run = std::min(a, L);
+    P.weight = (double)c.weight_of_td_iir_mfcc_bank;
+    h->static_dim = h->feature_dim = h->work_dim = TDIIR_NCEP;
+    return CTU_OK;
+}
+
 int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     if (!cfg || !out) { g_create_err = "CTU: null argument"; return CTU_ERR_CONFIG; }
     *out = nullptr;
@@ -633,6 +702,27 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     int st = ctu_config_finalize(&h->cfg);
     if (st) { h->err = ctu_config_error(); return bail(st); }
     if ((st = resolve_modes(h))) return bail(st);
+    if (h->fea_kind == FEA_TDIIR) {
+        std::vector<double> coefs, win, dct;
+        std::memset(&h->fp, 0, sizeof(h->fp)); std::memset(&h->dp, 0, sizeof(h->dp)); std::memset(&h->skp, 0, sizeof(h->skp));
+        h->skp.L = 1;                                // no delta chain, no stacking on this branch
+        if ((st = build_tdiir(h, coefs, win, dct))) return bail(st);
+        int ndev = 0;
+        cudaError_t ce = cudaGetDeviceCount(&ndev);
+        if (ce != cudaSuccess || ndev == 0 || device >= ndev) {
+            h->err = std::string("CUDA: no usable device (") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device index out of range") +
+                     "); libctucopy_b200 has no CPU fallback";
+            return bail(CTU_ERR_CUDA);
+        }
+        if (cudaSetDevice(device) != cudaSuccess) { h->err = "CUDA: cudaSetDevice failed"; return bail(CTU_ERR_CUDA); }
+        cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+        if ((st = upload(h, &h->d_td_coefs, coefs)) || (st = upload(h, &h->d_td_win, win)) || (st = upload(h, &h->d_td_dct, dct))) return bail(st);
+        h->tdp.coefs = h->d_td_coefs; h->tdp.win = h->d_td_win; h->tdp.dct = h->d_td_dct;
+        for (int i = 0; i < 3; i++)
+            if (cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking) != cudaSuccess) { h->err = "CUDA: stream creation failed"; return bail(CTU_ERR_CUDA); }
+        *out = h;
+        return CTU_OK;
+    }
     if (!h->signal_out && !h->fea_in) {
         std::string e = ctu_design_fb(h->cfg, h->fb);
         if (!e.empty()) { h->err = e; return bail(CTU_ERR_CONFIG); }
@@ -728,6 +818,7 @@ void ctu_destroy(ctu_handle *h) {
     cudaFree(h->d_g711[0]); cudaFree(h->d_g711[1]);
     cudaFree(h->d_any_tw); cudaFree(h->d_any_ts); cudaFree(h->d_any_fbw); cudaFree(h->d_any_bands);
     cudaFree(h->bank.d_bands); cudaFree(h->bank.d_w4); cudaFree(h->bank.d_m2);
+    cudaFree(h->d_td_coefs); cudaFree(h->d_td_win); cudaFree(h->d_td_dct);
     for (auto &b : h->pool) cudaFree(b.p);
     for (int i = 0; i < 3; i++) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     h->lc.clear();
@@ -845,6 +936,12 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     if (h->gather && !h->fea_in && (st = dev_alloc(h, p, &p->d_static, (size_t)rows * h->static_dim))) { ctu_plan_destroy(p); return st; }
     if (h->work_dim != h->feature_dim && (st = dev_alloc(h, p, &p->d_work, (size_t)rows * h->work_dim))) { ctu_plan_destroy(p); return st; }
     if (h->fea_in) { *out = p; return CTU_OK; }
+    if (h->fea_kind == FEA_TDIIR) {
+        const size_t nseg = (size_t)(rows * h->tdp.sps + (int64_t)n * (h->tdp.spf - h->tdp.sps));
+        if ((st = dev_alloc(h, p, &p->d_tdseg, nseg * TDIIR_BANDS + 1)) || (st = dev_alloc(h, p, &p->d_flags, (size_t)rows + 1))) { ctu_plan_destroy(p); return st; }
+        *out = p;
+        return CTU_OK;
+    }
     const bool nr_on = h->nr_mode != NR_NONE;
     // PCM -> spectrum (k_frames2, 4-5 CTAs per SM) followed by spectrum -> features is faster than the single fused kernel
     // (2 CTAs per SM) even though the spectrum then makes a round trip through HBM -- measured 12.4 -> 11.4 ms (MFCC_0_D_A),
@@ -1137,6 +1234,9 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     BatchDesc bd64{p->d_pcm_off, p->d_nframes, p->d_row_off, p->d_tiles64 + r.t64_0};
     FrameTiles ft{p->d_tiles32 + r.t32_0, r.t32_n, p->d_tilesF + r.tF_0, r.tF_n};
     int st;
+    if (h->fea_kind == FEA_TDIIR)        // time-domain IIR filter bank -> band energies -> log -> DCT (ctu_tdiir.cuh)
+        return launch_tdiir(h->tdp, bd64, r.t64_n, p->d_pcm_off, p->d_nframes, p->d_row_off, r.u0, r.u1, d_pcm, p->d_tdseg, d_fea, h->feature_dim, s,
+                            &h->lc, h->err);
     const int kind = kind_of(h);
     uint8_t *flags = d_vadnr ? d_vadnr : p->d_flags;
 
@@ -1397,6 +1497,9 @@ static int run_host_impl(ctu_plan *p, const int16_t *pcm, const uint8_t *ext_vad
     while (u0 < p->n_utts) {
         int u1 = u0 + 1;
         while (u1 < p->n_utts && p->offsets[u1 + 1] - p->offsets[u0] <= chunk_samples) u1++;
+        // td-iir-mfcc: the filter recurrence is sequential along an utterance, its parallelism is utterances x 24 bands --
+        // a chunk must hold enough utterances to fill the device (five CTAs of four utterances per SM), whatever their size
+        if (h->fea_kind == FEA_TDIIR) u1 = std::max(u1, std::min(p->n_utts, u0 + 20 * h->num_sms));
         cudaStream_t s = h->streams[ci % 3];
         Range r = make_range(p, u0, u1);
         int64_t so = p->offsets[u0] - base, sn = p->offsets[u1] - p->offsets[u0];

@@ -19,8 +19,8 @@ namespace ctu {
 //     partner's value arrives by shuffle, the rebuilt pair is written back over the registers it came from.  (Round 1
 //     materialised lo[8] / hi[8] / zn[8] next to a[16]: 236 registers, two CTAs per SM, FP64 pipe 41 % busy.)
 //   * lattice: sample i = c*CH + j lives in thread c's registers.  All updates and sums are unconditional; the elements the
-//     reference no longer reads (i < ik, src/vdet/Burg.h:64-68) are driven to exact zeros instead of being masked (see the
-//     stage loop).
+//     reference no longer reads (i < ik, src/vdet/Burg.h:64-68) are driven to exact zeros instead of being masked, and where
+//     the window fills the threads exactly the denominator is carried from stage to stage (see the stage loop).
 //   * the predictor coefficients are distributed (thread i holds a_i; one shuffle per stage).
 // CH: samples per thread; EXACT: window == 16*CH (no tail masking in the energy sums); GENA: the spectral exponent is not 1
 // or 2 (-nr_a): only that instantiation carries pow() -- inlined at the 17 bin sites of a thread it costs the common paths
@@ -42,7 +42,7 @@ __device__ __forceinline__ double group_sum16d_all(double v) {
     return v;
 }
 
-template <int CH, bool EXACT, int MINB, bool GENA, int CLR = 2, bool PERSIST = false>
+template <int CH, bool EXACT, int MINB, bool GENA, bool REC = EXACT>
 __global__ void __launch_bounds__(BURG_THREADS, MINB)
 k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, int nhalf, const int16_t *__restrict__ pcm, const float *__restrict__ spec,
        double *__restrict__ ceps, const double2 *__restrict__ g_tw256, const double2 *__restrict__ g_twsplit,
@@ -64,15 +64,13 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, int nha
         sWin[i] = (i < w) ? g_win[i] : 0.0;
         sHann[i] = (i < w) ? ((src_mode == BURG_SRC_NR) ? g_hann[i] : 1.0) : 0.0;
     }
-    // persistent CTAs: the tables above are staged once, the half tiles are walked with stride gridDim.x
-#pragma unroll 1
-    for (int ht = blockIdx.x; ht < nhalf; ht += (PERSIST ? gridDim.x : nhalf)) {
+    {
+    const int ht = blockIdx.x;
     const int2 tile = bd.tiles[ht >> 1];
     const int u = tile.x, t0 = tile.y + (ht & 1) * BURG_HALF;
     const int nf = min(BURG_HALF, bd.nframes[u] - t0);
-    if (nf <= 0) continue;                                   // (uniform over the CTA)
+    if (nf <= 0) return;                                     // (uniform over the CTA)
     const int64_t row0 = bd.row_off[u] + t0;
-    __syncthreads();                                          // the previous half tile's samples are no longer read
     // samples [first-1, first + nsamp): the one before the tile feeds the first pre-emphasis
     const int nsamp = (nf - 1) * s + w + 1;
     const bool at_start = (t0 == 0);
@@ -233,37 +231,62 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, int nha
                 ef[j] = eb[j] = v;
                 en += v * v;
             }
-            double alpha = group_sum16d_all(en) * inv_w;
+            const double en_all = group_sum16d_all(en);
+            double alpha = en_all * inv_w;
             // The reference's sums run over i >= ik (src/vdet/Burg.h:64-68).  Elements below ik can only belong to thread 0
             // (ik <= 15 < CH); they are kept at exact zeros instead of being masked out of the sums: thread 0 starts with
             // ef[0] = 0 and takes `below` = 0, which makes eb[ik-1] come out 0 by itself, and ef[ik] is cleared after stage
-            // ik.  CLR selects how (measured on 3.99 M frames, B200, k_burg alone): 0 = mask the 16 candidates in every
-            // stage's sums instead (96 selects per stage) 20.5 ms; 1 = a jump on the stage number 22.6 ms (the indirect branch
-            // costs more than it saves and spills); 2 = a select chain over the 15 candidates 18.7 ms -- kept.  PERSIST
-            // (tables staged once per CTA, half tiles walked with stride gridDim.x) lost 2 ms in each case -- not kept.
-            if (CLR != 0 && c == 0) ef[0] = 0.0;
+            // ik by a select chain over the 15 candidates.  (Measured alternatives, 3.99 M frames, k_burg alone: masking the
+            // 16 candidates in every stage's sums 20.5 ms, a jump on the stage number 22.6 ms, the select chain 18.7 ms;
+            // persistent CTAs lost 2 ms in each case.  DESIGN 10 has the later attempt with one "head" sample per thread.)
+            //
+            // REC: the denominator is carried from stage to stage instead of being summed again.  With
+            //   ef'[i] = ef[i] + rc eb[i-1],  eb'[i] = eb[i-1] + rc ef[i],  rc = -2 num / den:
+            //   sum_{i>=ik} (ef'[i]^2 + eb'[i]^2) = (1 + rc^2) den + 4 rc num = (1 - rc^2) den,   so
+            //   den_{ik+1} = sum_{i>=ik+1} ef'[i]^2 + sum_{i>=ik} eb'[i]^2 - eb'[N-1]^2 = (1 - rc^2) den_ik - ef'[ik]^2 - eb'[N-1]^2
+            // (Andersen 1978): one sum (num) instead of three per sample and stage, 3 DFMA instead of 5.  A rounding error of
+            // num or den is amplified by ~2 rc^2 / (1 - rc^2) per stage, i.e. the carried value drifts from the direct sum by
+            // ~1e-16 / (accumulated prediction gain); when that gain since the last direct sum passes 1e3 the stage sums den
+            // directly again (warp-uniform branch), which bounds the drift at ~1e-13.
+            const double v_first = shfl16d(ef[0], 0), v_last = shfl16d(ef[CH - 1], 15);
+            double den_c = 2.0 * en_all - v_first * v_first - v_last * v_last;       // stage 1: ef = eb = v
+            double gain_c = 1.0;
+            if (c == 0) ef[0] = 0.0;
             double a_c = (c == 0) ? 1.0 : 0.0, aa_c = a_c;            // thread i holds a_i
             // the stage loop stays rolled: unrolled 15 times the kernel was 14 k instructions and stalled on instruction fetch
 #pragma unroll 1
             for (int ik = 1; ik < ncoef; ik++) {
                 double below = shfl16d(eb[CH - 1], (c + 15) & 15);         // eb of sample i-1 across the thread boundary
-                if (CLR != 0 && c == 0) below = 0.0;
-                const int dead = (CLR == 0 && c == 0) ? ik : 0;
-                // three independent chains per parity: the sums are latency-bound otherwise
-                double nu[2] = {0, 0}, df[2] = {0, 0}, db[2] = {0, 0};
+                if (c == 0) below = 0.0;
+                double num, den;
+                if (!REC || __any_sync(0xffffffffu, gain_c < 1e-3)) {
+                    // three independent chains per parity: the sums are latency-bound otherwise
+                    double nu[2] = {0, 0}, df[2] = {0, 0}, db[2] = {0, 0};
 #pragma unroll
-                for (int j = 0; j < CH; j++) {
-                    const double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
-                    if ((EXACT || c * CH + j < w) && (CLR != 0 || j >= BURG_MAXC || j >= dead)) {
-                        df[j & 1] = fma(ef[j], ef[j], df[j & 1]);
-                        db[j & 1] = fma(pv, pv, db[j & 1]);
-                        nu[j & 1] = fma(ef[j], pv, nu[j & 1]);
+                    for (int j = 0; j < CH; j++) {
+                        const double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
+                        if (EXACT || c * CH + j < w) {
+                            df[j & 1] = fma(ef[j], ef[j], df[j & 1]);
+                            db[j & 1] = fma(pv, pv, db[j & 1]);
+                            nu[j & 1] = fma(ef[j], pv, nu[j & 1]);
+                        }
                     }
+                    num = group_sum16d_all(nu[0] + nu[1]) * 2.0;
+                    den = group_sum16d_all((df[0] + df[1]) + (db[0] + db[1]));
+                    gain_c = 1.0;
+                } else {
+                    double nu[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int j = 0; j < CH; j++) {
+                        const double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
+                        nu[j & 3] = fma(ef[j], pv, nu[j & 3]);
+                    }
+                    num = group_sum16d_all((nu[0] + nu[1]) + (nu[2] + nu[3])) * 2.0;
+                    den = den_c;
                 }
-                const double num = group_sum16d_all(nu[0] + nu[1]) * 2.0;
-                const double den = group_sum16d_all((df[0] + df[1]) + (db[0] + db[1]));
                 const double rc = -num / den;
-                alpha *= 1 - rc * rc;
+                const double om = 1 - rc * rc;
+                alpha *= om;
 #pragma unroll
                 for (int j = CH - 1; j >= 0; j--) {
                     const double pv = (j > 0) ? eb[j > 0 ? j - 1 : 0] : below;
@@ -271,20 +294,14 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, int nha
                     ef[j] = e0 + rc * pv;
                     eb[j] = pv + rc * e0;
                 }
-                // ef[ik] leaves the sums
-                if (CLR == 1) {
-                    if (c == 0) {
-                        switch (ik) {
-#define CTU_CLR(J) case J: if (J < CH) ef[J < CH ? J : 0] = 0.0; break;
-                            CTU_CLR(1) CTU_CLR(2) CTU_CLR(3) CTU_CLR(4) CTU_CLR(5) CTU_CLR(6) CTU_CLR(7) CTU_CLR(8)
-                            CTU_CLR(9) CTU_CLR(10) CTU_CLR(11) CTU_CLR(12) CTU_CLR(13) CTU_CLR(14) CTU_CLR(15)
-#undef CTU_CLR
-                            default: break;
-                        }
-                    }
-                } else if (CLR == 2) {
+                // ef[ik] leaves the sums (its value is what the carried denominator loses)
+                double gone = 0.0;
 #pragma unroll
-                    for (int j = 1; j < BURG_MAXC && j < CH; j++) if (c == 0 && j == ik) ef[j] = 0.0;
+                for (int j = 1; j < BURG_MAXC && j < CH; j++) if (c == 0 && j == ik) { gone = ef[j]; ef[j] = 0.0; }
+                if (REC) {
+                    const double e_first = shfl16d(gone, 0), b_last = shfl16d(eb[CH - 1], 15);
+                    den_c = om * den - e_first * e_first - b_last * b_last;
+                    gain_c *= om;
                 }
                 // a_i = aa_i + rc * aa_{ik-i} (0 < i < ik), a_ik = rc
                 const double other = shfl16d(aa_c, (ik - c) & 15);
@@ -312,7 +329,7 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, int nha
         }
         __syncwarp();
     }
-    }   // half tiles
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -53,6 +53,7 @@ int ctu_config_init(ctu_config *c) {
     c->fea_trapdct_traplen = 0; c->fea_trapdct_ndct = 0;  // the reference leaves these uninitialised
     c->fea_delta = 0; c->n_order = 0; c->d_win = c->a_win = c->t_win = 2;
     c->fea_trap = 0; c->trap_win = 5; c->fea_in = 0; c->nfeacoefs = 13;      // src/io/opts.cc:97-99
+    put(c->filters, "", CTU_FBDEF); c->weight_of_td_iir_mfcc_bank = 2.026f;  // src/io/opts.cc:100, 104
     put(c->vad_apply_mode, "none");
     put(c->vad_out_mode, "none");
     put(c->vad_cri_mode, "energy");
@@ -129,11 +130,11 @@ const Opt kOpts[] = {
     {"-vad_dyn_qmindec", K_DBL, O(vad_dyn_qmindec)}, {"-vad_dyn_qmininc", K_DBL, O(vad_dyn_qmininc)},
     {"-vad_filter_order", K_INT, O(vad_filter_order)},
     {"-fea_Z_exp", K_FLT, O(fea_Z_exp)}, {"-fea_Z_block", K_FLT, O(fea_Z_block)},
+    {"-weight_of_td_iir_mfcc_bank", K_FLT, O(weight_of_td_iir_mfcc_bank)},
     // owned by the host CLI, not by the hot path: accepted, no effect here
     {"-S", K_IGNORE, 0}, {"-i", K_IGNORE, 0}, {"-o", K_IGNORE, 0}, {"-C", K_IGNORE, 0},
     {"-endian_in", K_IGNORE, 0}, {"-endian_out", K_IGNORE, 0},
-    {"-vad_out", K_IGNORE, 0}, {"-filters", K_IGNORE, 0},
-    {"-weight_of_td_iir_mfcc_bank", K_IGNORE, 0}, {"-nr_rasta", K_IGNORE, 0},
+    {"-vad_out", K_IGNORE, 0}, {"-nr_rasta", K_IGNORE, 0},
     {"-online_in", K_FLAG_IGNORE, 0}, {"-online_out", K_FLAG_IGNORE, 0}, {"-fb_printself", K_FLAG_IGNORE, 0},
     {"-verbose", K_FLAG_IGNORE, 0}, {"-v", K_FLAG_IGNORE, 0}, {"-quiet", K_FLAG_IGNORE, 0},
     {"-info", K_FLAG_IGNORE, 0}, {"-h", K_FLAG_IGNORE, 0}, {"--help", K_FLAG_IGNORE, 0},
@@ -215,6 +216,7 @@ int ctu_config_set(ctu_config *c, const char *l, const char *r) {
         if (r) c->fea_in = !std::strcmp(r, "htk");
         return CTU_OK;
     }
+    if (opt == "-filters") { if (r) put(c->filters, r, CTU_FBDEF); return CTU_OK; }
     if (opt == "-nfeacoefs") { if (r) c->nfeacoefs = std::atoi(r); return CTU_OK; }
     for (const Opt &o : kOpts) {
         if (opt != o.name) continue;

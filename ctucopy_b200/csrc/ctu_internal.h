@@ -20,7 +20,7 @@ struct CtuFbDesign {
 std::string ctu_design_fb(const ctu_config &c, CtuFbDesign &out);
 
 // ---- enumerations resolved once at ctu_create ---------------------------------------------
-enum CtuFeaKind { FEA_NONE = 0, FEA_SPEC, FEA_LOGSPEC, FEA_DCTC, FEA_LPA, FEA_LPC, FEA_TRAPDCT };
+enum CtuFeaKind { FEA_NONE = 0, FEA_SPEC, FEA_LOGSPEC, FEA_DCTC, FEA_LPA, FEA_LPC, FEA_TRAPDCT, FEA_TDIIR };
 enum CtuNrMode { NR_NONE = 0, NR_EXTEN, NR_HWSS, NR_FWSS, NR_2FWSS };
 enum CtuVadSrc { VADSRC_NONE = 0, VADSRC_BURG, VADSRC_FILE };
 enum CtuVadCri { VCRI_ENERGY = 0, VCRI_CEPDIST_LPC, VCRI_CEPDIST_FEA };

@@ -366,29 +366,35 @@ k_nr_scan64(const __grid_constant__ NrParams N, const int *__restrict__ nframes,
     const uint8_t *fl = flags ? flags + row_off[u] : nullptr;
     const double p = N.pd, a = N.ad, b = (double)N.b;
     double Navg = (N.mode == NR_EXTEN) ? 0.95 : 0.0, Yavg = 0.05, Nravg = 0.0;
+    // Every product and sum below is rounded on its own (__dmul_rn / __dadd_rn / __dsub_rn: no FMA contraction), in the
+    // reference's order (src/nr/nr.cc:95-140, 224-261, 331-369, 397-442).  This path exists for fidelity: where the
+    // subtraction cancels almost everything (x - H x with H = 1 - 1e-13) the reference's result IS its rounding pattern --
+    // a fused x - H x gives the mathematically better value, 1 % away from what the reference writes (found by the
+    // 200-set sweep: TRAP-DCT of a band that exten takes from 21.9 to 1.9e-12).
+    const double omp = __dsub_rn(1.0, p);
     for (int t = 0; t < T; t++) {
         double xi = x[(int64_t)t * size];
         if (N.mode == NR_EXTEN) {
             double H;
-            if (N.a_kind == 1) H = Navg / (Navg + Yavg);
-            else if (N.a_kind == 2) H = Navg / sqrt(Navg * Navg + Yavg * Yavg);
-            else H = Navg / pow(pow(Navg, a) + pow(Yavg, a), 1. / a);
-            const double Nn = H * xi;
-            Navg = p * Navg + (1 - p) * Nn;
-            Yavg = (xi > Navg) ? xi - Navg : Navg - xi;
-            xi -= Nn;
+            if (N.a_kind == 1) H = Navg / __dadd_rn(Navg, Yavg);
+            else if (N.a_kind == 2) H = Navg / sqrt(__dadd_rn(__dmul_rn(Navg, Navg), __dmul_rn(Yavg, Yavg)));
+            else H = Navg / pow(__dadd_rn(pow(Navg, a), pow(Yavg, a)), 1. / a);
+            const double Nn = __dmul_rn(H, xi);
+            Navg = __dadd_rn(__dmul_rn(p, Navg), __dmul_rn(omp, Nn));
+            Yavg = (xi > Navg) ? __dsub_rn(xi, Navg) : __dsub_rn(Navg, xi);
+            xi = __dsub_rn(xi, Nn);
         } else {
             const int ninit = (N.mode == NR_HWSS) ? N.initsegs - (t + 1) : N.initsegs - t;
             const bool upd = (fl[t] == 0) || ninit > 0;
             if (N.mode == NR_2FWSS) {
-                if (upd) Navg = p * Navg + (1 - p) * xi;
-                xi -= Navg; if (xi < 0.) xi = -xi;
-                if (upd) Nravg = p * Nravg + (1 - p) * xi;
-                xi -= Nravg; if (xi < 0.) xi = -xi;
+                if (upd) Navg = __dadd_rn(__dmul_rn(p, Navg), __dmul_rn(omp, xi));
+                xi = __dsub_rn(xi, Navg); if (xi < 0.) xi = -xi;
+                if (upd) Nravg = __dadd_rn(__dmul_rn(p, Nravg), __dmul_rn(omp, xi));
+                xi = __dsub_rn(xi, Nravg); if (xi < 0.) xi = -xi;
             } else {
-                if (N.a_kind == 2) xi *= xi; else if (N.a_kind == 0) xi = pow(xi, a);
-                if (upd) Navg = p * Navg + (1 - p) * xi;
-                xi -= b * Navg;
+                if (N.a_kind == 2) xi = __dmul_rn(xi, xi); else if (N.a_kind == 0) xi = pow(xi, a);
+                if (upd) Navg = __dadd_rn(__dmul_rn(p, Navg), __dmul_rn(omp, xi));
+                xi = __dsub_rn(xi, __dmul_rn(b, Navg));
                 if (xi < 0.) xi = (N.mode == NR_HWSS) ? 0. : -xi;
                 if (N.a_kind == 2) xi = sqrt(xi); else if (N.a_kind == 0) xi = pow(xi, 1.0 / a);
             }

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CTU_ABI_VERSION 3
+#define CTU_ABI_VERSION 4
 #define CTU_STR 40
 #define CTU_FBDEF 1024
 
@@ -62,7 +62,7 @@ typedef struct ctu_config {
     int32_t nr_initsegs;
     int32_t nr_when;                 /* 0 = beforeFB, 1 = afterFB (opts::NRwhen)                  */
     /* parametrisation */
-    char    fea_kind[CTU_STR];       /* spec|logspec|dctc|lpa|lpc|trapdct|none                   */
+    char    fea_kind[CTU_STR];       /* spec|logspec|dctc|lpa|lpc|trapdct|td-iir-mfcc            */
     int32_t fea_lporder, fea_ncepcoefs, fea_c0, fea_E, fea_rawenergy, fea_lifter;
     int32_t fea_trapdct_traplen, fea_trapdct_ndct;
     int32_t fea_delta, n_order, d_win, a_win, t_win;
@@ -94,6 +94,10 @@ typedef struct ctu_config {
     int32_t fea_trap, trap_win;      /* -fea_trap N: rows t-(N-1)/2 .. t+(N-1)/2 stacked per coefficient     */
     int32_t fea_in;                  /* 1 = -format_in htk: the input is a feature matrix, not PCM           */
     int32_t nfeacoefs;               /* -nfeacoefs: floats per input feature row                             */
+    /* -fea_kind td-iir-mfcc (src/io/in.cc:242-262, 281-340): coefficient file of the 24 time-domain IIR band filters, one
+     * filter per line, ten TAB-separated numbers (b0..b4, input gain, a1..a4); read by ctu_create like rawIN::loadf_filters */
+    char    filters[CTU_FBDEF];
+    float   weight_of_td_iir_mfcc_bank;   /* float like the reference (src/io/opts.h:164), default 2.026          */
 } ctu_config;
 
 typedef struct ctu_handle ctu_handle;

@@ -86,6 +86,8 @@ class Opts:
     fea_trap: bool = False
     nfeacoefs: int = 13
     trap_win: int = 5
+    ffilters: str = ""                          # -filters (src/io/opts.cc:100, 705-706)
+    weight_of_td_iir_mfcc_bank: float = float(np.float32(2.026))    # C float (src/io/opts.h:164, src/io/opts.cc:104)
     vad_apply_mode: str = "none"
     vad_out_mode: str = "none"
     vad_cri_mode: str = "energy"
@@ -185,6 +187,10 @@ def _parse_one(o: Opts, l: str, r: Optional[str]) -> None:
             o.fea_trap, o.trap_win, o.fea_delta, o.n_order = True, int(r), True, 1
             o.d_win = (o.trap_win - 1) // 2
     elif l == "-nfeacoefs": o.nfeacoefs = int(r)
+    elif l == "-filters":
+        if r is not None: o.ffilters = r
+    elif l == "-weight_of_td_iir_mfcc_bank":
+        if r is not None: o.weight_of_td_iir_mfcc_bank = float(np.float32(float(r)))
     elif l == "-fs": o.fs = int(r)
     elif l == "-dither": o.dither = f(r)
     elif l == "-remove_dc": o.remove_dc = _onoff(r, o.remove_dc)
@@ -1138,9 +1144,13 @@ def nr_ss(X: np.ndarray, o: Opts, vad_flags=None, Xph: Optional[np.ndarray] = No
     return out, vout
 
 
-def apply_nr(X, o: Opts, Xph=None, vad_flags=None):
+def apply_nr(X, o: Opts, Xph=None, vad_flags=None, force_flags=None):
+    """force_flags: detector decisions to use instead of running the Burg detector (the sensitivity probe of
+    run_pipeline(perturb=...) keeps the decisions of the unperturbed run)."""
     if o.nr_mode == "none":
         return X, None
+    if force_flags is not None and o.nr_mode in ("hwss", "fwss", "2fwss"):
+        return nr_ss(X, o, vad_flags=force_flags)
     if o.nr_mode == "exten":
         return nr_exten(X, o), None
     if o.nr_mode in ("hwss", "fwss", "2fwss"):
@@ -1552,23 +1562,136 @@ def energy_column(o: Opts, fe: "FrontEnd", Xs: np.ndarray, Y: np.ndarray, kind: 
     return np.asarray(E, dtype=np.float64)[idx]
 
 
-def run_pipeline(pcm: np.ndarray, o: Opts, ext_vad: Optional[np.ndarray] = None, rand_offset: int = 0) -> Result:
-    """One utterance through the chain BATCH builds (src/io/batch.cc:24-69, 205-296)."""
+def load_iir_filters(path: str) -> np.ndarray:
+    """rawIN::loadf_filters, src/io/in.cc:242-262: one filter per line, ten TAB-separated numbers
+    (b0 b1 b2 b3 b4 | input gain | a1 a2 a3 a4); the first 24 lines are the bank."""
+    rows = []
+    with open(path) as fh:
+        for line in fh:
+            tok = line.rstrip("\n").split("\t")
+            if len(tok) < 10:
+                raise ValueError("IN: filter line with fewer than 10 coefficients (the reference hands strtok's NULL to atof)")
+            rows.append([_atof(t) for t in tok[:10]])
+            if len(rows) == 24:
+                break
+    if len(rows) < 24:
+        raise ValueError("IN: fewer than 24 filters (the reference would use coefficient rows it never set)")
+    return np.array(rows, dtype=np.float64)
+
+
+def _atof(t: str) -> float:
+    """C atof: the longest numeric prefix, 0.0 when there is none"""
+    import re
+    m = re.match(r"\s*[-+]?(\d+\.?\d*([eE][-+]?\d+)?|\.\d+([eE][-+]?\d+)?|inf(inity)?|nan)", t, re.I)
+    return float(m.group(0)) if m else 0.0
+
+
+def td_iir_mfcc(pcm: np.ndarray, o: Opts, coefs: np.ndarray) -> np.ndarray:
+    """-fea_kind td-iir-mfcc: 24 fourth-order IIR band filters in the time domain -> windowed band
+    energies per frame -> log -> 13-point DCT.  rawIN::compute_td_iir_mfcc src/io/in.cc:281-303, the td-iir branch of
+    rawIN::get_frame :317-340, tables :234-239; no pre-emphasis, no dither, no DC removal on this branch.
+    The filter state (second canonical form, Mat(24,5)) is zero at the first sample: the reference leaves column 0 of
+    its Mat unset (src/base/types.h:72) and reads it once, at the very first sample of a PROCESS; a fresh heap gives 0
+    there (the default run is byte-identical to one under MALLOC_PERTURB_=255, which zero-fills).  The state is
+    also carried from file to file of a list; like the *ss modes this path is defined per utterance (= the first file of
+    a list)."""
+    w, s = o.window, o.wshift
+    x = np.asarray(pcm, dtype=np.float64)
+    n_first = w - s
+    if len(x) < n_first:
+        raise ValueError("IO: Signal shorter than one frame!")
+    T = (len(x) - n_first) // s
+    N = n_first + T * s
+    W = hamming(w)
+    weight = float(o.weight_of_td_iir_mfcc_bank)
+    wdct = np.cos(3.14159265358979 * np.arange(4 * 24, dtype=np.float64) / (2 * 24))     # src/io/in.cc:236-237
+    normcoef = math.sqrt(2.0 / 24)
+    # filtered, windowed samples: the window weight goes by the sample's position in the circular buffer, n % window
+    # (src/io/in.cc:291-299) -- not by its position inside a frame
+    widx = np.arange(N) % w
+    # the 24 filters side by side (same operations in the same order per filter as the reference's scalar loops)
+    c = np.ascontiguousarray(coefs.T)                 # c[j] = coefficient j of every filter
+    s0 = np.zeros(24); s1 = np.zeros(24); s2 = np.zeros(24); s3 = np.zeros(24)
+    y = np.empty((N, 24), dtype=np.float64)
+    for n, xn in enumerate(x[:N].tolist()):
+        v = c[5] * xn
+        v = v - c[6] * s3
+        v = v - c[7] * s2
+        v = v - c[8] * s1
+        v = v - c[9] * s0
+        acc = c[0] * v
+        acc = acc + c[4] * s0
+        acc = acc + c[3] * s1
+        acc = acc + c[2] * s2
+        acc = acc + c[1] * s3
+        s0, s1, s2, s3 = s1, s2, s3, v
+        y[n] = acc
+    z = (y * W[widx][:, None]).T
+    out = np.empty((T, 13), dtype=np.float64)
+    for t in range(T):
+        # frame t holds samples t*s .. t*s + w - 1; the reference sums them in buffer order i = n % w (src/io/in.cc:322-324)
+        seg = z[:, t * s: t * s + w]
+        order = np.argsort((np.arange(t * s, t * s + w)) % w, kind="stable")
+        E = np.zeros(24)
+        for ff in range(24):
+            e = _seq_sum(seg[ff, order] * seg[ff, order])
+            with np.errstate(divide="ignore"):
+                E[23 - ff] = np.log((w * w * e / w) / weight)
+        for i in range(13):
+            acc = 0.0
+            for kk in range(1, 25):
+                acc += E[kk - 1] * wdct[((2 * kk - 1) * i) % (4 * 24)]
+            out[t, i] = acc * normcoef
+    return out
+
+
+def run_pipeline(pcm: np.ndarray, o: Opts, ext_vad: Optional[np.ndarray] = None, rand_offset: int = 0,
+                 perturb: Optional[Tuple[float, int]] = None, force_vad_nr: Optional[np.ndarray] = None) -> Result:
+    """One utterance through the chain BATCH builds (src/io/batch.cc:24-69, 205-296).
+    perturb = (eps, seed): CONDITIONING PROBE, not part of the reference's algorithm -- the spectrum that leaves the front
+    end is moved by eps (relative per bin, plus eps of the frame's mean level, random signs) before anything else sees it,
+    with the noise-reduction detector's decisions held at force_vad_nr.  The difference to the unperturbed output says how
+    far the result of THIS configuration on THIS input moves when its input spectrum moves by one rounding error of the
+    front end: where a spectral subtraction cancels many digits that is far more than the rounding error itself, and no
+    implementation that computes the spectrum in the stated precision can agree better (tools/parity_sweep.py).  With
+    noise reduction after the filter bank the band vector -- the subtraction's input there -- is what is moved."""
+    if o.fea_kind == "td-iir-mfcc" and o.format_out in ("htk", "pfile", "ark"):
+        # BATCH::BATCH src/io/batch.cc:61-62, process_frame :221-222: IN's vector goes straight to the writer
+        if o.fea_ncepcoefs != 12:
+            raise ValueError("CTU: td-iir-mfcc writes 13 coefficients into a vector of fea_ncepcoefs+1 (src/io/in.cc:168-170, 328)")
+        if not o.fea_c0 or o.fea_E or (o.fea_delta and o.n_order > 0) or o.stat_cmvn or o.apply_cmvn or \
+                o.vad_apply_mode != "none" or o.vad_out_mode != "none":
+            raise ValueError("CTU: td-iir-mfcc with -fea_c0 off / -fea_E / deltas / CMVN / the VAD module: the reference reads unset memory or null objects")
+        F = td_iir_mfcc(pcm, o, load_iir_filters(o.ffilters))
+        out = np.concatenate([F[:, 1:], F[:, :1]], axis=1)           # writer: c1..c12, c0 (src/io/out.cc:189-197)
+        return Result(F.shape[0], features=out.astype(np.float32))
     fe = front_end(pcm, o, rand_offset)
+
+    def _perturbed(A):
+        eps, seed = perturb
+        rng = np.random.default_rng(seed)
+        s1 = rng.choice([-1.0, 1.0], size=A.shape)
+        s2 = rng.choice([-1.0, 1.0], size=A.shape)
+        return np.abs(A * (1.0 + eps * s1) + eps * np.mean(A, axis=1, keepdims=True) * s2)
+
+    if perturb is not None and not (o.nr_when == "afterFB" and o.format_out not in ("raw", "wave")):
+        fe.Xabs = _perturbed(fe.Xabs)
     T = fe.Xabs.shape[0]
     signal_out = o.format_out in ("raw", "wave")
     if signal_out:
-        X, vnr = apply_nr(fe.Xabs, o, fe.Xph, ext_vad)
+        X, vnr = apply_nr(fe.Xabs, o, fe.Xph, ext_vad, force_vad_nr)
         return Result(T, waveform=synth(X, fe.Xph, o), vad_nr=vnr, spectrum=X)
     fb = fb_design(o)
     if o.nr_when == "afterFB":
         Y = fb_project(fe.Xabs, fb)
+        if perturb is not None:
+            Y = _perturbed(Y)                       # the subtraction's input is the band vector here
         if o.nr_mode in ("hwss", "fwss", "2fwss") and o.vadmode == "burg":
             raise ValueError("NR: Cannot use Burg detector after filter bank!")
-        Y, vnr = apply_nr(Y, o, None, ext_vad)
+        Y, vnr = apply_nr(Y, o, None, ext_vad, force_vad_nr)
         Xs = fe.Xabs
     else:
-        Xs, vnr = apply_nr(fe.Xabs, o, fe.Xph, ext_vad)
+        Xs, vnr = apply_nr(fe.Xabs, o, fe.Xph, ext_vad, force_vad_nr)
         Y = fb_project(Xs, fb)
     k = o.fea_kind
     latency = 0

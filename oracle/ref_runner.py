@@ -16,6 +16,8 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+# coefficient file of the td-iir-mfcc goldens (tests/golden/make_tdiir_filters.py)
+TDIIR_FILTERS = os.path.join(os.path.dirname(HERE), "tests", "golden", "tdiir_filters.asc")
 
 
 def ref_binary(opt: str = "O0") -> Optional[str]:
@@ -98,7 +100,7 @@ def run_reference(args: Sequence[str], pcms: List[np.ndarray], *, opt: str = "O0
                         line += " spk %s/u%d.vad" % (d, i)
                     fh.write(line + "\n")
             a = [s.replace("{ARK}", os.path.join(d, "out%d.ark" % gi)).replace("{PFILE}", os.path.join(d, "out%d.pfile" % gi))
-                 .replace("{VADIN}", os.path.join(d, "vadin.bin")) for s in args]
+                 .replace("{VADIN}", os.path.join(d, "vadin.bin")).replace("{FILTERS}", TDIIR_FILTERS) for s in args]
             pr = subprocess.run([exe] + a + ["-S", os.path.join(d, "list%d.scp" % gi)], capture_output=True, cwd=d)
             res["stderr"] += pr.stderr.decode(errors="replace")
             res["returncode"] = pr.returncode or res["returncode"]

@@ -153,6 +153,15 @@ CASES = {
     # odd window lengths inside 512-point frames (32 ms at 11.025 kHz = 353 samples): synthesis and the Burg detector
     "exten_raw_11k": (["-fs", "11025"] + B[2:] + ["-preset", "exten", "-format_out", "raw"], "raw", {}),
     "fwss_burg_11k": (["-fs", "11025"] + B[2:] + MF + ["-w", "32", "-s", "16", "-nr_mode", "fwss", "-vad", "burg", "-format_out", "htk"], "htk", {}),
+    # -fea_kind td-iir-mfcc (src/io/in.cc:281-340): 24 time-domain IIR band filters -> windowed band energies ->
+    # log -> DCT.  The coefficient file is tests/golden/tdiir_filters.asc (make_tdiir_filters.py; the reference ships none).
+    # egs/conf/20 verbatim (30 / 10 ms), 25 / 10 ms (window not a multiple of the shift) and 8 kHz
+    "tdiir_w30s10": (["-fs", "16000", "-format_in", "raw", "-format_out", "htk", "-endian_in", "little", "-endian_out", "little", "-w", "30", "-s", "10",
+                      "-nr_mode", "none", "-fea_kind", "td-iir-mfcc", "-filters", "{FILTERS}", "-fea_ncepcoefs", "12"], "htk", {}),
+    "tdiir_w25s10": (["-fs", "16000", "-format_in", "raw", "-format_out", "htk", "-w", "25", "-s", "10", "-fea_kind", "td-iir-mfcc",
+                      "-filters", "{FILTERS}", "-fea_ncepcoefs", "12", "-weight_of_td_iir_mfcc_bank", "1.5"], "htk", {}),
+    "tdiir_8k_w32s12": (["-fs", "8000", "-format_in", "raw", "-format_out", "htk", "-w", "32", "-s", "12", "-fea_kind", "td-iir-mfcc",
+                         "-filters", "{FILTERS}", "-fea_ncepcoefs", "12"], "htk", {}),
     "logspec32k_40": (["-fs", "32000"] + B[2:] + MF + ["-fea_kind", "logspec", "-fb_definition", "40filters", "-format_out", "htk"], "htk", {}),
 }
 

@@ -59,7 +59,7 @@ class Case:
 
     def oracle_args(self):
         """args as given to the reference, with container placeholders made harmless"""
-        return [a.replace("{ARK}", "out.ark").replace("{PFILE}", "out.pfile").replace("{VADIN}", "vadin.bin") for a in self.args]
+        return [a.replace("{ARK}", "out.ark").replace("{PFILE}", "out.pfile").replace("{VADIN}", "vadin.bin").replace("{FILTERS}", rr.TDIIR_FILTERS) for a in self.args]
 
     def payload(self, i):
         """golden payload of utterance i as an array (features float32 [T,dim] or int16 PCM)"""

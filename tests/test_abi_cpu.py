@@ -36,7 +36,7 @@ FIELDS = ["fs", "preem", "dither", "remove_dc", "remove_dc1", "window_ms", "wshi
           "vad_cepdist_init", "vad_lpc_coefs", "vad_absolute_thr", "vad_perc_init", "vad_perc_thr", "vad_adapt_init", "vad_adapt_q",
           "vad_adapt_za", "vad_dyn_init", "vad_dyn_perc", "vad_dyn_min", "vad_dyn_qmaxinc", "vad_dyn_qmaxdec", "vad_dyn_qmindec",
           "vad_dyn_qmininc", "vad_filter_order", "window", "wshift", "wfft", "wfftby2", "phase_needed", "format_out",
-          "fea_delta", "fea_trap", "trap_win", "nfeacoefs"]
+          "fea_delta", "fea_trap", "trap_win", "nfeacoefs", "weight_of_td_iir_mfcc_bank"]
 
 
 @pytest.mark.parametrize("name", gu.case_names() + gu.feain_case_names())
@@ -54,6 +54,7 @@ def test_config_parser_agrees_with_oracle_parser(name):
         assert a == b, (name, f, a, b)
     assert (o.nr_when == "afterFB") == bool(g.nr_when)
     assert (o.format_in == "htk") == bool(g.fea_in)
+    assert o.ffilters == g.filters.decode()
     if o.fea_kind == "trapdct":
         assert (o.fea_trapdct_traplen, o.fea_trapdct_ndct) == (g.fea_trapdct_traplen, g.fea_trapdct_ndct)
 

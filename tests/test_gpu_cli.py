@@ -24,7 +24,7 @@ def run_cli(tmp, args, utts, vad_out=False, ext_vad=None):
         for i in range(len(utts)):
             fh.write("%s/u%d.raw %s/u%d.out%s\n" % (tmp, i, tmp, i, (" spk %s/u%d.vad" % (tmp, i)) if vad_out else ""))
     a = [s.replace("{ARK}", os.path.join(tmp, "o.ark")).replace("{PFILE}", os.path.join(tmp, "o.pfile")).replace("{VADIN}", os.path.join(tmp, "vadin.bin"))
-         for s in args]
+         .replace("{FILTERS}", rr.TDIIR_FILTERS) for s in args]
     pr = subprocess.run([EXE] + a + ["-S", os.path.join(tmp, "list.scp")], capture_output=True, cwd=tmp)
     assert pr.returncode == 0, pr.stderr.decode()
     return pr
@@ -41,6 +41,21 @@ def test_cli_htk_files(tmp_path):
             assert len(got) == len(want) and got[:12] == want[:12], (name, i)       # header byte-exact
             a, b = rr.parse_htk(got, be)[1], rr.parse_htk(want, be)[1]
             assert np.all(np.abs(a - b) <= 1e-4 * np.abs(b) + 1e-3)
+
+
+def test_cli_td_iir_mfcc_files(tmp_path):
+    """-fea_kind td-iir-mfcc through the CLI: HTK header byte-exact (parmKind 9 | _0), rows within tolerance.
+    Every golden is the FIRST file of a reference process: the reference carries the filter state from file to file, this
+    path is defined per utterance, so each file of the list below must equal its own one-file golden."""
+    c = gu.Case("tdiir_w30s10")
+    idx = [0, 4, 5]
+    run_cli(str(tmp_path), c.args, [gu.inputs()[i] for i in idx])
+    for j, i in enumerate(idx):
+        got = open(tmp_path / ("u%d.out" % j), "rb").read()
+        want = c.raw[i]
+        assert len(got) == len(want) and got[:12] == want[:12], i
+        a, b = rr.parse_htk(got)[1], rr.parse_htk(want)[1]
+        assert np.all(np.abs(a - b) <= 1e-4 * np.abs(b) + 1e-3), (i, np.abs(a - b).max())
 
 
 def test_cli_pfile_band_domain_path_is_byte_identical(tmp_path):
