@@ -112,6 +112,13 @@ struct ctu_handle {
     int split_front = 1;                 // 1: PCM -> spectrum -> features as two kernels; 0: the single fused kernel
     int synth_from_pcm = 0;              // 1: synthesis recomputes the forward transform instead of reading the stored X
     int fuse_nr = 1;                     // 1: the noise-reduction scan runs inside k_bank (tile in shared memory) where it can
+    // hwss / fwss / 2fwss with the reference's LIST semantics (a file's noise estimate starts from the enhanced last frame of
+    // the file before it, src/nr/nr.cc:212-222, 397-408): opt-in, one handle = one list walked in order on one GPU
+    int ss_carry = 0;
+    float *d_carry = nullptr;            // the shared spectrum buffer between utterances, ranges, plans and calls
+    double *d_carry64 = nullptr;         // ... on the fp64 band path (noise reduction after the filter bank)
+    cudaEvent_t carry_ev = nullptr;      // orders the chained scans of consecutive chunks, which run on different streams
+    bool carry_ev_set = false;
     struct PoolBlock { void *p; size_t bytes; bool used; };
     std::vector<PoolBlock> pool;
 };
@@ -730,6 +737,7 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     if ((st = build_frame_params(h))) return bail(st);
     if ((st = build_delta_trap_params(h))) return bail(st);
     if (!h->fea_in && (st = build_nr_params(h->cfg, h->nr_mode, h->vad_src, h->signal_out, h->fb.nb, h->nrp, h->sp, h->bp, h->vp, h->err))) return bail(st);
+    h->nrp.carry_xform = (h->cfg.nr_when == 1 && !h->signal_out) ? (h->fea_kind == FEA_DCTC ? 1 : ((h->fea_kind == FEA_LPA || h->fea_kind == FEA_LPC) && !h->fb.inld) ? 2 : 0) : 0;
     h->vp.cri = h->vad_cri; h->vp.thr = h->vad_thr; h->vp.drop = h->vad_drop;
     h->vp.has_E = h->energy_mode ? 1 : 0;
     h->vp.nbins = h->nbins; h->vp.spitch = h->spitch; h->bp.spitch = h->spitch;
@@ -819,6 +827,8 @@ void ctu_destroy(ctu_handle *h) {
     cudaFree(h->d_any_tw); cudaFree(h->d_any_ts); cudaFree(h->d_any_fbw); cudaFree(h->d_any_bands);
     cudaFree(h->bank.d_bands); cudaFree(h->bank.d_w4); cudaFree(h->bank.d_m2);
     cudaFree(h->d_td_coefs); cudaFree(h->d_td_win); cudaFree(h->d_td_dct);
+    cudaFree(h->d_carry); cudaFree(h->d_carry64);
+    if (h->carry_ev) cudaEventDestroy(h->carry_ev);
     for (auto &b : h->pool) cudaFree(b.p);
     for (int i = 0; i < 3; i++) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     h->lc.clear();
@@ -1263,7 +1273,8 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
     // the scan runs inside k_bank, on the tile in shared memory, whenever nothing but the filter bank consumes the enhanced
     // spectrum (the enhanced spectrum then never exists in HBM)
     const bool bank_path = need_spec && !h->generic && !h->precise && !h->signal_out && h->fea_kind != FEA_NONE;
-    const bool fuse_scan = bank_path && nr_on && before && h->fuse_nr && !h->do_vad && h->nrp.a_kind != 0;
+    const bool carry = h->ss_carry && h->nr_mode >= NR_HWSS;
+    const bool fuse_scan = bank_path && nr_on && before && h->fuse_nr && !h->do_vad && h->nrp.a_kind != 0 && !carry;
     if (nr_on && before) {
         if (h->nr_mode >= NR_HWSS && h->vad_src == VADSRC_BURG) {
             if ((st = launch_burg(h->bp, BURG_SRC_NR, bd32, r.t32_n, d_pcm, nullptr, p->d_ceps, h->d_tw256d, h->d_twsplitd, h->d_twinvd, h->d_wind,
@@ -1272,6 +1283,13 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
         }
         const uint8_t *fl = (h->nr_mode >= NR_HWSS) ? (h->vad_src == VADSRC_FILE ? d_ext : flags) : nullptr;
         if (h->nr_mode >= NR_HWSS && !fl) return fail(h, CTU_ERR_INPUT, "NR: Unable to open VAD file!\n");
+        if (carry) {
+            if (h->carry_ev_set) CK(cudaStreamWaitEvent(s, h->carry_ev, 0));
+            if ((st = launch_nr_scan_carry(h->nrp, p->d_nframes, p->d_row_off, r.u0, r.u1, h->nbins, h->spitch, p->d_spec, fl, h->d_carry,
+                                           h->signal_out ? p->d_cspec : nullptr, s, &h->lc, h->err))) return st;
+            CK(cudaEventRecord(h->carry_ev, s));
+            h->carry_ev_set = true;
+        } else
         if (!fuse_scan && (st = launch_nr_scan(h->nrp, p->d_nframes, p->d_row_off, r.u0, r.u1, h->nbins, h->spitch, p->d_spec, fl, s, &h->lc, h->err))) return st;
         if (h->vad_src == VADSRC_FILE && d_vadnr && h->nr_mode >= NR_HWSS)
             CK(cudaMemcpyAsync(d_vadnr + r.row0, d_ext + r.row0, r.nrows, cudaMemcpyDeviceToDevice, s));
@@ -1328,7 +1346,9 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
             const uint8_t *fl = (h->nr_mode >= NR_HWSS) ? d_ext : nullptr;
             if (h->nr_mode >= NR_HWSS && !fl) return fail(h, CTU_ERR_INPUT, "NR: Unable to open VAD file!\n");
             if ((st = launch_frames64(SRC64_PCM, DST64_FB, KIND_SPEC, P, bd32, t64, r.t32_n, d_pcm, nullptr, nullptr, p->d_fb64, nullptr, s, &h->lc, h->err))) return st;
-            if ((st = launch_nr_scan64(h->nrp, p->d_nframes, p->d_row_off, r.u0, r.u1, h->fb.nb, p->d_fb64, fl, s, &h->lc, h->err))) return st;
+            if (carry && h->carry_ev_set) CK(cudaStreamWaitEvent(s, h->carry_ev, 0));
+            if ((st = launch_nr_scan64(h->nrp, p->d_nframes, p->d_row_off, r.u0, r.u1, h->fb.nb, p->d_fb64, fl, carry ? h->d_carry64 : nullptr, s, &h->lc, h->err))) return st;
+            if (carry) { CK(cudaEventRecord(h->carry_ev, s)); h->carry_ev_set = true; }
             if (d_vadnr && fl) CK(cudaMemcpyAsync(d_vadnr + r.row0, d_ext + r.row0, r.nrows, cudaMemcpyDeviceToDevice, s));
             if ((st = launch_frames64(SRC64_FB, DST64_FEA, kind, P, bd32, t64, r.t32_n, nullptr, p->d_fb64, nullptr, f64, fea_dst, s, &h->lc, h->err))) return st;
         } else if (nr_on && before) {
@@ -1744,6 +1764,23 @@ int ctu_set_option(ctu_handle *h, const char *name, int64_t value) {
     const std::string n(name);
     if (n == "copy_only") h->copy_only = value != 0;
     else if (n == "chunk_mb") h->chunk_mb = (int)std::max<int64_t>(1, value);
+    else if (n == "ss_carry") {
+        // (re)starts a list: the buffer is zero before the first file of a reference process (Vec's constructor, src/base/types.h:35-38)
+        if (value && h->nr_mode >= NR_HWSS) {
+            if (h->signal_out && h->synth_from_pcm) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: ss_carry with synth_from_pcm (the sign of the Nyquist bin comes from the stored spectrum)");
+            if (h->signal_out && h->bp.nfft) return fail(h, CTU_ERR_UNSUPPORTED, "CTU: ss_carry with waveform output at FFT sizes other than 512");
+            CK(cudaSetDevice(h->device));
+            const size_t nmax = (size_t)std::max(h->nbins, h->fb.nb) + 8;
+            if (!h->d_carry) CK(cudaMalloc(&h->d_carry, nmax * sizeof(float)));
+            if (!h->d_carry64) CK(cudaMalloc(&h->d_carry64, nmax * sizeof(double)));
+            if (!h->carry_ev) CK(cudaEventCreateWithFlags(&h->carry_ev, cudaEventDisableTiming));
+            CK(cudaMemset(h->d_carry, 0, nmax * sizeof(float)));
+            CK(cudaMemset(h->d_carry64, 0, nmax * sizeof(double)));
+            CK(cudaDeviceSynchronize());
+            h->carry_ev_set = false;
+        }
+        h->ss_carry = value != 0;
+    }
     else if (n == "split_front") h->split_front = value != 0;           // takes effect for plans created afterwards
     else if (n == "synth_from_pcm") h->synth_from_pcm = value != 0;     // takes effect for plans created afterwards
     else if (n == "fuse_nr") h->fuse_nr = value != 0;

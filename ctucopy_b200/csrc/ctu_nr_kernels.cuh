@@ -124,6 +124,74 @@ static inline void launch_nr_scan_a(const NrParams &N, unsigned grid, cudaStream
     else k_nr_scan<MODE, 0, 0><<<grid, 256, 0, s>>>(N, d_nframes, d_row_off, u0, n, size, X, flags);
 }
 
+// K2c: hwss / fwss / 2fwss with the reference's LIST semantics (opt-in: ctu_set_option "ss_carry").  hwssNR / dfwssNR::new_file
+// (src/nr/nr.cc:212-222, 397-408) start a file's noise estimate from whatever the shared spectrum buffer holds: the ENHANCED
+// last frame of the file before it (zeros for the first file of a process).  That chains every utterance to the one before, so
+// the only parallelism left is the bins: one thread per bin walks the utterances of the range in list order, `carry` holds the
+// buffer between ranges, plans and calls.  Waveform output: sigOUT::save_frame negates the Nyquist bin in that buffer when
+// its phase is not 0 (src/io/out.cc:414) -- cspec (the stored complex spectrum) gives the sign.
+constexpr int CARRY_UNROLL = 8;
+template <int MODE, int AKIND>
+__global__ void __launch_bounds__(128)
+k_nr_scan_carry(const __grid_constant__ NrParams N, const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int u0, int n_utts,
+                int size, int pitch, float *X, const uint8_t *__restrict__ flags, float *__restrict__ carry, const float2 *__restrict__ cspec) {
+    const int bin = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bin >= size) return;
+    float cv = carry[bin];
+    for (int i = 0; i < n_utts; i++) {
+        const int u = u0 + i, T = nframes[u];
+        if (T <= 0) continue;
+        ScanState S;
+        S.Navg = (MODE == NR_2FWSS || AKIND == 1) ? cv : (AKIND == 2) ? cv * cv : powf(cv, N.a);
+        S.Yavg = 0.05f; S.Nravg = 0.f; S.Nd = 0.95; S.Yd = 0.05;
+        float *x = X + row_off[u] * pitch + bin;
+        const uint8_t *fl = flags + row_off[u];
+        for (int t0 = 0; t0 < T; t0 += CARRY_UNROLL) {
+            float v[CARRY_UNROLL];
+            uint8_t f[CARRY_UNROLL];
+#pragma unroll
+            for (int j = 0; j < CARRY_UNROLL; j++) {
+                const int t = min(t0 + j, T - 1);
+                v[j] = x[(int64_t)t * pitch];
+                f[j] = fl[t];
+            }
+#pragma unroll
+            for (int j = 0; j < CARRY_UNROLL; j++)
+                if (t0 + j < T) {
+                    cv = nr_step<MODE, AKIND>(N, S, v[j], t0 + j, f[j]);
+                    x[(int64_t)(t0 + j) * pitch] = cv;
+                }
+        }
+        if (cspec && bin == size - 1 && cspec[(row_off[u] + T - 1) * (int64_t)size + bin].x < 0.f) cv = -cv;
+    }
+    carry[bin] = cv;
+}
+
+template <int MODE>
+static inline void launch_nr_scan_carry_a(const NrParams &N, cudaStream_t s, const int *d_nframes, const int64_t *d_row_off, int u0, int n, int size,
+                                          int pitch, float *X, const uint8_t *flags, float *carry, const float2 *cspec) {
+    const int ak = (N.a_kind == 1 || MODE == NR_2FWSS) ? 1 : N.a_kind;
+    const unsigned grid = (unsigned)((size + 127) / 128);
+    if (ak == 1) k_nr_scan_carry<MODE, 1><<<grid, 128, 0, s>>>(N, d_nframes, d_row_off, u0, n, size, pitch, X, flags, carry, cspec);
+    else if (ak == 2) k_nr_scan_carry<MODE, 2><<<grid, 128, 0, s>>>(N, d_nframes, d_row_off, u0, n, size, pitch, X, flags, carry, cspec);
+    else k_nr_scan_carry<MODE, 0><<<grid, 128, 0, s>>>(N, d_nframes, d_row_off, u0, n, size, pitch, X, flags, carry, cspec);
+}
+
+int launch_nr_scan_carry(const NrParams &N, const int *d_nframes, const int64_t *d_row_off, int u0, int u1, int size, int pitch, float *X,
+                         const uint8_t *flags, float *carry, const float2 *cspec, cudaStream_t s, LaunchCtx *lc, std::string &err) {
+    if (u1 <= u0) return CTU_OK;
+    lc->begin("k_nr_scan_carry", s);
+    switch (N.mode) {
+        case NR_HWSS: launch_nr_scan_carry_a<NR_HWSS>(N, s, d_nframes, d_row_off, u0, u1 - u0, size, pitch, X, flags, carry, cspec); break;
+        case NR_FWSS: launch_nr_scan_carry_a<NR_FWSS>(N, s, d_nframes, d_row_off, u0, u1 - u0, size, pitch, X, flags, carry, cspec); break;
+        default: launch_nr_scan_carry_a<NR_2FWSS>(N, s, d_nframes, d_row_off, u0, u1 - u0, size, pitch, X, flags, carry, cspec); break;
+    }
+    lc->end(s);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e) + " (k_nr_scan_carry)"; return CTU_ERR_CUDA; }
+    return CTU_OK;
+}
+
 // size: bins per row; pitch: floats per row (SPITCH for the 512-point spectrum, else = size)
 int launch_nr_scan(const NrParams &N, const int *d_nframes, const int64_t *d_row_off, int u0, int u1, int size, int pitch, float *X,
                                  const uint8_t *flags, cudaStream_t s, LaunchCtx *lc, std::string &err) {

@@ -28,6 +28,9 @@ struct NrParams {
     double ad, pd;
     int a_kind;          // 1: a == 1, 2: a == 2, 0: general
     int initsegs;
+    int carry_xform;     // list semantics on the band path: what FEA does IN PLACE to the band vector that the next file's noise
+                         // estimate starts from -- 1: log (dctcFEA, src/fea/fea_impl.cc:108), 2: square (lpaFEA without the
+                         // cube-root law, :166-169), 0: nothing
 };
 
 struct SynthParams {
@@ -210,6 +213,8 @@ constexpr int SYN_FRAMES = SYN_GROUPS;
 // ---- launchers defined in ctu_nr.cu / ctu_burg.cu -------------------------------------------------------------------
 int launch_nr_scan(const NrParams &N, const int *d_nframes, const int64_t *d_row_off, int u0, int u1, int size, int pitch, float *X,
                    const uint8_t *flags, cudaStream_t s, LaunchCtx *lc, std::string &err);
+int launch_nr_scan_carry(const NrParams &N, const int *d_nframes, const int64_t *d_row_off, int u0, int u1, int size, int pitch, float *X,
+                         const uint8_t *flags, float *carry, const float2 *cspec, cudaStream_t s, LaunchCtx *lc, std::string &err);
 int launch_burg(const BurgParams &B, int src_mode, const BatchDesc &bd, int64_t ntiles, const int16_t *pcm, const float *spec,
                 double *ceps, const double2 *tw, const double2 *ts, const double2 *ti, const double *win, const double *hann,
                 cudaStream_t s, LaunchCtx *lc, std::string &err);

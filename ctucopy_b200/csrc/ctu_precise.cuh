@@ -39,7 +39,7 @@ struct Tables64 {
 int launch_frames64(int src_kind, int dst_kind, int kind, const FrameParams &P, const BatchDesc &bd, const Tables64 &tb, int64_t ntiles, const int16_t *pcm,
                     const double *src64, const float *spec, double *dst64, float *dst, cudaStream_t stream, LaunchCtx *lc, std::string &err);
 int launch_nr_scan64(const NrParams &N, const int *d_nframes, const int64_t *d_row_off, int u0, int u1, int size, double *X,
-                     const uint8_t *flags, cudaStream_t s, LaunchCtx *lc, std::string &err);
+                     const uint8_t *flags, double *carry, cudaStream_t s, LaunchCtx *lc, std::string &err);
 
 #ifdef CTU_PRECISE_IMPL
 template <int LANES> __device__ __forceinline__ double lanes_sum_d(double v) {
@@ -357,15 +357,22 @@ static int launch_frames64_k(int kind, const FrameParams &P, const BatchDesc &bd
 // the reference writes them; cancellation is harmless at 53 bits) ----------------------------
 __global__ void __launch_bounds__(128)
 k_nr_scan64(const __grid_constant__ NrParams N, const int *__restrict__ nframes, const int64_t *__restrict__ row_off, int u0, int n_utts,
-            int size, double *X, const uint8_t *__restrict__ flags) {
+            int size, double *X, const uint8_t *__restrict__ flags, double *__restrict__ carry) {
+    // carry (opt-in list semantics of hwss / fwss / 2fwss, see k_nr_scan_carry): one thread per bin walks the utterances of the
+    // range in order, a file's noise estimate starts from the enhanced last frame of the file before it
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (int64_t)n_utts * size) return;
-    const int u = u0 + (int)(gid / size), bin = (int)(gid % size);
+    if (gid >= (carry ? (int64_t)size : (int64_t)n_utts * size)) return;
+    const int bin = (int)(gid % size);
+    const int ufirst = carry ? u0 : u0 + (int)(gid / size), ulast = carry ? u0 + n_utts : ufirst + 1;
+    const double p = N.pd, a = N.ad, b = (double)N.b;
+    double cv = carry ? carry[bin] : 0.0;
+    for (int u = ufirst; u < ulast; u++) {
     const int T = nframes[u];
+    if (T <= 0) continue;
     double *x = X + row_off[u] * size + bin;
     const uint8_t *fl = flags ? flags + row_off[u] : nullptr;
-    const double p = N.pd, a = N.ad, b = (double)N.b;
     double Navg = (N.mode == NR_EXTEN) ? 0.95 : 0.0, Yavg = 0.05, Nravg = 0.0;
+    if (carry && N.mode != NR_EXTEN) Navg = (N.mode == NR_2FWSS || N.a_kind == 1) ? cv : (N.a_kind == 2) ? __dmul_rn(cv, cv) : pow(cv, a);
     // Every product and sum below is rounded on its own (__dmul_rn / __dadd_rn / __dsub_rn: no FMA contraction), in the
     // reference's order (src/nr/nr.cc:95-140, 224-261, 331-369, 397-442).  This path exists for fidelity: where the
     // subtraction cancels almost everything (x - H x with H = 1 - 1e-13) the reference's result IS its rounding pattern --
@@ -400,15 +407,19 @@ k_nr_scan64(const __grid_constant__ NrParams N, const int *__restrict__ nframes,
             }
         }
         x[(int64_t)t * size] = xi;
+        cv = xi;
     }
+    if (N.carry_xform == 1) cv = log(cv); else if (N.carry_xform == 2) cv = __dmul_rn(cv, cv);
+    }
+    if (carry) carry[bin] = cv;
 }
 
 int launch_nr_scan64(const NrParams &N, const int *d_nframes, const int64_t *d_row_off, int u0, int u1, int size, double *X,
-                                   const uint8_t *flags, cudaStream_t s, LaunchCtx *lc, std::string &err) {
-    int64_t n = (int64_t)(u1 - u0) * size;
-    if (n <= 0) return CTU_OK;
+                                   const uint8_t *flags, double *carry, cudaStream_t s, LaunchCtx *lc, std::string &err) {
+    int64_t n = carry ? (int64_t)size : (int64_t)(u1 - u0) * size;
+    if (n <= 0 || u1 <= u0) return CTU_OK;
     lc->begin("k_nr_scan64", s);
-    k_nr_scan64<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(N, d_nframes, d_row_off, u0, u1 - u0, size, X, flags);
+    k_nr_scan64<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(N, d_nframes, d_row_off, u0, u1 - u0, size, X, flags, carry);
     lc->end(s);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e) + " (k_nr_scan64)"; return CTU_ERR_CUDA; }

@@ -5,7 +5,7 @@
 //   file: b0..b4 | input gain | a1..a4), the filtered sample is multiplied by the Hamming weight of its POSITION IN THE
 //   CIRCULAR BUFFER (n % window, not its position inside a frame), a frame's band energy is the sum of the squares of the
 //   `window` values in the buffer, then log((w*w*E/w)/weight), bands in reverse order, 13-point DCT.
-// fp64 throughout, the recurrence in the reference's operation order.  The filter state starts at zero for every utterance
+// fp64 throughout.  The filter state starts at zero for every utterance
 // (= the first file of a reference list whose heap came back zeroed).
 //
 // Two kernels:
@@ -63,6 +63,8 @@ k_tdiir_filter(const __grid_constant__ TdiirParams P, const int64_t *__restrict_
     __shared__ int sN[TDIIR_UTTS];
     const int tid = threadIdx.x, lu = tid / TDIIR_BANDS, b = tid % TDIIR_BANDS;
     const int L = P.chunk, run = P.run;
+    const int LP = L + 2;                                  // row pitch of sX: a warp holds the band threads of two utterances, whose rows
+                                                           // must not start in the same bank (ncu: every other load conflicted)
     for (int i = tid; i < P.window; i += TDIIR_THREADS) sWin[i] = P.win[i];
     if (tid < TDIIR_UTTS) {
         const int i = blockIdx.x * TDIIR_UTTS + tid;
@@ -88,14 +90,14 @@ k_tdiir_filter(const __grid_constant__ TdiirParams P, const int64_t *__restrict_
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;       // state(ff, 0..3): oldest .. newest (src/io/in.cc:289-297)
     double acc = 0.0;
     int wi = 0, gi = 0;                                   // n % window, n % seg at the start of a run
-    const double *xs = sX + lu * L;
+    const double *xs = sX + lu * LP;
     for (int base = 0; base < maxN; base += L) {
         // the chunk's samples, converted once per utterance instead of once per band (I2F.F64 is a quarter-rate instruction)
 #pragma unroll
         for (int k = 0; k < TDIIR_UTTS; k++) {
             const int16_t *src = pcm + sOff[k] + base;
             const int nk = sN[k] - base;
-            for (int i = tid; i < L; i += TDIIR_THREADS) sX[k * L + i] = (i < nk) ? (double)src[i] : 0.0;
+            for (int i = tid; i < L; i += TDIIR_THREADS) sX[k * LP + i] = (i < nk) ? (double)src[i] : 0.0;
         }
         __syncthreads();
         const int n = min(L, myN - base);                 // a multiple of `run`
@@ -105,11 +107,14 @@ k_tdiir_filter(const __grid_constant__ TdiirParams P, const int64_t *__restrict_
             const double *xp = xs + i0, *wp = sWin + wi;
 #pragma unroll 4
             for (int i = 0; i < run; i++) {
+                // the feedback terms are taken oldest first, so that only ONE multiply-add waits for the newest state (the
+                // reference subtracts a1 s3 first, src/io/in.cc:288-290: the same sum, rounded in another order -- 1e-16
+                // relative in fp64, against a tolerance of 1e-3 in the log domain)
                 double v = g * xp[i];
-                v -= a1 * s3;
-                v -= a2 * s2;
-                v -= a3 * s1;
                 v -= a4 * s0;
+                v -= a3 * s1;
+                v -= a2 * s2;
+                v -= a1 * s3;
                 double y = b0 * v;
                 y += b4 * s0;
                 y += b3 * s1;
@@ -165,7 +170,7 @@ int launch_tdiir(const TdiirParams &P, const BatchDesc &bd64, int64_t nt64, cons
                  LaunchCtx *lc, std::string &err) {
     const int n = u1 - u0;
     if (n <= 0 || nt64 <= 0) return CTU_OK;
-    const size_t bytes = sizeof(double) * ((size_t)P.window + (size_t)TDIIR_UTTS * P.chunk);
+    const size_t bytes = sizeof(double) * ((size_t)P.window + (size_t)TDIIR_UTTS * (P.chunk + 2));
     lc->begin("k_tdiir_filter", s);
     k_tdiir_filter<<<(unsigned)((n + TDIIR_UTTS - 1) / TDIIR_UTTS), TDIIR_THREADS, bytes, s>>>(P, d_pcm_off, d_nframes, d_row_off, u0, n, pcm, S);
     lc->end(s);

@@ -38,6 +38,8 @@ struct HostOpts {
     int gpus = 1;                 // -gpus N    : N worker threads in this process, one handle per GPU
     int shard_r = 0, shard_n = 1; // -shard r/N : this process handles shard r of N (one process per GPU)
     int merge_n = 0;              // -merge N   : merge the pfile / ark+scp shards of N finished `-shard` runs
+    bool ss_carry = false;        // -ss_carry on: hwss / fwss / 2fwss with the reference's list semantics (a file's noise estimate starts
+                                  // from the enhanced last frame of the file before it, src/nr/nr.cc:212-222); one GPU, list order
     int device = -1;              // -device d  : CUDA device (default: shard index modulo device count)
     std::string stat_cmvn, apply_cmvn;   // CMVN statistics file to write / to apply (src/io/opts.cc:678-685)
     std::string ark_ref;          // ark path recorded in scp lines (the merged file's name)
@@ -263,6 +265,7 @@ void take_host_option(HostOpts &o, const char *l, const char *r) {
     else if (opt == "-gpus" && r) o.gpus = std::max(1, std::atoi(r));
     else if (opt == "-device" && r) o.device = std::atoi(r);
     else if (opt == "-merge" && r) o.merge_n = std::atoi(r);
+    else if (opt == "-ss_carry") o.ss_carry = !r || val() == "on";
     else if (opt == "-shard" && r) {
         if (std::sscanf(r, "%d/%d", &o.shard_r, &o.shard_n) != 2 || o.shard_n < 1 || o.shard_r < 0 || o.shard_r >= o.shard_n)
             die("OPTS: -shard takes r/N with 0 <= r < N");
@@ -270,7 +273,8 @@ void take_host_option(HostOpts &o, const char *l, const char *r) {
 }
 
 bool is_host_extension(const char *opt) {
-    return !std::strcmp(opt, "-gpus") || !std::strcmp(opt, "-device") || !std::strcmp(opt, "-merge") || !std::strcmp(opt, "-shard");
+    return !std::strcmp(opt, "-gpus") || !std::strcmp(opt, "-device") || !std::strcmp(opt, "-merge") || !std::strcmp(opt, "-shard") ||
+           !std::strcmp(opt, "-ss_carry");
 }
 
 // samples a file will decode to, from its size / header only (used to balance shards and to
@@ -541,6 +545,7 @@ void process_range(const HostOpts &ho, const ctu_config &cfg, const std::vector<
     ctu_handle *h = nullptr;
     if (ctu_create(&cfg, device, &h)) die(ctu_last_error(nullptr));
     tmark("ctu_create (CUDA init)", t_start);
+    if (ho.ss_carry && ctu_set_option(h, "ss_carry", 1)) die(ctu_last_error(h));
     ctu_set_rand_offset(h, rand0);            // -dither: rand() values the list lines before this range have drawn
     const int dim = ctu_feature_dim(h);
     const bool sig = ctu_is_signal_output(h);
@@ -925,6 +930,8 @@ int run(int argc, char **argv) {
     std::vector<unsigned char> extvad;
     if (!std::strcmp(cfg.vadmode, "file")) extvad = slurp(ho.filevad, "NR: Unable to open VAD file!\n");
     const int nparts = ho.gpus > 1 ? ho.gpus : ho.shard_n;
+    if (ho.ss_carry && (nparts != 1 || !ho.stat_cmvn.empty() || !ho.apply_cmvn.empty()))
+        die("CTU: -ss_carry chains every file to the one before it: one GPU, one process, no CMVN passes");
     if (!ho.stat_cmvn.empty() || !ho.apply_cmvn.empty()) {
         if (ho.shard_n != 1) die("CTU: CMVN statistics span the whole list: run it in one process (-gpus N uses N GPUs from one process; -shard cannot)");
         process_cmvn(ho, cfg, list, ho.device < 0 ? 0 : ho.device, extvad, ho.gpus);

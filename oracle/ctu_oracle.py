@@ -1144,21 +1144,21 @@ def nr_ss(X: np.ndarray, o: Opts, vad_flags=None, Xph: Optional[np.ndarray] = No
     return out, vout
 
 
-def apply_nr(X, o: Opts, Xph=None, vad_flags=None, force_flags=None):
+def apply_nr(X, o: Opts, Xph=None, vad_flags=None, force_flags=None, navg0=None):
     """force_flags: detector decisions to use instead of running the Burg detector (the sensitivity probe of
     run_pipeline(perturb=...) keeps the decisions of the unperturbed run)."""
     if o.nr_mode == "none":
         return X, None
     if force_flags is not None and o.nr_mode in ("hwss", "fwss", "2fwss"):
-        return nr_ss(X, o, vad_flags=force_flags)
+        return nr_ss(X, o, vad_flags=force_flags, navg0=navg0)
     if o.nr_mode == "exten":
         return nr_exten(X, o), None
     if o.nr_mode in ("hwss", "fwss", "2fwss"):
         if o.vadmode == "file":
             if vad_flags is None:
                 raise ValueError("NR: Unable to open VAD file!\n")
-            return nr_ss(X, o, vad_flags=vad_flags)
-        return nr_ss(X, o, Xph=Xph)
+            return nr_ss(X, o, vad_flags=vad_flags, navg0=navg0)
+        return nr_ss(X, o, Xph=Xph, navg0=navg0)
     raise ValueError("NR: Unknown noise reduction mode!")
 
 
@@ -1378,6 +1378,7 @@ class Result:
     fb_out: Optional[np.ndarray] = None     # [T, nb] float64 (post NR if afterFB)
     spectrum: Optional[np.ndarray] = None   # [T, bins] float64 after NR (beforeFB)
     internal: Optional[np.ndarray] = None   # feature matrix before column reorder
+    navg0: Optional[np.ndarray] = None      # run_list_carry: the buffer this file's noise estimate started from
 
 
 def writer_order(F: np.ndarray, o: Opts) -> np.ndarray:
@@ -1646,7 +1647,8 @@ def td_iir_mfcc(pcm: np.ndarray, o: Opts, coefs: np.ndarray) -> np.ndarray:
 
 
 def run_pipeline(pcm: np.ndarray, o: Opts, ext_vad: Optional[np.ndarray] = None, rand_offset: int = 0,
-                 perturb: Optional[Tuple[float, int]] = None, force_vad_nr: Optional[np.ndarray] = None) -> Result:
+                 perturb: Optional[Tuple[float, int]] = None, force_vad_nr: Optional[np.ndarray] = None,
+                 navg0: Optional[np.ndarray] = None) -> Result:
     """One utterance through the chain BATCH builds (src/io/batch.cc:24-69, 205-296).
     perturb = (eps, seed): CONDITIONING PROBE, not part of the reference's algorithm -- the spectrum that leaves the front
     end is moved by eps (relative per bin, plus eps of the frame's mean level, random signs) before anything else sees it,
@@ -1679,7 +1681,7 @@ def run_pipeline(pcm: np.ndarray, o: Opts, ext_vad: Optional[np.ndarray] = None,
     T = fe.Xabs.shape[0]
     signal_out = o.format_out in ("raw", "wave")
     if signal_out:
-        X, vnr = apply_nr(fe.Xabs, o, fe.Xph, ext_vad, force_vad_nr)
+        X, vnr = apply_nr(fe.Xabs, o, fe.Xph, ext_vad, force_vad_nr, navg0)
         return Result(T, waveform=synth(X, fe.Xph, o), vad_nr=vnr, spectrum=X)
     fb = fb_design(o)
     if o.nr_when == "afterFB":
@@ -1688,10 +1690,10 @@ def run_pipeline(pcm: np.ndarray, o: Opts, ext_vad: Optional[np.ndarray] = None,
             Y = _perturbed(Y)                       # the subtraction's input is the band vector here
         if o.nr_mode in ("hwss", "fwss", "2fwss") and o.vadmode == "burg":
             raise ValueError("NR: Cannot use Burg detector after filter bank!")
-        Y, vnr = apply_nr(Y, o, None, ext_vad, force_vad_nr)
+        Y, vnr = apply_nr(Y, o, None, ext_vad, force_vad_nr, navg0)
         Xs = fe.Xabs
     else:
-        Xs, vnr = apply_nr(fe.Xabs, o, fe.Xph, ext_vad, force_vad_nr)
+        Xs, vnr = apply_nr(fe.Xabs, o, fe.Xph, ext_vad, force_vad_nr, navg0)
         Y = fb_project(Xs, fb)
     k = o.fea_kind
     latency = 0
@@ -1738,6 +1740,32 @@ def run_pipeline(pcm: np.ndarray, o: Opts, ext_vad: Optional[np.ndarray] = None,
         res.vad = vad_module(o, Xs[idx], fe.Xph[idx] if fe.Xph is not None else None, F)
         res.features = res.features[res.vad.keep]
     return res
+
+
+def run_list_carry(pcms: List[np.ndarray], o: Opts, ext_vads: Optional[List[np.ndarray]] = None) -> List[Result]:
+    """The files of ONE reference process in list order, for the VAD-driven subtraction modes: hwssNR / dfwssNR::new_file
+    (src/nr/nr.cc:212-222, 397-408) start a file's noise estimate from whatever the shared spectrum buffer holds -- the
+    ENHANCED last frame of the file before (zeros for the first file: Vec's constructor, src/base/types.h:35-38).  With
+    noise reduction after the filter bank the buffer is the band vector.  run_pipeline alone is the per-utterance definition
+    (every file = the first file of a process)."""
+    out, last = [], None
+    for k, u in enumerate(pcms):
+        r = run_pipeline(u, o, ext_vads[k] if ext_vads is not None else None, navg0=last)
+        r.navg0 = last
+        out.append(r)
+        if o.nr_mode in ("hwss", "fwss", "2fwss"):
+            buf = r.fb_out if (o.nr_when == "afterFB" and o.format_out not in ("raw", "wave")) else r.spectrum
+            if buf is not None and len(buf):
+                last = np.array(buf[-1], dtype=np.float64)
+                if o.nr_when == "afterFB" and o.format_out not in ("raw", "wave"):
+                    # FEA works IN PLACE on the band vector: dctcFEA takes its logarithm (src/fea/fea_impl.cc:108), lpaFEA
+                    # squares it when the cube-root law is off (:166-169)
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        if o.fea_kind == "dctc": last = np.log(last)
+                        elif o.fea_kind in ("lpa", "lpc") and not fb_design(o).inld: last = last * last
+                if o.format_out in ("raw", "wave") and front_end(u, o).Xph[-1][-1] != 0:
+                    last[-1] = -last[-1]           # sigOUT::save_frame negates the Nyquist bin IN the shared buffer (src/io/out.cc:414)
+    return out
 
 
 def run_features(Fin: np.ndarray, o: Opts) -> np.ndarray:

@@ -8,7 +8,7 @@ import os
 import re
 import sys
 
-FRAMES = {"mfcc_exten": 1996000, "mfcc_d_a": 1996000, "plp": 1996000, "trapdct": 1996000, "exten": 1248000, "fwss_burg": 499000}
+FRAMES = {"mfcc_exten": 1996000, "mfcc_d_a": 1996000, "plp": 1996000, "trapdct": 1996000, "exten": 1248000, "fwss_burg": 499000, "tdiir": 1996000}
 SRC = {0: "pcm", 1: "spec", 2: "fb"}
 DST = {0: "spec", 1: "fb", 2: "fea"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
@@ -20,6 +20,11 @@ def label(kernel):
     m = re.match(r"void k_frames<(\d+), (\d+)", kernel)
     if m:
         return "k_frames<%s,%s>" % (SRC[int(m.group(1))], DST[int(m.group(2))])
+    m = re.match(r"void k_bank<(\d+), (\d+), (\d+)>", kernel)          # <KIND, DST, NR>: the names ctu_bank.cuh gives its launches
+    if m:
+        return "k_bank<%s%s>" % ("nr," if int(m.group(3)) else "", DST[int(m.group(2))])
+    if "k_nr_scan4<" in kernel:
+        return "k_nr_scan"
     m = re.match(r"void (k_[a-z_]+?)(22|64)?<|void (k_[a-z_]+)\(|(k_[a-z_]+)\(", kernel)
     name = next(g for g in (m.group(1), m.group(3), m.group(4)) if g) if m else kernel
     return name
@@ -27,7 +32,8 @@ def label(kernel):
 
 def main():
     d = sys.argv[1]
-    out = {}
+    tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json")
+    out = json.load(open(tp)) if os.path.exists(tp) else {}      # workloads without a new capture keep their entries
     for w, frames in FRAMES.items():
         p = os.path.join(d, "raw_p_%s.csv" % w)
         if not os.path.exists(p):

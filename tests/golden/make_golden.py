@@ -208,6 +208,21 @@ G711_CASES = {
 }
 
 
+# hwss / fwss / 2fwss over a LIST in one reference process: a file's noise estimate starts from the enhanced last frame of the
+# file before it (src/nr/nr.cc:212-222, 397-408) -- the opt-in "ss_carry" mode of the library (per-utterance semantics are the
+# default and what every other golden pins).  name -> (args, input indices in list order, kind)
+CARRY_CASES = {
+    "carry_fwss_burg": (B + MF + ["-nr_mode", "fwss", "-vad", "burg", "-format_out", "htk"], [0, 5, 4], "htk"),
+    "carry_2fwss_burg_d": (B + MF + ["-nr_mode", "2fwss", "-vad", "burg", "-nr_initsegs", "5", "-fea_delta", "d", "-format_out", "htk"], [5, 0, 4, 1], "htk"),
+    "carry_hwss_spec_pow": (B + MF + ["-nr_mode", "hwss", "-nr_b", "1.5", "-vad", "burg", "-fea_kind", "spec", "-format_out", "htk"], [0, 5, 4], "htk"),
+    "carry_fwss_raw": (B + ["-w", "32", "-s", "16", "-nr_mode", "fwss", "-nr_b", "1.5", "-vad", "burg", "-format_out", "raw"], [0, 5, 4], "raw"),
+    "carry_hwss_a2_raw_2510": (B + ["-w", "25", "-s", "10", "-preem", "0.97", "-nr_mode", "hwss", "-nr_a", "2", "-vad", "burg", "-format_out", "raw"], [4, 5, 0], "raw"),
+    # the fp64 band path: FEA works in place on the band vector (dctc: its logarithm is what the next file starts from)
+    "carry_fwss_file_afterFB": (B + MF + ["-nr_mode", "fwss", "-vad", "file={VADIN}", "-nr_when", "afterFB", "-format_out", "htk"], [0, 5, 4], "htk"),
+    "carry_fwss_burg_8k": (["-fs", "8000"] + B[2:] + MF + ["-nr_mode", "fwss", "-vad", "burg", "-format_out", "htk"], [0, 5, 4], "htk"),
+}
+
+
 def g711_encode(pcm, alaw):
     """nearest code of the expansion table (ties: the smaller code); only used to make realistic test inputs"""
     import ctu_oracle as co
@@ -300,6 +315,31 @@ def main():
                     dd["out%d" % i] = np.frombuffer(open(pth, "rb").read(), dtype=np.uint8)
             np.savez_compressed(os.path.join(OUT, name + ".npz"), **dd)
             print(name, "ok")
+    # *ss modes over a list in ONE reference process
+    for name, (args, idx, kind) in CARRY_CASES.items():
+        if sys.argv[1:] and name not in sys.argv[1:]:
+            continue
+        import ctu_oracle as co
+        o = co.parse_args([a.replace("{VADIN}", "vadin.bin") for a in args])
+        pcms = [utts[i] for i in idx]
+        ev = None
+        if o.vadmode == "file":
+            rng2 = np.random.default_rng(11)
+            ev = []
+            for u in pcms:
+                T = co.num_frames(len(u), o)
+                e = (rng2.random(T) < 0.5).astype(np.uint8)
+                e[: min(12, T)] = 0
+                ev.append(e)
+        r = rr.run_reference(args, pcms, out_ext="out", ext_vad_bytes=None if ev is None else np.concatenate(ev).tobytes())
+        assert r["returncode"] == 0 and all(x is not None for x in r["outputs"]), (name, r["stderr"])
+        d = {"args": np.array(json.dumps(args)), "kind": np.array(kind), "idx": np.array(idx)}
+        for j in range(len(idx)):
+            d["out%d" % j] = np.frombuffer(r["outputs"][j], dtype=np.uint8)
+            if ev is not None:
+                d["extvad%d" % j] = ev[j]
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+        print(name, "ok")
     # feature-file input
     for name, args in FEAIN_CASES.items():
         if sys.argv[1:] and name not in sys.argv[1:]:

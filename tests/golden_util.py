@@ -20,7 +20,7 @@ def inputs():
 
 
 def case_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("inputs.npz", "fb_design.npz") and not f.startswith("cmvn") and not f.startswith("feain_") and not f.startswith("g711_"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("inputs.npz", "fb_design.npz") and not f.startswith("cmvn") and not f.startswith("feain_") and not f.startswith("g711_") and not f.startswith("carry_"))
 
 
 def g711_case(name):
@@ -33,6 +33,21 @@ def g711_case(name):
 def feain_case_names():
     """Feature-file input goldens (-format_in htk): Case(name).source names the golden whose payloads are the inputs."""
     return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.startswith("feain_") and f.endswith(".npz"))
+
+
+def carry_case_names():
+    """*ss modes over a list in one reference process (the opt-in "ss_carry" semantics)"""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.startswith("carry_") and f.endswith(".npz"))
+
+
+def carry_case(name):
+    """(args, kind, input indices in list order, [output bytes per file], [external VAD flags per file] or None)"""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    idx = [int(i) for i in z["idx"]]
+    outs = [z["out%d" % j].tobytes() for j in range(len(idx))]
+    ev = [z["extvad%d" % j] for j in range(len(idx))] if "extvad0" in z.files else None
+    args = [a.replace("{VADIN}", "vadin.bin") for a in json.loads(str(z["args"]))]
+    return args, str(z["kind"]), idx, outs, ev
 
 
 def cmvn_case(name):

@@ -58,6 +58,24 @@ def test_cli_td_iir_mfcc_files(tmp_path):
         assert np.all(np.abs(a - b) <= 1e-4 * np.abs(b) + 1e-3), (i, np.abs(a - b).max())
 
 
+def test_cli_ss_carry_reproduces_the_reference_list_run(tmp_path):
+    """-ss_carry on: fwss over a three-file list as ONE reference process writes it (every file's noise estimate starts from
+    the enhanced last frame of the file before, src/nr/nr.cc:212-222); without the option the second file differs grossly."""
+    args, kind, idx, outs, ev = gu.carry_case("carry_fwss_burg")
+    ins = [gu.inputs()[i] for i in idx]
+    run_cli(str(tmp_path), args + ["-ss_carry", "on"], ins)
+    for j in range(len(idx)):
+        got = open(tmp_path / ("u%d.out" % j), "rb").read()
+        assert len(got) == len(outs[j]) and got[:12] == outs[j][:12], j
+        a, b = rr.parse_htk(got)[1], rr.parse_htk(outs[j])[1]
+        assert np.all(np.abs(a - b) <= 1e-4 * np.abs(b) + 2e-3), (j, np.abs(a - b).max())
+    run_cli(str(tmp_path), args, ins)
+    a, b = rr.parse_htk(open(tmp_path / "u1.out", "rb").read())[1], rr.parse_htk(outs[1])[1]
+    assert np.abs(a - b).max() > 1.0
+    pr = subprocess.run([EXE] + args + ["-ss_carry", "on", "-gpus", "2", "-S", str(tmp_path / "list.scp")], capture_output=True)
+    assert pr.returncode != 0 and b"-ss_carry" in pr.stderr
+
+
 def test_cli_pfile_band_domain_path_is_byte_identical(tmp_path):
     c = gu.Case("fwss_file_afterFB_pfile")
     for i in (0, 4):

@@ -112,6 +112,41 @@ def test_cuda_matches_reference_golden(name):
             assert np.array_equal(gotv, v), (name, i, "VAD decisions differ at %d frames" % int((gotv != v).sum()))
 
 
+@pytest.mark.parametrize("name", gu.carry_case_names())
+def test_cuda_list_carry_matches_reference_golden(name):
+    """ss_carry (opt-in): hwss / fwss / 2fwss with the reference's LIST semantics -- a file's noise estimate starts from the
+    enhanced last frame of the file before it (src/nr/nr.cc:212-222, 397-408).  The goldens are the files of ONE reference
+    process; detector decisions bit for bit.  (The carried value itself has the tolerance of the previous file's last row,
+    so the conditioning probe starts from the oracle's carry.)"""
+    args, kind, idx, outs, ev = gu.carry_case(name)
+    o = co.parse_args(args)
+    ins = [gu.inputs()[i] for i in idx]
+    res = cb.extract(args, ins, ev, options={"ss_carry": 1})
+    refs = co.run_list_carry(ins, o, ev)
+    ps = _sweep_module()
+    for j, u in enumerate(ins):
+        if kind == "raw":
+            want = np.frombuffer(outs[j], dtype="<i2")
+            got = res.utt_waveform(j)
+            assert got.shape == want.shape, (name, j)
+            d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+            assert d.max() <= 1 and (d > 0).mean() < WAVE_MAX_FRAC, (name, j, d.max(), (d > 0).mean())
+        else:
+            want = gu.rr.parse_htk(outs[j])[1]
+            sens = ps.sensitivity(args, o, u, refs[j], None if ev is None else ev[j], refs[j].navg0)
+            check_features(name, j, res.utt_features(j), want, o.fea_kind, sens)
+        if refs[j].vad_nr is not None and o.vadmode == "burg":
+            r0 = int(res.row_offsets[j])
+            assert np.array_equal(res.vad_nr[r0: r0 + refs[j].nframes].astype(bool), refs[j].vad_nr), (name, j)
+    # and a second call on a fresh handle without the option gives the per-utterance result again
+    solo = cb.extract(args, ins[1:2], None if ev is None else ev[1:2])
+    ref1 = co.run_pipeline(ins[1], o, None if ev is None else ev[1])
+    if kind == "raw":
+        assert np.abs(solo.utt_waveform(0).astype(np.int32) - ref1.waveform.astype(np.int32)).max() <= 1
+    else:
+        check_features(name, 1, solo.utt_features(0), ref1.features, o.fea_kind, ps.sensitivity(args, o, ins[1], ref1, None if ev is None else ev[1]))
+
+
 PARITY_SET = [synthetic.utterance(k, sec) for k, sec in [(0, 1.0), (1, 2.5), (2, 1.0), (3, 2.5), (4, 1.0), (5, 1.0), (6, 2.5), (7, 1.0),
                                                          (8, 1.0), (9, 2.5), (10, 1.0), (11, 1.0), (12, 1.0), (13, 2.5), (14, 1.0)]]
 B = ["-fs", "16000", "-format_in", "raw", "-dither", "0"]

@@ -5,6 +5,7 @@ import pytest
 
 import ctu_oracle as co
 import golden_util as gu
+import ref_runner as rr
 
 
 # lpa on a mel bank without the ^0.33 law squares the band POWERS (src/fea/fea_impl.cc:165-169);
@@ -197,3 +198,23 @@ def test_oracle_g711_input_matches_reference_binary(name):
             assert np.array_equal(got, want), (name, i)
         else:
             np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", gu.carry_case_names())
+def test_oracle_list_carry_matches_reference_binary(name):
+    """hwss / fwss / 2fwss over a list in ONE reference process: a file's noise estimate starts from the enhanced last frame of
+    the file before it (src/nr/nr.cc:212-222, 397-408; for waveform output with the Nyquist bin negated by sigOUT,
+    src/io/out.cc:414; on the band path after FEA's in-place logarithm / square).  co.run_list_carry restates that; the files
+    of the list must come out bit for bit."""
+    args, kind, idx, outs, ev = gu.carry_case(name)
+    o = co.parse_args(args)
+    res = co.run_list_carry([gu.inputs()[i] for i in idx], o, ev)
+    for j in range(len(idx)):
+        if kind == "raw":
+            assert np.array_equal(res[j].waveform, np.frombuffer(outs[j], dtype="<i2")), (name, j)
+        else:
+            want = rr.parse_htk(outs[j])[1]
+            got = res[j].features
+            assert got.shape == want.shape and gu.same_nonfinite(got, want), (name, j)
+            fin = np.isfinite(want)
+            assert np.array_equal(got[fin], want[fin]), (name, j, np.abs(got - want)[fin].max())

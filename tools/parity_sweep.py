@@ -105,7 +105,7 @@ def draw16(rng):
     return a
 
 
-def sensitivity(args, o, pcm, ref=None, ext_vad=None):
+def sensitivity(args, o, pcm, ref=None, ext_vad=None, navg0=None):
     """How far the oracle's own output for this configuration and input moves when the spectrum that leaves its front end
     moves by one rounding error of the CUDA front end (co.run_pipeline(perturb=...)): |out(perturbed) - out|, the larger of
     two sign patterns.  None when the configuration has no spectral subtraction (every other chain is well conditioned and
@@ -117,12 +117,12 @@ def sensitivity(args, o, pcm, ref=None, ext_vad=None):
     if o.nr_mode == "none" or o.format_out in ("raw", "wave") or o.vad_apply_mode != "none" or o.vad_out_mode != "none":
         return None
     if ref is None:
-        ref = co.run_pipeline(pcm, o, ext_vad)
+        ref = co.run_pipeline(pcm, o, ext_vad, navg0=navg0)
     eps = 4.4e-16 if o.nr_when == "afterFB" else 2.4e-7
     sens = None
     for seed in (1, 2):
         with np.errstate(all="ignore"):
-            r = co.run_pipeline(pcm, o, ext_vad, perturb=(eps, seed), force_vad_nr=ref.vad_nr)
+            r = co.run_pipeline(pcm, o, ext_vad, perturb=(eps, seed), force_vad_nr=ref.vad_nr, navg0=navg0)
         if r.features.shape != ref.features.shape:
             return None
         d = np.abs(r.features.astype(np.float64) - ref.features.astype(np.float64))
