@@ -1,5 +1,5 @@
 // fp64 building blocks of the GENERAL kernels (FFT sizes other than 512): one warp owns a frame, the transform is an
-// in-place radix-2 FFT of nfft/2 complex points in shared memory.  Used by the general synthesis (ctu_synth_any.cuh) and
+// in-place FFT (radix-4 passes) of nfft/2 complex points in shared memory.  Used by the general synthesis (ctu_synth_any.cuh) and
 // by the general Burg front end below.  Speed is secondary here (every BASELINE configuration takes the 512-point
 // kernels); the arithmetic conventions are those of k_synth / k_burg, restated from the same reference lines.
 #ifndef CTU_ANY64_CUH
@@ -19,22 +19,38 @@ struct AnyTables64 {
 
 constexpr int ANY64_THREADS = 128;            // 4 warps per CTA
 
-// in-place radix-2 decimation-in-time FFT of M complex points held by one warp in shared memory
+// in-place decimation-in-time FFT of M complex points held by one warp in shared memory
 __device__ __forceinline__ void warp_fft_radix2(cpx<double> *z, int M, int log2m, const double2 *__restrict__ tw, int lane) {
     for (int n = lane; n < M; n += 32) {
         const int r = (int)(__brev((unsigned)n) >> (32 - log2m));
         if (r > n) { const cpx<double> t = z[n]; z[n] = z[r]; z[r] = t; }
     }
     __syncwarp();
-    for (int len = 2, shift = log2m - 1; len <= M; len <<= 1, shift--) {
-        const int half = len >> 1;
+    // one radix-2 stage when log2(M) is odd, then radix-4 passes (two radix-2 stages of half lengths h and 2h fused: the four
+    // points p, p+h, p+2h, p+3h are read and written once; the second stage's odd twiddle is -i times the even one)
+    int h = 1, sh = log2m - 1;
+    if (log2m & 1) {
         for (int b = lane; b < (M >> 1); b += 32) {
-            const int j0 = b & (half - 1), i0 = ((b - j0) << 1) + j0, i1 = i0 + half;
-            const double2 w = __ldg(tw + ((size_t)j0 << shift));
-            const cpx<double> t = cmul(z[i1], mk<double>(w.x, w.y));
-            const cpx<double> a = z[i0];
-            z[i0] = a + t;
-            z[i1] = a - t;
+            const cpx<double> a = z[2 * b], t = z[2 * b + 1];
+            z[2 * b] = a + t;
+            z[2 * b + 1] = a - t;
+        }
+        __syncwarp();
+        h = 2; sh--;
+    }
+    for (; 4 * h <= M; h <<= 2, sh -= 2) {
+        for (int q = lane; q < (M >> 2); q += 32) {
+            const int j = q & (h - 1), p0 = ((q - j) << 2) + j;
+            const double2 w1 = __ldg(tw + ((size_t)j << sh)), w2 = __ldg(tw + ((size_t)j << (sh - 1)));
+            const cpx<double> z0 = z[p0], t1 = cmul(z[p0 + h], mk<double>(w1.x, w1.y));
+            const cpx<double> z2 = z[p0 + 2 * h], t3 = cmul(z[p0 + 3 * h], mk<double>(w1.x, w1.y));
+            const cpx<double> a0 = z0 + t1, a1 = z0 - t1;
+            const cpx<double> u2 = cmul(z2 + t3, mk<double>(w2.x, w2.y)), u3 = cmul(z2 - t3, mk<double>(w2.x, w2.y));
+            const cpx<double> v3 = mk<double>(u3.y, -u3.x);           // -i u3
+            z[p0] = a0 + u2;
+            z[p0 + 2 * h] = a0 - u2;
+            z[p0 + h] = a1 + v3;
+            z[p0 + 3 * h] = a1 - v3;
         }
         __syncwarp();
     }

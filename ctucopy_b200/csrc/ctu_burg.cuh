@@ -34,6 +34,17 @@ constexpr int BURG_HALF = TILE_F / 2;                     // frames per CTA
 // without a frame of its own recomputes the tile's last frame and skips the stores).  With the per-group masks of round 1
 // every shuffle was wrapped in BSSY / WARPSYNC / ENDCOLLECTIVE / BSYNC: a fifth of the kernel's instructions.
 __device__ __forceinline__ double shfl16d(double v, int src) { return __shfl_sync(0xffffffffu, v, src, 16); }
+// num / den without the IEEE division sequence (range checks, a slow-path call: ~16 instructions and a branch, eleven times
+// per frame): hardware reciprocal seed, two Newton steps, one correction of the quotient -- within an ulp of the rounded
+// quotient; 0 / 0 and x / 0 come out NaN / inf as the reference's division gives them
+__device__ __forceinline__ double fast_div(double n, double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(fma(-d, r, 1.0), r, r);
+    r = fma(fma(-d, r, 1.0), r, r);
+    const double q = n * r;
+    return fma(fma(-d, q, n), r, q);
+}
 __device__ __forceinline__ double group_sum16d_all(double v) {
     v += __shfl_xor_sync(0xffffffffu, v, 8);
     v += __shfl_xor_sync(0xffffffffu, v, 4);
@@ -284,7 +295,7 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, int nha
                     num = group_sum16d_all((nu[0] + nu[1]) + (nu[2] + nu[3])) * 2.0;
                     den = den_c;
                 }
-                const double rc = -num / den;
+                const double rc = -fast_div(num, den);
                 const double om = 1 - rc * rc;
                 alpha *= om;
 #pragma unroll
@@ -321,7 +332,7 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, int nha
                     double sum = 0;
 #pragma unroll
                     for (int k = 1; k < BURG_MAXC; k++) if (k < n) sum += (double)(n - k) * cc[(n - k) & (BURG_MAXC - 1)] * av[k];
-                    cc[n] = -av[n] - sum / n;
+                    cc[n] = -av[n] - sum * (1.0 / n);                 // (1 / n is a compile-time constant: the loop is unrolled)
                     if (n < ncoef) o[n] = cc[n];
                 }
                 o[0] = log(alpha);

@@ -25,9 +25,33 @@ struct AnyTables {
     const float *fbw;        // packed filter-bank taps (scaled like FrameParams::w), bands 16-byte aligned
     const int4 *bands;       // [nb] {lo, ntaps, woff, 0}
     int nfft, log2m;
+    // CTA-level copies in shared memory behind the per-warp areas (float offsets, -1 = read from global): every butterfly,
+    // window multiply and filter-bank tap used to be a dependent global load; the host stages what fits without costing a
+    // resident CTA (any_stage_layout)
+    int o_tw, o_ts, o_win, o_fbw, nfbw;
+    int o_m2, nm2;           // the second-stage matrix (DCT + lifter), TRANSPOSED: [nb][nrows]
 };
 
 __host__ __device__ inline size_t any_smem_floats_per_warp(int nfft) { return (size_t)nfft /* M complex */ + (nfft / 2 + 4) /* bins */ + MAXB + 4; }
+
+// which tables go to shared memory: in the order twiddles, split twiddles, window, filter-bank taps, as long as the CTA keeps
+// the residency its per-warp areas alone would have (at most 8 CTAs of 256 threads per SM)
+inline size_t any_stage_layout(AnyTables &tb, int window) {
+    const size_t base = any_smem_floats_per_warp(tb.nfft) * (256 / 32);
+    const size_t cap = (227 * 1024 - 8 * 1024) / sizeof(float);                       // per SM, minus the per-CTA reservations
+    const size_t ctas = std::max<size_t>(1, std::min<size_t>(8, cap / base));
+    const size_t budget = cap / ctas;
+    const int M = tb.nfft / 2;
+    size_t o = base;
+    auto take = [&](int &off, size_t n) { n = (n + 3) & ~(size_t)3; if (o + n <= budget) { off = (int)o; o += n; } else off = -1; };
+    take(tb.o_m2, (size_t)tb.nm2);         // first: read with a per-lane index, which the constant bank serialises (13 x 26
+                                           // replays per frame: the DCT alone took half the time of an 8 kHz MFCC frame)
+    take(tb.o_tw, (size_t)M);              // M/2 float2
+    take(tb.o_ts, (size_t)2 * (M + 1));
+    take(tb.o_win, (size_t)window);
+    take(tb.o_fbw, (size_t)tb.nfbw);
+    return o * sizeof(float);
+}
 
 // -remove_dc1 (src/io/in.cc:343-350): mean of the ring at frame t, m_t = mean(raw frame t) - sum_d m_{t-d} (w - d s) / w
 // (the overlap with frame t-d has already lost m_{t-d}).  One warp per utterance, frames in order, fp64.
@@ -70,6 +94,20 @@ k_frames_any(const __grid_constant__ FrameParams P, BatchDesc bd, AnyTables tb, 
     const int nf = min(ANY_TILE, bd.nframes[u] - t0);
     const int64_t row0 = bd.row_off[u] + t0;
     const int w = P.window, s = P.wshift, nb = P.nb;
+    // tables: shared-memory copies where the host found room for them
+    const float2 *twp = tb.tw, *tsp = tb.twsplit;
+    const float *winp = tb.win, *fbwp = tb.fbw;
+    if (tb.o_tw >= 0) { float2 *d = reinterpret_cast<float2 *>(sm + tb.o_tw); for (int i = threadIdx.x; i < (M >> 1); i += ANY_THREADS) d[i] = tb.tw[i]; twp = d; }
+    if (tb.o_ts >= 0) { float2 *d = reinterpret_cast<float2 *>(sm + tb.o_ts); for (int i = threadIdx.x; i <= M; i += ANY_THREADS) d[i] = tb.twsplit[i]; tsp = d; }
+    if (tb.o_win >= 0 && SRC == SRC_PCM) { float *d = sm + tb.o_win; for (int i = threadIdx.x; i < w; i += ANY_THREADS) d[i] = tb.win[i]; winp = d; }
+    const float *m2t = nullptr;
+    if (tb.o_m2 >= 0 && DST == DST_FEA && KIND == KIND_DCTC) {
+        float *d = sm + tb.o_m2;
+        for (int i = threadIdx.x; i < P.nrows * nb; i += ANY_THREADS) d[(i % nb) * P.nrows + i / nb] = P.m2[(i / nb) * P.nbp + i % nb];
+        m2t = d;
+    }
+    if (tb.o_fbw >= 0 && SRC != SRC_FB && DST != DST_SPEC) { float *d = sm + tb.o_fbw; for (int i = threadIdx.x; i < tb.nfbw; i += ANY_THREADS) d[i] = tb.fbw[i]; fbwp = d; }
+    __syncthreads();
     constexpr bool WANT_LOG = (DST == DST_FEA) && (KIND == KIND_DCTC || KIND == KIND_LOGSPEC || KIND == KIND_TRAPLOG);
     for (int f = wv; f < nf; f += ANY_THREADS / 32) {
         // ---- A: frame -> spectrum row ------------------------------------------------------------
@@ -101,7 +139,7 @@ k_frames_any(const __grid_constant__ FrameParams P, BatchDesc bd, AnyTables tb, 
                         if (i > 0) xp -= ring_off(i - 1, 0);
                         else if (!at_start) xp -= ring_off(s - 1, 1);
                     }
-                    v = tb.win[i] * fmaf(-P.preem, xp, xi);
+                    v = winp[i] * fmaf(-P.preem, xp, xi);
                 }
                 y[i] = v;
                 sum += v;
@@ -120,23 +158,40 @@ k_frames_any(const __grid_constant__ FrameParams P, BatchDesc bd, AnyTables tb, 
                 if (r > n) { const cpx<float> t = z[n]; z[n] = z[r]; z[r] = t; }
             }
             __syncwarp();
-            // radix-2 decimation in time
-            for (int len = 2, shift = tb.log2m - 1; len <= M; len <<= 1, shift--) {
-                const int half = len >> 1;
+            // decimation in time on the bit-reversed points: one radix-2 stage when log2(M) is odd, then radix-4 passes (two
+            // radix-2 stages of half lengths h and 2h fused: the four points p, p+h, p+2h, p+3h are read and written once, the
+            // second stage's odd twiddle is -i times the even one).  A third of the shared-memory passes and warp barriers
+            // of the radix-2 loop this replaces.
+            int h = 1, sh = tb.log2m - 1;                             // first stage: half length h, twiddle tw[j << sh]
+            if (tb.log2m & 1) {
                 for (int b = lane; b < (M >> 1); b += 32) {
-                    const int j0 = b & (half - 1), i0 = ((b - j0) << 1) + j0, i1 = i0 + half;
-                    const float2 tw = __ldg(tb.tw + ((size_t)j0 << shift));
-                    const cpx<float> t = cmul(z[i1], mk<float>(tw.x, tw.y));
-                    const cpx<float> a = z[i0];
-                    z[i0] = a + t;
-                    z[i1] = a - t;
+                    const cpx<float> a = z[2 * b], t = z[2 * b + 1];
+                    z[2 * b] = a + t;
+                    z[2 * b + 1] = a - t;
+                }
+                __syncwarp();
+                h = 2; sh--;
+            }
+            for (; 4 * h <= M; h <<= 2, sh -= 2) {
+                for (int q = lane; q < (M >> 2); q += 32) {
+                    const int j = q & (h - 1), p0 = ((q - j) << 2) + j;
+                    const float2 w1 = twp[(size_t)j << sh], w2 = twp[(size_t)j << (sh - 1)];
+                    const cpx<float> z0 = z[p0], t1 = cmul(z[p0 + h], mk<float>(w1.x, w1.y));
+                    const cpx<float> z2 = z[p0 + 2 * h], t3 = cmul(z[p0 + 3 * h], mk<float>(w1.x, w1.y));
+                    const cpx<float> a0 = z0 + t1, a1 = z0 - t1;
+                    const cpx<float> u2 = cmul(z2 + t3, mk<float>(w2.x, w2.y)), u3 = cmul(z2 - t3, mk<float>(w2.x, w2.y));
+                    const cpx<float> v3 = mk<float>(u3.y, -u3.x);     // -i u3
+                    z[p0] = a0 + u2;
+                    z[p0 + 2 * h] = a0 - u2;
+                    z[p0 + h] = a1 + v3;
+                    z[p0 + 3 * h] = a1 - v3;
                 }
                 __syncwarp();
             }
             // real-input split, power / magnitude
             for (int k = lane; k <= M; k += 32) {
                 const cpx<float> A = z[k == M ? 0 : k], B = conj(z[k == 0 ? 0 : M - k]);
-                const float2 ts = __ldg(tb.twsplit + k);
+                const float2 ts = tsp[k];
                 const cpx<float> X = mk<float>(0.5f * (A.x + B.x), 0.5f * (A.y + B.y)) + cmul(mk<float>(ts.x, ts.y), A - B);
                 float p = X.x * X.x + X.y * X.y;
                 if (k == 0 && P.remove_dc) p = 1e-10f;                // fixed floor (src/io/in.cc:390)
@@ -166,9 +221,9 @@ k_frames_any(const __grid_constant__ FrameParams P, BatchDesc bd, AnyTables tb, 
             for (int b = lane; b < nb; b += 32) {
                 const int4 bs = __ldg(tb.bands + b);
                 const float *r = row + bs.x;
-                const float *wq = tb.fbw + bs.z;
+                const float *wq = fbwp + bs.z;
                 float acc = 0.f;
-                for (int k = 0; k < bs.y; k++) acc = fmaf(r[k], __ldg(wq + k), acc);   // the reference's summation order
+                for (int k = 0; k < bs.y; k++) acc = fmaf(r[k], wq[k], acc);   // the reference's summation order
                 const bool lg = WANT_LOG && !late_log;
                 float yv;
                 if (P.inld) { yv = powf(acc, 0.33f) * P.inld_scale; if (lg) yv = logf(yv); }
@@ -188,9 +243,13 @@ k_frames_any(const __grid_constant__ FrameParams P, BatchDesc bd, AnyTables tb, 
         float *g = dst + (row0 + f) * P.out_stride;
         if (KIND == KIND_DCTC) {
             for (int i = lane; i < P.nrows; i += 32) {
-                const float *m = P.m2 + i * P.nbp;
                 float acc = 0.f;
-                for (int k = 0; k < nb; k++) acc = fmaf(sY[k], m[k], acc);
+                if (m2t) {
+                    for (int k = 0; k < nb; k++) acc = fmaf(sY[k], m2t[k * P.nrows + i], acc);      // lanes read consecutive words
+                } else {
+                    const float *m = P.m2 + i * P.nbp;
+                    for (int k = 0; k < nb; k++) acc = fmaf(sY[k], m[k], acc);
+                }
                 g[i] = acc;
             }
         } else {
