@@ -1051,7 +1051,8 @@ static int launch_frames_w(ctu_handle *h, const FrameParams &P, const ctu_plan *
         int log2m = 0;
         while ((1 << (log2m + 1)) <= h->cfg.wfft / 2) log2m++;
         AnyTables tb{h->d_any_tw, h->d_any_ts, h->d_win, h->d_any_fbw, h->d_any_bands, h->cfg.wfft, log2m, -1, -1, -1, -1, (int)h->fbw_all.size(), -1,
-                     (DST == DST_FEA && KIND == KIND_DCTC) ? P.nrows * P.nb : 0};
+                     (DST == DST_FEA && KIND == KIND_DCTC) ? P.nrows * P.nb : 0, -1,
+                     (SRC == SRC_PCM && !P.dither && !P.dc1) ? (ANY_TILE - 1) * P.wshift + P.window : 0};
         const size_t bytes = any_stage_layout(tb, h->cfg.window);
         auto kern = k_frames_any<SRC, DST, KIND>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));

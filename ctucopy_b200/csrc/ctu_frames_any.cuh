@@ -30,6 +30,7 @@ struct AnyTables {
     // resident CTA (any_stage_layout)
     int o_tw, o_ts, o_win, o_fbw, nfbw;
     int o_m2, nm2;           // the second-stage matrix (DCT + lifter), TRANSPOSED: [nb][nrows]
+    int o_pcm, npcm;         // the tile's pre-emphasised samples as floats (plain configurations: no dither, no -remove_dc1)
 };
 
 __host__ __device__ inline size_t any_smem_floats_per_warp(int nfft) { return (size_t)nfft /* M complex */ + (nfft / 2 + 4) /* bins */ + MAXB + 4; }
@@ -46,6 +47,8 @@ inline size_t any_stage_layout(AnyTables &tb, int window) {
     auto take = [&](int &off, size_t n) { n = (n + 3) & ~(size_t)3; if (o + n <= budget) { off = (int)o; o += n; } else off = -1; };
     take(tb.o_m2, (size_t)tb.nm2);         // first: read with a per-lane index, which the constant bank serialises (13 x 26
                                            // replays per frame: the DCT alone took half the time of an 8 kHz MFCC frame)
+    take(tb.o_pcm, (size_t)tb.npcm);       // the 16 frames of a tile overlap 2-3 times: one coalesced pass instead of two 2-byte
+                                           // global loads and two conversions per sample and frame
     take(tb.o_tw, (size_t)M);              // M/2 float2
     take(tb.o_ts, (size_t)2 * (M + 1));
     take(tb.o_win, (size_t)window);
@@ -100,6 +103,17 @@ k_frames_any(const __grid_constant__ FrameParams P, BatchDesc bd, AnyTables tb, 
     if (tb.o_tw >= 0) { float2 *d = reinterpret_cast<float2 *>(sm + tb.o_tw); for (int i = threadIdx.x; i < (M >> 1); i += ANY_THREADS) d[i] = tb.tw[i]; twp = d; }
     if (tb.o_ts >= 0) { float2 *d = reinterpret_cast<float2 *>(sm + tb.o_ts); for (int i = threadIdx.x; i <= M; i += ANY_THREADS) d[i] = tb.twsplit[i]; tsp = d; }
     if (tb.o_win >= 0 && SRC == SRC_PCM) { float *d = sm + tb.o_win; for (int i = threadIdx.x; i < w; i += ANY_THREADS) d[i] = tb.win[i]; winp = d; }
+    const float *spcm = nullptr;
+    if (SRC == SRC_PCM && tb.o_pcm >= 0 && tb.npcm > 0 && !P.dither && !P.dc1) {
+        float *d = sm + tb.o_pcm;
+        const int16_t *x = pcm + bd.pcm_off[u] + (int64_t)t0 * s;
+        const int ns = (nf - 1) * s + w;
+        for (int i = threadIdx.x; i < ns; i += ANY_THREADS) {
+            const float xi = (float)x[i], xp = (i == 0 && t0 == 0) ? 0.f : (float)x[i - 1];
+            d[i] = fmaf(-P.preem, xp, xi);
+        }
+        spcm = d;
+    }
     const float *m2t = nullptr;
     if (tb.o_m2 >= 0 && DST == DST_FEA && KIND == KIND_DCTC) {
         float *d = sm + tb.o_m2;
@@ -127,21 +141,26 @@ k_frames_any(const __grid_constant__ FrameParams P, BatchDesc bd, AnyTables tb, 
                 for (int d = d0; d < nd; d++) if (i + (d - d0) * s < w) c += md[d];
                 return c;
             };
+            // the frame goes straight to its bit-reversed place: complex point n = i / 2 lands at rev(n)
+            const int rsh = 32 - tb.log2m;
             for (int i = lane; i < nfft; i += 32) {
                 float v = 0.f;
                 if (i < w) {
-                    float xi = (float)x[i];
-                    float xp = (i == 0 && at_start) ? 0.f : (float)x[i - 1];
-                    if (dn) { xi += dn[i]; if (!(i == 0 && at_start)) xp += dn[i - 1]; }
-                    if (P.dc1) {
-                        xi -= ring_off(i, 0);
-                        // the sample before the frame was remembered at the end of frame t-1 (src/io/in.cc:384)
-                        if (i > 0) xp -= ring_off(i - 1, 0);
-                        else if (!at_start) xp -= ring_off(s - 1, 1);
+                    if (spcm) v = winp[i] * spcm[f * s + i];
+                    else {
+                        float xi = (float)x[i];
+                        float xp = (i == 0 && at_start) ? 0.f : (float)x[i - 1];
+                        if (dn) { xi += dn[i]; if (!(i == 0 && at_start)) xp += dn[i - 1]; }
+                        if (P.dc1) {
+                            xi -= ring_off(i, 0);
+                            // the sample before the frame was remembered at the end of frame t-1 (src/io/in.cc:384)
+                            if (i > 0) xp -= ring_off(i - 1, 0);
+                            else if (!at_start) xp -= ring_off(s - 1, 1);
+                        }
+                        v = winp[i] * fmaf(-P.preem, xp, xi);
                     }
-                    v = winp[i] * fmaf(-P.preem, xp, xi);
                 }
-                y[i] = v;
+                y[2 * (int)(__brev((unsigned)(i >> 1)) >> rsh) + (i & 1)] = v;
                 sum += v;
             }
             if (P.remove_dc) {
@@ -149,13 +168,7 @@ k_frames_any(const __grid_constant__ FrameParams P, BatchDesc bd, AnyTables tb, 
                 for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
                 const float mean = sum / (float)w;                    // of the windowed frame, subtracted inside the window only
                 __syncwarp();
-                for (int i = lane; i < w; i += 32) y[i] -= mean;
-            }
-            __syncwarp();
-            // bit-reversal permutation of the M complex points (z[n] = y[2n] + i y[2n+1])
-            for (int n = lane; n < M; n += 32) {
-                const int r = (int)(__brev((unsigned)n) >> (32 - tb.log2m));
-                if (r > n) { const cpx<float> t = z[n]; z[n] = z[r]; z[r] = t; }
+                for (int i = lane; i < w; i += 32) y[2 * (int)(__brev((unsigned)(i >> 1)) >> rsh) + (i & 1)] -= mean;
             }
             __syncwarp();
             // decimation in time on the bit-reversed points: one radix-2 stage when log2(M) is odd, then radix-4 passes (two

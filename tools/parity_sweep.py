@@ -109,12 +109,12 @@ def sensitivity(args, o, pcm, ref=None, ext_vad=None, navg0=None):
     """How far the oracle's own output for this configuration and input moves when the spectrum that leaves its front end
     moves by one rounding error of the CUDA front end (co.run_pipeline(perturb=...)): |out(perturbed) - out|, the larger of
     two sign patterns.  None when the configuration has no spectral subtraction (every other chain is well conditioned and
-    is held to north_star's bar alone) or when the VAD module could change the row count.
+    is held to north_star's bar alone) or when the VAD module changes rows (drop / silence).
     The rounding error: the device computes the spectrum in fp32 (two ulps of the power spectrum = 2.4e-7) except on the
     fp64 band path taken by noise reduction after the filter bank (4.4e-16).  A spectral subtraction |X| - b N that cancels
     k digits turns that into 1e-7 x 10^k of its result, and a logarithm or a cube root behind it amplifies it again; the
     reference itself, run against another FFT library, moves by as much there."""
-    if o.nr_mode == "none" or o.format_out in ("raw", "wave") or o.vad_apply_mode != "none" or o.vad_out_mode != "none":
+    if o.nr_mode == "none" or o.format_out in ("raw", "wave") or o.vad_apply_mode != "none":
         return None
     if ref is None:
         ref = co.run_pipeline(pcm, o, ext_vad, navg0=navg0)
