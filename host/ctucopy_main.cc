@@ -433,7 +433,7 @@ constexpr int IO_THREADS = 8;
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 const bool g_timing = std::getenv("CTU_TIMING") != nullptr;     // stage times on stderr
 double g_t0 = now_s();
-void tmark(const char *what, double t0) { if (g_timing) std::fprintf(stderr, "[ctu timing] %-28s %.3f s   (ends at %.3f)\n", what, now_s() - t0, now_s() - g_t0); }
+void tmark(const char *what, double t0) { if (g_timing) std::fprintf(stderr, "[ctu timing] %-28s %.4f s   (ends at %.3f)\n", what, now_s() - t0, now_s() - g_t0); }
 
 void parallel_for(size_t n, int nthreads, const std::function<void(size_t)> &fn) {
     std::atomic<size_t> next{0};
