@@ -20,6 +20,7 @@
 #include "ctu_nr_params.cuh"
 #include "ctu_precise.cuh"
 #include "ctu_tdiir.cuh"
+#include "ctu_frames256.cuh"
 #include "ctu_bank.cuh"
 #include "ctu_synth_any.cuh"
 
@@ -85,6 +86,7 @@ struct ctu_handle {
     BankTables bank;                           // k_bank's packed filter bank (512-point feature chains)
     BankParams bkp{};
     float2 *d_any_tw = nullptr, *d_any_ts = nullptr;
+    float2 *d_tw128 = nullptr;                 // 256-point front end (ctu_frames256.cuh): W128^(g k1)
     double2 *d_any_tw64 = nullptr, *d_any_ts64 = nullptr;     // fp64 copies for the general synthesis (ctu_synth_any.cuh)
     float *d_any_fbw = nullptr;
     int4 *d_any_bands = nullptr;
@@ -112,6 +114,7 @@ struct ctu_handle {
     int split_front = 1;                 // 1: PCM -> spectrum -> features as two kernels; 0: the single fused kernel
     int synth_from_pcm = 0;              // 1: synthesis recomputes the forward transform instead of reading the stored X
     int fuse_nr = 1;                     // 1: the noise-reduction scan runs inside k_bank (tile in shared memory) where it can
+    int front256 = 1;                    // 1: 256-point frames take k_frames256 for PCM -> spectrum; 0: the general kernel throughout
     // hwss / fwss / 2fwss with the reference's LIST semantics (a file's noise estimate starts from the enhanced last frame of
     // the file before it, src/nr/nr.cc:212-222, 397-408): opt-in, one handle = one list walked in order on one GPU
     int ss_carry = 0;
@@ -529,6 +532,10 @@ static int build_delta_trap_params(ctu_handle *h) {
 
 // FFT size other than the specialised 512 points (the fp64 Burg / synthesis kernels then take their general form)
 static bool c_wfft_is_general(const ctu_handle *h) { return h->cfg.wfft != NFFT; }
+// 8 kHz-sized frames take the specialised 256-point front end (ctu_frames256.cuh) and the general kernel from the spectrum on
+static bool fast256(const ctu_handle *h) {
+    return h->generic && !h->fea_in && h->cfg.wfft == 256 && h->cfg.dither == 0.0 && !h->cfg.remove_dc1 && h->front256;
+}
 
 static int resolve_modes(ctu_handle *h) {
     const ctu_config &c = h->cfg;
@@ -704,6 +711,7 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     if (const char *e = getenv("CTU_SPLIT_FRONT")) h->split_front = atoi(e);
     if (getenv("CTU_SYNTH_FROM_PCM")) h->synth_from_pcm = 1;
     if (const char *e = getenv("CTU_FUSE_NR")) h->fuse_nr = atoi(e);
+    if (const char *e = getenv("CTU_FRONT256")) h->front256 = atoi(e);
     if (const char *e = getenv("CTU_CHUNK_MB")) h->chunk_mb = std::max(1, atoi(e));
     auto bail = [&](int st) { g_create_err = h->err; delete h; return st; };
     int st = ctu_config_finalize(&h->cfg);
@@ -780,6 +788,12 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
             while ((1 << lg) < M) lg++;
             h->bp.nfft = N; h->bp.log2m = lg; h->bp.any_tw = h->d_any_tw64; h->bp.any_ts = h->d_any_ts64;
         }
+        if (h->generic && N == 256) {
+            std::vector<float2> t128(128);
+            for (int k1 = 0; k1 < 16; k1++)
+                for (int g = 0; g < 8; g++) t128[k1 * 8 + g] = make_float2((float)cos(-2 * PI * (g * k1) / 128.0), (float)sin(-2 * PI * (g * k1) / 128.0));
+            if ((st = upload(h, &h->d_tw128, t128))) return bail(st);
+        }
         if (h->generic) {
             std::vector<float2> tw(std::max(1, M / 2)), ts(M + 1);
             for (int k = 0; k < M / 2; k++) tw[k] = make_float2((float)cos(-2 * PI * k / M), (float)sin(-2 * PI * k / M));
@@ -827,7 +841,7 @@ void ctu_destroy(ctu_handle *h) {
     cudaFree(h->d_any_tw); cudaFree(h->d_any_ts); cudaFree(h->d_any_fbw); cudaFree(h->d_any_bands);
     cudaFree(h->bank.d_bands); cudaFree(h->bank.d_w4); cudaFree(h->bank.d_m2);
     cudaFree(h->d_td_coefs); cudaFree(h->d_td_win); cudaFree(h->d_td_dct);
-    cudaFree(h->d_carry); cudaFree(h->d_carry64);
+    cudaFree(h->d_carry); cudaFree(h->d_carry64); cudaFree(h->d_tw128);
     if (h->carry_ev) cudaEventDestroy(h->carry_ev);
     for (auto &b : h->pool) cudaFree(b.p);
     for (int i = 0; i < 3; i++) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
@@ -958,7 +972,8 @@ int ctu_plan_create(ctu_handle *h, const int64_t *off, int32_t n, ctu_plan **out
     // 12.6 -> 11.8 (PLP), 14.9 -> 14.1 (TRAP-DCT) per 9.98 M frames; CTU_SPLIT_FRONT=0 restores the fused kernel
     const int split_front = h->split_front;
     const bool need_spec = h->signal_out || (nr_on && h->cfg.nr_when == 0) || (h->do_vad && h->vad_cri != VCRI_CEPDIST_FEA) ||
-                           (split_front && !h->precise && !h->generic && h->fea_kind != FEA_NONE);
+                           (split_front && !h->precise && !h->generic && h->fea_kind != FEA_NONE) ||
+                           (fast256(h) && !h->precise && h->fea_kind != FEA_NONE);
     const bool lpc_kind = (h->fea_kind == FEA_LPA || h->fea_kind == FEA_LPC);
     const bool need_fb = !h->signal_out && ((nr_on && h->cfg.nr_when == 1) || lpc_kind);
     if (need_spec && (st = dev_alloc(h, p, &p->d_spec, (size_t)rows * h->spitch))) { ctu_plan_destroy(p); return st; }
@@ -1046,6 +1061,20 @@ static int launch_frames_w(ctu_handle *h, const FrameParams &P, const ctu_plan *
     static const char *const names[3][3] = {{"k_frames<pcm,spec>", "k_frames<pcm,fb>", "k_frames<pcm,fea>"},
                                             {"k_frames<spec,spec>", "k_frames<spec,fb>", "k_frames<spec,fea>"},
                                             {"k_frames<fb,spec>", "k_frames<fb,fb>", "k_frames<fb,fea>"}};
+    if constexpr (SRC == SRC_PCM && DST == DST_SPEC) {
+        if (fast256(h) && !P.dither && !P.dc1) {
+            if (ft.n16 <= 0) return CTU_OK;
+            const size_t bytes = smem256_floats(P.window, P.wshift) * sizeof(float);
+            CK(cudaFuncSetAttribute(k_frames256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            BatchDesc bd{p->d_pcm_off, p->d_nframes, p->d_row_off, ft.t16};
+            Tables256 tb{h->d_tw128, h->d_any_ts, h->d_win};
+            h->lc.begin(names[SRC][DST], s);
+            k_frames256<<<(unsigned)ft.n16, F256_THREADS, bytes, s>>>(P, bd, tb, pcm, dst, h->nbins);
+            h->lc.end(s);
+            CK(cudaGetLastError());
+            return CTU_OK;
+        }
+    }
     if (h->generic) {
         if (ft.n16 <= 0) return CTU_OK;
         int log2m = 0;
@@ -1786,6 +1815,7 @@ int ctu_set_option(ctu_handle *h, const char *name, int64_t value) {
     else if (n == "split_front") h->split_front = value != 0;           // takes effect for plans created afterwards
     else if (n == "synth_from_pcm") h->synth_from_pcm = value != 0;     // takes effect for plans created afterwards
     else if (n == "fuse_nr") h->fuse_nr = value != 0;
+    else if (n == "front256") h->front256 = value != 0;                   // takes effect for plans created afterwards
     else return fail(h, CTU_ERR_CONFIG, "CTU: unknown run-time option " + n);
     return CTU_OK;
 }

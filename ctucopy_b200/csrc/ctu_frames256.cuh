@@ -1,0 +1,142 @@
+// K1t: PCM -> spectrum for 256-point frames (8 kHz telephone speech: 20-32 ms windows), the specialised front end of the
+// general path.  Same arithmetic as the 512-point front end k_frames2 (rawIN::get_frame, src/io/in.cc:305-419:
+// pre-emphasis, Hamming, mean of the windowed frame removed inside the window, real FFT, power, P[0] = 1e-10, optional
+// square root), organised the same way -- registers, one shared-memory transpose between two passes -- for half the
+// length:
+//   256 real points = 128 complex = 16 x 8.  A GROUP OF 8 THREADS owns a frame (four frames per warp); thread g holds the
+//   16 complex points z[8 n1 + g]: pass 1 is one 16-point DFT per thread over n1 (dft16, ctu_fft.cuh), the twiddle
+//   W128^(g k1), a transpose through a padded exchange tile; pass 2 is two 8-point DFTs per thread (k1 = g and g + 8) over
+//   the 8 threads' values; the real-input split reads Z[k] and Z[128 - k] from the tile and each thread finishes 17 of the
+//   129 bins.
+// The general kernel (k_frames_any: one WARP per frame, radix-4 passes in shared memory, a warp barrier per pass) needs
+// 14.7 ms per 8 M frames for this step; see DESIGN 11 for what this one measures.
+// Work unit: a tile of 16 consecutive frames of one utterance (the 16-frame tile list), 128 threads = 16 groups = one pass.
+#ifndef CTU_FRAMES256_CUH
+#define CTU_FRAMES256_CUH
+
+#include "ctu_kernels.cuh"
+
+namespace ctu {
+
+constexpr int F256_THREADS = 128;
+constexpr int F256_TILE = 16;                 // frames per CTA = groups per CTA
+constexpr int F256_M = 128;                   // complex points
+constexpr int F256_XP = 9;                    // pitch (complex) of a row of the 16 x 8 exchange tile
+constexpr int F256_GRP = 16 * F256_XP + 8;    // complex elements of a group's exchange tile: 144 (>= the 128 of the linear Z) + 8, so that
+                                              // the two groups of a half warp start 16 banks apart
+
+struct Tables256 {
+    const float2 *tw128;     // [16][8]: W128^(g k1) at [k1 * 8 + g]
+    const float2 *twsplit;   // -i/2 e^{-2 pi i k / 256}, k <= 128
+    const float *win;        // analysis window [window]
+};
+
+__host__ __device__ inline size_t smem256_floats(int window, int wshift) {
+    return (size_t)2 * F256_TILE * F256_GRP + 2 * 128 + 2 * 130 + 256 + (size_t)((F256_TILE - 1) * wshift + window + 4);
+}
+
+// forward 8-point DFT in registers, natural order in and out
+template <class T> CTU_HD void dft8(cpx<T> (&a)[8]) {
+    const T r2 = (T)0.70710678118654752440;
+    cpx<T> e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6], o0 = a[1], o1 = a[3], o2 = a[5], o3 = a[7];
+    dft4(e0, e1, e2, e3);
+    dft4(o0, o1, o2, o3);
+    o1 = mk<T>((o1.x + o1.y) * r2, (o1.y - o1.x) * r2);              // W8^1 = (r2, -r2)
+    o2 = mul_mi(o2);                                                 // W8^2 = -i
+    o3 = mk<T>((o3.y - o3.x) * r2, -(o3.x + o3.y) * r2);             // W8^3 = (-r2, -r2)
+    a[0] = e0 + o0; a[4] = e0 - o0;
+    a[1] = e1 + o1; a[5] = e1 - o1;
+    a[2] = e2 + o2; a[6] = e2 - o2;
+    a[3] = e3 + o3; a[7] = e3 - o3;
+}
+
+__device__ __forceinline__ float group_sum8(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+__global__ void __launch_bounds__(F256_THREADS)
+k_frames256(const __grid_constant__ FrameParams P, BatchDesc bd, Tables256 tb, const int16_t *__restrict__ pcm, float *__restrict__ dst, int nbins) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x, g = tid & 7, grp = tid >> 3;
+    const int w = P.window, s = P.wshift;
+    cpx<float> *sX = reinterpret_cast<cpx<float> *>(sm);                                // [16 groups][144]
+    cpx<float> *sTw = sX + F256_TILE * F256_GRP;                                        // 128
+    cpx<float> *sTs = sTw + 128;                                                        // 129 (+1)
+    float *sW = reinterpret_cast<float *>(sTs + 130);                                   // 256
+    float *sD = sW + 256;                                                               // the tile's pre-emphasised samples
+    const int2 tile = bd.tiles[blockIdx.x];
+    const int u = tile.x, t0 = tile.y;
+    const int nf = min(F256_TILE, bd.nframes[u] - t0);
+    const int64_t row0 = bd.row_off[u] + t0;
+    for (int i = tid; i < 128; i += F256_THREADS) sTw[i] = mk<float>(tb.tw128[i].x, tb.tw128[i].y);
+    for (int i = tid; i < 129; i += F256_THREADS) sTs[i] = mk<float>(tb.twsplit[i].x, tb.twsplit[i].y);
+    for (int i = tid; i < 256; i += F256_THREADS) sW[i] = (i < w) ? tb.win[i] : 0.f;
+    {
+        const int16_t *x = pcm + bd.pcm_off[u] + (int64_t)t0 * s;
+        const int ns = (nf - 1) * s + w;
+        for (int i = tid; i < ns; i += F256_THREADS) {
+            const float xi = (float)x[i], xp = (i == 0 && t0 == 0) ? 0.f : (float)x[i - 1];
+            sD[i] = fmaf(-P.preem, xp, xi);                                             // pre-emphasis once per sample
+        }
+    }
+    __syncthreads();
+    // a group past the end of the tile recomputes the tile's last frame and stores nothing (shuffles name the full warp)
+    const bool store = grp < nf;
+    const int f = min(grp, nf - 1);
+    const float *d = sD + f * s;
+    cpx<float> *xch = sX + grp * F256_GRP;
+    cpx<float> a[16];
+    float sum = 0.f;
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) {
+        const int i0 = 16 * n1 + 2 * g;                    // complex point 8 n1 + g = real samples i0, i0 + 1
+        const float y0 = (i0 < w) ? sW[i0] * d[i0] : 0.f;
+        const float y1 = (i0 + 1 < w) ? sW[i0 + 1] * d[i0 + 1] : 0.f;
+        a[n1] = mk<float>(y0, y1);
+        sum += y0 + y1;
+    }
+    if (P.remove_dc) {
+        // mean of the WINDOWED frame, subtracted from the window's samples only (src/io/in.cc:375-382)
+        const float mean = group_sum8(sum) / (float)w;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) {
+            const int i0 = 16 * n1 + 2 * g;
+            if (i0 < w) a[n1].x -= mean;
+            if (i0 + 1 < w) a[n1].y -= mean;
+        }
+    }
+    // pass 1: over n1; a[k1] = sum_n1 z[8 n1 + g] W16^(n1 k1), times W128^(g k1), to the tile at [k1][g]
+    dft16(a);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) xch[k1 * F256_XP + g] = (k1 > 0 && g > 0) ? cmul(a[k1], sTw[k1 * 8 + g]) : a[k1];
+    __syncwarp();
+    // pass 2: k1 = g and g + 8, over the 8 threads' values: Z[k1 + 16 k2]
+    cpx<float> b0[8], b1[8];
+#pragma unroll
+    for (int n2 = 0; n2 < 8; n2++) { b0[n2] = xch[g * F256_XP + n2]; b1[n2] = xch[(g + 8) * F256_XP + n2]; }
+    dft8(b0);
+    dft8(b1);
+    __syncwarp();                                          // every read of the transposed tile is done: it becomes the linear Z
+#pragma unroll
+    for (int k2 = 0; k2 < 8; k2++) { xch[g + 16 * k2] = b0[k2]; xch[g + 8 + 16 * k2] = b1[k2]; }
+    __syncwarp();
+    // real-input split (X[k] = (Z[k] + conj Z[128-k]) / 2 + twsplit[k] (Z[k] - conj Z[128-k])), power / magnitude
+    if (!store) return;
+    float *grow = dst + (row0 + f) * nbins;
+#pragma unroll
+    for (int j = 0; j < 17; j++) {
+        const int k = g + 8 * j;
+        if (k > F256_M) break;
+        const cpx<float> A = xch[k == F256_M ? 0 : k], B = conj(xch[k == 0 ? 0 : F256_M - k]);
+        const cpx<float> X = mk<float>(0.5f * (A.x + B.x), 0.5f * (A.y + B.y)) + cmul(sTs[k], A - B);
+        float p = X.x * X.x + X.y * X.y;
+        if (k == 0 && P.remove_dc) p = 1e-10f;             // fixed floor (src/io/in.cc:390)
+        grow[k] = P.take_sqrt ? sqrtf(p) : p;
+    }
+}
+
+}  // namespace ctu
+#endif

@@ -208,6 +208,21 @@ def test_alternative_kernel_paths_match_oracle(name, options):
             assert np.array_equal(res.vad_nr[r0: r0 + ref.nframes].astype(bool), ref.vad_nr), (name, j)
 
 
+@pytest.mark.parametrize("front256", [1, 0])
+def test_8khz_front_ends_match_oracle(front256):
+    """256-point frames (8 kHz): the specialised front end k_frames256 (default) and the general kernel k_frames_any, on a
+    ragged batch, plain MFCC_0_D_A and MFCC behind exten (the spectrum goes through the scan in between)."""
+    for extra in ([], ["-nr_mode", "exten"]):
+        args = ["-fs", "8000", "-format_in", "raw", "-dither", "0", "-preset", "mfcc", "-preem", "0.97"] + extra + ["-fea_delta", "d_a", "-format_out", "htk"]
+        o = co.parse_args(args)
+        utts = PARITY_SET[:6] + [PARITY_SET[1][:4000 + 37], PARITY_SET[3][:200 + 80 * 6]]
+        res = cb.extract(args, utts, options={"front256": front256})
+        for j, u in enumerate(utts):
+            ref = co.run_pipeline(u, o)
+            assert int(res.frames_per_utt[j]) == ref.nframes
+            check_features("mfcc8k", j, res.utt_features(j), ref.features, o.fea_kind, _sensitivity(args, o, u) if extra else None)
+
+
 def test_fused_and_standalone_scan_agree_bit_for_bit():
     """k_bank's in-tile scan and the standalone k_nr_scan4 run the same recursion step (nr_step): identical features."""
     for name in ("mfcc_exten", "fwss_burg"):
