@@ -534,7 +534,7 @@ static int build_delta_trap_params(ctu_handle *h) {
 static bool c_wfft_is_general(const ctu_handle *h) { return h->cfg.wfft != NFFT; }
 // 8 kHz-sized frames take the specialised 256-point front end (ctu_frames256.cuh) and the general kernel from the spectrum on
 static bool fast256(const ctu_handle *h) {
-    return h->generic && !h->fea_in && h->cfg.wfft == 256 && h->cfg.dither == 0.0 && !h->cfg.remove_dc1 && h->front256;
+    return h->generic && !h->fea_in && h->cfg.wfft == 256 && h->cfg.wshift <= h->cfg.window && h->cfg.dither == 0.0 && !h->cfg.remove_dc1 && h->front256;
 }
 
 static int resolve_modes(ctu_handle *h) {
