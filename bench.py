@@ -326,7 +326,7 @@ def main():
     ap.add_argument("--others", default="auto", choices=["auto", "all", "none"],
                     help="the other BASELINE configs under 'workloads': auto = all of them on one GPU, PLP only under torchrun")
     ap.add_argument("--no-selfcheck", action="store_true")
-    ap.add_argument("--cli-utts", type=int, default=4000, help="10 s files for the file -> file run of the command-line host (0 = skip)")
+    ap.add_argument("--cli-utts", type=int, default=20000, help="10 s files for the file -> file run of the command-line host (0 = skip)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
