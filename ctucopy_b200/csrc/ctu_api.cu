@@ -1333,7 +1333,7 @@ static int run_range(ctu_plan *p, const Range &r, const int16_t *d_pcm, const ui
         int lg = 0;
         while ((1 << lg) < M) lg++;
         AnyTables64 tb{h->d_any_tw64, h->d_any_ts64, h->d_wind, N, lg, h->spitch};
-        const size_t bytes = (size_t)(SYNANY_THREADS / 32) * (4 * M + 4) * sizeof(double);
+        const size_t bytes = (size_t)(SYNANY_THREADS / 32) * (2 * any64_zslots(M) + 2 * (M + 2)) * sizeof(double);
         CK(cudaFuncSetAttribute(k_synth_frames_any, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         h->lc.begin("k_synth_frames_any", s);
         k_synth_frames_any<<<(unsigned)r.tF_n, SYNANY_THREADS, bytes, s>>>(h->cfg.window, h->cfg.wshift, (double)h->cfg.preem, h->cfg.remove_dc, bdF, tb, d_pcm,

@@ -351,16 +351,19 @@ k_burg(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, int nha
 // The lattice keeps ef (aliasing the time signal) and eb in shared memory; a stage updates them in chunks of 32 samples
 // from the END of the frame, so that eb[i-1] is still the old value when sample i is updated.
 // ------------------------------------------------------------------------------------------
+// doubles of shared memory per warp of k_burg_any: z (padded), Y, eb
+__host__ __device__ inline size_t burg_any_doubles(int M) { return (size_t)2 * any64_zslots(M) + 2 * (M + 2) + 2 * M; }
+
 __global__ void __launch_bounds__(ANY64_THREADS)
 k_burg_any(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, AnyTables64 tb, const int16_t *__restrict__ pcm,
            const float *__restrict__ spec, double *__restrict__ ceps, const double *__restrict__ g_hann) {
     extern __shared__ __align__(16) double smd[];
     const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
     const int nfft = tb.nfft, M = nfft >> 1, nbins = M + 1;
-    cpx<double> *z = reinterpret_cast<cpx<double> *>(smd + (size_t)wv * (6 * M + 4));   // M complex = nfft reals
-    cpx<double> *Y = z + M;                                                             // M + 1 complex (+ pad)
-    double *eb = reinterpret_cast<double *>(Y + M + 2);                                 // nfft reals
-    double *ef = reinterpret_cast<double *>(z);
+    cpx<double> *z = reinterpret_cast<cpx<double> *>(smd + (size_t)wv * burg_any_doubles(M));   // M complex = nfft reals, padded (ctu_any64.cuh)
+    cpx<double> *Y = z + any64_zslots(M);                                                      // M + 1 complex (+ pad)
+    double *eb = reinterpret_cast<double *>(Y + M + 2);                                         // nfft reals
+    double *ef = reinterpret_cast<double *>(Y);                                                 // the lattice's forward errors: Y is dead by then
     const int2 tile = bd.tiles[blockIdx.x];
     const int u = tile.x, t0 = tile.y;
     const int nf = min(TILE_F, bd.nframes[u] - t0);
@@ -395,7 +398,7 @@ k_burg_any(const __grid_constant__ BurgParams B, int src_mode, BatchDesc bd, Any
         // ---- Burg lattice on the first w samples ------------------------------------------------------------------
         double en = 0.0;
         for (int i = lane; i < w; i += 32) {
-            const double v = ef[i] * ((src_mode == BURG_SRC_NR) ? g_hann[i] : 1.0);
+            const double v = any64_real(z, i) * ((src_mode == BURG_SRC_NR) ? g_hann[i] : 1.0);
             ef[i] = v; eb[i] = v;
             en += v * v;
         }
@@ -460,7 +463,7 @@ int launch_burg(const BurgParams &B, int src_mode, const BatchDesc &bd, int64_t 
     if (ntiles <= 0) return CTU_OK;
     if (B.nfft) {                                        // FFT sizes other than 512: the general kernel
         const int M = B.nfft / 2;
-        const size_t bytes_any = (size_t)(ANY64_THREADS / 32) * (6 * M + 4) * sizeof(double);
+        const size_t bytes_any = (size_t)(ANY64_THREADS / 32) * burg_any_doubles(M) * sizeof(double);
         AnyTables64 tb{B.any_tw, B.any_ts, win, B.nfft, B.log2m};
         cudaError_t e2 = cudaFuncSetAttribute(k_burg_any, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_any);
         lc->begin("k_burg_any", s);

@@ -271,9 +271,9 @@ k_frames64_any(const __grid_constant__ FrameParams P, BatchDesc bd, Tables64 tb,
     extern __shared__ __align__(16) double smd[];
     const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
     const int nfft = tb.nfft, M = nfft >> 1, nbins = M + 1;
-    double *base = smd + (size_t)wv * (nfft + (M + 4) + 64 + 64);
-    cpx<double> *z = reinterpret_cast<cpx<double> *>(base);
-    double *pr = base + nfft;
+    double *base = smd + (size_t)wv * (2 * any64_zslots(M) + (M + 4) + 64 + 64);
+    cpx<double> *z = reinterpret_cast<cpx<double> *>(base);                    // padded (ctu_any64.cuh)
+    double *pr = base + 2 * any64_zslots(M);
     double *sY = pr + (M + 4);
     double *sR = sY + 64;
     const AnyTables64 at{tb.any_tw, tb.any_ts, tb.win, nfft, tb.log2m};
@@ -310,7 +310,7 @@ static int launch_frames64_t(const FrameParams &P, const BatchDesc &bd, const Ta
                              std::string &err) {
     if (ntiles <= 0) return CTU_OK;
     if (tb.nfft) {
-        const size_t bytes_any = (size_t)(ANY64_THREADS / 32) * (tb.nfft + tb.nfft / 2 + 4 + 128) * sizeof(double);
+        const size_t bytes_any = (size_t)(ANY64_THREADS / 32) * (2 * any64_zslots(tb.nfft / 2) + tb.nfft / 2 + 4 + 128) * sizeof(double);
         auto ka = k_frames64_any<SRC, DST, KIND>;
         cudaError_t e2 = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_any);
         if (e2 == cudaSuccess) {

@@ -13,7 +13,7 @@
 
 namespace ctu {
 
-constexpr int SYNANY_THREADS = ANY64_THREADS;  // 4 warps: 4 x (4M + 4) doubles of shared memory, 131 KB at 2048 points
+constexpr int SYNANY_THREADS = ANY64_THREADS;  // 4 warps: 4 x (2 zslots(M) + 2M + 4) doubles of shared memory, 135 KB at 2048 points
 
 __global__ void __launch_bounds__(SYNANY_THREADS)
 k_synth_frames_any(int window, int wshift, double preem, int remove_dc, BatchDesc bd, AnyTables64 tb, const int16_t *__restrict__ pcm,
@@ -21,8 +21,8 @@ k_synth_frames_any(int window, int wshift, double preem, int remove_dc, BatchDes
     extern __shared__ __align__(16) double smd[];
     const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
     const int nfft = tb.nfft, M = nfft >> 1, nbins = M + 1;
-    cpx<double> *z = reinterpret_cast<cpx<double> *>(smd + (size_t)wv * (2 * M + 2 * (M + 2)));   // M complex
-    cpx<double> *Y = z + M;                                                                        // M + 1 complex (+ pad)
+    cpx<double> *z = reinterpret_cast<cpx<double> *>(smd + (size_t)wv * (2 * any64_zslots(M) + 2 * (M + 2)));   // M complex, padded
+    cpx<double> *Y = z + any64_zslots(M);                                                                        // M + 1 complex (+ pad)
     const int2 tile = bd.tiles[blockIdx.x];
     const int u = tile.x, t0 = tile.y;
     const int nf = min(ANY_TILE, bd.nframes[u] - t0);
@@ -47,9 +47,8 @@ k_synth_frames_any(int window, int wshift, double preem, int remove_dc, BatchDes
         }
         __syncwarp();
         any64_inverse(z, Y, tb, lane);
-        const double *yv = reinterpret_cast<const double *>(z);
         double *o = yt + (row0 + f) * w;
-        for (int i = lane; i < w; i += 32) o[i] = yv[i];
+        for (int i = lane; i < w; i += 32) o[i] = any64_real(z, i);
         __syncwarp();
     }
 }

@@ -428,7 +428,8 @@ void merge_pfile(const std::string &pf, int n) {
 // (2) the GPU (ctu_run: chunked H2D / kernels / D2H), (3) the writers (per-utterance files by
 // several threads, containers in list order).  Replaces the reference's file loop
 // (src/io/batch.cc:349-412) end to end.
-constexpr int IO_THREADS = 8;
+// reader and writer threads of a batch (each stage has its own pool); CTU_IO_THREADS overrides
+const int IO_THREADS = std::getenv("CTU_IO_THREADS") ? std::max(1, std::atoi(std::getenv("CTU_IO_THREADS"))) : 8;
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 const bool g_timing = std::getenv("CTU_TIMING") != nullptr;     // stage times on stderr
