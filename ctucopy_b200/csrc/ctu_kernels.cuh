@@ -734,14 +734,15 @@ k_lpc(const __grid_constant__ FrameParams P, int64_t row0, int64_t nrows, const 
     const int p = PORD ? PORD : P.lporder;
     constexpr int NA = PORD ? PORD + 1 : MAXR;
     double R[NA], a[NA], aa[NA];
+    // autocorrelation lags R[k] = sum_n y[n] m[k][n]: bands in the outer loop, so that a band value is converted to fp64 once
+    // instead of once per lag (the conversions were a third of the kernel's instructions); every R[k] still adds its terms in
+    // band order
 #pragma unroll
-    for (int k = 0; k < NA; k++) {
-        if (k <= p) {
-            const float *m = P.m2 + k * P.nbp;
-            double acc = 0.0;
-            for (int n = 0; n < nb; n++) acc += (double)y[n] * (double)m[n];
-            R[k] = acc;
-        }
+    for (int k = 0; k < NA; k++) R[k] = 0.0;
+    for (int n = 0; n < nb; n++) {
+        const double yn = (double)y[n];
+#pragma unroll
+        for (int k = 0; k < NA; k++) if (k <= p) R[k] += yn * (double)P.m2[k * P.nbp + n];
     }
     if (P.energy_mode == EN_LPC) P.energy[r0 + threadIdx.x] = (float)log(R[0]);
     double Pe = R[0];
@@ -779,7 +780,7 @@ k_lpc(const __grid_constant__ FrameParams P, int64_t row0, int64_t nrows, const 
             double sum = 0;
 #pragma unroll
             for (int k = 1; k < NA; k++) if (k <= p && k <= n - 1) sum += (double)(n - k) * cc[(n - k) > 0 ? (n - k) : 0] * a[k];
-            cc[n] = (n <= p ? -a[n < NA ? n : 0] : 0.0) - sum / n;
+            cc[n] = (n <= p ? -a[n < NA ? n : 0] : 0.0) - sum * (1.0 / n);            // (compile-time reciprocal: the loop is unrolled)
             o[n - 1] = (float)(cc[n] * (double)P.lift[n]);
         }
     }
