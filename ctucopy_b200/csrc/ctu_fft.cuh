@@ -127,6 +127,46 @@ CTU_HD void fft256_pass2(cpx<T> (&a)[16], int c, const cpx<T> *xch) {
     dft16(a);
 }
 
+// forward 8-point DFT in registers, natural order in and out
+template <class T> CTU_HD void dft8(cpx<T> (&a)[8]) {
+    const T r2 = (T)0.70710678118654752440;
+    cpx<T> e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6], o0 = a[1], o1 = a[3], o2 = a[5], o3 = a[7];
+    dft4(e0, e1, e2, e3);
+    dft4(o0, o1, o2, o3);
+    o1 = mk<T>((o1.x + o1.y) * r2, (o1.y - o1.x) * r2);              // W8^1 = (r2, -r2)
+    o2 = mul_mi(o2);                                                 // W8^2 = -i
+    o3 = mk<T>((o3.y - o3.x) * r2, -(o3.x + o3.y) * r2);             // W8^3 = (-r2, -r2)
+    a[0] = e0 + o0; a[4] = e0 - o0;
+    a[1] = e1 + o1; a[5] = e1 - o1;
+    a[2] = e2 + o2; a[6] = e2 - o2;
+    a[3] = e3 + o3; a[7] = e3 - o3;
+}
+
+// ---- 128-point complex FFT over a group of 8 threads (256-point real frames, ctu_frames256.cuh) -------------------
+// 128 = 16 x 8: thread g holds z[8 n1 + g], n1 = 0..15.
+// pass 1: 16-point DFT over n1, times W128^(g k1) (tw128[k1 * 8 + g]), to the exchange tile at [k1][g] (row pitch xp)
+template <class T>
+CTU_HD void fft128_pass1(cpx<T> (&a)[16], int g, const cpx<T> *tw128, cpx<T> *xch, int xp) {
+    dft16(a);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) xch[k1 * xp + g] = (k1 > 0 && g > 0) ? cmul(a[k1], tw128[k1 * 8 + g]) : a[k1];
+}
+// pass 2 (after a group-wide sync): thread g plays k1 = g and k1 = g + 8: two 8-point DFTs over the 8 threads' values; on
+// return b0[k2] = Z[g + 16 k2], b1[k2] = Z[g + 8 + 16 k2]
+template <class T>
+CTU_HD void fft128_pass2(cpx<T> (&b0)[8], cpx<T> (&b1)[8], int g, const cpx<T> *xch, int xp) {
+#pragma unroll
+    for (int n2 = 0; n2 < 8; n2++) { b0[n2] = xch[g * xp + n2]; b1[n2] = xch[(g + 8) * xp + n2]; }
+    dft8(b0);
+    dft8(b1);
+}
+// bin k (0..128) of the 256-point real transform from the linear Z[0..127]; twsplit[k] = -i/2 e^{-2 pi i k / 256}
+template <class T>
+CTU_HD cpx<T> rfft256_bin(const cpx<T> *zlin, const cpx<T> *twsplit, int k) {
+    const cpx<T> A = zlin[k == 128 ? 0 : k], B = conj(zlin[k == 0 ? 0 : 128 - k]);
+    return mk<T>((T)0.5 * (A.x + B.x), (T)0.5 * (A.y + B.y)) + cmul(twsplit[k], A - B);
+}
+
 // ---- real-input split ---------------------------------------------------------------------
 // After pass 2 every thread stores Z linearly (zlin[c + 16*k2] = a[k2]); after a sync,
 // thread c owns the bin pairs (k, 256-k) for k = c + 16*j, j = 0..7.

@@ -35,21 +35,7 @@ __host__ __device__ inline size_t smem256_floats(int window, int wshift) {
     return (size_t)2 * F256_TILE * F256_GRP + 2 * 128 + 2 * 130 + 256 + (size_t)((F256_TILE - 1) * wshift + window + 4);
 }
 
-// forward 8-point DFT in registers, natural order in and out
-template <class T> CTU_HD void dft8(cpx<T> (&a)[8]) {
-    const T r2 = (T)0.70710678118654752440;
-    cpx<T> e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6], o0 = a[1], o1 = a[3], o2 = a[5], o3 = a[7];
-    dft4(e0, e1, e2, e3);
-    dft4(o0, o1, o2, o3);
-    o1 = mk<T>((o1.x + o1.y) * r2, (o1.y - o1.x) * r2);              // W8^1 = (r2, -r2)
-    o2 = mul_mi(o2);                                                 // W8^2 = -i
-    o3 = mk<T>((o3.y - o3.x) * r2, -(o3.x + o3.y) * r2);             // W8^3 = (-r2, -r2)
-    a[0] = e0 + o0; a[4] = e0 - o0;
-    a[1] = e1 + o1; a[5] = e1 - o1;
-    a[2] = e2 + o2; a[6] = e2 - o2;
-    a[3] = e3 + o3; a[7] = e3 - o3;
-}
-
+// (dft8 and the index algebra of the 16 x 8 decomposition: ctu_fft.cuh, emulated on the CPU by tests/emu/emu_fft.cpp)
 __device__ __forceinline__ float group_sum8(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 4);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -109,16 +95,11 @@ k_frames256(const __grid_constant__ FrameParams P, BatchDesc bd, Tables256 tb, c
         }
     }
     // pass 1: over n1; a[k1] = sum_n1 z[8 n1 + g] W16^(n1 k1), times W128^(g k1), to the tile at [k1][g]
-    dft16(a);
-#pragma unroll
-    for (int k1 = 0; k1 < 16; k1++) xch[k1 * F256_XP + g] = (k1 > 0 && g > 0) ? cmul(a[k1], sTw[k1 * 8 + g]) : a[k1];
+    fft128_pass1(a, g, sTw, xch, F256_XP);
     __syncwarp();
     // pass 2: k1 = g and g + 8, over the 8 threads' values: Z[k1 + 16 k2]
     cpx<float> b0[8], b1[8];
-#pragma unroll
-    for (int n2 = 0; n2 < 8; n2++) { b0[n2] = xch[g * F256_XP + n2]; b1[n2] = xch[(g + 8) * F256_XP + n2]; }
-    dft8(b0);
-    dft8(b1);
+    fft128_pass2(b0, b1, g, xch, F256_XP);
     __syncwarp();                                          // every read of the transposed tile is done: it becomes the linear Z
 #pragma unroll
     for (int k2 = 0; k2 < 8; k2++) { xch[g + 16 * k2] = b0[k2]; xch[g + 8 + 16 * k2] = b1[k2]; }
@@ -130,8 +111,7 @@ k_frames256(const __grid_constant__ FrameParams P, BatchDesc bd, Tables256 tb, c
     for (int j = 0; j < 17; j++) {
         const int k = g + 8 * j;
         if (k > F256_M) break;
-        const cpx<float> A = xch[k == F256_M ? 0 : k], B = conj(xch[k == 0 ? 0 : F256_M - k]);
-        const cpx<float> X = mk<float>(0.5f * (A.x + B.x), 0.5f * (A.y + B.y)) + cmul(sTs[k], A - B);
+        const cpx<float> X = rfft256_bin(xch, sTs, k);
         float p = X.x * X.x + X.y * X.y;
         if (k == 0 && P.remove_dc) p = 1e-10f;             // fixed floor (src/io/in.cc:390)
         grow[k] = P.take_sqrt ? sqrtf(p) : p;

@@ -117,8 +117,36 @@ template <class T> int run(double tol) {
     bad |= (e5 / ref > 2 * tol);
     return bad;
 }
+// the 8-thread group of the 256-point front end (ctu_frames256.cuh): 128 complex points = 16 x 8, thread g holds z[8 n1 + g]
+template <class T> int run256(double tol) {
+    const double PI = 3.14159265358979323846;
+    const int XP = 9;
+    std::vector<cpx<T>> tw128(128), twsplit(129);
+    for (int k1 = 0; k1 < 16; k1++) for (int g = 0; g < 8; g++) {
+        double a = -2 * PI * (g * k1) / 128.0; tw128[k1 * 8 + g] = mk<T>((T)cos(a), (T)sin(a)); }
+    for (int k = 0; k <= 128; k++) { double th = 2 * PI * k / 256.0; twsplit[k] = mk<T>((T)(-sin(th) / 2), (T)(-cos(th) / 2)); }
+    std::vector<double> x(256, 0.0);
+    srand(5);
+    for (int i = 0; i < 200; i++) x[i] = (rand() / (double)RAND_MAX - 0.5) * 2000;
+    static cpx<T> reg[8][16], b0[8][8], b1[8][8];
+    std::vector<cpx<T>> xch(16 * XP + 8);
+    for (int g = 0; g < 8; g++) for (int n1 = 0; n1 < 16; n1++) { int n = 8 * n1 + g; reg[g][n1] = mk<T>((T)x[2 * n], (T)x[2 * n + 1]); }
+    for (int g = 0; g < 8; g++) fft128_pass1(reg[g], g, tw128.data(), xch.data(), XP);
+    for (int g = 0; g < 8; g++) fft128_pass2(b0[g], b1[g], g, xch.data(), XP);
+    for (int g = 0; g < 8; g++) for (int k2 = 0; k2 < 8; k2++) { xch[g + 16 * k2] = b0[g][k2]; xch[g + 8 + 16 * k2] = b1[g][k2]; }
+    double emax = 0, ref = 0;
+    for (int k = 0; k <= 128; k++) {
+        double re = 0, im = 0;
+        for (int n = 0; n < 256; n++) { double a = -2 * PI * ((n * k) % 256) / 256.0; re += x[n] * cos(a); im += x[n] * sin(a); }
+        ref = fmax(ref, hypot(re, im));
+        const cpx<T> X = rfft256_bin(xch.data(), twsplit.data(), k);
+        emax = fmax(emax, hypot(X.x - re, X.y - im));
+    }
+    printf("256-point forward (8 threads x 16 points): max err %.3g (rel %.3g)\n", emax, emax / ref);
+    return emax / ref > tol;
+}
 int main() {
-    int bad = run<float>(2e-6) | run<double>(1e-14);
+    int bad = run<float>(2e-6) | run<double>(1e-14) | run256<float>(2e-6) | run256<double>(1e-14);
     printf(bad ? "FAIL\n" : "OK\n");
     return bad;
 }

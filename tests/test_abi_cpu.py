@@ -103,8 +103,8 @@ def test_no_cpu_fallback():
 
 def test_fft_index_algebra_on_the_cpu(tmp_path):
     """ctu_fft.cuh is __host__ __device__: the four-step 256-point FFT, the on-the-fly twiddles, the real split
-    and the inverse pre-split (shared-memory and register-exchange variants) run here thread by thread
-    against a naive DFT (tests/emu/emu_fft.cpp)."""
+    and the inverse pre-split (shared-memory and register-exchange variants), and the 16 x 8 decomposition of the
+    256-point front end (8 threads per frame), run here thread by thread against a naive DFT (tests/emu/emu_fft.cpp)."""
     import subprocess
     exe = str(tmp_path / "emu_fft")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "emu", "emu_fft.cpp")])
