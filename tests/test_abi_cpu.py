@@ -10,6 +10,7 @@ import pytest
 
 import ctu_oracle as co
 import golden_util as gu
+import ref_runner as rr
 import ctucopy_b200 as cb
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -110,3 +111,35 @@ def test_fft_index_algebra_on_the_cpu(tmp_path):
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "emu", "emu_fft.cpp")])
     pr = subprocess.run([exe], capture_output=True, text=True)
     assert pr.returncode == 0 and "OK" in pr.stdout, pr.stdout
+
+
+def test_td_iir_mfcc_refusals_and_filter_file_errors(tmp_path):
+    """-fea_kind td-iir-mfcc: what the reference does not survive on this branch is refused before any device is
+    touched (status 3, with the reference line), and the coefficient file is read like rawIN::loadf_filters reads it, minus its
+    undefined cases (status 2).  A valid configuration then fails only for the missing GPU (status 4)."""
+    base = ["-fs", "16000", "-format_in", "raw", "-format_out", "htk", "-w", "30", "-s", "10", "-fea_kind", "td-iir-mfcc", "-fea_ncepcoefs", "12"]
+    good = base + ["-filters", rr.TDIIR_FILTERS]
+    for extra in (["-fea_E", "on"], ["-fea_delta", "d_a"], ["-fea_trap", "5"], ["-fea_c0", "off"], ["-fea_ncepcoefs", "13"],
+                  ["-stat_cmvn", "x.stat"], ["-vad_out_mode", "vad"], ["-format_out", "raw"]):
+        with pytest.raises(cb.CtuError) as e:
+            cb.Handle(good + extra)
+        assert e.value.status == 3 and "td-iir-mfcc" in e.value.message, (extra, e.value.message)
+    with pytest.raises(cb.CtuError) as e:
+        cb.Handle(base + ["-filters", str(tmp_path / "missing.asc")])
+    assert e.value.status == 2 and "filter coefficient file" in e.value.message
+    lines = open(rr.TDIIR_FILTERS).read().splitlines()
+    short = tmp_path / "short.asc"
+    short.write_text("\n".join(lines[:23]) + "\n")
+    with pytest.raises(cb.CtuError) as e:
+        cb.Handle(base + ["-filters", str(short)])
+    assert e.value.status == 2 and "fewer than 24" in e.value.message
+    ragged = tmp_path / "ragged.asc"
+    ragged.write_text("\n".join(lines[:5] + ["\t".join(lines[5].split("\t")[:9])] + lines[6:]) + "\n")
+    with pytest.raises(cb.CtuError) as e:
+        cb.Handle(base + ["-filters", str(ragged)])
+    assert e.value.status == 2 and "fewer than 10" in e.value.message
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(cb.CtuError) as e:
+            cb.Handle(good)
+        assert e.value.status == 4 and "no CPU fallback" in e.value.message
