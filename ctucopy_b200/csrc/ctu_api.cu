@@ -1069,7 +1069,10 @@ static int launch_frames_w(ctu_handle *h, const FrameParams &P, const ctu_plan *
             BatchDesc bd{p->d_pcm_off, p->d_nframes, p->d_row_off, ft.t16};
             Tables256 tb{h->d_tw128, h->d_any_ts, h->d_win};
             h->lc.begin(names[SRC][DST], s);
-            k_frames256<<<(unsigned)ft.n16, F256_THREADS, bytes, s>>>(P, bd, tb, pcm, dst, h->nbins);
+            int per_sm = 1;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frames256, F256_THREADS, bytes));
+            const unsigned grid = (unsigned)std::min<int64_t>(ft.n16, (int64_t)std::max(per_sm, 1) * h->num_sms);
+            k_frames256<<<grid, F256_THREADS, bytes, s>>>(P, bd, tb, pcm, dst, h->nbins, (int)ft.n16);
             h->lc.end(s);
             CK(cudaGetLastError());
             return CTU_OK;

@@ -10,7 +10,8 @@
 //   129 bins.
 // The general kernel (k_frames_any: one WARP per frame, radix-4 passes in shared memory, a warp barrier per pass) needs
 // 14.7 ms per 8 M frames for this step; see DESIGN 11 for what this one measures.
-// Work unit: a tile of 16 consecutive frames of one utterance (the 16-frame tile list), 128 threads = 16 groups = one pass.
+// Work unit: a tile of 16 consecutive frames of one utterance (the 16-frame tile list), 128 threads = 16 groups = one pass;
+// persistent CTAs with the next tile's samples prefetched (cp.async), like k_frames2.
 #ifndef CTU_FRAMES256_CUH
 #define CTU_FRAMES256_CUH
 
@@ -31,8 +32,11 @@ struct Tables256 {
     const float *win;        // analysis window [window]
 };
 
+// floats of the tile's pre-emphasised samples / of the raw int16 prefetch buffer (8-sample chunks, 16-byte phase kept)
+__host__ __device__ inline int smem256_samples(int window, int wshift) { return ((F256_TILE - 1) * wshift + window + 7) & ~7; }
+__host__ __device__ inline int smem256_raw(int window, int wshift) { return (((F256_TILE - 1) * wshift + window + 1 + 8 + 7) / 8) * 4; }
 __host__ __device__ inline size_t smem256_floats(int window, int wshift) {
-    return (size_t)2 * F256_TILE * F256_GRP + 2 * 128 + 2 * 130 + 256 + (size_t)((F256_TILE - 1) * wshift + window + 4);
+    return (size_t)2 * F256_TILE * F256_GRP + 2 * 128 + 2 * 130 + 256 + smem256_samples(window, wshift) + smem256_raw(window, wshift);
 }
 
 // (dft8 and the index algebra of the 16 x 8 decomposition: ctu_fft.cuh, emulated on the CPU by tests/emu/emu_fft.cpp)
@@ -44,36 +48,40 @@ __device__ __forceinline__ float group_sum8(float v) {
 }
 
 __global__ void __launch_bounds__(F256_THREADS)
-k_frames256(const __grid_constant__ FrameParams P, BatchDesc bd, Tables256 tb, const int16_t *__restrict__ pcm, float *__restrict__ dst, int nbins) {
+k_frames256(const __grid_constant__ FrameParams P, BatchDesc bd, Tables256 tb, const int16_t *__restrict__ pcm, float *__restrict__ dst, int nbins,
+            int ntiles) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, g = tid & 7, grp = tid >> 3;
     const int w = P.window, s = P.wshift;
-    cpx<float> *sX = reinterpret_cast<cpx<float> *>(sm);                                // [16 groups][144]
+    cpx<float> *sX = reinterpret_cast<cpx<float> *>(sm);                                // [16 groups][F256_GRP]
     cpx<float> *sTw = sX + F256_TILE * F256_GRP;                                        // 128
     cpx<float> *sTs = sTw + 128;                                                        // 129 (+1)
     float *sW = reinterpret_cast<float *>(sTs + 130);                                   // 256
     float *sD = sW + 256;                                                               // the tile's pre-emphasised samples
-    const int2 tile = bd.tiles[blockIdx.x];
-    const int u = tile.x, t0 = tile.y;
-    const int nf = min(F256_TILE, bd.nframes[u] - t0);
-    const int64_t row0 = bd.row_off[u] + t0;
+    int16_t *raw = reinterpret_cast<int16_t *>(sD + smem256_samples(w, s));             // int16 prefetch buffer
+    // persistent CTAs: the next tile's PCM travels HBM -> shared memory (cp.async) while this one is transformed
+    int tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    TileMeta cur = load_tile_meta(bd, tile, s, F256_TILE);
+    int edge = 0;
+    prefetch_pcm<F256_THREADS>(raw, pcm, cur, (cur.nf - 1) * s + w + 1, edge);
     for (int i = tid; i < 128; i += F256_THREADS) sTw[i] = mk<float>(tb.tw128[i].x, tb.tw128[i].y);
     for (int i = tid; i < 129; i += F256_THREADS) sTs[i] = mk<float>(tb.twsplit[i].x, tb.twsplit[i].y);
     for (int i = tid; i < 256; i += F256_THREADS) sW[i] = (i < w) ? tb.win[i] : 0.f;
-    {
-        const int16_t *x = pcm + bd.pcm_off[u] + (int64_t)t0 * s;
-        const int ns = (nf - 1) * s + w;
-        for (int i = tid; i < ns; i += F256_THREADS) {
-            const float xi = (float)x[i], xp = (i == 0 && t0 == 0) ? 0.f : (float)x[i - 1];
-            sD[i] = fmaf(-P.preem, xp, xi);                                             // pre-emphasis once per sample
-        }
-    }
-    __syncthreads();
+    cpx<float> *xch = sX + grp * F256_GRP;
+#pragma unroll 1
+    for (; tile < ntiles; tile += gridDim.x) {
+    const int next = tile + gridDim.x;
+    TileMeta nxt = cur;
+    if (next < ntiles) nxt = load_tile_meta(bd, next, s, F256_TILE);
+    const int nf = cur.nf;
+    finish_pcm<F256_THREADS>(raw, sD, pcm, cur, (nf - 1) * s + w + 1, edge, P.preem);   // pre-emphasis once per sample
+    __syncthreads();                                       // samples (and, the first time, the tables) staged; raw is free again
+    if (next < ntiles) prefetch_pcm<F256_THREADS>(raw, pcm, nxt, (nxt.nf - 1) * s + w + 1, edge);
     // a group past the end of the tile recomputes the tile's last frame and stores nothing (shuffles name the full warp)
     const bool store = grp < nf;
     const int f = min(grp, nf - 1);
     const float *d = sD + f * s;
-    cpx<float> *xch = sX + grp * F256_GRP;
     cpx<float> a[16];
     float sum = 0.f;
 #pragma unroll
@@ -105,16 +113,20 @@ k_frames256(const __grid_constant__ FrameParams P, BatchDesc bd, Tables256 tb, c
     for (int k2 = 0; k2 < 8; k2++) { xch[g + 16 * k2] = b0[k2]; xch[g + 8 + 16 * k2] = b1[k2]; }
     __syncwarp();
     // real-input split (X[k] = (Z[k] + conj Z[128-k]) / 2 + twsplit[k] (Z[k] - conj Z[128-k])), power / magnitude
-    if (!store) return;
-    float *grow = dst + (row0 + f) * nbins;
+    if (store) {
+        float *grow = dst + (cur.row0 + f) * nbins;
 #pragma unroll
-    for (int j = 0; j < 17; j++) {
-        const int k = g + 8 * j;
-        if (k > F256_M) break;
-        const cpx<float> X = rfft256_bin(xch, sTs, k);
-        float p = X.x * X.x + X.y * X.y;
-        if (k == 0 && P.remove_dc) p = 1e-10f;             // fixed floor (src/io/in.cc:390)
-        grow[k] = P.take_sqrt ? sqrtf(p) : p;
+        for (int j = 0; j < 17; j++) {
+            const int k = g + 8 * j;
+            if (k > F256_M) break;
+            const cpx<float> X = rfft256_bin(xch, sTs, k);
+            float p = X.x * X.x + X.y * X.y;
+            if (k == 0 && P.remove_dc) p = 1e-10f;         // fixed floor (src/io/in.cc:390)
+            grow[k] = P.take_sqrt ? sqrtf(p) : p;
+        }
+    }
+    __syncthreads();                                       // sD is re-staged by the next iteration
+    cur = nxt;
     }
 }
 
