@@ -503,7 +503,7 @@ static int build_delta_trap_params(ctu_handle *h) {
                 row[j] = 2.0 * hamm * cos(PI * (j + 0.5) * k / L);
                 sum += row[j];
             }
-            for (int j = 0; j < L; j++) T.m[(k - 1) * L + j] = (float)(row[j] - sum / L);
+            for (int j = 0; j < L; j++) T.m[j * n + (k - 1)] = (float)(row[j] - sum / L);
         }
         h->feature_dim = h->work_dim = h->fb.nb * n;
         T.out_stride = h->feature_dim;

@@ -257,13 +257,15 @@ k_bank(const __grid_constant__ BankParams B, BatchDesc bd, int ntiles, int u0, i
                 const int4 bnd = sBands[b];
                 const float4 *r = row4 + bnd.x;
                 const float4 *wq = sW4 + bnd.z;
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                // four partial sums as two register pairs: one packed FMA (FFMA2, ctu_fft.cuh) per two taps, the same values
+                cpx<float> a01 = mk<float>(0.f, 0.f), a23 = a01;
 #pragma unroll 4
                 for (int q = 0; q < bnd.y; q++) {
                     const float4 x = r[q], w = wq[q];
-                    a0 = fmaf(x.x, w.x, a0); a1 = fmaf(x.y, w.y, a1); a2 = fmaf(x.z, w.z, a2); a3 = fmaf(x.w, w.w, a3);
+                    a01 = pfma(mk<float>(x.x, x.y), mk<float>(w.x, w.y), a01);
+                    a23 = pfma(mk<float>(x.z, x.w), mk<float>(w.z, w.w), a23);
                 }
-                const float acc = (a0 + a1) + (a2 + a3);
+                const float acc = (a01.x + a01.y) + (a23.x + a23.y);
                 float y;
                 if (B.inld) {
                     y = powf(acc, 0.33f) * B.inld_scale;
@@ -296,13 +298,14 @@ k_bank(const __grid_constant__ BankParams B, BatchDesc bd, int ntiles, int u0, i
                 for (int i = wv; i < B.nrows; i += BANK_THREADS / 32) {
                     const float4 *m4 = reinterpret_cast<const float4 *>(sM + i * B.nbp);
                     const float4 *y4 = reinterpret_cast<const float4 *>(y);
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    cpx<float> a01 = mk<float>(0.f, 0.f), a23 = a01;
 #pragma unroll 4
                     for (int q = 0; q < B.nbp / 4; q++) {                      // pad taps are zero, pad y entries are zero
                         const float4 v = y4[q], m = m4[q];
-                        a0 = fmaf(v.x, m.x, a0); a1 = fmaf(v.y, m.y, a1); a2 = fmaf(v.z, m.z, a2); a3 = fmaf(v.w, m.w, a3);
+                        a01 = pfma(mk<float>(v.x, v.y), mk<float>(m.x, m.y), a01);
+                        a23 = pfma(mk<float>(v.z, v.w), mk<float>(m.z, m.w), a23);
                     }
-                    sO[lane * od + i] = (a0 + a1) + (a2 + a3);
+                    sO[lane * od + i] = (a01.x + a01.y) + (a23.x + a23.y);
                 }
             } else {
                 // with the energy of the band values wanted, logspec arrives here in true scale

@@ -29,11 +29,89 @@ constexpr int XPAD = 17;    // row pitch (in complex elements) of the 16x16 exch
 template <class T> struct cpx { T x, y; };
 
 template <class T> CTU_HD cpx<T> mk(T x, T y) { cpx<T> r; r.x = x; r.y = y; return r; }
-template <class T> CTU_HD cpx<T> operator+(cpx<T> a, cpx<T> b) { return mk<T>(a.x + b.x, a.y + b.y); }
-template <class T> CTU_HD cpx<T> operator-(cpx<T> a, cpx<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
-template <class T> CTU_HD cpx<T> cmul(cpx<T> a, cpx<T> b) { return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// ---- Blackwell packed FP32 (PTX add/sub/mul/fma.rn.f32x2, sm_100+) -----------------------------------------------------
+// A complex float is a register pair, and FADD2 / FMUL2 / FFMA2 work on such pairs in ONE issue slot, with the swap of the
+// halves (.LO_HI), the sign of one half (.NP) and the broadcast of a scalar (.F32) as operand modifiers: a complex add is
+// one instruction instead of two, a complex multiply two instead of four, and the multiplication by -i in front of an
+// add costs nothing (cuobjdump: `FADD2 R16, R6.F32x2.HI_LO, R10.F32x2.LO_HI.NP`).  The FFT kernels are bound by issue
+// slots (ncu, profiles/r02_ncu_mfcc_exten.txt: 70 % of the slots, 47 % of the FP32 pipe), and their arithmetic is
+// complex arithmetic.  Every lane is rounded exactly like the scalar instruction (IEEE round-to-nearest, no flush), and
+// the multiply keeps the contraction nvcc chooses for the scalar form: x = fma(ax, bx, -(ay by)), y = fma(ay, bx, ax by).
+// -DCTU_NO_F32X2 compiles the scalar form (A/B runs; the host build for tests/emu always takes it).
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(CTU_NO_F32X2)
+#define CTU_F32X2 1
+__device__ __forceinline__ unsigned long long f2pk(float x, float y) { unsigned long long u; asm("mov.b64 %0, {%1, %2};" : "=l"(u) : "f"(x), "f"(y)); return u; }
+__device__ __forceinline__ cpx<float> f2up(unsigned long long u) { cpx<float> c; asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(u)); return c; }
+__device__ __forceinline__ cpx<float> f2add(cpx<float> a, cpx<float> b) {
+    unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2pk(a.x, a.y)), "l"(f2pk(b.x, b.y))); return f2up(r);
+}
+__device__ __forceinline__ cpx<float> f2sub(cpx<float> a, cpx<float> b) {
+    unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2pk(a.x, a.y)), "l"(f2pk(b.x, b.y))); return f2up(r);
+}
+__device__ __forceinline__ cpx<float> f2mul(cpx<float> a, cpx<float> b) {
+    unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2pk(a.x, a.y)), "l"(f2pk(b.x, b.y))); return f2up(r);
+}
+__device__ __forceinline__ cpx<float> f2fma(cpx<float> a, cpx<float> b, cpx<float> d) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2pk(a.x, a.y)), "l"(f2pk(b.x, b.y)), "l"(f2pk(d.x, d.y)));
+    return f2up(r);
+}
+#else
+#define CTU_F32X2 0
+#endif
+
+template <class T> CTU_HD cpx<T> operator+(cpx<T> a, cpx<T> b) {
+#if CTU_F32X2
+    if constexpr (sizeof(T) == 4) return f2add(a, b);
+#endif
+    return mk<T>(a.x + b.x, a.y + b.y);
+}
+template <class T> CTU_HD cpx<T> operator-(cpx<T> a, cpx<T> b) {
+#if CTU_F32X2
+    if constexpr (sizeof(T) == 4) return f2sub(a, b);
+#endif
+    return mk<T>(a.x - b.x, a.y - b.y);
+}
+template <class T> CTU_HD cpx<T> cmul(cpx<T> a, cpx<T> b) {
+#if CTU_F32X2
+    if constexpr (sizeof(T) == 4) {
+        const cpx<T> t = f2mul(mk<T>(a.y, a.x), mk<T>(b.y, b.y));          // (ay by, ax by)
+        return f2fma(a, mk<T>(b.x, b.x), mk<T>(-t.x, t.y));
+    }
+#endif
+    return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * s, s real
+template <class T> CTU_HD cpx<T> cscale(cpx<T> a, T s) {
+#if CTU_F32X2
+    if constexpr (sizeof(T) == 4) return f2mul(a, mk<T>(s, s));
+#endif
+    return mk<T>(a.x * s, a.y * s);
+}
+// element by element: (ax bx, ay by) -- two real samples times their two window values
+template <class T> CTU_HD cpx<T> pmul(cpx<T> a, cpx<T> b) {
+#if CTU_F32X2
+    if constexpr (sizeof(T) == 4) return f2mul(a, b);
+#endif
+    return mk<T>(a.x * b.x, a.y * b.y);
+}
+// element by element: (fma(ax, bx, dx), fma(ay, by, dy)) -- two taps of a dot product whose partial sums are a register pair
+template <class T> CTU_HD cpx<T> pfma(cpx<T> a, cpx<T> b, cpx<T> d) {
+#if CTU_F32X2
+    if constexpr (sizeof(T) == 4) return f2fma(a, b, d);
+#endif
+#if defined(__CUDA_ARCH__)
+    return mk<T>(fma(a.x, b.x, d.x), fma(a.y, b.y, d.y));
+#else
+    return mk<T>(a.x * b.x + d.x, a.y * b.y + d.y);
+#endif
+}
 template <class T> CTU_HD cpx<T> conj(cpx<T> a) { return mk<T>(a.x, -a.y); }
 template <class T> CTU_HD cpx<T> mul_mi(cpx<T> a) { return mk<T>(a.y, -a.x); }   // a * (-i)
+// a * (1 - i) r and a * (-1 - i) r, r = sqrt(1/2): W8^1 and W8^3.  ((ax + ay) r, (ay - ax) r) and ((ay - ax) r, -(ax + ay) r)
+template <class T> CTU_HD cpx<T> mul_w8_1(cpx<T> a) { return cscale(a + mul_mi(a), (T)0.70710678118654752440); }
+template <class T> CTU_HD cpx<T> mul_w8_3(cpx<T> a) { return cscale(mul_mi(a) - a, (T)0.70710678118654752440); }
 
 // forward 4-point DFT, natural order in and out
 template <class T> CTU_HD void dft4(cpx<T> &a0, cpx<T> &a1, cpx<T> &a2, cpx<T> &a3) {
@@ -43,18 +121,18 @@ template <class T> CTU_HD void dft4(cpx<T> &a0, cpx<T> &a1, cpx<T> &a2, cpx<T> &
 
 // forward 16-point DFT in registers (4 x 4), natural order in and out
 template <class T> CTU_HD void dft16(cpx<T> (&a)[16]) {
-    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173, r2 = (T)0.70710678118654752440;
+    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173;
 #pragma unroll
     for (int n2 = 0; n2 < 4; n2++) dft4(a[n2], a[4 + n2], a[8 + n2], a[12 + n2]);
     // a[4*k1 + n2] *= W16^(n2*k1)
     a[5] = cmul(a[5], mk<T>(c1, -s1));                       // 1
-    a[6] = mk<T>((a[6].x + a[6].y) * r2, (a[6].y - a[6].x) * r2);   // 2: (r2,-r2)
+    a[6] = mul_w8_1(a[6]);                                    // 2: (r2,-r2)
     a[7] = cmul(a[7], mk<T>(s1, -c1));                       // 3
-    a[9] = mk<T>((a[9].x + a[9].y) * r2, (a[9].y - a[9].x) * r2);   // 2
+    a[9] = mul_w8_1(a[9]);                                    // 2
     a[10] = mul_mi(a[10]);                                   // 4
-    a[11] = mk<T>((a[11].y - a[11].x) * r2, -(a[11].x + a[11].y) * r2);  // 6: (-r2,-r2)
+    a[11] = mul_w8_3(a[11]);                                  // 6: (-r2,-r2)
     a[13] = cmul(a[13], mk<T>(s1, -c1));                     // 3
-    a[14] = mk<T>((a[14].y - a[14].x) * r2, -(a[14].x + a[14].y) * r2);  // 6
+    a[14] = mul_w8_3(a[14]);                                  // 6
     a[15] = cmul(a[15], mk<T>(-c1, s1));                     // 9
 #pragma unroll
     for (int k1 = 0; k1 < 4; k1++) dft4(a[4 * k1], a[4 * k1 + 1], a[4 * k1 + 2], a[4 * k1 + 3]);
@@ -129,13 +207,12 @@ CTU_HD void fft256_pass2(cpx<T> (&a)[16], int c, const cpx<T> *xch) {
 
 // forward 8-point DFT in registers, natural order in and out
 template <class T> CTU_HD void dft8(cpx<T> (&a)[8]) {
-    const T r2 = (T)0.70710678118654752440;
     cpx<T> e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6], o0 = a[1], o1 = a[3], o2 = a[5], o3 = a[7];
     dft4(e0, e1, e2, e3);
     dft4(o0, o1, o2, o3);
-    o1 = mk<T>((o1.x + o1.y) * r2, (o1.y - o1.x) * r2);              // W8^1 = (r2, -r2)
+    o1 = mul_w8_1(o1);                                               // W8^1 = (r2, -r2)
     o2 = mul_mi(o2);                                                 // W8^2 = -i
-    o3 = mk<T>((o3.y - o3.x) * r2, -(o3.x + o3.y) * r2);             // W8^3 = (-r2, -r2)
+    o3 = mul_w8_3(o3);                                               // W8^3 = (-r2, -r2)
     a[0] = e0 + o0; a[4] = e0 - o0;
     a[1] = e1 + o1; a[5] = e1 - o1;
     a[2] = e2 + o2; a[6] = e2 - o2;
@@ -164,7 +241,7 @@ CTU_HD void fft128_pass2(cpx<T> (&b0)[8], cpx<T> (&b1)[8], int g, const cpx<T> *
 template <class T>
 CTU_HD cpx<T> rfft256_bin(const cpx<T> *zlin, const cpx<T> *twsplit, int k) {
     const cpx<T> A = zlin[k == 128 ? 0 : k], B = conj(zlin[k == 0 ? 0 : 128 - k]);
-    return mk<T>((T)0.5 * (A.x + B.x), (T)0.5 * (A.y + B.y)) + cmul(twsplit[k], A - B);
+    return cscale(A + B, (T)0.5) + cmul(twsplit[k], A - B);
 }
 
 // ---- real-input split ---------------------------------------------------------------------
@@ -185,7 +262,7 @@ CTU_HD void rfft_split(const cpx<T> *zlin, int c, const cpx<T> *twsplit, cpx<T> 
             hi[j] = mk<T>(A.x - A.y, (T)0);
         } else {
             cpx<T> B = conj(zlin[NC - k]);
-            cpx<T> E = mk<T>((T)0.5 * (A.x + B.x), (T)0.5 * (A.y + B.y));
+            cpx<T> E = cscale(A + B, (T)0.5);
             cpx<T> Tt = cmul(twsplit[k], A - B);
             lo[j] = E + Tt;
             hi[j] = conj(E - Tt);
@@ -212,7 +289,7 @@ CTU_HD void rfft_split_pairs(const cpx<T> (&a)[16], const cpx<T> (&Zp)[8], int c
             hi[j] = mk<T>(A.x - A.y, (T)0);
         } else {
             const cpx<T> B = conj(Z);
-            const cpx<T> E = mk<T>((T)0.5 * (A.x + B.x), (T)0.5 * (A.y + B.y));
+            const cpx<T> E = cscale(A + B, (T)0.5);
             const cpx<T> Tt = cmul(twsplit[c + 16 * j], A - B);
             lo[j] = E + Tt;
             hi[j] = conj(E - Tt);
@@ -242,7 +319,7 @@ CTU_HD void rfft_split_pairs_rec(const cpx<T> (&a)[16], const cpx<T> (&Zp)[8], i
             hi[j] = mk<T>(A.x - A.y, (T)0);
         } else {
             const cpx<T> B = conj(Z);
-            const cpx<T> E = mk<T>((T)0.5 * (A.x + B.x), (T)0.5 * (A.y + B.y));
+            const cpx<T> E = cscale(A + B, (T)0.5);
             const cpx<T> tw = (j == 0) ? ts_c : cmul(ts_c, mk<T>(rc[j], rs[j]));
             const cpx<T> Tt = cmul(tw, A - B);
             lo[j] = E + Tt;
@@ -266,8 +343,8 @@ CTU_HD void irfft_presplit_local(cpx<T> (&a)[16], cpx<T> (&zn)[8], cpx<T> &z128,
         } else {
             const cpx<T> S = lo[j] + conj(hi[j]);
             const cpx<T> U = cmul(lo[j] - conj(hi[j]), twinv[c + 16 * j]);
-            a[j] = conj(mk<T>(S.x - U.y, S.y + U.x));           // conj(Zc[k])
-            zn[j] = conj(mk<T>(S.x + U.y, -S.y + U.x));         // conj(Zc[256-k])
+            a[j] = conj(S) - mk<T>(U.y, U.x);                   // conj(Zc[k]) = conj(S + i U) = (Sx - Uy, -Sy - Ux)
+            zn[j] = S + mul_mi(U);                              // conj(Zc[256-k]) = conj(conj(S) + i conj(U)) = (Sx + Uy, Sy - Ux)
         }
     }
     // Zc[128] pairs with itself (thread 0): S = 2 Re(mid), U = 2i Im(mid) * twinv[128]
@@ -299,10 +376,8 @@ CTU_HD void irfft_presplit(cpx<T> *zlin, int c, const cpx<T> *twinv, const cpx<T
             cpx<T> S = lo[j] + conj(hi[j]);
             cpx<T> U = cmul(lo[j] - conj(hi[j]), twinv[k]);
             // Zc[k] = S + i U ; Zc[256-k] = conj(S) + i conj(U)
-            cpx<T> zk = mk<T>(S.x - U.y, S.y + U.x);
-            cpx<T> zn = mk<T>(S.x + U.y, -S.y + U.x);
-            zlin[k] = conj(zk);
-            zlin[NC - k] = conj(zn);
+            zlin[k] = conj(S) - mk<T>(U.y, U.x);                // conj(Zc[k])
+            zlin[NC - k] = S + mul_mi(U);                       // conj(Zc[256-k])
         }
     }
     if (c == 0) {

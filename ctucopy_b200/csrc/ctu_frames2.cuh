@@ -107,29 +107,30 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, con
         // wavefronts per frame were these conflicts).  Needs an even shift; odd shifts take scalar loads.
         const float *d = sD + f * s;
         const bool pair = (s & 1) == 0;
-        float sum = 0.f;
+        // two samples and their two window values are register pairs: windowing, the sum for the mean and its
+        // subtraction are packed instructions (ctu_fft.cuh); the sum runs over even and odd samples separately
+        cpx<float> sum2 = mk<float>(0.f, 0.f);
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) {
             const int i0 = 32 * n1 + 2 * c;
-            float y0 = 0.f, y1 = 0.f;
             if (i0 + 1 < w && pair) {
                 const float2 dd = *reinterpret_cast<const float2 *>(d + i0);
-                y0 = wr[2 * n1] * dd.x; y1 = wr[2 * n1 + 1] * dd.y;
+                a[n1] = pmul(mk<float>(wr[2 * n1], wr[2 * n1 + 1]), mk<float>(dd.x, dd.y));
             } else {
+                float y0 = 0.f, y1 = 0.f;
                 if (i0 < w) y0 = wr[2 * n1] * d[i0];
                 if (i0 + 1 < w) y1 = wr[2 * n1 + 1] * d[i0 + 1];
+                a[n1] = mk<float>(y0, y1);
             }
-            a[n1] = mk<float>(y0, y1);
-            sum += y0 + y1;
+            if (32 * n1 < w) sum2 = sum2 + a[n1];
         }
         if (P.remove_dc) {
             // mean of the WINDOWED frame, subtracted from the window's samples only (src/io/in.cc:375-382)
-            const float mean = group_sum16_all(sum) * inv_w;
+            const float mean = group_sum16_all(sum2.x + sum2.y) * inv_w;
 #pragma unroll
             for (int n1 = 0; n1 < 16; n1++) {
                 const int i0 = 32 * n1 + 2 * c;
-                if (i0 < w) a[n1].x -= mean;
-                if (i0 + 1 < w) a[n1].y -= mean;
+                if (32 * n1 < w) a[n1] = a[n1] - mk<float>(i0 < w ? mean : 0.f, i0 + 1 < w ? mean : 0.f);
             }
         }
         fft256_pass1_reg(a, c, twr, xch);

@@ -958,13 +958,15 @@ constexpr int TRAP_MAXL = 128;
 constexpr int TRAP_MAXN = 16;
 struct TrapParams {
     int L, ndct, nb, h;         // h = (L+1)/2
-    int out_stride;
-    float m[TRAP_MAXN * TRAP_MAXL];   // [ndct][L]: 2*hamm[j]*cos(pi (j+.5) k / L) with the mean removal folded in
+    int out_stride, pad[3];     // m starts on a 16-byte boundary of the parameter bank
+    float m[TRAP_MAXN * TRAP_MAXL];   // [L][ndct], m[j * ndct + k-1] = 2*hamm[j]*cos(pi (j+.5) k / L) with the mean removal folded in:
+                                      // the coefficients of one trajectory position are neighbours (pairs for the packed FMA)
 };
 
 // LT / NT: trajectory length and coefficient count known at compile time (0 = runtime).
-// With both fixed the j and k loops unroll completely and every matrix entry becomes a
-// constant-bank operand of its FFMA (no load instruction at all).
+// With both fixed the j and k loops unroll completely and the matrix entries come out of the constant bank four at a time
+// (LDCU.128 into uniform registers) as operands of packed FMAs (FFMA2, ctu_fft.cuh): the folded pair (dj, sj) times the
+// entries of an even and an odd coefficient, into their two partial sums -- half the issue slots of one FFMA per entry.
 template <int LT, int NT>
 __global__ void __launch_bounds__(256)
 k_trapdct(const __grid_constant__ TrapParams Tp, BatchDesc bd, int tile_rows, const float *__restrict__ logfb,
@@ -1007,19 +1009,26 @@ k_trapdct(const __grid_constant__ TrapParams Tp, BatchDesc bd, int tile_rows, co
                 // x[j] +- x[L-1-j] first, half the multiplies.  The centre sample is `ref`, so its
                 // own term is zero.
                 constexpr int LH = (LT ? LT : 1) / 2;
+                static_assert(NA % 2 == 0, "coefficient pairs");
+                cpx<float> ac[NA / 2];
+#pragma unroll
+                for (int k = 0; k < NA / 2; k++) ac[k] = mk<float>(0.f, 0.f);
 #pragma unroll
                 for (int j = 0; j < LH; j++) {
-                    const float xa = v[j * nb] - ref, xb = v[((LT ? LT : 1) - 1 - j) * nb] - ref;
-                    const float sj = xa + xb, dj = xa - xb;
+                    const cpx<float> x = mk<float>(v[j * nb], v[((LT ? LT : 1) - 1 - j) * nb]) - mk<float>(ref, ref);
+                    const cpx<float> ds = x + mk<float>(-x.y, x.x);               // (xa - xb, xb + xa): the swap and the sign are operand modifiers
 #pragma unroll
-                    for (int k = 0; k < NA; k++) acc[k] = fmaf((k & 1) ? sj : dj, Tp.m[k * (LT ? LT : 1) + j], acc[k]);   // row k holds DCT index k+1
+                    for (int k = 0; k < NA / 2; k++)                                                       // entry k holds DCT index k+1
+                        ac[k] = pfma(ds, mk<float>(Tp.m[j * NA + 2 * k], Tp.m[j * NA + 2 * k + 1]), ac[k]);
                 }
+#pragma unroll
+                for (int k = 0; k < NA / 2; k++) { acc[2 * k] = ac[k].x; acc[2 * k + 1] = ac[k].y; }
             } else {
                 for (int j = 0; j < L; j++) {
                     const float x = v[j * nb] - ref;
 #pragma unroll
                     for (int k = 0; k < NA; k++)
-                        if (k < ND) acc[k] = fmaf(x, Tp.m[k * L + j], acc[k]);
+                        if (k < ND) acc[k] = fmaf(x, Tp.m[j * ND + k], acc[k]);
                 }
             }
         } else {
@@ -1031,7 +1040,7 @@ k_trapdct(const __grid_constant__ TrapParams Tp, BatchDesc bd, int tile_rows, co
                 if (j >= Z) x = sm[min(max(j - Z - (h - 1), 0), T - 1) * nb + b] - ref;
 #pragma unroll
                 for (int k = 0; k < NA; k++)
-                    if (k < ND) acc[k] = fmaf(x, Tp.m[k * L + j], acc[k]);
+                    if (k < ND) acc[k] = fmaf(x, Tp.m[j * ND + k], acc[k]);
             }
         }
         float *o = out + (row0 + t0 + r) * Tp.out_stride + b * ND;

@@ -499,7 +499,7 @@ k_synth(const __grid_constant__ SynthParams S, int window, int wshift, float pre
                 float m2 = X.x * X.x + X.y * X.y;
                 if (m2 == 0.f) return mk<float>(0.f, -A);
                 float g = A * rsqrtf(m2);
-                return mk<float>(X.x * g, X.y * g);
+                return cscale(X, g);
             };
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -648,7 +648,7 @@ k_synth_c(const __grid_constant__ SynthParams S, int window, int wshift, BatchDe
                 float m2 = X.x * X.x + X.y * X.y;
                 if (m2 == 0.f) return mk<float>(0.f, -A);
                 float g = A * rsqrtf(m2);
-                return mk<float>(X.x * g, X.y * g);
+                return cscale(X, g);
             };
 #pragma unroll
             for (int j = 0; j < 8; j++) {

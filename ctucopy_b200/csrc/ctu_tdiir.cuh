@@ -23,6 +23,7 @@
 #define CTU_TDIIR_CUH
 
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/ctucopy_b200.h"
@@ -53,7 +54,11 @@ __host__ __device__ inline int64_t tdiir_seg_base(const TdiirParams &P, int64_t 
 
 #ifdef CTU_TDIIR_IMPL
 
-__global__ void __launch_bounds__(TDIIR_THREADS)
+// PF: the next chunk's samples are loaded (to registers) before the current chunk is filtered, so the filter loop hides
+// their latency; without it every chunk starts with a round trip to HBM that the CTA's three warps wait for at the barrier
+// (ncu, profiles/r02_ncu_tdiir_full.txt: barrier 21 % + long scoreboard 10 % of the stall samples, FP64 pipe at 57 %).
+template <bool PF>
+__global__ void __launch_bounds__(TDIIR_THREADS, 8)
 k_tdiir_filter(const __grid_constant__ TdiirParams P, const int64_t *__restrict__ pcm_off, const int *__restrict__ nframes,
                const int64_t *__restrict__ row_off, int u0, int n_utts, const int16_t *__restrict__ pcm, double *__restrict__ S) {
     extern __shared__ __align__(16) double smd[];
@@ -86,20 +91,46 @@ k_tdiir_filter(const __grid_constant__ TdiirParams P, const int64_t *__restrict_
     const int u = u0 + min(ui, n_utts - 1);
     double *dst = S + tdiir_seg_base(P, row_off[u], u) * TDIIR_BANDS + b;
     const double *cf = P.coefs + b * 10;
-    const double b0 = cf[0], b1 = cf[1], b2 = cf[2], b3 = cf[3], b4 = cf[4], g = cf[5], a1 = cf[6], a2 = cf[7], a3 = cf[8], a4 = cf[9];
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;       // state(ff, 0..3): oldest .. newest (src/io/in.cc:289-297)
+    // the input gain g is folded into the numerator: with v' = v / g the recurrence reads v' = x - sum a_i s'_i,
+    // y = (g b0) v' + sum (g b_i) s'_i -- one multiplication per sample and band fewer (the products g b_i are rounded once:
+    // 1e-16 relative, like the order of the feedback sum below)
+    const double g = cf[5];
+    const double b0 = g * cf[0], b1 = g * cf[1], b2 = g * cf[2], b3 = g * cf[3], b4 = g * cf[4], a1 = cf[6], a2 = cf[7], a3 = cf[8], a4 = cf[9];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;       // state(ff, 0..3) / g: oldest .. newest (src/io/in.cc:289-297)
     double acc = 0.0;
     int wi = 0, gi = 0;                                   // n % window, n % seg at the start of a run
     const double *xs = sX + lu * LP;
-    for (int base = 0; base < maxN; base += L) {
-        // the chunk's samples, converted once per utterance instead of once per band (I2F.F64 is a quarter-rate instruction)
+    // a chunk's samples: TDIIR_UTTS x PER independent 2-byte loads per thread, all in flight at once; converted once per
+    // utterance instead of once per band (I2F.F64 is a quarter-rate instruction)
+    constexpr int PER = (TDIIR_CHUNK + TDIIR_THREADS - 1) / TDIIR_THREADS;
+    int16_t v16[TDIIR_UTTS][PER];
+    auto load_chunk = [&](int base) {
 #pragma unroll
         for (int k = 0; k < TDIIR_UTTS; k++) {
             const int16_t *src = pcm + sOff[k] + base;
-            const int nk = sN[k] - base;
-            for (int i = tid; i < L; i += TDIIR_THREADS) sX[k * LP + i] = (i < nk) ? (double)src[i] : 0.0;
+            const int nk = min(L, sN[k] - base);
+#pragma unroll
+            for (int j = 0; j < PER; j++) {
+                const int i = tid + j * TDIIR_THREADS;
+                v16[k][j] = (i < nk) ? src[i] : (int16_t)0;
+            }
         }
+    };
+    auto store_chunk = [&]() {
+#pragma unroll
+        for (int k = 0; k < TDIIR_UTTS; k++)
+#pragma unroll
+            for (int j = 0; j < PER; j++) {
+                const int i = tid + j * TDIIR_THREADS;
+                if (i < L) sX[k * LP + i] = (double)v16[k][j];
+            }
+    };
+    if (PF) load_chunk(0);
+    for (int base = 0; base < maxN; base += L) {
+        if (!PF) load_chunk(base);
+        store_chunk();
         __syncthreads();
+        if (PF && base + L < maxN) load_chunk(base + L);
         const int n = min(L, myN - base);                 // a multiple of `run`
         // runs of `run` samples: a run lies inside one segment and never wraps around the window (run | seg | window), so
         // the sample and window pointers just advance
@@ -110,7 +141,7 @@ k_tdiir_filter(const __grid_constant__ TdiirParams P, const int64_t *__restrict_
                 // the feedback terms are taken oldest first, so that only ONE multiply-add waits for the newest state (the
                 // reference subtracts a1 s3 first, src/io/in.cc:288-290: the same sum, rounded in another order -- 1e-16
                 // relative in fp64, against a tolerance of 1e-3 in the log domain)
-                double v = g * xp[i];
+                double v = xp[i];
                 v -= a4 * s0;
                 v -= a3 * s1;
                 v -= a2 * s2;
@@ -172,7 +203,9 @@ int launch_tdiir(const TdiirParams &P, const BatchDesc &bd64, int64_t nt64, cons
     if (n <= 0 || nt64 <= 0) return CTU_OK;
     const size_t bytes = sizeof(double) * ((size_t)P.window + (size_t)TDIIR_UTTS * (P.chunk + 2));
     lc->begin("k_tdiir_filter", s);
-    k_tdiir_filter<<<(unsigned)((n + TDIIR_UTTS - 1) / TDIIR_UTTS), TDIIR_THREADS, bytes, s>>>(P, d_pcm_off, d_nframes, d_row_off, u0, n, pcm, S);
+    static const bool pf = !(getenv("CTU_TDIIR_PF") && getenv("CTU_TDIIR_PF")[0] == '0');
+    if (pf) k_tdiir_filter<true><<<(unsigned)((n + TDIIR_UTTS - 1) / TDIIR_UTTS), TDIIR_THREADS, bytes, s>>>(P, d_pcm_off, d_nframes, d_row_off, u0, n, pcm, S);
+    else k_tdiir_filter<false><<<(unsigned)((n + TDIIR_UTTS - 1) / TDIIR_UTTS), TDIIR_THREADS, bytes, s>>>(P, d_pcm_off, d_nframes, d_row_off, u0, n, pcm, S);
     lc->end(s);
     lc->begin("k_tdiir_frames", s);
     k_tdiir_frames<<<(unsigned)nt64, 64, 0, s>>>(P, bd64, S, out, out_stride);
