@@ -12,6 +12,9 @@
 // 14.7 ms per 8 M frames for this step; see DESIGN 11 for what this one measures.
 // Work unit: a tile of 16 consecutive frames of one utterance (the 16-frame tile list), 128 threads = 16 groups = one pass;
 // persistent CTAs with the next tile's samples prefetched (cp.async), like k_frames2.
+// The transform runs on packed FP32 instructions (ctu_fft.cuh); the windowing stays scalar: as 8-byte loads and packed
+// multiplies (what k_frames2 does, with its window in registers) it measured 9.84 ms against 9.23 ms per 19.98 M frames
+// (all scalar: 9.54 ms; tools/gpu_jobs/r2_job44.sh, r2_job45.sh).
 #ifndef CTU_FRAMES256_CUH
 #define CTU_FRAMES256_CUH
 
@@ -83,29 +86,23 @@ k_frames256(const __grid_constant__ FrameParams P, BatchDesc bd, Tables256 tb, c
     const int f = min(grp, nf - 1);
     const float *d = sD + f * s;
     cpx<float> a[16];
-    // sample pairs and window pairs as 8-byte loads (even shifts), packed arithmetic for the window, the sum and the mean
-    const bool pair = (s & 1) == 0;
-    cpx<float> sum2 = mk<float>(0.f, 0.f);
+    float sum = 0.f;
 #pragma unroll
     for (int n1 = 0; n1 < 16; n1++) {
         const int i0 = 16 * n1 + 2 * g;                    // complex point 8 n1 + g = real samples i0, i0 + 1
-        if (i0 + 1 < w && pair) {
-            const float2 dd = *reinterpret_cast<const float2 *>(d + i0), ww = *reinterpret_cast<const float2 *>(sW + i0);
-            a[n1] = pmul(mk<float>(ww.x, ww.y), mk<float>(dd.x, dd.y));
-        } else {
-            const float y0 = (i0 < w) ? sW[i0] * d[i0] : 0.f;
-            const float y1 = (i0 + 1 < w) ? sW[i0 + 1] * d[i0 + 1] : 0.f;
-            a[n1] = mk<float>(y0, y1);
-        }
-        sum2 = sum2 + a[n1];
+        const float y0 = (i0 < w) ? sW[i0] * d[i0] : 0.f;
+        const float y1 = (i0 + 1 < w) ? sW[i0 + 1] * d[i0 + 1] : 0.f;
+        a[n1] = mk<float>(y0, y1);
+        sum += y0 + y1;
     }
     if (P.remove_dc) {
         // mean of the WINDOWED frame, subtracted from the window's samples only (src/io/in.cc:375-382)
-        const float mean = group_sum8(sum2.x + sum2.y) / (float)w;
+        const float mean = group_sum8(sum) / (float)w;
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) {
             const int i0 = 16 * n1 + 2 * g;
-            a[n1] = a[n1] - mk<float>(i0 < w ? mean : 0.f, i0 + 1 < w ? mean : 0.f);
+            if (i0 < w) a[n1].x -= mean;
+            if (i0 + 1 < w) a[n1].y -= mean;
         }
     }
     // pass 1: over n1; a[k1] = sum_n1 z[8 n1 + g] W16^(n1 k1), times W128^(g k1), to the tile at [k1][g]

@@ -966,7 +966,10 @@ struct TrapParams {
 // LT / NT: trajectory length and coefficient count known at compile time (0 = runtime).
 // With both fixed the j and k loops unroll completely and the matrix entries come out of the constant bank four at a time
 // (LDCU.128 into uniform registers) as operands of packed FMAs (FFMA2, ctu_fft.cuh): the folded pair (dj, sj) times the
-// entries of an even and an odd coefficient, into their two partial sums -- half the issue slots of one FFMA per entry.
+// entries of an even and an odd coefficient, into their two partial sums -- half the issue slots of one FFMA per entry
+// (4.73 -> 4.16 ms per 9.98 M frames).  Four consecutive rows of a band per thread with sliding pairs -- 12.5 shared-memory
+// loads per output instead of 51, the constants fetched once for four outputs, 250 instead of 370 instructions per output --
+// measured 4.26 ms (tools/gpu_jobs/r2_job45.sh): the kernel is not bound by its instruction count.
 template <int LT, int NT>
 __global__ void __launch_bounds__(256)
 k_trapdct(const __grid_constant__ TrapParams Tp, BatchDesc bd, int tile_rows, const float *__restrict__ logfb,

@@ -584,7 +584,10 @@ int launch_synth(const SynthParams &S, const FrameParams &F, const BatchDesc &bd
 // (the stored X is the very value k_synth would recompute), so the waveforms are bit-identical; it trades 2 x 2056 B of
 // HBM traffic per frame (write + read of X) for about 40 % of the synthesis kernel's instructions.
 template <int WT, int ST>
-__global__ void __launch_bounds__(SYN_THREADS, 3)
+#ifndef CTU_SYNC_MINB
+#define CTU_SYNC_MINB 3
+#endif
+__global__ void __launch_bounds__(SYN_THREADS, CTU_SYNC_MINB)
 k_synth_c(const __grid_constant__ SynthParams S, int window, int wshift, BatchDesc bd, int tile_frames, int ntiles,
           const int64_t *__restrict__ osamp_off, const float2 *__restrict__ cspec, const float *__restrict__ spec, int16_t *__restrict__ out,
           const float2 *__restrict__ g_tw256, const float2 *__restrict__ g_twinv) {

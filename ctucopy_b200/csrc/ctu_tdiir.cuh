@@ -23,7 +23,6 @@
 #define CTU_TDIIR_CUH
 
 #include <cstdint>
-#include <cstdlib>
 #include <string>
 
 #include "../../include/ctucopy_b200.h"
@@ -54,10 +53,9 @@ __host__ __device__ inline int64_t tdiir_seg_base(const TdiirParams &P, int64_t 
 
 #ifdef CTU_TDIIR_IMPL
 
-// PF: the next chunk's samples are loaded (to registers) before the current chunk is filtered, so the filter loop hides
-// their latency; without it every chunk starts with a round trip to HBM that the CTA's three warps wait for at the barrier
-// (ncu, profiles/r02_ncu_tdiir_full.txt: barrier 21 % + long scoreboard 10 % of the stall samples, FP64 pipe at 57 %).
-template <bool PF>
+// Eight resident CTAs per SM (80 registers); 9 and 10 (72 / 64 registers) measured the same, 38.1-38.3 ms.
+// (Loading the next chunk's samples to registers BEFORE the current chunk is filtered, so that the filter loop hides their
+// latency, was measured too: 40.9 ms against 38.1 ms -- the 24 extra live registers cost more than the round trip.)
 __global__ void __launch_bounds__(TDIIR_THREADS, 8)
 k_tdiir_filter(const __grid_constant__ TdiirParams P, const int64_t *__restrict__ pcm_off, const int *__restrict__ nframes,
                const int64_t *__restrict__ row_off, int u0, int n_utts, const int16_t *__restrict__ pcm, double *__restrict__ S) {
@@ -125,12 +123,10 @@ k_tdiir_filter(const __grid_constant__ TdiirParams P, const int64_t *__restrict_
                 if (i < L) sX[k * LP + i] = (double)v16[k][j];
             }
     };
-    if (PF) load_chunk(0);
     for (int base = 0; base < maxN; base += L) {
-        if (!PF) load_chunk(base);
+        load_chunk(base);
         store_chunk();
         __syncthreads();
-        if (PF && base + L < maxN) load_chunk(base + L);
         const int n = min(L, myN - base);                 // a multiple of `run`
         // runs of `run` samples: a run lies inside one segment and never wraps around the window (run | seg | window), so
         // the sample and window pointers just advance
@@ -203,9 +199,7 @@ int launch_tdiir(const TdiirParams &P, const BatchDesc &bd64, int64_t nt64, cons
     if (n <= 0 || nt64 <= 0) return CTU_OK;
     const size_t bytes = sizeof(double) * ((size_t)P.window + (size_t)TDIIR_UTTS * (P.chunk + 2));
     lc->begin("k_tdiir_filter", s);
-    static const bool pf = !(getenv("CTU_TDIIR_PF") && getenv("CTU_TDIIR_PF")[0] == '0');
-    if (pf) k_tdiir_filter<true><<<(unsigned)((n + TDIIR_UTTS - 1) / TDIIR_UTTS), TDIIR_THREADS, bytes, s>>>(P, d_pcm_off, d_nframes, d_row_off, u0, n, pcm, S);
-    else k_tdiir_filter<false><<<(unsigned)((n + TDIIR_UTTS - 1) / TDIIR_UTTS), TDIIR_THREADS, bytes, s>>>(P, d_pcm_off, d_nframes, d_row_off, u0, n, pcm, S);
+    k_tdiir_filter<<<(unsigned)((n + TDIIR_UTTS - 1) / TDIIR_UTTS), TDIIR_THREADS, bytes, s>>>(P, d_pcm_off, d_nframes, d_row_off, u0, n, pcm, S);
     lc->end(s);
     lc->begin("k_tdiir_frames", s);
     k_tdiir_frames<<<(unsigned)nt64, 64, 0, s>>>(P, bd64, S, out, out_stride);
