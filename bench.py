@@ -59,7 +59,7 @@ WORKLOADS = {
     # SURVEY 8f.4 (egs/conf/20): 24 time-domain IIR band filters -> windowed band energies -> log -> DCT; 30 ms / 10 ms; the
     # coefficient file is the committed test fixture (the reference ships none)
     "tdiir": (B + ["-format_out", "htk", "-w", "30", "-s", "10", "-nr_mode", "none", "-fea_kind", "td-iir-mfcc",
-                   "-filters", os.path.join(ROOT, "tests", "golden", "tdiir_filters.asc"), "-fea_ncepcoefs", "12"], 320 + 52, 160 * 24 * 24),
+                   "-filters", os.path.join(ROOT, "tests", "golden", "tdiir_filters.asc"), "-fea_ncepcoefs", "12"], 320 + 52, 160 * 24 * 22),
 }
 DEFAULT_WORKLOAD = "mfcc_exten"
 

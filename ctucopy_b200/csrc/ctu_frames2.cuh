@@ -43,8 +43,17 @@ __host__ __device__ inline Smem2 smem2_layout(int window, int wshift) {
 
 // CPLX: also store the complex spectrum X (float2 per bin) for the synthesis (k_synth_c): the phase then never has to be
 // recomputed from the samples.
+// WSM: the thread's 32 window values come from shared memory (16 eight-byte loads per frame) instead of living in
+// registers.  With packed arithmetic the kernel is latency bound at four CTAs per SM (ncu: issue slots 54 %, FP32 pipe 29 %,
+// shared-memory wavefronts 61 %, 16 warps per SM); without the 32 registers the 25 ms window fits five CTAs (92 registers,
+// no spills): 6.19 -> 6.05 ms per 9.98 M frames (tools/gpu_jobs/r2_job46.sh).  The other instantiations would spill at 102
+// registers (32 ms window, stored complex spectrum: 5.80 -> 6.33 ms) and keep the window in registers at four CTAs.
+template <int WT, bool CPLX> struct F2Cfg {
+    static constexpr bool wsm = (WT == 400) && !CPLX;
+    static constexpr int minb = wsm ? 5 : 4;
+};
 template <int WT, bool CPLX = false>
-__global__ void __launch_bounds__(F2_THREADS, 4)
+__global__ void __launch_bounds__(F2_THREADS, F2Cfg<WT, CPLX>::minb)
 k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, const int16_t *__restrict__ pcm, float *__restrict__ dst,
           int ntiles, float2 *__restrict__ cdst = nullptr) {
     extern __shared__ __align__(16) float sm[];
@@ -71,13 +80,18 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, con
     // a thread windows the same 2 x 16 sample positions of every frame it ever sees: its window values live in
     // registers for the whole (persistent) kernel instead of being re-read from shared memory per frame
     __syncthreads();
-    float wr[32];
+    constexpr bool WSM = F2Cfg<WT, CPLX>::wsm;
+    float wr[WSM ? 2 : 32];
+    if constexpr (!WSM) {
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) {
-        const int i0 = 32 * n1 + 2 * c;
-        wr[2 * n1] = (i0 < w) ? sW[i0] : 0.f;
-        wr[2 * n1 + 1] = (i0 + 1 < w) ? sW[i0 + 1] : 0.f;
+        for (int n1 = 0; n1 < 16; n1++) {
+            const int i0 = 32 * n1 + 2 * c;
+            wr[2 * n1] = (i0 < w) ? sW[i0] : 0.f;
+            wr[2 * n1 + 1] = (i0 + 1 < w) ? sW[i0 + 1] : 0.f;
+        }
     }
+    // window value i of this thread (i = 2 n1, 2 n1 + 1 <-> sample 32 n1 + 2 c, + 1; the caller keeps the index inside the window)
+    auto wv = [&](int i) -> float { if constexpr (WSM) return sW[32 * (i >> 1) + 2 * c + (i & 1)]; else return wr[i]; };
     // so do its twiddles: the six inter-pass ones it used to load per frame, and twsplit[c] (the other seven split
     // twiddles are that value times compile-time constants) -- 14 shared-memory loads per frame off the LSU pipe
     cpx<float> twr[6];
@@ -115,11 +129,16 @@ k_frames2(const __grid_constant__ FrameParams P, BatchDesc bd, FftTables tb, con
             const int i0 = 32 * n1 + 2 * c;
             if (i0 + 1 < w && pair) {
                 const float2 dd = *reinterpret_cast<const float2 *>(d + i0);
-                a[n1] = pmul(mk<float>(wr[2 * n1], wr[2 * n1 + 1]), mk<float>(dd.x, dd.y));
+                if constexpr (WSM) {
+                    const float2 ww = *reinterpret_cast<const float2 *>(sW + i0);
+                    a[n1] = pmul(mk<float>(ww.x, ww.y), mk<float>(dd.x, dd.y));
+                } else {
+                    a[n1] = pmul(mk<float>(wr[2 * n1], wr[2 * n1 + 1]), mk<float>(dd.x, dd.y));
+                }
             } else {
                 float y0 = 0.f, y1 = 0.f;
-                if (i0 < w) y0 = wr[2 * n1] * d[i0];
-                if (i0 + 1 < w) y1 = wr[2 * n1 + 1] * d[i0 + 1];
+                if (i0 < w) y0 = wv(2 * n1) * d[i0];
+                if (i0 + 1 < w) y1 = wv(2 * n1 + 1) * d[i0 + 1];
                 a[n1] = mk<float>(y0, y1);
             }
             if (32 * n1 < w) sum2 = sum2 + a[n1];

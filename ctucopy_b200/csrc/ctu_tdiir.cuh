@@ -18,7 +18,7 @@
 //   k_tdiir_frames   one thread per frame: adds the frame's segments per band, log, DCT, writes the row in writer order
 //                    (c1..c12, c0; src/io/out.cc:189-197).
 // Algorithmic bytes per frame: 2 * shift (PCM) + 52 (row); the segment sums add 2 x 192 * shift / g bytes of workspace
-// traffic.  The bound is the FP64 pipe: 12 DFMA / DMUL per sample and band.
+// traffic.  The bound is the FP64 pipe: 11 DFMA / DMUL per sample and band.
 #ifndef CTU_TDIIR_CUH
 #define CTU_TDIIR_CUH
 

@@ -31,7 +31,9 @@ def main():
                 continue
             m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", ln)
             if m:
-                cur["stack"], cur["spill_st"], cur["spill_ld"] = map(int, m.groups())
+                # an entry's own line and those of the device functions it calls (sqrt / division slow paths): keep the largest
+                st, ss, sl = map(int, m.groups())
+                cur["stack"], cur["spill_st"], cur["spill_ld"] = max(cur["stack"], st), max(cur["spill_st"], ss), max(cur["spill_ld"], sl)
             m = re.search(r"Used (\d+) registers", ln)
             if m:
                 cur["regs"] = int(m.group(1))
@@ -54,15 +56,18 @@ def main():
             cur = m.group(1); funcs[cur] = []
         elif cur and re.match(r"\s+/\*[0-9a-f]{4,5}\*/", ln):
             funcs[cur].append(re.sub(r"/\* 0x[0-9a-f]+ \*/", "", ln).rstrip())
-    want = [("k_frames2ILi400ELb0", ["LDGSTS", "SHFL", "STG", "LDS.64", "BAR"]),
-            ("k_bankILi3ELi2ELb1", ["UBLKCP", "SYNCS", "LDS.128", "MUFU", "BAR", "STG"]),
-            ("k_bankILi3ELi2ELb0", ["UBLKCP", "SYNCS", "LDS.128", "BAR", "STG"]),
+    want = [("k_frames2ILi400ELb0", ["FADD2", "FMUL2", "FFMA2", "LDGSTS", "SHFL", "STG", "LDS.64", "BAR"]),
+            ("k_bankILi3ELi2ELb1", ["UBLKCP", "SYNCS", "FFMA2", "LDS.128", "MUFU", "BAR", "STG"]),
+            ("k_bankILi3ELi2ELb0", ["UBLKCP", "SYNCS", "FFMA2", "LDS.128", "BAR", "STG"]),
+            ("k_trapdctILi51ELi8", ["FFMA2", "FADD2", "LDCU.128", "LDS"]),
+            ("k_frames256", ["FADD2", "FFMA2", "LDGSTS", "SHFL"]),
+            ("k_tdiir_filter", ["DFMA", "DMUL", "I2F", "LDS.64", "BAR"]),
             ("k_nr_scan4ILi1ELi1", ["LDG.E.128", "STG.E.128", "MUFU"]),
             ("k_burgILi25ELb1ELi4ELb0", ["DFMA", "DADD", "DMUL", "SHFL", "WARPSYNC", "LDL", "STL", "BAR"]),
             ("k_synth_cILi512ELi256", ["LDG", "STG", "SHFL", "BAR"])]
     with open(os.path.join(ROOT, "profiles", "r02_sass_excerpts.txt"), "w") as fh:
         fh.write("# cuobjdump -sass ctucopy_b200/libctucopy_b200.so: instruction counts of the hot kernels and the first occurrences of the\n")
-        fh.write("# instructions that matter (UBLKCP / SYNCS = cp.async.bulk + mbarrier, LDGSTS = cp.async, LDS.128 / LDG.E.128 = 16-byte accesses).\n")
+        fh.write("# instructions that matter (UBLKCP / SYNCS = cp.async.bulk + mbarrier, LDGSTS = cp.async, LDS.128 / LDG.E.128 = 16-byte accesses,\n# FADD2 / FMUL2 / FFMA2 = packed FP32 on register pairs with the .LO_HI swap, .NP sign and .F32 broadcast operand modifiers).\n")
         for key, pats in want:
             for fn, body in funcs.items():
                 if key not in fn:
