@@ -35,6 +35,7 @@ constexpr int TDIIR_NCEP = 13;
 constexpr int TDIIR_UTTS = 4;                              // utterances per CTA
 constexpr int TDIIR_THREADS = TDIIR_UTTS * TDIIR_BANDS;    // 96
 constexpr int TDIIR_CHUNK = 512;                           // most samples staged per utterance and step
+static_assert(TDIIR_THREADS == 96 && TDIIR_UTTS == TDIIR_THREADS / 32 + 1, "warp w holds band threads of utterances w and w + 1");
 
 struct TdiirParams {
     int window, wshift, seg;       // seg = gcd(window, wshift)
@@ -56,18 +57,25 @@ __host__ __device__ inline int64_t tdiir_seg_base(const TdiirParams &P, int64_t 
 // Eight resident CTAs per SM (80 registers); 9 and 10 (72 / 64 registers) measured the same, 38.1-38.3 ms.
 // (Loading the next chunk's samples to registers BEFORE the current chunk is filtered, so that the filter loop hides their
 // latency, was measured too: 40.9 ms against 38.1 ms -- the 24 extra live registers cost more than the round trip.)
+//
+// WARP-PRIVATE staging: a warp holds the band threads of TWO utterances (warp w of the CTA: the last 24 - 8 w bands of
+// utterance w and the first 8 + 8 w of utterance w + 1), stages those two utterances' samples in its own buffer and never
+// meets the other warps again -- __syncwarp() instead of two CTA barriers per chunk.  With the CTA-wide staging 26 % of the
+// stall samples sat at those barriers (profiles/r02_ncu_tdiir_full.txt): the three warps of a CTA run on different
+// sub-partitions whose FP64 pipes are not equally loaded, and every chunk made the faster ones wait.  Costs 6 instead of 4
+// utterance-chunks of conversions per CTA and chunk (a percent of the filter's work) and 24.7 instead of 16.5 KB.
+constexpr int TDIIR_WU = 2;                                // utterances a warp touches
 __global__ void __launch_bounds__(TDIIR_THREADS, 8)
 k_tdiir_filter(const __grid_constant__ TdiirParams P, const int64_t *__restrict__ pcm_off, const int *__restrict__ nframes,
                const int64_t *__restrict__ row_off, int u0, int n_utts, const int16_t *__restrict__ pcm, double *__restrict__ S) {
     extern __shared__ __align__(16) double smd[];
     double *sWin = smd;                                                        // window
-    double *sX = sWin + P.window;                                              // [TDIIR_UTTS][P.chunk] samples as doubles
     __shared__ int64_t sOff[TDIIR_UTTS];
     __shared__ int sN[TDIIR_UTTS];
-    const int tid = threadIdx.x, lu = tid / TDIIR_BANDS, b = tid % TDIIR_BANDS;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, lu = tid / TDIIR_BANDS, b = tid % TDIIR_BANDS;
     const int L = P.chunk, run = P.run;
-    const int LP = L + 2;                                  // row pitch of sX: a warp holds the band threads of two utterances, whose rows
-                                                           // must not start in the same bank (ncu: every other load conflicted)
+    const int LP = L + 2;                                  // row pitch: the rows of a warp's two utterances must not start in the same bank
+    double *sX = sWin + P.window + wid * (TDIIR_WU * LP);  // [TDIIR_WU][LP]: this warp's samples as doubles
     for (int i = tid; i < P.window; i += TDIIR_THREADS) sWin[i] = P.win[i];
     if (tid < TDIIR_UTTS) {
         const int i = blockIdx.x * TDIIR_UTTS + tid;
@@ -80,11 +88,9 @@ k_tdiir_filter(const __grid_constant__ TdiirParams P, const int64_t *__restrict_
         }
         sN[tid] = n; sOff[tid] = off;
     }
-    __syncthreads();
+    __syncthreads();                                       // the only CTA barrier
     const int myN = sN[lu];
-    int maxN = 0;
-#pragma unroll
-    for (int k = 0; k < TDIIR_UTTS; k++) maxN = max(maxN, sN[k]);
+    const int maxN = max(sN[wid], sN[wid + 1]);            // warp w: utterances w, w + 1 (TDIIR_UTTS = warps + 1)
     const int ui = blockIdx.x * TDIIR_UTTS + lu;
     const int u = u0 + min(ui, n_utts - 1);
     double *dst = S + tdiir_seg_base(P, row_off[u], u) * TDIIR_BANDS + b;
@@ -97,37 +103,32 @@ k_tdiir_filter(const __grid_constant__ TdiirParams P, const int64_t *__restrict_
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;       // state(ff, 0..3) / g: oldest .. newest (src/io/in.cc:289-297)
     double acc = 0.0;
     int wi = 0, gi = 0;                                   // n % window, n % seg at the start of a run
-    const double *xs = sX + lu * LP;
-    // a chunk's samples: TDIIR_UTTS x PER independent 2-byte loads per thread, all in flight at once; converted once per
-    // utterance instead of once per band (I2F.F64 is a quarter-rate instruction)
-    constexpr int PER = (TDIIR_CHUNK + TDIIR_THREADS - 1) / TDIIR_THREADS;
-    int16_t v16[TDIIR_UTTS][PER];
-    auto load_chunk = [&](int base) {
+    const double *xs = sX + (lu - wid) * LP;
+    // a chunk's samples: TDIIR_WU x PER independent 2-byte loads per lane, all in flight at once; converted once per
+    // utterance and warp instead of once per band (I2F.F64 is a quarter-rate instruction)
+    constexpr int PER = TDIIR_CHUNK / 32;
+    for (int base = 0; base < maxN; base += L) {
 #pragma unroll
-        for (int k = 0; k < TDIIR_UTTS; k++) {
-            const int16_t *src = pcm + sOff[k] + base;
-            const int nk = min(L, sN[k] - base);
+        for (int k = 0; k < TDIIR_WU; k++) {                // half an utterance-chunk at a time: 8 live values (32 or 16 spill)
+            const int16_t *src = pcm + sOff[wid + k] + base;
+            const int nk = min(L, sN[wid + k] - base);
 #pragma unroll
-            for (int j = 0; j < PER; j++) {
-                const int i = tid + j * TDIIR_THREADS;
-                v16[k][j] = (i < nk) ? src[i] : (int16_t)0;
+            for (int h = 0; h < 2; h++) {
+                int16_t v16[PER / 2];
+#pragma unroll
+                for (int j = 0; j < PER / 2; j++) {
+                    const int i = lane + (h * (PER / 2) + j) * 32;
+                    v16[j] = (i < nk) ? src[i] : (int16_t)0;
+                }
+#pragma unroll
+                for (int j = 0; j < PER / 2; j++) {
+                    const int i = lane + (h * (PER / 2) + j) * 32;
+                    if (i < L) sX[k * LP + i] = (double)v16[j];
+                }
             }
         }
-    };
-    auto store_chunk = [&]() {
-#pragma unroll
-        for (int k = 0; k < TDIIR_UTTS; k++)
-#pragma unroll
-            for (int j = 0; j < PER; j++) {
-                const int i = tid + j * TDIIR_THREADS;
-                if (i < L) sX[k * LP + i] = (double)v16[k][j];
-            }
-    };
-    for (int base = 0; base < maxN; base += L) {
-        load_chunk(base);
-        store_chunk();
-        __syncthreads();
-        const int n = min(L, myN - base);                 // a multiple of `run`
+        __syncwarp();
+        const int n = min(L, myN - base);                 // a multiple of `run` (<= 0: this lane's utterance has ended)
         // runs of `run` samples: a run lies inside one segment and never wraps around the window (run | seg | window), so
         // the sample and window pointers just advance
         for (int i0 = 0; i0 < n; i0 += run) {
@@ -160,7 +161,7 @@ k_tdiir_filter(const __grid_constant__ TdiirParams P, const int64_t *__restrict_
                 acc = 0.0;
             }
         }
-        __syncthreads();
+        __syncwarp();                                      // the buffer is re-staged by the next iteration
     }
 }
 
@@ -197,7 +198,7 @@ int launch_tdiir(const TdiirParams &P, const BatchDesc &bd64, int64_t nt64, cons
                  LaunchCtx *lc, std::string &err) {
     const int n = u1 - u0;
     if (n <= 0 || nt64 <= 0) return CTU_OK;
-    const size_t bytes = sizeof(double) * ((size_t)P.window + (size_t)TDIIR_UTTS * (P.chunk + 2));
+    const size_t bytes = sizeof(double) * ((size_t)P.window + (size_t)(TDIIR_THREADS / 32) * TDIIR_WU * (P.chunk + 2));
     lc->begin("k_tdiir_filter", s);
     k_tdiir_filter<<<(unsigned)((n + TDIIR_UTTS - 1) / TDIIR_UTTS), TDIIR_THREADS, bytes, s>>>(P, d_pcm_off, d_nframes, d_row_off, u0, n, pcm, S);
     lc->end(s);
