@@ -73,7 +73,8 @@ def kernel_alg_bytes(name, hop, dim, nb):
         # k_bank: one spectrum row in (257 bins; the three pad floats per row are overhead, not algorithmic bytes), one
         # feature / band row out; with the scan fused nothing else moves
         "k_bank<fea>": 4 * 257 + 4 * dim, "k_bank<nr,fea>": 4 * 257 + 4 * dim, "k_bank<fb>": 4 * 257 + 4 * nb, "k_bank<nr,fb>": 4 * 257 + 4 * nb,
-        "k_nr_scan": 2 * 4 * 257, "k_delta": 4 * dim + 8 * dim, "k_lpc": 4 * nb + 4 * dim, "k_trapdct": 4 * nb + 4 * dim,
+        "k_nr_scan": 2 * 4 * 257, "k_delta": 4 * dim + 12 * dim,   # compact static block in, c | delta | delta-delta out (whole rows)
+        "k_lpc": 4 * nb + 4 * dim, "k_trapdct": 4 * nb + 4 * dim,
         "k_synth": pcm + 4 * 257 + pcm, "k_burg": pcm + 8 * 16, "k_cepdet": 8 * 16 + 1,
         "k_stack": 4 * 13 + 4 * dim,          # static block read once, stacked row written once
         "k_synth_c": 8 * 257 + 4 * 257 + pcm,  # stored complex spectrum + enhanced magnitudes in, one hop of int16 out

@@ -115,6 +115,7 @@ struct ctu_handle {
     int synth_from_pcm = 0;              // 1: synthesis recomputes the forward transform instead of reading the stored X
     int fuse_nr = 1;                     // 1: the noise-reduction scan runs inside k_bank (tile in shared memory) where it can
     int front256 = 1;                    // 1: 256-point frames take k_frames256 for PCM -> spectrum; 0: the general kernel throughout
+    int compact_static = 1;              // 1: cepstra behind a delta chain are written as compact rows and the delta kernel writes the whole output row
     // hwss / fwss / 2fwss with the reference's LIST semantics (a file's noise estimate starts from the enhanced last frame of
     // the file before it, src/nr/nr.cc:212-222, 397-408): opt-in, one handle = one list walked in order on one GPU
     int ss_carry = 0;
@@ -449,6 +450,15 @@ static int build_delta_trap_params(ctu_handle *h) {
             h->gather = true;
             blk = fea_c;
             S.fea_c = fea_c; S.rot = cepstral ? 1 : 0; S.src_stride = h->static_dim;
+        } else if (h->compact_static && h->fea_kind == FEA_DCTC && !h->do_vad && !(h->nr_mode != NR_NONE && c.nr_when == 1)) {
+            // MFCC + deltas: the cepstra go to a compact [rows x static_dim] matrix (whole rows, coalesced) and the delta kernel
+            // takes its static block from there (the plain column gather above, no rotation: the block is in writer order
+            // already) and writes c | delta | delta-delta as whole output rows.  In place, the filter-bank kernel wrote 52 of
+            // every 156 bytes and the delta kernel 104, both as partial sectors: the delta kernel read 156 B per frame to
+            // use 52 and ran at a third of the HBM rate (profiles/r02_ncu_mfcc_exten.txt).  Not with the VAD module (its
+            // feature criterion reads the rows) nor on the fp64 band path.
+            h->gather = true;
+            S.fea_c = blk; S.rot = 0; S.src_stride = h->static_dim;
         }
     }
     if (trap) {
@@ -712,6 +722,7 @@ int ctu_create(const ctu_config *cfg, int device, ctu_handle **out) {
     if (getenv("CTU_SYNTH_FROM_PCM")) h->synth_from_pcm = 1;
     if (const char *e = getenv("CTU_FUSE_NR")) h->fuse_nr = atoi(e);
     if (const char *e = getenv("CTU_FRONT256")) h->front256 = atoi(e);
+    if (const char *e = getenv("CTU_COMPACT_STATIC")) h->compact_static = atoi(e);
     if (const char *e = getenv("CTU_CHUNK_MB")) h->chunk_mb = std::max(1, atoi(e));
     auto bail = [&](int st) { g_create_err = h->err; delete h; return st; };
     int st = ctu_config_finalize(&h->cfg);

@@ -231,6 +231,20 @@ def test_fused_and_standalone_scan_agree_bit_for_bit():
         assert np.array_equal(a.features, b.features), name
 
 
+def test_compact_and_in_place_cepstra_agree_bit_for_bit(monkeypatch):
+    """MFCC + deltas: the cepstra as a compact matrix with the delta kernel writing whole rows (default) and the in-place layout
+    (CTU_COMPACT_STATIC=0, read when the handle is created) run the same arithmetic on the same values: identical features, on a
+    ragged batch, with and without a noise-reduction scan in front."""
+    utts = PARITY_SET[:5] + [PARITY_SET[1][:4000 + 37], PARITY_SET[3][:400 + 160 * 6]]
+    for name in ("mfcc_d_a", "mfcc_exten"):
+        monkeypatch.delenv("CTU_COMPACT_STATIC", raising=False)
+        a = cb.extract(ORACLE_CASES[name], utts)
+        monkeypatch.setenv("CTU_COMPACT_STATIC", "0")
+        b = cb.extract(ORACLE_CASES[name], utts)
+        assert a.features.shape == b.features.shape and np.array_equal(a.features, b.features), name
+    monkeypatch.delenv("CTU_COMPACT_STATIC", raising=False)
+
+
 @pytest.mark.parametrize("name", [n for n in gu.case_names() if n.startswith("vaddbg_")])
 def test_vad_debug_side_files_match_reference(name):
     """-vad_out_mode debug: the side files next to the decision file (criterion, threshold and its state per written row,
