@@ -11,8 +11,9 @@
 // Two kernels:
 //   k_tdiir_filter   one thread per (utterance, band): the recurrence is sequential in time, the parallelism is
 //                    utterances x 24 bands (240 000 threads for BASELINE's 10 000 utterances).  A CTA of 96 threads takes
-//                    4 utterances; their samples are staged through shared memory in chunks, converted to fp64 once
-//                    (coalesced loads; the 24 band threads of an utterance then read the same address: a broadcast).  Each thread accumulates the
+//                    4 utterances; each of its three warps stages the samples of the two utterances its band threads belong
+//                    to in a buffer of its own, in chunks, converted to fp64 once (coalesced loads; the band threads of an
+//                    utterance then read the same address: a broadcast) -- no CTA barrier per chunk.  Each thread accumulates the
 //                    windowed energy over segments of g = gcd(window, shift) samples and stores one double per segment:
 //                    a frame is window / g whole segments, consecutive frames are shift / g segments apart.
 //   k_tdiir_frames   one thread per frame: adds the frame's segments per band, log, DCT, writes the row in writer order
